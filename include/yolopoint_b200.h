@@ -1,0 +1,205 @@
+/*
+ * yolopoint_b200.h  --  C ABI of libyolopoint_b200.so (B200 / sm_100a only).
+ *
+ * The reference (UniBwTAS/YOLOPoint) is pure Python/PyTorch and has no FFI seam:
+ * its "operator interface" for the hot path is a handful of Python call signatures.  Each entry point
+ * below is what a ctypes binding of one of those Python functions needs; the reference function it
+ * replaces is cited as file:line relative to the reference repository root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library never allocates device
+ *     memory, never frees and never keeps a pointer past the call;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises, so the
+ *     calls compose with CUDA graphs; variable-length results are written into caller-sized buffers
+ *     together with a device-side count;
+ *   - return value: YP_OK (0) or a negative YpStatus; never throws across the ABI.
+ *     yp_last_error() returns a thread-local message for the last failing call.
+ *   - re-entrant; no global mutable state except a once-initialised driver entry point and function
+ *     attributes.
+ */
+#ifndef YOLOPOINT_B200_H_
+#define YOLOPOINT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YP_ABI_VERSION 1
+
+typedef enum {
+  YP_OK = 0,
+  YP_ERR_SHAPE = -1,     /* unsupported / inconsistent shape */
+  YP_ERR_ALIGN = -2,     /* pointer or stride not 16-byte aligned */
+  YP_ERR_ARCH = -3,      /* device is not sm_100 */
+  YP_ERR_CUDA = -4,      /* a CUDA call failed; see yp_last_error() */
+  YP_ERR_CAPACITY = -5,  /* a caller-provided buffer is too small */
+  YP_ERR_ARG = -6        /* invalid argument value (e.g. negative nn_thresh) */
+} YpStatus;
+
+int yp_abi_version(void);
+const char* yp_last_error(void);
+/* 0 if the current device can run this library (compute capability 10.x). */
+int yp_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Activation views.  Activations live in HBM as NHWC tensors [planes][B][H][W][C_total]; a view is a
+ * channel slice of one of them (that is how torch.cat / nn.Upsample of the reference disappear:
+ * producers write into channel slices of their consumer's buffer).
+ *   format YP_FMT_F32X2 : two fp32 planes (hi, lo), both pre-rounded to TF32, value = hi + lo
+ *                         (operand format of the 3xTF32 tcgen05 path, fp32-grade accuracy)
+ *          YP_FMT_BF16  : one bf16 plane (fast path)
+ *          YP_FMT_F32   : one plain fp32 plane (network outputs: semi / desc / Detect logits)
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum { YP_FMT_F32X2 = 0, YP_FMT_BF16 = 1, YP_FMT_F32 = 2 } YpFormat;
+
+typedef struct {
+  void* base;           /* element (plane 0, b 0, h 0, w 0, first channel of the slice) */
+  int32_t B, H, W, C;   /* logical extent of the view; C = channels in the slice */
+  int64_t pix_stride;   /* elements between consecutive pixels (= C_total of the buffer) */
+  int64_t plane_stride; /* elements between planes (ignored for one-plane formats) */
+  int32_t format;       /* YpFormat */
+  int32_t upsample;     /* outputs only: 1 = store as is, 2 = store each pixel to the 2x2 block of a
+                           (2H x 2W) destination (nn.Upsample(2,'nearest') fused into the producer);
+                           H, W are then the SOURCE (pre-upsample) extents */
+} YpView;
+
+typedef enum { YP_ACT_NONE = 0, YP_ACT_SILU = 1 } YpAct;
+typedef enum { YP_ALGO_TCGEN05 = 0, YP_ALGO_SIMT = 1 } YpConvAlgo;
+#define YP_EPI_L2NORM 1u /* divide each output pixel by its L2 norm over all `cout` channels */
+
+/*
+ * yp_conv2d_nhwc_fwd -- one Conv block of the reference in eval/fused form:
+ *   act(conv(x) + bias) [+ residual] [-> L2 normalise], written to 1..2 destinations.
+ * Replaces models/common.py:22-34 (Conv.forward_fuse, BN folded per utils/torch_utils_yolo.py:194-214),
+ * the bare nn.Conv2d heads at models/YOLOPoint.py:186,195, Detect.m[i] at models/yolo.py:52, the residual
+ * add of models/common.py:88, torch.cat/nn.Upsample at models/YOLOPoint.py:214-242 (via channel-slice and
+ * 2x-replicated stores) and the descriptor normalisation at models/YOLOPoint.py:219-220.
+ *
+ * weight: packed [planes][cout][taps * Cin] in the input's operand format (F32X2 -> 2 fp32 planes hi/lo,
+ *         BF16 -> 1 plane), K index = tap * Cin + cin, tap = kh * KW + kw.   bias: fp32 [cout] or NULL.
+ * Supported geometry: 1x1 s1 p0, 3x3 s1 p1, 3x3 s2 p1 (the 6x6 s2 p2 stem is presented as 3x3 s1 p1 on
+ * the 2x2 space-to-depth input produced by yp_frame_to_s2d / yp_nchw_to_s2d).
+ * cout must be a multiple of 16; in.C a multiple of 16 (fp32) / 16 (bf16).
+ */
+typedef struct {
+  YpView in;
+  const void* weight;
+  const float* bias;
+  int32_t ksize, stride;  /* (1,1) (3,1) (3,2) */
+  int32_t cout;
+  int32_t act;            /* YpAct */
+  uint32_t epilogue;      /* YP_EPI_* flags */
+  YpView residual;        /* base == NULL -> none; same geometry/format family as out[0] */
+  int32_t n_out;          /* 1 or 2 */
+  YpView out[2];
+  int32_t algo;           /* YpConvAlgo */
+} YpConvDesc;
+
+int yp_conv2d_nhwc_fwd(const YpConvDesc* desc, void* stream);
+
+/* SPPF pooling: from slice 0 (C channels) of the [B,H,W,4C] concat buffer compute the 5x5, 9x9 and 13x13
+ * stride-1 max pools (== three chained MaxPool2d(5,1,2), models/common.py:220-229) into slices 1..3. */
+int yp_sppf_pool(const YpView* cat4, void* stream);
+
+/* Input conversion.  Both produce the 2x2 space-to-depth NHWC operand of the stem conv:
+ * out[b, h2, w2, (ph*2+pw)*3 + c] = x[b, c, 2*h2+ph, 2*w2+pw], channels 12..15 zero.
+ *   yp_nchw_to_s2d : x fp32 NCHW [B,3,H,W]                       (Model.forward input, YOLOPoint.py:70)
+ *   yp_frame_to_s2d: frame uint8 HWC [B,H,W,3], value/255         (demo.py:130-132 preprocessing)   */
+int yp_nchw_to_s2d(const float* x, int32_t B, int32_t H, int32_t W, const YpView* out, void* stream);
+int yp_frame_to_s2d(const uint8_t* frame, int32_t B, int32_t H, int32_t W, const YpView* out, void* stream);
+
+/* NHWC view (any format) -> dense fp32 NCHW [B,C,H,W] (the layout Model.forward returns). */
+int yp_nhwc_to_nchw(const YpView* in, int32_t C, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Detect decode (models/yolo.py:49-81, eval branch).
+ * logits: fp32 NHWC [B,ny,nx,ldc] with channel a*no + o   ->
+ *   raw  [B,na,ny,nx,no]  (the permuted logits the reference returns as x[i]; may be NULL)
+ *   pred [B,A_total,no] rows [row_off, row_off + na*ny*nx): xy=(2s-0.5+grid)*stride, wh=(2s)^2*anchor, s
+ * anchors_px: na*2 floats on the HOST = Detect.anchors[i] * stride[i] (pixels).
+ * ---------------------------------------------------------------------------------------------- */
+int yp_detect_decode(const float* logits, int32_t B, int32_t ny, int32_t nx, int32_t ldc, int32_t na, int32_t no,
+                     float stride_px, const float* anchors_px_host, float* raw, float* pred, int64_t A_total,
+                     int64_t row_off, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Box NMS = utils/general_yolo.py:124-235 (non_max_suppression) incl. torchvision.ops.nms semantics.
+ * pred [B,A,no] fp32.  Per image: obj > conf_thres; conf = cls*obj; xywh->xyxy; multi_label -> one
+ * candidate per (row, class) with conf > thr in row-major order, else best class; optional class filter
+ * (class_mask: 32-bit words, bit c set = keep class c; NULL = all); stable sort by conf desc, cap max_nms;
+ * greedy IoU (> iou_thres suppresses; boxes offset by cls*max_wh unless agnostic); cap max_det.
+ * out_boxes [B,max_det,6] (x1,y1,x2,y2,conf,cls), out_count int32 [B].
+ * workspace: yp_box_nms_workspace_bytes(B, A, no, cap) bytes; cap = per-image candidate capacity
+ * (candidates beyond cap set out_count[b] = -1 - n_candidates so the caller can detect overflow).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  float conf_thres, iou_thres;
+  int32_t multi_label, agnostic, max_det, max_nms;
+  float max_wh;
+  const uint32_t* class_mask; /* device, (nc+31)/32 words, or NULL */
+} YpNmsParams;
+
+size_t yp_box_nms_workspace_bytes(int32_t B, int64_t A, int32_t no, int32_t cap);
+int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, const YpNmsParams* p, int32_t cap,
+               float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Keypoint heatmap = utils/utils.py:232-262 (flattenDetection) / demo.py:140-150.
+ * semi: logits, element (b,c,hc,wc) at b*sB + c*sC + hc*sH + wc*sW (so NCHW and NHWC both work).
+ * heat [B, 8*Hc, 8*Wc] fp32: heat[8hc+i, 8wc+j] = softmax_c(semi)[8i+j]; channel 64 (dustbin) dropped.
+ * variant 0: torch.softmax (max-subtracted).  variant 1: demo.py's exp(x)/(sum+1e-5).
+ * ---------------------------------------------------------------------------------------------- */
+int yp_heatmap(const float* semi, int32_t B, int32_t Hc, int32_t Wc, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
+               int32_t variant, float* heat, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Keypoints = utils/utils.py:465-485 (getPtsFromHeatmap) + 118-182 (nms_fast) == demo.py:151-166,
+ * optionally followed by the keypoint-in-box filter of demo.py:178-198.
+ * heat [B,H,W] fp32.  Candidates: heat >= conf_thresh.  Exact greedy Chebyshev-radius NMS (parallel
+ * fixed point, identical survivors to the sequential reference), survivors sorted by confidence
+ * descending (ties: reverse raster order), border filter x<border | x>=W-border | y<border | y>=H-border.
+ * boxes (may be NULL): [B,box_ld,6] with box_count int32 [B]; points inside any box
+ * (np.rint corners, half-open, python negative-index wrap) are dropped.
+ * out_pts [B,max_pts,3] fp32 (x, y, conf), out_count int32 [B] (-1-n on overflow of max_pts).
+ * ---------------------------------------------------------------------------------------------- */
+size_t yp_keypoints_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t max_pts);
+int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, float conf_thresh, int32_t nms_dist,
+                 int32_t border, const float* boxes, const int32_t* box_count, int32_t box_ld,
+                 float* out_pts, int32_t* out_count, int32_t max_pts, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Descriptor sampling = demo.py:200-215 == evaluations/descriptor_evaluation.py:148-181:
+ * bilinear grid_sample(align_corners=True, zeros padding) at pixel coords (x,y) of an image of size
+ * (img_h,img_w), then L2 normalisation.  desc: element (b,d,hc,wc) at b*sB + d*sD + hc*sH + wc*sW.
+ * pts [B,pts_ld,3] fp32 (x,y,conf), count int32 [B] (device) -> out [B,pts_ld,D] fp32 (row-major per point).
+ * ---------------------------------------------------------------------------------------------- */
+int yp_sample_desc(const float* desc, int32_t B, int32_t D, int32_t Hc, int32_t Wc, int64_t sB, int64_t sD,
+                   int64_t sH, int64_t sW, int32_t img_h, int32_t img_w, const float* pts, const int32_t* count,
+                   int32_t pts_ld, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Two-way nearest-neighbour match = demo.py:300-341 (PointTracker.nn_match_two_way).
+ * d1 [n1_cap,D], d2 [n2_cap,D] fp32 row-major unit descriptors; n1/n2 device int32 counts (NULL -> caps).
+ * dist = sqrt(2 - 2*clip(d1.d2,-1,1)); row argmin (first index on ties), col argmin, mutual + dist < thr.
+ *   yp_match_partial: per-row / per-column packed keys (float_bits(dist) << 32 | index) for the column
+ *     shard [col_off, col_off + n2) -- the cross-GPU reduction is an integer MIN over row keys
+ *     (SURVEY.md section 8e); row_key uint64 [n1_cap], col_key uint64 [n2_cap].
+ *   yp_match_finalize: row_key [n1], col_best_row int32 [n2_total] -> matches [n1_cap,3] fp32 rows
+ *     (i, j, dist) ascending in i, match_count int32 [1].
+ * ---------------------------------------------------------------------------------------------- */
+int yp_match_partial(const float* d1, const int32_t* n1, int32_t n1_cap, const float* d2, const int32_t* n2,
+                     int32_t n2_cap, int32_t D, int32_t col_off, unsigned long long* row_key,
+                     unsigned long long* col_key, void* stream);
+int yp_match_finalize(const unsigned long long* row_key, const int32_t* n1, int32_t n1_cap,
+                      const unsigned long long* col_key, int32_t n2_total, float nn_thresh, float* matches,
+                      int32_t* match_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOPOINT_B200_H_ */

@@ -1,0 +1,159 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in this container.
+
+TEST INFRASTRUCTURE.  Run once in the build container (``python -m oracle.make_golden``); the GPU
+box has no /root/reference, so the fixtures are committed.  Every array below is produced by the
+reference's own functions (file:line cited per block); inputs are stored next to the outputs or are
+re-derivable from the seeds recorded in the file.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+from oracle import yolopoint_oracle as O  # noqa: E402
+from yolopoint_b200.synth import perturb_state_dict, synthetic_frame  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+NAMES80 = [str(i) for i in range(80)]
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrs)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB", {k: getattr(v, 'shape', None) for k, v in arrs.items()})
+
+
+def clustered_pred(rs, B, A, nc, size=320.0):
+    """Synthetic Detect output rows (xywh, obj, cls) with overlapping clusters so NMS has work to do."""
+    centers = rs.uniform(40, size - 40, (B, 24, 2))
+    which = rs.randint(0, 24, (B, A))
+    xy = np.take_along_axis(centers, which[..., None].repeat(2, -1), 1) + rs.normal(0, 6, (B, A, 2))
+    wh = rs.uniform(20, 80, (B, A, 2))
+    obj = rs.uniform(0, 1, (B, A, 1)) ** 2
+    cls = rs.uniform(0, 1, (B, A, nc)) ** 3
+    return np.concatenate((xy, wh, obj, cls), -1).astype(np.float32)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_import.load()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    # ---- 1. seeded initial state dicts (src/models/YOLOPoint.py:17-100) --------------------
+    for ver in ("n", "s"):
+        torch.manual_seed(0)
+        m = ns.Model(names=NAMES80, version=ver)
+        sd = m.state_dict()
+        keys = np.array(list(sd.keys()))
+        sums = np.array([float(v.double().sum()) for v in sd.values()])
+        asums = np.array([float(v.double().abs().sum()) for v in sd.values()])
+        shapes = np.array([str(tuple(v.shape)) for v in sd.values()])
+        pnames = np.array([n for n, _ in m.named_parameters()])
+        save(f"state_{ver}.npz", keys=keys, sums=sums, asums=asums, shapes=shapes, param_names=pnames,
+             stride=m.model.Detect.stride.numpy(), anchors=m.model.Detect.anchors.numpy())
+
+    # ---- 2. network forward, N model, B=2, 64x96 (src/models/YOLOPoint.py:198-246, fused) ---
+    torch.manual_seed(0)
+    m = ns.Model(names=NAMES80, version="n")
+    sd = perturb_state_dict(m.state_dict(), 0, "n")
+    m.load_state_dict(sd); m.eval().fuse()
+    x = torch.from_numpy(np.random.RandomState(7).rand(2, 3, 64, 96).astype(np.float32))
+    with torch.no_grad():
+        o = m(x)
+    save("net_n_64x96.npz", x=x.numpy(), semi=o["semi"].numpy(), desc=o["desc"].numpy(),
+         pred=o["objects"][0].numpy(), raw0=o["objects"][1][0].numpy(), raw1=o["objects"][1][1].numpy(),
+         raw2=o["objects"][1][2].numpy())
+
+    # ---- 3. whole-frame pipeline (src/demo.py:125-230 + 300-341) -----------------------------
+    for ver, (H, W) in (("n", (480, 640)), ("s", (640, 640))):
+        torch.manual_seed(0)
+        m = ns.Model(names=NAMES80, version=ver)
+        sd = perturb_state_dict(m.state_dict(), 0, ver)
+        m.load_state_dict(sd); m.eval().fuse()
+        fe = ref_import.make_frontend(ns, m, O.DEFAULT_CFG)
+        res = []
+        for seed in (0, 1):
+            pts, desc, obj = fe.process_img(synthetic_frame(H, W, seed))
+            res.append((pts, desc, obj[0].numpy()))
+        matches = ns.PointTracker.nn_match_two_way(res[0][1], res[1][1], O.DEFAULT_CFG["nn_thresh"])
+        save(f"e2e_{ver}_{H}x{W}.npz", pts0=res[0][0], desc0=res[0][1].astype(np.float32), boxes0=res[0][2],
+             pts1=res[1][0], desc1=res[1][1].astype(np.float32), boxes1=res[1][2], matches=matches)
+
+    # ---- 4. box NMS (src/utils/general_yolo.py:124-235) ---------------------------------------
+    rs = np.random.RandomState(11)
+    pred = clustered_pred(rs, 2, 600, 7)
+    arrs = dict(pred=pred)
+    cases = [(0.25, 0.45, False, False, 300, None), (0.4, 0.45, True, True, 1000, None),
+             (0.3, 0.6, True, False, 20, None), (0.25, 0.45, True, False, 300, [1, 3])]
+    for ci, (ct, it, ml, ag, md, cl) in enumerate(cases):
+        out = ns.non_max_suppression(torch.from_numpy(pred.copy()), ct, it, classes=cl, agnostic=ag,
+                                     multi_label=ml, max_det=md)
+        for b, t in enumerate(out):
+            arrs[f"case{ci}_img{b}"] = t.numpy()
+    arrs["cases"] = np.array([[c[0], c[1], float(c[2]), float(c[3]), c[4], -1 if c[5] is None else 13] for c in cases])
+    save("box_nms.npz", **arrs)
+
+    # ---- 5. heatmap (src/utils/utils.py:232-262 ; src/demo.py:140-150) -------------------------
+    semi = (rs.normal(0, 3, (2, 65, 12, 16))).astype(np.float32)
+    heat_t = ns.flattenDetection(torch.from_numpy(semi)).numpy()
+    dense = np.exp(semi[0]); dense = dense / (np.sum(dense, axis=0) + .00001)
+    nodust = dense[:-1].transpose(1, 2, 0)
+    heat_d = np.transpose(np.reshape(nodust, [12, 16, 8, 8]), [0, 2, 1, 3]).reshape(96, 128)
+    save("heatmap.npz", semi=semi, heat_torch=heat_t, heat_demo0=heat_d)
+
+    # ---- 6. keypoints (src/utils/utils.py:465-485, 118-182) -------------------------------------
+    heat = rs.uniform(0, 1, (96, 128)).astype(np.float32) ** 6
+    arrs = dict(heat=heat)
+    kcases = [(0.015, 4), (0.12, 8), (0.3, 2), (0.999999, 4)]
+    for ci, (thr, r) in enumerate(kcases):
+        arrs[f"pts{ci}"] = ns.getPtsFromHeatmap(heat, thr, r)
+    border = np.zeros((32, 48), np.float32); border[10, 2] = .9; border[10, 5] = .8; border[20, 30] = .5
+    arrs["border_heat"] = border
+    arrs["border_pts"] = ns.getPtsFromHeatmap(border, 0.1, 4)
+    single = np.zeros((32, 48), np.float32); single[12, 17] = .7
+    arrs["single_pts"] = ns.getPtsFromHeatmap(single, 0.1, 4)
+    arrs["kcases"] = np.array(kcases)
+    save("keypoints.npz", **arrs)
+
+    # ---- 7. keypoint-in-box filter (src/demo.py:178-198) ----------------------------------------
+    H, W = 96, 128
+    pts = ns.getPtsFromHeatmap(heat, 0.015, 2)
+    boxes = np.array([[10.4, 8.6, 50.5, 40.5, .9, 1], [-3.2, 60.1, 30.7, 90.9, .8, 0], [100.5, -5.0, 140.2, 30.0, .7, 2],
+                      [60.0, 50.0, 60.4, 80.0, .6, 3], [70.5, 70.5, 90.5, 200.0, .5, 1]], np.float32)
+    fe.filter_pts = True
+
+    def ref_filter(obj_preds, points, im_shape):  # verbatim semantics of the closure at src/demo.py:179-198
+        mask = np.ones(im_shape)
+        points = points.transpose()
+        points2 = points[:, :2].astype(int)
+        for *xyxy, _, _ in obj_preds:
+            x0, y0, x1, y1 = np.rint(xyxy).astype(int)
+            mask[y0:y1, x0:x1] = 0
+        return points[mask[points2[:, 1], points2[:, 0]] == 1].transpose()
+
+    save("filter_pts.npz", pts=pts, boxes=boxes, out=ref_filter(boxes, pts, (H, W)), HW=np.array([H, W]))
+
+    # ---- 8. descriptor sampling (src/evaluations/descriptor_evaluation.py:148-181) ---------------
+    coarse = rs.normal(0, 1, (1, 64, 12, 16)).astype(np.float32)
+    coarse /= np.linalg.norm(coarse, axis=1, keepdims=True)
+    spts = np.stack((rs.randint(0, 128, 200), rs.randint(0, 96, 200), rs.uniform(0, 1, 200))).astype(np.float64)
+    sdesc = ns.sample_desc_from_points(torch.from_numpy(coarse), spts, "cpu")
+    save("sample_desc.npz", coarse=coarse, pts=spts, desc=sdesc)
+
+    # ---- 9. two-way match (src/demo.py:300-341) ---------------------------------------------------
+    d1 = rs.normal(0, 1, (64, 300)).astype(np.float32); d1 /= np.linalg.norm(d1, axis=0)
+    perm = rs.permutation(300)[:260]
+    d2 = d1[:, perm] + 0.08 * rs.normal(0, 1, (64, 260)).astype(np.float32); d2 /= np.linalg.norm(d2, axis=0)
+    d2[:, 200:] = rs.normal(0, 1, (64, 60)); d2 /= np.linalg.norm(d2, axis=0)
+    d2 = d2.astype(np.float32)
+    save("match.npz", desc1=d1, desc2=d2, m07=ns.PointTracker.nn_match_two_way(d1, d2, 0.7),
+         m03=ns.PointTracker.nn_match_two_way(d1, d2, 0.3))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+// C-ABI glue: error reporting, device checks and the convolution dispatcher.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace yp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+int conv_tc_forward(const YpConvDesc& d, cudaStream_t st);
+int conv_simt_forward(const YpConvDesc& d, cudaStream_t st);
+
+}  // namespace yp
+
+extern "C" int yp_abi_version(void) { return YP_ABI_VERSION; }
+
+extern "C" const char* yp_last_error(void) { return yp::g_err; }
+
+extern "C" int yp_check_device(void) {
+  int dev = 0;
+  YP_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0;
+  YP_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  YP_REQUIRE(major == 10, YP_ERR_ARCH, "libyolopoint_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
+  return YP_OK;
+}
+
+extern "C" int yp_conv2d_nhwc_fwd(const YpConvDesc* d, void* stream) {
+  YP_REQUIRE(d && d->in.base && d->weight && d->n_out >= 1 && d->out[0].base, YP_ERR_ARG, "conv: null pointer in descriptor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->algo == YP_ALGO_SIMT) return yp::conv_simt_forward(*d, st);
+  if (d->algo == YP_ALGO_TCGEN05) return yp::conv_tc_forward(*d, st);
+  yp::set_error("conv: unknown algo %d", d->algo);
+  return YP_ERR_ARG;
+}

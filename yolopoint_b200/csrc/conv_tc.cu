@@ -1,0 +1,582 @@
+// tcgen05 implicit-GEMM convolution for sm_100a  (yp_conv2d_nhwc_fwd, algo YP_ALGO_TCGEN05).
+//
+// GEMM view: M = output pixels (one CTA = one Ht x Wt patch of one image, <= 128 pixels, the UMMA M=128
+// tile), N = output channels (tile Nt <= 256), K = taps * Cin.  The A operand is never materialised:
+// for every filter tap a TMA *tiled* load of the box (Ck channels, Wt, Ht) at the tap-shifted coordinate
+// lands in shared memory in exactly the K-major 128B/64B/32B-swizzled layout tcgen05.mma consumes; the
+// conv zero padding is TMA out-of-bounds fill.  Stride-2 convs read four parity views of the input
+// (even/odd rows x even/odd columns), each a plain strided 5-D tensor map, so no im2col mode is needed.
+//
+// Numerics: YP_FMT_F32X2 operands are (hi, lo) TF32 pairs; the kernel issues A_lo*W_hi + A_hi*W_lo +
+// A_hi*W_hi into one fp32 TMEM accumulator ("3xTF32", ~fp32 accuracy); YP_FMT_BF16 issues one bf16 MMA.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
+// epilogue (TMEM -> registers -> bias/SiLU/residual/L2-norm -> swizzled smem -> TMA store to 1..8 maps:
+// channel-slice (concat) destinations and the four parity views of a 2x-upsampled destination).
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+namespace yp {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a pipeline bug must fail loudly, not hang the GPU
+      printf("yolopoint_b200 conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives row (lane_base + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major shared-memory operand descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64).
+// For swizzled K-major tiles LBO is ignored (1), SBO = 8 rows * row bytes.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) |
+         (static_cast<uint64_t>((8u * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+// byte address inside a TMA-swizzled tile: row r, 16-byte chunk j, rows of row_bytes (128/64/32)
+__device__ __forceinline__ uint32_t swz_addr(uint32_t tile_base, uint32_t r, uint32_t j, uint32_t row_bytes) {
+  const uint32_t a = tile_base + r * row_bytes + j * 16u;
+  const uint32_t mask = (row_bytes >> 4) - 1u;  // 7, 3, 1
+  return a ^ (((a >> 7) & mask) << 4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel arguments
+// ---------------------------------------------------------------------------------------------
+struct alignas(64) ConvMaps {
+  CUtensorMap in[4];   // [0] for stride 1; (ph*2+pw) parity views for stride 2
+  CUtensorMap w;       // packed weights (K, Cout, plane)
+  CUtensorMap out[8];  // destinations: per output either 1 map or 4 parity maps (2x upsample)
+};
+
+struct ConvArgs {
+  int tiles_w, tiles_h, Ht, Wt, Ho, Wo;
+  int ksize, stride;
+  int n_taps, kb_per_tap, ck_bytes, ck_elems;
+  int n_terms, in_planes;
+  int Nt, stages, stage_bytes, a_tile_bytes, b_tile_bytes, bar_off;
+  uint32_t idesc, tmem_cols;
+  const float* bias;
+  int act, l2norm;
+  const void* res_base;
+  long long res_pix, res_plane;
+  int res_fmt;
+  int n_out_maps, out_planes, out_row_bytes, staging_set_bytes;
+};
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+
+template <int OUT_FMT>
+struct OutT { using type = float; };
+template <>
+struct OutT<YP_FMT_BF16> { using type = __nv_bfloat16; };
+
+// ---------------------------------------------------------------------------------------------
+// Kernel.  UNITS = 16-column TMEM units per staging row chunk (chunk_elems = 16 * UNITS).
+// ---------------------------------------------------------------------------------------------
+template <int OUT_FMT, int UNITS, bool kTf32>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_img = a.tiles_w * a.tiles_h;
+  const int b = blockIdx.x / per_img;
+  const int trem = blockIdx.x - b * per_img;
+  const int th = trem / a.tiles_w, tw = trem - th * a.tiles_w;
+  const int h0 = th * a.Ht, w0 = tw * a.Wt;
+  const int n0 = blockIdx.y * a.Nt;
+  const int num_kb = a.n_taps * a.kb_per_tap;
+
+  // barriers + tmem slot + bias live after the pipeline/staging region
+  const uint32_t bar_base = smem_base + a.bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * kMaxStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+  float* bias_s = reinterpret_cast<float*>(smem_gen + a.bar_off + 8 * (2 * kMaxStages + 2));
+
+  if (warp == 0 && lane == 0) {
+    const int n_in = a.stride == 2 ? 4 : 1;
+    for (int i = 0; i < n_in; ++i) tma_prefetch_desc(&maps.in[i]);
+    tma_prefetch_desc(&maps.w);
+    for (int i = 0; i < a.n_out_maps; ++i) tma_prefetch_desc(&maps.out[i]);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < a.Nt; i += 128) bias_s[i] = a.bias ? a.bias[n0 + i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % a.stages, ph = (kb / a.stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), a.stage_bytes);
+        const int tap = kb / a.kb_per_tap, cb = kb - tap * a.kb_per_tap;
+        int map = 0, dh = 0, dw = 0;
+        if (a.ksize == 3) {
+          const int kh = tap / 3, kw = tap - kh * 3;
+          if (a.stride == 1) { dh = kh - 1; dw = kw - 1; }
+          else { map = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1); dh = (kh == 0) ? -1 : 0; dw = (kw == 0) ? -1 : 0; }
+        }
+        const uint32_t st = smem_base + s * a.stage_bytes;
+        for (int pl = 0; pl < a.in_planes; ++pl) {
+          tma_load_5d(st + pl * a.a_tile_bytes, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, pl);
+          tma_load_3d(st + a.in_planes * a.a_tile_bytes + pl * a.b_tile_bytes, &maps.w, full_bar(s), kb * a.ck_elems, n0, pl);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const int ksteps = a.ck_bytes / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
+      uint32_t accum = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % a.stages, ph = (kb / a.stages) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * a.stage_bytes;
+        const uint32_t sb = sa + a.in_planes * a.a_tile_bytes;
+        for (int t = 0; t < a.n_terms; ++t) {
+          // fp32x2: small cross terms first (A_lo*W_hi, A_hi*W_lo), main term (A_hi*W_hi) last
+          const int pa = (a.n_terms == 3 && t == 0) ? 1 : 0;
+          const int pb = (a.n_terms == 3 && t == 1) ? 1 : 0;
+          const uint64_t ad = make_smem_desc(sa + pa * a.a_tile_bytes, a.ck_bytes);
+          const uint64_t bd = make_smem_desc(sb + pb * a.b_tile_bytes, a.ck_bytes);
+          for (int k = 0; k < ksteps; ++k) {
+            umma<kTf32>(tmem_base, ad + static_cast<uint64_t>(2 * k), bd + static_cast<uint64_t>(2 * k), a.idesc, accum);
+            accum = 1;
+          }
+        }
+        umma_commit(empty_bar(s));  // frees the smem stage when the MMAs above retire
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    // ===================== epilogue =====================
+    using TO = typename OutT<OUT_FMT>::type;
+    constexpr int CH = 16 * UNITS;                 // elements per staging row
+    constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
+    constexpr int V16 = ROWB / 16;                 // 16-byte vectors per row
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rh = row / a.Wt, rw = row - rh * a.Wt;
+    const int oh = h0 + rh, ow = w0 + rw;
+    const bool valid = (row < a.Ht * a.Wt) && (oh < a.Ho) && (ow < a.Wo);
+    const bool et0 = (threadIdx.x == 64);
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int n_chunks = a.Nt / CH;
+    const long long res_off = a.res_base ? ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0 : 0;
+
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+
+    auto finish = [&](float acc, int col) -> float {  // bias + activation + residual for column `col` of the tile
+      float v = acc + bias_s[col];
+      if (a.act == YP_ACT_SILU) v = (OUT_FMT == YP_FMT_BF16 && !kTf32) ? __fdividef(v, 1.0f + __expf(-v)) : silu_accurate(v);
+      if (a.res_base && valid) v += load_act(a.res_base, a.res_fmt, a.res_plane, res_off + col);
+      return v;
+    };
+
+    float inv_norm = 1.0f;
+    if (a.l2norm) {
+      float ss = 0.0f;
+      for (int u = 0; u < a.Nt / 16; ++u) {
+        float v[16];
+        tmem_ld16(taddr_row + u * 16, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float f = finish(v[i], u * 16 + i); ss += f * f; }
+      }
+      inv_norm = sqrtf(ss);  // divide below, as the reference does (desc.div(norm), no eps)
+    }
+
+    for (int c = 0; c < n_chunks; ++c) {
+      float v[CH];
+#pragma unroll
+      for (int u = 0; u < UNITS; ++u) tmem_ld16(taddr_row + c * CH + u * 16, v + u * 16);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        v[i] = finish(v[i], c * CH + i);
+        if (a.l2norm) v[i] = v[i] / inv_norm;
+      }
+      // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t stg = smem_base + (c & 1) * a.staging_set_bytes;
+      if (OUT_FMT == YP_FMT_F32X2) {
+#pragma unroll
+        for (int j = 0; j < V16; ++j) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { hi[e] = tf32_round(v[j * 4 + e]); lo[e] = tf32_round(v[j * 4 + e] - hi[e]); }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, row, j, ROWB)), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg + 128 * ROWB, row, j, ROWB)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+        }
+      } else if (OUT_FMT == YP_FMT_F32) {
+#pragma unroll
+        for (int j = 0; j < V16; ++j)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, row, j, ROWB)), "f"(v[j * 4]), "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < V16; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, row, j, ROWB)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et0) {
+        for (int m = 0; m < a.n_out_maps; ++m)
+          for (int pl = 0; pl < a.out_planes; ++pl)
+            tma_store_5d(&maps.out[m], stg + pl * 128 * ROWB, n0 + c * CH, w0, h0, b, pl);
+        tma_store_commit();
+        tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
+      }
+    }
+    if (et0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_encode_once;
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  return g_encode;
+}
+
+CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 5-D map over (C, W, H, B, plane) of an NHWC view; `sub` = spatial subsampling (2 -> parity view ph,pw).
+int encode_view(CUtensorMap* tm, const YpView& v, int sub, int ph, int pw, int Wfull, int Hfull, int box_c, int box_w,
+                int box_h) {
+  const int es = fmt_esize(v.format);
+  const int planes = fmt_planes(v.format);
+  const CUtensorMapDataType dt = v.format == YP_FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  char* base = static_cast<char*>(v.base) + (static_cast<int64_t>(ph) * Wfull + pw) * v.pix_stride * es;
+  cuuint64_t dims[5] = {(cuuint64_t)v.C, (cuuint64_t)(Wfull / sub), (cuuint64_t)(Hfull / sub), (cuuint64_t)v.B, (cuuint64_t)planes};
+  const int64_t img = static_cast<int64_t>(Hfull) * Wfull * v.pix_stride;
+  cuuint64_t strides[4] = {(cuuint64_t)(v.pix_stride * sub * es), (cuuint64_t)(v.pix_stride * Wfull * sub * es), (cuuint64_t)(img * es),
+                           (cuuint64_t)((planes > 1 ? v.plane_stride : img * v.B) * es)};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  YP_REQUIRE(aligned16(base), YP_ERR_ALIGN, "conv: view base %p not 16-byte aligned", (void*)base);
+  for (int i = 0; i < 4; ++i) YP_REQUIRE(strides[i] % 16 == 0, YP_ERR_ALIGN, "conv: view stride %d (%llu B) not a multiple of 16", i, (unsigned long long)strides[i]);
+  CUresult r = get_encode()(tm, dt, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_c * es),
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YP_REQUIRE(r == CUDA_SUCCESS, YP_ERR_CUDA, "cuTensorMapEncodeTiled(view) failed: %d (C=%d W=%d H=%d B=%d box %d,%d,%d)", (int)r, v.C,
+             Wfull / sub, Hfull / sub, v.B, box_c, box_w, box_h);
+  return YP_OK;
+}
+
+int encode_weight(CUtensorMap* tm, const void* w, int fmt, int Ktot, int cout, int box_k, int box_n) {
+  const int es = fmt_esize(fmt);
+  const int planes = fmt_planes(fmt);
+  const CUtensorMapDataType dt = fmt == YP_FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t dims[3] = {(cuuint64_t)Ktot, (cuuint64_t)cout, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)Ktot * es, (cuuint64_t)Ktot * cout * es};
+  cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_n, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  YP_REQUIRE(aligned16(w) && strides[0] % 16 == 0, YP_ERR_ALIGN, "conv: weight pointer/row stride not 16-byte aligned");
+  CUresult r = get_encode()(tm, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            swizzle_for(box_k * es), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YP_REQUIRE(r == CUDA_SUCCESS, YP_ERR_CUDA, "cuTensorMapEncodeTiled(weight) failed: %d (K=%d N=%d box %d,%d)", (int)r, Ktot, cout, box_k, box_n);
+  return YP_OK;
+}
+
+template <int OUT_FMT, int UNITS, bool kTf32>
+int launch(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = conv_tc_kernel<OUT_FMT, UNITS, kTf32>;
+  static thread_local size_t configured = 0;  // per (instantiation, thread): raise the dynamic smem limit once per size
+  if (smem > configured) {
+    YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  kern<<<grid, kThreads, smem, st>>>(maps, a);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+}  // namespace
+
+// Tile-shape selection shared with the Python planner via yp_conv_plan (debug / tests).
+void pick_patch(int Ho, int Wo, int* Ht, int* Wt) {
+  int best_tiles = 1 << 30, bw = 1, bh = 1;
+  for (int wt = 1; wt <= Wo && wt <= 128; ++wt) {
+    int ht = 128 / wt;
+    if (ht > Ho) ht = Ho;
+    if (ht < 1) continue;
+    const int tiles = ceil_div(Wo, wt) * ceil_div(Ho, ht);
+    if (tiles < best_tiles || (tiles == best_tiles && wt > bw)) { best_tiles = tiles; bw = wt; bh = ht; }
+  }
+  *Ht = bh; *Wt = bw;
+}
+
+int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
+  YP_REQUIRE(get_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const YpView& in = d.in;
+  const int in_fmt = in.format;
+  YP_REQUIRE(in_fmt == YP_FMT_F32X2 || in_fmt == YP_FMT_BF16, YP_ERR_SHAPE, "conv: input format %d unsupported", in_fmt);
+  const bool tf32 = in_fmt == YP_FMT_F32X2;
+  const int es = fmt_esize(in_fmt);
+  YP_REQUIRE((d.ksize == 1 && d.stride == 1) || (d.ksize == 3 && (d.stride == 1 || d.stride == 2)), YP_ERR_SHAPE,
+             "conv: k=%d s=%d unsupported", d.ksize, d.stride);
+  YP_REQUIRE(in.C % 16 == 0 && d.cout % 16 == 0, YP_ERR_SHAPE, "conv: Cin=%d / Cout=%d must be multiples of 16", in.C, d.cout);
+  YP_REQUIRE(d.stride == 1 || (in.H % 2 == 0 && in.W % 2 == 0), YP_ERR_SHAPE, "conv: stride 2 needs even H,W");
+  YP_REQUIRE(d.n_out >= 1 && d.n_out <= 2, YP_ERR_SHAPE, "conv: n_out=%d", d.n_out);
+  const int Ho = in.H / d.stride, Wo = in.W / d.stride;
+
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  a.Ho = Ho; a.Wo = Wo; a.ksize = d.ksize; a.stride = d.stride;
+  pick_patch(Ho, Wo, &a.Ht, &a.Wt);
+  a.tiles_w = ceil_div(Wo, a.Wt); a.tiles_h = ceil_div(Ho, a.Ht);
+  a.n_taps = d.ksize * d.ksize;
+  const int cin_bytes = in.C * es;
+  a.ck_bytes = cin_bytes % 128 == 0 ? 128 : (cin_bytes % 64 == 0 ? 64 : 32);
+  a.ck_elems = a.ck_bytes / es;
+  a.kb_per_tap = in.C / a.ck_elems;
+  a.n_terms = tf32 ? 3 : 1;
+  a.in_planes = tf32 ? 2 : 1;
+
+  // ---- output format / staging geometry
+  const int out_fmt = d.out[0].format;
+  for (int i = 0; i < d.n_out; ++i) {
+    YP_REQUIRE(d.out[i].format == out_fmt, YP_ERR_SHAPE, "conv: all outputs must share one format");
+    YP_REQUIRE(d.out[i].C == d.cout && d.out[i].B == in.B && d.out[i].H == Ho && d.out[i].W == Wo, YP_ERR_SHAPE,
+               "conv: output %d geometry mismatch (C %d vs %d, HxW %dx%d vs %dx%d)", i, d.out[i].C, d.cout, d.out[i].H, d.out[i].W, Ho, Wo);
+  }
+  YP_REQUIRE(tf32 ? (out_fmt == YP_FMT_F32X2 || out_fmt == YP_FMT_F32) : (out_fmt == YP_FMT_BF16 || out_fmt == YP_FMT_F32), YP_ERR_SHAPE,
+             "conv: output format %d incompatible with input format %d", out_fmt, in_fmt);
+  const int oes = fmt_esize(out_fmt);
+  a.out_planes = fmt_planes(out_fmt);
+  const int cout_bytes = d.cout * oes;
+  a.out_row_bytes = cout_bytes % 128 == 0 ? 128 : (cout_bytes % 64 == 0 ? 64 : 32);
+  const int chunk_elems = a.out_row_bytes / oes;
+  YP_REQUIRE(chunk_elems % 16 == 0, YP_ERR_SHAPE, "conv: Cout=%d gives a %d-element store chunk (<16)", d.cout, chunk_elems);
+  a.staging_set_bytes = a.out_planes * 128 * a.out_row_bytes;
+
+  // ---- N tile: largest divisor of Cout (multiple of chunk, <= 256) that still yields >= #SM CTAs
+  const int m_tiles = a.tiles_w * a.tiles_h * in.B;
+  const int nsm = sm_count();
+  int Nt = 0;
+  if (d.epilogue & YP_EPI_L2NORM) {
+    YP_REQUIRE(d.cout <= 256, YP_ERR_SHAPE, "conv: L2-norm epilogue needs Cout <= 256 (got %d)", d.cout);
+    Nt = d.cout;
+  } else {
+    const int nmax = tf32 ? 128 : 256;
+    int smallest = 0;
+    for (int n = nmax; n >= chunk_elems; n -= 16) {
+      if (d.cout % n || n % chunk_elems) continue;
+      smallest = n;
+      if (Nt == 0 && m_tiles * (d.cout / n) >= nsm) Nt = n;
+      if (n <= 32 && smallest) break;
+    }
+    if (Nt == 0) Nt = smallest;
+  }
+  YP_REQUIRE(Nt >= 16 && Nt % 16 == 0 && Nt <= 256, YP_ERR_SHAPE, "conv: no valid N tile for Cout=%d", d.cout);
+  a.Nt = Nt;
+  a.tmem_cols = 32;
+  while ((int)a.tmem_cols < Nt) a.tmem_cols <<= 1;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format [7,10)/[10,13)
+  // (TF32=2, BF16=1), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+  const uint32_t ab = tf32 ? 2u : 1u;
+  a.idesc = (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(Nt >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+
+  // ---- pipeline geometry
+  a.a_tile_bytes = 128 * a.ck_bytes;
+  a.b_tile_bytes = Nt * a.ck_bytes;
+  a.stage_bytes = a.in_planes * (a.a_tile_bytes + a.b_tile_bytes);
+  const int num_kb = a.n_taps * a.kb_per_tap;
+  const int budget = 200 * 1024;
+  int stages = budget / a.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > num_kb) stages = num_kb;
+  if (stages < 1) stages = 1;
+  YP_REQUIRE(a.stage_bytes <= budget, YP_ERR_SHAPE, "conv: stage of %d bytes exceeds shared memory", a.stage_bytes);
+  a.stages = stages;
+  int region = stages * a.stage_bytes;
+  if (region < 2 * a.staging_set_bytes) region = 2 * a.staging_set_bytes;
+  region = (region + 1023) & ~1023;
+  a.bar_off = region;
+  const size_t smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 2) + Nt * sizeof(float) + 16;
+  YP_REQUIRE(smem <= 227 * 1024, YP_ERR_SHAPE, "conv: needs %zu bytes of shared memory", smem);
+
+  a.bias = d.bias;
+  a.act = d.act;
+  a.l2norm = (d.epilogue & YP_EPI_L2NORM) ? 1 : 0;
+  if (d.residual.base) {
+    YP_REQUIRE(d.residual.C == d.cout && d.residual.H == Ho && d.residual.W == Wo && d.residual.B == in.B, YP_ERR_SHAPE, "conv: residual geometry mismatch");
+    a.res_base = d.residual.base; a.res_pix = d.residual.pix_stride; a.res_plane = d.residual.plane_stride; a.res_fmt = d.residual.format;
+  }
+
+  // ---- tensor maps
+  int rc;
+  if (d.stride == 1) {
+    if ((rc = encode_view(&maps.in[0], in, 1, 0, 0, in.W, in.H, a.ck_elems, a.Wt, a.Ht)) != YP_OK) return rc;
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        if ((rc = encode_view(&maps.in[ph * 2 + pw], in, 2, ph, pw, in.W, in.H, a.ck_elems, a.Wt, a.Ht)) != YP_OK) return rc;
+  }
+  if ((rc = encode_weight(&maps.w, d.weight, in_fmt, a.n_taps * in.C, d.cout, a.ck_elems, Nt)) != YP_OK) return rc;
+  int nm = 0;
+  for (int i = 0; i < d.n_out; ++i) {
+    const YpView& o = d.out[i];
+    if (o.upsample == 2) {
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw)
+          if ((rc = encode_view(&maps.out[nm++], o, 2, ph, pw, 2 * Wo, 2 * Ho, chunk_elems, a.Wt, a.Ht)) != YP_OK) return rc;
+    } else {
+      if ((rc = encode_view(&maps.out[nm++], o, 1, 0, 0, Wo, Ho, chunk_elems, a.Wt, a.Ht)) != YP_OK) return rc;
+    }
+  }
+  a.n_out_maps = nm;
+
+  const dim3 grid(m_tiles, d.cout / Nt);
+  const int units = chunk_elems / 16;
+#define YP_DISPATCH(FMT, U, TF) return launch<FMT, U, TF>(maps, a, grid, smem, st)
+  if (tf32) {
+    if (out_fmt == YP_FMT_F32X2) { if (units == 2) YP_DISPATCH(YP_FMT_F32X2, 2, true); if (units == 1) YP_DISPATCH(YP_FMT_F32X2, 1, true); }
+    else { if (units == 2) YP_DISPATCH(YP_FMT_F32, 2, true); if (units == 1) YP_DISPATCH(YP_FMT_F32, 1, true); }
+  } else {
+    if (out_fmt == YP_FMT_BF16) { if (units == 4) YP_DISPATCH(YP_FMT_BF16, 4, false); if (units == 2) YP_DISPATCH(YP_FMT_BF16, 2, false); if (units == 1) YP_DISPATCH(YP_FMT_BF16, 1, false); }
+    else { if (units == 2) YP_DISPATCH(YP_FMT_F32, 2, false); if (units == 1) YP_DISPATCH(YP_FMT_F32, 1, false); }
+  }
+#undef YP_DISPATCH
+  set_error("conv: no kernel instantiation for out_fmt=%d units=%d", out_fmt, units);
+  return YP_ERR_SHAPE;
+}
+
+}  // namespace yp

@@ -1,0 +1,365 @@
+// Detect decode + box NMS (models/yolo.py:49-81, utils/general_yolo.py:124-235 of the reference).
+// HBM/L2-bound integer+fp32 work; every fp32 expression that feeds a comparison is written with explicit
+// round-to-nearest intrinsics in the reference's operation order so that keep/suppress decisions and
+// indices are bit-identical to the PyTorch/torchvision CPU path (no FMA contraction).
+#include "common.cuh"
+
+namespace yp {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+struct DecodeArgs {
+  const float* logits;
+  float* raw;
+  float* pred;
+  int B, ny, nx, ldc, na, no;
+  float stride;
+  float anchor[16];
+  long long A_total, row_off;
+};
+
+__global__ void detect_decode_kernel(const DecodeArgs a) {
+  const int nch = a.na * a.no;
+  const int64_t total = static_cast<int64_t>(a.B) * a.ny * a.nx * nch;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = static_cast<int>(idx % nch);
+  int64_t p = idx / nch;
+  const int x = static_cast<int>(p % a.nx); p /= a.nx;
+  const int y = static_cast<int>(p % a.ny);
+  const int b = static_cast<int>(p / a.ny);
+  const int an = ch / a.no, o = ch - an * a.no;
+  const float v = a.logits[((static_cast<int64_t>(b) * a.ny + y) * a.nx + x) * a.ldc + ch];
+  const int64_t cell = (static_cast<int64_t>(an) * a.ny + y) * a.nx + x;
+  if (a.raw) a.raw[((static_cast<int64_t>(b) * a.na) * a.ny * a.nx + cell) * a.no + o] = v;
+  const float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+  float r = s;
+  if (o < 2) {
+    const float g = static_cast<float>(o == 0 ? x : y);
+    r = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(s, 2.0f), 0.5f), g), a.stride);
+  } else if (o < 4) {
+    const float t = __fmul_rn(s, 2.0f);
+    r = __fmul_rn(__fmul_rn(t, t), a.anchor[an * 2 + (o - 2)]);
+  }
+  a.pred[(static_cast<int64_t>(b) * a.A_total + a.row_off + cell) * a.no + o] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS stage 1: candidates.  One warp per prediction row.
+// ------------------------------------------------------------------------------------------------
+struct NmsWs {
+  int* row_count;       // [B*A]
+  int* row_offset;      // [B*A]
+  int* n_cand;          // [B]  candidates found (may exceed cap)
+  int* n_sorted;        // [B]  min(n_cand, cap, max_nms)
+  float* cand;          // [B][cap][6]  x1,y1,x2,y2,conf,cls in candidate order
+  float* sorted;        // [B][cap][6]  confidence-descending (stable)
+  unsigned long long* mask;  // [B][cap][cap/64]
+};
+
+__device__ __forceinline__ bool class_ok(const uint32_t* class_mask, int c) {
+  return class_mask == nullptr || ((class_mask[c >> 5] >> (c & 31)) & 1u);
+}
+
+// pass 0: count, pass 1: scatter
+template <int PASS>
+__global__ void nms_candidates_kernel(const float* __restrict__ pred, int B, long long A, int no, YpNmsParams p, int cap, NmsWs ws) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= static_cast<int64_t>(B) * A) return;
+  const int b = static_cast<int>(row / A);
+  const float* r = pred + row * no;
+  const int nc = no - 5;
+  const float obj = r[4];
+  int count = 0;
+  if (obj > p.conf_thres) {  // strict, general_yolo.py:146
+    float bx = 0, by = 0, bw = 0, bh = 0;
+    int base = 0;
+    if (PASS == 1) {
+      bx = r[0]; by = r[1]; bw = r[2]; bh = r[3];
+      base = ws.row_offset[row];
+    }
+    const bool multi = p.multi_label && nc > 1;
+    if (multi) {
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane;
+        float conf = 0.0f;
+        bool hit = false;
+        if (c < nc) { conf = __fmul_rn(r[5 + c], obj); hit = conf > p.conf_thres && class_ok(p.class_mask, c); }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (PASS == 1 && hit) {
+          const int pos = base + count + __popc(m & ((1u << lane) - 1u));
+          if (pos < cap) {
+            float* o = ws.cand + (static_cast<int64_t>(b) * cap + pos) * 6;
+            o[0] = __fsub_rn(bx, __fdiv_rn(bw, 2.0f)); o[1] = __fsub_rn(by, __fdiv_rn(bh, 2.0f));
+            o[2] = __fadd_rn(bx, __fdiv_rn(bw, 2.0f)); o[3] = __fadd_rn(by, __fdiv_rn(bh, 2.0f));
+            o[4] = conf; o[5] = static_cast<float>(c);
+          }
+        }
+        count += __popc(m);
+      }
+    } else {  // best class only (first maximum), general_yolo.py:195-196
+      float best = -INFINITY;
+      int bc = 0x7fffffff;
+      for (int c = lane; c < nc; c += 32) {
+        const float conf = __fmul_rn(r[5 + c], obj);
+        if (conf > best) { best = conf; bc = c; }
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, s);
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, s);
+        if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+      }
+      const bool hit = best > p.conf_thres && class_ok(p.class_mask, bc);
+      count = hit ? 1 : 0;
+      if (PASS == 1 && hit && lane == 0 && base < cap) {
+        float* o = ws.cand + (static_cast<int64_t>(b) * cap + base) * 6;
+        o[0] = __fsub_rn(bx, __fdiv_rn(bw, 2.0f)); o[1] = __fsub_rn(by, __fdiv_rn(bh, 2.0f));
+        o[2] = __fadd_rn(bx, __fdiv_rn(bw, 2.0f)); o[3] = __fadd_rn(by, __fdiv_rn(bh, 2.0f));
+        o[4] = best; o[5] = static_cast<float>(bc);
+      }
+    }
+  }
+  if (PASS == 0 && lane == 0) ws.row_count[row] = count;
+}
+
+// exclusive scan of row_count per image (one block per image)
+__global__ void nms_scan_kernel(long long A, int cap, int max_nms, NmsWs ws) {
+  __shared__ int warp_excl[32];
+  __shared__ int block_total;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  int carry = 0;  // identical in every thread
+  for (int64_t base = 0; base < A; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const int v = i < A ? ws.row_count[b * A + i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += t; }
+    __syncthreads();  // previous iteration's readers of warp_excl / block_total are done
+    if (lane == 31) warp_excl[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int wv = lane < nwarps ? warp_excl[lane] : 0;
+      int wincl = wv;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wincl, s); if (lane >= s) wincl += t; }
+      warp_excl[lane] = wincl - wv;
+      if (lane == 31) block_total = wincl;
+    }
+    __syncthreads();
+    if (i < A) ws.row_offset[b * A + i] = carry + warp_excl[wid] + incl - v;
+    carry += block_total;
+  }
+  if (threadIdx.x == 0) {
+    ws.n_cand[b] = carry;
+    const int n = carry < cap ? carry : cap;
+    ws.n_sorted[b] = n < max_nms ? n : max_nms;
+  }
+}
+
+// stable descending rank sort: rank(i) = #{j : conf_j > conf_i or (conf_j == conf_i and j < i)}
+__global__ void nms_rank_kernel(int cap, NmsWs ws) {
+  __shared__ float tile[256];
+  const int b = blockIdx.y;
+  int n = ws.n_cand[b];
+  if (n > cap) n = cap;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x * blockDim.x >= n) return;
+  const float* cand = ws.cand + static_cast<int64_t>(b) * cap * 6;
+  const float ci = i < n ? cand[i * 6 + 4] : 0.0f;
+  int rank = 0;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    tile[threadIdx.x] = j < n ? cand[j * 6 + 4] : -INFINITY;
+    __syncthreads();
+    const int lim = min(256, n - j0);
+    for (int k = 0; k < lim; ++k) {
+      const float cj = tile[k];
+      rank += (cj > ci || (cj == ci && (j0 + k) < i)) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  if (i < n && rank < ws.n_sorted[b]) {
+    float* o = ws.sorted + (static_cast<int64_t>(b) * cap + rank) * 6;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = cand[i * 6 + k];
+  }
+}
+
+// torchvision nms_kernel semantics: suppress j (> i in sorted order) iff inter / (area_i + area_j - inter) > thr
+__device__ __forceinline__ bool iou_gt(const float* a, const float* b, float thr) {
+  const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+  const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+  const float w = fmaxf(__fsub_rn(right, left), 0.0f), h = fmaxf(__fsub_rn(bottom, top), 0.0f);
+  const float inter = __fmul_rn(w, h);
+  const float sa = __fmul_rn(__fsub_rn(a[2], a[0]), __fsub_rn(a[3], a[1]));
+  const float sb = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
+}
+
+// 64x64 blocks of the upper-triangular suppression bit matrix; persistent over block pairs
+__global__ void nms_mask_kernel(int cap, float iou_thres, int agnostic, float max_wh, NmsWs ws) {
+  __shared__ float colbox[64][4];
+  const int b = blockIdx.y;
+  const int n = ws.n_sorted[b];
+  const int nb = (n + 63) >> 6;
+  const int words = cap >> 6;
+  const float* sorted = ws.sorted + static_cast<int64_t>(b) * cap * 6;
+  unsigned long long* mask = ws.mask + static_cast<int64_t>(b) * cap * words;
+  for (int t = blockIdx.x; t < nb * nb; t += gridDim.x) {
+    const int rb = t / nb, cb = t - rb * nb;
+    if (cb < rb) continue;
+    __syncthreads();
+    {
+      const int j = cb * 64 + threadIdx.x;
+      if (j < n) {
+        const float off = agnostic ? 0.0f : __fmul_rn(sorted[j * 6 + 5], max_wh);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) colbox[threadIdx.x][k] = __fadd_rn(sorted[j * 6 + k], off);
+      }
+    }
+    __syncthreads();
+    const int i = rb * 64 + threadIdx.x;
+    if (i < n) {
+      float me[4];
+      const float off = agnostic ? 0.0f : __fmul_rn(sorted[i * 6 + 5], max_wh);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) me[k] = __fadd_rn(sorted[i * 6 + k], off);
+      unsigned long long bits = 0;
+      const int lim = min(64, n - cb * 64);
+      const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+      for (int k = start; k < lim; ++k)
+        if (iou_gt(me, colbox[k], iou_thres)) bits |= 1ull << k;
+      mask[static_cast<int64_t>(i) * words + cb] = bits;
+    }
+  }
+}
+
+// ordered scan over the bit matrix; one block per image
+__global__ void nms_scan_keep_kernel(int cap, int max_det, NmsWs ws, float* __restrict__ out_boxes, int* __restrict__ out_count) {
+  extern __shared__ unsigned long long removed[];  // cap/64 words
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long keep_bits;
+  __shared__ int n_keep;
+  const int b = blockIdx.x;
+  const int n = ws.n_sorted[b];
+  const int nb = (n + 63) >> 6;
+  const int words = cap >> 6;
+  const float* sorted = ws.sorted + static_cast<int64_t>(b) * cap * 6;
+  const unsigned long long* mask = ws.mask + static_cast<int64_t>(b) * cap * words;
+  float* out = out_boxes + static_cast<int64_t>(b) * max_det * 6;
+  for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0;
+  if (threadIdx.x == 0) n_keep = 0;
+  __syncthreads();
+  for (int wc = 0; wc < nb; ++wc) {
+    if (n_keep >= max_det) break;  // uniform: n_keep only changes between barriers
+    const int lim = min(64, n - wc * 64);
+    if (threadIdx.x < 64) diag[threadIdx.x] = threadIdx.x < lim ? mask[static_cast<int64_t>(wc * 64 + threadIdx.x) * words + wc] : 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long rem = removed[wc], kb = 0;
+      int nk = n_keep;
+      for (int k = 0; k < lim && nk < max_det; ++k) {
+        if (!((rem >> k) & 1ull)) { kb |= 1ull << k; rem |= diag[k]; ++nk; }
+      }
+      keep_bits = kb;
+    }
+    __syncthreads();
+    const unsigned long long kb = keep_bits;
+    const int base = n_keep;
+    // write kept rows (ordered) and fold their suppression rows into `removed`
+    if (threadIdx.x < 64 && ((kb >> threadIdx.x) & 1ull)) {
+      const int pos = base + __popcll(kb & ((1ull << threadIdx.x) - 1ull));
+      const float* s = sorted + static_cast<int64_t>(wc * 64 + threadIdx.x) * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) out[pos * 6 + k] = s[k];
+    }
+    for (int w = wc + 1 + threadIdx.x; w < nb; w += blockDim.x) {
+      unsigned long long acc = removed[w];
+      unsigned long long bits = kb;
+      while (bits) {
+        const int k = __ffsll(bits) - 1;
+        bits &= bits - 1;
+        acc |= mask[static_cast<int64_t>(wc * 64 + k) * words + w];
+      }
+      removed[w] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) n_keep = base + __popcll(kb);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int nc = ws.n_cand[b];
+    out_count[b] = nc > cap ? -1 - nc : n_keep;
+  }
+}
+
+size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+size_t carve(NmsWs* ws, char* base, int B, long long A, int cap) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+  ws->row_count = reinterpret_cast<int*>(take(sizeof(int) * B * A));
+  ws->row_offset = reinterpret_cast<int*>(take(sizeof(int) * B * A));
+  ws->n_cand = reinterpret_cast<int*>(take(sizeof(int) * B));
+  ws->n_sorted = reinterpret_cast<int*>(take(sizeof(int) * B));
+  ws->cand = reinterpret_cast<float*>(take(sizeof(float) * 6 * B * cap));
+  ws->sorted = reinterpret_cast<float*>(take(sizeof(float) * 6 * B * cap));
+  ws->mask = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * cap * (cap / 64)));
+  return off;
+}
+
+}  // namespace
+}  // namespace yp
+
+extern "C" int yp_detect_decode(const float* logits, int32_t B, int32_t ny, int32_t nx, int32_t ldc, int32_t na, int32_t no,
+                                float stride_px, const float* anchors_px_host, float* raw, float* pred, int64_t A_total,
+                                int64_t row_off, void* stream) {
+  YP_REQUIRE(logits && pred && anchors_px_host, YP_ERR_ARG, "detect_decode: null pointer");
+  YP_REQUIRE(na >= 1 && na <= 8 && no >= 6 && na * no <= ldc, YP_ERR_SHAPE, "detect_decode: na=%d no=%d ldc=%d", na, no, ldc);
+  yp::DecodeArgs a;
+  a.logits = logits; a.raw = raw; a.pred = pred; a.B = B; a.ny = ny; a.nx = nx; a.ldc = ldc; a.na = na; a.no = no;
+  a.stride = stride_px; a.A_total = A_total; a.row_off = row_off;
+  for (int i = 0; i < na * 2; ++i) a.anchor[i] = anchors_px_host[i];
+  const int64_t total = static_cast<int64_t>(B) * ny * nx * na * no;
+  yp::detect_decode_kernel<<<static_cast<unsigned>(yp::ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+extern "C" size_t yp_box_nms_workspace_bytes(int32_t B, int64_t A, int32_t no, int32_t cap) {
+  (void)no;
+  if (B <= 0 || A <= 0 || cap <= 0 || cap % 64) return 0;
+  yp::NmsWs ws;
+  return yp::carve(&ws, nullptr, B, A, cap);
+}
+
+extern "C" int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, const YpNmsParams* p, int32_t cap,
+                          float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+  YP_REQUIRE(pred && p && out_boxes && out_count && workspace, YP_ERR_ARG, "box_nms: null pointer");
+  YP_REQUIRE(B > 0 && A > 0 && no >= 6, YP_ERR_SHAPE, "box_nms: B=%d A=%lld no=%d", B, (long long)A, no);
+  YP_REQUIRE(cap > 0 && cap % 64 == 0, YP_ERR_SHAPE, "box_nms: cap=%d must be a positive multiple of 64", cap);
+  YP_REQUIRE(p->conf_thres >= 0.f && p->conf_thres <= 1.f, YP_ERR_ARG, "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", p->conf_thres);
+  YP_REQUIRE(p->iou_thres >= 0.f && p->iou_thres <= 1.f, YP_ERR_ARG, "Invalid IoU %g, valid values are between 0.0 and 1.0", p->iou_thres);
+  YP_REQUIRE(p->max_det > 0 && p->max_nms > 0, YP_ERR_ARG, "box_nms: max_det/max_nms must be positive");
+  yp::NmsWs ws;
+  const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, A, cap);
+  YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "box_nms: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows = static_cast<int64_t>(B) * A;
+  const unsigned cblocks = static_cast<unsigned>(yp::ceil_div64(rows * 32, 256));
+  yp::nms_candidates_kernel<0><<<cblocks, 256, 0, st>>>(pred, B, A, no, *p, cap, ws);
+  yp::nms_scan_kernel<<<B, 1024, 0, st>>>(A, cap, p->max_nms, ws);
+  yp::nms_candidates_kernel<1><<<cblocks, 256, 0, st>>>(pred, B, A, no, *p, cap, ws);
+  yp::nms_rank_kernel<<<dim3(cap / 256 + (cap % 256 ? 1 : 0), B), 256, 0, st>>>(cap, ws);
+  yp::nms_mask_kernel<<<dim3(2 * yp::sm_count(), B), 64, 0, st>>>(cap, p->iou_thres, p->agnostic, p->max_wh, ws);
+  const size_t smem = sizeof(unsigned long long) * (cap / 64);
+  yp::nms_scan_keep_kernel<<<B, 128, smem, st>>>(cap, p->max_det, ws, out_boxes, out_count);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}

@@ -1,0 +1,260 @@
+// Keypoint heatmap (65-way cell softmax + depth-to-space) and exact parallel greedy keypoint NMS
+// (utils/utils.py:118-182, 232-262, 465-485 and demo.py:138-198 of the reference).
+#include "common.cuh"
+
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace yp {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// heatmap: one thread per 8x8 cell, 65 logits in registers
+// ------------------------------------------------------------------------------------------------
+__global__ void heatmap_kernel(const float* __restrict__ semi, int B, int Hc, int Wc, long long sB, long long sC, long long sH,
+                               long long sW, int variant, float* __restrict__ heat) {
+  const int64_t total = static_cast<int64_t>(B) * Hc * Wc;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int wc = static_cast<int>(idx % Wc);
+  const int hc = static_cast<int>((idx / Wc) % Hc);
+  const int b = static_cast<int>(idx / (static_cast<int64_t>(Wc) * Hc));
+  const float* s = semi + b * sB + hc * sH + wc * sW;
+  float v[65];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 65; ++c) { v[c] = s[c * sC]; mx = fmaxf(mx, v[c]); }
+  float sum = 0.0f;
+  if (variant == 0) {  // torch.softmax: exp(x - max) / sum
+#pragma unroll
+    for (int c = 0; c < 65; ++c) { v[c] = expf(__fsub_rn(v[c], mx)); sum = __fadd_rn(sum, v[c]); }
+  } else {  // demo.py:140-141: exp(x) / (sum + 1e-5)
+#pragma unroll
+    for (int c = 0; c < 65; ++c) { v[c] = expf(v[c]); sum = __fadd_rn(sum, v[c]); }
+    sum = __fadd_rn(sum, 0.00001f);
+  }
+  const int W = Wc * 8;
+  float* o = heat + (static_cast<int64_t>(b) * Hc * 8 + hc * 8) * W + wc * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 lo4 = make_float4(__fdiv_rn(v[8 * i], sum), __fdiv_rn(v[8 * i + 1], sum), __fdiv_rn(v[8 * i + 2], sum), __fdiv_rn(v[8 * i + 3], sum));
+    float4 hi4 = make_float4(__fdiv_rn(v[8 * i + 4], sum), __fdiv_rn(v[8 * i + 5], sum), __fdiv_rn(v[8 * i + 6], sum), __fdiv_rn(v[8 * i + 7], sum));
+    reinterpret_cast<float4*>(o + static_cast<int64_t>(i) * W)[0] = lo4;
+    reinterpret_cast<float4*>(o + static_cast<int64_t>(i) * W)[1] = hi4;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// keypoint NMS.  state per pixel: 0 = not a candidate, 1 = undecided, 2 = kept, 3 = suppressed.
+// Sequential reference: visit candidates by (confidence desc, raster index asc); a candidate is kept iff
+// no already-kept candidate lies within Chebyshev distance r.  Parallel fixed point with the same result:
+//   p becomes SUPPRESSED as soon as a higher-priority candidate in its window is KEPT,
+//   p becomes KEPT as soon as every higher-priority candidate in its window is SUPPRESSED.
+// Every decision is final and equals the sequential one (induction over priority), so in-place
+// asynchronous updates are safe; rounds repeat (grid-wide barrier) until nothing is undecided.
+// ------------------------------------------------------------------------------------------------
+struct KpWs {
+  unsigned char* state;        // [B*H*W]
+  unsigned int* remaining;     // [3]
+  int* n_list;                 // [B]
+  unsigned long long* list;    // [B][max_pts]  (ordered_conf << 32) | raster index
+};
+
+__device__ __forceinline__ bool higher(float cq, int q, float cp, int p) { return cq > cp || (cq == cp && q < p); }
+
+__global__ void kp_nms_kernel(const float* __restrict__ heat, int B, int H, int W, float thr, int r, KpWs ws) {
+  cg::grid_group grid = cg::this_grid();
+  const int64_t total = static_cast<int64_t>(B) * H * W;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  volatile unsigned char* state = ws.state;
+  for (int64_t p = tid; p < total; p += nthreads) state[p] = heat[p] >= thr ? 1 : 0;
+  if (tid == 0) { ws.remaining[0] = 0; ws.remaining[1] = 0; ws.remaining[2] = 0; }
+  for (int64_t i = tid; i < B; i += nthreads) ws.n_list[i] = 0;
+  __threadfence();
+  grid.sync();
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  for (int round = 0;; ++round) {
+    unsigned int undecided = 0;
+    for (int64_t p = tid; p < total; p += nthreads) {
+      if (state[p] != 1) continue;
+      const int b = static_cast<int>(p / HW);
+      const int pp = static_cast<int>(p - b * HW);
+      const int y = pp / W, x = pp - y * W;
+      const float cp = heat[p];
+      const unsigned char* sb = ws.state + b * HW;
+      const float* hb = heat + b * HW;
+      bool any_kept = false, any_pending = false;
+      const int y0 = max(0, y - r), y1 = min(H - 1, y + r), x0 = max(0, x - r), x1 = min(W - 1, x + r);
+      for (int yy = y0; yy <= y1 && !any_kept; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) {
+          const int q = yy * W + xx;
+          const unsigned char sq = __ldcg(sb + q);
+          if (sq == 0 || sq == 3 || q == pp) continue;
+          if (!higher(hb[q], q, cp, pp)) continue;
+          if (sq == 2) { any_kept = true; break; }
+          any_pending = true;
+        }
+      if (any_kept) state[p] = 3;
+      else if (!any_pending) state[p] = 2;
+      else ++undecided;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) undecided += __shfl_xor_sync(0xffffffffu, undecided, s);
+    if ((threadIdx.x & 31) == 0 && undecided) atomicAdd(&ws.remaining[round % 3], undecided);
+    if (tid == 0) ws.remaining[(round + 1) % 3] = 0;  // next round's slot: last read after barrier round-2, i.e. before barrier round-1
+    __threadfence();
+    grid.sync();
+    if (*(volatile unsigned int*)&ws.remaining[round % 3] == 0) break;
+  }
+}
+
+// python slice semantics of mask[y0:y1, x0:x1] on an axis of length L (demo.py:185-186)
+__device__ __forceinline__ void py_slice(int a, int b, int L, int* s, int* e) {
+  *s = a < 0 ? max(a + L, 0) : min(a, L);
+  *e = b < 0 ? max(b + L, 0) : min(b, L);
+}
+
+__device__ __forceinline__ unsigned int ordered_bits(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unordered_bits(unsigned int o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// survivors -> border filter -> box filter -> unordered list of packed keys
+__global__ void kp_collect_kernel(const float* __restrict__ heat, int B, int H, int W, int border, const float* __restrict__ boxes,
+                                  const int* __restrict__ box_count, int box_ld, int max_pts, KpWs ws) {
+  extern __shared__ int sbox[];  // [nb][4] slice bounds x0,x1,y0,y1
+  const int b = blockIdx.y;
+  int nb = 0;
+  if (boxes) {
+    nb = box_count[b];
+    if (nb < 0) nb = 0;  // overflowed NMS: no boxes are trusted
+    if (nb > box_ld) nb = box_ld;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      const float* bx = boxes + (static_cast<int64_t>(b) * box_ld + i) * 6;
+      int sx, ex, sy, ey;
+      py_slice(static_cast<int>(rintf(bx[0])), static_cast<int>(rintf(bx[2])), W, &sx, &ex);
+      py_slice(static_cast<int>(rintf(bx[1])), static_cast<int>(rintf(bx[3])), H, &sy, &ey);
+      sbox[4 * i] = sx; sbox[4 * i + 1] = ex; sbox[4 * i + 2] = sy; sbox[4 * i + 3] = ey;
+    }
+  }
+  __syncthreads();
+  const int HW = H * W;
+  for (int pp = blockIdx.x * blockDim.x + threadIdx.x; pp < HW; pp += gridDim.x * blockDim.x) {
+    if (ws.state[static_cast<int64_t>(b) * HW + pp] != 2) continue;
+    const int y = pp / W, x = pp - y * W;
+    if (x < border || x >= W - border || y < border || y >= H - border) continue;
+    bool inside = false;
+    for (int i = 0; i < nb && !inside; ++i)
+      inside = x >= sbox[4 * i] && x < sbox[4 * i + 1] && y >= sbox[4 * i + 2] && y < sbox[4 * i + 3];
+    if (inside) continue;
+    const int slot = atomicAdd(&ws.n_list[b], 1);
+    if (slot < max_pts)
+      ws.list[static_cast<int64_t>(b) * max_pts + slot] =
+          (static_cast<unsigned long long>(ordered_bits(heat[static_cast<int64_t>(b) * HW + pp])) << 32) | static_cast<unsigned int>(pp);
+  }
+}
+
+// rank sort by packed key descending (confidence desc, ties: larger raster index first) and emit (x, y, conf)
+__global__ void kp_emit_kernel(int W, int max_pts, KpWs ws, float* __restrict__ out_pts, int* __restrict__ out_count) {
+  __shared__ unsigned long long tile[256];
+  const int b = blockIdx.y;
+  const int nall = ws.n_list[b];
+  const int n = min(nall, max_pts);
+  if (blockIdx.x == 0 && threadIdx.x == 0) out_count[b] = nall > max_pts ? -1 - nall : nall;
+  if (blockIdx.x * blockDim.x >= n) return;
+  const unsigned long long* list = ws.list + static_cast<int64_t>(b) * max_pts;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long ki = i < n ? list[i] : 0ull;
+  int rank = 0;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    tile[threadIdx.x] = j < n ? list[j] : 0ull;
+    __syncthreads();
+    const int lim = min(256, n - j0);
+    for (int k = 0; k < lim; ++k) rank += tile[k] > ki ? 1 : 0;  // keys are unique (distinct raster index)
+    __syncthreads();
+  }
+  if (i < n) {
+    const unsigned int pp = static_cast<unsigned int>(ki & 0xffffffffull);
+    float* o = out_pts + (static_cast<int64_t>(b) * max_pts + rank) * 3;
+    o[0] = static_cast<float>(pp % W);
+    o[1] = static_cast<float>(pp / W);
+    o[2] = unordered_bits(static_cast<unsigned int>(ki >> 32));
+  }
+}
+
+size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+size_t carve(KpWs* ws, char* base, int B, int H, int W, int max_pts) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+  ws->state = reinterpret_cast<unsigned char*>(take(static_cast<size_t>(B) * H * W));
+  ws->remaining = reinterpret_cast<unsigned int*>(take(3 * sizeof(unsigned int)));
+  ws->n_list = reinterpret_cast<int*>(take(sizeof(int) * B));
+  ws->list = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * max_pts));
+  return off;
+}
+
+}  // namespace
+}  // namespace yp
+
+extern "C" int yp_heatmap(const float* semi, int32_t B, int32_t Hc, int32_t Wc, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
+                          int32_t variant, float* heat, void* stream) {
+  YP_REQUIRE(semi && heat, YP_ERR_ARG, "heatmap: null pointer");
+  YP_REQUIRE(B > 0 && Hc > 0 && Wc > 0 && (variant == 0 || variant == 1), YP_ERR_SHAPE, "heatmap: bad shape/variant");
+  YP_REQUIRE(yp::aligned16(heat), YP_ERR_ALIGN, "heatmap: output not 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * Hc * Wc;
+  yp::heatmap_kernel<<<static_cast<unsigned>(yp::ceil_div64(total, 128)), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      semi, B, Hc, Wc, sB, sC, sH, sW, variant, heat);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+extern "C" size_t yp_keypoints_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t max_pts) {
+  if (B <= 0 || H <= 0 || W <= 0 || max_pts <= 0) return 0;
+  yp::KpWs ws;
+  return yp::carve(&ws, nullptr, B, H, W, max_pts);
+}
+
+extern "C" int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, float conf_thresh, int32_t nms_dist, int32_t border,
+                            const float* boxes, const int32_t* box_count, int32_t box_ld, float* out_pts, int32_t* out_count,
+                            int32_t max_pts, void* workspace, size_t workspace_bytes, void* stream) {
+  YP_REQUIRE(heat && out_pts && out_count && workspace, YP_ERR_ARG, "keypoints: null pointer");
+  YP_REQUIRE(B > 0 && H > 0 && W > 0 && max_pts > 0 && nms_dist >= 0 && border >= 0, YP_ERR_SHAPE, "keypoints: bad shape");
+  YP_REQUIRE(static_cast<int64_t>(H) * W < (1ll << 31), YP_ERR_SHAPE, "keypoints: image too large");
+  YP_REQUIRE(!boxes || (box_count && box_ld > 0 && box_ld <= 8192), YP_ERR_ARG, "keypoints: boxes need box_count and 0 < box_ld <= 8192");
+  yp::KpWs ws;
+  const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, H, W, max_pts);
+  YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "keypoints: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  static thread_local int coop_blocks = 0;
+  if (coop_blocks == 0) {
+    int per_sm = 0;
+    YP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yp::kp_nms_kernel, 256, 0));
+    if (per_sm > 4) per_sm = 4;
+    YP_REQUIRE(per_sm >= 1, YP_ERR_CUDA, "keypoints: NMS kernel does not fit on an SM");
+    coop_blocks = per_sm * yp::sm_count();
+  }
+  int Bv = B, Hv = H, Wv = W, rv = nms_dist;
+  float thr = conf_thresh;
+  void* args[] = {(void*)&heat, &Bv, &Hv, &Wv, &thr, &rv, &ws};
+  YP_CUDA_OK(cudaLaunchCooperativeKernel((void*)yp::kp_nms_kernel, dim3(coop_blocks), dim3(256), args, 0, st));
+  const size_t smem = boxes ? sizeof(int) * 4 * box_ld : 0;
+  if (smem > 48 * 1024) {
+    static thread_local bool raised = false;
+    if (!raised) { YP_CUDA_OK(cudaFuncSetAttribute(yp::kp_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)); raised = true; }
+  }
+  const int HW = H * W;
+  int cblocks = yp::ceil_div(HW, 256);
+  if (cblocks > 4 * yp::sm_count()) cblocks = 4 * yp::sm_count();
+  yp::kp_collect_kernel<<<dim3(cblocks, B), 256, smem, st>>>(heat, B, H, W, border, boxes, box_count, box_ld, max_pts, ws);
+  yp::kp_emit_kernel<<<dim3(yp::ceil_div(max_pts, 256), B), 256, 0, st>>>(W, max_pts, ws, out_pts, out_count);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
