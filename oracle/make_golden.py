@@ -107,7 +107,9 @@ def main():
     save("heatmap.npz", semi=semi, heat_torch=heat_t, heat_demo0=heat_d)
 
     # ---- 6. keypoints (src/utils/utils.py:465-485, 118-182) -------------------------------------
-    heat = rs.uniform(0, 1, (96, 128)).astype(np.float32) ** 6
+    heat = (((rs.permutation(96 * 128) + 1.0) / (96 * 128 + 1.0)) ** 6).astype(np.float32).reshape(96, 128)
+    cand = heat[heat >= 0.015]
+    assert len(np.unique(cand)) == cand.size, "golden heatmap must be tie-free (the reference's sorts are unstable on ties)"
     arrs = dict(heat=heat)
     kcases = [(0.015, 4), (0.12, 8), (0.3, 2), (0.999999, 4)]
     for ci, (thr, r) in enumerate(kcases):

@@ -1,0 +1,135 @@
+"""GPU parity of yp_conv2d_nhwc_fwd (tcgen05 path and the SIMT cross-check) through the C ABI.
+
+Reference for a floating-point kernel: plain PyTorch fp32 conv2d on the same device with TF32 disabled,
+fed the exact operand values the kernel sees (hi+lo planes / bf16-rounded values)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from yolopoint_b200 import _lib
+from yolopoint_b200._lib import (YP_ACT_NONE, YP_ACT_SILU, YP_ALGO_SIMT, YP_ALGO_TCGEN05, YP_EPI_L2NORM, YP_FMT_BF16, YP_FMT_F32,
+                                  YP_FMT_F32X2, YpConvDesc)
+from yolopoint_b200.engine import make_view, split_tf32
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_act(vals: torch.Tensor, fmt: int, ctot: int, c_off: int):
+    """vals [B,H,W,C] fp32 (cuda) -> buffer [P,B,H,W,ctot] holding vals at channel offset c_off, rest = 7.0 sentinel."""
+    B, H, W, Cc = vals.shape
+    if fmt == YP_FMT_BF16:
+        buf = torch.full((1, B, H, W, ctot), 7.0, dtype=torch.bfloat16, device=vals.device)
+        buf[0, ..., c_off:c_off + Cc] = vals.to(torch.bfloat16)
+        eff = buf[0, ..., c_off:c_off + Cc].float()
+    else:
+        buf = torch.full((2, B, H, W, ctot), 7.0, dtype=torch.float32, device=vals.device)
+        buf[:, ..., c_off:c_off + Cc] = split_tf32(vals)
+        eff = buf[0, ..., c_off:c_off + Cc] + buf[1, ..., c_off:c_off + Cc]
+    return buf, eff
+
+
+def _read(buf: torch.Tensor, fmt: int, c_off: int, Cc: int):
+    t = buf[..., c_off:c_off + Cc].float()
+    return t[0] + t[1] if fmt == YP_FMT_F32X2 else t[0]
+
+
+CASES = [
+    # B, H, W, Cin, Cout, k, s, act, res, l2, up, out_fmt_plain
+    dict(B=1, H=16, W=16, Cin=32, Cout=32, k=1, s=1),
+    dict(B=2, H=20, W=20, Cin=64, Cout=64, k=3, s=1, res=True),
+    dict(B=1, H=40, W=24, Cin=32, Cout=64, k=3, s=2),
+    dict(B=1, H=80, W=80, Cin=128, Cout=128, k=3, s=1, act=False, l2=True, plain=True),
+    dict(B=1, H=20, W=20, Cin=256, Cout=128, k=1, s=1, up=True),
+    dict(B=1, H=24, W=40, Cin=16, Cout=16, k=3, s=1),
+    dict(B=2, H=12, W=20, Cin=48, Cout=96, k=3, s=2),
+    dict(B=1, H=8, W=8, Cin=512, Cout=256, k=1, s=1, act=False, plain=True),
+    dict(B=1, H=80, W=80, Cin=128, Cout=80, k=1, s=1, act=False, plain=True, nobias=True),
+    dict(B=3, H=34, W=18, Cin=64, Cout=32, k=3, s=1, res=True),
+]
+
+
+def run_case(c, fmt, algo):
+    L = _lib.lib(require_device=True)
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    B, H, W, Cin, Cout, k, s = c["B"], c["H"], c["W"], c["Cin"], c["Cout"], c["k"], c["s"]
+    act = YP_ACT_SILU if c.get("act", True) else YP_ACT_NONE
+    Ho, Wo = H // s, W // s
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev)
+    bias = None if c.get("nobias") else torch.randn(Cout, generator=g).to(dev)
+    in_buf, x_eff = _mk_act(x, fmt, Cin + 16, 16)                   # input is a channel slice of a wider buffer
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous()
+    if fmt == YP_FMT_BF16:
+        wp = wk.to(torch.bfloat16).unsqueeze(0).contiguous()
+        w_eff = wp[0].float()
+    else:
+        wp = split_tf32(wk).contiguous()
+        w_eff = wp[0] + wp[1]
+    out_fmt = YP_FMT_F32 if c.get("plain") else fmt
+    planes = 2 if out_fmt == YP_FMT_F32X2 else 1
+    odt = torch.bfloat16 if out_fmt == YP_FMT_BF16 else torch.float32
+    up = 2 if c.get("up") else 1
+    out_buf = torch.full((planes, B, Ho * up, Wo * up, Cout + 32), 5.0, dtype=odt, device=dev)   # slice at channel offset 32
+    out2_buf = torch.full((planes, B, Ho, Wo, Cout), 5.0, dtype=odt, device=dev) if c.get("up") else None
+    res_buf = res_eff = None
+    if c.get("res"):
+        r = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev)
+        res_buf, res_eff = _mk_act(r, fmt, Cout, 0)
+    d = YpConvDesc()
+    d.in_ = make_view(in_buf, fmt, 16, Cin)
+    d.weight, d.bias = wp.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    d.ksize, d.stride, d.cout, d.act = k, s, Cout, act
+    d.epilogue = YP_EPI_L2NORM if c.get("l2") else 0
+    if res_buf is not None:
+        d.residual = make_view(res_buf, fmt, 0, Cout)
+    d.n_out = 2 if c.get("up") else 1
+    d.out[0] = make_view(out_buf, out_fmt, 32, Cout, upsample=up)
+    if c.get("up"):
+        d.out[1] = make_view(out2_buf, out_fmt, 0, Cout)
+    d.algo = algo
+    _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    # reference
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    wr = w_eff.view(Cout, k, k, Cin).permute(0, 3, 1, 2).contiguous()
+    y = F.conv2d(x_eff.permute(0, 3, 1, 2).double(), wr.double(), None if bias is None else bias.double(), stride=s, padding=k // 2)
+    if act:
+        y = F.silu(y)
+    y = y.permute(0, 2, 3, 1)
+    if res_eff is not None:
+        y = y + res_eff.double()
+    if c.get("l2"):
+        y = y / y.norm(dim=-1, keepdim=True)
+    y = y.float()
+    got = _read(out_buf, out_fmt, 32, Cout)
+    if up == 2:
+        y_up = y.repeat_interleave(2, 1).repeat_interleave(2, 2)
+        got2 = _read(out2_buf, out_fmt, 0, Cout)
+    else:
+        y_up, got2 = y, None
+    tol = 2e-2 if fmt == YP_FMT_BF16 else 2e-5
+    scale = float(y.abs().max()) + 1e-6
+    err = float((got - y_up).abs().max()) / scale
+    assert err < tol, f"{c} fmt={fmt} algo={algo}: rel err {err:.3e}"
+    if got2 is not None:
+        err2 = float((got2 - y).abs().max()) / scale
+        assert err2 < tol, f"{c} second output rel err {err2:.3e}"
+    # untouched channels of the destination buffer keep their sentinel
+    assert float(out_buf[..., :32].float().min()) == 5.0 and float(out_buf[..., :32].float().max()) == 5.0
+    return err
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+@pytest.mark.parametrize("fmt", [YP_FMT_F32X2, YP_FMT_BF16])
+def test_conv_tcgen05(ci, fmt):
+    run_case(CASES[ci], fmt, YP_ALGO_TCGEN05)
+
+
+@pytest.mark.parametrize("ci", [1, 2, 3, 4])
+def test_conv_simt_crosscheck(ci):
+    run_case(CASES[ci], YP_FMT_F32X2, YP_ALGO_SIMT)

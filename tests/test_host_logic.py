@@ -1,0 +1,125 @@
+"""CPU-only tests of the host side: state-dict compatibility with the reference, launch plan + weight packing
+(through the CPU plan interpreter), C-ABI export table."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolopoint_oracle as O
+from yolopoint_b200 import Model, _lib
+from yolopoint_b200.engine import NetPlan, split_tf32, tf32_round
+from yolopoint_b200.synth import perturb_state_dict
+
+from plan_interp import run_plan
+
+NAMES = [str(i) for i in range(80)]
+
+
+@pytest.mark.parametrize("ver", ["n", "s"])
+def test_state_dict_matches_reference(golden, ver):
+    """Same keys, order, shapes and seeded values as the reference Model (src/models/YOLOPoint.py:17-100)."""
+    g = golden(f"state_{ver}.npz")
+    torch.manual_seed(0)
+    m = Model(names=NAMES, version=ver)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["keys"])
+    assert [str(tuple(v.shape)) for v in sd.values()] == list(g["shapes"])
+    np.testing.assert_allclose([float(v.double().sum()) for v in sd.values()], g["sums"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose([float(v.double().abs().sum()) for v in sd.values()], g["asums"], rtol=0, atol=1e-9)
+    assert [n for n, _ in m.named_parameters()] == list(g["param_names"])
+    np.testing.assert_array_equal(m.model.Detect.stride.numpy(), g["stride"])
+    np.testing.assert_array_equal(m.model.Detect.anchors.numpy(), g["anchors"])
+
+
+def test_torch_training_path_matches_oracle_in_eval_math(golden):
+    """The PyTorch module tree (used for training) computes the reference network: compare its eval math to the golden."""
+    g = golden("net_n_64x96.npz")
+    torch.manual_seed(0)
+    m = Model(names=NAMES, version="n")
+    m.load_state_dict(perturb_state_dict(m.state_dict(), 0, "n"))
+    m.model.eval()
+    with torch.no_grad():
+        o = m.model(torch.from_numpy(g["x"]))
+    np.testing.assert_allclose(o["semi"].numpy(), g["semi"], rtol=0, atol=5e-4)
+    np.testing.assert_allclose(o["desc"].numpy(), g["desc"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(o["objects"][0].numpy(), g["pred"], rtol=1e-5, atol=5e-4)
+
+
+def test_fuse_and_partial_load():
+    torch.manual_seed(0)
+    m = Model(names=NAMES, version="n")
+    sd = m.state_dict()
+    m2 = Model(names=["a", "b", "c"], version="n")
+    m2.load_state_dict(sd, strict=True)   # class count changed -> positional partial load, Detect kept
+    assert torch.equal(m2.state_dict()["model.Conv1.conv.weight"], sd["model.Conv1.conv.weight"])
+    assert m2.state_dict()["model.Detect.m.0.bias"].shape[0] == 3 * 8
+    m.eval().fuse()
+    assert "model.Conv1.conv.bias" in m.state_dict() and "model.Conv1.bn.weight" not in m.state_dict()
+    m.freeze_layers([0, 1], verbose=False)
+    assert not list(m.parameters())[0].requires_grad
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64))      # eval-mode inference on CPU must fail loudly
+
+
+def test_tf32_split_is_exact_enough():
+    x = torch.randn(10000) * 3
+    hi = tf32_round(x)
+    assert (hi.view(torch.int32) & 0x1FFF).abs().max() == 0
+    s = split_tf32(x)
+    assert ((s[0].double() + s[1].double() - x.double()).abs() / x.double().abs().clamp_min(1e-30)).max() < 2 ** -21
+
+
+@pytest.mark.parametrize("ver,shape", [("n", (2, 64, 96)), ("s", (1, 64, 64))])
+def test_plan_reproduces_oracle(ver, shape):
+    """Launch plan + packed weights, interpreted on the CPU, equal the oracle network."""
+    torch.manual_seed(0)
+    m = Model(names=NAMES, version=ver)
+    sd = perturb_state_dict(m.state_dict(), 0, ver)
+    B, H, W = shape
+    x = torch.from_numpy(np.random.RandomState(3).rand(B, 3, H, W).astype(np.float32))
+    ref = O.OracleNet(sd, ver, 80).forward(x)
+    net = NetPlan(ver, 80, "fp32")
+    bufs = run_plan(net, sd, x)
+    semi = bufs["semi"][..., :65].permute(0, 3, 1, 2)
+    desc = bufs["desc"].permute(0, 3, 1, 2)
+    np.testing.assert_allclose(semi.numpy(), ref["semi"].numpy(), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(desc.numpy(), ref["desc"].numpy(), rtol=0, atol=2e-5)
+    for i in range(3):
+        det = bufs[f"det{i}"][..., :255]
+        raw = det.view(B, det.shape[1], det.shape[2], 3, 85).permute(0, 3, 1, 2, 4)
+        np.testing.assert_allclose(raw.numpy(), ref["objects"][1][i].numpy(), rtol=0, atol=5e-4)
+
+
+def test_plan_launch_count_and_flops():
+    net = NetPlan("s", 80, "fp32")
+    assert len(net.conv_ops()) == 74 - 10          # 10 C3 blocks each merge cv1 || cv2 into one GEMM
+    torch.manual_seed(0)
+    m = Model(names=NAMES, version="s")
+    meta = {}
+    for op in net.conv_ops():
+        for n in op.names:
+            key = f"model.{n}.conv.weight" if op.bn else f"model.{n}.weight"
+            w = m.state_dict()[key]
+            meta[n] = (w.shape[0], w.shape[1], w.shape[2])
+    gf = net.flops_per_frame(640, 640, meta) / 1e9
+    assert abs(gf - 21.023) < 0.01, gf               # 21.023 GFLOP / frame for S @ 640x640
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads (no GPU needed) and exports exactly the symbols include/yolopoint_b200.h declares."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "yolopoint_b200.h")).read()
+    declared = set(re.findall(r"\b(yp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.yp_abi_version() == 1
+    # struct layouts must agree with the header (sizes only; offsets follow from the C rules both sides use)
+    assert ctypes.sizeof(_lib.YpView) == 48 and ctypes.sizeof(_lib.YpNmsParams) == 40

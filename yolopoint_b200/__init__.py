@@ -1,0 +1,21 @@
+"""yolopoint_b200 -- the YOLOPoint hot path (UniBwTAS/YOLOPoint) on hand-written sm_100a kernels.
+
+Public surface mirrors the reference's Python call signatures:
+
+    Model, load_model                                   src/models/YOLOPoint.py, src/utils/utils.py:55-57
+    non_max_suppression, xywh2xyxy                      src/utils/general_yolo.py
+    flattenDetection, getPtsFromHeatmap, getPtsFromSemi, nms_fast     src/utils/utils.py
+    sample_desc_from_points                             src/evaluations/descriptor_evaluation.py
+    PointTracker.nn_match_two_way, nn_match_two_way     src/demo.py
+    YoloPointFrontend.process_img                       src/demo.py
+    detect, extract_keypoints, match                    convenience names from BASELINE.json
+
+Nothing here falls back to PyTorch or the CPU for inference: the CUDA library must be built and an sm_100
+device present, otherwise the calls raise.
+"""
+from .model import Model, YOLOPoint, load_model  # noqa: F401
+from .api import (PointTracker, detect, extract_keypoints, flattenDetection, getPtsFromHeatmap, getPtsFromSemi, match,  # noqa: F401
+                  nms_fast, nn_match_two_way, non_max_suppression, sample_desc_from_points, xywh2xyxy)
+from .frontend import DEFAULT_CFG, FramePipeline, YoloPointFrontend  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,449 @@
+"""B200 inference engine for the YOLOPoint network (dataflow of src/models/YOLOPoint.py:198-246 of the reference).
+
+The network is compiled into a flat launch list over preallocated NHWC activation buffers in HBM:
+
+  * every ``Conv`` (conv + folded BN + SiLU) is one ``yp_conv2d_nhwc_fwd`` launch (tcgen05 implicit GEMM);
+  * ``torch.cat`` never runs: producers store into channel slices of their consumer's buffer;
+  * ``nn.Upsample(2,'nearest')`` never runs: the producer stores each pixel to the 2x2 block of the
+    consumer's concat buffer (4 parity TMA stores) in its epilogue;
+  * ``Bottleneck`` residual adds, the descriptor L2 normalisation and the C3 ``cv1 || cv2`` pair
+    (one GEMM with N = 2c_) are fused into conv launches;
+  * the three chained SPPF max-pools are one kernel writing the concat buffer in place.
+
+Precision modes: ``fp32`` = activations/weights as (hi, lo) TF32 pairs, 3xTF32 tcgen05 MMAs, fp32-grade
+results (the parity mode); ``bf16`` = bf16 operands, fp32 accumulation (the fast mode).
+
+The launch list for a given (B, H, W) is captured into a CUDA graph after the first eager run.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import YP_ACT_NONE, YP_ACT_SILU, YP_ALGO_TCGEN05, YP_EPI_L2NORM, YP_FMT_BF16, YP_FMT_F32, YP_FMT_F32X2, YpConvDesc, YpView
+
+BN_EPS = 1e-3
+VERSIONS = {"n": (0.33, 0.25), "s": (0.33, 0.5), "m": (0.67, 0.75), "l": (1.0, 1.0), "x": (1.33, 1.25)}
+
+
+def dims(version: str):
+    import math
+    dm, wm = VERSIONS[version]
+    cs = tuple(math.ceil(2 ** k * wm / 8) * 8 for k in range(6, 11))
+    ns = tuple(max(round(k * dm), 1) for k in (3, 6, 9))
+    return cs, ns
+
+
+def fold_conv_bn(w: torch.Tensor, bn) -> Tuple[torch.Tensor, torch.Tensor]:
+    """W' = diag(g/sqrt(var+eps)) W, b' = beta - g*mu/sqrt(var+eps)   (src/utils/torch_utils_yolo.py:194-214)."""
+    if isinstance(bn, dict):
+        g, beta, mu, var, eps = bn["weight"], bn["bias"], bn["running_mean"], bn["running_var"], BN_EPS
+    else:
+        g, beta, mu, var, eps = bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps
+    scale = g.float().div(torch.sqrt(eps + var.float()))
+    wf = w.float() * scale.view(-1, 1, 1, 1)
+    bf = beta.float() - g.float().mul(mu.float()).div(torch.sqrt(var.float() + eps))
+    return wf, bf
+
+
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to TF32 (10-bit mantissa), ties away from zero == PTX cvt.rna.tf32.f32."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def split_tf32(x: torch.Tensor) -> torch.Tensor:
+    """[...] fp32 -> [2, ...] (hi, lo) with hi = tf32(x), lo = tf32(x - hi)."""
+    hi = tf32_round(x)
+    return torch.stack((hi, tf32_round(x - hi)))
+
+
+# --------------------------------------------------------------------------------------------------
+# host-side description (CPU-testable: no CUDA needed to build it)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class BufSpec:
+    name: str
+    H: int
+    W: int
+    C: int
+    fmt: int
+
+
+@dataclass
+class SliceRef:
+    buf: str
+    c_off: int
+    C: int
+    upsample: int = 1
+
+
+@dataclass
+class ConvOp:
+    names: Tuple[str, ...]      # state-dict prefixes whose outputs are concatenated along Cout
+    src: SliceRef
+    dst: Tuple[SliceRef, ...]
+    k: int
+    s: int
+    cout: int                   # padded
+    act: int
+    bn: bool                    # Conv block (fold BN) vs bare nn.Conv2d
+    residual: Optional[SliceRef] = None
+    l2norm: bool = False
+    stem: bool = False
+
+
+@dataclass
+class PoolOp:
+    buf: str
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+class NetPlan:
+    """Shape-independent part: op list with symbolic buffers; instantiate() gives the buffer extents."""
+
+    def __init__(self, version: str, nc: int, precision: str = "fp32"):
+        assert precision in ("fp32", "bf16")
+        self.version, self.nc, self.no = version, nc, nc + 5
+        self.precision = precision
+        self.act_fmt = YP_FMT_F32X2 if precision == "fp32" else YP_FMT_BF16
+        (c1, c2, c3, c4, c5), (n1, n2, n3) = dims(version)
+        self.c = (c1, c2, c3, c4, c5)
+        self.D = c3
+        self.bufs: Dict[str, Tuple[int, int, int]] = {}   # name -> (stride level, C, fmt)
+        self.ops: List[object] = []
+        self.det_pad = _pad16(3 * self.no)
+        self.semi_pad = _pad16(65)
+        self._build(c1, c2, c3, c4, c5, n1, n2, n3)
+
+    # level L means spatial (H / 2**L, W / 2**L)
+    def _buf(self, name, level, C_, fmt=None):
+        self.bufs[name] = (level, C_, self.act_fmt if fmt is None else fmt)
+        return SliceRef(name, 0, C_)
+
+    def _conv(self, names, src, dst, k, s, cout, act=True, bn=True, residual=None, l2norm=False, stem=False):
+        if isinstance(names, str):
+            names = (names,)
+        if isinstance(dst, SliceRef):
+            dst = (dst,)
+        self.ops.append(ConvOp(tuple(names), src, tuple(dst), k, s, cout, YP_ACT_SILU if act else YP_ACT_NONE, bn, residual, l2norm, stem))
+
+    def _c3(self, name, src: SliceRef, level, cout, n, dst):
+        c_ = cout // 2
+        U = self._buf(name + ".U", level, 2 * c_)
+        h = self._buf(name + ".h", level, c_)
+        y = SliceRef(U.buf, 0, c_)
+        self._conv((name + ".cv1", name + ".cv2"), src, U, 1, 1, 2 * c_)
+        for i in range(n):
+            self._conv(f"{name}.m.{i}.cv1", y, h, 1, 1, c_)
+            self._conv(f"{name}.m.{i}.cv2", h, y, 3, 1, c_, residual=y)
+        self._conv(name + ".cv3", U, dst, 1, 1, cout)
+
+    def _build(self, c1, c2, c3, c4, c5, n1, n2, n3):
+        S = SliceRef
+        x0 = self._buf("in_s2d", 1, 16)
+        t1 = self._buf("t1", 1, c1)
+        t2 = self._buf("t2", 2, c2)
+        xa = self._buf("xa", 2, c2)
+        x3 = self._buf("x3", 3, c3)
+        cat6 = self._buf("cat6", 3, 2 * c3)      # up(xe) | xb
+        cat5 = self._buf("cat5", 4, 2 * c4)      # up(xd) | xc
+        cat7 = self._buf("cat7", 4, 2 * c3)      # Conv8(xf) | xe
+        cat8 = self._buf("cat8", 5, 2 * c4)      # Conv9(xg) | xd
+        catd = self._buf("catd", 3, 2 * c2)      # ConvDescA(xa) | up(ConvDescB(xb))
+        xb = S("cat6", c3, c3)
+        xc = S("cat5", c4, c4)
+        # shared encoder
+        self._conv("Conv1", x0, t1, 3, 1, c1, stem=True)
+        self._conv("Conv2", t1, t2, 3, 2, c2)
+        self._c3("Bottleneck1", t2, 2, c2, n1, xa)
+        self._conv("Conv3", xa, x3, 3, 2, c3)
+        # keypoint head
+        sdet = self._buf("sdet", 3, c3)
+        self._c3("BottleneckDet", x3, 3, c3, n1, sdet)
+        semi = self._buf("semi", 3, self.semi_pad, YP_FMT_F32)
+        self._conv("ConvDet", sdet, semi, 1, 1, self.semi_pad, act=False, bn=False)
+        # desc + yolo encoder
+        self._c3("Bottleneck2", x3, 3, c3, n2, xb)
+        # descriptor head
+        self._conv("ConvDescA", xa, S("catd", 0, c2), 3, 2, c2)
+        self._conv("ConvDescB", xb, S("catd", c2, c2, upsample=2), 3, 2, c2)
+        dd = self._buf("dd", 3, c3)
+        self._c3("BottleneckDesc", catd, 3, c3, n1, dd)
+        desc = self._buf("desc", 3, c3, YP_FMT_F32)
+        self._conv("ConvDesc", dd, desc, 3, 1, c3, act=False, bn=False, l2norm=True)
+        # yolo encoder
+        x4 = self._buf("x4", 4, c4)
+        self._conv("Conv4", xb, x4, 3, 2, c4)
+        self._c3("Bottleneck3", x4, 4, c4, n3, xc)
+        x5 = self._buf("x5", 5, c5)
+        self._conv("Conv5", xc, x5, 3, 2, c5)
+        x5b = self._buf("x5b", 5, c5)
+        self._c3("Bottleneck4", x5, 5, c5, n1, x5b)
+        spp = self._buf("sppcat", 5, 2 * c5)     # x | y1 | y2 | y3, each c5/2
+        self._conv("SPPooling.cv1", x5b, S("sppcat", 0, c5 // 2), 1, 1, c5 // 2)
+        self.ops.append(PoolOp("sppcat"))
+        x5c = self._buf("x5c", 5, c5)
+        self._conv("SPPooling.cv2", spp, x5c, 1, 1, c5)
+        # neck
+        self._conv("Conv6", x5c, (S("cat8", c4, c4), S("cat5", 0, c4, upsample=2)), 1, 1, c4)     # xd
+        x6 = self._buf("x6", 4, c4)
+        self._c3("Bottleneck5", cat5, 4, c4, n1, x6)
+        self._conv("Conv7", x6, (S("cat7", c3, c3), S("cat6", 0, c3, upsample=2)), 1, 1, c3)      # xe
+        xf = self._buf("xf", 3, c3)
+        self._c3("Bottleneck6", cat6, 3, c3, n1, xf)
+        self._conv("Conv8", xf, S("cat7", 0, c3), 3, 2, c3)
+        xg = self._buf("xg", 4, c4)
+        self._c3("Bottleneck7", cat7, 4, c4, n1, xg)
+        self._conv("Conv9", xg, S("cat8", 0, c4), 3, 2, c4)
+        xh = self._buf("xh", 5, c5)
+        self._c3("Bottleneck8", cat8, 5, c5, n1, xh)
+        for i, (src, lvl) in enumerate(((xf, 3), (xg, 4), (xh, 5))):
+            det = self._buf(f"det{i}", lvl, self.det_pad, YP_FMT_F32)
+            self._conv(f"Detect.m.{i}", src, det, 1, 1, self.det_pad, act=False, bn=False)
+
+    def conv_ops(self):
+        return [op for op in self.ops if isinstance(op, ConvOp)]
+
+    def buffer_specs(self, H: int, W: int) -> List[BufSpec]:
+        return [BufSpec(n, H >> l, W >> l, c, f) for n, (l, c, f) in self.bufs.items()]
+
+    def flops_per_frame(self, H: int, W: int, weights_meta: Dict[str, Tuple[int, int, int]]) -> float:
+        """Algorithmic conv FLOPs (unpadded channels, stem counted as the original 6x6)."""
+        total = 0.0
+        for op in self.conv_ops():
+            lvl = self.bufs[op.dst[0].buf][0]
+            ho, wo = H >> lvl, W >> lvl
+            if op.dst[0].upsample == 2:
+                ho, wo = ho // 2, wo // 2
+            for n in op.names:
+                co, ci, k = weights_meta[n]
+                total += 2.0 * ho * wo * co * ci * k * k
+        return total
+
+
+# --------------------------------------------------------------------------------------------------
+# weight packing (pure torch, CPU or CUDA)
+# --------------------------------------------------------------------------------------------------
+def _get(sd, key):
+    return sd[key] if key in sd else sd["model." + key]
+
+
+def _has(sd, key):
+    return key in sd or ("model." + key) in sd
+
+
+def folded_weight(sd, name: str, bn: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    if bn:
+        w = _get(sd, name + ".conv.weight").float()
+        if _has(sd, name + ".bn.weight"):
+            return fold_conv_bn(w, {k: _get(sd, f"{name}.bn.{k}") for k in ("weight", "bias", "running_mean", "running_var")})
+        return w, _get(sd, name + ".conv.bias").float()  # already fused state dict
+    w = _get(sd, name + ".weight").float()
+    b = _get(sd, name + ".bias").float() if _has(sd, name + ".bias") else None
+    return w, b
+
+
+def pack_conv(sd, op: ConvOp, cin_view: int, precision: str) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """-> (weight [planes, cout_pad, taps*cin_view], bias [cout_pad] or None) in the operand format."""
+    ws, bs = [], []
+    for n in op.names:
+        w, b = folded_weight(sd, n, op.bn)
+        ws.append(w)
+        bs.append(b)
+    w = torch.cat(ws, 0)
+    bias = None if all(b is None for b in bs) else torch.cat([b if b is not None else torch.zeros(x.shape[0]) for b, x in zip(bs, ws)])
+    co, ci, kh, kw = w.shape
+    if op.stem:  # 6x6 s2 p2 on 3 channels == 3x3 s1 p1 on the 2x2 space-to-depth image (channel = (ph*2+pw)*3 + c)
+        assert (kh, kw, ci) == (6, 6, 3)
+        w = w.view(co, 3, 3, 2, 3, 2).permute(0, 2, 4, 3, 5, 1).reshape(co, 9, 12)  # [co, (dh,dw), (ph,pw,c)]
+        wk = torch.zeros(co, 9, cin_view, dtype=torch.float32, device=w.device)
+        wk[:, :, :12] = w
+    else:
+        assert ci <= cin_view and kh == op.k
+        wk = torch.zeros(co, kh * kw, cin_view, dtype=torch.float32, device=w.device)
+        wk[:, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+    full = torch.zeros(op.cout, wk.shape[1] * cin_view, dtype=torch.float32, device=w.device)
+    full[:co] = wk.reshape(co, -1)
+    if bias is not None:
+        bfull = torch.zeros(op.cout, dtype=torch.float32, device=w.device)
+        bfull[:co] = bias
+        bias = bfull
+    packed = split_tf32(full) if precision == "fp32" else full.to(torch.bfloat16).unsqueeze(0)
+    return packed.contiguous(), bias
+
+
+# --------------------------------------------------------------------------------------------------
+# device side
+# --------------------------------------------------------------------------------------------------
+_TORCH_DT = {YP_FMT_F32X2: torch.float32, YP_FMT_F32: torch.float32, YP_FMT_BF16: torch.bfloat16}
+_PLANES = {YP_FMT_F32X2: 2, YP_FMT_F32: 1, YP_FMT_BF16: 1}
+
+
+def make_view(t: torch.Tensor, fmt: int, c_off: int = 0, C_: Optional[int] = None, upsample: int = 1) -> YpView:
+    """t: [planes, B, H, W, Ctot] contiguous device tensor."""
+    P, B, H, W, Ct = t.shape
+    C_ = Ct - c_off if C_ is None else C_
+    v = YpView()
+    v.base = t.data_ptr() + c_off * t.element_size()
+    if upsample == 2:
+        H, W = H // 2, W // 2
+    v.B, v.H, v.W, v.C = B, H, W, C_
+    v.pix_stride = Ct
+    v.plane_stride = t.stride(0)
+    v.format = fmt
+    v.upsample = upsample
+    return v
+
+
+class ShapePlan:
+    """Buffers + launch list for one (B, H, W)."""
+
+    def __init__(self, eng: "Engine", B: int, H: int, W: int):
+        assert H % 32 == 0 and W % 32 == 0, "H and W must be multiples of 32 (src/demo.py:112-121)"
+        self.eng, self.B, self.H, self.W = eng, B, H, W
+        net, dev = eng.net, eng.device
+        self.bufs: Dict[str, torch.Tensor] = {}
+        for s in net.buffer_specs(H, W):
+            self.bufs[s.name] = torch.zeros((_PLANES[s.fmt], B, s.H, s.W, s.C), dtype=_TORCH_DT[s.fmt], device=dev)
+        self.fmt = {n: f for n, (_, _, f) in net.bufs.items()}
+        Hc, Wc = H // 8, W // 8
+        self.x_in = torch.zeros((B, 3, H, W), dtype=torch.float32, device=dev)
+        self.frame_in = torch.zeros((B, H, W, 3), dtype=torch.uint8, device=dev)
+        self.semi = torch.empty((B, 65, Hc, Wc), dtype=torch.float32, device=dev)
+        self.desc = torch.empty((B, net.D, Hc, Wc), dtype=torch.float32, device=dev)
+        self.A = 3 * (Hc * Wc + (Hc // 2) * (Wc // 2) + (Hc // 4) * (Wc // 4))
+        self.pred = torch.empty((B, self.A, net.no), dtype=torch.float32, device=dev)
+        self.raw = [torch.empty((B, 3, Hc >> i, Wc >> i, net.no), dtype=torch.float32, device=dev) for i in range(3)]
+        self._keep = []      # ctypes objects referenced by the launch closures
+        self.launches = []   # callables (stream_ptr) -> None
+        self._compile()
+        self.graphs = {}
+
+    def view(self, ref: SliceRef) -> YpView:
+        return make_view(self.bufs[ref.buf], self.fmt[ref.buf], ref.c_off, ref.C, ref.upsample)
+
+    def _compile(self):
+        L = _lib.lib()
+        eng = self.eng
+        for op in eng.net.ops:
+            if isinstance(op, PoolOp):
+                v = self.view(SliceRef(op.buf, 0, self.bufs[op.buf].shape[-1]))
+                self._keep.append(v)
+                self.launches.append(lambda st, v=v: _lib.check(L.yp_sppf_pool(C.byref(v), st)))
+                continue
+            w, b = eng.weights[op.names]
+            d = YpConvDesc()
+            d.in_ = self.view(op.src)
+            d.weight = w.data_ptr()
+            d.bias = b.data_ptr() if b is not None else None
+            d.ksize, d.stride, d.cout, d.act = op.k, op.s, op.cout, op.act
+            d.epilogue = YP_EPI_L2NORM if op.l2norm else 0
+            if op.residual is not None:
+                d.residual = self.view(op.residual)
+            d.n_out = len(op.dst)
+            for i, ds in enumerate(op.dst):
+                d.out[i] = self.view(ds)
+            d.algo = eng.algo
+            self._keep.append(d)
+            self.launches.append(lambda st, d=d: _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), st)))
+
+    # ---- pieces -------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.eng.device).cuda_stream)
+
+    def run_input(self, frame: bool):
+        L = _lib.lib()
+        v = self.view(SliceRef("in_s2d", 0, 16))
+        if frame:
+            _lib.check(L.yp_frame_to_s2d(self.frame_in.data_ptr(), self.B, self.H, self.W, C.byref(v), self._stream()))
+        else:
+            _lib.check(L.yp_nchw_to_s2d(self.x_in.data_ptr(), self.B, self.H, self.W, C.byref(v), self._stream()))
+
+    def run_net(self):
+        st = self._stream()
+        for f in self.launches:
+            f(st)
+
+    def run_decode(self, want_raw: bool = True):
+        L, net, st = _lib.lib(), self.eng.net, self._stream()
+        row = 0
+        for i in range(3):
+            det = self.bufs[f"det{i}"]
+            _, B, ny, nx, ldc = det.shape
+            anc = (C.c_float * 6)(*[float(v) for v in self.eng.anchors_px[i]])
+            _lib.check(L.yp_detect_decode(det.data_ptr(), B, ny, nx, ldc, 3, net.no, float(self.eng.stride[i]), anc,
+                                          self.raw[i].data_ptr() if want_raw else None, self.pred.data_ptr(), self.A, row, st))
+            row += 3 * ny * nx
+
+    def run_export(self):
+        """NHWC fp32 head outputs -> the NCHW tensors Model.forward returns."""
+        L, st = _lib.lib(), self._stream()
+        vs = self.view(SliceRef("semi", 0, self.bufs["semi"].shape[-1]))
+        vd = self.view(SliceRef("desc", 0, self.bufs["desc"].shape[-1]))
+        _lib.check(L.yp_nhwc_to_nchw(C.byref(vs), 65, self.semi.data_ptr(), st))
+        _lib.check(L.yp_nhwc_to_nchw(C.byref(vd), self.eng.net.D, self.desc.data_ptr(), st))
+
+    def run_forward(self, frame: bool = False):
+        self.run_input(frame)
+        self.run_net()
+        self.run_decode(True)
+        self.run_export()
+
+    def graphed(self, key: str, fn):
+        """Run ``fn`` through a CUDA graph captured on first use (after one eager warm-up run)."""
+        g = self.graphs.get(key)
+        if g is None:
+            fn()  # eager: sets function attributes, fills caches
+            torch.cuda.synchronize(self.eng.device)
+            if not self.eng.use_graphs:
+                return
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self.graphs[key] = g
+        g.replay()
+
+
+class Engine:
+    def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True):
+        _lib.lib(require_device=True)
+        self.device = torch.device(device)
+        self.net = NetPlan(version, nc, precision)
+        self.precision, self.algo, self.use_graphs = precision, algo, use_graphs
+        sd = {k: v.detach() for k, v in sd.items()}
+        self.anchors = _get(sd, "Detect.anchors").float().cpu()
+        self.stride = torch.tensor([8.0, 16.0, 32.0])
+        self.anchors_px = (self.anchors * self.stride.view(-1, 1, 1)).reshape(3, 6).tolist()
+        self.weights = {}
+        for op in self.net.conv_ops():
+            cin_view = op.src.C
+            w, b = pack_conv({k: v.cpu() for k, v in sd.items() if any(k.startswith(n) or k.startswith("model." + n) for n in op.names)},
+                             op, cin_view, precision)
+            self.weights[op.names] = (w.to(self.device), None if b is None else b.to(self.device))
+        self.plans: Dict[Tuple[int, int, int], ShapePlan] = {}
+
+    def plan(self, B: int, H: int, W: int) -> ShapePlan:
+        key = (B, H, W)
+        if key not in self.plans:
+            self.plans[key] = ShapePlan(self, B, H, W)
+        return self.plans[key]
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor):
+        """x: float32 NCHW [B,3,H,W] on this device -> the reference's eval-mode output dict (fresh tensors)."""
+        if x.device != self.device:
+            raise RuntimeError(f"input on {x.device}, engine on {self.device}; yolopoint_b200 has no CPU path")
+        B, Cc, H, W = x.shape
+        assert Cc == 3
+        p = self.plan(B, H, W)
+        p.x_in.copy_(x)
+        p.graphed("forward", lambda: p.run_forward(False))
+        return {"semi": p.semi.clone(), "desc": p.desc.clone(), "objects": (p.pred.clone(), [r.clone() for r in p.raw])}

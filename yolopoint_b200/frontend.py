@@ -1,0 +1,189 @@
+"""Whole-frame pipeline: the body of ``YoloPointFrontend.process_img`` (src/demo.py:125-230 of the reference) plus the
+tracker's two-way match against the previous frame (src/demo.py:386, 300-341), as ONE CUDA graph per frame parity:
+
+  uint8 frame -> space-to-depth operand -> network -> Detect decode -> box NMS -> cell softmax heatmap ->
+  keypoint NMS (+ border and in-box filters) -> descriptor sampling -> match with the previous frame
+
+The reference crosses the host/device boundary four times per frame and runs NMS / matching on the CPU; here the
+frame goes up once and the compact results come back once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import YpNmsParams
+from .engine import SliceRef
+
+DEFAULT_CFG = dict(  # configs/kitti_inference.yaml:5-16 of the reference
+    detection_threshold=0.12, nms=8, nn_thresh=0.7, conf_thres_box=0.4, iou_thres_box=0.45, max_det=1000,
+)
+
+
+class FramePipeline:
+    """Static buffers + graphs for frames of one shape.  All results stay on the device until ``fetch``."""
+
+    def __init__(self, model, B: int, H: int, W: int, cfg: Optional[dict] = None, filter_pts: bool = True, max_pts: int = 4096,
+                 nms_cap: int = 4096, heat_variant: int = 1, do_match: bool = True):
+        self.cfg = dict(DEFAULT_CFG, **(cfg or {}))
+        self.eng = model.engine() if hasattr(model, "engine") else model
+        self.plan = self.eng.plan(B, H, W)
+        self.B, self.H, self.W = B, H, W
+        self.filter_pts, self.max_pts, self.nms_cap, self.heat_variant, self.do_match = filter_pts, max_pts, (nms_cap + 63) // 64 * 64, heat_variant, do_match
+        dev, D = self.eng.device, self.eng.net.D
+        self.D = D
+        L = _lib.lib(require_device=True)
+        md = self.cfg["max_det"]
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)
+        self.boxes, self.bcount = z(B, md, 6), z(B, dt=torch.int32)
+        self.heat = z(B, H, W)
+        self.pts = [z(B, max_pts, 3), z(B, max_pts, 3)]
+        self.kcount = [z(B, dt=torch.int32), z(B, dt=torch.int32)]
+        self.descs = [z(B, max_pts, D), z(B, max_pts, D)]
+        self.row_key, self.col_key = z(B, max_pts, dt=torch.int64), z(B, max_pts, dt=torch.int64)
+        self.matches, self.mcount = z(B, max_pts, 3), z(B, dt=torch.int32)
+        self.ws_nms = torch.empty(L.yp_box_nms_workspace_bytes(B, self.plan.A, self.eng.net.no, self.nms_cap), dtype=torch.uint8, device=dev)
+        self.ws_kp = torch.empty(L.yp_keypoints_workspace_bytes(B, H, W, max_pts), dtype=torch.uint8, device=dev)
+        self.nms_params = YpNmsParams(float(self.cfg["conf_thres_box"]), float(self.cfg["iou_thres_box"]), 1, 1, int(md), 30000, 7680.0, None)
+        self.parity = 0
+        # pinned host mirrors for the single read-back
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        self.h_frame = torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        self.h_counts = torch.empty((3, B), dtype=torch.int32, pin_memory=True)
+        self.d_counts = z(3, B, dt=torch.int32)
+        self.h_pts, self.h_boxes, self.h_desc, self.h_matches = pin(self.pts[0]), pin(self.boxes), pin(self.descs[0]), pin(self.matches)
+        self.launch_count = None
+
+    # ---- device work ---------------------------------------------------------------------------
+    def _enqueue(self, k: int, from_frame: bool = True):
+        """Everything for the frame currently in plan.frame_in (or plan.x_in), results into parity-k buffers."""
+        L, p, dev = _lib.lib(), self.plan, self.eng.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        B, H, W, cfg = self.B, self.H, self.W, self.cfg
+        p.run_input(from_frame)
+        p.run_net()
+        p.run_decode(False)
+        _lib.check(L.yp_box_nms(p.pred.data_ptr(), B, p.A, self.eng.net.no, C.byref(self.nms_params), self.nms_cap, self.boxes.data_ptr(),
+                                self.bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), st))
+        semi = p.bufs["semi"][0]   # [B,Hc,Wc,80] fp32 NHWC
+        sB, sH, sW, sC = semi.stride()
+        _lib.check(L.yp_heatmap(semi.data_ptr(), B, H // 8, W // 8, sB, sC, sH, sW, self.heat_variant, self.heat.data_ptr(), st))
+        _lib.check(L.yp_keypoints(self.heat.data_ptr(), B, H, W, float(cfg["detection_threshold"]), int(cfg["nms"]), 4,
+                                  self.boxes.data_ptr() if self.filter_pts else None, self.bcount.data_ptr() if self.filter_pts else None,
+                                  self.boxes.shape[1] if self.filter_pts else 0, self.pts[k].data_ptr(), self.kcount[k].data_ptr(), self.max_pts,
+                                  self.ws_kp.data_ptr(), self.ws_kp.numel(), st))
+        desc = p.bufs["desc"][0]   # [B,Hc,Wc,D] fp32 NHWC, unit norm
+        dB, dH, dW, dD = desc.stride()
+        _lib.check(L.yp_sample_desc(desc.data_ptr(), B, self.D, H // 8, W // 8, dB, dD, dH, dW, H, W, self.pts[k].data_ptr(),
+                                    self.kcount[k].data_ptr(), self.max_pts, self.descs[k].data_ptr(), st))
+        if self.do_match:
+            for b in range(B):  # previous frame (parity 1-k) is desc1, current is desc2, as PointTracker.update does
+                _lib.check(L.yp_match_partial(self.descs[1 - k][b].data_ptr(), self.kcount[1 - k][b:].data_ptr(), self.max_pts,
+                                              self.descs[k][b].data_ptr(), self.kcount[k][b:].data_ptr(), self.max_pts, self.D, 0,
+                                              self.row_key[b].data_ptr(), self.col_key[b].data_ptr(), st))
+                _lib.check(L.yp_match_finalize(self.row_key[b].data_ptr(), self.kcount[1 - k][b:].data_ptr(), self.max_pts,
+                                               self.col_key[b].data_ptr(), self.max_pts, float(cfg["nn_thresh"]), self.matches[b].data_ptr(),
+                                               self.mcount[b:].data_ptr(), st))
+        self.d_counts[0].copy_(self.kcount[k]); self.d_counts[1].copy_(self.bcount); self.d_counts[2].copy_(self.mcount)
+
+    def n_launches(self) -> int:
+        """Kernels of this library launched per frame batch (for bench.py's gpu_launches)."""
+        net_launches = len(self.plan.launches)
+        per = 1 + net_launches + 3 + 6 + 1 + 3 + 1 + (self.B * 3 if self.do_match else 0)
+        return per
+
+    def step_device(self, from_frame: bool = True):
+        """Process the frame already resident in plan.frame_in / plan.x_in; flips the parity."""
+        k = self.parity
+        self.plan.graphed(f"frame{k}{int(from_frame)}", lambda: self._enqueue(k, from_frame))
+        self.parity = 1 - k
+        return k
+
+    def reset_tracking(self):
+        for c in self.kcount:
+            c.zero_()
+        self.parity = 0
+
+    # ---- host boundary -------------------------------------------------------------------------
+    def step_host(self, frames_u8: np.ndarray):
+        """frames [B,H,W,3] uint8 on the host -> per-image (pts[3,N] f64, desc[D,N] f32, boxes[n,6] f32, matches[3,L] f64)."""
+        dev = self.eng.device
+        self.h_frame.copy_(torch.from_numpy(np.ascontiguousarray(frames_u8)).view(self.B, self.H, self.W, 3))
+        self.plan.frame_in.copy_(self.h_frame, non_blocking=True)
+        k = self.step_device(True)
+        self.h_counts.copy_(self.d_counts, non_blocking=True)
+        self.h_pts.copy_(self.pts[k], non_blocking=True)
+        self.h_boxes.copy_(self.boxes, non_blocking=True)
+        self.h_desc.copy_(self.descs[k], non_blocking=True)
+        self.h_matches.copy_(self.matches, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        out = []
+        for b in range(self.B):
+            nk, nb, nm = (int(v) for v in self.h_counts[:, b])
+            if nk < 0 or nb < 0:
+                raise RuntimeError(f"buffer overflow (keypoints {nk}, boxes {nb}): raise max_pts / nms_cap")
+            pts = self.h_pts[b, :nk].numpy().astype(np.float64).T.copy()
+            desc = self.h_desc[b, :nk].numpy().T.copy()
+            boxes = self.h_boxes[b, :nb].numpy().copy()
+            matches = self.h_matches[b, :max(nm, 0)].numpy().astype(np.float64).T.copy()
+            out.append((pts, desc, boxes, matches))
+        return out
+
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.h_counts, self.h_pts, self.h_boxes, self.h_desc, self.h_matches))
+
+    def h2d_bytes(self) -> int:
+        return self.h_frame.numel()
+
+
+class YoloPointFrontend:
+    """Drop-in for the reference frontend's per-frame call (src/demo.py:15-230) around an already-built model.
+
+    ``process_img(img)`` takes a uint8 HxWx3 frame and returns ``(pts [3,N] float64, desc [D,N] float32, [boxes [n,6]])``
+    exactly like the reference (crop to multiples of 32 included; ``crop_resize`` is not supported)."""
+
+    def __init__(self, model, config: Optional[dict] = None, filter_pts: bool = True, max_pts: int = 4096, nms_cap: int = 4096):
+        self.model = model
+        cfg = dict(DEFAULT_CFG)
+        if config:
+            m = config.get("model", config)
+            cfg.update({k: v for k, v in m.get("superpoint", {}).items() if k in cfg})
+            cfg.update({k: v for k, v in m.get("yolo", {}).items() if k in cfg})
+            cfg.update({k: v for k, v in config.items() if k in cfg})
+        self.cfg, self.filter_pts, self.max_pts, self.nms_cap = cfg, filter_pts, max_pts, nms_cap
+        self.cell, self.border_remove = 8, 4
+        self._pipes: Dict[Tuple[int, int], FramePipeline] = {}
+        self.last_matches = None
+
+    def preprocess(self, img):  # src/demo.py:97-123 without crop_resize
+        h0, w0 = img.shape[:2]
+        cut_h0 = cut_w0 = 0
+        if h0 % 32 or w0 % 32:
+            cut_h, cut_w = (h0 % 32) / 2, (w0 % 32) / 2
+            cut_h0, cut_h1 = int(np.ceil(cut_h)), int(np.floor(cut_h))
+            cut_w0, cut_w1 = int(np.ceil(cut_w)), int(np.floor(cut_w))
+            img = img[cut_h0:h0 - cut_h1, cut_w0:w0 - cut_w1]
+        return img, cut_h0, cut_w0, 1.0
+
+    def pipeline(self, H: int, W: int) -> FramePipeline:
+        if (H, W) not in self._pipes:
+            self._pipes[(H, W)] = FramePipeline(self.model, 1, H, W, self.cfg, self.filter_pts, self.max_pts, self.nms_cap)
+        return self._pipes[(H, W)]
+
+    @torch.no_grad()
+    def process_img(self, img, rostpc=None):
+        img, cth, ctw, _ = self.preprocess(img)
+        H, W, _ = img.shape
+        pts, desc, boxes, matches = self.pipeline(H, W).step_host(img[None])[0]
+        self.last_matches = matches
+        obj = torch.from_numpy(boxes)
+        if pts.shape[1] == 0:
+            return np.zeros((3, 0)), None, None  # src/demo.py:152-153
+        pts[0] += ctw
+        pts[1] += cth
+        obj[:, :4] += torch.tensor([ctw, cth, ctw, cth], dtype=obj.dtype)
+        return pts, desc, [obj]

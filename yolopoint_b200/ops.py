@@ -1,0 +1,170 @@
+"""Device-side post-processing operators (thin wrappers over the C ABI; torch tensors carry the memory).
+
+All functions take and return CUDA tensors, enqueue on the current torch stream and never synchronise;
+variable-length results come back as (max-size buffer, int32 count) pairs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import YpNmsParams
+
+_ws_cache = {}
+
+
+def _stream(dev) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _workspace(dev, kind: str, nbytes: int) -> torch.Tensor:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), kind)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = t
+    return t
+
+
+def _need_cuda(t: torch.Tensor, what: str):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"{what} must be a CUDA tensor: yolopoint_b200 has no CPU path")
+
+
+def class_mask_tensor(classes: Optional[Sequence[int]], nc: int, dev) -> Optional[torch.Tensor]:
+    if classes is None:
+        return None
+    words = [0] * ((nc + 31) // 32)
+    for c in classes:
+        c = int(c)
+        if 0 <= c < nc:
+            words[c >> 5] |= 1 << (c & 31)
+    return torch.tensor([w - (1 << 32) if w >= (1 << 31) else w for w in words], dtype=torch.int32, device=dev)
+
+
+def box_nms(pred: torch.Tensor, conf_thres: float, iou_thres: float, multi_label: bool, agnostic: bool, max_det: int,
+            classes: Optional[Sequence[int]] = None, cap: int = 4096, max_nms: int = 30000, max_wh: float = 7680.0,
+            out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, class_mask: Optional[torch.Tensor] = None):
+    """pred [B,A,no] fp32 -> (boxes [B,max_det,6], count int32 [B]).  count < 0 means -1-n candidates overflowed `cap`."""
+    _need_cuda(pred, "prediction")
+    L = _lib.lib(require_device=True)
+    pred = pred.contiguous().float()
+    B, A, no = pred.shape
+    dev = pred.device
+    cap = (int(cap) + 63) // 64 * 64
+    if out is None:
+        out = (torch.zeros((B, max_det, 6), dtype=torch.float32, device=dev), torch.zeros((B,), dtype=torch.int32, device=dev))
+    boxes, count = out
+    nbytes = L.yp_box_nms_workspace_bytes(B, A, no, cap)
+    ws = _workspace(dev, "nms", nbytes)
+    if class_mask is None:
+        class_mask = class_mask_tensor(classes, no - 5, dev)
+    p = YpNmsParams(float(conf_thres), float(iou_thres), int(bool(multi_label)), int(bool(agnostic)), int(max_det), int(max_nms),
+                    float(max_wh), class_mask.data_ptr() if class_mask is not None else None)
+    _lib.check(L.yp_box_nms(pred.data_ptr(), B, A, no, C.byref(p), cap, boxes.data_ptr(), count.data_ptr(), ws.data_ptr(), ws.numel(),
+                            _stream(dev)))
+    return boxes, count
+
+
+def heatmap(semi: torch.Tensor, layout: str = "nchw", variant: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """semi: [B,65,Hc,Wc] (layout 'nchw') or [B,Hc,Wc,C>=65] ('nhwc') fp32 logits -> heat [B,8Hc,8Wc]."""
+    _need_cuda(semi, "semi")
+    L = _lib.lib(require_device=True)
+    assert semi.dtype == torch.float32 and semi.dim() == 4
+    if layout == "nchw":
+        B, Cc, Hc, Wc = semi.shape
+        sB, sC, sH, sW = semi.stride()
+    else:
+        B, Hc, Wc, Cc = semi.shape
+        sB, sH, sW, sC = semi.stride()
+    assert Cc >= 65
+    if out is None:
+        out = torch.empty((B, Hc * 8, Wc * 8), dtype=torch.float32, device=semi.device)
+    _lib.check(L.yp_heatmap(semi.data_ptr(), B, Hc, Wc, sB, sC, sH, sW, int(variant), out.data_ptr(), _stream(semi.device)))
+    return out
+
+
+def keypoints(heat: torch.Tensor, conf_thresh: float, nms_dist: int, border: int = 4, boxes: Optional[torch.Tensor] = None,
+              box_count: Optional[torch.Tensor] = None, max_pts: int = 8192, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """heat [B,H,W] fp32 -> (pts [B,max_pts,3] (x,y,conf) confidence-descending, count int32 [B])."""
+    _need_cuda(heat, "heatmap")
+    L = _lib.lib(require_device=True)
+    heat = heat.contiguous()
+    B, H, W = heat.shape
+    dev = heat.device
+    if out is None:
+        out = (torch.zeros((B, max_pts, 3), dtype=torch.float32, device=dev), torch.zeros((B,), dtype=torch.int32, device=dev))
+    pts, count = out
+    nbytes = L.yp_keypoints_workspace_bytes(B, H, W, max_pts)
+    ws = _workspace(dev, "kp", nbytes)
+    bptr = cptr = None
+    box_ld = 0
+    if boxes is not None:
+        assert boxes.is_contiguous() and boxes.dim() == 3 and boxes.shape[2] == 6 and box_count is not None
+        bptr, cptr, box_ld = boxes.data_ptr(), box_count.data_ptr(), boxes.shape[1]
+    _lib.check(L.yp_keypoints(heat.data_ptr(), B, H, W, float(conf_thresh), int(nms_dist), int(border), bptr, cptr, box_ld,
+                              pts.data_ptr(), count.data_ptr(), max_pts, ws.data_ptr(), ws.numel(), _stream(dev)))
+    return pts, count
+
+
+def sample_desc(desc: torch.Tensor, pts: torch.Tensor, count: Optional[torch.Tensor], img_hw: Tuple[int, int], layout: str = "nchw",
+                D: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """desc [B,D,Hc,Wc] ('nchw') or [B,Hc,Wc,D] ('nhwc'); pts [B,N,3] -> [B,N,D] unit descriptors (rows >= count untouched)."""
+    _need_cuda(desc, "coarse_desc")
+    L = _lib.lib(require_device=True)
+    assert desc.dtype == torch.float32 and pts.dtype == torch.float32 and pts.is_contiguous()
+    if layout == "nchw":
+        B, Dd, Hc, Wc = desc.shape
+        sB, sD, sH, sW = desc.stride()
+    else:
+        B, Hc, Wc, Dd = desc.shape
+        sB, sH, sW, sD = desc.stride()
+    D = Dd if D is None else D
+    N = pts.shape[1]
+    if out is None:
+        out = torch.zeros((B, N, D), dtype=torch.float32, device=desc.device)
+    _lib.check(L.yp_sample_desc(desc.data_ptr(), B, D, Hc, Wc, sB, sD, sH, sW, int(img_hw[0]), int(img_hw[1]), pts.data_ptr(),
+                                count.data_ptr() if count is not None else None, N, out.data_ptr(), _stream(desc.device)))
+    return out
+
+
+def match_partial(d1: torch.Tensor, n1: Optional[torch.Tensor], d2: torch.Tensor, n2: Optional[torch.Tensor], col_off: int = 0,
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """d1 [N1,D], d2 [N2,D] fp32 rows -> (row_key int64 [N1], col_key int64 [N2]); keys = dist_bits<<32 | index."""
+    _need_cuda(d1, "desc1")
+    L = _lib.lib(require_device=True)
+    assert d1.is_contiguous() and d2.is_contiguous() and d1.dtype == torch.float32 and d2.dtype == torch.float32
+    N1, D = d1.shape
+    N2 = d2.shape[0]
+    dev = d1.device
+    if out is None:
+        out = (torch.empty((N1,), dtype=torch.int64, device=dev), torch.empty((N2,), dtype=torch.int64, device=dev))
+    rk, ck = out
+    _lib.check(L.yp_match_partial(d1.data_ptr(), n1.data_ptr() if n1 is not None else None, N1, d2.data_ptr(),
+                                  n2.data_ptr() if n2 is not None else None, N2, D, int(col_off), rk.data_ptr(), ck.data_ptr(), _stream(dev)))
+    return rk, ck
+
+
+def match_finalize(row_key: torch.Tensor, n1: Optional[torch.Tensor], col_key: torch.Tensor, nn_thresh: float,
+                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """-> (matches [N1,3] fp32 rows (i, j, dist), count int32 [1])."""
+    L = _lib.lib(require_device=True)
+    N1, N2 = row_key.shape[0], col_key.shape[0]
+    dev = row_key.device
+    if out is None:
+        out = (torch.zeros((N1, 3), dtype=torch.float32, device=dev), torch.zeros((1,), dtype=torch.int32, device=dev))
+    m, cnt = out
+    _lib.check(L.yp_match_finalize(row_key.data_ptr(), n1.data_ptr() if n1 is not None else None, N1, col_key.data_ptr(), N2,
+                                   float(nn_thresh), m.data_ptr(), cnt.data_ptr(), _stream(dev)))
+    return m, cnt
+
+
+def match_two_way(d1: torch.Tensor, n1, d2: torch.Tensor, n2, nn_thresh: float):
+    """Single-GPU two-way match of row-major descriptors."""
+    if nn_thresh < 0.0:
+        raise ValueError("'nn_thresh' should be non-negative")
+    rk, ck = match_partial(d1, n1, d2, n2)
+    return match_finalize(rk, n1, ck, nn_thresh)
