@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""Benchmark of the YOLOPoint hot path on B200 (contract: see the task statement / DESIGN.md section "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload s640|n480|m1280] [--precision fp32|bf16]
+
+A "step" is one pass of the whole per-frame hot path (uint8 frame -> network -> Detect decode -> box NMS -> heatmap ->
+keypoint NMS -> descriptor sampling -> two-way match with the previous frame) over one batch of synthetic frames.
+Default workload = BASELINE.json configs[1]: YOLOPoint-S, 640x640, batch 1 per GPU.  N > 1 (torchrun) shards
+independent frames over ranks with no data-path collective (weak scaling).
+
+One JSON line is printed by rank 0.  `value` = frames/s with the input frames resident in HBM; `e2e` = frames/s through
+FramePipeline.step_host (pinned host frame -> H2D -> pipeline -> D2H of keypoints/descriptors/boxes/matches);
+`roofline` describes the dominant kernel (tcgen05 conv) against the measured bf16 tensor peak; `cpu_baseline` is the CPU
+oracle (a port of the reference's PyTorch/numpy path) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    #  name: (version, H, W, frames per GPU per step)
+    "s640": ("s", 640, 640, 1),     # BASELINE.json configs[1]
+    "n480": ("n", 480, 640, 1),     # configs[0] geometry (the reference's CPU case) on the GPU
+    "m1280": ("m", 736, 1280, 4),   # configs[2]: 32 frames over 8 GPUs = 4 per GPU
+}
+NAMES = [str(i) for i in range(80)]
+CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398}   # SURVEY.md section 8a, per frame
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+def build_weights(version):
+    from yolopoint_b200 import Model
+    from yolopoint_b200.synth import perturb_state_dict
+    torch.manual_seed(0)
+    m = Model(names=NAMES, version=version)
+    sd = perturb_state_dict(m.state_dict(), 0, version)
+    m.load_state_dict(sd)
+    return m, sd
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, n): n.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", "")
+                 for n in dir(nv) if n.startswith("nvmlClocksThrottleReason") or n.startswith("nvmlClocksEventReason")}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) and n not in ("None", "All", "GpuIdle"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_fps(version, H, W, steps, warmup, sd=None):
+    """The reference's CPU path (oracle port: same torch-CPU convs / numpy post-processing) on all host threads."""
+    from oracle import yolopoint_oracle as O
+    from yolopoint_b200.synth import synthetic_frame
+    if sd is None:
+        _, sd = build_weights(version)
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = O.OracleNet(sd, version, 80)
+    frames = [synthetic_frame(H, W, s) for s in range(2)]
+    prev = None
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        pts, desc, boxes = O.process_frame(net, frames[i % 2])
+        if prev is not None and desc is not None:
+            O.nn_match_two_way(prev, desc, O.DEFAULT_CFG["nn_thresh"])
+        prev = desc
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return len(times) / sum(times), torch.get_num_threads(), float(np.median(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="s640", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    version, H, W, per_gpu = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, Wm = args.steps, max(args.warmup, 3)
+    config = {"workload": f"YOLOPoint-{version.upper()} {W}x{H} batch={per_gpu}/GPU full per-frame pipeline (net+decode+boxNMS+heatmap+kpNMS+desc+match)",
+              "frames_per_gpu_per_step": per_gpu, "precision": args.precision, "parallelism": f"frames sharded over {world} GPU(s), no collective"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = min(K, 30)
+        fps, cores, med = cpu_reference_fps(version, H, W, steps, min(Wm, 3))
+        line = {"impl": "reference", "metric": "frames/sec end-to-end (backbone+heads+NMS+match)", "value": fps, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(Wm, 3), "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": f"{steps} frames of the same workload, batch 1, oracle port of the reference CPU path"},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    from yolopoint_b200 import FramePipeline
+    from yolopoint_b200.synth import synthetic_frame
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    model, sd = build_weights(version)
+    model.precision = args.precision
+    model = model.to(dev).eval()
+    pipe = FramePipeline(model, per_gpu, H, W, max_pts=4096, nms_cap=4096)
+    plan = pipe.plan
+
+    # input pool larger than L2 (126 MB): every step reads a different frame batch from HBM
+    frame_bytes = per_gpu * H * W * 3
+    n_pool = max(8, int(160e6 // frame_bytes) + 1)
+    base = [synthetic_frame(H, W, s + 17 * rank) for s in range(4)]
+    pool = torch.empty((n_pool, per_gpu, H, W, 3), dtype=torch.uint8, device=dev)
+    for i in range(n_pool):
+        for b in range(per_gpu):
+            pool[i, b] = torch.from_numpy(np.roll(base[(i + b) % 4], shift=(3 * i) % W, axis=1)).to(dev)
+    config["l2"] = f"inputs larger than L2: pool of {n_pool} frame batches ({n_pool * frame_bytes / 1e6:.0f} MB) cycled, weights stay L2-resident"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(i):
+        plan.frame_in.copy_(pool[i % n_pool])
+        pipe.step_device(True)
+
+    for i in range(Wm):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(Wm + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    sampler.join()
+    launches = K * (pipe.n_launches())
+
+    # ---- dominant kernel: conv launches only, timed live with events on the launching stream
+    def net_only():
+        plan.run_net()
+    for _ in range(3):
+        plan.graphed("net_only", net_only)
+    torch.cuda.synchronize(dev)
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(20, min(K, 200))
+    n0.record()
+    for _ in range(reps):
+        plan.graphed("net_only", net_only)
+    n1.record()
+    torch.cuda.synchronize(dev)
+    net_ms = n0.elapsed_time(n1) / reps
+    n_conv = len(model.engine().net.conv_ops())
+    flops_step = CONV_GFLOP[args.workload] * 1e9 * per_gpu
+    achieved_tf = flops_step / (net_ms * 1e-3) / 1e12
+
+    # ---- end to end through the public host API
+    host_frames = [np.stack([np.roll(base[(i + b) % 4], (5 * i) % W, axis=1) for b in range(per_gpu)]) for i in range(8)]
+    pipe.reset_tracking()
+    for i in range(3):
+        pipe.step_host(host_frames[i % 8])
+    barrier()
+    t0 = time.perf_counter()
+    Ke = min(K, 100)
+    for i in range(Ke):
+        res = pipe.step_host(host_frames[i % 8])
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    kp_n, box_n, match_n = res[0][0].shape[1], res[0][2].shape[0], res[0][3].shape[1]
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    fps = K * per_gpu * world / (ms * 1e-3)
+    line = {"metric": "frames/sec end-to-end (backbone+heads+NMS+match)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor-core MMA, fp32 accumulate)" if args.precision == "fp32" else "bf16",
+            "data": "synthetic", "config": config, "clocks": sampler.summary(), "gpu_launches": launches,
+            "e2e": {"value": Ke * per_gpu * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
+                    "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": Ke},
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved_tf, "peak": peaks["tf"],
+                         "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained",
+                         "launches_per_step": n_conv, "avg_launch_us": net_ms * 1e3 / n_conv, "algorithmic_gflop_per_step": flops_step / 1e9,
+                         "note": "achieved = SURVEY 8a conv FLOPs per frame x frames per step / live CUDA-event time of the conv launches of one step"},
+            "detail": {"net_only_ms": net_ms, "keypoints": kp_n, "boxes": box_n, "matches": match_n}}
+    if not args.no_cpu_baseline and world == 1:
+        n = max(3, min(30, int(args.cpu_seconds / 0.3)))
+        cfps, cores, med = cpu_reference_fps(version, H, W, n, 2, sd)
+        line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"{n} frames of the same workload (batch 1), median {med * 1e3:.1f} ms/frame"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -152,7 +152,7 @@ struct ConvArgs {
   int ksize, stride;
   int n_taps, kb_per_tap, ck_bytes, ck_elems;
   int n_terms, in_planes;
-  int Nt, stages, stage_bytes, a_tile_bytes, b_tile_bytes, bar_off;
+  int Nt, stages, stage_bytes, a_tile_bytes, b_tile_bytes, bar_off, tx_bytes;
   uint32_t idesc, tmem_cols;
   const float* bias;
   int act, l2norm;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % a.stages, ph = (kb / a.stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), a.stage_bytes);
+        mbar_expect_tx(full_bar(s), a.tx_bytes);
         const int tap = kb / a.kb_per_tap, cb = kb - tap * a.kb_per_tap;
         int map = 0, dh = 0, dw = 0;
         if (a.ksize == 3) {
@@ -518,6 +518,8 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   a.a_tile_bytes = 128 * a.ck_bytes;
   a.b_tile_bytes = Nt * a.ck_bytes;
   a.stage_bytes = a.in_planes * (a.a_tile_bytes + a.b_tile_bytes);
+  // TMA counts the bytes of the box actually written: Ht*Wt (<= 128) rows of the A tile, Nt rows of the B tile
+  a.tx_bytes = a.in_planes * (a.Ht * a.Wt * a.ck_bytes + a.b_tile_bytes);
   const int num_kb = a.n_taps * a.kb_per_tap;
   const int budget = 200 * 1024;
   int stages = budget / a.stage_bytes;

@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing for the two places the hot path shards.  One process per GPU,
+``torch.distributed`` (NCCL over NVLink/NVSwitch on the box, gloo in the CPU tests).
+
+  * frames: independent units -> contiguous split over ranks, NO data-path collective (``shard_range``);
+  * descriptor match: desc1 replicated, desc2 sharded by columns.  Each rank computes packed keys
+    (float_bits(dist) << 32 | index) for its column shard; the exchange step is
+        all_reduce(MIN) over int64[N1] row keys   (global row winner, numpy first-index tie-break for free)
+      + all_gather of the int64[N2/G] column keys (each rank owns complete columns)
+    after which the mutual check + threshold run replicated (``yp_match_finalize``).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) of n units owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def reduce_match_keys(row_key: torch.Tensor, col_key_local: torch.Tensor, n2_total: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """row_key int64 [N1] (local winners), col_key_local int64 [n2_local] -> (global row keys, all column keys [n2_total]).
+
+    Keys are non-negative int64 (dist >= 0 => float bits < 2^31), so signed MIN orders them like the unsigned keys."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return row_key, col_key_local
+    rank = dist.get_rank(group)
+    dist.all_reduce(row_key, op=dist.ReduceOp.MIN, group=group)
+    sizes = [shard_range(n2_total, r, world) for r in range(world)]
+    pad = max(hi - lo for lo, hi in sizes)
+    send = torch.full((pad,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=col_key_local.device)
+    send[:col_key_local.numel()] = col_key_local
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    full = torch.cat([recv[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)])
+    return row_key, full
+
+
+def match_two_way_sharded(d1: torch.Tensor, d2_full_or_local: torch.Tensor, nn_thresh: float, n2_total: Optional[int] = None,
+                          local: bool = False, group=None):
+    """Two-way match with desc2 column-sharded over the ranks of `group`.
+
+    d1 [N1,D] replicated on every rank; d2 either the full [N2,D] (each rank slices its shard) or, with local=True,
+    this rank's shard.  Returns (matches [N1,3], count int32 [1]) replicated on every rank."""
+    from . import ops
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if local:
+        assert n2_total is not None
+        lo, hi = shard_range(n2_total, rank, world)
+        d2 = d2_full_or_local
+        assert d2.shape[0] == hi - lo
+    else:
+        n2_total = d2_full_or_local.shape[0]
+        lo, hi = shard_range(n2_total, rank, world)
+        d2 = d2_full_or_local[lo:hi].contiguous()
+    if hi > lo:
+        rk, ck = ops.match_partial(d1, None, d2, None, col_off=lo)
+    else:
+        rk = torch.full((d1.shape[0],), torch.iinfo(torch.int64).max, dtype=torch.int64, device=d1.device)
+        ck = torch.empty((0,), dtype=torch.int64, device=d1.device)
+    rk, ck_full = reduce_match_keys(rk, ck, n2_total, group)
+    return ops.match_finalize(rk, None, ck_full, nn_thresh)
