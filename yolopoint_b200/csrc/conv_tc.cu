@@ -46,7 +46,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (ok) break;
     if (clock64() - t0 > 4000000000LL) {  // ~2 s: a pipeline bug must fail loudly, not hang the GPU
-      printf("yolopoint_b200 conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      if ((threadIdx.x & 31) == 0)
+        printf("yolopoint_b200 conv_tc: mbarrier timeout (block %d,%d warp %d)\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5);
       __trap();
     }
   }

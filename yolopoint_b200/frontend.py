@@ -56,7 +56,7 @@ class FramePipeline:
         self.h_counts = torch.empty((3, B), dtype=torch.int32, pin_memory=True)
         self.d_counts = z(3, B, dt=torch.int32)
         self.h_pts, self.h_boxes, self.h_desc, self.h_matches = pin(self.pts[0]), pin(self.boxes), pin(self.descs[0]), pin(self.matches)
-        self.launch_count = None
+        self.graphs = {}   # graphs bake THIS pipeline's buffer addresses, so they are owned here, not by the shared plan
 
     # ---- device work ---------------------------------------------------------------------------
     def _enqueue(self, k: int, from_frame: bool = True):
@@ -99,7 +99,19 @@ class FramePipeline:
     def step_device(self, from_frame: bool = True):
         """Process the frame already resident in plan.frame_in / plan.x_in; flips the parity."""
         k = self.parity
-        self.plan.graphed(f"frame{k}{int(from_frame)}", lambda: self._enqueue(k, from_frame))
+        key = (k, bool(from_frame))
+        g = self.graphs.get(key)
+        if g is None:
+            self._enqueue(k, from_frame)            # eager first run: sets function attributes, fills caches
+            torch.cuda.synchronize(self.eng.device)
+            if self.eng.use_graphs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(k, from_frame)
+                self.graphs[key] = g
+                # the eager run already produced this frame's results; replaying is idempotent (same inputs)
+        else:
+            g.replay()
         self.parity = 1 - k
         return k
 
