@@ -46,6 +46,7 @@ SIGNATURES = {
     "yp_last_error": (C.c_char_p, []),
     "yp_check_device": (_i32, []),
     "yp_conv2d_nhwc_fwd": (_i32, [_PC, _vp]),
+    "yp_debug_conv_timeline": (_i32, [_vp]),
     "yp_sppf_pool": (_i32, [_PV, _vp]),
     "yp_nchw_to_s2d": (_i32, [_vp, _i32, _i32, _i32, _PV, _vp]),
     "yp_frame_to_s2d": (_i32, [_vp, _i32, _i32, _i32, _PV, _vp]),

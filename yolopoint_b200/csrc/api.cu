@@ -29,6 +29,7 @@ int sm_count() {
 
 int conv_tc_forward(const YpConvDesc& d, cudaStream_t st);
 int conv_simt_forward(const YpConvDesc& d, cudaStream_t st);
+void set_conv_timeline(long long* p);
 
 }  // namespace yp
 
@@ -52,4 +53,9 @@ extern "C" int yp_conv2d_nhwc_fwd(const YpConvDesc* d, void* stream) {
   if (d->algo == YP_ALGO_TCGEN05) return yp::conv_tc_forward(*d, st);
   yp::set_error("conv: unknown algo %d", d->algo);
   return YP_ERR_ARG;
+}
+
+extern "C" int yp_debug_conv_timeline(void* device_buf_512_i64) {
+  yp::set_conv_timeline(static_cast<long long*>(device_buf_512_i64));
+  return YP_OK;
 }

@@ -161,6 +161,7 @@ struct ConvArgs {
   long long res_pix, res_plane;
   int res_fmt;
   int n_out_maps, out_planes, out_row_bytes, staging_set_bytes;
+  long long* dbg;  // optional timeline buffer (yp_debug_conv_timeline); CTA (0,0) records clock64 stamps
 };
 
 constexpr int kThreads = 192;
@@ -188,6 +189,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int h0 = th * a.Ht, w0 = tw * a.Wt;
   const int n0 = blockIdx.y * a.Nt;
   const int num_kb = a.n_taps * a.kb_per_tap;
+  long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
+  auto stamp = [&](int slot) { if (dbg) dbg[slot] = clock64(); };
+  if (threadIdx.x == 0) stamp(0);
 
   // barriers + tmem slot + bias live after the pipeline/staging region
   const uint32_t bar_base = smem_base + a.bar_off;
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -235,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tma_load_5d(st + pl * a.a_tile_bytes, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, pl);
           tma_load_3d(st + a.in_planes * a.a_tile_bytes + pl * a.b_tile_bytes, &maps.w, full_bar(s), kb * a.ck_elems, n0, pl);
         }
+        if (kb < 96) stamp(8 + kb);
       }
     }
   } else if (warp == 1) {
@@ -246,6 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int s = kb % a.stages, ph = (kb / a.stages) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        if (kb < 96) stamp(104 + kb);
         const uint32_t sa = smem_base + s * a.stage_bytes;
         const uint32_t sb = sa + a.in_planes * a.a_tile_bytes;
         for (int t = 0; t < a.n_terms; ++t) {
@@ -260,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
         umma_commit(empty_bar(s));  // frees the smem stage when the MMAs above retire
+        if (kb < 96) stamp(200 + kb);
       }
       umma_commit(accum_bar);
     }
@@ -281,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (et0) stamp(2);
 
     auto finish = [&](float acc, int col) -> float {  // bias + activation + residual for column `col` of the tile
       float v = acc + bias_s[col];
@@ -310,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         v[i] = finish(v[i], c * CH + i);
         if (a.l2norm) v[i] = v[i] / inv_norm;
       }
+      if (et0 && c < 8) stamp(300 + 4 * c);
       // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t stg = smem_base + (c & 1) * a.staging_set_bytes;
@@ -340,25 +350,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et0 && c < 8) stamp(301 + 4 * c);
       if (et0) {
         for (int m = 0; m < a.n_out_maps; ++m)
           for (int pl = 0; pl < a.out_planes; ++pl)
             tma_store_5d(&maps.out[m], stg + pl * 128 * ROWB, n0 + c * CH, w0, h0, b, pl);
         tma_store_commit();
         tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
+        if (c < 8) stamp(302 + 4 * c);
       }
     }
-    if (et0) tma_store_wait_read<0>();
+    if (et0) { tma_store_wait_read<0>(); stamp(3); }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(4);
   if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (threadIdx.x == 32) stamp(5);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
+long long* g_timeline = nullptr;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 std::once_flag g_encode_once;
 
@@ -429,7 +444,9 @@ int launch(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t smem, cuda
 
 }  // namespace
 
-// Tile-shape selection shared with the Python planner via yp_conv_plan (debug / tests).
+void set_conv_timeline(long long* p) { g_timeline = p; }
+
+// Tile-shape selection (fewest 128-row tiles; ties -> widest patch).
 void pick_patch(int Ho, int Wo, int* Ht, int* Wt) {
   int best_tiles = 1 << 30, bw = 1, bh = 1;
   for (int wt = 1; wt <= Wo && wt <= 128; ++wt) {
@@ -536,6 +553,7 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   const size_t smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 2) + Nt * sizeof(float) + 16;
   YP_REQUIRE(smem <= 227 * 1024, YP_ERR_SHAPE, "conv: needs %zu bytes of shared memory", smem);
 
+  a.dbg = g_timeline;
   a.bias = d.bias;
   a.act = d.act;
   a.l2norm = (d.epilogue & YP_EPI_L2NORM) ? 1 : 0;
