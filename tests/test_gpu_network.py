@@ -1,7 +1,7 @@
 """GPU parity of the network (Model.forward through the engine) and of the whole-frame pipeline.
 
 Tolerances (fp32 / 3xTF32 mode): the oracle itself is fp32 PyTorch, whose own rounding noise after ~70 layers is
-~1e-5 relative; logits are compared at 2e-3 abs (|logit| up to ~50), unit descriptors at 1e-4 abs (north_star),
+~1e-5 relative; logits are compared at 1e-4 of the tensor's max magnitude, unit descriptors at 1e-4 abs (north_star),
 decoded boxes/scores at 1e-4 relative + 1e-3 abs.  Indices (keypoints, NMS survivors, matches) are compared
 bit-exact by feeding the SAME network outputs to the kernels and to the oracle."""
 import numpy as np
@@ -29,13 +29,15 @@ def build(ver, precision="fp32"):
     return _cache[key]
 
 
-def check_outputs(out, ref, tag, atol_logit=2e-3, atol_desc=1e-4):
+def check_outputs(out, ref, tag, atol_logit=1e-4, atol_desc=1e-4):
     semi, desc, (pred, raw) = out["semi"].cpu(), out["desc"].cpu(), out["objects"]
     rs, rd, (rp, rr) = ref["semi"], ref["desc"], ref["objects"]
     assert semi.shape == rs.shape and desc.shape == rd.shape and pred.shape == rp.shape
-    e = dict(semi=float((semi - rs).abs().max()), desc=float((desc - rd).abs().max()),
+    # logits are compared relative to the tensor's scale (synthetic weights give |logit| up to ~10^2)
+    e = dict(semi=float((semi - rs).abs().max()) / max(1.0, float(rs.abs().max())), desc=float((desc - rd).abs().max()),
              pred=float(((pred.cpu() - rp).abs() / (1.0 + rp.abs())).max()),
-             raw=max(float((a.cpu() - b).abs().max()) for a, b in zip(raw, rr)))
+             raw=max(float((a.cpu() - b).abs().max()) / max(1.0, float(b.abs().max())) for a, b in zip(raw, rr)),
+             scale_semi=float(rs.abs().max()), scale_raw=max(float(b.abs().max()) for b in rr))
     print(tag, e)
     assert e["semi"] < atol_logit and e["raw"] < atol_logit, (tag, e)
     assert e["desc"] < atol_desc, (tag, e)

@@ -150,6 +150,6 @@ def test_match_full_size_properties():
     assert int(cnt.item()) == N
     inv = torch.empty_like(perm); inv[perm] = torch.arange(N, device="cuda")
     assert torch.equal(m[:, 0].long(), torch.arange(N, device="cuda")) and torch.equal(m[:, 1].long(), inv)
-    assert float(m[:, 2].max()) < 1e-3
+    assert float(m[:, 2].max()) < 3e-3   # sqrt(2-2*d) with d = 1 - O(1e-7): self-distance noise is O(1e-3)
     m2, cnt2 = ops.match_two_way(d2, None, d1, None, 0.7)
     assert int(cnt2.item()) == N and torch.equal(m2[:, 1].long(), perm)

@@ -109,7 +109,8 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         : "memory");
   }
 }
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives row (lane_base + i)
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives row (lane_base + i).  Asynchronous:
+// the registers are valid only after tmem_ld_wait().
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -118,10 +119,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory operand descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64).
@@ -152,14 +153,15 @@ struct ConvArgs {
   int tiles_w, tiles_h, Ht, Wt, Ho, Wo;
   int ksize, stride;
   int n_taps, kb_per_tap, ck_bytes, ck_elems;
-  int n_terms, in_planes;
-  int Nt, stages, stage_bytes, a_tile_bytes, b_tile_bytes, bar_off, tx_bytes;
+  int in_planes, a_split;          // a_split: 1 = both planes of A arrive with one TMA (box plane dim 2)
+  int a_plane_off;                 // smem byte offset of the lo plane inside the A region
+  int Nt, stages, stage_bytes, a_region_bytes, bar_off, tx_bytes;
+  int n_small, n_main;             // TMEM accumulators: cross terms / main terms (see kernel comment)
   uint32_t idesc, tmem_cols;
   const float* bias;
   int act, l2norm;
   const void* res_base;
   long long res_pix, res_plane;
-  int res_fmt;
   int n_out_maps, out_planes, out_row_bytes, staging_set_bytes;
   long long* dbg;  // optional timeline buffer (yp_debug_conv_timeline); CTA (0,0) records clock64 stamps
 };
@@ -172,8 +174,26 @@ struct OutT { using type = float; };
 template <>
 struct OutT<YP_FMT_BF16> { using type = __nv_bfloat16; };
 
+// branch-free SiLU with ~1 ulp sigmoid: ex2.approx (rel err 2^-22) + rcp.approx refined by one Newton step
+__device__ __forceinline__ float silu_fast(float v) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * v));
+  const float d = 1.0f + t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  r = fmaf(r, fmaf(-d, r, 1.0f), r);
+  return v * r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel.  UNITS = 16-column TMEM units per staging row chunk (chunk_elems = 16 * UNITS).
+//
+// Accumulators.  A tcgen05.mma that accumulates into the tile written by the previous MMA waits for it
+// (~140 cycles measured), far longer than the math of one small MMA, and the tensor core adds into an fp32
+// accumulator with truncation, so the error grows linearly with the number of MMAs chained on one accumulator.
+// Both are cured by spreading the MMAs of a tile over several independent TMEM accumulators that the epilogue
+// sums with round-to-nearest adds: `n_main` accumulators take the main products round-robin; in 3xTF32 mode
+// `n_small` (<= 2) more take the two cross terms (A_lo*W_hi, A_hi*W_lo), whose partial sums are ~2^-11 of the
+// result so that their truncation error is negligible.
 // ---------------------------------------------------------------------------------------------
 template <int OUT_FMT, int UNITS, bool kTf32>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
@@ -224,11 +244,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      int s = 0, ph = 0, tap = 0, cb = 0;
+      const uint32_t b_off = a.a_region_bytes;
+      const uint32_t b_plane = a.Nt * a.ck_bytes;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % a.stages, ph = (kb / a.stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_expect_tx(full_bar(s), a.tx_bytes);
-        const int tap = kb / a.kb_per_tap, cb = kb - tap * a.kb_per_tap;
         int map = 0, dh = 0, dw = 0;
         if (a.ksize == 3) {
           const int kh = tap / 3, kw = tap - kh * 3;
@@ -236,38 +257,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           else { map = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1); dh = (kh == 0) ? -1 : 0; dw = (kw == 0) ? -1 : 0; }
         }
         const uint32_t st = smem_base + s * a.stage_bytes;
-        for (int pl = 0; pl < a.in_planes; ++pl) {
-          tma_load_5d(st + pl * a.a_tile_bytes, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, pl);
-          tma_load_3d(st + a.in_planes * a.a_tile_bytes + pl * a.b_tile_bytes, &maps.w, full_bar(s), kb * a.ck_elems, n0, pl);
-        }
+        tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
+        if (a.in_planes == 2 && !a.a_split) tma_load_5d(st + a.a_plane_off, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 1);
+        tma_load_3d(st + b_off, &maps.w, full_bar(s), kb * a.ck_elems, n0, 0);   // box covers both weight planes
+        (void)b_plane;
         if (kb < 96) stamp(8 + kb);
+        if (++cb == a.kb_per_tap) { cb = 0; ++tap; }
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const int ksteps = a.ck_bytes / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
-      uint32_t accum = 0;
+      const uint32_t b_plane = a.Nt * a.ck_bytes;
+      uint32_t used = 0;                   // bit j set = accumulator j already holds a partial sum
+      int s = 0, ph = 0, next_main = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % a.stages, ph = (kb / a.stages) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         if (kb < 96) stamp(104 + kb);
         const uint32_t sa = smem_base + s * a.stage_bytes;
-        const uint32_t sb = sa + a.in_planes * a.a_tile_bytes;
-        for (int t = 0; t < a.n_terms; ++t) {
-          // fp32x2: small cross terms first (A_lo*W_hi, A_hi*W_lo), main term (A_hi*W_hi) last
-          const int pa = (a.n_terms == 3 && t == 0) ? 1 : 0;
-          const int pb = (a.n_terms == 3 && t == 1) ? 1 : 0;
-          const uint64_t ad = make_smem_desc(sa + pa * a.a_tile_bytes, a.ck_bytes);
-          const uint64_t bd = make_smem_desc(sb + pb * a.b_tile_bytes, a.ck_bytes);
-          for (int k = 0; k < ksteps; ++k) {
-            umma<kTf32>(tmem_base, ad + static_cast<uint64_t>(2 * k), bd + static_cast<uint64_t>(2 * k), a.idesc, accum);
-            accum = 1;
+        const uint32_t sb = sa + a.a_region_bytes;
+        const uint64_t a_hi = make_smem_desc(sa, a.ck_bytes), a_lo = make_smem_desc(sa + a.a_plane_off, a.ck_bytes);
+        const uint64_t w_hi = make_smem_desc(sb, a.ck_bytes), w_lo = make_smem_desc(sb + b_plane, a.ck_bytes);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ko = static_cast<uint64_t>(2 * k);
+          if (kTf32) {
+            const int c0 = a.n_main, c1 = a.n_main + a.n_small - 1;   // cross-term accumulators (may coincide)
+            umma<kTf32>(tmem_base + c0 * a.Nt, a_lo + ko, w_hi + ko, a.idesc, (used >> c0) & 1u); used |= 1u << c0;
+            umma<kTf32>(tmem_base + c1 * a.Nt, a_hi + ko, w_lo + ko, a.idesc, (used >> c1) & 1u); used |= 1u << c1;
           }
+          const int m = next_main;
+          umma<kTf32>(tmem_base + m * a.Nt, a_hi + ko, w_hi + ko, a.idesc, (used >> m) & 1u); used |= 1u << m;
+          if (++next_main == a.n_main) next_main = 0;
         }
         umma_commit(empty_bar(s));  // frees the smem stage when the MMAs above retire
         if (kb < 96) stamp(200 + kb);
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
       umma_commit(accum_bar);
     }
@@ -285,40 +312,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool et0 = (threadIdx.x == 64);
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int n_chunks = a.Nt / CH;
-    const long long res_off = a.res_base ? ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0 : 0;
+    const int n_acc = a.n_main + a.n_small;
+    const bool has_res = a.res_base != nullptr && valid;
+    const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
 
+    // residual of chunk `c` for this thread's pixel, planes summed (residual format == output format family)
+    auto load_res = [&](int c, float* r) {
+      if (!has_res) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) r[i] = 0.0f;
+        return;
+      }
+      if (OUT_FMT == YP_FMT_BF16) {
+        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_base) + res_off + c * CH);
+#pragma unroll
+        for (int j = 0; j < CH / 8; ++j) {
+          const uint4 u = __ldg(p + j);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); r[j * 8 + 2 * e] = f.x; r[j * 8 + 2 * e + 1] = f.y; }
+        }
+      } else {
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + c * CH);
+        const float4* pl = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + a.res_plane + c * CH);
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) {
+          const float4 hi = __ldg(p + j);
+          float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (OUT_FMT == YP_FMT_F32X2) lo = __ldg(pl + j);
+          r[j * 4] = hi.x + lo.x; r[j * 4 + 1] = hi.y + lo.y; r[j * 4 + 2] = hi.z + lo.z; r[j * 4 + 3] = hi.w + lo.w;
+        }
+      }
+    };
+    // accumulator columns [col, col+16) of this thread's row, summed over all TMEM accumulators (main first)
+    auto load_acc16 = [&](int col, float* v) {
+      float t[4][16];
+      tmem_ld16(taddr_row + col, v);
+      int j = 1;
+      for (; j + 2 < n_acc; j += 3) {   // batches of three loads in flight
+        tmem_ld16(taddr_row + (j + 0) * a.Nt + col, t[0]);
+        tmem_ld16(taddr_row + (j + 1) * a.Nt + col, t[1]);
+        tmem_ld16(taddr_row + (j + 2) * a.Nt + col, t[2]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = ((v[i] + t[0][i]) + t[1][i]) + t[2][i];
+      }
+      for (; j < n_acc; ++j) {
+        tmem_ld16(taddr_row + j * a.Nt + col, t[3]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[3][i];
+      }
+      tmem_ld_wait();
+    };
+    auto finish = [&](float acc, int col, float res) -> float {
+      float v = acc + bias_s[col];
+      const float sv = silu_fast(v);
+      v = a.act == YP_ACT_SILU ? sv : v;
+      return v + res;
+    };
+
+    float res[CH];
+    load_res(0, res);               // in flight while the main loop runs
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (et0) stamp(2);
 
-    auto finish = [&](float acc, int col) -> float {  // bias + activation + residual for column `col` of the tile
-      float v = acc + bias_s[col];
-      if (a.act == YP_ACT_SILU) v = (OUT_FMT == YP_FMT_BF16 && !kTf32) ? __fdividef(v, 1.0f + __expf(-v)) : silu_accurate(v);
-      if (a.res_base && valid) v += load_act(a.res_base, a.res_fmt, a.res_plane, res_off + col);
-      return v;
-    };
-
     float inv_norm = 1.0f;
-    if (a.l2norm) {
+    if (a.l2norm) {                 // desc / ||desc||_2 over all Nt channels of the pixel (single N tile)
       float ss = 0.0f;
       for (int u = 0; u < a.Nt / 16; ++u) {
         float v[16];
-        tmem_ld16(taddr_row + u * 16, v);
+        load_acc16(u * 16, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const float f = finish(v[i], u * 16 + i); ss += f * f; }
+        for (int i = 0; i < 16; ++i) { const float f = finish(v[i], u * 16 + i, 0.0f); ss = fmaf(f, f, ss); }
       }
-      inv_norm = sqrtf(ss);  // divide below, as the reference does (desc.div(norm), no eps)
+      inv_norm = 1.0f / sqrtf(ss);
     }
 
     for (int c = 0; c < n_chunks; ++c) {
       float v[CH];
 #pragma unroll
-      for (int u = 0; u < UNITS; ++u) tmem_ld16(taddr_row + c * CH + u * 16, v + u * 16);
+      for (int u = 0; u < UNITS; ++u) load_acc16(c * CH + u * 16, v + u * 16);
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        v[i] = finish(v[i], c * CH + i);
-        if (a.l2norm) v[i] = v[i] / inv_norm;
-      }
+      for (int i = 0; i < CH; ++i) v[i] = finish(v[i], c * CH + i, res[i]) * inv_norm;
+      if (c + 1 < n_chunks) load_res(c + 1, res);   // overlaps the staging / store of this chunk
       if (et0 && c < 8) stamp(300 + 4 * c);
       // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -394,7 +472,7 @@ CUtensorMapSwizzle swizzle_for(int row_bytes) {
 
 // 5-D map over (C, W, H, B, plane) of an NHWC view; `sub` = spatial subsampling (2 -> parity view ph,pw).
 int encode_view(CUtensorMap* tm, const YpView& v, int sub, int ph, int pw, int Wfull, int Hfull, int box_c, int box_w,
-                int box_h) {
+                int box_h, int box_p = 1) {
   const int es = fmt_esize(v.format);
   const int planes = fmt_planes(v.format);
   const CUtensorMapDataType dt = v.format == YP_FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -403,7 +481,7 @@ int encode_view(CUtensorMap* tm, const YpView& v, int sub, int ph, int pw, int W
   const int64_t img = static_cast<int64_t>(Hfull) * Wfull * v.pix_stride;
   cuuint64_t strides[4] = {(cuuint64_t)(v.pix_stride * sub * es), (cuuint64_t)(v.pix_stride * Wfull * sub * es), (cuuint64_t)(img * es),
                            (cuuint64_t)((planes > 1 ? v.plane_stride : img * v.B) * es)};
-  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, (cuuint32_t)box_p};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   YP_REQUIRE(aligned16(base), YP_ERR_ALIGN, "conv: view base %p not 16-byte aligned", (void*)base);
   for (int i = 0; i < 4; ++i) YP_REQUIRE(strides[i] % 16 == 0, YP_ERR_ALIGN, "conv: view stride %d (%llu B) not a multiple of 16", i, (unsigned long long)strides[i]);
@@ -420,7 +498,7 @@ int encode_weight(CUtensorMap* tm, const void* w, int fmt, int Ktot, int cout, i
   const CUtensorMapDataType dt = fmt == YP_FMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   cuuint64_t dims[3] = {(cuuint64_t)Ktot, (cuuint64_t)cout, (cuuint64_t)planes};
   cuuint64_t strides[2] = {(cuuint64_t)Ktot * es, (cuuint64_t)Ktot * cout * es};
-  cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_n, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_n, (cuuint32_t)planes};  // one TMA brings both weight planes
   cuuint32_t estr[3] = {1, 1, 1};
   YP_REQUIRE(aligned16(w) && strides[0] % 16 == 0, YP_ERR_ALIGN, "conv: weight pointer/row stride not 16-byte aligned");
   CUresult r = get_encode()(tm, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -454,7 +532,8 @@ void pick_patch(int Ho, int Wo, int* Ht, int* Wt) {
     if (ht > Ho) ht = Ho;
     if (ht < 1) continue;
     const int tiles = ceil_div(Wo, wt) * ceil_div(Ho, ht);
-    if (tiles < best_tiles || (tiles == best_tiles && wt > bw)) { best_tiles = tiles; bw = wt; bh = ht; }
+    const bool al = (wt * ht) % 8 == 0, bal = (bw * bh) % 8 == 0;  // 8-row aligned patches let one TMA bring both operand planes
+    if (tiles < best_tiles || (tiles == best_tiles && ((al && !bal) || (al == bal && wt > bw)))) { best_tiles = tiles; bw = wt; bh = ht; }
   }
   *Ht = bh; *Wt = bw;
 }
@@ -485,8 +564,12 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   a.ck_bytes = cin_bytes % 128 == 0 ? 128 : (cin_bytes % 64 == 0 ? 64 : 32);
   a.ck_elems = a.ck_bytes / es;
   a.kb_per_tap = in.C / a.ck_elems;
-  a.n_terms = tf32 ? 3 : 1;
   a.in_planes = tf32 ? 2 : 1;
+  const int rows = a.Ht * a.Wt;
+  a.a_split = (a.in_planes == 2 && rows % 8 == 0) ? 1 : 0;   // lo plane lands right behind the hi plane, swizzle-aligned
+  a.a_plane_off = ((rows + 7) & ~7) * a.ck_bytes;
+  const int num_kb = a.n_taps * a.kb_per_tap;
+  const int main_mmas = num_kb * (a.ck_bytes / 32);
 
   // ---- output format / staging geometry
   const int out_fmt = d.out[0].format;
@@ -505,7 +588,8 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   YP_REQUIRE(chunk_elems % 16 == 0, YP_ERR_SHAPE, "conv: Cout=%d gives a %d-element store chunk (<16)", d.cout, chunk_elems);
   a.staging_set_bytes = a.out_planes * 128 * a.out_row_bytes;
 
-  // ---- N tile: largest divisor of Cout (multiple of chunk, <= 256) that still yields >= #SM CTAs
+  // ---- N tile.  Fewer than #SM CTAs -> prefer small tiles (latency); long K chains in 3xTF32 mode -> Nt <= 64 so
+  // that at least six main accumulators fit into the 512 TMEM columns (accuracy + MMA pipelining).
   const int m_tiles = a.tiles_w * a.tiles_h * in.B;
   const int nsm = sm_count();
   int Nt = 0;
@@ -513,7 +597,8 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
     YP_REQUIRE(d.cout <= 256, YP_ERR_SHAPE, "conv: L2-norm epilogue needs Cout <= 256 (got %d)", d.cout);
     Nt = d.cout;
   } else {
-    const int nmax = tf32 ? 128 : 256;
+    int nmax = tf32 ? 128 : 256;
+    if (tf32 && main_mmas > 96) nmax = 64;
     int smallest = 0;
     for (int n = nmax; n >= chunk_elems; n -= 16) {
       if (d.cout % n || n % chunk_elems) continue;
@@ -522,23 +607,34 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
       if (n <= 32 && smallest) break;
     }
     if (Nt == 0) Nt = smallest;
+    if (Nt == 0) {  // no divisor below the cap (e.g. Cout = 80 or 96 with a 64 cap): fall back to the unrestricted search
+      for (int n = tf32 ? 128 : 256; n >= chunk_elems && Nt == 0; n -= 16)
+        if (d.cout % n == 0 && n % chunk_elems == 0) Nt = n;
+    }
   }
   YP_REQUIRE(Nt >= 16 && Nt % 16 == 0 && Nt <= 256, YP_ERR_SHAPE, "conv: no valid N tile for Cout=%d", d.cout);
   a.Nt = Nt;
+  a.n_small = tf32 ? 2 : 0;
+  int n_main = 512 / Nt - a.n_small;
+  if (n_main < 1) { a.n_small = tf32 ? 1 : 0; n_main = 512 / Nt - a.n_small; }
+  const int main_cap = tf32 ? 6 : 4;
+  if (n_main > main_cap) n_main = main_cap;
+  if (n_main > main_mmas) n_main = main_mmas;
+  YP_REQUIRE(n_main >= 1, YP_ERR_SHAPE, "conv: Nt=%d leaves no TMEM accumulator", Nt);
+  a.n_main = n_main;
   a.tmem_cols = 32;
-  while ((int)a.tmem_cols < Nt) a.tmem_cols <<= 1;
+  while ((int)a.tmem_cols < (a.n_main + a.n_small) * Nt) a.tmem_cols <<= 1;
   // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format [7,10)/[10,13)
   // (TF32=2, BF16=1), K-major both, N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t ab = tf32 ? 2u : 1u;
   a.idesc = (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(Nt >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 
   // ---- pipeline geometry
-  a.a_tile_bytes = 128 * a.ck_bytes;
-  a.b_tile_bytes = Nt * a.ck_bytes;
-  a.stage_bytes = a.in_planes * (a.a_tile_bytes + a.b_tile_bytes);
-  // TMA counts the bytes of the box actually written: Ht*Wt (<= 128) rows of the A tile, Nt rows of the B tile
-  a.tx_bytes = a.in_planes * (a.Ht * a.Wt * a.ck_bytes + a.b_tile_bytes);
-  const int num_kb = a.n_taps * a.kb_per_tap;
+  a.a_region_bytes = a.in_planes * 128 * a.ck_bytes;
+  const int b_region_bytes = a.in_planes * Nt * a.ck_bytes;
+  a.stage_bytes = a.a_region_bytes + b_region_bytes;
+  // TMA counts the bytes of the boxes actually written: Ht*Wt (<= 128) rows per A plane, Nt rows per B plane
+  a.tx_bytes = a.in_planes * (rows * a.ck_bytes + Nt * a.ck_bytes);
   const int budget = 200 * 1024;
   int stages = budget / a.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -559,17 +655,19 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   a.l2norm = (d.epilogue & YP_EPI_L2NORM) ? 1 : 0;
   if (d.residual.base) {
     YP_REQUIRE(d.residual.C == d.cout && d.residual.H == Ho && d.residual.W == Wo && d.residual.B == in.B, YP_ERR_SHAPE, "conv: residual geometry mismatch");
-    a.res_base = d.residual.base; a.res_pix = d.residual.pix_stride; a.res_plane = d.residual.plane_stride; a.res_fmt = d.residual.format;
+    YP_REQUIRE(d.residual.format == out_fmt, YP_ERR_SHAPE, "conv: residual format %d must equal the output format %d", d.residual.format, out_fmt);
+    YP_REQUIRE(aligned16(d.residual.base) && d.residual.pix_stride % 8 == 0 && d.residual.plane_stride % 4 == 0, YP_ERR_ALIGN, "conv: residual view not 16-byte aligned");
+    a.res_base = d.residual.base; a.res_pix = d.residual.pix_stride; a.res_plane = d.residual.plane_stride;
   }
 
   // ---- tensor maps
   int rc;
   if (d.stride == 1) {
-    if ((rc = encode_view(&maps.in[0], in, 1, 0, 0, in.W, in.H, a.ck_elems, a.Wt, a.Ht)) != YP_OK) return rc;
+    if ((rc = encode_view(&maps.in[0], in, 1, 0, 0, in.W, in.H, a.ck_elems, a.Wt, a.Ht, a.a_split ? 2 : 1)) != YP_OK) return rc;
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
-        if ((rc = encode_view(&maps.in[ph * 2 + pw], in, 2, ph, pw, in.W, in.H, a.ck_elems, a.Wt, a.Ht)) != YP_OK) return rc;
+        if ((rc = encode_view(&maps.in[ph * 2 + pw], in, 2, ph, pw, in.W, in.H, a.ck_elems, a.Wt, a.Ht, a.a_split ? 2 : 1)) != YP_OK) return rc;
   }
   if ((rc = encode_weight(&maps.w, d.weight, in_fmt, a.n_taps * in.C, d.cout, a.ck_elems, Nt)) != YP_OK) return rc;
   int nm = 0;

@@ -61,49 +61,119 @@ struct KpWs {
   unsigned long long* list;    // [B][max_pts]  (ordered_conf << 32) | raster index
 };
 
-__device__ __forceinline__ bool higher(float cq, int q, float cp, int p) { return cq > cp || (cq == cp && q < p); }
 
-__global__ void kp_nms_kernel(const float* __restrict__ heat, int B, int H, int W, float thr, int r, KpWs ws) {
+__device__ __forceinline__ unsigned int ordered_bits(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unordered_bits(unsigned int o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// Tile-local formulation.  Each CTA owns 32x32-pixel tiles; per global round it loads the tile plus an r-wide halo of
+// states into shared memory, sorts the tile's undecided candidates by priority (rank sort) and lets one warp resolve
+// them IN PRIORITY ORDER -- inside a tile that is the reference's sequential scan, so long dependency chains cost
+// shared-memory latency, not grid barriers.  Only decisions that depend on a still-undecided halo candidate of a
+// neighbouring tile are deferred to the next round (cooperative grid barrier in between).
+constexpr int KT = 32;       // tile edge
+constexpr int KR_MAX = 16;   // largest supported nms_dist
+
+__global__ void __launch_bounds__(256) kp_nms_kernel(const float* __restrict__ heat, int B, int H, int W, float thr, int r, KpWs ws) {
   cg::grid_group grid = cg::this_grid();
-  const int64_t total = static_cast<int64_t>(B) * H * W;
-  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  volatile unsigned char* state = ws.state;
-  for (int64_t p = tid; p < total; p += nthreads) state[p] = heat[p] >= thr ? 1 : 0;
-  if (tid == 0) { ws.remaining[0] = 0; ws.remaining[1] = 0; ws.remaining[2] = 0; }
-  for (int64_t i = tid; i < B; i += nthreads) ws.n_list[i] = 0;
-  __threadfence();
-  grid.sync();
+  extern __shared__ unsigned char kp_smem[];
+  const int RW = KT + 2 * r, RN = RW * RW;
+  float* sheat = reinterpret_cast<float*>(kp_smem);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(kp_smem + ((RN * 4 + 7) & ~7));
+  unsigned short* cand = reinterpret_cast<unsigned short*>(keys + KT * KT);
+  unsigned short* sorted = cand + KT * KT;
+  unsigned char* sstate = reinterpret_cast<unsigned char*>(sorted + KT * KT);
+  __shared__ int n_list;
+  const int tiles_x = (W + KT - 1) / KT, tiles_y = (H + KT - 1) / KT;
+  const int T = B * tiles_x * tiles_y;
   const int64_t HW = static_cast<int64_t>(H) * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int win = 2 * r + 1;
+
   for (int round = 0;; ++round) {
     unsigned int undecided = 0;
-    for (int64_t p = tid; p < total; p += nthreads) {
-      if (state[p] != 1) continue;
-      const int b = static_cast<int>(p / HW);
-      const int pp = static_cast<int>(p - b * HW);
-      const int y = pp / W, x = pp - y * W;
-      const float cp = heat[p];
-      const unsigned char* sb = ws.state + b * HW;
+    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+      const int b = t / (tiles_x * tiles_y);
+      const int tr = t - b * tiles_x * tiles_y;
+      const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+      const int y0 = ty * KT - r, x0 = tx * KT - r;
       const float* hb = heat + b * HW;
-      bool any_kept = false, any_pending = false;
-      const int y0 = max(0, y - r), y1 = min(H - 1, y + r), x0 = max(0, x - r), x1 = min(W - 1, x + r);
-      for (int yy = y0; yy <= y1 && !any_kept; ++yy)
-        for (int xx = x0; xx <= x1; ++xx) {
-          const int q = yy * W + xx;
-          const unsigned char sq = __ldcg(sb + q);
-          if (sq == 0 || sq == 3 || q == pp) continue;
-          if (!higher(hb[q], q, cp, pp)) continue;
-          if (sq == 2) { any_kept = true; break; }
-          any_pending = true;
+      unsigned char* sb = ws.state + b * HW;
+      for (int c = threadIdx.x; c < RN; c += blockDim.x) {
+        const int ly = c / RW, lx = c - ly * RW;
+        const int gy = y0 + ly, gx = x0 + lx;
+        const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        const float h = inside ? hb[gy * W + gx] : -INFINITY;
+        sheat[c] = h;
+        unsigned char st = 0;
+        if (inside) st = round == 0 ? (h >= thr ? 1 : 0) : __ldcg(sb + gy * W + gx);
+        sstate[c] = st;
+      }
+      if (threadIdx.x == 0) n_list = 0;
+      __syncthreads();
+      for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
+        const int ly = c / KT + r, lx = c % KT + r;
+        const int cell = ly * RW + lx;
+        if (sstate[cell] == 1) {
+          const int slot = atomicAdd(&n_list, 1);
+          const unsigned int raster = static_cast<unsigned int>((y0 + ly) * W + (x0 + lx));
+          keys[slot] = (static_cast<unsigned long long>(ordered_bits(sheat[cell])) << 32) | (0xffffffffu - raster);
+          cand[slot] = static_cast<unsigned short>(cell);
         }
-      if (any_kept) state[p] = 3;
-      else if (!any_pending) state[p] = 2;
-      else ++undecided;
+      }
+      __syncthreads();
+      const int n = n_list;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {  // rank sort, descending priority (keys are unique)
+        const unsigned long long ki = keys[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += keys[j] > ki ? 1 : 0;
+        sorted[rank] = cand[i];
+      }
+      __syncthreads();
+      if (warp == 0) {
+        for (int i = 0; i < n; ++i) {
+          const int p = sorted[i];
+          const int py = p / RW, px = p - py * RW;
+          const float hp = sheat[p];
+          const int gp = (y0 + py) * W + (x0 + px);
+          bool kept = false, pend = false;
+          for (int idx = lane; idx < win * win; idx += 32) {
+            const int dy = idx / win - r, dx = idx % win - r;
+            const int q = (py + dy) * RW + (px + dx);
+            const unsigned char sq = sstate[q];
+            if (sq == 2) kept = true;
+            else if (sq == 1 && q != p) {
+              const float hq = sheat[q];
+              const int gq = (y0 + py + dy) * W + (x0 + px + dx);
+              if (hq > hp || (hq == hp && gq < gp)) pend = true;
+            }
+          }
+          kept = __any_sync(0xffffffffu, kept);
+          pend = __any_sync(0xffffffffu, pend);
+          if (lane == 0) sstate[p] = kept ? 3 : (pend ? 1 : 2);
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
+        const int ly = c / KT + r, lx = c % KT + r;
+        const int gy = y0 + ly, gx = x0 + lx;
+        if (gy < H && gx < W) {
+          const unsigned char st = sstate[ly * RW + lx];
+          sb[gy * W + gx] = st;
+          undecided += st == 1 ? 1u : 0u;
+        }
+      }
+      __syncthreads();
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) undecided += __shfl_xor_sync(0xffffffffu, undecided, s);
-    if ((threadIdx.x & 31) == 0 && undecided) atomicAdd(&ws.remaining[round % 3], undecided);
-    if (tid == 0) ws.remaining[(round + 1) % 3] = 0;  // next round's slot: last read after barrier round-2, i.e. before barrier round-1
+    for (int sft = 16; sft > 0; sft >>= 1) undecided += __shfl_xor_sync(0xffffffffu, undecided, sft);
+    if (lane == 0 && undecided) atomicAdd(&ws.remaining[round % 3], undecided);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.remaining[(round + 1) % 3] = 0;  // next round's slot (last read before the previous barrier)
     __threadfence();
     grid.sync();
     if (*(volatile unsigned int*)&ws.remaining[round % 3] == 0) break;
@@ -114,14 +184,6 @@ __global__ void kp_nms_kernel(const float* __restrict__ heat, int B, int H, int 
 __device__ __forceinline__ void py_slice(int a, int b, int L, int* s, int* e) {
   *s = a < 0 ? max(a + L, 0) : min(a, L);
   *e = b < 0 ? max(b + L, 0) : min(b, L);
-}
-
-__device__ __forceinline__ unsigned int ordered_bits(float f) {
-  const unsigned int u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float unordered_bits(unsigned int o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
 // survivors -> border filter -> box filter -> unordered list of packed keys
@@ -233,18 +295,26 @@ extern "C" int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, 
   YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "keypoints: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  static thread_local int coop_blocks = 0;
-  if (coop_blocks == 0) {
+  YP_REQUIRE(nms_dist <= yp::KR_MAX, YP_ERR_SHAPE, "keypoints: nms_dist=%d exceeds the supported maximum %d", nms_dist, yp::KR_MAX);
+  const int RW = yp::KT + 2 * nms_dist;
+  const size_t nms_smem = ((static_cast<size_t>(RW) * RW * 4 + 7) & ~static_cast<size_t>(7)) + yp::KT * yp::KT * (8 + 2 + 2) + static_cast<size_t>(RW) * RW;
+  static thread_local int coop_per_sm[yp::KR_MAX + 1] = {0};
+  if (coop_per_sm[nms_dist] == 0) {
+    if (nms_smem > 48 * 1024) YP_CUDA_OK(cudaFuncSetAttribute(yp::kp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     int per_sm = 0;
-    YP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yp::kp_nms_kernel, 256, 0));
-    if (per_sm > 4) per_sm = 4;
+    YP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yp::kp_nms_kernel, 256, nms_smem));
     YP_REQUIRE(per_sm >= 1, YP_ERR_CUDA, "keypoints: NMS kernel does not fit on an SM");
-    coop_blocks = per_sm * yp::sm_count();
+    coop_per_sm[nms_dist] = per_sm > 4 ? 4 : per_sm;
   }
+  const int tiles = B * yp::ceil_div(H, yp::KT) * yp::ceil_div(W, yp::KT);
+  int coop_blocks = coop_per_sm[nms_dist] * yp::sm_count();
+  if (coop_blocks > tiles) coop_blocks = tiles;
+  YP_CUDA_OK(cudaMemsetAsync(ws.remaining, 0, 3 * sizeof(unsigned int), st));
+  YP_CUDA_OK(cudaMemsetAsync(ws.n_list, 0, sizeof(int) * B, st));
   int Bv = B, Hv = H, Wv = W, rv = nms_dist;
   float thr = conf_thresh;
   void* args[] = {(void*)&heat, &Bv, &Hv, &Wv, &thr, &rv, &ws};
-  YP_CUDA_OK(cudaLaunchCooperativeKernel((void*)yp::kp_nms_kernel, dim3(coop_blocks), dim3(256), args, 0, st));
+  YP_CUDA_OK(cudaLaunchCooperativeKernel((void*)yp::kp_nms_kernel, dim3(coop_blocks), dim3(256), args, nms_smem, st));
   const size_t smem = boxes ? sizeof(int) * 4 * box_ld : 0;
   if (smem > 48 * 1024) {
     static thread_local bool raised = false;
