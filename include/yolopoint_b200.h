@@ -148,6 +148,13 @@ typedef struct {
 } YpNmsParams;
 
 size_t yp_box_nms_workspace_bytes(int32_t B, int64_t A, int32_t no, int32_t cap);
+/* Fused front end for the whole-frame pipeline: Detect decode (models/yolo.py:60-68) + the NMS above, straight from the
+ * three levels' raw logits (fp32 NHWC [B,ny,nx,ldc], channel a*no+o), so that `pred` is never written: only rows whose
+ * sigmoid(objectness) passes conf_thres are decoded.  Arrays of 3 (levels) live on the HOST; anchors_px_host = 18 floats
+ * (level, anchor, w/h) in pixels.  Same outputs / workspace as yp_box_nms with A = sum_l na*ny*nx. */
+int yp_detect_nms(const float* const* logits3_host, const int32_t* ny3_host, const int32_t* nx3_host, const int32_t* ldc3_host,
+                  const float* stride3_host, const float* anchors_px_host, int32_t B, int32_t na, int32_t no, const YpNmsParams* p,
+                  int32_t cap, float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, const YpNmsParams* p, int32_t cap,
                float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -54,6 +54,8 @@ SIGNATURES = {
     "yp_detect_decode": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, C.POINTER(C.c_float), _vp, _vp, _i64, _i64, _vp]),
     "yp_box_nms_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "yp_box_nms": (_i32, [_vp, _i32, _i64, _i32, _PN, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "yp_detect_nms": (_i32, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                             C.POINTER(C.c_float), _i32, _i32, _i32, _PN, _i32, _vp, _vp, _vp, _sz, _vp]),
     "yp_heatmap": (_i32, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "yp_keypoints_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "yp_keypoints": (_i32, [_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),

@@ -156,7 +156,9 @@ struct ConvArgs {
   int in_planes, a_split;          // a_split: 1 = both planes of A arrive with one TMA (box plane dim 2)
   int a_plane_off;                 // smem byte offset of the lo plane inside the A region
   int Nt, stages, stage_bytes, a_region_bytes, bar_off, tx_bytes;
-  int n_small, n_main;             // TMEM accumulators: cross terms / main terms (see kernel comment)
+  int n_iss;                       // MMA-issuing threads (1..3), each with its own accumulator set
+  int acc_base[3], acc_cnt[3];     // accumulator index range of issuer q; n_acc = sum(acc_cnt)
+  int n_acc;
   uint32_t idesc, tmem_cols;
   const float* bias;
   int act, l2norm;
@@ -226,8 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int i = 0; i < n_in; ++i) tma_prefetch_desc(&maps.in[i]);
     tma_prefetch_desc(&maps.w);
     for (int i = 0; i < a.n_out_maps; ++i) tma_prefetch_desc(&maps.out[i]);
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), a.n_iss); }
+    mbar_init(accum_bar, a.n_iss);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
@@ -266,39 +268,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const int ksteps = a.ck_bytes / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
-      const uint32_t b_plane = a.Nt * a.ck_bytes;
-      uint32_t used = 0;                   // bit j set = accumulator j already holds a partial sum
-      int s = 0, ph = 0, next_main = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        if (kb < 96) stamp(104 + kb);
-        const uint32_t sa = smem_base + s * a.stage_bytes;
-        const uint32_t sb = sa + a.a_region_bytes;
-        const uint64_t a_hi = make_smem_desc(sa, a.ck_bytes), a_lo = make_smem_desc(sa + a.a_plane_off, a.ck_bytes);
-        const uint64_t w_hi = make_smem_desc(sb, a.ck_bytes), w_lo = make_smem_desc(sb + b_plane, a.ck_bytes);
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ko = static_cast<uint64_t>(2 * k);
-          if (kTf32) {
-            const int c0 = a.n_main, c1 = a.n_main + a.n_small - 1;   // cross-term accumulators (may coincide)
-            umma<kTf32>(tmem_base + c0 * a.Nt, a_lo + ko, w_hi + ko, a.idesc, (used >> c0) & 1u); used |= 1u << c0;
-            umma<kTf32>(tmem_base + c1 * a.Nt, a_hi + ko, w_lo + ko, a.idesc, (used >> c1) & 1u); used |= 1u << c1;
-          }
-          const int m = next_main;
-          umma<kTf32>(tmem_base + m * a.Nt, a_hi + ko, w_hi + ko, a.idesc, (used >> m) & 1u); used |= 1u << m;
-          if (++next_main == a.n_main) next_main = 0;
+  }
+  // ===================== MMA issuers =====================
+  // A single thread issues a tcgen05.mma every ~65-100 cycles (measured), far less than the tensor pipe can retire for
+  // these small tiles, so the products of a k-block are split over up to three issuing threads (warp 1 and lane 0 of the
+  // first two epilogue warps, idle until the accumulators are complete).  3xTF32: issuer 0 = A_hi*W_hi, issuer 1 =
+  // A_lo*W_hi, issuer 2 = A_hi*W_lo (two issuers: 1 takes both cross terms); bf16: k-steps are dealt round-robin.
+  // Each issuer owns a disjoint accumulator set and rotates through it.
+  if (warp >= 1 && warp - 1 < a.n_iss && lane == 0) {
+    const int q = warp - 1;
+    const int ksteps = a.ck_bytes / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
+    const uint32_t b_plane = a.Nt * a.ck_bytes;
+    const int base = a.acc_base[q], cnt = a.acc_cnt[q];
+    uint32_t used = 0;                   // bit j set = accumulator base+j already holds a partial sum
+    int s = 0, ph = 0, nxt = 0;
+    auto issue = [&](uint64_t ad, uint64_t bd) {
+      umma<kTf32>(tmem_base + (base + nxt) * a.Nt, ad, bd, a.idesc, (used >> nxt) & 1u);
+      used |= 1u << nxt;
+      if (++nxt == cnt) nxt = 0;
+    };
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (q == 0 && kb < 96) stamp(104 + kb);
+      const uint32_t sa = smem_base + s * a.stage_bytes;
+      const uint32_t sb = sa + a.a_region_bytes;
+      const uint64_t a_hi = make_smem_desc(sa, a.ck_bytes), a_lo = make_smem_desc(sa + a.a_plane_off, a.ck_bytes);
+      const uint64_t w_hi = make_smem_desc(sb, a.ck_bytes), w_lo = make_smem_desc(sb + b_plane, a.ck_bytes);
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t ko = static_cast<uint64_t>(2 * k);
+        if (kTf32) {
+          if (q == 0) issue(a_hi + ko, w_hi + ko);
+          if (q == 1) issue(a_lo + ko, w_hi + ko);
+          if (q == a.n_iss - 1 && q >= 1) issue(a_hi + ko, w_lo + ko);
+          if (a.n_iss == 1) { issue(a_lo + ko, w_hi + ko); issue(a_hi + ko, w_lo + ko); }
+        } else {
+          if (k % a.n_iss == q) issue(a_hi + ko, w_hi + ko);
         }
-        umma_commit(empty_bar(s));  // frees the smem stage when the MMAs above retire
-        if (kb < 96) stamp(200 + kb);
-        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(accum_bar);
+      umma_commit(empty_bar(s));  // one arrival per issuer: the stage is free when all their MMAs have retired
+      if (q == 0 && kb < 96) stamp(200 + kb);
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
-  } else {
+    umma_commit(accum_bar);
+  }
+  __syncwarp();
+  if (warp >= 2) {
     // ===================== epilogue =====================
     using TO = typename OutT<OUT_FMT>::type;
     constexpr int CH = 16 * UNITS;                 // elements per staging row
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool et0 = (threadIdx.x == 64);
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int n_chunks = a.Nt / CH;
-    const int n_acc = a.n_main + a.n_small;
+    const int n_acc = a.n_acc;
     const bool has_res = a.res_base != nullptr && valid;
     const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
 
@@ -614,16 +629,36 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   }
   YP_REQUIRE(Nt >= 16 && Nt % 16 == 0 && Nt <= 256, YP_ERR_SHAPE, "conv: no valid N tile for Cout=%d", d.cout);
   a.Nt = Nt;
-  a.n_small = tf32 ? 2 : 0;
-  int n_main = 512 / Nt - a.n_small;
-  if (n_main < 1) { a.n_small = tf32 ? 1 : 0; n_main = 512 / Nt - a.n_small; }
-  const int main_cap = tf32 ? 6 : 4;
-  if (n_main > main_cap) n_main = main_cap;
-  if (n_main > main_mmas) n_main = main_mmas;
-  YP_REQUIRE(n_main >= 1, YP_ERR_SHAPE, "conv: Nt=%d leaves no TMEM accumulator", Nt);
-  a.n_main = n_main;
+  // accumulators per issuing thread (see the kernel comment); all sets are disjoint
+  {
+    const int total = 512 / Nt;
+    int cnt[3] = {0, 0, 0};
+    if (tf32) {
+      if (total >= 16) { a.n_iss = 3; cnt[0] = 8; cnt[1] = 4; cnt[2] = 4; }
+      else if (total >= 8) { a.n_iss = 3; cnt[0] = 4; cnt[1] = 2; cnt[2] = 2; }
+      else if (total >= 5) { a.n_iss = 3; cnt[0] = total - 2; cnt[1] = 1; cnt[2] = 1; }
+      else if (total == 4) { a.n_iss = 3; cnt[0] = 2; cnt[1] = 1; cnt[2] = 1; }
+      else if (total == 3) { a.n_iss = 3; cnt[0] = 1; cnt[1] = 1; cnt[2] = 1; }
+      else { a.n_iss = 2; cnt[0] = 1; cnt[1] = 1; }                 // Nt = 192..256: one accumulator for both cross terms
+      if (cnt[0] > main_mmas) cnt[0] = main_mmas;                  // every accumulator must receive at least one MMA
+      if (cnt[1] > main_mmas) cnt[1] = main_mmas;
+      if (cnt[2] > main_mmas) cnt[2] = main_mmas;
+    } else {
+      const int ksteps = a.ck_bytes / 32;
+      a.n_iss = (total >= 2 && ksteps >= 2) ? 2 : 1;
+      const int per = main_mmas / a.n_iss;                         // MMAs each issuer emits (ksteps is even when n_iss == 2)
+      int each = total / a.n_iss;
+      if (each > 2) each = 2;
+      if (each > per) each = per;
+      for (int q = 0; q < a.n_iss; ++q) cnt[q] = each;
+    }
+    int base = 0;
+    for (int q = 0; q < 3; ++q) { a.acc_base[q] = base; a.acc_cnt[q] = cnt[q]; base += cnt[q]; }
+    a.n_acc = base;
+    YP_REQUIRE(a.n_acc >= 1 && a.n_acc * Nt <= 512, YP_ERR_SHAPE, "conv: accumulator plan %d x %d exceeds TMEM", a.n_acc, Nt);
+  }
   a.tmem_cols = 32;
-  while ((int)a.tmem_cols < (a.n_main + a.n_small) * Nt) a.tmem_cols <<= 1;
+  while ((int)a.tmem_cols < a.n_acc * Nt) a.tmem_cols <<= 1;
   // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format [7,10)/[10,13)
   // (TF32=2, BF16=1), K-major both, N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t ab = tf32 ? 2u : 1u;

@@ -50,11 +50,10 @@ __global__ void detect_decode_kernel(const DecodeArgs a) {
 // NMS stage 1: candidates.  One warp per prediction row.
 // ------------------------------------------------------------------------------------------------
 struct NmsWs {
-  int* row_count;       // [B*A]
-  int* row_offset;      // [B*A]
-  int* n_cand;          // [B]  candidates found (may exceed cap)
+  int* n_cand;          // [B]  candidates found (may exceed cap); slots are handed out with atomicAdd
   int* n_sorted;        // [B]  min(n_cand, cap, max_nms)
-  float* cand;          // [B][cap][6]  x1,y1,x2,y2,conf,cls in candidate order
+  unsigned int* ord;    // [B][cap]  position of the candidate in the reference's row-major (box, class) order
+  float* cand;          // [B][cap][6]  x1,y1,x2,y2,conf,cls in arbitrary (slot) order
   float* sorted;        // [B][cap][6]  confidence-descending (stable)
   unsigned long long* mask;  // [B][cap][cap/64]
 };
@@ -63,124 +62,113 @@ __device__ __forceinline__ bool class_ok(const uint32_t* class_mask, int c) {
   return class_mask == nullptr || ((class_mask[c >> 5] >> (c & 31)) & 1u);
 }
 
-// pass 0: count, pass 1: scatter
-template <int PASS>
-__global__ void nms_candidates_kernel(const float* __restrict__ pred, int B, long long A, int no, YpNmsParams p, int cap, NmsWs ws) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+// Candidate emission shared by the two front ends (decoded `pred` rows, or raw Detect logits).
+// x,y,w,h,obj and a class-score accessor cls(c) are already sigmoid-decoded values.
+template <typename ClsFn>
+__device__ __forceinline__ void emit_candidates(float bx, float by, float bw, float bh, float obj, int nc, ClsFn cls, unsigned int row,
+                                                const YpNmsParams& p, int cap, int b, const NmsWs& ws) {
+  auto put = [&](float conf, int c, unsigned int ord) {
+    const int slot = atomicAdd(&ws.n_cand[b], 1);
+    if (slot < cap) {
+      float* o = ws.cand + (static_cast<int64_t>(b) * cap + slot) * 6;
+      o[0] = __fsub_rn(bx, __fdiv_rn(bw, 2.0f)); o[1] = __fsub_rn(by, __fdiv_rn(bh, 2.0f));   // xywh2xyxy, general_yolo.py:623-630
+      o[2] = __fadd_rn(bx, __fdiv_rn(bw, 2.0f)); o[3] = __fadd_rn(by, __fdiv_rn(bh, 2.0f));
+      o[4] = conf; o[5] = static_cast<float>(c);
+      ws.ord[static_cast<int64_t>(b) * cap + slot] = ord;
+    }
+  };
+  if (p.multi_label && nc > 1) {  // one candidate per (row, class) with conf > thr, general_yolo.py:191-193
+    for (int c = 0; c < nc; ++c) {
+      const float conf = __fmul_rn(cls(c), obj);
+      if (conf > p.conf_thres && class_ok(p.class_mask, c)) put(conf, c, row * static_cast<unsigned int>(nc) + c);
+    }
+  } else {                        // best class only (first maximum), general_yolo.py:195-196
+    float best = -INFINITY;
+    int bc = 0;
+    for (int c = 0; c < nc; ++c) {
+      const float conf = __fmul_rn(cls(c), obj);
+      if (conf > best) { best = conf; bc = c; }
+    }
+    if (best > p.conf_thres && class_ok(p.class_mask, bc)) put(best, bc, row);
+  }
+}
+
+// front end 1: decoded predictions [B,A,no]; one thread per row (objectness survivors are rare)
+__global__ void nms_candidates_pred_kernel(const float* __restrict__ pred, int B, long long A, int no, YpNmsParams p, int cap, NmsWs ws) {
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (row >= static_cast<int64_t>(B) * A) return;
   const int b = static_cast<int>(row / A);
   const float* r = pred + row * no;
-  const int nc = no - 5;
   const float obj = r[4];
-  int count = 0;
-  if (obj > p.conf_thres) {  // strict, general_yolo.py:146
-    float bx = 0, by = 0, bw = 0, bh = 0;
-    int base = 0;
-    if (PASS == 1) {
-      bx = r[0]; by = r[1]; bw = r[2]; bh = r[3];
-      base = ws.row_offset[row];
-    }
-    const bool multi = p.multi_label && nc > 1;
-    if (multi) {
-      for (int c0 = 0; c0 < nc; c0 += 32) {
-        const int c = c0 + lane;
-        float conf = 0.0f;
-        bool hit = false;
-        if (c < nc) { conf = __fmul_rn(r[5 + c], obj); hit = conf > p.conf_thres && class_ok(p.class_mask, c); }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (PASS == 1 && hit) {
-          const int pos = base + count + __popc(m & ((1u << lane) - 1u));
-          if (pos < cap) {
-            float* o = ws.cand + (static_cast<int64_t>(b) * cap + pos) * 6;
-            o[0] = __fsub_rn(bx, __fdiv_rn(bw, 2.0f)); o[1] = __fsub_rn(by, __fdiv_rn(bh, 2.0f));
-            o[2] = __fadd_rn(bx, __fdiv_rn(bw, 2.0f)); o[3] = __fadd_rn(by, __fdiv_rn(bh, 2.0f));
-            o[4] = conf; o[5] = static_cast<float>(c);
-          }
-        }
-        count += __popc(m);
-      }
-    } else {  // best class only (first maximum), general_yolo.py:195-196
-      float best = -INFINITY;
-      int bc = 0x7fffffff;
-      for (int c = lane; c < nc; c += 32) {
-        const float conf = __fmul_rn(r[5 + c], obj);
-        if (conf > best) { best = conf; bc = c; }
-      }
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, s);
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, s);
-        if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
-      }
-      const bool hit = best > p.conf_thres && class_ok(p.class_mask, bc);
-      count = hit ? 1 : 0;
-      if (PASS == 1 && hit && lane == 0 && base < cap) {
-        float* o = ws.cand + (static_cast<int64_t>(b) * cap + base) * 6;
-        o[0] = __fsub_rn(bx, __fdiv_rn(bw, 2.0f)); o[1] = __fsub_rn(by, __fdiv_rn(bh, 2.0f));
-        o[2] = __fadd_rn(bx, __fdiv_rn(bw, 2.0f)); o[3] = __fadd_rn(by, __fdiv_rn(bh, 2.0f));
-        o[4] = best; o[5] = static_cast<float>(bc);
-      }
-    }
-  }
-  if (PASS == 0 && lane == 0) ws.row_count[row] = count;
+  if (!(obj > p.conf_thres)) return;  // strict, general_yolo.py:146
+  emit_candidates(r[0], r[1], r[2], r[3], obj, no - 5, [&](int c) { return r[5 + c]; }, static_cast<unsigned int>(row - b * A), p, cap, b, ws);
 }
 
-// exclusive scan of row_count per image (one block per image)
-__global__ void nms_scan_kernel(long long A, int cap, int max_nms, NmsWs ws) {
-  __shared__ int warp_excl[32];
-  __shared__ int block_total;
-  const int b = blockIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
-  int carry = 0;  // identical in every thread
-  for (int64_t base = 0; base < A; base += blockDim.x) {
-    const int64_t i = base + threadIdx.x;
-    const int v = i < A ? ws.row_count[b * A + i] : 0;
-    int incl = v;
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += t; }
-    __syncthreads();  // previous iteration's readers of warp_excl / block_total are done
-    if (lane == 31) warp_excl[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      const int wv = lane < nwarps ? warp_excl[lane] : 0;
-      int wincl = wv;
-#pragma unroll
-      for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wincl, s); if (lane >= s) wincl += t; }
-      warp_excl[lane] = wincl - wv;
-      if (lane == 31) block_total = wincl;
-    }
-    __syncthreads();
-    if (i < A) ws.row_offset[b * A + i] = carry + warp_excl[wid] + incl - v;
-    carry += block_total;
-  }
-  if (threadIdx.x == 0) {
-    ws.n_cand[b] = carry;
-    const int n = carry < cap ? carry : cap;
-    ws.n_sorted[b] = n < max_nms ? n : max_nms;
-  }
+// front end 2: raw Detect logits of the three levels (NHWC, channel a*no+o): decode (models/yolo.py:60-68) only the rows
+// whose objectness passes, so `pred` is never materialised in the whole-frame pipeline.
+struct DetLevels {
+  const float* logits[3];
+  int ny[3], nx[3], ldc[3];
+  float stride[3];
+  float anchor[3][6];
+  long long row_off[3];
+  int na, no;
+};
+
+__device__ __forceinline__ float sigmoid_rn(float v) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v))); }
+
+__global__ void nms_candidates_logits_kernel(const DetLevels lv, int B, long long A, YpNmsParams p, int cap, NmsWs ws) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<int64_t>(B) * A) return;
+  const int b = static_cast<int>(idx / A);
+  const long long row = idx - b * A;
+  const int l = row >= lv.row_off[2] ? 2 : (row >= lv.row_off[1] ? 1 : 0);
+  const int ny = lv.ny[l], nx = lv.nx[l];
+  long long cell = row - lv.row_off[l];                 // (anchor, y, x) order, models/yolo.py:56
+  const int x = static_cast<int>(cell % nx); cell /= nx;
+  const int y = static_cast<int>(cell % ny);
+  const int an = static_cast<int>(cell / ny);
+  const float* r = lv.logits[l] + ((static_cast<int64_t>(b) * ny + y) * nx + x) * lv.ldc[l] + an * lv.no;
+  const float obj = sigmoid_rn(r[4]);
+  if (!(obj > p.conf_thres)) return;
+  const float sx = sigmoid_rn(r[0]), sy = sigmoid_rn(r[1]), sw = sigmoid_rn(r[2]), sh = sigmoid_rn(r[3]);
+  const float bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), static_cast<float>(x)), lv.stride[l]);
+  const float by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), static_cast<float>(y)), lv.stride[l]);
+  const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
+  const float bw = __fmul_rn(__fmul_rn(tw, tw), lv.anchor[l][an * 2]);
+  const float bh = __fmul_rn(__fmul_rn(th, th), lv.anchor[l][an * 2 + 1]);
+  emit_candidates(bx, by, bw, bh, obj, lv.no - 5, [&](int c) { return sigmoid_rn(r[5 + c]); }, static_cast<unsigned int>(row), p, cap, b, ws);
 }
 
-// stable descending rank sort: rank(i) = #{j : conf_j > conf_i or (conf_j == conf_i and j < i)}
+__global__ void nms_counts_kernel(int B, int cap, int max_nms, NmsWs ws) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int n = min(ws.n_cand[b], cap);
+  ws.n_sorted[b] = min(n, max_nms);
+}
+
+// descending rank sort, ties in the reference's candidate order: rank(i) = #{j : conf_j > conf_i or (conf_j == conf_i and ord_j < ord_i)}
 __global__ void nms_rank_kernel(int cap, NmsWs ws) {
   __shared__ float tile[256];
+  __shared__ unsigned int tord[256];
   const int b = blockIdx.y;
-  int n = ws.n_cand[b];
-  if (n > cap) n = cap;
+  const int n = min(ws.n_cand[b], cap);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x * blockDim.x >= n) return;
   const float* cand = ws.cand + static_cast<int64_t>(b) * cap * 6;
+  const unsigned int* ord = ws.ord + static_cast<int64_t>(b) * cap;
   const float ci = i < n ? cand[i * 6 + 4] : 0.0f;
+  const unsigned int oi = i < n ? ord[i] : 0u;
   int rank = 0;
   for (int j0 = 0; j0 < n; j0 += 256) {
     const int j = j0 + threadIdx.x;
     tile[threadIdx.x] = j < n ? cand[j * 6 + 4] : -INFINITY;
+    tord[threadIdx.x] = j < n ? ord[j] : 0xffffffffu;
     __syncthreads();
     const int lim = min(256, n - j0);
     for (int k = 0; k < lim; ++k) {
       const float cj = tile[k];
-      rank += (cj > ci || (cj == ci && (j0 + k) < i)) ? 1 : 0;
+      rank += (cj > ci || (cj == ci && tord[k] < oi)) ? 1 : 0;
     }
     __syncthreads();
   }
@@ -279,15 +267,14 @@ __global__ void nms_scan_keep_kernel(int cap, int max_det, NmsWs ws, float* __re
 #pragma unroll
       for (int k = 0; k < 6; ++k) out[pos * 6 + k] = s[k];
     }
-    for (int w = wc + 1 + threadIdx.x; w < nb; w += blockDim.x) {
-      unsigned long long acc = removed[w];
-      unsigned long long bits = kb;
-      while (bits) {
-        const int k = __ffsll(bits) - 1;
-        bits &= bits - 1;
-        acc |= mask[static_cast<int64_t>(wc * 64 + k) * words + w];
+    // fold the suppression rows of the kept boxes into `removed`: one (row, word) pair per thread, loads all in flight
+    const int later = nb - (wc + 1);
+    for (int t = threadIdx.x; t < 64 * later; t += blockDim.x) {
+      const int k = t / later, w = wc + 1 + (t - k * later);
+      if ((kb >> k) & 1ull) {
+        const unsigned long long m = mask[static_cast<int64_t>(wc * 64 + k) * words + w];
+        if (m) atomicOr(&removed[w], m);
       }
-      removed[w] = acc;
     }
     __syncthreads();
     if (threadIdx.x == 0) n_keep = base + __popcll(kb);
@@ -304,14 +291,24 @@ size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 size_t carve(NmsWs* ws, char* base, int B, long long A, int cap) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
-  ws->row_count = reinterpret_cast<int*>(take(sizeof(int) * B * A));
-  ws->row_offset = reinterpret_cast<int*>(take(sizeof(int) * B * A));
+  (void)A;
   ws->n_cand = reinterpret_cast<int*>(take(sizeof(int) * B));
   ws->n_sorted = reinterpret_cast<int*>(take(sizeof(int) * B));
+  ws->ord = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * B * cap));
   ws->cand = reinterpret_cast<float*>(take(sizeof(float) * 6 * B * cap));
   ws->sorted = reinterpret_cast<float*>(take(sizeof(float) * 6 * B * cap));
   ws->mask = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * cap * (cap / 64)));
   return off;
+}
+
+int nms_tail(int B, int cap, const YpNmsParams& p, const NmsWs& ws, float* out_boxes, int32_t* out_count, cudaStream_t st) {
+  nms_counts_kernel<<<ceil_div(B, 128), 128, 0, st>>>(B, cap, p.max_nms, ws);
+  nms_rank_kernel<<<dim3(cap / 256 + (cap % 256 ? 1 : 0), B), 256, 0, st>>>(cap, ws);
+  nms_mask_kernel<<<dim3(2 * sm_count(), B), 64, 0, st>>>(cap, p.iou_thres, p.agnostic, p.max_wh, ws);
+  const size_t smem = sizeof(unsigned long long) * (cap / 64);
+  nms_scan_keep_kernel<<<B, 128, smem, st>>>(cap, p.max_det, ws, out_boxes, out_count);
+  YP_LAUNCH_OK();
+  return YP_OK;
 }
 
 }  // namespace
@@ -352,14 +349,37 @@ extern "C" int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, c
   YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "box_nms: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = static_cast<int64_t>(B) * A;
-  const unsigned cblocks = static_cast<unsigned>(yp::ceil_div64(rows * 32, 256));
-  yp::nms_candidates_kernel<0><<<cblocks, 256, 0, st>>>(pred, B, A, no, *p, cap, ws);
-  yp::nms_scan_kernel<<<B, 1024, 0, st>>>(A, cap, p->max_nms, ws);
-  yp::nms_candidates_kernel<1><<<cblocks, 256, 0, st>>>(pred, B, A, no, *p, cap, ws);
-  yp::nms_rank_kernel<<<dim3(cap / 256 + (cap % 256 ? 1 : 0), B), 256, 0, st>>>(cap, ws);
-  yp::nms_mask_kernel<<<dim3(2 * yp::sm_count(), B), 64, 0, st>>>(cap, p->iou_thres, p->agnostic, p->max_wh, ws);
-  const size_t smem = sizeof(unsigned long long) * (cap / 64);
-  yp::nms_scan_keep_kernel<<<B, 128, smem, st>>>(cap, p->max_det, ws, out_boxes, out_count);
-  YP_LAUNCH_OK();
-  return YP_OK;
+  YP_CUDA_OK(cudaMemsetAsync(ws.n_cand, 0, sizeof(int) * B, st));
+  yp::nms_candidates_pred_kernel<<<static_cast<unsigned>(yp::ceil_div64(rows, 256)), 256, 0, st>>>(pred, B, A, no, *p, cap, ws);
+  return yp::nms_tail(B, cap, *p, ws, out_boxes, out_count, st);
 }
+
+extern "C" int yp_detect_nms(const float* const* logits3, const int32_t* ny3, const int32_t* nx3, const int32_t* ldc3, const float* stride3,
+                             const float* anchors_px_host, int32_t B, int32_t na, int32_t no, const YpNmsParams* p, int32_t cap,
+                             float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+  YP_REQUIRE(logits3 && ny3 && nx3 && ldc3 && stride3 && anchors_px_host && p && out_boxes && out_count && workspace, YP_ERR_ARG, "detect_nms: null pointer");
+  YP_REQUIRE(B > 0 && na == 3 && no >= 6, YP_ERR_SHAPE, "detect_nms: B=%d na=%d no=%d (na must be 3)", B, na, no);
+  YP_REQUIRE(cap > 0 && cap % 64 == 0, YP_ERR_SHAPE, "detect_nms: cap=%d must be a positive multiple of 64", cap);
+  YP_REQUIRE(p->conf_thres >= 0.f && p->conf_thres <= 1.f, YP_ERR_ARG, "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", p->conf_thres);
+  YP_REQUIRE(p->iou_thres >= 0.f && p->iou_thres <= 1.f, YP_ERR_ARG, "Invalid IoU %g, valid values are between 0.0 and 1.0", p->iou_thres);
+  YP_REQUIRE(p->max_det > 0 && p->max_nms > 0, YP_ERR_ARG, "detect_nms: max_det/max_nms must be positive");
+  yp::DetLevels lv;
+  long long A = 0;
+  for (int l = 0; l < 3; ++l) {
+    YP_REQUIRE(logits3[l] && na * no <= ldc3[l], YP_ERR_SHAPE, "detect_nms: level %d logits missing or ldc too small", l);
+    lv.logits[l] = logits3[l]; lv.ny[l] = ny3[l]; lv.nx[l] = nx3[l]; lv.ldc[l] = ldc3[l]; lv.stride[l] = stride3[l];
+    for (int i = 0; i < 6; ++i) lv.anchor[l][i] = anchors_px_host[l * 6 + i];
+    lv.row_off[l] = A;
+    A += static_cast<long long>(na) * ny3[l] * nx3[l];
+  }
+  lv.na = na; lv.no = no;
+  yp::NmsWs ws;
+  const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, A, cap);
+  YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "detect_nms: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  YP_CUDA_OK(cudaMemsetAsync(ws.n_cand, 0, sizeof(int) * B, st));
+  yp::nms_candidates_logits_kernel<<<static_cast<unsigned>(yp::ceil_div64(static_cast<int64_t>(B) * A, 256)), 256, 0, st>>>(lv, B, A, *p, cap, ws);
+  return yp::nms_tail(B, cap, *p, ws, out_boxes, out_count, st);
+}
+
+

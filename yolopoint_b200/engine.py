@@ -95,6 +95,7 @@ class ConvOp:
     residual: Optional[SliceRef] = None
     l2norm: bool = False
     stem: bool = False
+    lane: int = 0               # 0 = trunk / detection branch, 1 = keypoint head, 2 = descriptor head (independent streams)
 
 
 @dataclass
@@ -119,6 +120,7 @@ class NetPlan:
         self.D = c3
         self.bufs: Dict[str, Tuple[int, int, int]] = {}   # name -> (stride level, C, fmt)
         self.ops: List[object] = []
+        self._lane = 0
         self.det_pad = _pad16(3 * self.no)
         self.semi_pad = _pad16(65)
         self._build(c1, c2, c3, c4, c5, n1, n2, n3)
@@ -133,7 +135,7 @@ class NetPlan:
             names = (names,)
         if isinstance(dst, SliceRef):
             dst = (dst,)
-        self.ops.append(ConvOp(tuple(names), src, tuple(dst), k, s, cout, YP_ACT_SILU if act else YP_ACT_NONE, bn, residual, l2norm, stem))
+        self.ops.append(ConvOp(tuple(names), src, tuple(dst), k, s, cout, YP_ACT_SILU if act else YP_ACT_NONE, bn, residual, l2norm, stem, self._lane))
 
     def _c3(self, name, src: SliceRef, level, cout, n, dst):
         c_ = cout // 2
@@ -165,14 +167,17 @@ class NetPlan:
         self._conv("Conv2", t1, t2, 3, 2, c2)
         self._c3("Bottleneck1", t2, 2, c2, n1, xa)
         self._conv("Conv3", xa, x3, 3, 2, c3)
-        # keypoint head
+        # keypoint head (lane 1: only needs x3)
+        self._lane = 1
         sdet = self._buf("sdet", 3, c3)
         self._c3("BottleneckDet", x3, 3, c3, n1, sdet)
         semi = self._buf("semi", 3, self.semi_pad, YP_FMT_F32)
         self._conv("ConvDet", sdet, semi, 1, 1, self.semi_pad, act=False, bn=False)
         # desc + yolo encoder
+        self._lane = 0
         self._c3("Bottleneck2", x3, 3, c3, n2, xb)
-        # descriptor head
+        # descriptor head (lane 2: needs xa and xb)
+        self._lane = 2
         self._conv("ConvDescA", xa, S("catd", 0, c2), 3, 2, c2)
         self._conv("ConvDescB", xb, S("catd", c2, c2, upsample=2), 3, 2, c2)
         dd = self._buf("dd", 3, c3)
@@ -180,6 +185,7 @@ class NetPlan:
         desc = self._buf("desc", 3, c3, YP_FMT_F32)
         self._conv("ConvDesc", dd, desc, 3, 1, c3, act=False, bn=False, l2norm=True)
         # yolo encoder
+        self._lane = 0
         x4 = self._buf("x4", 4, c4)
         self._conv("Conv4", xb, x4, 3, 2, c4)
         self._c3("Bottleneck3", x4, 4, c4, n3, xc)
@@ -322,6 +328,7 @@ class ShapePlan:
         self.A = 3 * (Hc * Wc + (Hc // 2) * (Wc // 2) + (Hc // 4) * (Wc // 4))
         self.pred = torch.empty((B, self.A, net.no), dtype=torch.float32, device=dev)
         self.raw = [torch.empty((B, 3, Hc >> i, Wc >> i, net.no), dtype=torch.float32, device=dev) for i in range(3)]
+        self._side = None
         self._keep = []      # ctypes objects referenced by the launch closures
         self.launches = []   # callables (stream_ptr) -> None
         self._compile()
@@ -337,7 +344,7 @@ class ShapePlan:
             if isinstance(op, PoolOp):
                 v = self.view(SliceRef(op.buf, 0, self.bufs[op.buf].shape[-1]))
                 self._keep.append(v)
-                self.launches.append(lambda st, v=v: _lib.check(L.yp_sppf_pool(C.byref(v), st)))
+                self.launches.append((0, lambda st, v=v: _lib.check(L.yp_sppf_pool(C.byref(v), st))))
                 continue
             w, b = eng.weights[op.names]
             d = YpConvDesc()
@@ -353,7 +360,7 @@ class ShapePlan:
                 d.out[i] = self.view(ds)
             d.algo = eng.algo
             self._keep.append(d)
-            self.launches.append(lambda st, d=d: _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), st)))
+            self.launches.append((op.lane, lambda st, d=d: _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), st))))
 
     # ---- pieces -------------------------------------------------------------------------------
     def _stream(self):
@@ -368,9 +375,31 @@ class ShapePlan:
             _lib.check(L.yp_nchw_to_s2d(self.x_in.data_ptr(), self.B, self.H, self.W, C.byref(v), self._stream()))
 
     def run_net(self):
-        st = self._stream()
-        for f in self.launches:
-            f(st)
+        """Launch list; the keypoint and descriptor heads run on side streams that fork from / join the current stream
+        (also under graph capture), so their small grids overlap the detection branch."""
+        dev = self.eng.device
+        main = torch.cuda.current_stream(dev)
+        if not self.eng.multi_stream:
+            st = C.c_void_p(main.cuda_stream)
+            for _, f in self.launches:
+                f(st)
+            return
+        if self._side is None:
+            self._side = {1: torch.cuda.Stream(dev), 2: torch.cuda.Stream(dev)}
+        started = {}
+        ptr = {0: C.c_void_p(main.cuda_stream)}
+        for lane, f in self.launches:
+            if lane and lane not in started:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._side[lane].wait_event(ev)
+                started[lane] = True
+                ptr[lane] = C.c_void_p(self._side[lane].cuda_stream)
+            f(ptr[lane])
+        for lane in started:
+            ev = torch.cuda.Event()
+            ev.record(self._side[lane])
+            main.wait_event(ev)
 
     def run_decode(self, want_raw: bool = True):
         L, net, st = _lib.lib(), self.eng.net, self._stream()
@@ -413,11 +442,12 @@ class ShapePlan:
 
 
 class Engine:
-    def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True):
+    def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True,
+                 multi_stream: bool = True):
         _lib.lib(require_device=True)
         self.device = torch.device(device)
         self.net = NetPlan(version, nc, precision)
-        self.precision, self.algo, self.use_graphs = precision, algo, use_graphs
+        self.precision, self.algo, self.use_graphs, self.multi_stream = precision, algo, use_graphs, multi_stream
         sd = {k: v.detach() for k, v in sd.items()}
         self.anchors = _get(sd, "Detect.anchors").float().cpu()
         self.stride = torch.tensor([8.0, 16.0, 32.0])

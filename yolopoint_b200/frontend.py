@@ -66,9 +66,15 @@ class FramePipeline:
         B, H, W, cfg = self.B, self.H, self.W, self.cfg
         p.run_input(from_frame)
         p.run_net()
-        p.run_decode(False)
-        _lib.check(L.yp_box_nms(p.pred.data_ptr(), B, p.A, self.eng.net.no, C.byref(self.nms_params), self.nms_cap, self.boxes.data_ptr(),
-                                self.bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), st))
+        # Detect decode fused into the NMS front end: pred [B,A,85] is never materialised here
+        dets = [p.bufs[f"det{i}"] for i in range(3)]
+        lg = (C.c_void_p * 3)(*[d.data_ptr() for d in dets])
+        ny = (C.c_int32 * 3)(*[d.shape[2] for d in dets]); nx = (C.c_int32 * 3)(*[d.shape[3] for d in dets])
+        ldc = (C.c_int32 * 3)(*[d.shape[4] for d in dets])
+        strd = (C.c_float * 3)(*[float(v) for v in self.eng.stride])
+        anc = (C.c_float * 18)(*[float(v) for row in self.eng.anchors_px for v in row])
+        _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, self.eng.net.no, C.byref(self.nms_params), self.nms_cap,
+                                   self.boxes.data_ptr(), self.bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), st))
         semi = p.bufs["semi"][0]   # [B,Hc,Wc,80] fp32 NHWC
         sB, sH, sW, sC = semi.stride()
         _lib.check(L.yp_heatmap(semi.data_ptr(), B, H // 8, W // 8, sB, sC, sH, sW, self.heat_variant, self.heat.data_ptr(), st))
@@ -93,7 +99,8 @@ class FramePipeline:
     def n_launches(self) -> int:
         """Kernels of this library launched per frame batch (for bench.py's gpu_launches)."""
         net_launches = len(self.plan.launches)
-        per = 1 + net_launches + 3 + 6 + 1 + 3 + 1 + (self.B * 3 if self.do_match else 0)
+        # input + net + fused decode/NMS (candidates, counts, rank, mask, scan) + heatmap + keypoints (nms, collect, emit) + sample + match
+        per = 1 + net_launches + 5 + 1 + 3 + 1 + (self.B * 3 if self.do_match else 0)
         return per
 
     def step_device(self, from_frame: bool = True):

@@ -27,9 +27,9 @@ import torch
 TUNING = {
     "n": (2.5, 32.0, -2.5, 12.0, -3.0),
     "s": (2.5, 12.0, -3.0, 12.0, -3.0),
-    "m": (2.5, 12.0, -3.0, 12.0, -3.0),
-    "l": (2.5, 12.0, -3.0, 12.0, -3.0),
-    "x": (2.5, 12.0, -3.0, 12.0, -3.0),
+    "m": (2.2, 12.0, -3.0, 12.0, -3.0),   # deeper nets need a smaller gain to stay O(1)
+    "l": (2.0, 12.0, -3.0, 12.0, -3.0),
+    "x": (2.0, 12.0, -3.0, 12.0, -3.0),
 }
 
 
