@@ -18,6 +18,7 @@
 #include <cudaTypedefs.h>
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace yp {
 namespace {
@@ -214,6 +215,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
   auto stamp = [&](int slot) { if (dbg) dbg[slot] = clock64(); };
   if (threadIdx.x == 0) stamp(0);
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue (barrier init, TMEM allocation,
+  // descriptor prefetch) now; it blocks in griddepcontrol.wait until this grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // barriers + tmem slot + bias live after the pipeline/staging region
   const uint32_t bar_base = smem_base + a.bar_off;
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
       int s = 0, ph = 0, tap = 0, cb = 0;
       const uint32_t b_off = a.a_region_bytes;
       const uint32_t b_plane = a.Nt * a.ck_bytes;
@@ -388,6 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     };
 
     float res[CH];
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // the residual may be the previous kernel's output
     load_res(0, res);               // in flight while the main loop runs
     mbar_wait(accum_bar, 0);
     tc_fence_after();
@@ -530,8 +536,14 @@ int launch(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t smem, cuda
     YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
-  kern<<<grid, kThreads, smem, st>>>(maps, a);
-  YP_LAUNCH_OK();
+  static const bool use_pdl = getenv("YP_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  YP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, a));
   return YP_OK;
 }
 
