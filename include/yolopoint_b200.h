@@ -97,9 +97,15 @@ typedef struct {
   int32_t n_out;          /* 1 or 2 */
   YpView out[2];
   int32_t algo;           /* YpConvAlgo */
+  int32_t split_k;        /* 0 = let the library slice K over several CTAs when the layer cannot fill the GPU, 1 = never, n = n slices */
+  void* workspace;        /* split-K scratch (zero-initialised once by the caller, reusable by later launches on the same
+                             stream; launches that may run concurrently need distinct workspaces); NULL -> never split */
+  uint64_t workspace_bytes;
 } YpConvDesc;
 
 int yp_conv2d_nhwc_fwd(const YpConvDesc* desc, void* stream);
+/* Bytes of split-K workspace yp_conv2d_nhwc_fwd would like for this descriptor (0 = it will not split). */
+size_t yp_conv2d_workspace_bytes(const YpConvDesc* desc);
 
 /* Debug aid: when set to a device buffer of 512 int64, CTA (0,0) of every following tcgen05 conv launch records clock64
  * stamps of its pipeline events there (see tools/conv_timeline.py); NULL switches it off.  Not thread safe. */

@@ -48,6 +48,9 @@ CASES = [
     dict(B=1, H=8, W=8, Cin=512, Cout=256, k=1, s=1, act=False, plain=True),
     dict(B=1, H=80, W=80, Cin=128, Cout=80, k=1, s=1, act=False, plain=True, nobias=True),
     dict(B=3, H=34, W=18, Cin=64, Cout=32, k=3, s=1, res=True),
+    dict(B=1, H=20, W=20, Cin=256, Cout=256, k=3, s=1, res=True),     # deep layer on a small map: split-K
+    dict(B=1, H=40, W=40, Cin=128, Cout=128, k=3, s=2),
+    dict(B=1, H=20, W=20, Cin=1024, Cout=512, k=1, s=1, split=4),
 ]
 
 
@@ -91,7 +94,15 @@ def run_case(c, fmt, algo):
     if c.get("up"):
         d.out[1] = make_view(out2_buf, out_fmt, 0, Cout)
     d.algo = algo
-    _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    d.split_k = c.get("split", 0)
+    ws = None
+    if algo == YP_ALGO_TCGEN05:
+        nbytes = int(L.yp_conv2d_workspace_bytes(C.byref(d)))
+        if nbytes:
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
+    for _ in range(2):   # twice: the split-K arrival counters must reset themselves
+      _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     # reference
     torch.backends.cudnn.allow_tf32 = False

@@ -29,7 +29,8 @@ class YpView(C.Structure):
 class YpConvDesc(C.Structure):
     _fields_ = [("in_", YpView), ("weight", C.c_void_p), ("bias", C.c_void_p), ("ksize", C.c_int32), ("stride", C.c_int32),
                 ("cout", C.c_int32), ("act", C.c_int32), ("epilogue", C.c_uint32), ("residual", YpView), ("n_out", C.c_int32),
-                ("out", YpView * 2), ("algo", C.c_int32)]
+                ("out", YpView * 2), ("algo", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_uint64)]
 
 
 class YpNmsParams(C.Structure):
@@ -46,6 +47,7 @@ SIGNATURES = {
     "yp_last_error": (C.c_char_p, []),
     "yp_check_device": (_i32, []),
     "yp_conv2d_nhwc_fwd": (_i32, [_PC, _vp]),
+    "yp_conv2d_workspace_bytes": (_sz, [_PC]),
     "yp_debug_conv_timeline": (_i32, [_vp]),
     "yp_sppf_pool": (_i32, [_PV, _vp]),
     "yp_nchw_to_s2d": (_i32, [_vp, _i32, _i32, _i32, _PV, _vp]),

@@ -28,6 +28,7 @@ int sm_count() {
 }
 
 int conv_tc_forward(const YpConvDesc& d, cudaStream_t st);
+size_t conv_tc_workspace_bytes(const YpConvDesc& d);
 int conv_simt_forward(const YpConvDesc& d, cudaStream_t st);
 void set_conv_timeline(long long* p);
 
@@ -58,4 +59,9 @@ extern "C" int yp_conv2d_nhwc_fwd(const YpConvDesc* d, void* stream) {
 extern "C" int yp_debug_conv_timeline(void* device_buf_512_i64) {
   yp::set_conv_timeline(static_cast<long long*>(device_buf_512_i64));
   return YP_OK;
+}
+
+extern "C" size_t yp_conv2d_workspace_bytes(const YpConvDesc* d) {
+  if (!d || d->algo != YP_ALGO_TCGEN05) return 0;
+  return yp::conv_tc_workspace_bytes(*d);
 }

@@ -157,10 +157,17 @@ struct ConvArgs {
   int in_planes, a_split;          // a_split: 1 = both planes of A arrive with one TMA (box plane dim 2)
   int a_plane_off;                 // smem byte offset of the lo plane inside the A region
   int Nt, stages, stage_bytes, a_region_bytes, bar_off, tx_bytes;
-  int n_iss;                       // MMA-issuing threads (1..3), each with its own accumulator set
-  int acc_base[3], acc_cnt[3];     // accumulator index range of issuer q; n_acc = sum(acc_cnt)
-  int n_acc;
-  uint32_t idesc, tmem_cols;
+  // MMA issuers (see kernel comment).  Issuer q emits, per 32-byte k-step, n_jobs[q] MMAs (A plane ja, W plane jb) with
+  // instruction descriptor iss_idesc[q] into accumulator (iss_col[q] + r * iss_stride[q]), r rotating over iss_cnt[q].
+  int n_iss, kstep_mod;            // kstep_mod: 0 = every issuer takes every k-step, else issuer q takes k % kstep_mod == q
+  int n_jobs[2], job_a[2][2], job_b[2][2];
+  int iss_col[2], iss_stride[2], iss_cnt[2];
+  uint32_t iss_idesc[2];
+  int n_src, src_col[16];          // TMEM column bases whose sum is the result (main products first)
+  int split_k, kb_per_split;       // grid.z CTAs share one output tile, each reducing a slice of K
+  float* ws_partial;               // [split][m_tile][n_tile][128][Nt] fp32 partial sums
+  int* ws_counter;                 // [m_tile][n_tile] arrival counters (self-resetting)
+  uint32_t tmem_cols;
   const float* bias;
   int act, l2norm;
   const void* res_base;
@@ -211,8 +218,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int th = trem / a.tiles_w, tw = trem - th * a.tiles_w;
   const int h0 = th * a.Ht, w0 = tw * a.Wt;
   const int n0 = blockIdx.y * a.Nt;
-  const int num_kb = a.n_taps * a.kb_per_tap;
-  long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
+  const int num_kb_all = a.n_taps * a.kb_per_tap;
+  const int kb0 = blockIdx.z * a.kb_per_split;                       // this CTA's slice of the K loop (split-K)
+  const int num_kb = min(num_kb_all, kb0 + a.kb_per_split) - kb0;
+  long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
   auto stamp = [&](int slot) { if (dbg) dbg[slot] = clock64(); };
   if (threadIdx.x == 0) stamp(0);
   // Programmatic dependent launch: let the next kernel of the stream start its prologue (barrier init, TMEM allocation,
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
   const uint32_t accum_bar = bar_base + 8u * (2 * kMaxStages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
+  volatile int* split_flag = reinterpret_cast<volatile int*>(smem_gen + a.bar_off + 8 * (2 * kMaxStages + 1) + 4);
   float* bias_s = reinterpret_cast<float*>(smem_gen + a.bar_off + 8 * (2 * kMaxStages + 2));
 
   if (warp == 0 && lane == 0) {
@@ -251,9 +261,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
-      int s = 0, ph = 0, tap = 0, cb = 0;
+      int s = 0, ph = 0, tap = kb0 / a.kb_per_tap, cb = kb0 - tap * a.kb_per_tap;
       const uint32_t b_off = a.a_region_bytes;
-      const uint32_t b_plane = a.Nt * a.ck_bytes;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_expect_tx(full_bar(s), a.tx_bytes);
@@ -266,8 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t st = smem_base + s * a.stage_bytes;
         tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
         if (a.in_planes == 2 && !a.a_split) tma_load_5d(st + a.a_plane_off, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 1);
-        tma_load_3d(st + b_off, &maps.w, full_bar(s), kb * a.ck_elems, n0, 0);   // box covers both weight planes
-        (void)b_plane;
+        tma_load_3d(st + b_off, &maps.w, full_bar(s), (kb0 + kb) * a.ck_elems, n0, 0);   // box covers both weight planes
         if (kb < 96) stamp(8 + kb);
         if (++cb == a.kb_per_tap) { cb = 0; ++tap; }
         if (++s == a.stages) { s = 0; ph ^= 1; }
@@ -275,41 +283,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   }
   // ===================== MMA issuers =====================
-  // A single thread issues a tcgen05.mma every ~65-100 cycles (measured), far less than the tensor pipe can retire for
-  // these small tiles, so the products of a k-block are split over up to three issuing threads (warp 1 and lane 0 of the
-  // first two epilogue warps, idle until the accumulators are complete).  3xTF32: issuer 0 = A_hi*W_hi, issuer 1 =
-  // A_lo*W_hi, issuer 2 = A_hi*W_lo (two issuers: 1 takes both cross terms); bf16: k-steps are dealt round-robin.
-  // Each issuer owns a disjoint accumulator set and rotates through it.
+  // Measured on B200: one small tcgen05.mma (N <= 128, 32 bytes of K) occupies the tensor pipe for ~75-100 cycles whatever
+  // its N, plus ~350 cycles per k-block for the barrier round trip of the issuing thread.  Hence (i) 3xTF32 stacks
+  // W_hi and W_lo along N -- the two weight planes are adjacent in shared memory, so A_hi x [W_hi; W_lo] is ONE MMA of
+  // N = 2*Nt yielding the main product and one cross term -- leaving A_lo x W_hi as the only other MMA per k-step, and
+  // (ii) the two MMA streams are issued by two threads (warp 1 and lane 0 of the first epilogue warp, idle until the
+  // accumulators are complete); bf16 deals the k-steps to the two issuers round-robin.  Each issuer rotates through its
+  // own accumulators (dependent MMAs on one accumulator serialise, and fp32 accumulation in the tensor core truncates).
   if (warp >= 1 && warp - 1 < a.n_iss && lane == 0) {
     const int q = warp - 1;
     const int ksteps = a.ck_bytes / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
     const uint32_t b_plane = a.Nt * a.ck_bytes;
-    const int base = a.acc_base[q], cnt = a.acc_cnt[q];
-    uint32_t used = 0;                   // bit j set = accumulator base+j already holds a partial sum
+    const int cnt = a.iss_cnt[q];
+    const uint32_t col0 = tmem_base + a.iss_col[q], cstride = a.iss_stride[q], idesc = a.iss_idesc[q];
+    uint32_t used = 0;                   // bit r set = accumulator r of this issuer already holds a partial sum
     int s = 0, ph = 0, nxt = 0;
-    auto issue = [&](uint64_t ad, uint64_t bd) {
-      umma<kTf32>(tmem_base + (base + nxt) * a.Nt, ad, bd, a.idesc, (used >> nxt) & 1u);
-      used |= 1u << nxt;
-      if (++nxt == cnt) nxt = 0;
-    };
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       if (q == 0 && kb < 96) stamp(104 + kb);
       const uint32_t sa = smem_base + s * a.stage_bytes;
       const uint32_t sb = sa + a.a_region_bytes;
-      const uint64_t a_hi = make_smem_desc(sa, a.ck_bytes), a_lo = make_smem_desc(sa + a.a_plane_off, a.ck_bytes);
-      const uint64_t w_hi = make_smem_desc(sb, a.ck_bytes), w_lo = make_smem_desc(sb + b_plane, a.ck_bytes);
+      const uint64_t ad0 = make_smem_desc(sa + a.job_a[q][0] * a.a_plane_off, a.ck_bytes);
+      const uint64_t bd0 = make_smem_desc(sb + a.job_b[q][0] * b_plane, a.ck_bytes);
+      const uint64_t ad1 = make_smem_desc(sa + a.job_a[q][1] * a.a_plane_off, a.ck_bytes);
+      const uint64_t bd1 = make_smem_desc(sb + a.job_b[q][1] * b_plane, a.ck_bytes);
+      const bool two = a.n_jobs[q] == 2;
       for (int k = 0; k < ksteps; ++k) {
+        if (a.kstep_mod && (k % a.kstep_mod) != q) continue;
         const uint64_t ko = static_cast<uint64_t>(2 * k);
-        if (kTf32) {
-          if (q == 0) issue(a_hi + ko, w_hi + ko);
-          if (q == 1) issue(a_lo + ko, w_hi + ko);
-          if (q == a.n_iss - 1 && q >= 1) issue(a_hi + ko, w_lo + ko);
-          if (a.n_iss == 1) { issue(a_lo + ko, w_hi + ko); issue(a_hi + ko, w_lo + ko); }
-        } else {
-          if (k % a.n_iss == q) issue(a_hi + ko, w_hi + ko);
-        }
+        umma<kTf32>(col0 + nxt * cstride, ad0 + ko, bd0 + ko, idesc, (used >> nxt) & 1u);
+        if (two) umma<kTf32>(col0 + nxt * cstride, ad1 + ko, bd1 + ko, idesc, 1u);
+        used |= 1u << nxt;
+        if (++nxt == cnt) nxt = 0;
       }
       umma_commit(empty_bar(s));  // one arrival per issuer: the stage is free when all their MMAs have retired
       if (q == 0 && kb < 96) stamp(200 + kb);
@@ -332,7 +338,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool et0 = (threadIdx.x == 64);
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int n_chunks = a.Nt / CH;
-    const int n_acc = a.n_acc;
     const bool has_res = a.res_base != nullptr && valid;
     const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
 
@@ -364,26 +369,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     };
-    // accumulator columns [col, col+16) of this thread's row, summed over all TMEM accumulators (main first)
-    auto load_acc16 = [&](int col, float* v) {
+    // accumulator columns [col, col+16) of this thread's row: sum of all TMEM sources (main products first)
+    auto tmem_acc16 = [&](int col, float* v) {
       float t[4][16];
-      tmem_ld16(taddr_row + col, v);
+      tmem_ld16(taddr_row + a.src_col[0] + col, v);
       int j = 1;
-      for (; j + 2 < n_acc; j += 3) {   // batches of three loads in flight
-        tmem_ld16(taddr_row + (j + 0) * a.Nt + col, t[0]);
-        tmem_ld16(taddr_row + (j + 1) * a.Nt + col, t[1]);
-        tmem_ld16(taddr_row + (j + 2) * a.Nt + col, t[2]);
+      for (; j + 2 < a.n_src; j += 3) {   // batches of three loads in flight
+        tmem_ld16(taddr_row + a.src_col[j] + col, t[0]);
+        tmem_ld16(taddr_row + a.src_col[j + 1] + col, t[1]);
+        tmem_ld16(taddr_row + a.src_col[j + 2] + col, t[2]);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = ((v[i] + t[0][i]) + t[1][i]) + t[2][i];
       }
-      for (; j < n_acc; ++j) {
-        tmem_ld16(taddr_row + j * a.Nt + col, t[3]);
+      for (; j < a.n_src; ++j) {
+        tmem_ld16(taddr_row + a.src_col[j] + col, t[3]);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += t[3][i];
       }
       tmem_ld_wait();
+    };
+    const int S = a.split_k;
+    const long long tile_id = static_cast<long long>(blockIdx.x) * gridDim.y + blockIdx.y;
+    const long long n_tiles_all = static_cast<long long>(gridDim.x) * gridDim.y;
+    // split-K: partial sums of the S CTAs of a tile, read back in fixed order z = 0..S-1 (deterministic)
+    auto load_acc16 = [&](int col, float* v) {
+      if (S == 1) { tmem_acc16(col, v); return; }
+      const float* p = a.ws_partial + (tile_id * 128 + row) * a.Nt + col;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+      for (int z = 0; z < S; ++z) {
+        const float4* p4 = reinterpret_cast<const float4*>(p + z * n_tiles_all * 128 * a.Nt);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 f = __ldcg(p4 + j);
+          v[j * 4] += f.x; v[j * 4 + 1] += f.y; v[j * 4 + 2] += f.z; v[j * 4 + 3] += f.w;
+        }
+      }
     };
     auto finish = [&](float acc, int col, float res) -> float {
       float v = acc + bias_s[col];
@@ -399,6 +422,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tc_fence_after();
     if (et0) stamp(2);
 
+    bool run_epilogue = true;
+    if (S > 1) {
+      // publish this CTA's partial tile, then the last CTA to arrive (per tile) reduces all of them and finishes
+      float* mine = a.ws_partial + ((blockIdx.z * n_tiles_all + tile_id) * 128 + row) * a.Nt;
+      for (int u = 0; u < a.Nt / 16; ++u) {
+        float v[16];
+        tmem_acc16(u * 16, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) __stcg(reinterpret_cast<float4*>(mine + u * 16) + j, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et0) {
+        const int old = atomicAdd(a.ws_counter + tile_id, 1);
+        const int last = old == S - 1;
+        if (last) a.ws_counter[tile_id] = 0;   // ready for the next launch that uses this workspace
+        *split_flag = last;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      run_epilogue = *split_flag != 0;
+      __threadfence();
+    }
+    if (run_epilogue) {
     float inv_norm = 1.0f;
     if (a.l2norm) {                 // desc / ||desc||_2 over all Nt channels of the pixel (single N tile)
       float ss = 0.0f;
@@ -460,6 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     if (et0) { tma_store_wait_read<0>(); stamp(3); }
+    }  // run_epilogue
   }
 
   tc_fence_before();
@@ -565,8 +612,18 @@ void pick_patch(int Ho, int Wo, int* Ht, int* Wt) {
   *Ht = bh; *Wt = bw;
 }
 
-int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
-  YP_REQUIRE(get_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+namespace {
+
+struct ConvPlan {
+  ConvArgs a;
+  dim3 grid;
+  size_t smem, ws_bytes, ws_counter_bytes;
+  int out_fmt, units, chunk_elems;
+  bool tf32;
+};
+
+// Everything that does not need device pointers: tile shapes, accumulator plan, split-K factor, workspace need.
+int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   const YpView& in = d.in;
   const int in_fmt = in.format;
   YP_REQUIRE(in_fmt == YP_FMT_F32X2 || in_fmt == YP_FMT_BF16, YP_ERR_SHAPE, "conv: input format %d unsupported", in_fmt);
@@ -579,10 +636,9 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   YP_REQUIRE(d.n_out >= 1 && d.n_out <= 2, YP_ERR_SHAPE, "conv: n_out=%d", d.n_out);
   const int Ho = in.H / d.stride, Wo = in.W / d.stride;
 
-  ConvArgs a;
+  ConvArgs& a = P->a;
   memset(&a, 0, sizeof(a));
-  ConvMaps maps;
-  memset(&maps, 0, sizeof(maps));
+  P->tf32 = tf32;
   a.Ho = Ho; a.Wo = Wo; a.ksize = d.ksize; a.stride = d.stride;
   pick_patch(Ho, Wo, &a.Ht, &a.Wt);
   a.tiles_w = ceil_div(Wo, a.Wt); a.tiles_h = ceil_div(Ho, a.Ht);
@@ -596,10 +652,11 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   a.a_split = (a.in_planes == 2 && rows % 8 == 0) ? 1 : 0;   // lo plane lands right behind the hi plane, swizzle-aligned
   a.a_plane_off = ((rows + 7) & ~7) * a.ck_bytes;
   const int num_kb = a.n_taps * a.kb_per_tap;
-  const int main_mmas = num_kb * (a.ck_bytes / 32);
+  const int ksteps = a.ck_bytes / 32;
 
   // ---- output format / staging geometry
   const int out_fmt = d.out[0].format;
+  P->out_fmt = out_fmt;
   for (int i = 0; i < d.n_out; ++i) {
     YP_REQUIRE(d.out[i].format == out_fmt, YP_ERR_SHAPE, "conv: all outputs must share one format");
     YP_REQUIRE(d.out[i].C == d.cout && d.out[i].B == in.B && d.out[i].H == Ho && d.out[i].W == Wo, YP_ERR_SHAPE,
@@ -613,10 +670,12 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   a.out_row_bytes = cout_bytes % 128 == 0 ? 128 : (cout_bytes % 64 == 0 ? 64 : 32);
   const int chunk_elems = a.out_row_bytes / oes;
   YP_REQUIRE(chunk_elems % 16 == 0, YP_ERR_SHAPE, "conv: Cout=%d gives a %d-element store chunk (<16)", d.cout, chunk_elems);
+  P->chunk_elems = chunk_elems;
+  P->units = chunk_elems / 16;
   a.staging_set_bytes = a.out_planes * 128 * a.out_row_bytes;
 
-  // ---- N tile.  Fewer than #SM CTAs -> prefer small tiles (latency); long K chains in 3xTF32 mode -> Nt <= 64 so
-  // that at least six main accumulators fit into the 512 TMEM columns (accuracy + MMA pipelining).
+  // ---- N tile: the largest divisor of Cout (<= 128 in 3xTF32 mode so that [W_hi; W_lo] stacks into one N <= 256 MMA) that
+  // still yields >= #SM CTAs; when the layer cannot fill the GPU anyway, the smallest tile >= 32 (latency).
   const int m_tiles = a.tiles_w * a.tiles_h * in.B;
   const int nsm = sm_count();
   int Nt = 0;
@@ -624,8 +683,7 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
     YP_REQUIRE(d.cout <= 256, YP_ERR_SHAPE, "conv: L2-norm epilogue needs Cout <= 256 (got %d)", d.cout);
     Nt = d.cout;
   } else {
-    int nmax = tf32 ? 128 : 256;
-    if (tf32 && main_mmas > 96) nmax = 64;
+    const int nmax = tf32 ? 128 : 256;
     int smallest = 0;
     for (int n = nmax; n >= chunk_elems; n -= 16) {
       if (d.cout % n || n % chunk_elems) continue;
@@ -634,47 +692,77 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
       if (n <= 32 && smallest) break;
     }
     if (Nt == 0) Nt = smallest;
-    if (Nt == 0) {  // no divisor below the cap (e.g. Cout = 80 or 96 with a 64 cap): fall back to the unrestricted search
-      for (int n = tf32 ? 128 : 256; n >= chunk_elems && Nt == 0; n -= 16)
-        if (d.cout % n == 0 && n % chunk_elems == 0) Nt = n;
-    }
   }
   YP_REQUIRE(Nt >= 16 && Nt % 16 == 0 && Nt <= 256, YP_ERR_SHAPE, "conv: no valid N tile for Cout=%d", d.cout);
   a.Nt = Nt;
-  // accumulators per issuing thread (see the kernel comment); all sets are disjoint
-  {
-    const int total = 512 / Nt;
-    int cnt[3] = {0, 0, 0};
-    if (tf32) {
-      if (total >= 16) { a.n_iss = 3; cnt[0] = 8; cnt[1] = 4; cnt[2] = 4; }
-      else if (total >= 8) { a.n_iss = 3; cnt[0] = 4; cnt[1] = 2; cnt[2] = 2; }
-      else if (total >= 5) { a.n_iss = 3; cnt[0] = total - 2; cnt[1] = 1; cnt[2] = 1; }
-      else if (total == 4) { a.n_iss = 3; cnt[0] = 2; cnt[1] = 1; cnt[2] = 1; }
-      else if (total == 3) { a.n_iss = 3; cnt[0] = 1; cnt[1] = 1; cnt[2] = 1; }
-      else { a.n_iss = 2; cnt[0] = 1; cnt[1] = 1; }                 // Nt = 192..256: one accumulator for both cross terms
-      if (cnt[0] > main_mmas) cnt[0] = main_mmas;                  // every accumulator must receive at least one MMA
-      if (cnt[1] > main_mmas) cnt[1] = main_mmas;
-      if (cnt[2] > main_mmas) cnt[2] = main_mmas;
-    } else {
-      const int ksteps = a.ck_bytes / 32;
-      a.n_iss = (total >= 2 && ksteps >= 2) ? 2 : 1;
-      const int per = main_mmas / a.n_iss;                         // MMAs each issuer emits (ksteps is even when n_iss == 2)
-      int each = total / a.n_iss;
-      if (each > 2) each = 2;
-      if (each > per) each = per;
-      for (int q = 0; q < a.n_iss; ++q) cnt[q] = each;
-    }
-    int base = 0;
-    for (int q = 0; q < 3; ++q) { a.acc_base[q] = base; a.acc_cnt[q] = cnt[q]; base += cnt[q]; }
-    a.n_acc = base;
-    YP_REQUIRE(a.n_acc >= 1 && a.n_acc * Nt <= 512, YP_ERR_SHAPE, "conv: accumulator plan %d x %d exceeds TMEM", a.n_acc, Nt);
+  const int n_tiles = d.cout / Nt;
+
+  // ---- split-K: deep layers on small feature maps occupy few CTAs; slice K over grid.z so that ~#SM CTAs are busy.
+  int S = 1;
+  if (allow_split && !(d.epilogue & YP_EPI_L2NORM) && d.split_k != 1) {
+    const int ctas = m_tiles * n_tiles;
+    int want = d.split_k > 1 ? d.split_k : nsm / ctas;
+    if (want > 8) want = 8;
+    if (want > num_kb / 4) want = num_kb / 4;     // every slice keeps >= 4 k-blocks
+    if (want >= 2) S = want;
   }
-  a.tmem_cols = 32;
-  while ((int)a.tmem_cols < a.n_acc * Nt) a.tmem_cols <<= 1;
-  // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format [7,10)/[10,13)
-  // (TF32=2, BF16=1), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+  a.kb_per_split = ceil_div(num_kb, S);
+  S = ceil_div(num_kb, a.kb_per_split);
+  a.split_k = S;
+  const int kb_min = num_kb - (S - 1) * a.kb_per_split;   // k-blocks of the last (shortest) slice
+  const int mmas_min = kb_min * ksteps;                    // main MMAs every CTA issues at least
+
+  // ---- accumulator / issuer plan (see the kernel comment)
   const uint32_t ab = tf32 ? 2u : 1u;
-  a.idesc = (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(Nt >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  auto idesc = [&](int n) {  // cute::UMMA::InstrDescriptor: c F32 [4,6)=1, a/b format [7,10)/[10,13), K-major, N>>3 [17,23), M>>4 [24,29)
+    return (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  };
+  int cols = 0;
+  if (tf32 && Nt <= 128) {
+    // issuer 0: A_hi x [W_hi; W_lo]  (N = 2 Nt)  -> pairs [main | cross2];  issuer 1: A_lo x W_hi (N = Nt) -> cross1
+    int n_s = 2, n_p = (512 - n_s * Nt) / (2 * Nt);
+    if (n_p < 1) { n_s = 1; n_p = (512 - Nt) / (2 * Nt); }
+    if (n_p > 6) n_p = 6;
+    if (n_p > mmas_min) n_p = mmas_min;
+    if (n_s > mmas_min) n_s = mmas_min;
+    YP_REQUIRE(n_p >= 1 && n_s >= 1, YP_ERR_SHAPE, "conv: no accumulator plan for Nt=%d", Nt);
+    a.n_iss = 2; a.kstep_mod = 0;
+    a.n_jobs[0] = 1; a.job_a[0][0] = 0; a.job_b[0][0] = 0; a.iss_col[0] = 0; a.iss_stride[0] = 2 * Nt; a.iss_cnt[0] = n_p; a.iss_idesc[0] = idesc(2 * Nt);
+    a.n_jobs[1] = 1; a.job_a[1][0] = 1; a.job_b[1][0] = 0; a.iss_col[1] = n_p * 2 * Nt; a.iss_stride[1] = Nt; a.iss_cnt[1] = n_s; a.iss_idesc[1] = idesc(Nt);
+    int k = 0;
+    for (int j = 0; j < n_p; ++j) a.src_col[k++] = j * 2 * Nt;               // main products first
+    for (int j = 0; j < n_p; ++j) a.src_col[k++] = j * 2 * Nt + Nt;          // A_hi x W_lo
+    for (int j = 0; j < n_s; ++j) a.src_col[k++] = n_p * 2 * Nt + j * Nt;    // A_lo x W_hi
+    a.n_src = k;
+    cols = n_p * 2 * Nt + n_s * Nt;
+  } else if (tf32) {
+    // Nt in (128, 256] (L2-norm head of wide models): main accumulator + one accumulator for both cross terms
+    a.n_iss = 2; a.kstep_mod = 0;
+    a.n_jobs[0] = 1; a.job_a[0][0] = 0; a.job_b[0][0] = 0; a.iss_col[0] = 0; a.iss_stride[0] = 0; a.iss_cnt[0] = 1; a.iss_idesc[0] = idesc(Nt);
+    a.n_jobs[1] = 2; a.job_a[1][0] = 1; a.job_b[1][0] = 0; a.job_a[1][1] = 0; a.job_b[1][1] = 1;
+    a.iss_col[1] = Nt; a.iss_stride[1] = 0; a.iss_cnt[1] = 1; a.iss_idesc[1] = idesc(Nt);
+    a.n_src = 2; a.src_col[0] = 0; a.src_col[1] = Nt;
+    cols = 2 * Nt;
+  } else {
+    const int total = 512 / Nt;
+    a.n_iss = (total >= 2 && ksteps >= 2) ? 2 : 1;
+    a.kstep_mod = a.n_iss == 2 ? 2 : 0;
+    int each = total / a.n_iss;
+    if (each > 2) each = 2;
+    const int per = mmas_min / a.n_iss;
+    if (each > per) each = per;
+    YP_REQUIRE(each >= 1, YP_ERR_SHAPE, "conv: no accumulator plan for Nt=%d", Nt);
+    int k = 0;
+    for (int q = 0; q < a.n_iss; ++q) {
+      a.n_jobs[q] = 1; a.job_a[q][0] = 0; a.job_b[q][0] = 0; a.iss_col[q] = q * each * Nt; a.iss_stride[q] = Nt; a.iss_cnt[q] = each; a.iss_idesc[q] = idesc(Nt);
+      for (int j = 0; j < each; ++j) a.src_col[k++] = (q * each + j) * Nt;
+    }
+    a.n_src = k;
+    cols = a.n_iss * each * Nt;
+  }
+  YP_REQUIRE(cols <= 512 && a.n_src <= 16, YP_ERR_SHAPE, "conv: accumulator plan needs %d TMEM columns", cols);
+  a.tmem_cols = 32;
+  while ((int)a.tmem_cols < cols) a.tmem_cols <<= 1;
 
   // ---- pipeline geometry
   a.a_region_bytes = a.in_planes * 128 * a.ck_bytes;
@@ -685,7 +773,7 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   const int budget = 200 * 1024;
   int stages = budget / a.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > num_kb) stages = num_kb;
+  if (stages > a.kb_per_split) stages = a.kb_per_split;
   if (stages < 1) stages = 1;
   YP_REQUIRE(a.stage_bytes <= budget, YP_ERR_SHAPE, "conv: stage of %d bytes exceeds shared memory", a.stage_bytes);
   a.stages = stages;
@@ -693,8 +781,40 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   if (region < 2 * a.staging_set_bytes) region = 2 * a.staging_set_bytes;
   region = (region + 1023) & ~1023;
   a.bar_off = region;
-  const size_t smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 2) + Nt * sizeof(float) + 16;
-  YP_REQUIRE(smem <= 227 * 1024, YP_ERR_SHAPE, "conv: needs %zu bytes of shared memory", smem);
+  P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 2) + Nt * sizeof(float) + 16;
+  YP_REQUIRE(P->smem <= 227 * 1024, YP_ERR_SHAPE, "conv: needs %zu bytes of shared memory", P->smem);
+  P->grid = dim3(m_tiles, n_tiles, S);
+  P->ws_counter_bytes = (static_cast<size_t>(m_tiles) * n_tiles * sizeof(int) + 255) & ~static_cast<size_t>(255);
+  P->ws_bytes = S > 1 ? P->ws_counter_bytes + static_cast<size_t>(S) * m_tiles * n_tiles * 128 * Nt * sizeof(float) : 0;
+  return YP_OK;
+}
+
+}  // namespace
+
+size_t conv_tc_workspace_bytes(const YpConvDesc& d) {
+  ConvPlan P;
+  if (plan_conv(d, &P, true) != YP_OK) return 0;
+  return P.ws_bytes;
+}
+
+int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
+  YP_REQUIRE(get_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  ConvPlan P;
+  int rc = plan_conv(d, &P, d.workspace != nullptr);
+  if (rc != YP_OK) return rc;
+  if (P.ws_bytes > d.workspace_bytes) {   // workspace too small for the split the planner wants: run unsplit
+    if ((rc = plan_conv(d, &P, false)) != YP_OK) return rc;
+  }
+  ConvArgs& a = P.a;
+  const YpView& in = d.in;
+  const int Ho = a.Ho, Wo = a.Wo, Nt = a.Nt, out_fmt = P.out_fmt, chunk_elems = P.chunk_elems;
+  if (a.split_k > 1) {
+    YP_REQUIRE(aligned16(d.workspace), YP_ERR_ALIGN, "conv: workspace not 16-byte aligned");
+    a.ws_counter = static_cast<int*>(d.workspace);
+    a.ws_partial = reinterpret_cast<float*>(static_cast<char*>(d.workspace) + P.ws_counter_bytes);
+  }
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
 
   a.dbg = g_timeline;
   a.bias = d.bias;
@@ -708,7 +828,6 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   }
 
   // ---- tensor maps
-  int rc;
   if (d.stride == 1) {
     if ((rc = encode_view(&maps.in[0], in, 1, 0, 0, in.W, in.H, a.ck_elems, a.Wt, a.Ht, a.a_split ? 2 : 1)) != YP_OK) return rc;
   } else {
@@ -716,7 +835,7 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
       for (int pw = 0; pw < 2; ++pw)
         if ((rc = encode_view(&maps.in[ph * 2 + pw], in, 2, ph, pw, in.W, in.H, a.ck_elems, a.Wt, a.Ht, a.a_split ? 2 : 1)) != YP_OK) return rc;
   }
-  if ((rc = encode_weight(&maps.w, d.weight, in_fmt, a.n_taps * in.C, d.cout, a.ck_elems, Nt)) != YP_OK) return rc;
+  if ((rc = encode_weight(&maps.w, d.weight, in.format, a.n_taps * in.C, d.cout, a.ck_elems, Nt)) != YP_OK) return rc;
   int nm = 0;
   for (int i = 0; i < d.n_out; ++i) {
     const YpView& o = d.out[i];
@@ -730,8 +849,10 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   }
   a.n_out_maps = nm;
 
-  const dim3 grid(m_tiles, d.cout / Nt);
-  const int units = chunk_elems / 16;
+  const dim3 grid = P.grid;
+  const size_t smem = P.smem;
+  const int units = P.units;
+  const bool tf32 = P.tf32;
 #define YP_DISPATCH(FMT, U, TF) return launch<FMT, U, TF>(maps, a, grid, smem, st)
   if (tf32) {
     if (out_fmt == YP_FMT_F32X2) { if (units == 2) YP_DISPATCH(YP_FMT_F32X2, 2, true); if (units == 1) YP_DISPATCH(YP_FMT_F32X2, 1, true); }

@@ -340,6 +340,7 @@ class ShapePlan:
     def _compile(self):
         L = _lib.lib()
         eng = self.eng
+        need, descs = {}, []
         for op in eng.net.ops:
             if isinstance(op, PoolOp):
                 v = self.view(SliceRef(op.buf, 0, self.bufs[op.buf].shape[-1]))
@@ -359,8 +360,18 @@ class ShapePlan:
             for i, ds in enumerate(op.dst):
                 d.out[i] = self.view(ds)
             d.algo = eng.algo
+            d.split_k = 0 if eng.split_k else 1
+            need[op.lane] = max(need.get(op.lane, 0), int(L.yp_conv2d_workspace_bytes(C.byref(d)))) if eng.split_k else 0
+            descs.append((op.lane, d))
             self._keep.append(d)
             self.launches.append((op.lane, lambda st, d=d: _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), st))))
+        # split-K scratch: one zero-initialised buffer per lane (lanes may run concurrently; launches of one lane are
+        # stream-ordered and the arrival counters reset themselves)
+        self.workspaces = {lane: torch.zeros(max(n, 16), dtype=torch.uint8, device=eng.device) for lane, n in need.items() if n > 0}
+        for lane, d in descs:
+            if lane in self.workspaces:
+                d.workspace = self.workspaces[lane].data_ptr()
+                d.workspace_bytes = self.workspaces[lane].numel()
 
     # ---- pieces -------------------------------------------------------------------------------
     def _stream(self):
@@ -443,11 +454,11 @@ class ShapePlan:
 
 class Engine:
     def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True,
-                 multi_stream: bool = True):
+                 multi_stream: bool = True, split_k: bool = True):
         _lib.lib(require_device=True)
         self.device = torch.device(device)
         self.net = NetPlan(version, nc, precision)
-        self.precision, self.algo, self.use_graphs, self.multi_stream = precision, algo, use_graphs, multi_stream
+        self.precision, self.algo, self.use_graphs, self.multi_stream, self.split_k = precision, algo, use_graphs, multi_stream, split_k
         sd = {k: v.detach() for k, v in sd.items()}
         self.anchors = _get(sd, "Detect.anchors").float().cpu()
         self.stride = torch.tensor([8.0, 16.0, 32.0])
