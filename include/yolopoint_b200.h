@@ -184,6 +184,13 @@ int yp_heatmap(const float* semi, int32_t B, int32_t Hc, int32_t Wc, int64_t sB,
  * out_pts [B,max_pts,3] fp32 (x, y, conf), out_count int32 [B] (-1-n on overflow of max_pts).
  * ---------------------------------------------------------------------------------------------- */
 size_t yp_keypoints_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t max_pts);
+/* The two halves of yp_keypoints, so that a pipeline can run the NMS (which only needs the heatmap) on another stream
+ * while the boxes are still being computed, and collect (border + in-box filters, sort, emit) afterwards. */
+int yp_keypoints_nms(const float* heat, int32_t B, int32_t H, int32_t W, float conf_thresh, int32_t nms_dist, int32_t max_pts,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int yp_keypoints_collect(const float* heat, int32_t B, int32_t H, int32_t W, int32_t border, const float* boxes,
+                         const int32_t* box_count, int32_t box_ld, float* out_pts, int32_t* out_count, int32_t max_pts,
+                         void* workspace, size_t workspace_bytes, void* stream);
 int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, float conf_thresh, int32_t nms_dist,
                  int32_t border, const float* boxes, const int32_t* box_count, int32_t box_ld,
                  float* out_pts, int32_t* out_count, int32_t max_pts, void* workspace, size_t workspace_bytes,

@@ -60,6 +60,8 @@ SIGNATURES = {
                              C.POINTER(C.c_float), _i32, _i32, _i32, _PN, _i32, _vp, _vp, _vp, _sz, _vp]),
     "yp_heatmap": (_i32, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "yp_keypoints_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "yp_keypoints_nms": (_i32, [_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _sz, _vp]),
+    "yp_keypoints_collect": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "yp_keypoints": (_i32, [_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "yp_sample_desc": (_i32, [_vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "yp_match_partial": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),

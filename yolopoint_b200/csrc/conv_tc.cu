@@ -674,8 +674,10 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   P->units = chunk_elems / 16;
   a.staging_set_bytes = a.out_planes * 128 * a.out_row_bytes;
 
-  // ---- N tile: the largest divisor of Cout (<= 128 in 3xTF32 mode so that [W_hi; W_lo] stacks into one N <= 256 MMA) that
-  // still yields >= #SM CTAs; when the layer cannot fill the GPU anyway, the smallest tile >= 32 (latency).
+  // ---- N tile and split-K.  Measured on B200: the TMA engine of an SM delivers one 128-byte operand row every ~4 cycles
+  // (~60 GB/s per SM), which -- not the tensor pipe -- bounds these layers.  So (i) take the largest N tile (operand rows per
+  // MAC fall with Nt: the A tile is re-read once per N tile), (ii) when the tiles cannot occupy every SM, slice K over
+  // grid.z CTAs (each SM brings its own TMA engine) and let the last CTA of a tile reduce the partial sums.
   const int m_tiles = a.tiles_w * a.tiles_h * in.B;
   const int nsm = sm_count();
   int Nt = 0;
@@ -684,26 +686,19 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
     Nt = d.cout;
   } else {
     const int nmax = tf32 ? 128 : 256;
-    int smallest = 0;
-    for (int n = nmax; n >= chunk_elems; n -= 16) {
-      if (d.cout % n || n % chunk_elems) continue;
-      smallest = n;
-      if (Nt == 0 && m_tiles * (d.cout / n) >= nsm) Nt = n;
-      if (n <= 32 && smallest) break;
-    }
-    if (Nt == 0) Nt = smallest;
+    for (int n = nmax; n >= chunk_elems && Nt == 0; n -= 16)
+      if (d.cout % n == 0 && n % chunk_elems == 0) Nt = n;
   }
   YP_REQUIRE(Nt >= 16 && Nt % 16 == 0 && Nt <= 256, YP_ERR_SHAPE, "conv: no valid N tile for Cout=%d", d.cout);
   a.Nt = Nt;
   const int n_tiles = d.cout / Nt;
 
-  // ---- split-K: deep layers on small feature maps occupy few CTAs; slice K over grid.z so that ~#SM CTAs are busy.
   int S = 1;
   if (allow_split && !(d.epilogue & YP_EPI_L2NORM) && d.split_k != 1) {
     const int ctas = m_tiles * n_tiles;
     int want = d.split_k > 1 ? d.split_k : nsm / ctas;
-    if (want > 8) want = 8;
-    if (want > num_kb / 4) want = num_kb / 4;     // every slice keeps >= 4 k-blocks
+    if (want > 16) want = 16;
+    if (want > num_kb / 2) want = num_kb / 2;     // every slice keeps >= 2 k-blocks
     if (want >= 2) S = want;
   }
   a.kb_per_split = ceil_div(num_kb, S);

@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(256) kp_nms_kernel(const float* __restrict__ h
   const int64_t HW = static_cast<int64_t>(H) * W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int win = 2 * r + 1;
+  // One tile per CTA (the common case): heat, states and the sorted candidate list stay in shared memory for all rounds;
+  // later rounds only refresh the halo states and revisit the still-undecided candidates.
+  const bool resident = T <= static_cast<int>(gridDim.x);
+  int n_sorted = 0;
 
   for (int round = 0;; ++round) {
     unsigned int undecided = 0;
@@ -103,40 +107,50 @@ __global__ void __launch_bounds__(256) kp_nms_kernel(const float* __restrict__ h
       const int y0 = ty * KT - r, x0 = tx * KT - r;
       const float* hb = heat + b * HW;
       unsigned char* sb = ws.state + b * HW;
+      const bool fresh = round == 0 || !resident;
       for (int c = threadIdx.x; c < RN; c += blockDim.x) {
         const int ly = c / RW, lx = c - ly * RW;
         const int gy = y0 + ly, gx = x0 + lx;
         const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        const float h = inside ? hb[gy * W + gx] : -INFINITY;
-        sheat[c] = h;
-        unsigned char st = 0;
-        if (inside) st = round == 0 ? (h >= thr ? 1 : 0) : __ldcg(sb + gy * W + gx);
-        sstate[c] = st;
-      }
-      if (threadIdx.x == 0) n_list = 0;
-      __syncthreads();
-      for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
-        const int ly = c / KT + r, lx = c % KT + r;
-        const int cell = ly * RW + lx;
-        if (sstate[cell] == 1) {
-          const int slot = atomicAdd(&n_list, 1);
-          const unsigned int raster = static_cast<unsigned int>((y0 + ly) * W + (x0 + lx));
-          keys[slot] = (static_cast<unsigned long long>(ordered_bits(sheat[cell])) << 32) | (0xffffffffu - raster);
-          cand[slot] = static_cast<unsigned short>(cell);
+        if (fresh) {
+          const float h = inside ? hb[gy * W + gx] : -INFINITY;
+          sheat[c] = h;
+          unsigned char st = 0;
+          if (inside) st = round == 0 ? (h >= thr ? 1 : 0) : __ldcg(sb + gy * W + gx);
+          sstate[c] = st;
+        } else {
+          const bool halo = ly < r || ly >= r + KT || lx < r || lx >= r + KT;
+          if (halo && inside && sstate[c] == 1) sstate[c] = __ldcg(sb + gy * W + gx);   // only undecided halo cells can change
         }
       }
+      if (threadIdx.x == 0 && fresh) n_list = 0;
       __syncthreads();
-      const int n = n_list;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {  // rank sort, descending priority (keys are unique)
-        const unsigned long long ki = keys[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) rank += keys[j] > ki ? 1 : 0;
-        sorted[rank] = cand[i];
+      if (fresh) {
+        for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
+          const int ly = c / KT + r, lx = c % KT + r;
+          const int cell = ly * RW + lx;
+          if (sstate[cell] == 1) {
+            const int slot = atomicAdd(&n_list, 1);
+            const unsigned int raster = static_cast<unsigned int>((y0 + ly) * W + (x0 + lx));
+            keys[slot] = (static_cast<unsigned long long>(ordered_bits(sheat[cell])) << 32) | (0xffffffffu - raster);
+            cand[slot] = static_cast<unsigned short>(cell);
+          }
+        }
+        __syncthreads();
+        const int n = n_list;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {  // rank sort, descending priority (keys are unique)
+          const unsigned long long ki = keys[i];
+          int rank = 0;
+          for (int j = 0; j < n; ++j) rank += keys[j] > ki ? 1 : 0;
+          sorted[rank] = cand[i];
+        }
+        n_sorted = n;
+        __syncthreads();
       }
-      __syncthreads();
       if (warp == 0) {
-        for (int i = 0; i < n; ++i) {
+        for (int i = 0; i < n_sorted; ++i) {
           const int p = sorted[i];
+          if (sstate[p] != 1) continue;            // decided in an earlier round (warp-uniform)
           const int py = p / RW, px = p - py * RW;
           const float hp = sheat[p];
           const int gp = (y0 + py) * W + (x0 + px);
@@ -154,20 +168,23 @@ __global__ void __launch_bounds__(256) kp_nms_kernel(const float* __restrict__ h
           }
           kept = __any_sync(0xffffffffu, kept);
           pend = __any_sync(0xffffffffu, pend);
-          if (lane == 0) sstate[p] = kept ? 3 : (pend ? 1 : 2);
+          if (lane == 0) {
+            const unsigned char st = kept ? 3 : (pend ? 1 : 2);
+            sstate[p] = st;
+            if (st != 1 && !fresh) sb[gp] = st;   // resident rounds publish decisions one by one
+          }
           __syncwarp();
         }
       }
       __syncthreads();
-      for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
-        const int ly = c / KT + r, lx = c % KT + r;
-        const int gy = y0 + ly, gx = x0 + lx;
-        if (gy < H && gx < W) {
-          const unsigned char st = sstate[ly * RW + lx];
-          sb[gy * W + gx] = st;
-          undecided += st == 1 ? 1u : 0u;
+      if (fresh) {  // publish the whole interior (neighbours read candidates' states from global memory in later rounds)
+        for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
+          const int ly = c / KT + r, lx = c % KT + r;
+          const int gy = y0 + ly, gx = x0 + lx;
+          if (gy < H && gx < W) sb[gy * W + gx] = sstate[ly * RW + lx];
         }
       }
+      for (int i = threadIdx.x; i < n_sorted; i += blockDim.x) undecided += sstate[sorted[i]] == 1 ? 1u : 0u;
       __syncthreads();
     }
 #pragma unroll
@@ -283,19 +300,16 @@ extern "C" size_t yp_keypoints_workspace_bytes(int32_t B, int32_t H, int32_t W, 
   return yp::carve(&ws, nullptr, B, H, W, max_pts);
 }
 
-extern "C" int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, float conf_thresh, int32_t nms_dist, int32_t border,
-                            const float* boxes, const int32_t* box_count, int32_t box_ld, float* out_pts, int32_t* out_count,
-                            int32_t max_pts, void* workspace, size_t workspace_bytes, void* stream) {
-  YP_REQUIRE(heat && out_pts && out_count && workspace, YP_ERR_ARG, "keypoints: null pointer");
-  YP_REQUIRE(B > 0 && H > 0 && W > 0 && max_pts > 0 && nms_dist >= 0 && border >= 0, YP_ERR_SHAPE, "keypoints: bad shape");
+extern "C" int yp_keypoints_nms(const float* heat, int32_t B, int32_t H, int32_t W, float conf_thresh, int32_t nms_dist, int32_t max_pts,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  YP_REQUIRE(heat && workspace, YP_ERR_ARG, "keypoints: null pointer");
+  YP_REQUIRE(B > 0 && H > 0 && W > 0 && max_pts > 0 && nms_dist >= 0, YP_ERR_SHAPE, "keypoints: bad shape");
   YP_REQUIRE(static_cast<int64_t>(H) * W < (1ll << 31), YP_ERR_SHAPE, "keypoints: image too large");
-  YP_REQUIRE(!boxes || (box_count && box_ld > 0 && box_ld <= 8192), YP_ERR_ARG, "keypoints: boxes need box_count and 0 < box_ld <= 8192");
+  YP_REQUIRE(nms_dist <= yp::KR_MAX, YP_ERR_SHAPE, "keypoints: nms_dist=%d exceeds the supported maximum %d", nms_dist, yp::KR_MAX);
   yp::KpWs ws;
   const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, H, W, max_pts);
   YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "keypoints: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-
-  YP_REQUIRE(nms_dist <= yp::KR_MAX, YP_ERR_SHAPE, "keypoints: nms_dist=%d exceeds the supported maximum %d", nms_dist, yp::KR_MAX);
   const int RW = yp::KT + 2 * nms_dist;
   const size_t nms_smem = ((static_cast<size_t>(RW) * RW * 4 + 7) & ~static_cast<size_t>(7)) + yp::KT * yp::KT * (8 + 2 + 2) + static_cast<size_t>(RW) * RW;
   static thread_local int coop_per_sm[yp::KR_MAX + 1] = {0};
@@ -315,6 +329,19 @@ extern "C" int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, 
   float thr = conf_thresh;
   void* args[] = {(void*)&heat, &Bv, &Hv, &Wv, &thr, &rv, &ws};
   YP_CUDA_OK(cudaLaunchCooperativeKernel((void*)yp::kp_nms_kernel, dim3(coop_blocks), dim3(256), args, nms_smem, st));
+  return YP_OK;
+}
+
+extern "C" int yp_keypoints_collect(const float* heat, int32_t B, int32_t H, int32_t W, int32_t border, const float* boxes,
+                                    const int32_t* box_count, int32_t box_ld, float* out_pts, int32_t* out_count, int32_t max_pts,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  YP_REQUIRE(heat && out_pts && out_count && workspace, YP_ERR_ARG, "keypoints: null pointer");
+  YP_REQUIRE(B > 0 && H > 0 && W > 0 && max_pts > 0 && border >= 0, YP_ERR_SHAPE, "keypoints: bad shape");
+  YP_REQUIRE(!boxes || (box_count && box_ld > 0 && box_ld <= 8192), YP_ERR_ARG, "keypoints: boxes need box_count and 0 < box_ld <= 8192");
+  yp::KpWs ws;
+  const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, H, W, max_pts);
+  YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "keypoints: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = boxes ? sizeof(int) * 4 * box_ld : 0;
   if (smem > 48 * 1024) {
     static thread_local bool raised = false;
@@ -327,4 +354,12 @@ extern "C" int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, 
   yp::kp_emit_kernel<<<dim3(yp::ceil_div(max_pts, 256), B), 256, 0, st>>>(W, max_pts, ws, out_pts, out_count);
   YP_LAUNCH_OK();
   return YP_OK;
+}
+
+extern "C" int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, float conf_thresh, int32_t nms_dist, int32_t border,
+                            const float* boxes, const int32_t* box_count, int32_t box_ld, float* out_pts, int32_t* out_count,
+                            int32_t max_pts, void* workspace, size_t workspace_bytes, void* stream) {
+  const int rc = yp_keypoints_nms(heat, B, H, W, conf_thresh, nms_dist, max_pts, workspace, workspace_bytes, stream);
+  if (rc != YP_OK) return rc;
+  return yp_keypoints_collect(heat, B, H, W, border, boxes, box_count, box_ld, out_pts, out_count, max_pts, workspace, workspace_bytes, stream);
 }

@@ -98,45 +98,57 @@ __global__ void nhwc_to_nchw_kernel(YpView in, int C, float* __restrict__ out) {
   }
 }
 
-// SPPF: one pass over the 13x13 neighbourhood produces the 5x5 / 9x9 / 13x13 clipped-window maxima, which
-// equal the three chained MaxPool2d(5,1,2) outputs (padding is -inf, so clipping commutes with chaining).
-__global__ void sppf_pool_kernel(YpView cat4, int C) {
-  const int64_t total = static_cast<int64_t>(cat4.B) * cat4.H * cat4.W * C;
-  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % C);
-  int64_t p = idx / C;
-  const int w = static_cast<int>(p % cat4.W); p /= cat4.W;
-  const int h = static_cast<int>(p % cat4.H);
-  const int b = static_cast<int>(p / cat4.H);
-  float best[3] = {-INFINITY, -INFINITY, -INFINITY};
-  int64_t arg[3] = {0, 0, 0};
-  for (int dy = -6; dy <= 6; ++dy) {
-    const int y = h + dy;
-    if (y < 0 || y >= cat4.H) continue;
-    for (int dx = -6; dx <= 6; ++dx) {
-      const int x = w + dx;
-      if (x < 0 || x >= cat4.W) continue;
-      const int64_t off = ((static_cast<int64_t>(b) * cat4.H + y) * cat4.W + x) * cat4.pix_stride + c;
-      const float v = load_act(cat4.base, cat4.format, cat4.plane_stride, off);
-      const int ring = max(abs(dy), abs(dx));  // <=2 -> all three windows, <=4 -> 9x9 and 13x13, else 13x13
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (ring <= 2 * (k + 1) && v > best[k]) { best[k] = v; arg[k] = off; }
-    }
+// SPPF: three chained 5x5 stride-1 max pools (padding = -inf, i.e. clipped windows), all in shared memory.
+// One CTA owns G channels of one image: stage the (value, source pixel) pairs of the whole map, run the three
+// pooling passes ping-pong between two shared buffers and copy the operand planes of the winning source pixel into
+// concat slices 1..3, so the stored (hi, lo) pairs are bit-identical to the source element's.
+constexpr int SPPF_G = 8;
+
+__global__ void __launch_bounds__(256) sppf_pool_kernel(YpView cat4, int C) {
+  extern __shared__ unsigned char sp_smem[];
+  const int H = cat4.H, W = cat4.W, HW = H * W;
+  float* val[2] = {reinterpret_cast<float*>(sp_smem), reinterpret_cast<float*>(sp_smem) + HW * SPPF_G};
+  unsigned short* src[2] = {reinterpret_cast<unsigned short*>(val[1] + HW * SPPF_G), reinterpret_cast<unsigned short*>(val[1] + HW * SPPF_G) + HW * SPPF_G};
+  const int b = blockIdx.y, c0 = blockIdx.x * SPPF_G;
+  const int64_t img = static_cast<int64_t>(b) * HW * cat4.pix_stride;
+  const int n = HW * SPPF_G;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int p = i / SPPF_G, g = i - p * SPPF_G;
+    val[0][i] = load_act(cat4.base, cat4.format, cat4.plane_stride, img + static_cast<int64_t>(p) * cat4.pix_stride + c0 + g);
+    src[0][i] = static_cast<unsigned short>(p);
   }
-  const int64_t self = ((static_cast<int64_t>(b) * cat4.H + h) * cat4.W + w) * cat4.pix_stride + c;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int64_t dst = self + static_cast<int64_t>(k + 1) * C;
-    if (cat4.format == YP_FMT_BF16) {
-      __nv_bfloat16* f = static_cast<__nv_bfloat16*>(cat4.base);
-      f[dst] = f[arg[k]];
-    } else {  // copy the planes of the arg-max element verbatim (hi/lo are a canonical function of the value)
-      float* f = static_cast<float*>(cat4.base);
-      f[dst] = f[arg[k]];
-      if (cat4.format == YP_FMT_F32X2) f[dst + cat4.plane_stride] = f[arg[k] + cat4.plane_stride];
+  __syncthreads();
+  for (int pass = 0; pass < 3; ++pass) {
+    const float* vi = val[pass & 1];
+    const unsigned short* si = src[pass & 1];
+    float* vo = val[(pass + 1) & 1];
+    unsigned short* so = src[(pass + 1) & 1];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int p = i / SPPF_G, g = i - p * SPPF_G;
+      const int y = p / W, x = p - y * W;
+      float best = -INFINITY;
+      unsigned short arg = 0;
+      for (int yy = max(0, y - 2); yy <= min(H - 1, y + 2); ++yy)
+        for (int xx = max(0, x - 2); xx <= min(W - 1, x + 2); ++xx) {
+          const int q = (yy * W + xx) * SPPF_G + g;
+          const float v = vi[q];
+          if (v > best) { best = v; arg = si[q]; }
+        }
+      vo[i] = best;
+      so[i] = arg;
+      // slice (pass+1) of the concat buffer <- planes of the winning source element
+      const int64_t dst = img + static_cast<int64_t>(p) * cat4.pix_stride + c0 + g + static_cast<int64_t>(pass + 1) * C;
+      const int64_t from = img + static_cast<int64_t>(arg) * cat4.pix_stride + c0 + g;
+      if (cat4.format == YP_FMT_BF16) {
+        __nv_bfloat16* f = static_cast<__nv_bfloat16*>(cat4.base);
+        f[dst] = f[from];
+      } else {
+        float* f = static_cast<float*>(cat4.base);
+        f[dst] = f[from];
+        if (cat4.format == YP_FMT_F32X2) f[dst + cat4.plane_stride] = f[from + cat4.plane_stride];
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -163,10 +175,18 @@ extern "C" int yp_nhwc_to_nchw(const YpView* in, int32_t C, float* out, void* st
 
 extern "C" int yp_sppf_pool(const YpView* cat4, void* stream) {
   YP_REQUIRE(cat4 && cat4->base, YP_ERR_ARG, "sppf_pool: null view");
-  YP_REQUIRE(cat4->C % 4 == 0, YP_ERR_SHAPE, "sppf_pool: concat buffer channels %d not a multiple of 4", cat4->C);
+  YP_REQUIRE(cat4->C % 4 == 0 && (cat4->C / 4) % yp::SPPF_G == 0, YP_ERR_SHAPE, "sppf_pool: concat buffer channels %d not a multiple of %d", cat4->C, 4 * yp::SPPF_G);
   const int C = cat4->C / 4;
-  const int64_t total = static_cast<int64_t>(cat4->B) * cat4->H * cat4->W * C;
-  yp::sppf_pool_kernel<<<static_cast<unsigned>(yp::ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*cat4, C);
+  const int HW = cat4->H * cat4->W;
+  YP_REQUIRE(HW <= 65535, YP_ERR_SHAPE, "sppf_pool: feature map %dx%d too large", cat4->H, cat4->W);
+  const size_t smem = static_cast<size_t>(HW) * yp::SPPF_G * (2 * sizeof(float) + 2 * sizeof(unsigned short));
+  YP_REQUIRE(smem <= 200 * 1024, YP_ERR_SHAPE, "sppf_pool: feature map %dx%d needs %zu bytes of shared memory", cat4->H, cat4->W, smem);
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    YP_CUDA_OK(cudaFuncSetAttribute(yp::sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  yp::sppf_pool_kernel<<<dim3(C / yp::SPPF_G, cat4->B), 256, smem, static_cast<cudaStream_t>(stream)>>>(*cat4, C);
   YP_LAUNCH_OK();
   return YP_OK;
 }

@@ -385,15 +385,19 @@ class ShapePlan:
         else:
             _lib.check(L.yp_nchw_to_s2d(self.x_in.data_ptr(), self.B, self.H, self.W, C.byref(v), self._stream()))
 
-    def run_net(self):
+    def run_net(self, tails=None):
         """Launch list; the keypoint and descriptor heads run on side streams that fork from / join the current stream
-        (also under graph capture), so their small grids overlap the detection branch."""
+        (also under graph capture), so their small grids overlap the detection branch.  ``tails`` maps a lane to a
+        callable(stream_ptr) enqueued on that lane's stream after its last layer (e.g. heatmap + keypoint NMS)."""
+        tails = tails or {}
         dev = self.eng.device
         main = torch.cuda.current_stream(dev)
         if not self.eng.multi_stream:
             st = C.c_void_p(main.cuda_stream)
             for _, f in self.launches:
                 f(st)
+            for lane in sorted(tails):
+                tails[lane](st)
             return
         if self._side is None:
             self._side = {1: torch.cuda.Stream(dev), 2: torch.cuda.Stream(dev)}
@@ -408,6 +412,8 @@ class ShapePlan:
                 ptr[lane] = C.c_void_p(self._side[lane].cuda_stream)
             f(ptr[lane])
         for lane in started:
+            if lane in tails:
+                tails[lane](ptr[lane])
             ev = torch.cuda.Event()
             ev.record(self._side[lane])
             main.wait_event(ev)

@@ -65,7 +65,15 @@ class FramePipeline:
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         B, H, W, cfg = self.B, self.H, self.W, self.cfg
         p.run_input(from_frame)
-        p.run_net()
+        semi = p.bufs["semi"][0]   # [B,Hc,Wc,80] fp32 NHWC
+        sB, sH, sW, sC = semi.stride()
+
+        def kp_tail(stp):   # runs on the keypoint head's stream, overlapping the detection branch
+            _lib.check(L.yp_heatmap(semi.data_ptr(), B, H // 8, W // 8, sB, sC, sH, sW, self.heat_variant, self.heat.data_ptr(), stp))
+            _lib.check(L.yp_keypoints_nms(self.heat.data_ptr(), B, H, W, float(cfg["detection_threshold"]), int(cfg["nms"]), self.max_pts,
+                                          self.ws_kp.data_ptr(), self.ws_kp.numel(), stp))
+
+        p.run_net(tails={1: kp_tail})
         # Detect decode fused into the NMS front end: pred [B,A,85] is never materialised here
         dets = [p.bufs[f"det{i}"] for i in range(3)]
         lg = (C.c_void_p * 3)(*[d.data_ptr() for d in dets])
@@ -75,13 +83,10 @@ class FramePipeline:
         anc = (C.c_float * 18)(*[float(v) for row in self.eng.anchors_px for v in row])
         _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, self.eng.net.no, C.byref(self.nms_params), self.nms_cap,
                                    self.boxes.data_ptr(), self.bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), st))
-        semi = p.bufs["semi"][0]   # [B,Hc,Wc,80] fp32 NHWC
-        sB, sH, sW, sC = semi.stride()
-        _lib.check(L.yp_heatmap(semi.data_ptr(), B, H // 8, W // 8, sB, sC, sH, sW, self.heat_variant, self.heat.data_ptr(), st))
-        _lib.check(L.yp_keypoints(self.heat.data_ptr(), B, H, W, float(cfg["detection_threshold"]), int(cfg["nms"]), 4,
-                                  self.boxes.data_ptr() if self.filter_pts else None, self.bcount.data_ptr() if self.filter_pts else None,
-                                  self.boxes.shape[1] if self.filter_pts else 0, self.pts[k].data_ptr(), self.kcount[k].data_ptr(), self.max_pts,
-                                  self.ws_kp.data_ptr(), self.ws_kp.numel(), st))
+        _lib.check(L.yp_keypoints_collect(self.heat.data_ptr(), B, H, W, 4, self.boxes.data_ptr() if self.filter_pts else None,
+                                          self.bcount.data_ptr() if self.filter_pts else None, self.boxes.shape[1] if self.filter_pts else 0,
+                                          self.pts[k].data_ptr(), self.kcount[k].data_ptr(), self.max_pts, self.ws_kp.data_ptr(),
+                                          self.ws_kp.numel(), st))
         desc = p.bufs["desc"][0]   # [B,Hc,Wc,D] fp32 NHWC, unit norm
         dB, dH, dW, dD = desc.stride()
         _lib.check(L.yp_sample_desc(desc.data_ptr(), B, self.D, H // 8, W // 8, dB, dD, dH, dW, H, W, self.pts[k].data_ptr(),
