@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, help="independent camera streams (frame pipelines) in flight per GPU")
     args = ap.parse_args()
     version, H, W, per_gpu = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,8 +165,12 @@ def main():
     model, sd = build_weights(version)
     model.precision = args.precision
     model = model.to(dev).eval()
-    pipe = FramePipeline(model, per_gpu, H, W, max_pts=4096, nms_cap=4096)
+    NS = max(1, args.streams)
+    pipes = [FramePipeline(model, per_gpu, H, W, max_pts=4096, nms_cap=4096, slot=i) for i in range(NS)]
+    cuda_streams = [torch.cuda.Stream(dev) for _ in range(NS)]
+    pipe = pipes[0]
     plan = pipe.plan
+    config["streams_per_gpu"] = NS
 
     # input pool larger than L2 (126 MB): every step reads a different frame batch from HBM
     frame_bytes = per_gpu * H * W * 3
@@ -183,8 +188,19 @@ def main():
         torch.cuda.synchronize(dev)
 
     def step(i):
-        plan.frame_in.copy_(pool[i % n_pool])
-        pipe.step_device(True)
+        """One step = every camera stream processes its next frame batch (independent graphs on independent CUDA streams)."""
+        if NS == 1:
+            plan.frame_in.copy_(pool[i % n_pool])
+            pipe.step_device(True)
+            return
+        cur = torch.cuda.current_stream(dev)
+        for s_i, (pp, cs) in enumerate(zip(pipes, cuda_streams)):
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                pp.plan.frame_in.copy_(pool[(i * NS + s_i) % n_pool])
+                pp.step_device(True)
+        for cs in cuda_streams:
+            cur.wait_stream(cs)
 
     for i in range(Wm):
         step(i)
@@ -201,7 +217,7 @@ def main():
     ms = e0.elapsed_time(e1)
     sampler.stop_flag = True
     sampler.join()
-    launches = K * (pipe.n_launches())
+    launches = K * NS * (pipe.n_launches())
 
     # ---- dominant kernel: conv launches only, timed live with events on the launching stream
     def net_only():
@@ -218,19 +234,29 @@ def main():
     torch.cuda.synchronize(dev)
     net_ms = n0.elapsed_time(n1) / reps
     n_conv = len(model.engine().net.conv_ops())
-    flops_step = CONV_GFLOP[args.workload] * 1e9 * per_gpu
+    flops_step = CONV_GFLOP[args.workload] * 1e9 * per_gpu   # one pipeline's conv launches (timed alone, below)
     achieved_tf = flops_step / (net_ms * 1e-3) / 1e12
 
     # ---- end to end through the public host API
     host_frames = [np.stack([np.roll(base[(i + b) % 4], (5 * i) % W, axis=1) for b in range(per_gpu)]) for i in range(8)]
-    pipe.reset_tracking()
+    for pp in pipes:
+        pp.reset_tracking()
+
+    def host_step(i):
+        if NS == 1:
+            return pipe.step_host(host_frames[i % 8])
+        for s_i, (pp, cs) in enumerate(zip(pipes, cuda_streams)):
+            with torch.cuda.stream(cs):
+                pp.submit_host(host_frames[(i * NS + s_i) % 8])
+        return [pp.collect() for pp in pipes][0]
+
     for i in range(3):
-        pipe.step_host(host_frames[i % 8])
+        host_step(i)
     barrier()
     t0 = time.perf_counter()
     Ke = min(K, 100)
     for i in range(Ke):
-        res = pipe.step_host(host_frames[i % 8])
+        res = host_step(i)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     kp_n, box_n, match_n = res[0][0].shape[1], res[0][2].shape[0], res[0][3].shape[1]
@@ -244,13 +270,13 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    fps = K * per_gpu * world / (ms * 1e-3)
+    fps = K * NS * per_gpu * world / (ms * 1e-3)
     line = {"metric": "frames/sec end-to-end (backbone+heads+NMS+match)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (3xTF32 tensor-core MMA, fp32 accumulate)" if args.precision == "fp32" else "bf16",
             "data": "synthetic", "config": config, "clocks": sampler.summary(), "gpu_launches": launches,
-            "e2e": {"value": Ke * per_gpu * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
-                    "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": Ke},
+            "e2e": {"value": Ke * NS * per_gpu * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": NS * pipe.h2d_bytes(),
+                    "d2h_bytes_per_step": NS * pipe.d2h_bytes(), "steps": Ke},
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved_tf, "peak": peaks["tf"],
                          "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained",
                          "launches_per_step": n_conv, "avg_launch_us": net_ms * 1e3 / n_conv, "algorithmic_gflop_per_step": flops_step / 1e9,

@@ -399,13 +399,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const float* p = a.ws_partial + (tile_id * 128 + row) * a.Nt + col;
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = 0.0f;
-      for (int z = 0; z < S; ++z) {
-        const float4* p4 = reinterpret_cast<const float4*>(p + z * n_tiles_all * 128 * a.Nt);
+      const long long zstride = n_tiles_all * 128 * a.Nt;
+      for (int z0 = 0; z0 < S; z0 += 4) {   // four slices (16 x 16-byte loads) in flight per thread; summed in z order
+        float4 f[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 f = __ldcg(p4 + j);
-          v[j * 4] += f.x; v[j * 4 + 1] += f.y; v[j * 4 + 2] += f.z; v[j * 4 + 3] += f.w;
+        for (int zz = 0; zz < 4; ++zz) {
+          const float4* p4 = reinterpret_cast<const float4*>(p + (z0 + zz) * zstride);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f[zz][j] = (z0 + zz < S) ? __ldcg(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int zz = 0; zz < 4; ++zz)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { v[j * 4] += f[zz][j].x; v[j * 4 + 1] += f[zz][j].y; v[j * 4 + 2] += f[zz][j].z; v[j * 4 + 3] += f[zz][j].w; }
       }
     };
     auto finish = [&](float acc, int col, float res) -> float {
@@ -674,10 +680,8 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   P->units = chunk_elems / 16;
   a.staging_set_bytes = a.out_planes * 128 * a.out_row_bytes;
 
-  // ---- N tile and split-K.  Measured on B200: the TMA engine of an SM delivers one 128-byte operand row every ~4 cycles
-  // (~60 GB/s per SM), which -- not the tensor pipe -- bounds these layers.  So (i) take the largest N tile (operand rows per
-  // MAC fall with Nt: the A tile is re-read once per N tile), (ii) when the tiles cannot occupy every SM, slice K over
-  // grid.z CTAs (each SM brings its own TMA engine) and let the last CTA of a tile reduce the partial sums.
+  // ---- N tile: the largest divisor of Cout (<= 128 in 3xTF32 mode so that [W_hi; W_lo] stacks into one N <= 256 MMA) that
+  // still yields >= #SM CTAs; when the layer cannot fill the GPU anyway, the smallest tile >= 32 (latency).
   const int m_tiles = a.tiles_w * a.tiles_h * in.B;
   const int nsm = sm_count();
   int Nt = 0;
@@ -686,19 +690,26 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
     Nt = d.cout;
   } else {
     const int nmax = tf32 ? 128 : 256;
-    for (int n = nmax; n >= chunk_elems && Nt == 0; n -= 16)
-      if (d.cout % n == 0 && n % chunk_elems == 0) Nt = n;
+    int smallest = 0;
+    for (int n = nmax; n >= chunk_elems; n -= 16) {
+      if (d.cout % n || n % chunk_elems) continue;
+      smallest = n;
+      if (Nt == 0 && m_tiles * (d.cout / n) >= nsm) Nt = n;
+      if (n <= 32 && smallest) break;
+    }
+    if (Nt == 0) Nt = smallest;
   }
   YP_REQUIRE(Nt >= 16 && Nt % 16 == 0 && Nt <= 256, YP_ERR_SHAPE, "conv: no valid N tile for Cout=%d", d.cout);
   a.Nt = Nt;
   const int n_tiles = d.cout / Nt;
 
+  // ---- split-K: deep layers on small feature maps occupy few CTAs; slice K over grid.z so that ~#SM CTAs are busy.
   int S = 1;
   if (allow_split && !(d.epilogue & YP_EPI_L2NORM) && d.split_k != 1) {
     const int ctas = m_tiles * n_tiles;
     int want = d.split_k > 1 ? d.split_k : nsm / ctas;
-    if (want > 16) want = 16;
-    if (want > num_kb / 2) want = num_kb / 2;     // every slice keeps >= 2 k-blocks
+    if (want > 8) want = 8;
+    if (want > num_kb / 4) want = num_kb / 4;     // every slice keeps >= 4 k-blocks
     if (want >= 2) S = want;
   }
   a.kb_per_split = ceil_div(num_kb, S);

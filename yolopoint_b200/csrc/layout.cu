@@ -102,7 +102,7 @@ __global__ void nhwc_to_nchw_kernel(YpView in, int C, float* __restrict__ out) {
 // One CTA owns G channels of one image: stage the (value, source pixel) pairs of the whole map, run the three
 // pooling passes ping-pong between two shared buffers and copy the operand planes of the winning source pixel into
 // concat slices 1..3, so the stored (hi, lo) pairs are bit-identical to the source element's.
-constexpr int SPPF_G = 8;
+constexpr int SPPF_G = 2;   // channels per CTA: small groups -> C/2 CTAs per image (the map is tiny, parallelism comes from channels)
 
 __global__ void __launch_bounds__(256) sppf_pool_kernel(YpView cat4, int C) {
   extern __shared__ unsigned char sp_smem[];

@@ -477,8 +477,10 @@ class Engine:
             self.weights[op.names] = (w.to(self.device), None if b is None else b.to(self.device))
         self.plans: Dict[Tuple[int, int, int], ShapePlan] = {}
 
-    def plan(self, B: int, H: int, W: int) -> ShapePlan:
-        key = (B, H, W)
+    def plan(self, B: int, H: int, W: int, slot: int = 0) -> ShapePlan:
+        """Buffers + launch list for one input shape; `slot` selects an independent copy (own activation buffers, own
+        graphs) so that several frames can be in flight on different streams."""
+        key = (B, H, W, slot)
         if key not in self.plans:
             self.plans[key] = ShapePlan(self, B, H, W)
         return self.plans[key]

@@ -28,10 +28,10 @@ class FramePipeline:
     """Static buffers + graphs for frames of one shape.  All results stay on the device until ``fetch``."""
 
     def __init__(self, model, B: int, H: int, W: int, cfg: Optional[dict] = None, filter_pts: bool = True, max_pts: int = 4096,
-                 nms_cap: int = 4096, heat_variant: int = 1, do_match: bool = True):
+                 nms_cap: int = 4096, heat_variant: int = 1, do_match: bool = True, slot: int = 0):
         self.cfg = dict(DEFAULT_CFG, **(cfg or {}))
         self.eng = model.engine() if hasattr(model, "engine") else model
-        self.plan = self.eng.plan(B, H, W)
+        self.plan = self.eng.plan(B, H, W, slot)
         self.B, self.H, self.W = B, H, W
         self.filter_pts, self.max_pts, self.nms_cap, self.heat_variant, self.do_match = filter_pts, max_pts, (nms_cap + 63) // 64 * 64, heat_variant, do_match
         dev, D = self.eng.device, self.eng.net.D
@@ -133,8 +133,8 @@ class FramePipeline:
         self.parity = 0
 
     # ---- host boundary -------------------------------------------------------------------------
-    def step_host(self, frames_u8: np.ndarray):
-        """frames [B,H,W,3] uint8 on the host -> per-image (pts[3,N] f64, desc[D,N] f32, boxes[n,6] f32, matches[3,L] f64)."""
+    def submit_host(self, frames_u8: np.ndarray):
+        """Enqueue (on the current stream) H2D of the frames, the whole pipeline and the D2H of the compact results."""
         dev = self.eng.device
         self.h_frame.copy_(torch.from_numpy(np.ascontiguousarray(frames_u8)).view(self.B, self.H, self.W, 3))
         self.plan.frame_in.copy_(self.h_frame, non_blocking=True)
@@ -144,7 +144,12 @@ class FramePipeline:
         self.h_boxes.copy_(self.boxes, non_blocking=True)
         self.h_desc.copy_(self.descs[k], non_blocking=True)
         self.h_matches.copy_(self.matches, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        self._done = torch.cuda.Event()
+        self._done.record(torch.cuda.current_stream(dev))
+
+    def collect(self):
+        """Wait for the last submit_host and unpack per-image (pts[3,N] f64, desc[D,N] f32, boxes[n,6] f32, matches[3,L] f64)."""
+        self._done.synchronize()
         out = []
         for b in range(self.B):
             nk, nb, nm = (int(v) for v in self.h_counts[:, b])
@@ -156,6 +161,11 @@ class FramePipeline:
             matches = self.h_matches[b, :max(nm, 0)].numpy().astype(np.float64).T.copy()
             out.append((pts, desc, boxes, matches))
         return out
+
+    def step_host(self, frames_u8: np.ndarray):
+        """frames [B,H,W,3] uint8 on the host -> per-image (pts, desc, boxes, matches); one H2D, one D2H, one sync."""
+        self.submit_host(frames_u8)
+        return self.collect()
 
     def d2h_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.h_counts, self.h_pts, self.h_boxes, self.h_desc, self.h_matches))
