@@ -97,6 +97,7 @@ typedef struct {
   int32_t n_out;          /* 1 or 2 */
   YpView out[2];
   int32_t algo;           /* YpConvAlgo */
+  int32_t tile_n;         /* 0 = library heuristic; else the N (output-channel) tile: a divisor of cout, multiple of 16, <= 128 (fp32) / 256 (bf16) */
   int32_t split_k;        /* 0 = let the library slice K over several CTAs when the layer cannot fill the GPU, 1 = never, n = n slices */
   void* workspace;        /* split-K scratch (zero-initialised once by the caller, reusable by later launches on the same
                              stream; launches that may run concurrently need distinct workspaces); NULL -> never split */

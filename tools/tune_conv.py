@@ -1,0 +1,101 @@
+"""Per-layer autotuning of the tcgen05 conv launch parameters (N tile, split-K factor) on the GPU box.
+
+  python tools/tune_conv.py [--version s] [--size 640 640] [--batch 1] [--precision fp32]
+
+Times every conv layer of the network (real buffers / weights of a ShapePlan) for each valid (tile_n, split_k) with
+CUDA events over a captured graph of back-to-back launches and writes yolopoint_b200/tuning/<cfg>.json, which the engine
+loads at plan time.  The network has only ~33 distinct conv shapes, so the table is small."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from yolopoint_b200 import Model, _lib  # noqa: E402
+from yolopoint_b200.engine import tuning_path  # noqa: E402
+from yolopoint_b200.synth import perturb_state_dict  # noqa: E402
+
+
+def time_desc(L, d, reps=20):
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        sp = C.c_void_p(st.cuda_stream)
+        for _ in range(2):
+            rc = L.yp_conv2d_nhwc_fwd(C.byref(d), sp)
+            if rc != 0:
+                return None
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                L.yp_conv2d_nhwc_fwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        g.replay()
+        st.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            g.replay()
+            e1.record(st)
+            st.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--version", default="s")
+    ap.add_argument("--size", type=int, nargs=2, default=[640, 640])
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    H, W = args.size
+    L = _lib.lib(require_device=True)
+    torch.manual_seed(0)
+    m = Model(names=[str(i) for i in range(80)], version=args.version, precision=args.precision)
+    m.load_state_dict(perturb_state_dict(m.state_dict(), 0, args.version))
+    m = m.cuda().eval()
+    eng = m.engine()
+    eng.use_tuning = False
+    plan = eng.plan(args.batch, H, W)
+    scratch = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
+    nmax = 128 if args.precision == "fp32" else 256
+    table, report, seen = {}, [], {}
+    for op, d in plan.conv_descs:
+        name = "+".join(op.names)
+        sig = (op.k, op.s, op.src.C, op.cout, d.in_.H, d.in_.W, op.residual is not None, len(op.dst), tuple(x.upsample for x in op.dst), op.l2norm, d.out[0].format)
+        if sig in seen:
+            table[name] = seen[sig]
+            continue
+        d.workspace, d.workspace_bytes = scratch.data_ptr(), scratch.numel()
+        d.tile_n, d.split_k = 0, 0
+        base = time_desc(L, d)
+        best = (base, 0, 0)
+        tiles = [0] if op.l2norm else [n for n in range(16, nmax + 1, 16) if op.cout % n == 0]
+        for tn in tiles:
+            for sk in ([1] if op.l2norm else [1, 2, 3, 4, 6, 8, 12, 16]):
+                d.tile_n, d.split_k = tn, sk
+                t = time_desc(L, d)
+                if t is not None and t < best[0]:
+                    best = (t, tn, sk)
+        seen[sig] = table[name] = [best[1], best[2]]
+        report.append((name, base, best))
+        print(f"{name:40s} k{op.k}s{op.s} Cin{op.src.C:4d} Cout{op.cout:4d} {d.in_.H:3d}x{d.in_.W:<3d}  heuristic {base:7.2f} us -> best {best[0]:7.2f} us  tile_n={best[1]} split_k={best[2]}", flush=True)
+    tot_base = sum(r[1] for r in report)
+    tot_best = sum(r[2][0] for r in report)
+    print(f"distinct shapes {len(report)}; sum heuristic {tot_base:.1f} us, sum tuned {tot_best:.1f} us")
+    out = args.out or tuning_path(args.version, args.batch, H, W, args.precision)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with open(out, "w") as f:
+        json.dump({"device": torch.cuda.get_device_name(0), "config": vars(args), "layers": table}, f, indent=1)
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

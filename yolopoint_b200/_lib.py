@@ -29,7 +29,7 @@ class YpView(C.Structure):
 class YpConvDesc(C.Structure):
     _fields_ = [("in_", YpView), ("weight", C.c_void_p), ("bias", C.c_void_p), ("ksize", C.c_int32), ("stride", C.c_int32),
                 ("cout", C.c_int32), ("act", C.c_int32), ("epilogue", C.c_uint32), ("residual", YpView), ("n_out", C.c_int32),
-                ("out", YpView * 2), ("algo", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p),
+                ("out", YpView * 2), ("algo", C.c_int32), ("tile_n", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_uint64)]
 
 

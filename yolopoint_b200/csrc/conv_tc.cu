@@ -688,6 +688,10 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   if (d.epilogue & YP_EPI_L2NORM) {
     YP_REQUIRE(d.cout <= 256, YP_ERR_SHAPE, "conv: L2-norm epilogue needs Cout <= 256 (got %d)", d.cout);
     Nt = d.cout;
+  } else if (d.tile_n > 0) {
+    YP_REQUIRE(d.tile_n % chunk_elems == 0 && d.cout % d.tile_n == 0 && d.tile_n <= (tf32 ? 128 : 256), YP_ERR_SHAPE,
+               "conv: tile_n=%d invalid for Cout=%d (store chunk %d)", d.tile_n, d.cout, chunk_elems);
+    Nt = d.tile_n;
   } else {
     const int nmax = tf32 ? 128 : 256;
     int smallest = 0;
@@ -708,8 +712,11 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   if (allow_split && !(d.epilogue & YP_EPI_L2NORM) && d.split_k != 1) {
     const int ctas = m_tiles * n_tiles;
     int want = d.split_k > 1 ? d.split_k : nsm / ctas;
-    if (want > 8) want = 8;
-    if (want > num_kb / 4) want = num_kb / 4;     // every slice keeps >= 4 k-blocks
+    if (want > 16) want = 16;
+    if (d.split_k <= 1) {                         // heuristic: at most 8 slices of >= 4 k-blocks
+      if (want > 8) want = 8;
+      if (want > num_kb / 4) want = num_kb / 4;
+    } else if (want > num_kb) want = num_kb;
     if (want >= 2) S = want;
   }
   a.kb_per_split = ceil_div(num_kb, S);

@@ -2,10 +2,6 @@
 // (utils/utils.py:118-182, 232-262, 465-485 and demo.py:138-198 of the reference).
 #include "common.cuh"
 
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
-
 namespace yp {
 namespace {
 
@@ -56,7 +52,7 @@ __global__ void heatmap_kernel(const float* __restrict__ semi, int B, int Hc, in
 // ------------------------------------------------------------------------------------------------
 struct KpWs {
   unsigned char* state;        // [B*H*W]
-  unsigned int* remaining;     // [3]
+  unsigned int* tile_undecided;  // [B * tiles]
   int* n_list;                 // [B]
   unsigned long long* list;    // [B][max_pts]  (ordered_conf << 32) | raster index
 };
@@ -70,130 +66,167 @@ __device__ __forceinline__ float unordered_bits(unsigned int o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
-// Tile-local formulation.  Each CTA owns 32x32-pixel tiles; per global round it loads the tile plus an r-wide halo of
-// states into shared memory, sorts the tile's undecided candidates by priority (rank sort) and lets one warp resolve
-// them IN PRIORITY ORDER -- inside a tile that is the reference's sequential scan, so long dependency chains cost
-// shared-memory latency, not grid barriers.  Only decisions that depend on a still-undecided halo candidate of a
-// neighbouring tile are deferred to the next round (cooperative grid barrier in between).
+// Tile-local formulation.  Each CTA owns a 32x32-pixel tile; per round it loads the tile plus an r-wide halo of states
+// into shared memory, sorts the tile's undecided candidates by priority (rank sort) and lets one warp resolve them IN
+// PRIORITY ORDER -- inside a tile that is the reference's sequential scan, so long dependency chains cost shared-memory
+// latency.  Only decisions that depend on a still-undecided halo candidate of a neighbouring tile are deferred to the
+// next round.  Rounds are separate (ordinary, non-cooperative) launches, so any number of these pipelines can run
+// concurrently on one GPU; tiles without undecided candidates exit at once; a final single-CTA kernel sweeps until
+// nothing is undecided, which bounds the launch count without giving up exactness.
 constexpr int KT = 32;       // tile edge
 constexpr int KR_MAX = 16;   // largest supported nms_dist
+constexpr int KP_ROUNDS = 8; // parallel rounds before the sequential sweep (dense noise needs ~7)
 
-__global__ void __launch_bounds__(256) kp_nms_kernel(const float* __restrict__ heat, int B, int H, int W, float thr, int r, KpWs ws) {
-  cg::grid_group grid = cg::this_grid();
-  extern __shared__ unsigned char kp_smem[];
+struct KpTileSmem {
+  float* sheat; unsigned long long* keys; unsigned short* cand; unsigned short* sorted; unsigned char* sstate; int* n_list;
+};
+
+// One round for tile t.  Returns (to thread 0 only... every thread gets its partial) the number of still-undecided
+// interior candidates counted by this thread.
+__device__ unsigned int kp_process_tile(const float* __restrict__ heat, int B, int H, int W, float thr, int r, const KpWs& ws, int t,
+                                        bool first, const KpTileSmem& sm) {
   const int RW = KT + 2 * r, RN = RW * RW;
-  float* sheat = reinterpret_cast<float*>(kp_smem);
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(kp_smem + ((RN * 4 + 7) & ~7));
-  unsigned short* cand = reinterpret_cast<unsigned short*>(keys + KT * KT);
-  unsigned short* sorted = cand + KT * KT;
-  unsigned char* sstate = reinterpret_cast<unsigned char*>(sorted + KT * KT);
-  __shared__ int n_list;
   const int tiles_x = (W + KT - 1) / KT, tiles_y = (H + KT - 1) / KT;
-  const int T = B * tiles_x * tiles_y;
   const int64_t HW = static_cast<int64_t>(H) * W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int win = 2 * r + 1;
-  // One tile per CTA (the common case): heat, states and the sorted candidate list stay in shared memory for all rounds;
-  // later rounds only refresh the halo states and revisit the still-undecided candidates.
-  const bool resident = T <= static_cast<int>(gridDim.x);
-  int n_sorted = 0;
+  const int b = t / (tiles_x * tiles_y);
+  const int tr = t - b * tiles_x * tiles_y;
+  const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+  const int y0 = ty * KT - r, x0 = tx * KT - r;
+  const float* hb = heat + b * HW;
+  unsigned char* sb = ws.state + b * HW;
+  for (int c = threadIdx.x; c < RN; c += blockDim.x) {
+    const int ly = c / RW, lx = c - ly * RW;
+    const int gy = y0 + ly, gx = x0 + lx;
+    const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    const float h = inside ? hb[gy * W + gx] : -INFINITY;
+    sm.sheat[c] = h;
+    unsigned char st = 0;
+    if (inside) st = first ? (h >= thr ? 1 : 0) : __ldcg(sb + gy * W + gx);
+    sm.sstate[c] = st;
+  }
+  if (threadIdx.x == 0) *sm.n_list = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
+    const int ly = c / KT + r, lx = c % KT + r;
+    const int cell = ly * RW + lx;
+    if (sm.sstate[cell] == 1) {
+      const int slot = atomicAdd(sm.n_list, 1);
+      const unsigned int raster = static_cast<unsigned int>((y0 + ly) * W + (x0 + lx));
+      sm.keys[slot] = (static_cast<unsigned long long>(ordered_bits(sm.sheat[cell])) << 32) | (0xffffffffu - raster);
+      sm.cand[slot] = static_cast<unsigned short>(cell);
+    }
+  }
+  __syncthreads();
+  const int n = *sm.n_list;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {  // rank sort, descending priority (keys are unique)
+    const unsigned long long ki = sm.keys[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += sm.keys[j] > ki ? 1 : 0;
+    sm.sorted[rank] = sm.cand[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int i = 0; i < n; ++i) {
+      const int p = sm.sorted[i];
+      const int py = p / RW, px = p - py * RW;
+      const float hp = sm.sheat[p];
+      const int gp = (y0 + py) * W + (x0 + px);
+      bool kept = false, pend = false;
+      for (int idx = lane; idx < win * win; idx += 32) {
+        const int dy = idx / win - r, dx = idx % win - r;
+        const int q = (py + dy) * RW + (px + dx);
+        const unsigned char sq = sm.sstate[q];
+        if (sq == 2) kept = true;
+        else if (sq == 1 && q != p) {
+          const float hq = sm.sheat[q];
+          const int gq = (y0 + py + dy) * W + (x0 + px + dx);
+          if (hq > hp || (hq == hp && gq < gp)) pend = true;
+        }
+      }
+      kept = __any_sync(0xffffffffu, kept);
+      pend = __any_sync(0xffffffffu, pend);
+      if (lane == 0) sm.sstate[p] = kept ? 3 : (pend ? 1 : 2);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  unsigned int undecided = 0;
+  if (first) {   // publish the whole interior: neighbours read the candidates' states from global memory in later rounds
+    for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
+      const int ly = c / KT + r, lx = c % KT + r;
+      const int gy = y0 + ly, gx = x0 + lx;
+      if (gy < H && gx < W) {
+        const unsigned char st = sm.sstate[ly * RW + lx];
+        sb[gy * W + gx] = st;
+        undecided += st == 1 ? 1u : 0u;
+      }
+    }
+  } else {       // later rounds: only the candidates that were undecided can have changed
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int p = sm.sorted[i];
+      const int py = p / RW, px = p - py * RW;
+      const unsigned char st = sm.sstate[p];
+      if (st != 1) sb[(y0 + py) * W + (x0 + px)] = st; else ++undecided;
+    }
+  }
+  __syncthreads();
+  return undecided;
+}
 
-  for (int round = 0;; ++round) {
-    unsigned int undecided = 0;
-    for (int t = blockIdx.x; t < T; t += gridDim.x) {
-      const int b = t / (tiles_x * tiles_y);
-      const int tr = t - b * tiles_x * tiles_y;
-      const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
-      const int y0 = ty * KT - r, x0 = tx * KT - r;
-      const float* hb = heat + b * HW;
-      unsigned char* sb = ws.state + b * HW;
-      const bool fresh = round == 0 || !resident;
-      for (int c = threadIdx.x; c < RN; c += blockDim.x) {
-        const int ly = c / RW, lx = c - ly * RW;
-        const int gy = y0 + ly, gx = x0 + lx;
-        const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        if (fresh) {
-          const float h = inside ? hb[gy * W + gx] : -INFINITY;
-          sheat[c] = h;
-          unsigned char st = 0;
-          if (inside) st = round == 0 ? (h >= thr ? 1 : 0) : __ldcg(sb + gy * W + gx);
-          sstate[c] = st;
-        } else {
-          const bool halo = ly < r || ly >= r + KT || lx < r || lx >= r + KT;
-          if (halo && inside && sstate[c] == 1) sstate[c] = __ldcg(sb + gy * W + gx);   // only undecided halo cells can change
-        }
-      }
-      if (threadIdx.x == 0 && fresh) n_list = 0;
+__device__ __forceinline__ KpTileSmem kp_carve(unsigned char* base, int r, int* n_list) {
+  const int RW = KT + 2 * r, RN = RW * RW;
+  KpTileSmem sm;
+  sm.sheat = reinterpret_cast<float*>(base);
+  sm.keys = reinterpret_cast<unsigned long long*>(base + ((RN * 4 + 7) & ~7));
+  sm.cand = reinterpret_cast<unsigned short*>(sm.keys + KT * KT);
+  sm.sorted = sm.cand + KT * KT;
+  sm.sstate = reinterpret_cast<unsigned char*>(sm.sorted + KT * KT);
+  sm.n_list = n_list;
+  return sm;
+}
+
+// ws.tile_undecided[t]: undecided interior candidates of tile t after its last processed round
+__global__ void __launch_bounds__(256) kp_round_kernel(const float* __restrict__ heat, int B, int H, int W, float thr, int r, KpWs ws, int first) {
+  extern __shared__ unsigned char kp_smem[];
+  __shared__ int n_list;
+  __shared__ unsigned int total;
+  const int t = blockIdx.x;
+  if (!first && ws.tile_undecided[t] == 0) return;
+  const KpTileSmem sm = kp_carve(kp_smem, r, &n_list);
+  if (threadIdx.x == 0) total = 0;
+  unsigned int u = kp_process_tile(heat, B, H, W, thr, r, ws, t, first != 0, sm);
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) u += __shfl_xor_sync(0xffffffffu, u, sft);
+  if ((threadIdx.x & 31) == 0 && u) atomicAdd(&total, u);
+  __syncthreads();
+  if (threadIdx.x == 0) ws.tile_undecided[t] = total;
+}
+
+// sequential safety net: one CTA sweeps the tiles that still have undecided candidates until none is left
+__global__ void __launch_bounds__(256) kp_sweep_kernel(const float* __restrict__ heat, int B, int H, int W, float thr, int r, KpWs ws, int T) {
+  extern __shared__ unsigned char kp_smem[];
+  __shared__ int n_list;
+  __shared__ unsigned int total, any;
+  const KpTileSmem sm = kp_carve(kp_smem, r, &n_list);
+  for (;;) {
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+      if (ws.tile_undecided[t] == 0) continue;   // uniform: written by thread 0 before a barrier, read after it
+      if (threadIdx.x == 0) total = 0;
+      unsigned int u = kp_process_tile(heat, B, H, W, thr, r, ws, t, false, sm);
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) u += __shfl_xor_sync(0xffffffffu, u, sft);
+      if ((threadIdx.x & 31) == 0 && u) atomicAdd(&total, u);
       __syncthreads();
-      if (fresh) {
-        for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
-          const int ly = c / KT + r, lx = c % KT + r;
-          const int cell = ly * RW + lx;
-          if (sstate[cell] == 1) {
-            const int slot = atomicAdd(&n_list, 1);
-            const unsigned int raster = static_cast<unsigned int>((y0 + ly) * W + (x0 + lx));
-            keys[slot] = (static_cast<unsigned long long>(ordered_bits(sheat[cell])) << 32) | (0xffffffffu - raster);
-            cand[slot] = static_cast<unsigned short>(cell);
-          }
-        }
-        __syncthreads();
-        const int n = n_list;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {  // rank sort, descending priority (keys are unique)
-          const unsigned long long ki = keys[i];
-          int rank = 0;
-          for (int j = 0; j < n; ++j) rank += keys[j] > ki ? 1 : 0;
-          sorted[rank] = cand[i];
-        }
-        n_sorted = n;
-        __syncthreads();
-      }
-      if (warp == 0) {
-        for (int i = 0; i < n_sorted; ++i) {
-          const int p = sorted[i];
-          if (sstate[p] != 1) continue;            // decided in an earlier round (warp-uniform)
-          const int py = p / RW, px = p - py * RW;
-          const float hp = sheat[p];
-          const int gp = (y0 + py) * W + (x0 + px);
-          bool kept = false, pend = false;
-          for (int idx = lane; idx < win * win; idx += 32) {
-            const int dy = idx / win - r, dx = idx % win - r;
-            const int q = (py + dy) * RW + (px + dx);
-            const unsigned char sq = sstate[q];
-            if (sq == 2) kept = true;
-            else if (sq == 1 && q != p) {
-              const float hq = sheat[q];
-              const int gq = (y0 + py + dy) * W + (x0 + px + dx);
-              if (hq > hp || (hq == hp && gq < gp)) pend = true;
-            }
-          }
-          kept = __any_sync(0xffffffffu, kept);
-          pend = __any_sync(0xffffffffu, pend);
-          if (lane == 0) {
-            const unsigned char st = kept ? 3 : (pend ? 1 : 2);
-            sstate[p] = st;
-            if (st != 1 && !fresh) sb[gp] = st;   // resident rounds publish decisions one by one
-          }
-          __syncwarp();
-        }
-      }
-      __syncthreads();
-      if (fresh) {  // publish the whole interior (neighbours read candidates' states from global memory in later rounds)
-        for (int c = threadIdx.x; c < KT * KT; c += blockDim.x) {
-          const int ly = c / KT + r, lx = c % KT + r;
-          const int gy = y0 + ly, gx = x0 + lx;
-          if (gy < H && gx < W) sb[gy * W + gx] = sstate[ly * RW + lx];
-        }
-      }
-      for (int i = threadIdx.x; i < n_sorted; i += blockDim.x) undecided += sstate[sorted[i]] == 1 ? 1u : 0u;
+      if (threadIdx.x == 0) { ws.tile_undecided[t] = total; any |= total; }
+      __threadfence();
       __syncthreads();
     }
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) undecided += __shfl_xor_sync(0xffffffffu, undecided, sft);
-    if (lane == 0 && undecided) atomicAdd(&ws.remaining[round % 3], undecided);
-    if (blockIdx.x == 0 && threadIdx.x == 0) ws.remaining[(round + 1) % 3] = 0;  // next round's slot (last read before the previous barrier)
-    __threadfence();
-    grid.sync();
-    if (*(volatile unsigned int*)&ws.remaining[round % 3] == 0) break;
+    if (any == 0) break;
+    __syncthreads();
   }
 }
 
@@ -273,7 +306,7 @@ size_t carve(KpWs* ws, char* base, int B, int H, int W, int max_pts) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
   ws->state = reinterpret_cast<unsigned char*>(take(static_cast<size_t>(B) * H * W));
-  ws->remaining = reinterpret_cast<unsigned int*>(take(3 * sizeof(unsigned int)));
+  ws->tile_undecided = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * B * ((H + 31) / 32) * ((W + 31) / 32)));
   ws->n_list = reinterpret_cast<int*>(take(sizeof(int) * B));
   ws->list = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * max_pts));
   return off;
@@ -312,23 +345,18 @@ extern "C" int yp_keypoints_nms(const float* heat, int32_t B, int32_t H, int32_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int RW = yp::KT + 2 * nms_dist;
   const size_t nms_smem = ((static_cast<size_t>(RW) * RW * 4 + 7) & ~static_cast<size_t>(7)) + yp::KT * yp::KT * (8 + 2 + 2) + static_cast<size_t>(RW) * RW;
-  static thread_local int coop_per_sm[yp::KR_MAX + 1] = {0};
-  if (coop_per_sm[nms_dist] == 0) {
-    if (nms_smem > 48 * 1024) YP_CUDA_OK(cudaFuncSetAttribute(yp::kp_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    int per_sm = 0;
-    YP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yp::kp_nms_kernel, 256, nms_smem));
-    YP_REQUIRE(per_sm >= 1, YP_ERR_CUDA, "keypoints: NMS kernel does not fit on an SM");
-    coop_per_sm[nms_dist] = per_sm > 4 ? 4 : per_sm;
+  static thread_local bool raised = false;
+  if (nms_smem > 48 * 1024 && !raised) {
+    YP_CUDA_OK(cudaFuncSetAttribute(yp::kp_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    YP_CUDA_OK(cudaFuncSetAttribute(yp::kp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    raised = true;
   }
   const int tiles = B * yp::ceil_div(H, yp::KT) * yp::ceil_div(W, yp::KT);
-  int coop_blocks = coop_per_sm[nms_dist] * yp::sm_count();
-  if (coop_blocks > tiles) coop_blocks = tiles;
-  YP_CUDA_OK(cudaMemsetAsync(ws.remaining, 0, 3 * sizeof(unsigned int), st));
   YP_CUDA_OK(cudaMemsetAsync(ws.n_list, 0, sizeof(int) * B, st));
-  int Bv = B, Hv = H, Wv = W, rv = nms_dist;
-  float thr = conf_thresh;
-  void* args[] = {(void*)&heat, &Bv, &Hv, &Wv, &thr, &rv, &ws};
-  YP_CUDA_OK(cudaLaunchCooperativeKernel((void*)yp::kp_nms_kernel, dim3(coop_blocks), dim3(256), args, nms_smem, st));
+  for (int round = 0; round < yp::KP_ROUNDS; ++round)
+    yp::kp_round_kernel<<<tiles, 256, nms_smem, st>>>(heat, B, H, W, conf_thresh, nms_dist, ws, round == 0 ? 1 : 0);
+  yp::kp_sweep_kernel<<<1, 256, nms_smem, st>>>(heat, B, H, W, conf_thresh, nms_dist, ws, tiles);
+  YP_LAUNCH_OK();
   return YP_OK;
 }
 

@@ -18,6 +18,8 @@ The launch list for a given (B, H, W) is captured into a CUDA graph after the fi
 from __future__ import annotations
 
 import ctypes as C
+import json
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -289,6 +291,22 @@ def pack_conv(sd, op: ConvOp, cin_view: int, precision: str) -> Tuple[torch.Tens
 # --------------------------------------------------------------------------------------------------
 # device side
 # --------------------------------------------------------------------------------------------------
+TUNING_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning")
+
+
+def tuning_path(version: str, B: int, H: int, W: int, precision: str) -> str:
+    return os.path.join(TUNING_DIR, f"{version}_{B}x{H}x{W}_{precision}.json")
+
+
+def load_tuning(version: str, B: int, H: int, W: int, precision: str) -> Dict[str, Tuple[int, int]]:
+    """Per-layer (tile_n, split_k) measured on a B200 by tools/tune_conv.py; absent file -> library heuristics."""
+    p = tuning_path(version, B, H, W, precision)
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        return {k: tuple(v) for k, v in json.load(f).get("layers", {}).items()}
+
+
 _TORCH_DT = {YP_FMT_F32X2: torch.float32, YP_FMT_F32: torch.float32, YP_FMT_BF16: torch.bfloat16}
 _PLANES = {YP_FMT_F32X2: 2, YP_FMT_F32: 1, YP_FMT_BF16: 1}
 
@@ -341,6 +359,8 @@ class ShapePlan:
         L = _lib.lib()
         eng = self.eng
         need, descs = {}, []
+        self.conv_descs = []
+        self.tuning = load_tuning(eng.net.version, self.B, self.H, self.W, eng.precision) if eng.use_tuning else {}
         for op in eng.net.ops:
             if isinstance(op, PoolOp):
                 v = self.view(SliceRef(op.buf, 0, self.bufs[op.buf].shape[-1]))
@@ -361,6 +381,10 @@ class ShapePlan:
                 d.out[i] = self.view(ds)
             d.algo = eng.algo
             d.split_k = 0 if eng.split_k else 1
+            tuned = self.tuning.get("+".join(op.names))
+            if tuned and eng.split_k:
+                d.tile_n, d.split_k = int(tuned[0]), int(tuned[1])
+            self.conv_descs.append((op, d))
             need[op.lane] = max(need.get(op.lane, 0), int(L.yp_conv2d_workspace_bytes(C.byref(d)))) if eng.split_k else 0
             descs.append((op.lane, d))
             self._keep.append(d)
@@ -460,11 +484,12 @@ class ShapePlan:
 
 class Engine:
     def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True,
-                 multi_stream: bool = True, split_k: bool = True):
+                 multi_stream: bool = True, split_k: bool = True, use_tuning: bool = True):
         _lib.lib(require_device=True)
         self.device = torch.device(device)
         self.net = NetPlan(version, nc, precision)
         self.precision, self.algo, self.use_graphs, self.multi_stream, self.split_k = precision, algo, use_graphs, multi_stream, split_k
+        self.use_tuning = use_tuning
         sd = {k: v.detach() for k, v in sd.items()}
         self.anchors = _get(sd, "Detect.anchors").float().cpu()
         self.stride = torch.tensor([8.0, 16.0, 32.0])

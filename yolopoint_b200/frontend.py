@@ -105,7 +105,8 @@ class FramePipeline:
         """Kernels of this library launched per frame batch (for bench.py's gpu_launches)."""
         net_launches = len(self.plan.launches)
         # input + net + fused decode/NMS (candidates, counts, rank, mask, scan) + heatmap + keypoints (nms, collect, emit) + sample + match
-        per = 1 + net_launches + 5 + 1 + 3 + 1 + (self.B * 3 if self.do_match else 0)
+        # keypoints = 8 NMS rounds + 1 sweep + collect + emit (see csrc/keypoints.cu)
+        per = 1 + net_launches + 5 + 1 + 11 + 1 + (self.B * 3 if self.do_match else 0)
         return per
 
     def step_device(self, from_frame: bool = True):
