@@ -129,6 +129,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=1, help="independent camera streams (frame pipelines) in flight per GPU")
+    ap.add_argument("--also-streams", type=int, default=3, help="extra (untimed-for-value) run with this many camera streams, reported under detail")
     args = ap.parse_args()
     version, H, W, per_gpu = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,6 +220,34 @@ def main():
     sampler.join()
     launches = K * NS * (pipe.n_launches())
 
+    # ---- informational: several independent camera streams in flight (each batch 1), reported under detail only
+    multi = None
+    if NS == 1 and args.also_streams > 1:
+        M = args.also_streams
+        xp = [pipe] + [FramePipeline(model, per_gpu, H, W, max_pts=4096, nms_cap=4096, slot=i) for i in range(1, M)]
+        xs = [torch.cuda.Stream(dev) for _ in range(M)]
+
+        def mstep(i):
+            cur = torch.cuda.current_stream(dev)
+            for s_i, (pp, cs) in enumerate(zip(xp, xs)):
+                cs.wait_stream(cur)
+                with torch.cuda.stream(cs):
+                    pp.plan.frame_in.copy_(pool[(i * M + s_i) % n_pool])
+                    pp.step_device(True)
+            for cs in xs:
+                cur.wait_stream(cs)
+        for i in range(4):
+            mstep(i)
+        torch.cuda.synchronize(dev)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Km = min(K, 100)
+        m0.record()
+        for i in range(Km):
+            mstep(i)
+        m1.record()
+        torch.cuda.synchronize(dev)
+        multi = {"streams": M, "fps_per_gpu": Km * M * per_gpu / (m0.elapsed_time(m1) * 1e-3)}
+
     # ---- dominant kernel: conv launches only, timed live with events on the launching stream
     def net_only():
         plan.run_net()
@@ -281,7 +310,7 @@ def main():
                          "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained",
                          "launches_per_step": n_conv, "avg_launch_us": net_ms * 1e3 / n_conv, "algorithmic_gflop_per_step": flops_step / 1e9,
                          "note": "achieved = SURVEY 8a conv FLOPs per frame x frames per step / live CUDA-event time of the conv launches of one step"},
-            "detail": {"net_only_ms": net_ms, "keypoints": kp_n, "boxes": box_n, "matches": match_n}}
+            "detail": {"net_only_ms": net_ms, "keypoints": kp_n, "boxes": box_n, "matches": match_n, "concurrent_camera_streams": multi}}
     if not args.no_cpu_baseline and world == 1:
         n = max(3, min(30, int(args.cpu_seconds / 0.3)))
         cfps, cores, med = cpu_reference_fps(version, H, W, n, 2, sd)

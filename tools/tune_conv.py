@@ -79,7 +79,7 @@ def main():
         best = (base, 0, 0)
         tiles = [0] if op.l2norm else [n for n in range(16, nmax + 1, 16) if op.cout % n == 0]
         for tn in tiles:
-            for sk in ([1] if op.l2norm else [1, 2, 3, 4, 6, 8, 12, 16]):
+            for sk in [1, 2, 3, 4, 6, 8, 12, 16]:
                 d.tile_n, d.split_k = tn, sk
                 t = time_desc(L, d)
                 if t is not None and t < best[0]:

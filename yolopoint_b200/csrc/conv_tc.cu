@@ -709,7 +709,7 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
 
   // ---- split-K: deep layers on small feature maps occupy few CTAs; slice K over grid.z so that ~#SM CTAs are busy.
   int S = 1;
-  if (allow_split && !(d.epilogue & YP_EPI_L2NORM) && d.split_k != 1) {
+  if (allow_split && d.split_k != 1) {
     const int ctas = m_tiles * n_tiles;
     int want = d.split_k > 1 ? d.split_k : nsm / ctas;
     if (want > 16) want = 16;
