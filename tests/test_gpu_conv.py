@@ -51,6 +51,8 @@ CASES = [
     dict(B=1, H=20, W=20, Cin=256, Cout=256, k=3, s=1, res=True),     # deep layer on a small map: split-K
     dict(B=1, H=40, W=40, Cin=128, Cout=128, k=3, s=2),
     dict(B=1, H=20, W=20, Cin=1024, Cout=512, k=1, s=1, split=4),
+    dict(B=1, H=80, W=80, Cin=128, Cout=128, k=3, s=1, act=False, l2=True, plain=True, nobias=True, split=3),   # L2-norm head with split-K
+    dict(B=1, H=40, W=40, Cin=128, Cout=128, k=3, s=1, res=True, split=4, tile=64),
 ]
 
 
@@ -95,6 +97,7 @@ def run_case(c, fmt, algo):
         d.out[1] = make_view(out2_buf, out_fmt, 0, Cout)
     d.algo = algo
     d.split_k = c.get("split", 0)
+    d.tile_n = c.get("tile", 0)
     ws = None
     if algo == YP_ALGO_TCGEN05:
         nbytes = int(L.yp_conv2d_workspace_bytes(C.byref(d)))
