@@ -228,51 +228,68 @@ __global__ void nms_mask_kernel(int cap, float iou_thres, int agnostic, float ma
   }
 }
 
-// ordered scan over the bit matrix; one block per image
-__global__ void nms_scan_keep_kernel(int cap, int max_det, NmsWs ws, float* __restrict__ out_boxes, int* __restrict__ out_count) {
-  extern __shared__ unsigned long long removed[];  // cap/64 words
-  __shared__ unsigned long long diag[64];
+// ordered scan over the bit matrix; one block per image.  The upper-triangular part of the matrix that the scan touches
+// (n rows x ceil(n/64) words) is staged in shared memory when it fits, the 64-step dependent scan of a chunk runs in one
+// warp on registers (diagonal words exchanged by shuffles), and the suppression rows of the kept boxes are folded in
+// parallel.
+constexpr int kScanSmemBytes = 160 * 1024;
+
+__global__ void __launch_bounds__(256) nms_scan_keep_kernel(int cap, int max_det, NmsWs ws, float* __restrict__ out_boxes, int* __restrict__ out_count,
+                                                            int stage_words) {
+  extern __shared__ unsigned long long scan_smem[];   // removed[cap/64] then (optionally) the staged matrix
   __shared__ unsigned long long keep_bits;
   __shared__ int n_keep;
   const int b = blockIdx.x;
   const int n = ws.n_sorted[b];
   const int nb = (n + 63) >> 6;
   const int words = cap >> 6;
+  unsigned long long* removed = scan_smem;
+  unsigned long long* staged = scan_smem + words;
+  const bool in_smem = static_cast<long long>(n) * nb <= stage_words;
   const float* sorted = ws.sorted + static_cast<int64_t>(b) * cap * 6;
   const unsigned long long* mask = ws.mask + static_cast<int64_t>(b) * cap * words;
   float* out = out_boxes + static_cast<int64_t>(b) * max_det * 6;
   for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0;
+  if (in_smem)
+    for (int t = threadIdx.x; t < n * nb; t += blockDim.x) {
+      const int i = t / nb, w = t - i * nb;
+      staged[t] = w >= (i >> 6) ? mask[static_cast<int64_t>(i) * words + w] : 0ull;   // words left of the diagonal are never written
+    }
   if (threadIdx.x == 0) n_keep = 0;
   __syncthreads();
+  auto row_word = [&](int i, int w) -> unsigned long long {
+    return in_smem ? staged[i * nb + w] : mask[static_cast<int64_t>(i) * words + w];
+  };
   for (int wc = 0; wc < nb; ++wc) {
     if (n_keep >= max_det) break;  // uniform: n_keep only changes between barriers
     const int lim = min(64, n - wc * 64);
-    if (threadIdx.x < 64) diag[threadIdx.x] = threadIdx.x < lim ? mask[static_cast<int64_t>(wc * 64 + threadIdx.x) * words + wc] : 0ull;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    const int base = n_keep;
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const unsigned long long d0 = lane < lim ? row_word(wc * 64 + lane, wc) : 0ull;
+      const unsigned long long d1 = lane + 32 < lim ? row_word(wc * 64 + 32 + lane, wc) : 0ull;
       unsigned long long rem = removed[wc], kb = 0;
-      int nk = n_keep;
+      int nk = base;
       for (int k = 0; k < lim && nk < max_det; ++k) {
-        if (!((rem >> k) & 1ull)) { kb |= 1ull << k; rem |= diag[k]; ++nk; }
+        const unsigned long long dk = __shfl_sync(0xffffffffu, k < 32 ? d0 : d1, k & 31);
+        if (!((rem >> k) & 1ull)) { kb |= 1ull << k; rem |= dk; ++nk; }
       }
-      keep_bits = kb;
+      if (lane == 0) keep_bits = kb;
     }
     __syncthreads();
     const unsigned long long kb = keep_bits;
-    const int base = n_keep;
-    // write kept rows (ordered) and fold their suppression rows into `removed`
-    if (threadIdx.x < 64 && ((kb >> threadIdx.x) & 1ull)) {
+    if (threadIdx.x < 64 && ((kb >> threadIdx.x) & 1ull)) {   // kept rows, in order
       const int pos = base + __popcll(kb & ((1ull << threadIdx.x) - 1ull));
-      const float* s = sorted + static_cast<int64_t>(wc * 64 + threadIdx.x) * 6;
+      const float* sr = sorted + static_cast<int64_t>(wc * 64 + threadIdx.x) * 6;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) out[pos * 6 + k] = s[k];
+      for (int k = 0; k < 6; ++k) out[pos * 6 + k] = sr[k];
     }
-    // fold the suppression rows of the kept boxes into `removed`: one (row, word) pair per thread, loads all in flight
+    // fold the suppression rows of the kept boxes into `removed`: one (row, word) pair per thread
     const int later = nb - (wc + 1);
     for (int t = threadIdx.x; t < 64 * later; t += blockDim.x) {
       const int k = t / later, w = wc + 1 + (t - k * later);
       if ((kb >> k) & 1ull) {
-        const unsigned long long m = mask[static_cast<int64_t>(wc * 64 + k) * words + w];
+        const unsigned long long m = row_word(wc * 64 + k, w);
         if (m) atomicOr(&removed[w], m);
       }
     }
@@ -305,8 +322,10 @@ int nms_tail(int B, int cap, const YpNmsParams& p, const NmsWs& ws, float* out_b
   nms_counts_kernel<<<ceil_div(B, 128), 128, 0, st>>>(B, cap, p.max_nms, ws);
   nms_rank_kernel<<<dim3(cap / 256 + (cap % 256 ? 1 : 0), B), 256, 0, st>>>(cap, ws);
   nms_mask_kernel<<<dim3(2 * sm_count(), B), 64, 0, st>>>(cap, p.iou_thres, p.agnostic, p.max_wh, ws);
-  const size_t smem = sizeof(unsigned long long) * (cap / 64);
-  nms_scan_keep_kernel<<<B, 128, smem, st>>>(cap, p.max_det, ws, out_boxes, out_count);
+  static thread_local bool raised = false;
+  if (!raised) { YP_CUDA_OK(cudaFuncSetAttribute(nms_scan_keep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes)); raised = true; }
+  const int stage_words = (kScanSmemBytes - static_cast<int>(sizeof(unsigned long long)) * (cap / 64)) / static_cast<int>(sizeof(unsigned long long));
+  nms_scan_keep_kernel<<<B, 256, kScanSmemBytes, st>>>(cap, p.max_det, ws, out_boxes, out_count, stage_words > 0 ? stage_words : 0);
   YP_LAUNCH_OK();
   return YP_OK;
 }
