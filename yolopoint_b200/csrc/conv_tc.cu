@@ -206,7 +206,7 @@ __device__ __forceinline__ float silu_fast(float v) {
 // result so that their truncation error is negligible.
 // ---------------------------------------------------------------------------------------------
 template <int OUT_FMT, int UNITS, bool kTf32>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+__global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 4) ? 1 : 2) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -725,6 +725,11 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   const int kb_min = num_kb - (S - 1) * a.kb_per_split;   // k-blocks of the last (shortest) slice
   const int mmas_min = kb_min * ksteps;                    // main MMAs every CTA issues at least
 
+  // Layers with more CTAs than SMs run two CTAs per SM (the epilogue of one overlaps the main loop of the other): each CTA
+  // then gets half of the shared memory and at most 256 TMEM columns.
+  const bool dense = static_cast<long long>(m_tiles) * n_tiles * S > nsm;
+  const int tmem_limit = dense ? 256 : 512;
+
   // ---- accumulator / issuer plan (see the kernel comment)
   const uint32_t ab = tf32 ? 2u : 1u;
   auto idesc = [&](int n) {  // cute::UMMA::InstrDescriptor: c F32 [4,6)=1, a/b format [7,10)/[10,13), K-major, N>>3 [17,23), M>>4 [24,29)
@@ -733,7 +738,8 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   int cols = 0;
   if (tf32 && Nt <= 128) {
     // issuer 0: A_hi x [W_hi; W_lo]  (N = 2 Nt)  -> pairs [main | cross2];  issuer 1: A_lo x W_hi (N = Nt) -> cross1
-    int n_s = 2, n_p = (512 - n_s * Nt) / (2 * Nt);
+    int n_s = 2, n_p = (tmem_limit - n_s * Nt) / (2 * Nt);
+    if (n_p < 1) { n_s = 1; n_p = (tmem_limit - Nt) / (2 * Nt); }
     if (n_p < 1) { n_s = 1; n_p = (512 - Nt) / (2 * Nt); }
     if (n_p > 6) n_p = 6;
     if (n_p > mmas_min) n_p = mmas_min;
@@ -757,7 +763,7 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
     a.n_src = 2; a.src_col[0] = 0; a.src_col[1] = Nt;
     cols = 2 * Nt;
   } else {
-    const int total = 512 / Nt;
+    const int total = (tmem_limit / Nt) >= 1 ? tmem_limit / Nt : 512 / Nt;
     a.n_iss = (total >= 2 && ksteps >= 2) ? 2 : 1;
     a.kstep_mod = a.n_iss == 2 ? 2 : 0;
     int each = total / a.n_iss;
@@ -783,12 +789,13 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   a.stage_bytes = a.a_region_bytes + b_region_bytes;
   // TMA counts the bytes of the boxes actually written: Ht*Wt (<= 128) rows per A plane, Nt rows per B plane
   a.tx_bytes = a.in_planes * (rows * a.ck_bytes + Nt * a.ck_bytes);
-  const int budget = 200 * 1024;
+  int budget = dense ? 104 * 1024 : 200 * 1024;
+  if (a.stage_bytes * 2 > budget) budget = 200 * 1024;   // keep at least two stages
   int stages = budget / a.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > a.kb_per_split) stages = a.kb_per_split;
   if (stages < 1) stages = 1;
-  YP_REQUIRE(a.stage_bytes <= budget, YP_ERR_SHAPE, "conv: stage of %d bytes exceeds shared memory", a.stage_bytes);
+  YP_REQUIRE(a.stage_bytes <= 200 * 1024, YP_ERR_SHAPE, "conv: stage of %d bytes exceeds shared memory", a.stage_bytes);
   a.stages = stages;
   int region = stages * a.stage_bytes;
   if (region < 2 * a.staging_set_bytes) region = 2 * a.staging_set_bytes;
