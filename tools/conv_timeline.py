@@ -20,6 +20,8 @@ SHAPES = [
     dict(B=1, H=20, W=20, Cin=256, Cout=256, k=3, s=1, res=True),
     dict(B=1, H=20, W=20, Cin=1024, Cout=512, k=1, s=1),
     dict(B=1, H=320, W=320, Cin=16, Cout=32, k=3, s=1),
+    dict(B=4, H=23, W=40, Cin=384, Cout=384, k=3, s=1, res=True),      # YOLOPoint-M stride-32 layer, batch 4 (192 CTAs)
+    dict(B=4, H=46, W=80, Cin=192, Cout=192, k=3, s=1, res=True),
 ]
 
 

@@ -727,7 +727,8 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
 
   // Layers with more CTAs than SMs run two CTAs per SM (the epilogue of one overlaps the main loop of the other): each CTA
   // then gets half of the shared memory and at most 256 TMEM columns.
-  const bool dense = static_cast<long long>(m_tiles) * n_tiles * S > nsm;
+  static const bool allow_dense = getenv("YP_CONV_NO_DENSE") == nullptr;
+  const bool dense = allow_dense && static_cast<long long>(m_tiles) * n_tiles * S > nsm;
   const int tmem_limit = dense ? 256 : 512;
 
   // ---- accumulator / issuer plan (see the kernel comment)

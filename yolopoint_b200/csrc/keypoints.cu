@@ -53,6 +53,7 @@ __global__ void heatmap_kernel(const float* __restrict__ semi, int B, int Hc, in
 struct KpWs {
   unsigned char* state;        // [B*H*W]
   unsigned int* tile_undecided;  // [B * tiles]
+  unsigned int* round_total;     // [KP_ROUNDS] undecided candidates left after each round
   int* n_list;                 // [B]
   unsigned long long* list;    // [B][max_pts]  (ordered_conf << 32) | raster index
 };
@@ -188,7 +189,7 @@ __device__ __forceinline__ KpTileSmem kp_carve(unsigned char* base, int r, int* 
 }
 
 // ws.tile_undecided[t]: undecided interior candidates of tile t after its last processed round
-__global__ void __launch_bounds__(256) kp_round_kernel(const float* __restrict__ heat, int B, int H, int W, float thr, int r, KpWs ws, int first) {
+__global__ void __launch_bounds__(256) kp_round_kernel(const float* __restrict__ heat, int B, int H, int W, float thr, int r, KpWs ws, int first, int round) {
   extern __shared__ unsigned char kp_smem[];
   __shared__ int n_list;
   __shared__ unsigned int total;
@@ -201,7 +202,10 @@ __global__ void __launch_bounds__(256) kp_round_kernel(const float* __restrict__
   for (int sft = 16; sft > 0; sft >>= 1) u += __shfl_xor_sync(0xffffffffu, u, sft);
   if ((threadIdx.x & 31) == 0 && u) atomicAdd(&total, u);
   __syncthreads();
-  if (threadIdx.x == 0) ws.tile_undecided[t] = total;
+  if (threadIdx.x == 0) {
+    ws.tile_undecided[t] = total;
+    if (total) atomicAdd(&ws.round_total[round], total);
+  }
 }
 
 // sequential safety net: one CTA sweeps the tiles that still have undecided candidates until none is left
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(256) kp_sweep_kernel(const float* __restrict__
   extern __shared__ unsigned char kp_smem[];
   __shared__ int n_list;
   __shared__ unsigned int total, any;
+  if (ws.round_total[KP_ROUNDS - 1] == 0) return;   // the parallel rounds finished everything (the usual case)
   const KpTileSmem sm = kp_carve(kp_smem, r, &n_list);
   for (;;) {
     if (threadIdx.x == 0) any = 0;
@@ -307,6 +312,7 @@ size_t carve(KpWs* ws, char* base, int B, int H, int W, int max_pts) {
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
   ws->state = reinterpret_cast<unsigned char*>(take(static_cast<size_t>(B) * H * W));
   ws->tile_undecided = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * B * ((H + 31) / 32) * ((W + 31) / 32)));
+  ws->round_total = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 16));
   ws->n_list = reinterpret_cast<int*>(take(sizeof(int) * B));
   ws->list = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * max_pts));
   return off;
@@ -353,8 +359,9 @@ extern "C" int yp_keypoints_nms(const float* heat, int32_t B, int32_t H, int32_t
   }
   const int tiles = B * yp::ceil_div(H, yp::KT) * yp::ceil_div(W, yp::KT);
   YP_CUDA_OK(cudaMemsetAsync(ws.n_list, 0, sizeof(int) * B, st));
+  YP_CUDA_OK(cudaMemsetAsync(ws.round_total, 0, sizeof(unsigned int) * 16, st));
   for (int round = 0; round < yp::KP_ROUNDS; ++round)
-    yp::kp_round_kernel<<<tiles, 256, nms_smem, st>>>(heat, B, H, W, conf_thresh, nms_dist, ws, round == 0 ? 1 : 0);
+    yp::kp_round_kernel<<<tiles, 256, nms_smem, st>>>(heat, B, H, W, conf_thresh, nms_dist, ws, round == 0 ? 1 : 0, round);
   yp::kp_sweep_kernel<<<1, 256, nms_smem, st>>>(heat, B, H, W, conf_thresh, nms_dist, ws, tiles);
   YP_LAUNCH_OK();
   return YP_OK;
