@@ -70,6 +70,7 @@ typedef struct {
 typedef enum { YP_ACT_NONE = 0, YP_ACT_SILU = 1 } YpAct;
 typedef enum { YP_ALGO_TCGEN05 = 0, YP_ALGO_SIMT = 1 } YpConvAlgo;
 #define YP_EPI_L2NORM 1u /* divide each output pixel by its L2 norm over all `cout` channels */
+#define YP_EPI_NO_PATCH 2u /* planner hint: do not use the shared-memory patch formulation of 3x3 stride-1 convs */
 
 /*
  * yp_conv2d_nhwc_fwd -- one Conv block of the reference in eval/fused form:

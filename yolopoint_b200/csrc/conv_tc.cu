@@ -17,6 +17,7 @@
 
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <mutex>
 #include <stdlib.h>
 
@@ -133,6 +134,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) |
          (static_cast<uint64_t>((8u * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
+// Same for a 128B-swizzled operand whose first row is NOT at a 1024-byte boundary (a row-shifted window of a larger
+// shared-memory patch): `base_offset` [49,52) = (start >> 7) & 7 tells the tensor core the swizzle phase of row 0.
+__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr, int use_base_offset) {
+  uint64_t d = make_smem_desc(saddr, 128);
+  if (use_base_offset) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
+  return d;
+}
 
 // byte address inside a TMA-swizzled tile: row r, 16-byte chunk j, rows of row_bytes (128/64/32)
 __device__ __forceinline__ uint32_t swz_addr(uint32_t tile_base, uint32_t r, uint32_t j, uint32_t row_bytes) {
@@ -165,6 +173,9 @@ struct ConvArgs {
   uint32_t iss_idesc[2];
   int n_src, src_col[16];          // TMEM column bases whose sum is the result (main products first)
   int split_k, kb_per_split;       // grid.z CTAs share one output tile, each reducing a slice of K
+  // patch mode (3x3 stride 1): one (Ht+2) x (Wt+2) input patch per channel block stays in shared memory and the nine taps
+  // are row-shifted windows of it; M rows index the padded patch (row = h * Wp + w), halo columns are discarded.
+  int patch, Wp, a_rows, a_stage_bytes, a_tx, b_stage_bytes, b_tx, b_stages, b_ring_off, base_offset_mode;
   float* ws_partial;               // [split][m_tile][n_tile][128][Nt] fp32 partial sums
   int* ws_counter;                 // [m_tile][n_tile] arrival counters (self-resetting)
   uint32_t tmem_cols;
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
   const int th = trem / a.tiles_w, tw = trem - th * a.tiles_w;
   const int h0 = th * a.Ht, w0 = tw * a.Wt;
   const int n0 = blockIdx.y * a.Nt;
-  const int num_kb_all = a.n_taps * a.kb_per_tap;
+  const int num_kb_all = a.patch ? a.kb_per_tap : a.n_taps * a.kb_per_tap;   // K-loop units (patch mode: channel blocks)
   const int kb0 = blockIdx.z * a.kb_per_split;                       // this CTA's slice of the K loop (split-K)
   const int num_kb = min(num_kb_all, kb0 + a.kb_per_split) - kb0;
   long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
@@ -235,14 +246,17 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
   const uint32_t accum_bar = bar_base + 8u * (2 * kMaxStages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 1);
   volatile int* split_flag = reinterpret_cast<volatile int*>(smem_gen + a.bar_off + 8 * (2 * kMaxStages + 1) + 4);
-  float* bias_s = reinterpret_cast<float*>(smem_gen + a.bar_off + 8 * (2 * kMaxStages + 2));
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };
+  float* bias_s = reinterpret_cast<float*>(smem_gen + a.bar_off + 8 * (2 * kMaxStages + 6));
 
   if (warp == 0 && lane == 0) {
     const int n_in = a.stride == 2 ? 4 : 1;
     for (int i = 0; i < n_in; ++i) tma_prefetch_desc(&maps.in[i]);
     tma_prefetch_desc(&maps.w);
     for (int i = 0; i < a.n_out_maps; ++i) tma_prefetch_desc(&maps.out[i]);
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), a.n_iss); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), a.n_iss); }
+    for (int s = 0; s < 2; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), a.n_iss); }
     mbar_init(accum_bar, a.n_iss);
     fence_barrier_init();
   }
@@ -261,6 +275,26 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
     // ===================== TMA producer =====================
     if (lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
+      if (a.patch) {
+        // K order = (channel block, tap): one patch load per channel block, nine weight tiles streamed through the B ring
+        int sa = 0, pha = 0, sb = 0, phb = 0;
+        for (int cbi = 0; cbi < num_kb; ++cbi) {
+          const int cb = kb0 + cbi;
+          mbar_wait(aempty_bar(sa), pha ^ 1);
+          mbar_expect_tx(afull_bar(sa), a.a_tx);
+          const uint32_t sta = smem_base + sa * a.a_stage_bytes;
+          tma_load_5d(sta, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 0);
+          if (a.in_planes == 2 && !a.a_split) tma_load_5d(sta + a.a_plane_off, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 1);
+          if (cbi < 96) stamp(8 + cbi);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(empty_bar(sb), phb ^ 1);
+            mbar_expect_tx(full_bar(sb), a.b_tx);
+            tma_load_3d(smem_base + a.b_ring_off + sb * a.b_stage_bytes, &maps.w, full_bar(sb), (tap * a.kb_per_tap + cb) * a.ck_elems, n0, 0);
+            if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+          }
+          if (++sa == 2) { sa = 0; pha ^= 1; }
+        }
+      } else {
       int s = 0, ph = 0, tap = kb0 / a.kb_per_tap, cb = kb0 - tap * a.kb_per_tap;
       const uint32_t b_off = a.a_region_bytes;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -280,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
         if (++cb == a.kb_per_tap) { cb = 0; ++tap; }
         if (++s == a.stages) { s = 0; ph ^= 1; }
       }
+      }
     }
   }
   // ===================== MMA issuers =====================
@@ -298,6 +333,40 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
     const uint32_t col0 = tmem_base + a.iss_col[q], cstride = a.iss_stride[q], idesc = a.iss_idesc[q];
     uint32_t used = 0;                   // bit r set = accumulator r of this issuer already holds a partial sum
     int s = 0, ph = 0, nxt = 0;
+    if (a.patch) {
+      int sa = 0, pha = 0;
+      for (int cbi = 0; cbi < num_kb; ++cbi) {
+        mbar_wait(afull_bar(sa), pha);
+        tc_fence_after();
+        if (q == 0 && cbi < 96) stamp(104 + cbi);
+        const uint32_t pa = smem_base + sa * a.a_stage_bytes;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const int kh = tap / 3, kw = tap - kh * 3;
+          const uint32_t shift = static_cast<uint32_t>(kh * a.Wp + kw) * 128u;   // window of the patch for this tap
+          const uint32_t sb = smem_base + a.b_ring_off + s * a.b_stage_bytes;
+          const uint64_t ad0 = make_smem_desc_shifted(pa + a.job_a[q][0] * a.a_plane_off + shift, a.base_offset_mode);
+          const uint64_t bd0 = make_smem_desc(sb + a.job_b[q][0] * b_plane, 128);
+          const uint64_t ad1 = make_smem_desc_shifted(pa + a.job_a[q][1] * a.a_plane_off + shift, a.base_offset_mode);
+          const uint64_t bd1 = make_smem_desc(sb + a.job_b[q][1] * b_plane, 128);
+          const bool two = a.n_jobs[q] == 2;
+          for (int k = 0; k < 4; ++k) {
+            if (a.kstep_mod && (k % a.kstep_mod) != q) continue;
+            const uint64_t ko = static_cast<uint64_t>(2 * k);
+            umma<kTf32>(col0 + nxt * cstride, ad0 + ko, bd0 + ko, idesc, (used >> nxt) & 1u);
+            if (two) umma<kTf32>(col0 + nxt * cstride, ad1 + ko, bd1 + ko, idesc, 1u);
+            used |= 1u << nxt;
+            if (++nxt == cnt) nxt = 0;
+          }
+          umma_commit(empty_bar(s));
+          if (++s == a.b_stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(aempty_bar(sa));
+        if (q == 0 && cbi < 96) stamp(200 + cbi);
+        if (++sa == 2) { sa = 0; pha ^= 1; }
+      }
+    } else
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
@@ -331,10 +400,13 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
     constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
     constexpr int V16 = ROWB / 16;                 // 16-byte vectors per row
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int rh = row / a.Wt, rw = row - rh * a.Wt;
+    const int row = q * 32 + lane;               // accumulator row (TMEM lane) of this thread
+    const int rdiv = a.patch ? a.Wp : a.Wt;      // patch mode: rows index the padded patch, halo columns are dropped
+    const int rh = row / rdiv, rw = row - rh * rdiv;
     const int oh = h0 + rh, ow = w0 + rw;
-    const bool valid = (row < a.Ht * a.Wt) && (oh < a.Ho) && (ow < a.Wo);
+    const bool in_tile = rh < a.Ht && rw < a.Wt;
+    const bool valid = in_tile && (oh < a.Ho) && (ow < a.Wo);
+    const int srow = in_tile ? rh * a.Wt + rw : 127;   // row of the (compact Ht x Wt) staging tile this thread fills
     const bool et0 = (threadIdx.x == 64);
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int n_chunks = a.Nt / CH;
@@ -474,19 +546,21 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
       // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t stg = smem_base + (c & 1) * a.staging_set_bytes;
-      if (OUT_FMT == YP_FMT_F32X2) {
+      if (!in_tile) {
+        // halo / padding row: nothing to stage
+      } else if (OUT_FMT == YP_FMT_F32X2) {
 #pragma unroll
         for (int j = 0; j < V16; ++j) {
           float hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { hi[e] = tf32_round(v[j * 4 + e]); lo[e] = tf32_round(v[j * 4 + e] - hi[e]); }
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, row, j, ROWB)), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg + 128 * ROWB, row, j, ROWB)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j, ROWB)), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg + 128 * ROWB, srow, j, ROWB)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
         }
       } else if (OUT_FMT == YP_FMT_F32) {
 #pragma unroll
         for (int j = 0; j < V16; ++j)
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, row, j, ROWB)), "f"(v[j * 4]), "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j, ROWB)), "f"(v[j * 4]), "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
       } else {
 #pragma unroll
         for (int j = 0; j < V16; ++j) {
@@ -496,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
             pk[e] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, row, j, ROWB)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j, ROWB)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
       }
       fence_proxy_async_smem();
@@ -618,6 +692,19 @@ void pick_patch(int Ho, int Wo, int* Ht, int* Wt) {
   *Ht = bh; *Wt = bw;
 }
 
+// Patch mode: M rows index an Ht x (Wt+2) padded patch, so Ht * (Wt + 2) <= 128.
+void pick_patch_padded(int Ho, int Wo, int* Ht, int* Wt) {
+  int best_tiles = 1 << 30, bw = 1, bh = 1;
+  for (int wt = 1; wt <= Wo && wt <= 126; ++wt) {
+    int ht = 128 / (wt + 2);
+    if (ht > Ho) ht = Ho;
+    if (ht < 1) continue;
+    const int tiles = ceil_div(Wo, wt) * ceil_div(Ho, ht);
+    if (tiles < best_tiles || (tiles == best_tiles && wt > bw)) { best_tiles = tiles; bw = wt; bh = ht; }
+  }
+  *Ht = bh; *Wt = bw;
+}
+
 namespace {
 
 struct ConvPlan {
@@ -654,11 +741,24 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   a.ck_elems = a.ck_bytes / es;
   a.kb_per_tap = in.C / a.ck_elems;
   a.in_planes = tf32 ? 2 : 1;
-  const int rows = a.Ht * a.Wt;
-  a.a_split = (a.in_planes == 2 && rows % 8 == 0) ? 1 : 0;   // lo plane lands right behind the hi plane, swizzle-aligned
-  a.a_plane_off = ((rows + 7) & ~7) * a.ck_bytes;
-  const int num_kb = a.n_taps * a.kb_per_tap;
-  const int ksteps = a.ck_bytes / 32;
+  static const bool allow_patch = getenv("YP_CONV_NO_PATCH") == nullptr;
+  static const int base_offset_mode = getenv("YP_CONV_BASE_OFFSET") ? atoi(getenv("YP_CONV_BASE_OFFSET")) : 1;
+  a.patch = (allow_patch && d.ksize == 3 && d.stride == 1 && a.ck_bytes == 128 && !(d.epilogue & YP_EPI_NO_PATCH)) ? 1 : 0;
+  a.base_offset_mode = base_offset_mode;
+  if (a.patch) {
+    pick_patch_padded(Ho, Wo, &a.Ht, &a.Wt);
+    a.tiles_w = ceil_div(Wo, a.Wt); a.tiles_h = ceil_div(Ho, a.Ht);
+    a.Wp = a.Wt + 2;
+    a.a_rows = (a.Ht + 2) * a.Wp;
+  }
+  const int rows = a.patch ? a.a_rows : a.Ht * a.Wt;           // rows one TMA box of the A operand writes
+  // rows the tensor core may touch: the last tap's window starts (2*Wp+2) rows into the patch and always spans 128 rows
+  const int rows_alloc = a.patch ? ((std::max(a.a_rows, 128 + 2 * a.Wp + 2) + 7) & ~7) : 128;
+  a.a_split = (!a.patch && a.in_planes == 2 && rows % 8 == 0) ? 1 : 0;   // lo plane lands right behind the hi plane, swizzle-aligned
+  a.a_plane_off = a.patch ? rows_alloc * a.ck_bytes : ((rows + 7) & ~7) * a.ck_bytes;
+  // K loop units: (tap, channel block) pairs, or channel blocks (each covering all nine taps) in patch mode
+  const int num_kb = a.patch ? a.kb_per_tap : a.n_taps * a.kb_per_tap;
+  const int ksteps = (a.patch ? 9 : 1) * (a.ck_bytes / 32);   // MMA k-steps per K-loop unit
 
   // ---- output format / staging geometry
   const int out_fmt = d.out[0].format;
@@ -713,9 +813,10 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
     const int ctas = m_tiles * n_tiles;
     int want = d.split_k > 1 ? d.split_k : nsm / ctas;
     if (want > 16) want = 16;
-    if (d.split_k <= 1) {                         // heuristic: at most 8 slices of >= 4 k-blocks
+    if (d.split_k <= 1) {                         // heuristic: at most 8 slices of >= 4 k-blocks (>= 1 channel block in patch mode)
       if (want > 8) want = 8;
-      if (want > num_kb / 4) want = num_kb / 4;
+      const int lim = a.patch ? num_kb : num_kb / 4;
+      if (want > lim) want = lim;
     } else if (want > num_kb) want = num_kb;
     if (want >= 2) S = want;
   }
@@ -791,18 +892,34 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   // TMA counts the bytes of the boxes actually written: Ht*Wt (<= 128) rows per A plane, Nt rows per B plane
   a.tx_bytes = a.in_planes * (rows * a.ck_bytes + Nt * a.ck_bytes);
   int budget = dense ? 104 * 1024 : 200 * 1024;
-  if (a.stage_bytes * 2 > budget) budget = 200 * 1024;   // keep at least two stages
-  int stages = budget / a.stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > a.kb_per_split) stages = a.kb_per_split;
-  if (stages < 1) stages = 1;
-  YP_REQUIRE(a.stage_bytes <= 200 * 1024, YP_ERR_SHAPE, "conv: stage of %d bytes exceeds shared memory", a.stage_bytes);
-  a.stages = stages;
-  int region = stages * a.stage_bytes;
+  int region = 0;
+  if (a.patch) {
+    a.a_stage_bytes = a.in_planes * rows_alloc * 128;
+    a.a_tx = a.in_planes * a.a_rows * 128;
+    a.b_stage_bytes = b_region_bytes;
+    a.b_tx = b_region_bytes;
+    a.b_ring_off = 2 * a.a_stage_bytes;
+    if (2 * a.a_stage_bytes + 2 * a.b_stage_bytes > budget) budget = 200 * 1024;
+    int bs = (budget - 2 * a.a_stage_bytes) / a.b_stage_bytes;
+    if (bs > kMaxStages) bs = kMaxStages;
+    YP_REQUIRE(bs >= 2, YP_ERR_SHAPE, "conv(patch): %d-byte patch stages leave no room for the weight ring", a.a_stage_bytes);
+    a.b_stages = bs;
+    a.stages = bs;
+    region = 2 * a.a_stage_bytes + bs * a.b_stage_bytes;
+  } else {
+    if (a.stage_bytes * 2 > budget) budget = 200 * 1024;   // keep at least two stages
+    int stages = budget / a.stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > a.kb_per_split) stages = a.kb_per_split;
+    if (stages < 1) stages = 1;
+    YP_REQUIRE(a.stage_bytes <= 200 * 1024, YP_ERR_SHAPE, "conv: stage of %d bytes exceeds shared memory", a.stage_bytes);
+    a.stages = stages;
+    region = stages * a.stage_bytes;
+  }
   if (region < 2 * a.staging_set_bytes) region = 2 * a.staging_set_bytes;
   region = (region + 1023) & ~1023;
   a.bar_off = region;
-  P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 2) + Nt * sizeof(float) + 16;
+  P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 6) + Nt * sizeof(float) + 16;
   YP_REQUIRE(P->smem <= 227 * 1024, YP_ERR_SHAPE, "conv: needs %zu bytes of shared memory", P->smem);
   P->grid = dim3(m_tiles, n_tiles, S);
   P->ws_counter_bytes = (static_cast<size_t>(m_tiles) * n_tiles * sizeof(int) + 255) & ~static_cast<size_t>(255);
@@ -850,7 +967,9 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
 
   // ---- tensor maps
   if (d.stride == 1) {
-    if ((rc = encode_view(&maps.in[0], in, 1, 0, 0, in.W, in.H, a.ck_elems, a.Wt, a.Ht, a.a_split ? 2 : 1)) != YP_OK) return rc;
+    if (a.patch) {
+      if ((rc = encode_view(&maps.in[0], in, 1, 0, 0, in.W, in.H, a.ck_elems, a.Wp, a.Ht + 2, 1)) != YP_OK) return rc;
+    } else if ((rc = encode_view(&maps.in[0], in, 1, 0, 0, in.W, in.H, a.ck_elems, a.Wt, a.Ht, a.a_split ? 2 : 1)) != YP_OK) return rc;
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
