@@ -135,7 +135,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
          (static_cast<uint64_t>((8u * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 // Same for a 128B-swizzled operand whose first row is NOT at a 1024-byte boundary (a row-shifted window of a larger
-// shared-memory patch): `base_offset` [49,52) = (start >> 7) & 7 tells the tensor core the swizzle phase of row 0.
+// shared-memory patch).  Measured on B200: the tensor core derives the swizzle phase from the absolute shared-memory
+// address (as TMA does), so a window that starts at any 128-byte row of a 1024-byte-aligned patch needs base_offset = 0;
+// setting base_offset = (start >> 7) & 7 gives wrong results (tests/test_gpu_conv.py with YP_CONV_BASE_OFFSET=1).
 __device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr, int use_base_offset) {
   uint64_t d = make_smem_desc(saddr, 128);
   if (use_base_offset) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
@@ -742,7 +744,7 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   a.kb_per_tap = in.C / a.ck_elems;
   a.in_planes = tf32 ? 2 : 1;
   static const bool allow_patch = getenv("YP_CONV_NO_PATCH") == nullptr;
-  static const int base_offset_mode = getenv("YP_CONV_BASE_OFFSET") ? atoi(getenv("YP_CONV_BASE_OFFSET")) : 1;
+  static const int base_offset_mode = getenv("YP_CONV_BASE_OFFSET") ? atoi(getenv("YP_CONV_BASE_OFFSET")) : 0;
   a.patch = (allow_patch && d.ksize == 3 && d.stride == 1 && a.ck_bytes == 128 && !(d.epilogue & YP_EPI_NO_PATCH)) ? 1 : 0;
   a.base_offset_mode = base_offset_mode;
   if (a.patch) {
@@ -798,7 +800,7 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
     for (int n = nmax; n >= chunk_elems; n -= 16) {
       if (d.cout % n || n % chunk_elems) continue;
       smallest = n;
-      if (Nt == 0 && m_tiles * (d.cout / n) >= nsm) Nt = n;
+      if (Nt == 0 && m_tiles * (d.cout / n) >= nsm / 2) Nt = n;   // measured: wider tiles win as soon as half the SMs are busy
       if (n <= 32 && smallest) break;
     }
     if (Nt == 0) Nt = smallest;
