@@ -138,8 +138,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
 // shared-memory patch).  Measured on B200: the tensor core derives the swizzle phase from the absolute shared-memory
 // address (as TMA does), so a window that starts at any 128-byte row of a 1024-byte-aligned patch needs base_offset = 0;
 // setting base_offset = (start >> 7) & 7 gives wrong results (tests/test_gpu_conv.py with YP_CONV_BASE_OFFSET=1).
-__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr, int use_base_offset) {
-  uint64_t d = make_smem_desc(saddr, 128);
+__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr, uint32_t row_bytes, int use_base_offset) {
+  uint64_t d = make_smem_desc(saddr, row_bytes);
   if (use_base_offset) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
   return d;
 }
@@ -346,14 +346,14 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const int kh = tap / 3, kw = tap - kh * 3;
-          const uint32_t shift = static_cast<uint32_t>(kh * a.Wp + kw) * 128u;   // window of the patch for this tap
+          const uint32_t shift = static_cast<uint32_t>(kh * a.Wp + kw) * a.ck_bytes;   // window of the patch for this tap
           const uint32_t sb = smem_base + a.b_ring_off + s * a.b_stage_bytes;
-          const uint64_t ad0 = make_smem_desc_shifted(pa + a.job_a[q][0] * a.a_plane_off + shift, a.base_offset_mode);
-          const uint64_t bd0 = make_smem_desc(sb + a.job_b[q][0] * b_plane, 128);
-          const uint64_t ad1 = make_smem_desc_shifted(pa + a.job_a[q][1] * a.a_plane_off + shift, a.base_offset_mode);
-          const uint64_t bd1 = make_smem_desc(sb + a.job_b[q][1] * b_plane, 128);
+          const uint64_t ad0 = make_smem_desc_shifted(pa + a.job_a[q][0] * a.a_plane_off + shift, a.ck_bytes, a.base_offset_mode);
+          const uint64_t bd0 = make_smem_desc(sb + a.job_b[q][0] * b_plane, a.ck_bytes);
+          const uint64_t ad1 = make_smem_desc_shifted(pa + a.job_a[q][1] * a.a_plane_off + shift, a.ck_bytes, a.base_offset_mode);
+          const uint64_t bd1 = make_smem_desc(sb + a.job_b[q][1] * b_plane, a.ck_bytes);
           const bool two = a.n_jobs[q] == 2;
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < ksteps; ++k) {
             if (a.kstep_mod && (k % a.kstep_mod) != q) continue;
             const uint64_t ko = static_cast<uint64_t>(2 * k);
             umma<kTf32>(col0 + nxt * cstride, ad0 + ko, bd0 + ko, idesc, (used >> nxt) & 1u);
@@ -745,7 +745,7 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   a.in_planes = tf32 ? 2 : 1;
   static const bool allow_patch = getenv("YP_CONV_NO_PATCH") == nullptr;
   static const int base_offset_mode = getenv("YP_CONV_BASE_OFFSET") ? atoi(getenv("YP_CONV_BASE_OFFSET")) : 0;
-  a.patch = (allow_patch && d.ksize == 3 && d.stride == 1 && a.ck_bytes == 128 && !(d.epilogue & YP_EPI_NO_PATCH)) ? 1 : 0;
+  a.patch = (allow_patch && d.ksize == 3 && d.stride == 1 && a.ck_bytes >= 64 && !(d.epilogue & YP_EPI_NO_PATCH)) ? 1 : 0;
   a.base_offset_mode = base_offset_mode;
   if (a.patch) {
     pick_patch_padded(Ho, Wo, &a.Ht, &a.Wt);
@@ -896,8 +896,8 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   int budget = dense ? 104 * 1024 : 200 * 1024;
   int region = 0;
   if (a.patch) {
-    a.a_stage_bytes = a.in_planes * rows_alloc * 128;
-    a.a_tx = a.in_planes * a.a_rows * 128;
+    a.a_stage_bytes = a.in_planes * rows_alloc * a.ck_bytes;
+    a.a_tx = a.in_planes * a.a_rows * a.ck_bytes;
     a.b_stage_bytes = b_region_bytes;
     a.b_tx = b_region_bytes;
     a.b_ring_off = 2 * a.a_stage_bytes;
