@@ -56,7 +56,7 @@ CASES = [
 ]
 
 
-def run_case(c, fmt, algo):
+def run_case(c, fmt, algo, shared_ws=None):
     L = _lib.lib(require_device=True)
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(1234)
@@ -101,7 +101,10 @@ def run_case(c, fmt, algo):
     ws = None
     if algo == YP_ALGO_TCGEN05:
         nbytes = int(L.yp_conv2d_workspace_bytes(C.byref(d)))
-        if nbytes:
+        if nbytes and shared_ws is not None:
+            assert nbytes <= shared_ws.numel()
+            d.workspace, d.workspace_bytes = shared_ws.data_ptr(), shared_ws.numel()
+        elif nbytes:
             ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
             d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
     for _ in range(2):   # twice: the split-K arrival counters must reset themselves
@@ -147,3 +150,14 @@ def test_conv_tcgen05(ci, fmt):
 @pytest.mark.parametrize("ci", [1, 2, 3, 4])
 def test_conv_simt_crosscheck(ci):
     run_case(CASES[ci], YP_FMT_F32X2, YP_ALGO_SIMT)
+
+
+def test_split_k_layers_share_one_workspace():
+    """Layers of one lane share a split-K workspace (engine.ShapePlan): the arrival counters of a layer with many tiles
+    must not alias the partial sums an earlier layer with few tiles left behind (regression: per-layer counter area)."""
+    ws = torch.zeros(192 << 20, dtype=torch.uint8, device="cuda")
+    few = dict(B=1, H=20, W=20, Cin=1024, Cout=512, k=1, s=1, split=4, tile=128)       # 4 x 4 tiles
+    many = dict(B=1, H=40, W=40, Cin=512, Cout=256, k=1, s=1, split=2, tile=32)        # 13 x 8 tiles
+    more = dict(B=2, H=48, W=80, Cin=384, Cout=384, k=1, s=1, split=12, tile=64)       # 60 x 6 tiles
+    for c in (few, many, few, more, many):
+        run_case(c, YP_FMT_F32X2, YP_ALGO_TCGEN05, shared_ws=ws)

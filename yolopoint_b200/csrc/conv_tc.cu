@@ -190,6 +190,7 @@ struct ConvArgs {
 };
 
 constexpr int kThreads = 192;
+constexpr size_t kWsCounterBytes = 64 * 1024;   // split-K arrival counters: one int per output tile, <= 16384 tiles
 constexpr int kMaxStages = 8;
 
 template <int OUT_FMT>
@@ -718,7 +719,7 @@ struct ConvPlan {
 };
 
 // Everything that does not need device pointers: tile shapes, accumulator plan, split-K factor, workspace need.
-int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
+int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_patch, bool* patch_no_fit) {
   const YpView& in = d.in;
   const int in_fmt = in.format;
   YP_REQUIRE(in_fmt == YP_FMT_F32X2 || in_fmt == YP_FMT_BF16, YP_ERR_SHAPE, "conv: input format %d unsupported", in_fmt);
@@ -745,7 +746,7 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   a.in_planes = tf32 ? 2 : 1;
   static const bool allow_patch = getenv("YP_CONV_NO_PATCH") == nullptr;
   static const int base_offset_mode = getenv("YP_CONV_BASE_OFFSET") ? atoi(getenv("YP_CONV_BASE_OFFSET")) : 0;
-  a.patch = (allow_patch && d.ksize == 3 && d.stride == 1 && a.ck_bytes >= 64 && !(d.epilogue & YP_EPI_NO_PATCH)) ? 1 : 0;
+  a.patch = (allow_patch && !no_patch && d.ksize == 3 && d.stride == 1 && a.ck_bytes >= 64 && !(d.epilogue & YP_EPI_NO_PATCH)) ? 1 : 0;
   a.base_offset_mode = base_offset_mode;
   if (a.patch) {
     pick_patch_padded(Ho, Wo, &a.Ht, &a.Wt);
@@ -811,7 +812,7 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
 
   // ---- split-K: deep layers on small feature maps occupy few CTAs; slice K over grid.z so that ~#SM CTAs are busy.
   int S = 1;
-  if (allow_split && d.split_k != 1) {
+  if (allow_split && d.split_k != 1 && static_cast<size_t>(m_tiles) * n_tiles * sizeof(int) <= kWsCounterBytes) {
     const int ctas = m_tiles * n_tiles;
     int want = d.split_k > 1 ? d.split_k : nsm / ctas;
     if (want > 16) want = 16;
@@ -904,7 +905,7 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
     if (2 * a.a_stage_bytes + 2 * a.b_stage_bytes > budget) budget = 200 * 1024;
     int bs = (budget - 2 * a.a_stage_bytes) / a.b_stage_bytes;
     if (bs > kMaxStages) bs = kMaxStages;
-    YP_REQUIRE(bs >= 2, YP_ERR_SHAPE, "conv(patch): %d-byte patch stages leave no room for the weight ring", a.a_stage_bytes);
+    if (bs < 2) { *patch_no_fit = true; return YP_ERR_SHAPE; }   // caller re-plans with per-tap loads
     a.b_stages = bs;
     a.stages = bs;
     region = 2 * a.a_stage_bytes + bs * a.b_stage_bytes;
@@ -924,9 +925,20 @@ int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
   P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 6) + Nt * sizeof(float) + 16;
   YP_REQUIRE(P->smem <= 227 * 1024, YP_ERR_SHAPE, "conv: needs %zu bytes of shared memory", P->smem);
   P->grid = dim3(m_tiles, n_tiles, S);
-  P->ws_counter_bytes = (static_cast<size_t>(m_tiles) * n_tiles * sizeof(int) + 255) & ~static_cast<size_t>(255);
+  // The arrival counters live in a FIXED-size area at the start of the workspace: layers of one lane share the workspace,
+  // and a per-layer counter area would overlap the partial sums an earlier (smaller) layer left behind.
+  P->ws_counter_bytes = kWsCounterBytes;
   P->ws_bytes = S > 1 ? P->ws_counter_bytes + static_cast<size_t>(S) * m_tiles * n_tiles * 128 * Nt * sizeof(float) : 0;
   return YP_OK;
+}
+
+// Patch mode keeps two input patches resident; when the weight ring no longer fits beside them (wide L2-norm head)
+// the layer is planned with per-tap loads instead.
+int plan_conv(const YpConvDesc& d, ConvPlan* P, bool allow_split) {
+  bool no_fit = false;
+  const int rc = plan_conv_impl(d, P, allow_split, false, &no_fit);
+  if (rc != YP_OK && no_fit) return plan_conv_impl(d, P, allow_split, true, &no_fit);
+  return rc;
 }
 
 }  // namespace
