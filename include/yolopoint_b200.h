@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YP_ABI_VERSION 1
+#define YP_ABI_VERSION 2
 
 typedef enum {
   YP_OK = 0,
@@ -64,8 +64,11 @@ typedef struct {
   int32_t format;       /* YpFormat */
   int32_t upsample;     /* outputs only: 1 = store as is, 2 = store each pixel to the 2x2 block of a
                            (2H x 2W) destination (nn.Upsample(2,'nearest') fused into the producer);
-                           H, W are then the SOURCE (pre-upsample) extents */
+                           H, W are then the SOURCE (pre-upsample) extents;
+                           YP_UP_PARITY + 2*ph + pw = store pixel (h, w) to (2h+ph, 2w+pw) of a (2H x 2W) destination only
+                           (one parity class of a stride-2 data gradient, see yp_conv2d_nhwc_fwd) */
 } YpView;
+#define YP_UP_PARITY 16
 
 typedef enum { YP_ACT_NONE = 0, YP_ACT_SILU = 1 } YpAct;
 typedef enum { YP_ALGO_TCGEN05 = 0, YP_ALGO_SIMT = 1 } YpConvAlgo;
@@ -90,7 +93,7 @@ typedef struct {
   YpView in;
   const void* weight;
   const float* bias;
-  int32_t ksize, stride;  /* (1,1) (3,1) (3,2) */
+  int32_t ksize, stride;  /* (1,1) (3,1) (3,2); (0,1) = custom tap list below */
   int32_t cout;
   int32_t act;            /* YpAct */
   uint32_t epilogue;      /* YP_EPI_* flags */
@@ -103,11 +106,35 @@ typedef struct {
   void* workspace;        /* split-K scratch (zero-initialised once by the caller, reusable by later launches on the same
                              stream; launches that may run concurrently need distinct workspaces); NULL -> never split */
   uint64_t workspace_bytes;
+  /* ksize == 0: out[p] = sum_t W[:, t, :] . in[p + (tap_dh[t], tap_dw[t])], zero outside the input; 1 <= n_taps <= 9, offsets in
+     [-8, 7].  Used for the data gradient of stride-2 convs (one launch per output parity class, see yolopoint_b200/train.py:
+     autograd of models/common.py:22-34 in the reference's training step, train.py:208-220). */
+  int32_t n_taps;
+  int8_t tap_dh[9], tap_dw[9];
 } YpConvDesc;
 
 int yp_conv2d_nhwc_fwd(const YpConvDesc* desc, void* stream);
 /* Bytes of split-K workspace yp_conv2d_nhwc_fwd would like for this descriptor (0 = it will not split). */
 size_t yp_conv2d_workspace_bytes(const YpConvDesc* desc);
+
+/*
+ * yp_conv2d_nhwc_wgrad -- weight gradient of a Conv2d (bias-free, pad = k/2) for the training step: what autograd computes
+ * for nn.Conv2d inside models/common.py:22-34 when train.py:208-220 calls loss.backward().
+ *   dw[co][tap * Cin + ci] += sum_{b,oh,ow} dy[b,oh,ow,co] * x[b, oh*s + kh - k/2, ow*s + kw - k/2, ci]     (tap = kh*3 + kw)
+ * x, dy: bf16 NHWC views; dw: fp32 [Cout][taps*Cin] (the packed layout of yp_conv2d_nhwc_fwd weights), ACCUMULATED into --
+ * the caller zero-fills it (or keeps accumulating over micro-batches).  Geometry: 1x1 s1, 3x3 s1, 3x3 s2; Cin, Cout multiples
+ * of 8; output width <= 254.  Partial sums of the CTAs that share a dw tile are combined with fp32 reductions in L2
+ * (summation order, hence the last bits, may differ between runs -- like the reference's cuDNN wgrad).
+ * The data gradient needs no entry point of its own: it is yp_conv2d_nhwc_fwd on dy with the transposed, tap-flipped weights
+ * (stride 2: four launches with a custom tap list, one per output parity class).
+ */
+typedef struct {
+  YpView x;
+  YpView dy;
+  int32_t ksize, stride;
+  float* dw;
+} YpWgradDesc;
+int yp_conv2d_nhwc_wgrad(const YpWgradDesc* desc, void* stream);
 
 /* Debug aid: when set to a device buffer of 512 int64, CTA (0,0) of every following tcgen05 conv launch records clock64
  * stamps of its pipeline events there (see tools/conv_timeline.py); NULL switches it off.  Not thread safe. */

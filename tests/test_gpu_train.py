@@ -1,0 +1,149 @@
+"""GPU parity of the training-step convolutions: forward, data gradient and weight gradient on
+the tcgen05 kernels vs PyTorch autograd (fp64 conv on the SAME bf16-rounded operands), and one whole train-mode
+forward/backward of the model vs the PyTorch/cuDNN fp32 path.
+
+Tolerances: the kernels multiply bf16 operands exactly and accumulate in fp32, so against an fp64 reference on the same
+operands the only differences are fp32 summation order and the bf16 rounding of the result (forward / dgrad outputs are
+bf16: 2^-8 relative; wgrad output is fp32: 1e-4 of the tensor's scale)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from yolopoint_b200 import Model
+from yolopoint_b200 import train as T
+
+pytestmark = pytest.mark.gpu
+CL = torch.channels_last
+
+
+def _mk(B, Ci, Co, H, W, k, s, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Ci, H, W, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=CL)
+    w = (torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5).cuda().to(torch.bfloat16).float()
+    dy = torch.randn(B, Co, H // s, W // s, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=CL)
+    return x, w, dy
+
+
+def _ref(x, w, dy, k, s):
+    xd = x.double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    y = F.conv2d(xd, wd, None, s, k // 2)
+    y.backward(dy.double())
+    return y.detach(), xd.grad, wd.grad
+
+
+def _rel(a, b):
+    return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+SHAPES = [
+    # B, Ci, Co, H, W, k, s
+    (2, 64, 128, 16, 24, 1, 1),
+    (2, 128, 128, 20, 20, 3, 1),
+    (1, 64, 64, 40, 40, 3, 1),
+    (2, 64, 128, 32, 48, 3, 2),
+    (1, 256, 128, 20, 20, 1, 1),
+    (2, 96, 192, 24, 40, 3, 2),      # YOLOPoint-M widths: ci / co blocks that are not multiples of 64 / 128
+    (1, 192, 96, 23, 40, 3, 1),      # odd height
+    (3, 16, 64, 48, 80, 3, 1),       # stem-like: Cin = 16
+    (1, 512, 512, 8, 8, 3, 1),
+    (1, 128, 256, 80, 160, 1, 1),    # strip longer than one row pair
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_wgrad(shape):
+    B, Ci, Co, H, W, k, s = shape
+    x, w, dy = _mk(*shape)
+    _, _, dw_ref = _ref(x, w, dy, k, s)
+    dw = T.conv_wgrad(x, dy, k, s)
+    e = _rel(dw, dw_ref)
+    print(shape, "wgrad rel err", e)
+    assert e < 1e-4, (shape, e)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_dgrad(shape):
+    B, Ci, Co, H, W, k, s = shape
+    x, w, dy = _mk(*shape)
+    _, dx_ref, _ = _ref(x, w, dy, k, s)
+    dx = T.conv_dgrad(dy, w, s, H, W)
+    e = _rel(dx, dx_ref)
+    print(shape, "dgrad rel err", e)
+    assert e < 1e-2, (shape, e)          # bf16 output: 2^-8 relative
+
+
+@pytest.mark.parametrize("shape", SHAPES[:6])
+def test_autograd_function(shape):
+    B, Ci, Co, H, W, k, s = shape
+    x, w, dy = _mk(*shape)
+    y_ref, dx_ref, dw_ref = _ref(x, w, dy, k, s)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    y = T.conv2d_tc(xr, wr, None, s)
+    y.backward(dy)
+    assert _rel(y, y_ref) < 1e-2 and _rel(xr.grad, dx_ref) < 1e-2 and _rel(wr.grad, dw_ref) < 1e-4
+
+
+def test_padded_channels_and_bias():
+    """Cout = 255 (Detect) and 65 (ConvDet) go through zero padding around the kernel; bias is added outside."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 128, 12, 20, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=CL)
+    for co in (255, 65):
+        w = (torch.randn(co, 128, 1, 1, generator=g) / 11.0).cuda().to(torch.bfloat16).float().requires_grad_(True)
+        b = torch.randn(co, generator=g).cuda().requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        y = T.conv2d_tc(xr, w, b, 1)
+        dy = torch.randn(y.shape, generator=g).cuda().to(torch.bfloat16)
+        y.backward(dy)
+        xd, wd, bd = x.double().requires_grad_(True), w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+        yr = F.conv2d(xd, wd, bd)
+        yr.backward(dy.double())
+        assert y.shape == yr.shape
+        assert _rel(y, yr.detach()) < 2e-2 and _rel(xr.grad, xd.grad) < 1e-2 and _rel(w.grad, wd.grad) < 1e-4 and _rel(b.grad, bd.grad) < 1e-2
+
+
+def test_model_train_step_matches_torch():
+    """One train-mode forward/backward of YOLOPoint-N through the B200 conv kernels vs the PyTorch fp32 path on the same
+    parameters: outputs within bf16 noise, every parameter receives a gradient that points the same way."""
+    torch.manual_seed(0)
+    names = [str(i) for i in range(80)]
+    m = Model(names=names, version="n").cuda().train()
+    x = torch.rand(2, 3, 128, 160, device="cuda")
+
+    def run(backend):
+        m.train_backend = backend
+        m.zero_grad(set_to_none=True)
+        out = m(x)
+        loss = out["semi"].float().square().mean() + out["desc"].float()[:, ::2].mean() * 3 + sum(r.float().square().mean() for r in out["objects"])
+        loss.backward()
+        grads = {n: p.grad.detach().float().clone() for n, p in m.named_parameters() if p.grad is not None}
+        return {k: (v if k != "objects" else v) for k, v in out.items()}, float(loss), grads
+
+    bn_state = {k: v.clone() for k, v in m.state_dict().items()}
+    res = {}
+    for backend in ("torch", "cudnn_bf16", "b200"):
+        m.load_state_dict(bn_state)           # same BN running statistics for every run
+        res[backend] = run(backend)
+    assert any(type(mod).__name__ == "TcConv2d" and not mod._tc_cudnn for mod in m.modules())
+    (out_t, loss_t, g_t), (out_c, loss_c, g_c), (out_b, loss_b, g_b) = res["torch"], res["cudnn_bf16"], res["b200"]
+    assert len(g_b) == len(g_t) == len(list(m.parameters()))
+    assert abs(loss_b - loss_t) < 2e-2 * max(1.0, abs(loss_t)), (loss_b, loss_t)
+    assert _rel(out_b["semi"].detach(), out_t["semi"].detach().double()) < 5e-2
+
+    def cosines(ga, gb):
+        cs = []
+        for n in gb:
+            a, b = ga[n].flatten().double(), gb[n].flatten().double()
+            if float(b.norm()) >= 1e-12:
+                cs.append(float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30)))
+        return np.array(cs)
+
+    c_kernel = cosines(g_b, g_c)      # same rounding points, different conv kernels: isolates the kernels
+    c_bf16 = cosines(g_c, g_t)        # what bf16 itself costs against fp32 on this (random-weight, batch 2) network
+    c_total = cosines(g_b, g_t)
+    for tag, c in (("b200 vs cudnn_bf16", c_kernel), ("cudnn_bf16 vs fp32", c_bf16), ("b200 vs fp32", c_total)):
+        print(f"grad cosine {tag}: min {c.min():.4f} median {np.median(c):.4f} n {len(c)}")
+    assert np.median(c_kernel) > 0.995 and c_kernel.min() > 0.9
+    assert np.median(c_total) > np.median(c_bf16) - 0.05

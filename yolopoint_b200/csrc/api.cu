@@ -31,6 +31,7 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st);
 size_t conv_tc_workspace_bytes(const YpConvDesc& d);
 int conv_simt_forward(const YpConvDesc& d, cudaStream_t st);
 void set_conv_timeline(long long* p);
+int wgrad_tc(const YpWgradDesc& d, cudaStream_t st);
 
 }  // namespace yp
 
@@ -64,4 +65,9 @@ extern "C" int yp_debug_conv_timeline(void* device_buf_512_i64) {
 extern "C" size_t yp_conv2d_workspace_bytes(const YpConvDesc* d) {
   if (!d || d->algo != YP_ALGO_TCGEN05) return 0;
   return yp::conv_tc_workspace_bytes(*d);
+}
+
+extern "C" int yp_conv2d_nhwc_wgrad(const YpWgradDesc* d, void* stream) {
+  YP_REQUIRE(d && d->x.base && d->dy.base && d->dw, YP_ERR_ARG, "wgrad: null pointer in descriptor");
+  return yp::wgrad_tc(*d, static_cast<cudaStream_t>(stream));
 }

@@ -14,6 +14,7 @@
 // epilogue (TMEM -> registers -> bias/SiLU/residual/L2-norm -> swizzled smem -> TMA store to 1..8 maps:
 // channel-slice (concat) destinations and the four parity views of a 2x-upsampled destination).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -23,133 +24,6 @@
 
 namespace yp {
 namespace {
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a pipeline bug must fail loudly, not hang the GPU
-      if ((threadIdx.x & 31) == 0)
-        printf("yolopoint_b200 conv_tc: mbarrier timeout (block %d,%d warp %d)\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <bool kTf32>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if (kTf32) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  }
-}
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives row (lane_base + i).  Asynchronous:
-// the registers are valid only after tmem_ld_wait().
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major shared-memory operand descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64).
-// For swizzled K-major tiles LBO is ignored (1), SBO = 8 rows * row bytes.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_bytes) {
-  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) |
-         (static_cast<uint64_t>((8u * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
-}
-// Same for a 128B-swizzled operand whose first row is NOT at a 1024-byte boundary (a row-shifted window of a larger
-// shared-memory patch).  Measured on B200: the tensor core derives the swizzle phase from the absolute shared-memory
-// address (as TMA does), so a window that starts at any 128-byte row of a 1024-byte-aligned patch needs base_offset = 0;
-// setting base_offset = (start >> 7) & 7 gives wrong results (tests/test_gpu_conv.py with YP_CONV_BASE_OFFSET=1).
-__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t saddr, uint32_t row_bytes, int use_base_offset) {
-  uint64_t d = make_smem_desc(saddr, row_bytes);
-  if (use_base_offset) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
-  return d;
-}
-
-// byte address inside a TMA-swizzled tile: row r, 16-byte chunk j, rows of row_bytes (128/64/32)
-__device__ __forceinline__ uint32_t swz_addr(uint32_t tile_base, uint32_t r, uint32_t j, uint32_t row_bytes) {
-  const uint32_t a = tile_base + r * row_bytes + j * 16u;
-  const uint32_t mask = (row_bytes >> 4) - 1u;  // 7, 3, 1
-  return a ^ (((a >> 7) & mask) << 4);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Kernel arguments
@@ -163,6 +37,7 @@ struct alignas(64) ConvMaps {
 struct ConvArgs {
   int tiles_w, tiles_h, Ht, Wt, Ho, Wo;
   int ksize, stride;
+  unsigned long long tap_dh, tap_dw;   // custom tap list (ksize == 0): 4 bits per tap, offset + 8
   int n_taps, kb_per_tap, ck_bytes, ck_elems;
   int in_planes, a_split;          // a_split: 1 = both planes of A arrive with one TMA (box plane dim 2)
   int a_plane_off;                 // smem byte offset of the lo plane inside the A region
@@ -308,6 +183,9 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
           const int kh = tap / 3, kw = tap - kh * 3;
           if (a.stride == 1) { dh = kh - 1; dw = kw - 1; }
           else { map = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1); dh = (kh == 0) ? -1 : 0; dw = (kw == 0) ? -1 : 0; }
+        } else if (a.ksize == 0) {
+          dh = static_cast<int>((a.tap_dh >> (4 * tap)) & 15ull) - 8;
+          dw = static_cast<int>((a.tap_dw >> (4 * tap)) & 15ull) - 8;
         }
         const uint32_t st = smem_base + s * a.stage_bytes;
         tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
@@ -725,8 +603,9 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   YP_REQUIRE(in_fmt == YP_FMT_F32X2 || in_fmt == YP_FMT_BF16, YP_ERR_SHAPE, "conv: input format %d unsupported", in_fmt);
   const bool tf32 = in_fmt == YP_FMT_F32X2;
   const int es = fmt_esize(in_fmt);
-  YP_REQUIRE((d.ksize == 1 && d.stride == 1) || (d.ksize == 3 && (d.stride == 1 || d.stride == 2)), YP_ERR_SHAPE,
-             "conv: k=%d s=%d unsupported", d.ksize, d.stride);
+  YP_REQUIRE((d.ksize == 1 && d.stride == 1) || (d.ksize == 3 && (d.stride == 1 || d.stride == 2)) ||
+                 (d.ksize == 0 && d.stride == 1 && d.n_taps >= 1 && d.n_taps <= 9), YP_ERR_SHAPE,
+             "conv: k=%d s=%d (n_taps=%d) unsupported", d.ksize, d.stride, d.n_taps);
   YP_REQUIRE(in.C % 16 == 0 && d.cout % 16 == 0, YP_ERR_SHAPE, "conv: Cin=%d / Cout=%d must be multiples of 16", in.C, d.cout);
   YP_REQUIRE(d.stride == 1 || (in.H % 2 == 0 && in.W % 2 == 0), YP_ERR_SHAPE, "conv: stride 2 needs even H,W");
   YP_REQUIRE(d.n_out >= 1 && d.n_out <= 2, YP_ERR_SHAPE, "conv: n_out=%d", d.n_out);
@@ -738,7 +617,12 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   a.Ho = Ho; a.Wo = Wo; a.ksize = d.ksize; a.stride = d.stride;
   pick_patch(Ho, Wo, &a.Ht, &a.Wt);
   a.tiles_w = ceil_div(Wo, a.Wt); a.tiles_h = ceil_div(Ho, a.Ht);
-  a.n_taps = d.ksize * d.ksize;
+  a.n_taps = d.ksize ? d.ksize * d.ksize : d.n_taps;
+  for (int t = 0; t < a.n_taps && d.ksize == 0; ++t) {
+    YP_REQUIRE(d.tap_dh[t] >= -8 && d.tap_dh[t] <= 7 && d.tap_dw[t] >= -8 && d.tap_dw[t] <= 7, YP_ERR_SHAPE, "conv: tap offset out of range");
+    a.tap_dh |= static_cast<unsigned long long>(d.tap_dh[t] + 8) << (4 * t);
+    a.tap_dw |= static_cast<unsigned long long>(d.tap_dw[t] + 8) << (4 * t);
+  }
   const int cin_bytes = in.C * es;
   a.ck_bytes = cin_bytes % 128 == 0 ? 128 : (cin_bytes % 64 == 0 ? 64 : 32);
   a.ck_elems = a.ck_bytes / es;
@@ -997,6 +881,9 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
       for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw)
           if ((rc = encode_view(&maps.out[nm++], o, 2, ph, pw, 2 * Wo, 2 * Ho, chunk_elems, a.Wt, a.Ht)) != YP_OK) return rc;
+    } else if (o.upsample >= YP_UP_PARITY && o.upsample < YP_UP_PARITY + 4) {   // one parity class of a 2x larger destination
+      const int pp = o.upsample - YP_UP_PARITY;
+      if ((rc = encode_view(&maps.out[nm++], o, 2, pp >> 1, pp & 1, 2 * Wo, 2 * Ho, chunk_elems, a.Wt, a.Ht)) != YP_OK) return rc;
     } else {
       if ((rc = encode_view(&maps.out[nm++], o, 1, 0, 0, Wo, Ho, chunk_elems, a.Wt, a.Ht)) != YP_OK) return rc;
     }

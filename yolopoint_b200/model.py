@@ -8,8 +8,9 @@ seeded initialisation -- and the same ``forward`` contract
 Execution:
   * eval mode  -> the B200 engine (``engine.Engine``): hand-written sm_100a kernels through the C ABI.  There is
     no fallback; a missing library or a non-sm_100 device raises.
-  * train mode -> plain PyTorch autograd over the same parameters (what the reference itself does).  The
-    training-step kernels are not part of this round; see DESIGN.md.
+  * train mode -> the same module tree under autograd; on a CUDA device every convolution (forward, data gradient, weight
+    gradient: SURVEY.md section 8 row a11) runs on the tcgen05 kernels (``train.py``), bf16 operands / fp32 accumulation;
+    BatchNorm, SiLU, concat, pooling and the losses stay PyTorch ops on the same channels-last tensors.
 """
 from __future__ import annotations
 
@@ -109,7 +110,8 @@ class Detect(nn.Module):
         for i, x in enumerate(xs):
             x = self.m[i](x)
             bs, _, ny, nx = x.shape
-            x = x.view(bs, self.na, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
+            # reshape, not view: the B200 training path hands over channels-last tensors (bf16), returned to the losses as fp32
+            x = x.float().reshape(bs, self.na, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
             raw.append(x)
             if not self.training:
                 yv, xv = torch.meshgrid(torch.arange(ny, device=x.device), torch.arange(nx, device=x.device), indexing="ij")
@@ -154,10 +156,10 @@ class YOLOPoint(nn.Module):
     def forward(self, x):  # PyTorch path (training); dataflow of src/models/YOLOPoint.py:198-246
         xa = self.Bottleneck1(self.Conv2(self.Conv1(x)))
         x = self.Conv3(xa)
-        semi = self.ConvDet(self.BottleneckDet(x))
+        semi = self.ConvDet(self.BottleneckDet(x)).float()
         xb = self.Bottleneck2(x)
         desc = torch.cat((self.ConvDescA(xa), self.ups(self.ConvDescB(xb))), 1)
-        desc = self.ConvDesc(self.BottleneckDesc(desc))
+        desc = self.ConvDesc(self.BottleneckDesc(desc)).float()
         desc = desc.div(torch.unsqueeze(torch.norm(desc, p=2, dim=1), 1))
         xc = self.Bottleneck3(self.Conv4(xb))
         xd = self.Conv6(self.SPPooling(self.Bottleneck4(self.Conv5(xc))))
@@ -203,6 +205,9 @@ class Model(nn.Module):
         self._initialize_biases()
         self._engine = None
         self._fused = False
+        # "b200": tcgen05 conv fwd/dgrad/wgrad on CUDA inputs; "torch": PyTorch/cuDNN fp32 autograd (the reference's own path);
+        # "cudnn_bf16": the b200 dataflow (bf16 channels-last) with cuDNN convolutions -- cross-check for the tests
+        self.train_backend = "b200"
 
     @staticmethod
     def _check_anchor_order(m):
@@ -222,6 +227,17 @@ class Model(nn.Module):
     # -- execution ---------------------------------------------------------------------------
     def forward(self, x):
         if self.training:
+            # CUDA tensors: the convolutions (forward, data and weight gradients) run on the tcgen05 kernels (train.py), bf16
+            # operands with fp32 accumulation; CPU tensors: plain PyTorch autograd over the same parameters (host-side tests).
+            if x.is_cuda and self.train_backend in ("b200", "cudnn_bf16"):
+                if getattr(self, "_tc_train", None) != self.train_backend:
+                    from . import train as _train
+                    _train.enable(self, cudnn_crosscheck=self.train_backend == "cudnn_bf16")
+                    self._tc_train = self.train_backend
+            elif getattr(self, "_tc_train", None):
+                from . import train as _train
+                _train.disable(self)
+                self._tc_train = None
             return self.model(x)
         return self.engine().forward(x)
 

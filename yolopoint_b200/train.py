@@ -1,0 +1,221 @@
+"""Training-step convolutions on the B200 kernels.
+
+The reference trains by calling ``loss.backward()`` on the outputs of ``Model.forward`` in train mode
+(src/train.py:208-220); autograd then needs, for every ``nn.Conv2d`` of src/models/common.py:22-34, the forward product,
+the data gradient and the weight gradient.  Those three dense contractions are the training hot path (>97 % of the step's
+FLOPs) and run here on the tcgen05 kernels of libyolopoint_b200.so:
+
+  forward   y  = conv(x, W)              yp_conv2d_nhwc_fwd        (bf16 operands, fp32 accumulation, bf16 result)
+  dgrad     dx = conv^T(dy, W)           yp_conv2d_nhwc_fwd on dy with transposed, tap-flipped weights; stride 2 = four
+                                         launches with a custom tap list, one per output parity class (no zero insertion)
+  wgrad     dW = x^T * dy                yp_conv2d_nhwc_wgrad      (MN-major tcgen05 GEMM over pixels, fp32 result)
+
+Everything between the convolutions (BatchNorm statistics, SiLU, concat, upsample, max-pool, the losses, Adam) is PyTorch
+glue on channels-last bf16 tensors, exactly the tensors the kernels read and write (no layout conversion in between).
+
+``enable(model)`` switches a ``yolopoint_b200.Model`` in train mode to this path; there is no silent fallback: on a device
+that is not sm_100 the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import YP_ACT_NONE, YP_ALGO_TCGEN05, YP_FMT_BF16, YP_UP_PARITY, YpConvDesc, YpView, YpWgradDesc
+
+_CL = torch.channels_last
+
+
+def _view(t: torch.Tensor, upsample: int = 1, hw=None) -> YpView:
+    """t: [B,C,H,W] bf16 tensor that is contiguous in channels-last order -> NHWC view of all its channels."""
+    B, Cc, H, W = t.shape
+    assert t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=_CL), (t.dtype, t.shape, t.stride())
+    v = YpView()
+    v.base = t.data_ptr()
+    v.B, v.C = B, Cc
+    v.H, v.W = hw if hw is not None else (H, W)
+    v.pix_stride = Cc
+    v.plane_stride = 0
+    v.format = YP_FMT_BF16
+    v.upsample = upsample
+    return v
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    t = t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
+    return t.contiguous(memory_format=_CL)
+
+
+def pack_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Co,Ci,kh,kw] -> bf16 [Co, taps*Ci] with K index = tap*Ci + ci (the layout of yp_conv2d_nhwc_fwd weights)."""
+    co = w.shape[0]
+    return w.permute(0, 2, 3, 1).reshape(co, -1).to(torch.bfloat16).contiguous()
+
+
+def _launch_conv(x, wp, y, ksize, stride, n_taps=0, dh=(), dw=(), up=1, out_hw=None):
+    L = _lib.lib(require_device=True)
+    d = YpConvDesc()
+    d.in_ = _view(x)
+    d.weight, d.bias = wp.data_ptr(), None
+    d.ksize, d.stride, d.cout, d.act, d.epilogue, d.n_out = ksize, stride, wp.shape[0], YP_ACT_NONE, 0, 1
+    d.out[0] = _view(y, upsample=up, hw=out_hw)
+    d.algo, d.split_k = YP_ALGO_TCGEN05, 1
+    if ksize == 0:
+        d.n_taps = n_taps
+        for i in range(n_taps):
+            d.tap_dh[i], d.tap_dw[i] = dh[i], dw[i]
+    _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), _stream()))
+
+
+def conv_forward(x: torch.Tensor, w: torch.Tensor, stride: int) -> torch.Tensor:
+    B, Ci, H, W = x.shape
+    Co, _, k, _ = w.shape
+    y = torch.empty((B, Co, H // stride, W // stride), dtype=torch.bfloat16, device=x.device, memory_format=_CL)
+    _launch_conv(x, pack_weight(w), y, k, stride)
+    return y
+
+
+def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, H: int, W: int) -> torch.Tensor:
+    """dx[b,ih,iw,ci] = sum_{kh,kw,co} dy[b,(ih+p-kh)/s,(iw+p-kw)/s,co] * w[co,ci,kh,kw]  (terms with integral indices)."""
+    B, Co, Ho, Wo = dy.shape
+    _, Ci, k, _ = w.shape
+    dx = torch.empty((B, Ci, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=_CL)
+    if stride == 1:
+        # a forward conv over dy with the taps flipped and (co, ci) transposed
+        wt = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, -1).to(torch.bfloat16).contiguous()   # [Ci, taps*Co]
+        _launch_conv(dy, wt, dx, k, 1)
+        return dx
+    assert k == 3 and stride == 2
+    wb = w.to(torch.bfloat16)
+    for ph in range(2):
+        for pw in range(2):
+            khs = [1] if ph == 0 else [0, 2]
+            kws = [1] if pw == 0 else [0, 2]
+            taps = [(kh, kw) for kh in khs for kw in kws]
+            dh = [(ph + 1 - kh) // 2 for kh, _ in taps]
+            dw = [(pw + 1 - kw) // 2 for _, kw in taps]
+            wt = torch.stack([wb[:, :, kh, kw].t() for kh, kw in taps], 1).reshape(Ci, -1).contiguous()   # [Ci, n_taps*Co]
+            _launch_conv(dy, wt, dx, 0, 1, len(taps), dh, dw, up=YP_UP_PARITY + 2 * ph + pw, out_hw=(Ho, Wo))
+    return dx
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, stride: int) -> torch.Tensor:
+    """-> fp32 [Co,Ci,k,k]"""
+    L = _lib.lib(require_device=True)
+    Ci, Co = x.shape[1], dy.shape[1]
+    dwp = torch.zeros((Co, ksize * ksize * Ci), dtype=torch.float32, device=x.device)
+    d = YpWgradDesc()
+    d.x, d.dy = _view(x), _view(dy)
+    d.ksize, d.stride, d.dw = ksize, stride, dwp.data_ptr()
+    _lib.check(L.yp_conv2d_nhwc_wgrad(C.byref(d), _stream()))
+    return dwp.view(Co, ksize, ksize, Ci).permute(0, 3, 1, 2)
+
+
+class _Conv2dTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stride):
+        x = _cl(x)
+        ctx.save_for_backward(x, w)
+        ctx.stride = stride
+        return conv_forward(x, w, stride)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _cl(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_dgrad(dy, w, ctx.stride, x.shape[2], x.shape[3])
+        if ctx.needs_input_grad[1]:
+            dw = conv_wgrad(x, dy, w.shape[2], ctx.stride).to(w.dtype)
+        return dx, dw, None
+
+
+def supported(w: torch.Tensor, stride: int, x: Optional[torch.Tensor] = None) -> bool:
+    co, ci, k, k2 = w.shape
+    ok = k == k2 and ((k == 1 and stride == 1) or (k == 3 and stride in (1, 2)))
+    if x is not None:
+        wo = x.shape[3] // stride
+        ok = ok and (wo + (2 if k == 3 else 0)) <= 256 and x.shape[2] % stride == 0 and x.shape[3] % stride == 0
+    return ok
+
+
+def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1) -> torch.Tensor:
+    """Differentiable bias-free conv (pad = k // 2) on the tcgen05 kernels; x [B,Ci,H,W] (any float dtype, converted to
+    channels-last bf16), w [Co,Ci,k,k] (fp32 master weights) -> bf16 channels-last [B,Co,H/s,W/s].  Channel counts that are
+    not multiples of 16 (Detect: 255, ConvDet: 65) are zero-padded with differentiable torch ops around the kernel."""
+    co, ci = w.shape[0], w.shape[1]
+    pad_o, pad_i = (-co) % 16, (-ci) % 16
+    if pad_i:
+        x = F.pad(x, (0, 0, 0, 0, 0, pad_i))
+    if pad_o or pad_i:
+        w = F.pad(w, (0, 0, 0, 0, 0, pad_i, 0, pad_o))
+    y = _Conv2dTC.apply(x, w, stride)
+    if pad_o:
+        y = y[:, :co]
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1).to(y.dtype)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# module-tree integration
+# ------------------------------------------------------------------------------------------------------------------
+def _stem_s2d(x: torch.Tensor, w: torch.Tensor):
+    """6x6 s2 p2 conv on 3 channels == 3x3 s1 p1 conv on the 2x2 space-to-depth image (channel = (ph*2+pw)*3 + c); both
+    rearrangements are differentiable torch ops, so autograd maps the kernel's [Co,12,3,3] gradient back to [Co,3,6,6]."""
+    B, Cc, H, W = x.shape
+    xs = x.view(B, Cc, H // 2, 2, W // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(B, 4 * Cc, H // 2, W // 2)
+    co = w.shape[0]
+    ws = w.view(co, Cc, 3, 2, 3, 2).permute(0, 3, 5, 1, 2, 4).reshape(co, 4 * Cc, 3, 3)
+    return xs, ws
+
+
+class TcConv2d(nn.Conv2d):
+    """nn.Conv2d whose training-mode forward/backward run on the tcgen05 kernels (same parameters / state-dict keys)."""
+
+    def forward(self, x):
+        if not (self.training and x.is_cuda):
+            return super().forward(x)
+        k, s, p = self.kernel_size[0], self.stride[0], self.padding[0]
+        w = self.weight
+        if getattr(self, "_tc_cudnn", False):   # cross-check mode (tests): cuDNN on the same bf16 channels-last tensors
+            return F.conv2d(_cl(x), w.to(torch.bfloat16), None if self.bias is None else self.bias.to(torch.bfloat16), self.stride, self.padding)
+        if (k, s, p) == (6, 2, 2) and w.shape[1] == 3 and x.shape[3] // 2 + 2 <= 256:
+            xs, ws = _stem_s2d(x, w)
+            return conv2d_tc(xs, ws, self.bias, 1)
+        if p == k // 2 and supported(w, s, x):
+            return conv2d_tc(x, w, self.bias, s)
+        # geometry outside the kernels' range (e.g. a stem wider than 508 pixels): cuDNN on the same bf16 channels-last tensors
+        y = F.conv2d(_cl(x), w.to(torch.bfloat16), None if self.bias is None else self.bias.to(torch.bfloat16), self.stride, self.padding)
+        return y
+
+
+def enable(model: nn.Module, cudnn_crosscheck: bool = False) -> nn.Module:
+    """Route every nn.Conv2d of the module tree through the B200 kernels in train mode (in place; parameters are shared,
+    state-dict keys unchanged).  BatchNorm keeps fp32 parameters / statistics and consumes the bf16 activations directly.
+    ``cudnn_crosscheck`` keeps the same bf16 channels-last dataflow but calls cuDNN for the convolutions (test oracle)."""
+    _lib.lib(require_device=True)
+    for mod in model.modules():
+        if type(mod) in (nn.Conv2d, TcConv2d):
+            mod.__class__ = TcConv2d
+            mod._tc_cudnn = cudnn_crosscheck
+    model._tc_train = True
+    return model
+
+
+def disable(model: nn.Module) -> nn.Module:
+    for mod in model.modules():
+        if type(mod) is TcConv2d:
+            mod.__class__ = nn.Conv2d
+    model._tc_train = False
+    return model
