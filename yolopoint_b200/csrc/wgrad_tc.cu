@@ -196,10 +196,11 @@ PFN_cuTensorMapEncodeTiled_v12000 wg_encode() {
   return g_wg_encode;
 }
 
-// 4-D map (C, W, H, B) over a bf16 NHWC view; sub = 2 selects the (ph, pw) parity view.
-int encode_nhwc(CUtensorMap* tm, const YpView& v, int sub, int ph, int pw, int box_w, int box_h) {
-  char* base = static_cast<char*>(v.base) + (static_cast<int64_t>(ph) * v.W + pw) * v.pix_stride * 2;
-  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)(v.W / sub), (cuuint64_t)(v.H / sub), (cuuint64_t)v.B};
+// 4-D map (C, W, H, B) over a bf16 NHWC view.  sub = 2 selects the (ph, pw) parity view; `col0` / `n_cols` restrict the map to
+// the columns [col0, col0 + n_cols) of that (sub-sampled) view, so that everything outside reads as zero (TMA out-of-bounds fill).
+int encode_nhwc(CUtensorMap* tm, const YpView& v, int sub, int ph, int pw, int col0, int n_cols, int box_w, int box_h) {
+  char* base = static_cast<char*>(v.base) + ((static_cast<int64_t>(ph) * v.W + pw) + static_cast<int64_t>(col0) * sub) * v.pix_stride * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)n_cols, (cuuint64_t)(v.H / sub), (cuuint64_t)v.B};
   cuuint64_t strides[3] = {(cuuint64_t)(v.pix_stride * sub * 2), (cuuint64_t)(v.pix_stride * v.W * sub * 2),
                            (cuuint64_t)(static_cast<int64_t>(v.H) * v.W * v.pix_stride * 2)};
   cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
@@ -208,46 +209,38 @@ int encode_nhwc(CUtensorMap* tm, const YpView& v, int sub, int ph, int pw, int b
   for (int i = 0; i < 3; ++i) YP_REQUIRE(strides[i] % 16 == 0, YP_ERR_ALIGN, "wgrad: view stride %d (%llu B) not a multiple of 16", i, (unsigned long long)strides[i]);
   CUresult r = wg_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  YP_REQUIRE(r == CUDA_SUCCESS, YP_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad) failed: %d (C=%d W=%d H=%d B=%d box %d,%d)", (int)r, v.C, v.W / sub,
+  YP_REQUIRE(r == CUDA_SUCCESS, YP_ERR_CUDA, "cuTensorMapEncodeTiled(wgrad) failed: %d (C=%d cols=%d H=%d B=%d box %d,%d)", (int)r, v.C, n_cols,
              v.H / sub, v.B, box_w, box_h);
   return YP_OK;
 }
 
-}  // namespace
-
-int wgrad_tc(const YpWgradDesc& d, cudaStream_t st) {
-  YP_REQUIRE(wg_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+// One launch (three for stride 2: one per filter row) over the output columns [c0, c1) of every row.
+int wgrad_segment(const YpWgradDesc& d, int c0, int c1, cudaStream_t st) {
   const YpView& x = d.x;
   const YpView& dy = d.dy;
-  YP_REQUIRE(x.format == YP_FMT_BF16 && dy.format == YP_FMT_BF16, YP_ERR_SHAPE, "wgrad: operands must be bf16");
-  YP_REQUIRE((d.ksize == 1 && d.stride == 1) || (d.ksize == 3 && (d.stride == 1 || d.stride == 2)), YP_ERR_SHAPE, "wgrad: k=%d s=%d unsupported",
-             d.ksize, d.stride);
-  YP_REQUIRE(x.C % 8 == 0 && dy.C % 8 == 0, YP_ERR_SHAPE, "wgrad: Cin=%d / Cout=%d must be multiples of 8", x.C, dy.C);
-  YP_REQUIRE(d.stride == 1 || (x.H % 2 == 0 && x.W % 2 == 0), YP_ERR_SHAPE, "wgrad: stride 2 needs even H,W");
-  YP_REQUIRE(dy.B == x.B && dy.H == x.H / d.stride && dy.W == x.W / d.stride, YP_ERR_SHAPE, "wgrad: dY geometry %dx%dx%d does not match X %dx%dx%d / s%d",
-             dy.B, dy.H, dy.W, x.B, x.H, x.W, d.stride);
-  YP_REQUIRE(aligned16(d.dw), YP_ERR_ALIGN, "wgrad: dW not 16-byte aligned");
-
   WgradArgs a;
   memset(&a, 0, sizeof(a));
-  a.Ho = dy.H; a.Wo = dy.W; a.Cin = x.C; a.Cout = dy.C; a.ksize = d.ksize; a.stride = d.stride;
-  const int taps_total = d.ksize * d.ksize;
-  a.Ktot = taps_total * x.C;
+  const int Wfull = dy.W;                       // output columns of the whole layer
+  a.Ho = dy.H; a.Wo = c1 - c0; a.Cin = x.C; a.Cout = dy.C; a.ksize = d.ksize; a.stride = d.stride;
+  a.Ktot = d.ksize * d.ksize * x.C;
   a.dw = d.dw;
   a.Wp = d.ksize == 3 ? a.Wo + 2 : a.Wo;
-  YP_REQUIRE(a.Wp <= 256, YP_ERR_SHAPE, "wgrad: output width %d too large for one strip (max %d)", a.Wo, d.ksize == 3 ? 254 : 256);
+  // X strips.  Stride 1 (3x3): one strip whose row j holds input column c0 - 1 + j.  Stride 2: strip 0 = even input columns from
+  // output column c0 (tap kw = 1), strip 1 = odd input columns from c0 - 1 (kw = 0 -> shift 0, kw = 2 -> shift 1).  A strip that
+  // would start left of the image starts at the image edge and is loaded at coordinate -1 instead (zero fill = conv padding).
+  int x_col0[2] = {c0, c0}, x_sub = d.stride;
   if (d.ksize == 1) {
     a.n_taps = 1; a.n_box = 1; a.tap_box[0] = 0; a.tap_shift[0] = 0; a.x_w0[0] = 0;
   } else if (d.stride == 1) {
-    a.n_taps = 3; a.n_box = 1; a.x_w0[0] = -1;
+    a.n_taps = 3; a.n_box = 1;
     for (int t = 0; t < 3; ++t) { a.tap_box[t] = 0; a.tap_shift[t] = t; }
+    if (c0 > 0) { x_col0[0] = c0 - 1; a.x_w0[0] = 0; } else { x_col0[0] = 0; a.x_w0[0] = -1; }
   } else {
-    // kw = 0 -> odd column ow - 1, kw = 1 -> even column ow, kw = 2 -> odd column ow; strip 0 = even columns from 0,
-    // strip 1 = odd columns from -1
-    a.n_taps = 3; a.n_box = 2; a.x_w0[0] = 0; a.x_w0[1] = -1;
+    a.n_taps = 3; a.n_box = 2; a.x_w0[0] = 0;
     a.tap_box[0] = 1; a.tap_shift[0] = 0;
     a.tap_box[1] = 0; a.tap_shift[1] = 0;
     a.tap_box[2] = 1; a.tap_shift[2] = 1;
+    if (c0 > 0) { x_col0[1] = c0 - 1; a.x_w0[1] = 0; } else { x_col0[1] = 0; a.x_w0[1] = -1; }
   }
   // tile geometry: the widest N (ci) and tallest strip that leave >= 2 pipeline stages
   const int budget = 200 * 1024;
@@ -261,7 +254,7 @@ int wgrad_tc(const YpWgradDesc& d, cudaStream_t st) {
       if (stages >= (Kp <= 128 ? 3 : 2)) { best_NB = NB; best_Ht = Ht; best_stages = stages; best_Kp = Kp; break; }
     }
   }
-  YP_REQUIRE(best_NB > 0, YP_ERR_SHAPE, "wgrad: no strip geometry fits shared memory (Wo=%d)", a.Wo);
+  YP_REQUIRE(best_NB > 0, YP_ERR_SHAPE, "wgrad: no strip geometry fits shared memory (segment of %d columns)", a.Wo);
   a.NB = best_NB; a.Ht = best_Ht; a.stages = best_stages; a.Kp = best_Kp;
   a.dy_blk_bytes = a.Kp * 128;
   a.x_blk_bytes = (a.Kp + 8) * 128;
@@ -289,28 +282,54 @@ int wgrad_tc(const YpWgradDesc& d, cudaStream_t st) {
   WgradMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
-  if ((rc = encode_nhwc(&maps.dy, dy, 1, 0, 0, a.Wp, a.Ht)) != YP_OK) return rc;
-  if (d.stride == 1) {
-    if ((rc = encode_nhwc(&maps.x[0], x, 1, 0, 0, a.Wp, a.Ht)) != YP_OK) return rc;
-  }
+  if ((rc = encode_nhwc(&maps.dy, dy, 1, 0, 0, c0, a.Wo, a.Wp, a.Ht)) != YP_OK) return rc;
+  const int Wx = x.W / x_sub;                   // columns of the (sub-sampled) input view
   static thread_local bool configured = false;
   if (!configured) {
     YP_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
+  (void)Wfull;
   if (d.stride == 1) {
+    if ((rc = encode_nhwc(&maps.x[0], x, 1, 0, 0, x_col0[0], Wx - x_col0[0], a.Wp, a.Ht)) != YP_OK) return rc;
     wgrad_tc_kernel<<<dim3(P, tiles_y, tiles_z), kWgThreads, smem, st>>>(maps, a);
     YP_LAUNCH_OK();
   } else {
     // one launch per filter row: rows kh = 0 / 2 read the odd input rows, kh = 1 the even ones
     for (int kh = 0; kh < 3; ++kh) {
       const int ph = (kh == 1) ? 0 : 1;
-      if ((rc = encode_nhwc(&maps.x[0], x, 2, ph, 0, a.Wp, a.Ht)) != YP_OK) return rc;
-      if ((rc = encode_nhwc(&maps.x[1], x, 2, ph, 1, a.Wp, a.Ht)) != YP_OK) return rc;
+      if ((rc = encode_nhwc(&maps.x[0], x, 2, ph, 0, x_col0[0], Wx - x_col0[0], a.Wp, a.Ht)) != YP_OK) return rc;
+      if ((rc = encode_nhwc(&maps.x[1], x, 2, ph, 1, x_col0[1], Wx - x_col0[1], a.Wp, a.Ht)) != YP_OK) return rc;
       a.kh0 = kh;
       wgrad_tc_kernel<<<dim3(P, tiles_y, 1), kWgThreads, smem, st>>>(maps, a);
       YP_LAUNCH_OK();
     }
+  }
+  return YP_OK;
+}
+
+}  // namespace
+
+int wgrad_tc(const YpWgradDesc& d, cudaStream_t st) {
+  YP_REQUIRE(wg_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const YpView& x = d.x;
+  const YpView& dy = d.dy;
+  YP_REQUIRE(x.format == YP_FMT_BF16 && dy.format == YP_FMT_BF16, YP_ERR_SHAPE, "wgrad: operands must be bf16");
+  YP_REQUIRE((d.ksize == 1 && d.stride == 1) || (d.ksize == 3 && (d.stride == 1 || d.stride == 2)), YP_ERR_SHAPE, "wgrad: k=%d s=%d unsupported",
+             d.ksize, d.stride);
+  YP_REQUIRE(x.C % 8 == 0 && dy.C % 8 == 0, YP_ERR_SHAPE, "wgrad: Cin=%d / Cout=%d must be multiples of 8", x.C, dy.C);
+  YP_REQUIRE(d.stride == 1 || (x.H % 2 == 0 && x.W % 2 == 0), YP_ERR_SHAPE, "wgrad: stride 2 needs even H,W");
+  YP_REQUIRE(dy.B == x.B && dy.H == x.H / d.stride && dy.W == x.W / d.stride, YP_ERR_SHAPE, "wgrad: dY geometry %dx%dx%d does not match X %dx%dx%d / s%d",
+             dy.B, dy.H, dy.W, x.B, x.H, x.W, d.stride);
+  YP_REQUIRE(aligned16(d.dw), YP_ERR_ALIGN, "wgrad: dW not 16-byte aligned");
+  // A strip spans whole output rows (the zero columns right of the row are what lets one X strip serve three taps); rows wider
+  // than one TMA box (256 columns) are processed as column segments, each with its own launch.
+  const int max_cols = d.ksize == 3 ? 254 : 256;
+  const int n_seg = ceil_div(dy.W, max_cols);
+  const int seg = ceil_div(dy.W, n_seg);
+  for (int c0 = 0; c0 < dy.W; c0 += seg) {
+    const int rc = wgrad_segment(d, c0, std::min(dy.W, c0 + seg), st);
+    if (rc != YP_OK) return rc;
   }
   return YP_OK;
 }

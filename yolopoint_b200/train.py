@@ -144,8 +144,7 @@ def supported(w: torch.Tensor, stride: int, x: Optional[torch.Tensor] = None) ->
     co, ci, k, k2 = w.shape
     ok = k == k2 and ((k == 1 and stride == 1) or (k == 3 and stride in (1, 2)))
     if x is not None:
-        wo = x.shape[3] // stride
-        ok = ok and (wo + (2 if k == 3 else 0)) <= 256 and x.shape[2] % stride == 0 and x.shape[3] % stride == 0
+        ok = ok and x.shape[2] % stride == 0 and x.shape[3] % stride == 0
     return ok
 
 
@@ -190,12 +189,12 @@ class TcConv2d(nn.Conv2d):
         w = self.weight
         if getattr(self, "_tc_cudnn", False):   # cross-check mode (tests): cuDNN on the same bf16 channels-last tensors
             return F.conv2d(_cl(x), w.to(torch.bfloat16), None if self.bias is None else self.bias.to(torch.bfloat16), self.stride, self.padding)
-        if (k, s, p) == (6, 2, 2) and w.shape[1] == 3 and x.shape[3] // 2 + 2 <= 256:
+        if (k, s, p) == (6, 2, 2) and w.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
             xs, ws = _stem_s2d(x, w)
             return conv2d_tc(xs, ws, self.bias, 1)
         if p == k // 2 and supported(w, s, x):
             return conv2d_tc(x, w, self.bias, s)
-        # geometry outside the kernels' range (e.g. a stem wider than 508 pixels): cuDNN on the same bf16 channels-last tensors
+        # geometry outside the kernels' range (not used by any YOLOPoint layer): cuDNN on the same bf16 channels-last tensors
         y = F.conv2d(_cl(x), w.to(torch.bfloat16), None if self.bias is None else self.bias.to(torch.bfloat16), self.stride, self.padding)
         return y
 
