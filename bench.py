@@ -31,9 +31,10 @@ WORKLOADS = {
     "s640": ("s", 640, 640, 1),     # BASELINE.json configs[1]
     "n480": ("n", 480, 640, 1),     # configs[0] geometry (the reference's CPU case) on the GPU
     "m1280": ("m", 736, 1280, 4),   # configs[2]: 32 frames over 8 GPUs = 4 per GPU
+    "l640train": ("l", 640, 640, 8),  # configs[4]: YOLOPoint-L bf16 training step, 64 samples over 8 GPUs = 8 per GPU
 }
 NAMES = [str(i) for i in range(80)]
-CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398}   # SURVEY.md section 8a, per frame
+CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398, "l640train": 135.526}   # SURVEY.md section 8a, per frame (forward)
 
 
 def load_peaks():
@@ -118,6 +119,86 @@ def cpu_reference_fps(version, H, W, steps, warmup, sd=None):
     return len(times) / sum(times), torch.get_num_threads(), float(np.median(times))
 
 
+def train_main(args, version, H, W, per_gpu, world, rank, local_rank):
+    """configs[4]: one training step = 2 forwards + 3 losses + backward + gradient all-reduce + Adam (yolopoint_b200/trainer.py).
+    value = samples/s over all ranks with the synthetic batch resident in HBM; e2e = the same step fed from pinned host memory
+    (H2D of the sample inside the timed region, D2H of the loss)."""
+    from yolopoint_b200 import Model
+    from yolopoint_b200.trainer import TrainStep, synthetic_sample
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    torch.manual_seed(0)
+    model = Model(names=NAMES, version=version).to(dev).train()
+    model.train_backend = args.train_backend
+    ts = TrainStep(model)
+    K, Wm = args.steps, max(args.warmup, 3)
+    host = [synthetic_sample(per_gpu, H, W, seed=7 * rank + i) for i in range(2)]
+    host = [{k: v.pin_memory() for k, v in smp.items()} for smp in host]
+    resident = [{k: v.to(dev) for k, v in smp.items()} for smp in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(Wm):
+        ts.step(resident[i % 2])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        loss = ts.step(resident[i % 2])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    sampler.join()
+    # end to end: host sample -> H2D -> step -> loss to host
+    Ke = min(K, 10)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        smp = {k: v.to(dev, non_blocking=True) for k, v in host[i % 2].items()}
+        lv = float(ts.step(smp))
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        n_conv = sum(1 for m_ in model.modules() if isinstance(m_, torch.nn.Conv2d))
+        # per sample: 2 forwards + their backward (dgrad + wgrad = 2x forward; the stem has no dgrad) = 6 x forward conv FLOPs
+        flops_step = 6.0 * CONV_GFLOP[args.workload] * 1e9 * per_gpu
+        step_s = ms * 1e-3 / K
+        ach = flops_step / step_s / 1e12
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+        line = {"metric": "training samples/sec (2 fwd + losses + bwd + grad all-reduce + Adam)", "value": K * per_gpu * world / (ms * 1e-3),
+                "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16 operands, fp32 accumulation, fp32 master weights / BN / Adam", "data": "synthetic",
+                "config": {"workload": f"YOLOPoint-{version.upper()} {W}x{H} training step, batch {per_gpu}/GPU (global {per_gpu * world})",
+                           "conv_backend": args.train_backend, "parallelism": f"data parallel over {world} GPU(s), bucketed flat-buffer gradient all-reduce",
+                           "l2": "activations of one step (GBs) exceed L2"},
+                "clocks": sampler.summary(), "gpu_launches": K * n_conv * 2 * 3,
+                "e2e": {"value": Ke * per_gpu * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": Ke},
+                "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + wgrad_tc_kernel (tcgen05 conv forward / data gradient / weight gradient)",
+                             "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"], "traffic": None,
+                             "peak_source": f"{peaks['src']} bf16 sustained", "algorithmic_gflop_per_step": flops_step / 1e9,
+                             "note": "whole-step time (convs + PyTorch glue: BN, SiLU, losses, Adam); 6 x forward conv FLOPs per sample"},
+                "detail": {"loss": lv}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -130,11 +211,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=1, help="independent camera streams (frame pipelines) in flight per GPU")
     ap.add_argument("--also-streams", type=int, default=3, help="extra (untimed-for-value) run with this many camera streams, reported under detail")
+    ap.add_argument("--train-backend", default="b200", choices=["b200", "cudnn_bf16", "torch"], help="l640train only: conv kernels used by the step")
+    ap.add_argument("--train-batch", type=int, default=0, help="l640train only: samples per GPU (default 8)")
     args = ap.parse_args()
     version, H, W, per_gpu = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "l640train" and args.impl != "reference":
+        return train_main(args, version, H, W, args.train_batch or per_gpu, world, rank, local_rank)
     K, Wm = args.steps, max(args.warmup, 3)
     config = {"workload": f"YOLOPoint-{version.upper()} {W}x{H} batch={per_gpu}/GPU full per-frame pipeline (net+decode+boxNMS+heatmap+kpNMS+desc+match)",
               "frames_per_gpu_per_step": per_gpu, "precision": args.precision, "parallelism": f"frames sharded over {world} GPU(s), no collective"}

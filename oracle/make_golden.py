@@ -157,5 +157,47 @@ def main():
          m03=ns.PointTracker.nn_match_two_way(d1, d2, 0.3))
 
 
+def golden_losses():
+    """Training losses (SURVEY.md section 8 row a11 consumers): the reference's own ComputeObjectLoss / ComputeDetectorLoss /
+    descriptor_loss_sparse (src/utils/loss_functions.py:90-234, 600-619, 361-481) on seeded synthetic network outputs."""
+    ns = ref_import.load()
+    from utils.loss_functions import ComputeDetectorLoss, ComputeObjectLoss, descriptor_loss_sparse
+    from utils.utils import getMasks, labels2Dto3D
+    torch.manual_seed(0)
+    m = ns.Model(names=NAMES80, version="n")
+    cfg = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, iou_t=0.2, anchor_t=4.0, label_smoothing=0.0, fl_gamma=0.0)
+    B, H, W = 2, 128, 160
+    rs = np.random.RandomState(0)
+    p = [torch.from_numpy(rs.randn(B, 3, H // s, W // s, 85).astype(np.float32)) for s in (8, 16, 32)]
+    t = np.concatenate([np.stack([np.full(6, b), rs.randint(0, 80, 6), rs.uniform(.1, .9, 6), rs.uniform(.1, .9, 6), rs.uniform(.05, .5, 6),
+                                  rs.uniform(.05, .5, 6)], 1) for b in range(B)]).astype(np.float32)
+    for pi in p:
+        pi.requires_grad_(True)
+    lobj, items = ComputeObjectLoss(m, cfg, "cpu")(p, torch.from_numpy(t))
+    lobj.backward()
+    semi = torch.from_numpy(rs.randn(B, 65, H // 8, W // 8).astype(np.float32)).requires_grad_(True)
+    lab = (rs.rand(B, 1, H, W) < 0.005).astype(np.float32)
+    mask = np.ones((B, 1, H, W), np.float32)
+    mask[:, :, :16] = 0
+    ldet = ComputeDetectorLoss("cpu")(semi, labels2Dto3D(torch.from_numpy(lab)), getMasks(torch.from_numpy(mask), "cpu"))
+    ldet.backward()
+    d1 = torch.nn.functional.normalize(torch.from_numpy(rs.randn(B, 64, H // 8, W // 8).astype(np.float32)), dim=1)
+    d2 = torch.nn.functional.normalize(d1 + 0.3 * torch.from_numpy(rs.randn(*d1.shape).astype(np.float32)), dim=1)
+    Hm = torch.eye(3).repeat(B, 1, 1)
+    Hm[1, 0, 2] = 0.1
+    np.random.seed(0)
+    ldesc = np.array([descriptor_loss_sparse(d1, d2, torch.from_numpy(mask), Hm, num_samples_per_image=200, num_masked_non_matches_per_match=50).item()
+                      for _ in range(8)], np.float32)
+    save("losses.npz", p0=p[0].detach().numpy(), p1=p[1].detach().numpy(), p2=p[2].detach().numpy(), targets=t, lobj=lobj.detach().numpy(),
+         lobj_items=items.numpy(), g0=p[0].grad.numpy(), semi=semi.detach().numpy(), labels=lab, mask=mask, ldet=ldet.detach().numpy(),
+         gsemi=semi.grad.numpy(), d1=d1.numpy(), d2=d2.numpy(), Hm=Hm.numpy(), ldesc=ldesc,
+         labels3d=labels2Dto3D(torch.from_numpy(lab)).numpy(), mask3d=getMasks(torch.from_numpy(mask), "cpu").numpy())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":
+        os.makedirs(OUT, exist_ok=True)
+        golden_losses()
+    else:
+        main()
+        golden_losses()

@@ -70,3 +70,67 @@ def test_sharded_match_reduction_gloo():
     for _, m in outs:
         np.testing.assert_array_equal(m[:2], ref[:2])
         np.testing.assert_allclose(m[2], ref[2], rtol=0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training step: flat-buffer gradient all-reduce (training row)
+# ---------------------------------------------------------------------------------------------------------------------
+def _train_worker(rank, world, port, q):
+    import torch
+    from yolopoint_b200 import Model
+    from yolopoint_b200.trainer import TrainStep, synthetic_sample
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    torch.manual_seed(0)
+    m = Model(names=[str(i) for i in range(80)], version="n")            # identical weights on every rank
+    sample = synthetic_sample(2, 64, 96, seed=10 + rank)                  # a different batch slice per rank
+    ts = TrainStep(m, sparse_cfg=dict(num_samples_per_image=40, num_masked_non_matches_per_match=10), bucket_bytes=1 << 20)
+    assert len(ts.reducer.buckets) > 3
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    # expectation: mean over ranks of the purely local gradients, computed with plain autograd on a fresh model copy
+    torch.manual_seed(0)
+    m2 = Model(names=[str(i) for i in range(80)], version="n")
+    m2.load_state_dict(state)
+    m2.train()
+    from yolopoint_b200 import losses as Lz
+    from yolopoint_b200.trainer import LAMBDA_DESC, LAMBDA_OBJ, LOSS_CFG
+    ref_step = TrainStep.__new__(TrainStep)
+    ref_step.model, ref_step.device = m2, torch.device("cpu")
+    ref_step.obj_loss, ref_step.det_loss = Lz.ComputeObjectLoss(m2, LOSS_CFG, "cpu"), Lz.ComputeDetectorLoss("cpu")
+    ref_step.sparse_cfg = ts.sparse_cfg
+    torch.manual_seed(100 + rank)
+    l2, _ = ref_step.losses(sample)
+    l2.backward()
+    g_local = torch.cat([p.grad.flatten() for p in m2.parameters()])
+    both = [torch.empty_like(g_local) for _ in range(world)]
+    dist.all_gather(both, g_local)
+    expect = sum(both) / world
+    # the real step
+    m.load_state_dict(state)
+    torch.manual_seed(100 + rank)
+    before = [p.detach().clone() for p in m.parameters()]
+    loss = ts.step(sample)
+    got = ts.reducer.flat.clone()
+    changed = sum(int(not torch.equal(a, p.detach())) for a, p in zip(before, m.parameters()))
+    q.put((rank, float((got - expect).abs().max()), float(expect.abs().max()), float(loss), changed, len(before), len(ts.reducer.handles)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_training_step_gradient_allreduce_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for rank, err, scale, loss, changed, n_params, n_handles in outs:
+        assert np.isfinite(loss) and n_handles > 3                    # one asynchronous all-reduce per bucket
+        assert err <= 1e-5 * max(scale, 1.0), (rank, err, scale)     # averaged gradients == mean of the per-rank gradients
+        assert changed > 0.9 * n_params                                # Adam moved (nearly) every parameter

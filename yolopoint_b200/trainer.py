@@ -1,0 +1,142 @@
+"""One training step of the reference (src/train.py:196-250) on the B200 path, data parallel over the GPUs of one box.
+
+  step = forward(image) + forward(warped image)                    (tcgen05 convs, train.py)
+       + object loss + 2 x detector loss + sparse descriptor loss   (losses.py; train.py:212-241 of the reference)
+       + backward                                                   (tcgen05 dgrad / wgrad)
+       + gradient all-reduce (mean over ranks)                      (NCCL over NVLink; gloo in the CPU tests)
+       + Adam step (lr 1e-3 over all parameters, src/train.py:88) and the linear LambdaLR schedule (:91-93)
+
+Data parallelism follows the reference's DDP setup (src/train.py:46: ``broadcast_buffers=False``, no SyncBN): every rank owns
+its slice of the batch and its own BN statistics; gradients are averaged.  The gradients live in ONE flat fp32 buffer (each
+``p.grad`` is a view of it), cut into buckets in reverse parameter order; a bucket is all-reduced asynchronously as soon as
+autograd has produced its last gradient, so the collective overlaps the rest of the backward pass.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import losses as Lz
+
+LOSS_CFG = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, iou_t=0.2, anchor_t=4.0, label_smoothing=0.0, fl_gamma=0.0)  # configs/coco.yaml:128-140
+SPARSE_CFG = dict(num_samples_per_image=3000, num_masked_non_matches_per_match=200)                                            # configs/coco.yaml:122-124
+LAMBDA_DESC, LAMBDA_OBJ = 0.1, 10.0                                                                                             # configs/coco.yaml:113-115
+
+
+class FlatGradReducer:
+    """Flat gradient buffer + bucketed asynchronous all-reduce (mean)."""
+
+    def __init__(self, params: List[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # reverse parameter order ~ the order in which backward produces gradients: bucket 0 = the last parameters
+        off = total
+        self.bucket_of: Dict[int, int] = {}
+        self.buckets: List[List[int]] = [[total, total, 0]]      # [lo, hi, n_params]
+        for i in reversed(range(len(self.params))):
+            p = self.params[i]
+            off -= p.numel()
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            b = self.buckets[-1]
+            if (b[1] - b[0]) * 4 >= bucket_bytes:
+                self.buckets.append([off + p.numel(), off + p.numel(), 0])
+                b = self.buckets[-1]
+            b[0] = off
+            b[2] += 1
+            self.bucket_of[i] = len(self.buckets) - 1
+        self.pending = [0] * len(self.buckets)
+        self.handles = []
+        if self.world > 1:
+            for i, p in enumerate(self.params):
+                p.register_post_accumulate_grad_hook(lambda _p, i=i: self._ready(i))
+
+    def zero(self):
+        self.flat.zero_()
+        for i, p in enumerate(self.params):      # autograd accumulates in place into the existing views
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * self._offset(i):
+                raise RuntimeError("a parameter's .grad no longer aliases the flat gradient buffer (do not call zero_grad(set_to_none=True))")
+        self.pending = [b[2] for b in self.buckets]
+        self.handles = []
+
+    def _offset(self, i):
+        if not hasattr(self, "_offs"):
+            offs, o = [], 0
+            for p in self.params:
+                offs.append(o)
+                o += p.numel()
+            self._offs = offs
+        return self._offs[i]
+
+    def _ready(self, i):
+        b = self.bucket_of[i]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            lo, hi, _ = self.buckets[b]
+            self.handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Wait for the bucket all-reduces (buckets whose parameters received no gradient are reduced here) and average."""
+        if self.world == 1:
+            return
+        for b, n in enumerate(self.pending):
+            if n > 0:
+                lo, hi, _ = self.buckets[b]
+                self.handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for h in self.handles:
+            h.wait()
+        self.flat.mul_(1.0 / self.world)
+
+
+def synthetic_sample(B: int, H: int, W: int, seed: int, device="cpu", boxes_per_image: int = 8, nc: int = 80) -> Dict[str, torch.Tensor]:
+    """The synthetic training sample of SURVEY.md section 8d (config 5): images U(0,1), keypoint labels Bernoulli(0.005), valid masks
+    of ones, 8 boxes per image, identity homographies."""
+    rs = np.random.RandomState(seed)
+    f = lambda a: torch.from_numpy(a.astype(np.float32)).to(device)
+    boxes = np.concatenate([np.stack([np.full(boxes_per_image, b), rs.randint(0, nc, boxes_per_image), rs.uniform(0.1, 0.9, boxes_per_image),
+                                      rs.uniform(0.1, 0.9, boxes_per_image), rs.uniform(0.05, 0.4, boxes_per_image), rs.uniform(0.05, 0.4, boxes_per_image)], 1)
+                            for b in range(B)])
+    return dict(image=f(rs.rand(B, 3, H, W)), warped_image=f(rs.rand(B, 3, H, W)), labels_2D=f(rs.rand(B, 1, H, W) < 0.005),
+                warped_labels=f(rs.rand(B, 1, H, W) < 0.005), valid_mask=torch.ones(B, 1, H, W, device=device),
+                warped_valid_mask=torch.ones(B, 1, H, W, device=device), box_labels=f(boxes), inv_homographies=torch.eye(3, device=device).repeat(B, 1, 1))
+
+
+class TrainStep:
+    def __init__(self, model, epochs: int = 100, lr: float = 1e-3, lrf: float = 0.01, sparse_cfg: Optional[dict] = None, group=None,
+                 bucket_bytes: int = 32 << 20):
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.obj_loss = Lz.ComputeObjectLoss(model, LOSS_CFG, self.device)
+        self.det_loss = Lz.ComputeDetectorLoss(self.device)
+        self.sparse_cfg = dict(SPARSE_CFG if sparse_cfg is None else sparse_cfg)
+        self.reducer = FlatGradReducer(list(model.parameters()), bucket_bytes, group)
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr)
+        self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lr_lambda=lambda e: (1 - e / epochs) * (1.0 - lrf) + lrf)
+
+    def losses(self, sample):
+        m, dev = self.model, self.device
+        out = m(sample["image"])
+        semi, desc, obj = out["semi"], out["desc"], out["objects"]
+        loss_obj, items = self.obj_loss(obj, sample["box_labels"])
+        loss_det = self.det_loss(semi, Lz.labels2Dto3D(sample["labels_2D"]), Lz.getMasks(sample["valid_mask"], dev))
+        out_w = m(sample["warped_image"])
+        loss_det_w = self.det_loss(out_w["semi"], Lz.labels2Dto3D(sample["warped_labels"]), Lz.getMasks(sample["warped_valid_mask"], dev))
+        loss_desc = Lz.descriptor_loss_sparse(desc, out_w["desc"], sample["warped_valid_mask"], sample["inv_homographies"], **self.sparse_cfg)
+        loss = loss_det + loss_det_w + LAMBDA_DESC * loss_desc + LAMBDA_OBJ * loss_obj
+        return loss, dict(det=loss_det.detach(), det_warp=loss_det_w.detach(), desc=loss_desc.detach(), obj=loss_obj.detach())
+
+    def step(self, sample) -> torch.Tensor:
+        """sample: dict as produced by the reference's data loader (src/train.py:196-205) with tensors on the model's device."""
+        self.model.train()
+        self.reducer.zero()
+        loss, _ = self.losses(sample)
+        loss.backward()
+        self.reducer.finish()
+        self.opt.step()
+        return loss.detach()
