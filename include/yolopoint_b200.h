@@ -136,9 +136,10 @@ typedef struct {
 } YpWgradDesc;
 int yp_conv2d_nhwc_wgrad(const YpWgradDesc* desc, void* stream);
 
-/* Debug aid: when set to a device buffer of 512 int64, CTA (0,0) of every following tcgen05 conv launch records clock64
- * stamps of its pipeline events there (see tools/conv_timeline.py); NULL switches it off.  Not thread safe. */
-int yp_debug_conv_timeline(void* device_buf_512_i64);
+/* Debug aid: when set to a device buffer of 512 + 3 * 20000 int64, CTA (0,0) of every following tcgen05 conv launch records
+ * clock64 stamps of its pipeline events in the first 512 slots and every CTA records (SM id, start ns, end ns) behind them
+ * (see tools/conv_timeline.py); NULL switches it off.  Not thread safe. */
+int yp_debug_conv_timeline(void* device_buf_i64);
 
 /* SPPF pooling: from slice 0 (C channels) of the [B,H,W,4C] concat buffer compute the 5x5, 9x9 and 13x13
  * stride-1 max pools (== three chained MaxPool2d(5,1,2), models/common.py:220-229) into slices 1..3. */

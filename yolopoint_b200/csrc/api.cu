@@ -57,8 +57,8 @@ extern "C" int yp_conv2d_nhwc_fwd(const YpConvDesc* d, void* stream) {
   return YP_ERR_ARG;
 }
 
-extern "C" int yp_debug_conv_timeline(void* device_buf_512_i64) {
-  yp::set_conv_timeline(static_cast<long long*>(device_buf_512_i64));
+extern "C" int yp_debug_conv_timeline(void* device_buf_i64) {
+  yp::set_conv_timeline(static_cast<long long*>(device_buf_i64));
   return YP_OK;
 }
 

@@ -61,6 +61,7 @@ struct ConvArgs {
   const void* res_base;
   long long res_pix, res_plane;
   int n_out_maps, out_planes, out_row_bytes, staging_set_bytes;
+  int ablate;      // debug (YP_CONV_ABLATE): 1 = issue no MMAs, 2 = issue no TMA loads (timing experiments; results are garbage)
   long long* dbg;  // optional timeline buffer (yp_debug_conv_timeline); CTA (0,0) records clock64 stamps
 };
 
@@ -95,12 +96,12 @@ __device__ __forceinline__ float silu_fast(float v) {
 // result so that their truncation error is negligible.
 // ---------------------------------------------------------------------------------------------
 template <int OUT_FMT, int UNITS, bool kTf32>
-__global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 4) ? 1 : 2) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index as a warp-uniform value
   const int per_img = a.tiles_w * a.tiles_h;
   const int b = blockIdx.x / per_img;
   const int trem = blockIdx.x - b * per_img;
@@ -111,8 +112,16 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
   const int kb0 = blockIdx.z * a.kb_per_split;                       // this CTA's slice of the K loop (split-K)
   const int num_kb = min(num_kb_all, kb0 + a.kb_per_split) - kb0;
   long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
-  auto stamp = [&](int slot) { if (dbg) dbg[slot] = clock64(); };
+  auto stamp = [&](int slot) { if (dbg) dbg[slot] = clock64(); };   // callers restrict it to one lane
   if (threadIdx.x == 0) stamp(0);
+  // whole-grid occupancy picture: every CTA records (SM id, start, end) in nanoseconds at dbg[512 + 3 * linear CTA index]
+  const long long cta_lin = (static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (a.dbg && threadIdx.x == 0 && cta_lin < 20000) {
+    unsigned smid; unsigned long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[512 + 3 * cta_lin] = smid; a.dbg[513 + 3 * cta_lin] = static_cast<long long>(t);
+  }
   // Programmatic dependent launch: let the next kernel of the stream start its prologue (barrier init, TMEM allocation,
   // descriptor prefetch) now; it blocks in griddepcontrol.wait until this grid has completed and flushed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -150,34 +159,39 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
   if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
-      if (a.patch) {
-        // K order = (channel block, tap): one patch load per channel block, nine weight tiles streamed through the B ring
-        int sa = 0, pha = 0, sb = 0, phb = 0;
-        for (int cbi = 0; cbi < num_kb; ++cbi) {
-          const int cb = kb0 + cbi;
-          mbar_wait(aempty_bar(sa), pha ^ 1);
-          mbar_expect_tx(afull_bar(sa), a.a_tx);
-          const uint32_t sta = smem_base + sa * a.a_stage_bytes;
-          tma_load_5d(sta, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 0);
-          if (a.in_planes == 2 && !a.a_split) tma_load_5d(sta + a.a_plane_off, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 1);
-          if (cbi < 96) stamp(8 + cbi);
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(empty_bar(sb), phb ^ 1);
-            mbar_expect_tx(full_bar(sb), a.b_tx);
-            tma_load_3d(smem_base + a.b_ring_off + sb * a.b_stage_bytes, &maps.w, full_bar(sb), (tap * a.kb_per_tap + cb) * a.ck_elems, n0, 0);
-            if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
+    const bool load = a.ablate != 2;
+    if (a.patch) {
+      // K order = (channel block, tap): one patch load per channel block, nine weight tiles streamed through the B ring
+      int sa = 0, pha = 0, sb = 0, phb = 0;
+      for (int cbi = 0; cbi < num_kb; ++cbi) {
+        const int cb = kb0 + cbi;
+        mbar_wait(aempty_bar(sa), pha ^ 1);
+        const uint32_t sta = smem_base + sa * a.a_stage_bytes;
+        if (elect_one()) {
+          mbar_expect_tx(afull_bar(sa), load ? a.a_tx : 0);
+          if (load) {
+            tma_load_5d(sta, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 0);
+            if (a.in_planes == 2 && !a.a_split) tma_load_5d(sta + a.a_plane_off, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 1);
           }
-          if (++sa == 2) { sa = 0; pha ^= 1; }
+          if (cbi < 96) stamp(8 + cbi);
         }
-      } else {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(empty_bar(sb), phb ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(sb), load ? a.b_tx : 0);
+            if (load) tma_load_3d(smem_base + a.b_ring_off + sb * a.b_stage_bytes, &maps.w, full_bar(sb), (tap * a.kb_per_tap + cb) * a.ck_elems, n0, 0);
+          }
+          if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+        }
+        if (++sa == 2) { sa = 0; pha ^= 1; }
+      }
+    } else {
       int s = 0, ph = 0, tap = kb0 / a.kb_per_tap, cb = kb0 - tap * a.kb_per_tap;
       const uint32_t b_off = a.a_region_bytes;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), a.tx_bytes);
         int map = 0, dh = 0, dw = 0;
         if (a.ksize == 3) {
           const int kh = tap / 3, kw = tap - kh * 3;
@@ -188,13 +202,17 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
           dw = static_cast<int>((a.tap_dw >> (4 * tap)) & 15ull) - 8;
         }
         const uint32_t st = smem_base + s * a.stage_bytes;
-        tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
-        if (a.in_planes == 2 && !a.a_split) tma_load_5d(st + a.a_plane_off, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 1);
-        tma_load_3d(st + b_off, &maps.w, full_bar(s), (kb0 + kb) * a.ck_elems, n0, 0);   // box covers both weight planes
-        if (kb < 96) stamp(8 + kb);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), load ? a.tx_bytes : 0);
+          if (load) {
+            tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
+            if (a.in_planes == 2 && !a.a_split) tma_load_5d(st + a.a_plane_off, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 1);
+            tma_load_3d(st + b_off, &maps.w, full_bar(s), (kb0 + kb) * a.ck_elems, n0, 0);   // box covers both weight planes
+          }
+          if (kb < 96) stamp(8 + kb);
+        }
         if (++cb == a.kb_per_tap) { cb = 0; ++tap; }
         if (++s == a.stages) { s = 0; ph ^= 1; }
-      }
       }
     }
   }
@@ -206,12 +224,22 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
   // (ii) the two MMA streams are issued by two threads (warp 1 and lane 0 of the first epilogue warp, idle until the
   // accumulators are complete); bf16 deals the k-steps to the two issuers round-robin.  Each issuer rotates through its
   // own accumulators (dependent MMAs on one accumulator serialise, and fp32 accumulation in the tensor core truncates).
-  if (warp >= 1 && warp - 1 < a.n_iss && lane == 0) {
+  // The issuing code is written warp-uniform (the whole warp walks the loop, one elected lane executes each tcgen05
+  // instruction) with 32-bit descriptor arithmetic: tcgen05.mma / tcgen05.commit take uniform-register operands, and code
+  // under a `lane == 0` branch makes the compiler move every operand through an elect / R2UR loop and 64-bit adds -- measured
+  // ~450 cycles of issue overhead per MMA, several times the 64-128 cycles the MMA occupies the tensor pipe.
+  if (warp >= 1 && warp - 1 < a.n_iss) {
     const int q = warp - 1;
     const int ksteps = a.ck_bytes / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
     const uint32_t b_plane = a.Nt * a.ck_bytes;
     const int cnt = a.iss_cnt[q];
     const uint32_t col0 = tmem_base + a.iss_col[q], cstride = a.iss_stride[q], idesc = a.iss_idesc[q];
+    const int kstart = a.kstep_mod ? q : 0, kinc = a.kstep_mod ? a.kstep_mod : 1;
+    const uint32_t a_off0 = a.job_a[q][0] * a.a_plane_off, b_off0 = a.job_b[q][0] * b_plane;
+    const uint32_t a_off1 = a.job_a[q][1] * a.a_plane_off, b_off1 = a.job_b[q][1] * b_plane;
+    const bool two = a.n_jobs[q] == 2;
+    const uint32_t dhi = smem_desc_hi(a.ck_bytes);
+    const bool live = a.ablate != 1;
     uint32_t used = 0;                   // bit r set = accumulator r of this issuer already holds a partial sum
     int s = 0, ph = 0, nxt = 0;
     if (a.patch) {
@@ -219,59 +247,52 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
       for (int cbi = 0; cbi < num_kb; ++cbi) {
         mbar_wait(afull_bar(sa), pha);
         tc_fence_after();
-        if (q == 0 && cbi < 96) stamp(104 + cbi);
+        if (q == 0 && cbi < 96 && lane == 0) stamp(104 + cbi);
         const uint32_t pa = smem_base + sa * a.a_stage_bytes;
+        uint32_t shift = 0;               // byte offset of the tap's window inside the patch: (kh * Wp + kw) rows
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const int kh = tap / 3, kw = tap - kh * 3;
-          const uint32_t shift = static_cast<uint32_t>(kh * a.Wp + kw) * a.ck_bytes;   // window of the patch for this tap
           const uint32_t sb = smem_base + a.b_ring_off + s * a.b_stage_bytes;
-          const uint64_t ad0 = make_smem_desc_shifted(pa + a.job_a[q][0] * a.a_plane_off + shift, a.ck_bytes, a.base_offset_mode);
-          const uint64_t bd0 = make_smem_desc(sb + a.job_b[q][0] * b_plane, a.ck_bytes);
-          const uint64_t ad1 = make_smem_desc_shifted(pa + a.job_a[q][1] * a.a_plane_off + shift, a.ck_bytes, a.base_offset_mode);
-          const uint64_t bd1 = make_smem_desc(sb + a.job_b[q][1] * b_plane, a.ck_bytes);
-          const bool two = a.n_jobs[q] == 2;
-          for (int k = 0; k < ksteps; ++k) {
-            if (a.kstep_mod && (k % a.kstep_mod) != q) continue;
-            const uint64_t ko = static_cast<uint64_t>(2 * k);
-            umma<kTf32>(col0 + nxt * cstride, ad0 + ko, bd0 + ko, idesc, (used >> nxt) & 1u);
-            if (two) umma<kTf32>(col0 + nxt * cstride, ad1 + ko, bd1 + ko, idesc, 1u);
+          uint32_t al0 = smem_desc_lo(pa + a_off0 + shift) + 2 * kstart, bl0 = smem_desc_lo(sb + b_off0) + 2 * kstart;
+          uint32_t al1 = smem_desc_lo(pa + a_off1 + shift) + 2 * kstart, bl1 = smem_desc_lo(sb + b_off1) + 2 * kstart;
+          for (int k = kstart; k < ksteps && live; k += kinc) {
+            umma32<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
+            if (two) umma32<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
             used |= 1u << nxt;
-            if (++nxt == cnt) nxt = 0;
+            nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+            al0 += 2 * kinc; bl0 += 2 * kinc; al1 += 2 * kinc; bl1 += 2 * kinc;
           }
-          umma_commit(empty_bar(s));
+          umma_commit_elect(empty_bar(s));
           if (++s == a.b_stages) { s = 0; ph ^= 1; }
+          shift += (tap % 3 == 2) ? (a.Wp - 2) * a.ck_bytes : a.ck_bytes;
         }
-        umma_commit(aempty_bar(sa));
-        if (q == 0 && cbi < 96) stamp(200 + cbi);
+        umma_commit_elect(aempty_bar(sa));
+        if (q == 0 && cbi < 96 && lane == 0) stamp(200 + cbi);
         if (++sa == 2) { sa = 0; pha ^= 1; }
       }
-    } else
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      if (q == 0 && kb < 96) stamp(104 + kb);
-      const uint32_t sa = smem_base + s * a.stage_bytes;
-      const uint32_t sb = sa + a.a_region_bytes;
-      const uint64_t ad0 = make_smem_desc(sa + a.job_a[q][0] * a.a_plane_off, a.ck_bytes);
-      const uint64_t bd0 = make_smem_desc(sb + a.job_b[q][0] * b_plane, a.ck_bytes);
-      const uint64_t ad1 = make_smem_desc(sa + a.job_a[q][1] * a.a_plane_off, a.ck_bytes);
-      const uint64_t bd1 = make_smem_desc(sb + a.job_b[q][1] * b_plane, a.ck_bytes);
-      const bool two = a.n_jobs[q] == 2;
-      for (int k = 0; k < ksteps; ++k) {
-        if (a.kstep_mod && (k % a.kstep_mod) != q) continue;
-        const uint64_t ko = static_cast<uint64_t>(2 * k);
-        umma<kTf32>(col0 + nxt * cstride, ad0 + ko, bd0 + ko, idesc, (used >> nxt) & 1u);
-        if (two) umma<kTf32>(col0 + nxt * cstride, ad1 + ko, bd1 + ko, idesc, 1u);
-        used |= 1u << nxt;
-        if (++nxt == cnt) nxt = 0;
+    } else {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (q == 0 && kb < 96 && lane == 0) stamp(104 + kb);
+        const uint32_t sa = smem_base + s * a.stage_bytes;
+        const uint32_t sb = sa + a.a_region_bytes;
+        uint32_t al0 = smem_desc_lo(sa + a_off0) + 2 * kstart, bl0 = smem_desc_lo(sb + b_off0) + 2 * kstart;
+        uint32_t al1 = smem_desc_lo(sa + a_off1) + 2 * kstart, bl1 = smem_desc_lo(sb + b_off1) + 2 * kstart;
+        for (int k = kstart; k < ksteps && live; k += kinc) {
+          umma32<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
+          if (two) umma32<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
+          used |= 1u << nxt;
+          nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+          al0 += 2 * kinc; bl0 += 2 * kinc; al1 += 2 * kinc; bl1 += 2 * kinc;
+        }
+        umma_commit_elect(empty_bar(s));  // one arrival per issuer: the stage is free when all their MMAs have retired
+        if (q == 0 && kb < 96 && lane == 0) stamp(200 + kb);
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(empty_bar(s));  // one arrival per issuer: the stage is free when all their MMAs have retired
-      if (q == 0 && kb < 96) stamp(200 + kb);
-      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
-    umma_commit(accum_bar);
+    umma_commit_elect(accum_bar);
   }
   __syncwarp();
   if (warp >= 2) {
@@ -279,7 +300,6 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
     using TO = typename OutT<OUT_FMT>::type;
     constexpr int CH = 16 * UNITS;                 // elements per staging row
     constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
-    constexpr int V16 = ROWB / 16;                 // 16-byte vectors per row
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;               // accumulator row (TMEM lane) of this thread
     const int rdiv = a.patch ? a.Wp : a.Wt;      // patch mode: rows index the padded patch, halo columns are dropped
@@ -294,27 +314,32 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
     const bool has_res = a.res_base != nullptr && valid;
     const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
 
-    // residual of chunk `c` for this thread's pixel, planes summed (residual format == output format family)
-    auto load_res = [&](int c, float* r) {
+    // A chunk (one staging row, CH columns) is computed in passes of at most 32 columns so that the live accumulator /
+    // residual registers stay small enough for two CTAs per SM (one CTA's epilogue then overlaps the other's main loop).
+    constexpr int PU = UNITS > 2 ? 2 : UNITS;      // 16-column units per pass
+    constexpr int PE = 16 * PU;                    // columns per pass
+    constexpr int NP = UNITS / PU;                 // passes per chunk
+    // residual of columns [col0, col0 + PE) for this thread's pixel, planes summed (residual format == output format family)
+    auto load_res = [&](int col0, float* r) {
       if (!has_res) {
 #pragma unroll
-        for (int i = 0; i < CH; ++i) r[i] = 0.0f;
+        for (int i = 0; i < PE; ++i) r[i] = 0.0f;
         return;
       }
       if (OUT_FMT == YP_FMT_BF16) {
-        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_base) + res_off + c * CH);
+        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_base) + res_off + col0);
 #pragma unroll
-        for (int j = 0; j < CH / 8; ++j) {
+        for (int j = 0; j < PE / 8; ++j) {
           const uint4 u = __ldg(p + j);
           const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
           for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); r[j * 8 + 2 * e] = f.x; r[j * 8 + 2 * e + 1] = f.y; }
         }
       } else {
-        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + c * CH);
-        const float4* pl = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + a.res_plane + c * CH);
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + col0);
+        const float4* pl = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + a.res_plane + col0);
 #pragma unroll
-        for (int j = 0; j < CH / 4; ++j) {
+        for (int j = 0; j < PE / 4; ++j) {
           const float4 hi = __ldg(p + j);
           float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
           if (OUT_FMT == YP_FMT_F32X2) lo = __ldg(pl + j);
@@ -374,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
       return v + res;
     };
 
-    float res[CH];
+    float res[PE];
     asm volatile("griddepcontrol.wait;" ::: "memory");     // the residual may be the previous kernel's output
     load_res(0, res);               // in flight while the main loop runs
     mbar_wait(accum_bar, 0);
@@ -416,44 +441,51 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
       inv_norm = 1.0f / sqrtf(ss);
     }
 
+    const int n_pass = n_chunks * NP;
     for (int c = 0; c < n_chunks; ++c) {
-      float v[CH];
-#pragma unroll
-      for (int u = 0; u < UNITS; ++u) load_acc16(c * CH + u * 16, v + u * 16);
-#pragma unroll
-      for (int i = 0; i < CH; ++i) v[i] = finish(v[i], c * CH + i, res[i]) * inv_norm;
-      if (c + 1 < n_chunks) load_res(c + 1, res);   // overlaps the staging / store of this chunk
-      if (et0 && c < 8) stamp(300 + 4 * c);
-      // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t stg = smem_base + (c & 1) * a.staging_set_bytes;
+#pragma unroll
+      for (int ps = 0; ps < NP; ++ps) {
+      float v[PE];
+      const int col0 = c * CH + ps * PE;
+#pragma unroll
+      for (int u = 0; u < PU; ++u) load_acc16(col0 + u * 16, v + u * 16);
+#pragma unroll
+      for (int i = 0; i < PE; ++i) v[i] = finish(v[i], col0 + i, res[i]) * inv_norm;
+      if (c * NP + ps + 1 < n_pass) load_res(col0 + PE, res);   // overlaps the staging / store of this pass
+      if (et0 && c < 8 && ps == NP - 1) stamp(300 + 4 * c);
+      // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
+      if (ps == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      constexpr int VP = PE * (int)sizeof(TO) / 16;     // 16-byte vectors this pass contributes to the staging row
+      const int j0 = ps * VP;
       if (!in_tile) {
         // halo / padding row: nothing to stage
       } else if (OUT_FMT == YP_FMT_F32X2) {
 #pragma unroll
-        for (int j = 0; j < V16; ++j) {
+        for (int j = 0; j < VP; ++j) {
           float hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { hi[e] = tf32_round(v[j * 4 + e]); lo[e] = tf32_round(v[j * 4 + e] - hi[e]); }
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j, ROWB)), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg + 128 * ROWB, srow, j, ROWB)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j0 + j, ROWB)), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg + 128 * ROWB, srow, j0 + j, ROWB)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
         }
       } else if (OUT_FMT == YP_FMT_F32) {
 #pragma unroll
-        for (int j = 0; j < V16; ++j)
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j, ROWB)), "f"(v[j * 4]), "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
+        for (int j = 0; j < VP; ++j)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j0 + j, ROWB)), "f"(v[j * 4]), "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
       } else {
 #pragma unroll
-        for (int j = 0; j < V16; ++j) {
+        for (int j = 0; j < VP; ++j) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
             pk[e] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j, ROWB)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j0 + j, ROWB)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
       }
+      }  // passes
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et0 && c < 8) stamp(301 + 4 * c);
@@ -475,6 +507,11 @@ __global__ void __launch_bounds__(kThreads, (OUT_FMT == YP_FMT_BF16 && UNITS == 
   if (threadIdx.x == 0) stamp(4);
   if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
   if (threadIdx.x == 32) stamp(5);
+  if (a.dbg && threadIdx.x == 0 && cta_lin < 20000) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[514 + 3 * cta_lin] = static_cast<long long>(t);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -753,7 +790,8 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     cols = 2 * Nt;
   } else {
     const int total = (tmem_limit / Nt) >= 1 ? tmem_limit / Nt : 512 / Nt;
-    a.n_iss = (total >= 2 && ksteps >= 2) ? 2 : 1;
+    static const int max_iss = getenv("YP_CONV_ISSUERS") ? atoi(getenv("YP_CONV_ISSUERS")) : 2;
+    a.n_iss = (total >= 2 && ksteps >= 2 && max_iss >= 2) ? 2 : 1;
     a.kstep_mod = a.n_iss == 2 ? 2 : 0;
     int each = total / a.n_iss;
     if (each > 2) each = 2;
@@ -853,6 +891,8 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   memset(&maps, 0, sizeof(maps));
 
   a.dbg = g_timeline;
+  static const int ablate = getenv("YP_CONV_ABLATE") ? atoi(getenv("YP_CONV_ABLATE")) : 0;
+  a.ablate = ablate;
   a.bias = d.bias;
   a.act = d.act;
   a.l2norm = (d.epilogue & YP_EPI_L2NORM) ? 1 : 0;

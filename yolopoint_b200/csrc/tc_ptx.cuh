@@ -132,5 +132,41 @@ __device__ __forceinline__ uint32_t swz_addr(uint32_t tile_base, uint32_t r, uin
   return a ^ (((a >> 7) & mask) << 4);
 }
 
+// ---- warp-uniform issue helpers ------------------------------------------------------------------------------------
+// One lane of the (converged) warp is elected; the others skip the instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// 32-bit halves of the K-major swizzled operand descriptor (see make_smem_desc): the low word carries the start address
+// (advanced by 2 per 32-byte k-step) and LBO = 1, the high word SBO = 8 rows, version 1 and the swizzle mode.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  return ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+}
+template <bool kTf32>
+__device__ __forceinline__ void umma32(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accum) {
+  if (elect_one()) {
+    if (kTf32) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+          "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+          ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+          ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum)
+          : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  if (elect_one()) umma_commit(bar);
+}
+
 }  // namespace
 }  // namespace yp
