@@ -62,6 +62,10 @@ def main():
             prod = [us(v) for v in t[8:8 + nkb]]
             full = [us(v) for v in t[104:104 + nkb]]
             iss = [us(v) for v in t[200:200 + nkb]]
+            for ci in range(4):
+                aa, bb, dd = t[300 + 4 * ci], t[301 + 4 * ci], t[302 + 4 * ci]
+                if aa:
+                    print(f"    chunk {ci}: math done {us(aa):7.2f}  staged {us(bb):7.2f}  store issued {us(dd):7.2f}")
             for i in list(range(min(nkb, 4))) + ([nkb - 1] if nkb > 4 else []):
                 print(f"    unit {i:3d}: TMA issued {prod[i]:7.2f}  landed {full[i]:7.2f}  MMAs issued {iss[i]:7.2f}")
 

@@ -314,9 +314,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     const bool has_res = a.res_base != nullptr && valid;
     const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
 
-    // A chunk (one staging row, CH columns) is computed in passes of at most 32 columns so that the live accumulator /
-    // residual registers stay small enough for two CTAs per SM (one CTA's epilogue then overlaps the other's main loop).
-    constexpr int PU = UNITS > 2 ? 2 : UNITS;      // 16-column units per pass
+    // A chunk (one staging row, CH columns) is computed in passes of 16 columns by a rolled loop: few live registers (two
+    // CTAs per SM, so that one CTA's epilogue overlaps the other's main loop) and a loop body that stays in the instruction
+    // cache -- the unrolled epilogue ran once per CTA from cold code and spent ~40 % of its issue slots waiting for
+    // instruction fetch (ncu source view, stall_no_inst).
+    constexpr int PU = 1;                          // 16-column units per pass
     constexpr int PE = 16 * PU;                    // columns per pass
     constexpr int NP = UNITS / PU;                 // passes per chunk
     // residual of columns [col0, col0 + PE) for this thread's pixel, planes summed (residual format == output format family)
@@ -444,21 +446,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     const int n_pass = n_chunks * NP;
     for (int c = 0; c < n_chunks; ++c) {
       const uint32_t stg = smem_base + (c & 1) * a.staging_set_bytes;
-#pragma unroll
+#pragma unroll 1
       for (int ps = 0; ps < NP; ++ps) {
       float v[PE];
       const int col0 = c * CH + ps * PE;
+      if (a.ablate != 3) load_acc16(col0, v);
+      if (a.act == YP_ACT_SILU) {
 #pragma unroll
-      for (int u = 0; u < PU; ++u) load_acc16(col0 + u * 16, v + u * 16);
+        for (int i = 0; i < PE; ++i) v[i] = (silu_fast(v[i] + bias_s[col0 + i]) + res[i]) * inv_norm;
+      } else {
 #pragma unroll
-      for (int i = 0; i < PE; ++i) v[i] = finish(v[i], col0 + i, res[i]) * inv_norm;
+        for (int i = 0; i < PE; ++i) v[i] = (v[i] + bias_s[col0 + i] + res[i]) * inv_norm;
+      }
       if (c * NP + ps + 1 < n_pass) load_res(col0 + PE, res);   // overlaps the staging / store of this pass
       if (et0 && c < 8 && ps == NP - 1) stamp(300 + 4 * c);
       // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
       if (ps == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       constexpr int VP = PE * (int)sizeof(TO) / 16;     // 16-byte vectors this pass contributes to the staging row
       const int j0 = ps * VP;
-      if (!in_tile) {
+      if (!in_tile || a.ablate == 4) {
         // halo / padding row: nothing to stage
       } else if (OUT_FMT == YP_FMT_F32X2) {
 #pragma unroll
@@ -489,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et0 && c < 8) stamp(301 + 4 * c);
-      if (et0) {
+      if (et0 && a.ablate != 5) {
         for (int m = 0; m < a.n_out_maps; ++m)
           for (int pl = 0; pl < a.out_planes; ++pl)
             tma_store_5d(&maps.out[m], stg + pl * 128 * ROWB, n0 + c * CH, w0, h0, b, pl);
@@ -793,8 +799,11 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     static const int max_iss = getenv("YP_CONV_ISSUERS") ? atoi(getenv("YP_CONV_ISSUERS")) : 2;
     a.n_iss = (total >= 2 && ksteps >= 2 && max_iss >= 2) ? 2 : 1;
     a.kstep_mod = a.n_iss == 2 ? 2 : 0;
-    int each = total / a.n_iss;
-    if (each > 2) each = 2;
+    // one accumulator per issuer: every accumulator costs a 128-lane TMEM read in the epilogue; short K loops (<= 16
+    // k-steps, the 1x1 layers) are issued by a single thread into a single accumulator
+    if (mmas_min <= 16) a.n_iss = 1;
+    if (a.n_iss == 1) a.kstep_mod = 0;
+    int each = 1;
     const int per = mmas_min / a.n_iss;
     if (each > per) each = per;
     YP_REQUIRE(each >= 1, YP_ERR_SHAPE, "conv: no accumulator plan for Nt=%d", Nt);

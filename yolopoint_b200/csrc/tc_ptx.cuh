@@ -16,9 +16,16 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// A pipeline bug must fail loudly, not hang the GPU: a wait that exceeds ~2 s traps.  Kept out of line so that the ~25 wait
+// sites of a kernel do not each carry the printf call sequence (instruction-cache footprint).
+__device__ __noinline__ void mbar_timeout_trap() {
+  if ((threadIdx.x & 31) == 0)
+    printf("yolopoint_b200: mbarrier timeout (block %d,%d,%d warp %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x >> 5);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  long long t0 = clock64();
+  const long long t0 = clock64();
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -28,11 +35,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) break;
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a pipeline bug must fail loudly, not hang the GPU
-      if ((threadIdx.x & 31) == 0)
-        printf("yolopoint_b200 conv_tc: mbarrier timeout (block %d,%d warp %d)\n", blockIdx.x, blockIdx.y, threadIdx.x >> 5);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mbar_timeout_trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
