@@ -134,7 +134,8 @@ def train_main(args, version, H, W, per_gpu, world, rank, local_rank):
     torch.manual_seed(0)
     model = Model(names=NAMES, version=version).to(dev).train()
     model.train_backend = args.train_backend
-    ts = TrainStep(model)
+    graph_x = torch.rand(per_gpu, 3, H, W, device=dev) if args.train_graphs else None
+    ts = TrainStep(model, graph_sample=graph_x)
     K, Wm = args.steps, max(args.warmup, 3)
     host = [synthetic_sample(per_gpu, H, W, seed=7 * rank + i) for i in range(2)]
     host = [{k: v.pin_memory() for k, v in smp.items()} for smp in host]
@@ -184,7 +185,7 @@ def train_main(args, version, H, W, per_gpu, world, rank, local_rank):
                 "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16 operands, fp32 accumulation, fp32 master weights / BN / Adam", "data": "synthetic",
                 "config": {"workload": f"YOLOPoint-{version.upper()} {W}x{H} training step, batch {per_gpu}/GPU (global {per_gpu * world})",
-                           "conv_backend": args.train_backend, "parallelism": f"data parallel over {world} GPU(s), bucketed flat-buffer gradient all-reduce",
+                           "conv_backend": args.train_backend, "cuda_graphs": bool(args.train_graphs), "parallelism": f"data parallel over {world} GPU(s), bucketed flat-buffer gradient all-reduce",
                            "l2": "activations of one step (GBs) exceed L2"},
                 "clocks": sampler.summary(), "gpu_launches": K * n_conv * 2 * 3,
                 "e2e": {"value": Ke * per_gpu * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": Ke},
@@ -213,6 +214,7 @@ def main():
     ap.add_argument("--also-streams", type=int, default=3, help="extra (untimed-for-value) run with this many camera streams, reported under detail")
     ap.add_argument("--train-backend", default="b200", choices=["b200", "cudnn_bf16", "torch"], help="l640train only: conv kernels used by the step")
     ap.add_argument("--train-batch", type=int, default=0, help="l640train only: samples per GPU (default 8)")
+    ap.add_argument("--train-graphs", type=int, default=1, help="l640train only: 1 = forward/backward passes replayed from CUDA graphs, 0 = eager launches")
     args = ap.parse_args()
     version, H, W, per_gpu = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -98,7 +98,7 @@ def _train_worker(rank, world, port, q):
     ref_step = TrainStep.__new__(TrainStep)
     ref_step.model, ref_step.device = m2, torch.device("cpu")
     ref_step.obj_loss, ref_step.det_loss = Lz.ComputeObjectLoss(m2, LOSS_CFG, "cpu"), Lz.ComputeDetectorLoss("cpu")
-    ref_step.sparse_cfg = ts.sparse_cfg
+    ref_step.sparse_cfg, ref_step.graphed = ts.sparse_cfg, None
     torch.manual_seed(100 + rank)
     l2, _ = ref_step.losses(sample)
     l2.backward()
@@ -126,7 +126,7 @@ def test_training_step_gradient_allreduce_gloo():
     procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    outs = [q.get(timeout=600) for _ in procs]
+    outs = [q.get(timeout=240) for _ in procs]
     for p in procs:
         p.join(120)
         assert p.exitcode == 0

@@ -107,9 +107,26 @@ def synthetic_sample(B: int, H: int, W: int, seed: int, device="cpu", boxes_per_
                 warped_valid_mask=torch.ones(B, 1, H, W, device=device), box_labels=f(boxes), inv_homographies=torch.eye(3, device=device).repeat(B, 1, 1))
 
 
+class _FlatOutputs(torch.nn.Module):
+    """Model.forward with its train-mode outputs flattened to a tuple of tensors (what torch.cuda.make_graphed_callables wants)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.m = model
+
+    def forward(self, x):
+        out = self.m(x)
+        return (out["semi"], out["desc"], *out["objects"])
+
+
 class TrainStep:
     def __init__(self, model, epochs: int = 100, lr: float = 1e-3, lrf: float = 0.01, sparse_cfg: Optional[dict] = None, group=None,
-                 bucket_bytes: int = 32 << 20):
+                 bucket_bytes: int = 32 << 20, graph_sample: Optional[torch.Tensor] = None):
+        """``graph_sample``: an image batch [B,3,H,W] on the model's device.  When given, the two forward passes of a step and
+        their backward passes are captured into CUDA graphs (torch.cuda.make_graphed_callables: one forward + one backward graph
+        per pass, shared parameters), so that the ~10^4 kernel launches of a step replay from four graph launches instead of
+        being issued one by one from Python; the batch shape is then fixed.  BatchNorm statistics, the losses, the gradient
+        all-reduce and Adam are unchanged."""
         self.model = model
         self.device = next(model.parameters()).device
         self.obj_loss = Lz.ComputeObjectLoss(model, LOSS_CFG, self.device)
@@ -118,16 +135,31 @@ class TrainStep:
         self.reducer = FlatGradReducer(list(model.parameters()), bucket_bytes, group)
         self.opt = torch.optim.Adam(model.parameters(), lr=lr)
         self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lr_lambda=lambda e: (1 - e / epochs) * (1.0 - lrf) + lrf)
+        self.graphed = None
+        if graph_sample is not None:
+            model.train()
+            bn_state = {k: v.clone() for k, v in model.state_dict().items() if "running_" in k or "num_batches" in k}
+            passes = (_FlatOutputs(model), _FlatOutputs(model))
+            x = graph_sample.detach().clone()
+            self.graphed = torch.cuda.make_graphed_callables(passes, ((x,), (x.clone(),)), num_warmup_iters=3)
+            model.load_state_dict(bn_state, strict=False)      # the warm-up / capture passes updated the running statistics
+            self.reducer.zero()
+
+    def _forward(self, x, which):
+        if self.graphed is None:
+            out = self.model(x)
+            return out["semi"], out["desc"], out["objects"]
+        flat = self.graphed[which](x)
+        return flat[0], flat[1], list(flat[2:])
 
     def losses(self, sample):
         m, dev = self.model, self.device
-        out = m(sample["image"])
-        semi, desc, obj = out["semi"], out["desc"], out["objects"]
+        semi, desc, obj = self._forward(sample["image"], 0)
         loss_obj, items = self.obj_loss(obj, sample["box_labels"])
         loss_det = self.det_loss(semi, Lz.labels2Dto3D(sample["labels_2D"]), Lz.getMasks(sample["valid_mask"], dev))
-        out_w = m(sample["warped_image"])
-        loss_det_w = self.det_loss(out_w["semi"], Lz.labels2Dto3D(sample["warped_labels"]), Lz.getMasks(sample["warped_valid_mask"], dev))
-        loss_desc = Lz.descriptor_loss_sparse(desc, out_w["desc"], sample["warped_valid_mask"], sample["inv_homographies"], **self.sparse_cfg)
+        semi_w, desc_w, _ = self._forward(sample["warped_image"], 1)
+        loss_det_w = self.det_loss(semi_w, Lz.labels2Dto3D(sample["warped_labels"]), Lz.getMasks(sample["warped_valid_mask"], dev))
+        loss_desc = Lz.descriptor_loss_sparse(desc, desc_w, sample["warped_valid_mask"], sample["inv_homographies"], **self.sparse_cfg)
         loss = loss_det + loss_det_w + LAMBDA_DESC * loss_desc + LAMBDA_OBJ * loss_obj
         return loss, dict(det=loss_det.detach(), det_warp=loss_det_w.detach(), desc=loss_desc.detach(), obj=loss_obj.detach())
 
