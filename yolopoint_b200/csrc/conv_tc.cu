@@ -65,7 +65,7 @@ struct ConvArgs {
   long long* dbg;  // optional timeline buffer (yp_debug_conv_timeline); CTA (0,0) records clock64 stamps
 };
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;   // 8 warps: warp 0 TMA producer, warps 1-2 MMA issuers, then all 8 run the epilogue
 constexpr size_t kWsCounterBytes = 64 * 1024;   // split-K arrival counters: one int per output tile, <= 16384 tiles
 constexpr int kMaxStages = 8;
 
@@ -148,9 +148,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < a.Nt; i += 128) bias_s[i] = a.bias ? a.bias[n0 + i] : 0.0f;
-  }
+  for (int i = threadIdx.x; i < a.Nt; i += kThreads) bias_s[i] = a.bias ? a.bias[n0 + i] : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -295,12 +293,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     umma_commit_elect(accum_bar);
   }
   __syncwarp();
-  if (warp >= 2) {
+  {
     // ===================== epilogue =====================
+    // All eight warps take part (the producer and issuer warps join when their loops are done): two warps per TMEM lane
+    // quarter, which split the 16-column units of the tile between them (hf = 0 / 1 takes the even / odd units).  With one
+    // warp per scheduler the epilogue was bound by single-warp instruction latency (~4 cycles per instruction).
     using TO = typename OutT<OUT_FMT>::type;
     constexpr int CH = 16 * UNITS;                 // elements per staging row
     constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int hf = warp >> 2;                      // which half of the column units this warp handles
     const int row = q * 32 + lane;               // accumulator row (TMEM lane) of this thread
     const int rdiv = a.patch ? a.Wp : a.Wt;      // patch mode: rows index the padded patch, halo columns are dropped
     const int rh = row / rdiv, rw = row - rh * rdiv;
@@ -403,7 +405,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
 
     float res[PE];
     asm volatile("griddepcontrol.wait;" ::: "memory");     // the residual may be the previous kernel's output
-    load_res(0, res);               // in flight while the main loop runs
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (et0) stamp(2);
@@ -412,21 +413,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     if (S > 1) {
       // publish this CTA's partial tile, then the last CTA to arrive (per tile) reduces all of them and finishes
       float* mine = a.ws_partial + ((blockIdx.z * n_tiles_all + tile_id) * 128 + row) * a.Nt;
-      for (int u = 0; u < a.Nt / 16; ++u) {
+      for (int u = hf; u < a.Nt / 16; u += 2) {
         float v[16];
         tmem_acc16(u * 16, v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) __stcg(reinterpret_cast<float4*>(mine + u * 16) + j, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
       }
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et0) {
         const int old = atomicAdd(a.ws_counter + tile_id, 1);
         const int last = old == S - 1;
         if (last) a.ws_counter[tile_id] = 0;   // ready for the next launch that uses this workspace
         *split_flag = last;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       run_epilogue = *split_flag != 0;
       __threadfence();
     }
@@ -443,13 +444,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       inv_norm = 1.0f / sqrtf(ss);
     }
 
-    const int n_pass = n_chunks * NP;
     for (int c = 0; c < n_chunks; ++c) {
       const uint32_t stg = smem_base + (c & 1) * a.staging_set_bytes;
+      // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
       for (int ps = 0; ps < NP; ++ps) {
+      if (((c * NP + ps) & 1) != hf) continue;       // the other warp of this lane quarter takes this unit
       float v[PE];
       const int col0 = c * CH + ps * PE;
+      load_res(col0, res);
       if (a.ablate != 3) load_acc16(col0, v);
       if (a.act == YP_ACT_SILU) {
 #pragma unroll
@@ -458,10 +462,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < PE; ++i) v[i] = (v[i] + bias_s[col0 + i] + res[i]) * inv_norm;
       }
-      if (c * NP + ps + 1 < n_pass) load_res(col0 + PE, res);   // overlaps the staging / store of this pass
-      if (et0 && c < 8 && ps == NP - 1) stamp(300 + 4 * c);
-      // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
-      if (ps == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et0 && c < 8) stamp(300 + 4 * c);
       constexpr int VP = PE * (int)sizeof(TO) / 16;     // 16-byte vectors this pass contributes to the staging row
       const int j0 = ps * VP;
       if (!in_tile || a.ablate == 4) {
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       }
       }  // passes
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et0 && c < 8) stamp(301 + 4 * c);
       if (et0 && a.ablate != 5) {
         for (int m = 0; m < a.n_out_maps; ++m)

@@ -50,12 +50,16 @@ class FramePipeline:
         self.ws_kp = torch.empty(L.yp_keypoints_workspace_bytes(B, H, W, max_pts), dtype=torch.uint8, device=dev)
         self.nms_params = YpNmsParams(float(self.cfg["conf_thres_box"]), float(self.cfg["iou_thres_box"]), 1, 1, int(md), 30000, 7680.0, None)
         self.parity = 0
-        # pinned host mirrors for the single read-back
+        # pinned host mirrors for the single read-back, double-buffered so that one frame can be staged / unpacked on the host
+        # while the previous one is still on the GPU (submit_host may run one frame ahead of collect)
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        self.h_frame = torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True)
-        self.h_counts = torch.empty((3, B), dtype=torch.int32, pin_memory=True)
         self.d_counts = z(3, B, dt=torch.int32)
-        self.h_pts, self.h_boxes, self.h_desc, self.h_matches = pin(self.pts[0]), pin(self.boxes), pin(self.descs[0]), pin(self.matches)
+        self._host = [dict(frame=torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True),
+                           counts=torch.empty((3, B), dtype=torch.int32, pin_memory=True), pts=pin(self.pts[0]), boxes=pin(self.boxes),
+                           desc=pin(self.descs[0]), matches=pin(self.matches), done=None) for _ in range(2)]
+        self.h_frame, self.h_counts = self._host[0]["frame"], self._host[0]["counts"]
+        self.h_pts, self.h_boxes, self.h_desc, self.h_matches = (self._host[0][k] for k in ("pts", "boxes", "desc", "matches"))
+        self._n_submit = self._n_collect = 0
         self.graphs = {}   # graphs bake THIS pipeline's buffer addresses, so they are owned here, not by the shared plan
 
     # ---- device work ---------------------------------------------------------------------------
@@ -135,31 +139,42 @@ class FramePipeline:
 
     # ---- host boundary -------------------------------------------------------------------------
     def submit_host(self, frames_u8: np.ndarray):
-        """Enqueue (on the current stream) H2D of the frames, the whole pipeline and the D2H of the compact results."""
+        """Enqueue (on the current stream) H2D of the frames, the whole pipeline and the D2H of the compact results.  At most two
+        submissions may be outstanding (double-buffered pinned host memory): ``submit(i+1)`` before ``collect(i)`` lets the host
+        stage / unpack one frame while the GPU works on the other."""
+        if self._n_submit - self._n_collect >= 2:
+            raise RuntimeError("FramePipeline: two frames already in flight; call collect() first")
         dev = self.eng.device
-        self.h_frame.copy_(torch.from_numpy(np.ascontiguousarray(frames_u8)).view(self.B, self.H, self.W, 3))
-        self.plan.frame_in.copy_(self.h_frame, non_blocking=True)
+        h = self._host[self._n_submit % 2]
+        h["frame"].copy_(torch.from_numpy(np.ascontiguousarray(frames_u8)).view(self.B, self.H, self.W, 3))
+        self.plan.frame_in.copy_(h["frame"], non_blocking=True)
         k = self.step_device(True)
-        self.h_counts.copy_(self.d_counts, non_blocking=True)
-        self.h_pts.copy_(self.pts[k], non_blocking=True)
-        self.h_boxes.copy_(self.boxes, non_blocking=True)
-        self.h_desc.copy_(self.descs[k], non_blocking=True)
-        self.h_matches.copy_(self.matches, non_blocking=True)
-        self._done = torch.cuda.Event()
-        self._done.record(torch.cuda.current_stream(dev))
+        h["counts"].copy_(self.d_counts, non_blocking=True)
+        h["pts"].copy_(self.pts[k], non_blocking=True)
+        h["boxes"].copy_(self.boxes, non_blocking=True)
+        h["desc"].copy_(self.descs[k], non_blocking=True)
+        h["matches"].copy_(self.matches, non_blocking=True)
+        h["done"] = torch.cuda.Event()
+        h["done"].record(torch.cuda.current_stream(dev))
+        self._n_submit += 1
 
     def collect(self):
-        """Wait for the last submit_host and unpack per-image (pts[3,N] f64, desc[D,N] f32, boxes[n,6] f32, matches[3,L] f64)."""
-        self._done.synchronize()
+        """Wait for the oldest outstanding submit_host and unpack per-image (pts[3,N] f64, desc[D,N] f32, boxes[n,6] f32,
+        matches[3,L] f64)."""
+        if self._n_collect >= self._n_submit:
+            raise RuntimeError("FramePipeline.collect() without a matching submit_host()")
+        h = self._host[self._n_collect % 2]
+        self._n_collect += 1
+        h["done"].synchronize()
         out = []
         for b in range(self.B):
-            nk, nb, nm = (int(v) for v in self.h_counts[:, b])
+            nk, nb, nm = (int(v) for v in h["counts"][:, b])
             if nk < 0 or nb < 0:
                 raise RuntimeError(f"buffer overflow (keypoints {nk}, boxes {nb}): raise max_pts / nms_cap")
-            pts = self.h_pts[b, :nk].numpy().astype(np.float64).T.copy()
-            desc = self.h_desc[b, :nk].numpy().T.copy()
-            boxes = self.h_boxes[b, :nb].numpy().copy()
-            matches = self.h_matches[b, :max(nm, 0)].numpy().astype(np.float64).T.copy()
+            pts = h["pts"][b, :nk].numpy().astype(np.float64).T.copy()
+            desc = h["desc"][b, :nk].numpy().T.copy()
+            boxes = h["boxes"][b, :nb].numpy().copy()
+            matches = h["matches"][b, :max(nm, 0)].numpy().astype(np.float64).T.copy()
             out.append((pts, desc, boxes, matches))
         return out
 
