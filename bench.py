@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the YOLOPoint hot path on B200 (contract: see the task statement / DESIGN.md section "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload s640|n480|m1280] [--precision fp32|bf16]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload s640|n480|m1280|l640train] [--precision fp32|bf16]
 
 A "step" is one pass of the whole per-frame hot path (uint8 frame -> network -> Detect decode -> box NMS -> heatmap ->
 keypoint NMS -> descriptor sampling -> two-way match with the previous frame) over one batch of synthetic frames.
@@ -9,7 +9,8 @@ Default workload = BASELINE.json configs[1]: YOLOPoint-S, 640x640, batch 1 per G
 independent frames over ranks with no data-path collective (weak scaling).
 
 One JSON line is printed by rank 0.  `value` = frames/s with the input frames resident in HBM; `e2e` = frames/s through
-FramePipeline.step_host (pinned host frame -> H2D -> pipeline -> D2H of keypoints/descriptors/boxes/matches);
+FramePipeline.submit_host/collect (pinned host frame -> H2D -> pipeline -> D2H of keypoints/descriptors/boxes/matches; one camera
+stream, the host runs one frame ahead);
 `roofline` describes the dominant kernel (tcgen05 conv) against the measured bf16 tensor peak; `cpu_baseline` is the CPU
 oracle (a port of the reference's PyTorch/numpy path) timed on this box's host cores on a bounded sample.
 """
@@ -33,6 +34,7 @@ WORKLOADS = {
     "m1280": ("m", 736, 1280, 4),   # configs[2]: 32 frames over 8 GPUs = 4 per GPU
     "l640train": ("l", 640, 640, 8),  # configs[4]: YOLOPoint-L bf16 training step, 64 samples over 8 GPUs = 8 per GPU
 }
+CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 7.27e6}   # profiles/r01_conv_tc_ncu_full.md: mean of the three YOLOPoint-S layer geometries captured
 NAMES = [str(i) for i in range(80)]
 CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398, "l640train": 135.526}   # SURVEY.md section 8a, per frame (forward)
 
@@ -403,7 +405,9 @@ def main():
             "e2e": {"value": Ke * NS * per_gpu * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": NS * pipe.h2d_bytes(),
                     "d2h_bytes_per_step": NS * pipe.d2h_bytes(), "steps": Ke},
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved_tf, "peak": peaks["tf"],
-                         "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained",
+                         "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": CONV_DRAM_BYTES_PER_LAUNCH.get(args.workload),
+                         "traffic_note": "dram__bytes_read+write per conv launch, mean over the layers in profiles/r01_conv_tc_ncu_full.md (ncu, cold L2)",
+                         "peak_source": f"{peaks['src']} bf16 sustained",
                          "launches_per_step": n_conv, "avg_launch_us": net_ms * 1e3 / n_conv, "algorithmic_gflop_per_step": flops_step / 1e9,
                          "note": "achieved = SURVEY 8a conv FLOPs per frame x frames per step / live CUDA-event time of the conv launches of one step"},
             "detail": {"net_only_ms": net_ms, "keypoints": kp_n, "boxes": box_n, "matches": match_n, "concurrent_camera_streams": multi}}
