@@ -13,7 +13,8 @@ them from here:
 
 One deliberate difference: the negative-sample indices of ``descriptor_loss_sparse`` are drawn with ``torch.randint`` on the
 tensor's device instead of ``numpy.random.randint`` on the host (the reference forces a host round trip per step there,
-loss_functions.py:451-466); the distribution is the same, the random stream is not.
+loss_functions.py:451-466); the distribution is the same, the random stream is not.  On CUDA the sampled negative similarities
+are gathered from one ``da @ db^T`` GEMM instead of a materialised ``[K, n, D]`` product (same values up to TF32 rounding).
 """
 from __future__ import annotations
 
@@ -221,7 +222,18 @@ def descriptor_loss_sparse(descriptors, descriptors_warped, mask_valid_warp, inv
         rnd = torch.randint(0, n, (K, n), device=device)
         same = rnd == torch.arange(n, device=device).unsqueeze(0)
         rnd = torch.where(same, (rnd + 1 + torch.randint(0, max(n - 1, 1), (K, n), device=device)) % n, rnd)   # never the match itself
-    neg = (da.unsqueeze(0) * db[rnd]).sum(-1)
+    if da.is_cuda and n <= 40000:
+        # The reference materialises db[rnd] as a [K, n, D] tensor (4.9 GB for 8 x 3000 samples, K = 200, D = 256) and multiplies it
+        # by the broadcast queries (loss_functions.py:468-471).  The same K x n similarities are entries of the n x n matrix
+        # da @ db^T: one GEMM (TF32 tensor cores, 2.3 GB result) + a gather, ~5x less memory traffic forward and backward.
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            neg = (da @ db.t()).gather(1, rnd.t()).t()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+    else:
+        neg = (da.unsqueeze(0) * db[rnd]).sum(-1)
     neg = torch.clamp(neg - 0.1, min=0).flatten()
     neg_loss = neg.sum() / (torch.count_nonzero(neg) + 1)
     return torch.clamp(1 - pos, min=0).mean() + neg_loss

@@ -61,6 +61,27 @@ def pack_weight(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).reshape(co, -1).to(torch.bfloat16).contiguous()
 
 
+# Packed operand copies of the master weights (nn.Parameter leaves only), reused until the optimizer changes the parameter (tensor
+# version counter): a step uses every weight in two forward passes and two data-gradient passes.
+_PACK_CACHE: dict = {}
+
+
+def _cached(kind: str, w: torch.Tensor, make):
+    if torch.cuda.is_current_stream_capturing() or not (w.is_leaf and isinstance(w, nn.Parameter)):
+        # inside a CUDA graph the packing kernels must be part of the graph; temporaries (zero-padded / rearranged weights) get a
+        # new allocation every call, whose address may later be reused by a different tensor -- never cache those
+        return make()
+    key = (kind, w.data_ptr(), tuple(w.shape))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1]
+    out = make()
+    if len(_PACK_CACHE) > 4096:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (w._version, out)
+    return out
+
+
 def _launch_conv(x, wp, y, ksize, stride, n_taps=0, dh=(), dw=(), up=1, out_hw=None):
     L = _lib.lib(require_device=True)
     d = YpConvDesc()
@@ -80,7 +101,7 @@ def conv_forward(x: torch.Tensor, w: torch.Tensor, stride: int) -> torch.Tensor:
     B, Ci, H, W = x.shape
     Co, _, k, _ = w.shape
     y = torch.empty((B, Co, H // stride, W // stride), dtype=torch.bfloat16, device=x.device, memory_format=_CL)
-    _launch_conv(x, pack_weight(w), y, k, stride)
+    _launch_conv(x, _cached("fwd", w, lambda: pack_weight(w)), y, k, stride)
     return y
 
 
@@ -91,11 +112,10 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, H: int, W: int) -
     dx = torch.empty((B, Ci, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=_CL)
     if stride == 1:
         # a forward conv over dy with the taps flipped and (co, ci) transposed
-        wt = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, -1).to(torch.bfloat16).contiguous()   # [Ci, taps*Co]
+        wt = _cached("dgrad", w, lambda: w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, -1).to(torch.bfloat16).contiguous())   # [Ci, taps*Co]
         _launch_conv(dy, wt, dx, k, 1)
         return dx
     assert k == 3 and stride == 2
-    wb = w.to(torch.bfloat16)
     for ph in range(2):
         for pw in range(2):
             khs = [1] if ph == 0 else [0, 2]
@@ -103,7 +123,8 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, H: int, W: int) -
             taps = [(kh, kw) for kh in khs for kw in kws]
             dh = [(ph + 1 - kh) // 2 for kh, _ in taps]
             dw = [(pw + 1 - kw) // 2 for _, kw in taps]
-            wt = torch.stack([wb[:, :, kh, kw].t() for kh, kw in taps], 1).reshape(Ci, -1).contiguous()   # [Ci, n_taps*Co]
+            wt = _cached(f"dgrad{ph}{pw}", w, lambda: torch.stack([w[:, :, kh, kw].t() for kh, kw in taps], 1).reshape(Ci, -1)
+                         .to(torch.bfloat16).contiguous())   # [Ci, n_taps*Co]
             _launch_conv(dy, wt, dx, 0, 1, len(taps), dh, dw, up=YP_UP_PARITY + 2 * ph + pw, out_hw=(Ho, Wo))
     return dx
 
