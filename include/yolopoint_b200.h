@@ -136,6 +136,21 @@ typedef struct {
 } YpWgradDesc;
 int yp_conv2d_nhwc_wgrad(const YpWgradDesc* desc, void* stream);
 
+/*
+ * yp_bn_act_fwd / yp_bn_act_bwd -- training-mode BatchNorm2d (batch statistics) + SiLU of a Conv block, i.e. the `act(bn(.))` of
+ * models/common.py:22-34 (BN eps / momentum from common.py:18-20) and its backward, on bf16 NHWC activations [P = B*H*W][C], C % 8 == 0.
+ *   fwd: mean/var over the P pixels per channel -> out = act(gamma * (y - mean) * rstd + beta)  (act: 1 = SiLU, 0 = identity);
+ *        running_mean / running_var (may be NULL) are updated in place with `momentum` and the unbiased variance like
+ *        nn.BatchNorm2d; save [4][C] fp32 receives (mean, rstd, scale, shift) for the backward; acc [2][C] fp32 is scratch.
+ *   bwd: dy = gamma*rstd * (dz - mean(dz) - xhat * mean(dz*xhat)), dz = dout * act'(z); dgamma_dbeta [2][C] fp32 receives
+ *        (dbeta = sum dz, dgamma = sum dz*xhat).
+ * Four streaming passes over the activation (2 + 4 bytes per element forward, 4 + 6 backward), fp32 reductions.
+ */
+int yp_bn_act_fwd(const void* y, int64_t P, int32_t C, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                  float momentum, float eps, int32_t act, void* out, float* save, float* acc, void* stream);
+int yp_bn_act_bwd(const void* dout, const void* y, int64_t P, int32_t C, const float* gamma, const float* save, int32_t act, void* dy,
+                  float* dgamma_dbeta, void* stream);
+
 /* Debug aid: when set to a device buffer of 512 + 3 * 20000 int64, CTA (0,0) of every following tcgen05 conv launch records
  * clock64 stamps of its pipeline events in the first 512 slots and every CTA records (SM id, start ns, end ns) behind them
  * (see tools/conv_timeline.py); NULL switches it off.  Not thread safe. */

@@ -107,6 +107,36 @@ def test_padded_channels_and_bias():
         assert _rel(y, yr.detach()) < 2e-2 and _rel(xr.grad, xd.grad) < 1e-2 and _rel(w.grad, wd.grad) < 1e-4 and _rel(b.grad, bd.grad) < 1e-2
 
 
+@pytest.mark.parametrize("shape,act", [((2, 64, 20, 24), True), ((4, 48, 17, 9), True), ((1, 1024, 5, 7), True), ((3, 96, 16, 16), False),
+                                       ((8, 128, 80, 80), True)])
+def test_bn_act_matches_torch(shape, act):
+    """yp_bn_act_fwd / yp_bn_act_bwd vs F.batch_norm (training) + F.silu in fp32 on the same bf16 input: output / input gradient
+    within bf16 rounding (2^-8 of the tensor scale), parameter gradients and running statistics to fp32 reduction accuracy."""
+    B, Cc, H, W = shape
+    g = torch.Generator().manual_seed(Cc)
+    y = (torch.randn(shape, generator=g) * 1.7 + 0.3).cuda().to(torch.bfloat16).contiguous(memory_format=CL)
+    dout = torch.randn(shape, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=CL)
+    bn = torch.nn.BatchNorm2d(Cc, eps=1e-3, momentum=0.03).cuda()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(Cc, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(Cc, generator=g) * 0.2)
+    ref_bn = torch.nn.BatchNorm2d(Cc, eps=1e-3, momentum=0.03).cuda()
+    ref_bn.load_state_dict(bn.state_dict())
+    yr = y.float().requires_grad_(True)
+    zr = ref_bn(yr)
+    outr = F.silu(zr) if act else zr
+    outr.backward(dout.float())
+    yt = y.clone().requires_grad_(True)
+    out = T.bn_act_tc(yt, bn, act)
+    out.backward(dout)
+    scale = float(outr.abs().max())
+    assert float((out.float() - outr).abs().max()) < 2 ** -7 * scale
+    assert float((yt.grad.float() - yr.grad).abs().max()) < 2 ** -6 * float(yr.grad.abs().max())
+    assert _rel(bn.weight.grad, ref_bn.weight.grad.double()) < 1e-3 and _rel(bn.bias.grad, ref_bn.bias.grad.double()) < 1e-3
+    assert _rel(bn.running_mean, ref_bn.running_mean.double()) < 1e-5 and _rel(bn.running_var, ref_bn.running_var.double()) < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
+
+
 def test_model_train_step_matches_torch():
     """One train-mode forward/backward of YOLOPoint-N through the B200 conv kernels vs the PyTorch fp32 path on the same
     parameters: outputs within bf16 noise, every parameter receives a gradient that points the same way."""

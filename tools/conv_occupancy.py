@@ -22,6 +22,7 @@ SHAPES = [
     dict(B=8, H=160, W=160, Cin=64, Cout=128, k=3, s=2, act=False, nobias=True),
     dict(B=1, H=80, W=80, Cin=64, Cout=64, k=3, s=1, res=True),                     # YOLOPoint-S batch 1
     dict(B=1, H=80, W=80, Cin=128, Cout=128, k=1, s=1),
+    dict(B=1, H=160, W=160, Cin=32, Cout=32, k=1, s=1),                             # smallest layer of YOLOPoint-S
 ]
 
 
@@ -62,6 +63,8 @@ def main():
             prod = [us(v) for v in t[8:8 + nkb]]
             full = [us(v) for v in t[104:104 + nkb]]
             iss = [us(v) for v in t[200:200 + nkb]]
+            if t[320]:
+                print(f"    epilogue c0: first barrier {us(t[320]):.2f}  residual loaded {us(t[321]):.2f}  accumulators loaded {us(t[322]):.2f}")
             for ci in range(4):
                 aa, bb, dd = t[300 + 4 * ci], t[301 + 4 * ci], t[302 + 4 * ci]
                 if aa:

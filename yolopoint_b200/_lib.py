@@ -54,6 +54,8 @@ SIGNATURES = {
     "yp_conv2d_nhwc_fwd": (_i32, [_PC, _vp]),
     "yp_conv2d_workspace_bytes": (_sz, [_PC]),
     "yp_conv2d_nhwc_wgrad": (_i32, [C.POINTER(YpWgradDesc), _vp]),
+    "yp_bn_act_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    "yp_bn_act_bwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "yp_debug_conv_timeline": (_i32, [_vp]),
     "yp_sppf_pool": (_i32, [_PV, _vp]),
     "yp_nchw_to_s2d": (_i32, [_vp, _i32, _i32, _i32, _PV, _vp]),

@@ -1,0 +1,220 @@
+// Training-mode BatchNorm2d + SiLU of a Conv block (models/common.py:22-34 of the reference: act(bn(conv(x))) with batch statistics)
+// on bf16 NHWC activations: forward (statistics, normalise + activate) and backward (reductions, input gradient).
+//
+// All four passes are HBM-bound streaming kernels over a [P, C] matrix (P = B*H*W pixels, C channels contiguous); a thread owns one
+// group of 8 channels (one 16-byte vector) and walks the pixels with a stride, so every access is a coalesced 16-byte load/store and
+// the per-channel partial sums live in registers.  Per-block partials are combined in shared memory and added to fp32 accumulators
+// in global memory (2*C floats per pass).
+//   forward : read y (2 B/elem) for the statistics; read y, write out (4 B/elem) for normalise + SiLU
+//   backward: read dout, y (4 B/elem) for sum(dz), sum(dz * xhat); read dout, y, write dy (6 B/elem)
+#include "common.cuh"
+
+namespace yp {
+namespace {
+
+constexpr int kBnThreads = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+
+// Thread layout shared by the passes: G = C/8 channel groups; a block covers `gpb` consecutive groups x `rpb` pixel rows per
+// iteration (gpb * rpb = 256); blockIdx.y walks the group tiles, blockIdx.x the pixel chunks.
+struct Layout {
+  int gpb, rpb;
+};
+__host__ __device__ inline Layout make_layout(int C) {
+  const int G = C / 8;
+  int gpb = 1;
+  while (gpb * 2 <= G && gpb * 2 <= kBnThreads && G % (gpb * 2) == 0) gpb *= 2;   // largest power of two dividing G (<= 256)
+  return Layout{gpb, kBnThreads / gpb};
+}
+
+// two per-channel sums over the pixels: MODE 0 -> (sum y, sum y^2); MODE 1 -> (sum dz, sum dz * xhat)
+template <int MODE>
+__global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dout, long long P, int C,
+                                                               const float* __restrict__ save, int act, float* __restrict__ acc, int rows_per_block) {
+  __shared__ float red[2][kBnThreads][8 + 1];
+  const Layout L = make_layout(C);
+  const int G = C / 8;
+  const int gl = threadIdx.x % L.gpb, rl = threadIdx.x / L.gpb;
+  const int g = blockIdx.y * L.gpb + gl;
+  const long long p0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long p1 = p0 + rows_per_block < P ? p0 + rows_per_block : P;
+  float s0[8], s1[8], mean[8], rstd[8], scale[8], shift[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s0[e] = 0.f; s1[e] = 0.f; }
+  if (MODE == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mean[e] = save[g * 8 + e]; rstd[e] = save[C + g * 8 + e]; scale[e] = save[2 * C + g * 8 + e]; shift[e] = save[3 * C + g * 8 + e];
+    }
+  }
+  for (long long p = p0 + rl; p < p1; p += L.rpb) {
+    float v[8];
+    unpack8(__ldg(y + p * G + g), v);
+    if (MODE == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s0[e] += v[e]; s1[e] = fmaf(v[e], v[e], s1[e]); }
+    } else {
+      float d[8];
+      unpack8(__ldg(dout + p * G + g), d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float dz = d[e];
+        if (act) {
+          const float z = fmaf(v[e], scale[e], shift[e]);
+          const float s = 1.0f / (1.0f + __expf(-z));
+          dz *= s * fmaf(z, 1.0f - s, 1.0f);
+        }
+        s0[e] += dz;
+        s1[e] = fmaf(dz, (v[e] - mean[e]) * rstd[e], s1[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red[0][threadIdx.x][e] = s0[e]; red[1][threadIdx.x][e] = s1[e]; }
+  __syncthreads();
+  // thread t < gpb * 8 * 2 sums one (which, group, channel) column over the rpb row-threads
+  for (int t = threadIdx.x; t < L.gpb * 16; t += kBnThreads) {
+    const int which = t / (L.gpb * 8), rem = t % (L.gpb * 8), gg = rem / 8, e = rem % 8;
+    float s = 0.f;
+    for (int r = 0; r < L.rpb; ++r) s += red[which][r * L.gpb + gg][e];
+    atomicAdd(acc + which * C + (blockIdx.y * L.gpb + gg) * 8 + e, s);
+  }
+}
+
+// per channel: batch statistics -> (mean, rstd, scale, shift); running statistics update (momentum, unbiased variance)
+__global__ void bn_finalize_kernel(const float* __restrict__ acc, long long P, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps, float* __restrict__ save) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = static_cast<double>(P);
+  const double m = acc[c] / n;
+  double var = acc[C + c] / n - m * m;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * rstd;
+  save[c] = static_cast<float>(m);
+  save[C + c] = rstd;
+  save[2 * C + c] = sc;
+  save[3 * C + c] = beta[c] - static_cast<float>(m) * sc;
+  if (running_mean) {
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(m);
+    const double unbiased = P > 1 ? var * n / (n - 1.0) : var;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const uint4* __restrict__ y, long long n_vec, int C, const float* __restrict__ save, int act,
+                                                                  uint4* __restrict__ out) {
+  const int G = C / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    float v[8];
+    unpack8(__ldg(y + i), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float z = fmaf(v[e], __ldg(save + 2 * C + g * 8 + e), __ldg(save + 3 * C + g * 8 + e));
+      v[e] = act ? z / (1.0f + __expf(-z)) : z;
+    }
+    out[i] = pack8(v);
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads) bn_apply_bwd_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y, long long n_vec, long long P, int C,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ save, const float* __restrict__ acc,
+                                                                  int act, uint4* __restrict__ dy) {
+  const int G = C / 8;
+  const float inv_n = 1.0f / static_cast<float>(P);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    float v[8], d[8];
+    unpack8(__ldg(y + i), v);
+    unpack8(__ldg(dout + i), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      const float mean = __ldg(save + c), rstd = __ldg(save + C + c);
+      float dz = d[e];
+      if (act) {
+        const float z = fmaf(v[e], __ldg(save + 2 * C + c), __ldg(save + 3 * C + c));
+        const float s = 1.0f / (1.0f + __expf(-z));
+        dz *= s * fmaf(z, 1.0f - s, 1.0f);
+      }
+      const float xhat = (v[e] - mean) * rstd;
+      v[e] = __ldg(gamma + c) * rstd * (dz - __ldg(acc + c) * inv_n - xhat * __ldg(acc + C + c) * inv_n);
+    }
+    dy[i] = pack8(v);
+  }
+}
+
+int grid_for(long long n_vec) {
+  long long b = (n_vec + kBnThreads - 1) / kBnThreads;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  return static_cast<int>(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+int launch_reduce(int mode, const void* y, const void* dout, long long P, int C, const float* save, int act, float* acc, cudaStream_t st) {
+  const Layout L = make_layout(C);
+  const int gy = (C / 8) / L.gpb;
+  // ~4 blocks per SM in total; every block walks a contiguous range of pixels
+  long long bx = (static_cast<long long>(sm_count()) * 4 + gy - 1) / gy;
+  const long long max_bx = (P + L.rpb - 1) / L.rpb;
+  if (bx > max_bx) bx = max_bx;
+  if (bx < 1) bx = 1;
+  const int rows = static_cast<int>((P + bx - 1) / bx);
+  const dim3 grid(static_cast<unsigned>((P + rows - 1) / rows), gy);
+  if (mode == 0)
+    bn_reduce_kernel<0><<<grid, kBnThreads, 0, st>>>(static_cast<const uint4*>(y), nullptr, P, C, nullptr, act, acc, rows);
+  else
+    bn_reduce_kernel<1><<<grid, kBnThreads, 0, st>>>(static_cast<const uint4*>(y), static_cast<const uint4*>(dout), P, C, save, act, acc, rows);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+}  // namespace
+}  // namespace yp
+
+extern "C" int yp_bn_act_fwd(const void* y, int64_t P, int32_t C, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                             float momentum, float eps, int32_t act, void* out, float* save, float* acc, void* stream) {
+  YP_REQUIRE(y && gamma && beta && out && save && acc, YP_ERR_ARG, "bn_act_fwd: null pointer");
+  YP_REQUIRE(P > 0 && C > 0 && C % 8 == 0, YP_ERR_SHAPE, "bn_act_fwd: P=%lld C=%d (C must be a multiple of 8)", static_cast<long long>(P), C);
+  YP_REQUIRE(yp::aligned16(y) && yp::aligned16(out), YP_ERR_ALIGN, "bn_act_fwd: activations not 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  YP_CUDA_OK(cudaMemsetAsync(acc, 0, 2 * sizeof(float) * C, st));
+  int rc = yp::launch_reduce(0, y, nullptr, P, C, nullptr, act, acc, st);
+  if (rc != YP_OK) return rc;
+  yp::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, P, C, gamma, beta, running_mean, running_var, momentum, eps, save);
+  YP_LAUNCH_OK();
+  const long long n_vec = static_cast<long long>(P) * (C / 8);
+  yp::bn_apply_fwd_kernel<<<yp::grid_for(n_vec), yp::kBnThreads, 0, st>>>(static_cast<const uint4*>(y), n_vec, C, save, act, static_cast<uint4*>(out));
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+extern "C" int yp_bn_act_bwd(const void* dout, const void* y, int64_t P, int32_t C, const float* gamma, const float* save, int32_t act, void* dy,
+                             float* dgamma_dbeta, void* stream) {
+  YP_REQUIRE(dout && y && gamma && save && dy && dgamma_dbeta, YP_ERR_ARG, "bn_act_bwd: null pointer");
+  YP_REQUIRE(P > 0 && C > 0 && C % 8 == 0, YP_ERR_SHAPE, "bn_act_bwd: P=%lld C=%d (C must be a multiple of 8)", static_cast<long long>(P), C);
+  YP_REQUIRE(yp::aligned16(y) && yp::aligned16(dout) && yp::aligned16(dy), YP_ERR_ALIGN, "bn_act_bwd: activations not 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // dgamma_dbeta = [sum dz (= dbeta) | sum dz * xhat (= dgamma)], also the two reductions the input gradient needs
+  YP_CUDA_OK(cudaMemsetAsync(dgamma_dbeta, 0, 2 * sizeof(float) * C, st));
+  int rc = yp::launch_reduce(1, y, dout, P, C, save, act, dgamma_dbeta, st);
+  if (rc != YP_OK) return rc;
+  const long long n_vec = static_cast<long long>(P) * (C / 8);
+  yp::bn_apply_bwd_kernel<<<yp::grid_for(n_vec), yp::kBnThreads, 0, st>>>(static_cast<const uint4*>(dout), static_cast<const uint4*>(y), n_vec, P, C, gamma, save,
+                                                                        dgamma_dbeta, act, static_cast<uint4*>(dy));
+  YP_LAUNCH_OK();
+  return YP_OK;
+}

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (threadIdx.x == 0) stamp(1);
+  if (a.ablate != 6) {   // 6 = launch + prologue only (timing experiment)
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -409,8 +410,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     tc_fence_after();
     if (et0) stamp(2);
 
-    bool run_epilogue = true;
-    if (S > 1) {
+    bool run_epilogue = a.ablate != 7;   // 7 = main loop only (timing experiment)
+    if (S > 1 && a.ablate != 7) {
       // publish this CTA's partial tile, then the last CTA to arrive (per tile) reduces all of them and finishes
       float* mine = a.ws_partial + ((blockIdx.z * n_tiles_all + tile_id) * 128 + row) * a.Nt;
       for (int u = hf; u < a.Nt / 16; u += 2) {
@@ -448,13 +449,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       const uint32_t stg = smem_base + (c & 1) * a.staging_set_bytes;
       // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et0 && c == 0) stamp(320);
 #pragma unroll 1
       for (int ps = 0; ps < NP; ++ps) {
       if (((c * NP + ps) & 1) != hf) continue;       // the other warp of this lane quarter takes this unit
       float v[PE];
       const int col0 = c * CH + ps * PE;
       load_res(col0, res);
+      if (et0 && c == 0 && ps == 0) stamp(321);
       if (a.ablate != 3) load_acc16(col0, v);
+      if (et0 && c == 0 && ps == 0) stamp(322);
       if (a.act == YP_ACT_SILU) {
 #pragma unroll
         for (int i = 0; i < PE; ++i) v[i] = (silu_fast(v[i] + bias_s[col0 + i]) + res[i]) * inv_norm;
@@ -509,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     }  // run_epilogue
   }
 
+  }  // ablate != 6
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) stamp(4);

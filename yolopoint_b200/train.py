@@ -188,6 +188,48 @@ def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# BatchNorm (batch statistics) + SiLU of a Conv block
+# ------------------------------------------------------------------------------------------------------------------
+class _BnActTC(torch.autograd.Function):
+    """act(bn(y)) of models/common.py:22-34 in train mode on yp_bn_act_fwd / yp_bn_act_bwd (bf16 NHWC, fp32 statistics)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, act):
+        L = _lib.lib(require_device=True)
+        y = _cl(y)
+        B, Cc, H, W = y.shape
+        P = B * H * W
+        out = torch.empty_like(y, memory_format=_CL)
+        save = torch.empty(4 * Cc, dtype=torch.float32, device=y.device)
+        acc = torch.empty(2 * Cc, dtype=torch.float32, device=y.device)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        _lib.check(L.yp_bn_act_fwd(y.data_ptr(), P, Cc, g32.data_ptr(), b32.data_ptr(), running_mean.data_ptr() if running_mean is not None else None,
+                                   running_var.data_ptr() if running_var is not None else None, float(momentum), float(eps), int(act), out.data_ptr(),
+                                   save.data_ptr(), acc.data_ptr(), _stream()))
+        ctx.save_for_backward(y, g32, save)
+        ctx.act = int(act)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib(require_device=True)
+        y, g32, save = ctx.saved_tensors
+        dout = _cl(dout)
+        B, Cc, H, W = y.shape
+        dy = torch.empty_like(y, memory_format=_CL)
+        gb = torch.empty(2 * Cc, dtype=torch.float32, device=y.device)
+        _lib.check(L.yp_bn_act_bwd(dout.data_ptr(), y.data_ptr(), B * H * W, Cc, g32.data_ptr(), save.data_ptr(), ctx.act, dy.data_ptr(), gb.data_ptr(), _stream()))
+        return dy, gb[Cc:], gb[:Cc], None, None, None, None, None
+
+
+def bn_act_tc(y: torch.Tensor, bn: nn.BatchNorm2d, act: bool) -> torch.Tensor:
+    out = _BnActTC.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, act)
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # module-tree integration
 # ------------------------------------------------------------------------------------------------------------------
 def _stem_s2d(x: torch.Tensor, w: torch.Tensor):
@@ -220,11 +262,24 @@ class TcConv2d(nn.Conv2d):
         return y
 
 
+def _conv_block_forward(self, x):
+    """Conv.forward (conv -> BN -> SiLU, models/common.py:30-31) with the BN + activation on the fused streaming kernels."""
+    bn = getattr(self, "bn", None)
+    if (self.training and x.is_cuda and bn is not None and isinstance(self.conv, TcConv2d) and not self.conv._tc_cudnn and bn.momentum is not None
+            and bn.track_running_stats and bn.weight is not None and bn.weight.shape[0] % 8 == 0 and isinstance(self.act, (nn.SiLU, nn.Identity))):
+        return bn_act_tc(self.conv(x), bn, isinstance(self.act, nn.SiLU))
+    return self._yp_plain_forward(x)
+
+
 def enable(model: nn.Module, cudnn_crosscheck: bool = False) -> nn.Module:
     """Route every nn.Conv2d of the module tree through the B200 kernels in train mode (in place; parameters are shared,
     state-dict keys unchanged).  BatchNorm keeps fp32 parameters / statistics and consumes the bf16 activations directly.
     ``cudnn_crosscheck`` keeps the same bf16 channels-last dataflow but calls cuDNN for the convolutions (test oracle)."""
     _lib.lib(require_device=True)
+    from .model import Conv
+    if not hasattr(Conv, "_yp_plain_forward"):
+        Conv._yp_plain_forward = Conv.forward
+        Conv.forward = _conv_block_forward
     for mod in model.modules():
         if type(mod) in (nn.Conv2d, TcConv2d):
             mod.__class__ = TcConv2d
