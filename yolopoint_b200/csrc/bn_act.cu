@@ -115,65 +115,83 @@ __global__ void bn_finalize_kernel(const float* __restrict__ acc, long long P, i
   }
 }
 
-__global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const uint4* __restrict__ y, long long n_vec, int C, const float* __restrict__ save, int act,
-                                                                  uint4* __restrict__ out) {
+__global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const uint4* __restrict__ y, long long P, int C, const float* __restrict__ save, int act,
+                                                                  uint4* __restrict__ out, int rows_per_block) {
+  const Layout L = make_layout(C);
   const int G = C / 8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % G);
+  const int gl = threadIdx.x % L.gpb, rl = threadIdx.x / L.gpb;
+  const int g = blockIdx.y * L.gpb + gl;
+  const long long p0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long p1 = p0 + rows_per_block < P ? p0 + rows_per_block : P;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { scale[e] = save[2 * C + g * 8 + e]; shift[e] = save[3 * C + g * 8 + e]; }
+  for (long long p = p0 + rl; p < p1; p += L.rpb) {
     float v[8];
-    unpack8(__ldg(y + i), v);
+    unpack8(__ldg(y + p * G + g), v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float z = fmaf(v[e], __ldg(save + 2 * C + g * 8 + e), __ldg(save + 3 * C + g * 8 + e));
+      const float z = fmaf(v[e], scale[e], shift[e]);
       v[e] = act ? z / (1.0f + __expf(-z)) : z;
     }
-    out[i] = pack8(v);
+    out[p * G + g] = pack8(v);
   }
 }
 
-__global__ void __launch_bounds__(kBnThreads) bn_apply_bwd_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y, long long n_vec, long long P, int C,
+__global__ void __launch_bounds__(kBnThreads) bn_apply_bwd_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y, long long P, int C,
                                                                   const float* __restrict__ gamma, const float* __restrict__ save, const float* __restrict__ acc,
-                                                                  int act, uint4* __restrict__ dy) {
+                                                                  int act, uint4* __restrict__ dy, int rows_per_block) {
+  const Layout L = make_layout(C);
   const int G = C / 8;
+  const int gl = threadIdx.x % L.gpb, rl = threadIdx.x / L.gpb;
+  const int g = blockIdx.y * L.gpb + gl;
+  const long long p0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long p1 = p0 + rows_per_block < P ? p0 + rows_per_block : P;
   const float inv_n = 1.0f / static_cast<float>(P);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % G);
+  float mean[8], rstd[8], scale[8], shift[8], k0[8], k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = g * 8 + e;
+    mean[e] = save[c]; rstd[e] = save[C + c]; scale[e] = save[2 * C + c]; shift[e] = save[3 * C + c];
+    k0[e] = gamma[c] * rstd[e];              // dy = k0 * (dz - k1 - xhat * k2)
+    k1[e] = acc[c] * inv_n;
+    k2[e] = acc[C + c] * inv_n;
+  }
+  for (long long p = p0 + rl; p < p1; p += L.rpb) {
     float v[8], d[8];
-    unpack8(__ldg(y + i), v);
-    unpack8(__ldg(dout + i), d);
+    unpack8(__ldg(y + p * G + g), v);
+    unpack8(__ldg(dout + p * G + g), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int c = g * 8 + e;
-      const float mean = __ldg(save + c), rstd = __ldg(save + C + c);
       float dz = d[e];
       if (act) {
-        const float z = fmaf(v[e], __ldg(save + 2 * C + c), __ldg(save + 3 * C + c));
+        const float z = fmaf(v[e], scale[e], shift[e]);
         const float s = 1.0f / (1.0f + __expf(-z));
         dz *= s * fmaf(z, 1.0f - s, 1.0f);
       }
-      const float xhat = (v[e] - mean) * rstd;
-      v[e] = __ldg(gamma + c) * rstd * (dz - __ldg(acc + c) * inv_n - xhat * __ldg(acc + C + c) * inv_n);
+      const float xhat = (v[e] - mean[e]) * rstd[e];
+      v[e] = k0[e] * (dz - k1[e] - xhat * k2[e]);
     }
-    dy[i] = pack8(v);
+    dy[p * G + g] = pack8(v);
   }
 }
 
-int grid_for(long long n_vec) {
-  long long b = (n_vec + kBnThreads - 1) / kBnThreads;
-  const long long cap = static_cast<long long>(sm_count()) * 8;
-  return static_cast<int>(b < cap ? (b < 1 ? 1 : b) : cap);
-}
-
-int launch_reduce(int mode, const void* y, const void* dout, long long P, int C, const float* save, int act, float* acc, cudaStream_t st) {
+// grid of the streaming passes: blockIdx.y walks the channel-group tiles, blockIdx.x contiguous pixel ranges (~`waves` blocks per SM)
+dim3 pass_grid(long long P, int C, int waves, int* rows_per_block) {
   const Layout L = make_layout(C);
   const int gy = (C / 8) / L.gpb;
-  // ~4 blocks per SM in total; every block walks a contiguous range of pixels
-  long long bx = (static_cast<long long>(sm_count()) * 4 + gy - 1) / gy;
+  long long bx = (static_cast<long long>(sm_count()) * waves + gy - 1) / gy;
   const long long max_bx = (P + L.rpb - 1) / L.rpb;
   if (bx > max_bx) bx = max_bx;
   if (bx < 1) bx = 1;
   const int rows = static_cast<int>((P + bx - 1) / bx);
-  const dim3 grid(static_cast<unsigned>((P + rows - 1) / rows), gy);
+  *rows_per_block = rows;
+  return dim3(static_cast<unsigned>((P + rows - 1) / rows), gy);
+}
+
+int launch_reduce(int mode, const void* y, const void* dout, long long P, int C, const float* save, int act, float* acc, cudaStream_t st) {
+  int rows = 0;
+  const dim3 grid = pass_grid(P, C, 4, &rows);
   if (mode == 0)
     bn_reduce_kernel<0><<<grid, kBnThreads, 0, st>>>(static_cast<const uint4*>(y), nullptr, P, C, nullptr, act, acc, rows);
   else
@@ -196,8 +214,9 @@ extern "C" int yp_bn_act_fwd(const void* y, int64_t P, int32_t C, const float* g
   if (rc != YP_OK) return rc;
   yp::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, P, C, gamma, beta, running_mean, running_var, momentum, eps, save);
   YP_LAUNCH_OK();
-  const long long n_vec = static_cast<long long>(P) * (C / 8);
-  yp::bn_apply_fwd_kernel<<<yp::grid_for(n_vec), yp::kBnThreads, 0, st>>>(static_cast<const uint4*>(y), n_vec, C, save, act, static_cast<uint4*>(out));
+  int rows = 0;
+  const dim3 grid = yp::pass_grid(P, C, 8, &rows);
+  yp::bn_apply_fwd_kernel<<<grid, yp::kBnThreads, 0, st>>>(static_cast<const uint4*>(y), P, C, save, act, static_cast<uint4*>(out), rows);
   YP_LAUNCH_OK();
   return YP_OK;
 }
@@ -212,9 +231,10 @@ extern "C" int yp_bn_act_bwd(const void* dout, const void* y, int64_t P, int32_t
   YP_CUDA_OK(cudaMemsetAsync(dgamma_dbeta, 0, 2 * sizeof(float) * C, st));
   int rc = yp::launch_reduce(1, y, dout, P, C, save, act, dgamma_dbeta, st);
   if (rc != YP_OK) return rc;
-  const long long n_vec = static_cast<long long>(P) * (C / 8);
-  yp::bn_apply_bwd_kernel<<<yp::grid_for(n_vec), yp::kBnThreads, 0, st>>>(static_cast<const uint4*>(dout), static_cast<const uint4*>(y), n_vec, P, C, gamma, save,
-                                                                        dgamma_dbeta, act, static_cast<uint4*>(dy));
+  int rows = 0;
+  const dim3 grid = yp::pass_grid(P, C, 8, &rows);
+  yp::bn_apply_bwd_kernel<<<grid, yp::kBnThreads, 0, st>>>(static_cast<const uint4*>(dout), static_cast<const uint4*>(y), P, C, gamma, save, dgamma_dbeta, act,
+                                                        static_cast<uint4*>(dy), rows);
   YP_LAUNCH_OK();
   return YP_OK;
 }
