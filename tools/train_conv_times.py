@@ -2,8 +2,8 @@
 
   python tools/train_conv_times.py [--version l] [--size 640 640] [--batch 8]
 
-The distinct conv shapes are collected from one train-mode forward of the module tree; each kernel is then timed alone with
-CUDA events on the launching stream (10 launches, best of 3) next to cuDNN's bf16 kernels for the same operation."""
+The distinct conv shapes are collected from one train-mode forward of the module tree; each operation is then timed alone: 10 calls captured in
+a CUDA graph and replayed (CUDA events on the launching stream, best of 3) next to cuDNN's bf16 kernels for the same operation."""
 import argparse
 import os
 import sys
@@ -18,17 +18,28 @@ from yolopoint_b200 import Model, train as T  # noqa: E402
 
 
 def timeit(fn, reps=10):
+    """GPU time per call: `reps` calls captured in a CUDA graph (no Python / ctypes / tensor-map encoding time between the
+    launches, as in the graph-replayed training step), replayed 3 times, best."""
     fn()
     torch.cuda.synchronize()
-    best = 1e9
-    for _ in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+    st = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        fn()
+        st.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        st.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            g.replay()
+            e1.record(st)
+            st.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
     return best
 
 

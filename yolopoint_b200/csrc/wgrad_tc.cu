@@ -51,12 +51,6 @@ struct WgradArgs {
 constexpr int kWgThreads = 192;
 constexpr int kWgMaxStages = 4;
 
-// MN-major shared-memory operand descriptor, SWIZZLE_128B: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version 1 | layout 2
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
-         (static_cast<uint64_t>(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -72,7 +66,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index as a warp-uniform value
 
   const int n_ci_tiles = (a.Cin + 64 * a.NB - 1) / (64 * a.NB);
   const int co0 = (blockIdx.y / n_ci_tiles) * 128;
@@ -114,7 +108,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t x_off = 2u * a.dy_blk_bytes;                 // X strips follow the two dY blocks inside a stage
   const uint32_t x_box_bytes = a.NB * a.x_blk_bytes;
 
-  if (warp == 0 && lane == 0) {
+  // Producer and issuer loops are warp-uniform (the whole warp walks the loop, one elected lane executes each TMA / tcgen05
+  // instruction, 32-bit descriptor arithmetic) -- see conv_tc.cu: issuing under `lane == 0` costs ~450 cycles per MMA.
+  if (warp == 0) {
     // ===================== TMA producer =====================
     int s = 0, ph = 0;
     for (int i = 0; i < n_my; ++i) {
@@ -122,21 +118,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       const int b = strip / a.strips_per_img;
       const int h0 = (strip - b * a.strips_per_img) * a.Ht;
       mbar_wait(empty_bar(s), ph ^ 1);
-      mbar_expect_tx(full_bar(s), a.tx_bytes);
       const uint32_t st = smem_base + s * a.stage_bytes;
-      for (int j = 0; j < 2; ++j) tma_load_4d(st + j * a.dy_blk_bytes, &maps.dy, full_bar(s), co0 + 64 * j, 0, h0, b);
-      for (int bx = 0; bx < a.n_box; ++bx) {
-        // stride 2: the tensor map of strip bx already selects (row parity, column parity); see the host code
-        const CUtensorMap* m = &maps.x[bx];
-        for (int j = 0; j < a.NB; ++j)
-          tma_load_4d(st + x_off + bx * x_box_bytes + j * a.x_blk_bytes, m, full_bar(s), ci0 + 64 * j, a.x_w0[bx], h0 + x_dh, b);
+      if (elect_one()) {
+        mbar_expect_tx(full_bar(s), a.tx_bytes);
+        for (int j = 0; j < 2; ++j) tma_load_4d(st + j * a.dy_blk_bytes, &maps.dy, full_bar(s), co0 + 64 * j, 0, h0, b);
+        for (int bx = 0; bx < a.n_box; ++bx) {
+          // stride 2: the tensor map of strip bx already selects (row parity, column parity); see the host code
+          const CUtensorMap* m = &maps.x[bx];
+          for (int j = 0; j < a.NB; ++j)
+            tma_load_4d(st + x_off + bx * x_box_bytes + j * a.x_blk_bytes, m, full_bar(s), ci0 + 64 * j, a.x_w0[bx], h0 + x_dh, b);
+        }
       }
       if (++s == a.stages) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const int ksteps = a.Kp / 16;
     const uint32_t ncol = 64u * a.NB;
+    // MN-major SWIZZLE_128B descriptor halves: low = start >> 4 | LBO >> 4 << 16, high = SBO (1024 B) | version 1 | layout 2
+    const uint32_t dhi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lbo = static_cast<uint32_t>(a.dy_blk_bytes >> 4) << 16, b_lbo = static_cast<uint32_t>(a.x_blk_bytes >> 4) << 16;
     int s = 0, ph = 0;
     for (int i = 0; i < n_my; ++i) {
       mbar_wait(full_bar(s), ph);
@@ -144,17 +145,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t st = smem_base + s * a.stage_bytes;
       for (int t = 0; t < a.n_taps; ++t) {
         const uint32_t xb = st + x_off + a.tap_box[t] * x_box_bytes + a.tap_shift[t] * 128u;
-        const uint64_t ad = make_desc_mn(st, a.dy_blk_bytes);
-        const uint64_t bd = make_desc_mn(xb, a.x_blk_bytes);
+        uint32_t al = ((st & 0x3FFFFu) >> 4) | a_lbo, bl = ((xb & 0x3FFFFu) >> 4) | b_lbo;
+        const uint32_t dcol = tmem_base + t * ncol;
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ko = static_cast<uint64_t>(k) * (16u * 128u >> 4);   // 16 pixel rows of 128 bytes
-          umma<false>(tmem_base + t * ncol, ad + ko, bd + ko, a.idesc, (i | k) ? 1u : 0u);
+          umma32<false>(dcol, al, bl, dhi, a.idesc, (i | k) ? 1u : 0u);
+          al += (16u * 128u) >> 4; bl += (16u * 128u) >> 4;   // 16 pixel rows of 128 bytes
         }
       }
-      umma_commit(empty_bar(s));
+      umma_commit_elect(empty_bar(s));
       if (++s == a.stages) { s = 0; ph ^= 1; }
     }
-    umma_commit(accum_bar);
+    umma_commit_elect(accum_bar);
   }
   __syncwarp();
   if (warp >= 2) {
