@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YP_ABI_VERSION 2
+#define YP_ABI_VERSION 3
 
 typedef enum {
   YP_OK = 0,
@@ -74,6 +74,10 @@ typedef enum { YP_ACT_NONE = 0, YP_ACT_SILU = 1 } YpAct;
 typedef enum { YP_ALGO_TCGEN05 = 0, YP_ALGO_SIMT = 1 } YpConvAlgo;
 #define YP_EPI_L2NORM 1u /* divide each output pixel by its L2 norm over all `cout` channels */
 #define YP_EPI_NO_PATCH 2u /* planner hint: do not use the shared-memory patch formulation of 3x3 stride-1 convs */
+#define YP_EPI_ROWMIN 4u   /* descriptor matching on the tensor cores: nothing is stored; for every input pixel i (a descriptor of set 1, the
+                              1x1 "conv" weights being the descriptors of set 2) the epilogue reduces key(i, j) = float_bits(sqrt(2 - 2*clip(<d1_i, d2_j>,
+                              -1, 1))) << 32 | (j + col_off) over the output channels j with an integer MIN into row_key[i] (the keys of
+                              yp_match_partial; PointTracker.nn_match_two_way, demo.py:300-341).  Needs ksize 1, F32X2 operands, n_out = 0. */
 
 /*
  * yp_conv2d_nhwc_fwd -- one Conv block of the reference in eval/fused form:
@@ -111,6 +115,11 @@ typedef struct {
      autograd of models/common.py:22-34 in the reference's training step, train.py:208-220). */
   int32_t n_taps;
   int8_t tap_dh[9], tap_dw[9];
+  /* YP_EPI_ROWMIN: */
+  unsigned long long* row_key; /* [in.W] keys, pre-filled with ~0 by the caller */
+  const int32_t* n_rows;       /* device count of valid input pixels (descriptors of set 1), NULL = in.W */
+  const int32_t* n_cols;       /* device count of valid output channels (descriptors of set 2), NULL = cout */
+  int32_t col_off;             /* added to j in the key (column shard offset of the multi-GPU match) */
 } YpConvDesc;
 
 int yp_conv2d_nhwc_fwd(const YpConvDesc* desc, void* stream);

@@ -138,6 +138,32 @@ def test_match_vs_oracle_planted(N1, N2, D):
     np.testing.assert_allclose(got[2], ref[2], rtol=0, atol=1e-4)
 
 
+@pytest.mark.parametrize("N1,N2,D", [(700, 900, 64), (2048, 2300, 128), (4096, 4000, 256)])
+def test_match_tensor_core_path_vs_oracle(N1, N2, D):
+    """The tcgen05 row-minimum passes (3xTF32) give the same matches as the oracle: indices bit-exact, scores 1e-4 abs; device-side
+    counts mask the padded rows / columns."""
+    rs = np.random.RandomState(N2 + D)
+    d1 = rs.normal(0, 1, (D, N1)).astype(np.float32); d1 /= np.linalg.norm(d1, axis=0)
+    perm = rs.permutation(N1)[:min(N1, N2)]
+    d2 = rs.normal(0, 1, (D, N2)).astype(np.float32)
+    d2[:, :len(perm)] = d1[:, perm] + 0.05 * rs.normal(0, 1, (D, len(perm))).astype(np.float32)
+    d2 /= np.linalg.norm(d2, axis=0)
+    ref = O.nn_match_two_way(d1, d2, 0.7)
+    a = torch.from_numpy(np.ascontiguousarray(d1.T)).cuda()
+    b = torch.from_numpy(np.ascontiguousarray(d2.T)).cuda()
+    m, cnt = ops.match_two_way(a, None, b, None, 0.7, algo="tc")
+    got = m[:int(cnt.item())].cpu().numpy().T.astype(np.float64)
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got[:2], ref[:2])
+    np.testing.assert_allclose(got[2], ref[2], rtol=0, atol=1e-4)
+    # capacity > count: rows / columns beyond the device-side counts must be ignored
+    a2 = torch.cat((a, torch.randn(300, D, device="cuda")), 0).contiguous()
+    b2 = torch.cat((b, torch.randn(500, D, device="cuda")), 0).contiguous()
+    n1 = torch.tensor([N1], dtype=torch.int32, device="cuda"); n2 = torch.tensor([N2], dtype=torch.int32, device="cuda")
+    m2, cnt2 = ops.match_two_way(a2, n1, b2, n2, 0.7, algo="tc")
+    assert int(cnt2.item()) == int(cnt.item()) and torch.equal(m2[:int(cnt2.item())], m[:int(cnt.item())])
+
+
 def test_match_full_size_properties():
     """BASELINE config 4 upper size (16384 x 16384, D=256): too slow for the CPU oracle, so check size-independent
     properties: matching a set against a permutation of itself returns the permutation with distance ~0, symmetric."""

@@ -36,7 +36,8 @@ def main():
         perm = torch.randperm(N, generator=g)
         d2 = d1[perm] + 0.05 * torch.randn(N, D, generator=g); d2 /= d2.norm(dim=1, keepdim=True)   # planted matches
         d1, d2 = d1.to(dev), d2.to(dev).contiguous()
-        fn = (lambda: match_two_way_sharded(d1, d2, 0.7)) if world > 1 else (lambda: ops.match_two_way(d1, None, d2, None, 0.7))
+        algo = os.environ.get("YP_MATCH_ALGO", "auto")
+        fn = (lambda: match_two_way_sharded(d1, d2, 0.7)) if world > 1 else (lambda: ops.match_two_way(d1, None, d2, None, 0.7, algo=algo))
         for _ in range(3):
             m, cnt = fn()
         torch.cuda.synchronize()

@@ -17,6 +17,7 @@ YP_FMT_F32X2, YP_FMT_BF16, YP_FMT_F32 = 0, 1, 2
 YP_ACT_NONE, YP_ACT_SILU = 0, 1
 YP_ALGO_TCGEN05, YP_ALGO_SIMT = 0, 1
 YP_EPI_L2NORM = 1
+YP_EPI_ROWMIN = 4
 YP_UP_PARITY = 16
 STATUS = {0: "YP_OK", -1: "YP_ERR_SHAPE", -2: "YP_ERR_ALIGN", -3: "YP_ERR_ARCH", -4: "YP_ERR_CUDA",
           -5: "YP_ERR_CAPACITY", -6: "YP_ERR_ARG"}
@@ -31,7 +32,8 @@ class YpConvDesc(C.Structure):
     _fields_ = [("in_", YpView), ("weight", C.c_void_p), ("bias", C.c_void_p), ("ksize", C.c_int32), ("stride", C.c_int32),
                 ("cout", C.c_int32), ("act", C.c_int32), ("epilogue", C.c_uint32), ("residual", YpView), ("n_out", C.c_int32),
                 ("out", YpView * 2), ("algo", C.c_int32), ("tile_n", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_uint64), ("n_taps", C.c_int32), ("tap_dh", C.c_int8 * 9), ("tap_dw", C.c_int8 * 9)]
+                ("workspace_bytes", C.c_uint64), ("n_taps", C.c_int32), ("tap_dh", C.c_int8 * 9), ("tap_dw", C.c_int8 * 9),
+                ("row_key", C.c_void_p), ("n_rows", C.c_void_p), ("n_cols", C.c_void_p), ("col_off", C.c_int32)]
 
 
 class YpWgradDesc(C.Structure):
@@ -102,7 +104,7 @@ def lib(require_device: bool = False):
                     except AttributeError as e:  # pragma: no cover
                         raise YoloPointB200Error(f"{LIB_PATH} does not export {name}") from e
                     fn.restype, fn.argtypes = res, args
-                if handle.yp_abi_version() != 2:
+                if handle.yp_abi_version() != 3:
                     raise YoloPointB200Error("ABI version mismatch between _lib.py and libyolopoint_b200.so")
                 _lib = handle
     if require_device:

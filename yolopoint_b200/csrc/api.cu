@@ -49,7 +49,12 @@ extern "C" int yp_check_device(void) {
 }
 
 extern "C" int yp_conv2d_nhwc_fwd(const YpConvDesc* d, void* stream) {
-  YP_REQUIRE(d && d->in.base && d->weight && d->n_out >= 1 && d->out[0].base, YP_ERR_ARG, "conv: null pointer in descriptor");
+  YP_REQUIRE(d && d->in.base && d->weight, YP_ERR_ARG, "conv: null pointer in descriptor");
+  if (d->epilogue & YP_EPI_ROWMIN)
+    YP_REQUIRE(d->row_key && d->n_out == 0 && d->ksize == 1 && d->algo == YP_ALGO_TCGEN05 && d->in.format == YP_FMT_F32X2, YP_ERR_ARG,
+               "conv: YP_EPI_ROWMIN needs row_key, n_out = 0, ksize 1, the tcgen05 algorithm and F32X2 operands");
+  else
+    YP_REQUIRE(d->n_out >= 1 && d->out[0].base, YP_ERR_ARG, "conv: null output in descriptor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d->algo == YP_ALGO_SIMT) return yp::conv_simt_forward(*d, st);
   if (d->algo == YP_ALGO_TCGEN05) return yp::conv_tc_forward(*d, st);

@@ -58,6 +58,10 @@ struct ConvArgs {
   uint32_t tmem_cols;
   const float* bias;
   int act, l2norm;
+  int rowmin, col_off;                 // YP_EPI_ROWMIN: reduce distance keys over the output channels instead of storing
+  unsigned long long* row_key;
+  const int* n_rows;
+  const int* n_cols;
   const void* res_base;
   long long res_pix, res_plane;
   int n_out_maps, out_planes, out_row_bytes, staging_set_bytes;
@@ -432,6 +436,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       run_epilogue = *split_flag != 0;
       __threadfence();
     }
+    if (run_epilogue && a.rowmin) {
+      // descriptor matching: key(i, j) = bits(sqrt(2 - 2 clip(<d1_i, d2_j>))) << 32 | j, integer MIN over this tile's columns
+      const int n_rows = a.n_rows ? min(*a.n_rows, a.Wo) : a.Wo;
+      const int n_cols = a.n_cols ? *a.n_cols : (int)(gridDim.y * a.Nt);
+      unsigned long long best = ~0ull;
+      for (int u = hf; u < a.Nt / 16; u += 2) {
+        float v[16];
+        load_acc16(u * 16, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int j = n0 + u * 16 + e;
+          const float d = fminf(fmaxf(v[e], -1.0f), 1.0f);
+          const float dist = sqrtf(__fsub_rn(2.0f, __fmul_rn(2.0f, d)));
+          const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(dist)) << 32) | static_cast<unsigned int>(j + a.col_off);
+          if (j < n_cols) best = min(best, key);
+        }
+      }
+      if (valid && ow < n_rows && best != ~0ull) atomicMin(a.row_key + ow, best);
+      run_epilogue = false;
+    }
     if (run_epilogue) {
     float inv_norm = 1.0f;
     if (a.l2norm) {                 // desc / ||desc||_2 over all Nt channels of the pixel (single N tile)
@@ -657,7 +681,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
              "conv: k=%d s=%d (n_taps=%d) unsupported", d.ksize, d.stride, d.n_taps);
   YP_REQUIRE(in.C % 16 == 0 && d.cout % 16 == 0, YP_ERR_SHAPE, "conv: Cin=%d / Cout=%d must be multiples of 16", in.C, d.cout);
   YP_REQUIRE(d.stride == 1 || (in.H % 2 == 0 && in.W % 2 == 0), YP_ERR_SHAPE, "conv: stride 2 needs even H,W");
-  YP_REQUIRE(d.n_out >= 1 && d.n_out <= 2, YP_ERR_SHAPE, "conv: n_out=%d", d.n_out);
+  YP_REQUIRE((d.n_out >= 1 && d.n_out <= 2) || ((d.epilogue & YP_EPI_ROWMIN) && d.n_out == 0), YP_ERR_SHAPE, "conv: n_out=%d", d.n_out);
   const int Ho = in.H / d.stride, Wo = in.W / d.stride;
 
   ConvArgs& a = P->a;
@@ -697,7 +721,8 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   const int ksteps = (a.patch ? 9 : 1) * (a.ck_bytes / 32);   // MMA k-steps per K-loop unit
 
   // ---- output format / staging geometry
-  const int out_fmt = d.out[0].format;
+  const bool rowmin = (d.epilogue & YP_EPI_ROWMIN) != 0;
+  const int out_fmt = rowmin ? YP_FMT_F32 : d.out[0].format;
   P->out_fmt = out_fmt;
   for (int i = 0; i < d.n_out; ++i) {
     YP_REQUIRE(d.out[i].format == out_fmt, YP_ERR_SHAPE, "conv: all outputs must share one format");
@@ -745,7 +770,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
 
   // ---- split-K: deep layers on small feature maps occupy few CTAs; slice K over grid.z so that ~#SM CTAs are busy.
   int S = 1;
-  if (allow_split && d.split_k != 1 && static_cast<size_t>(m_tiles) * n_tiles * sizeof(int) <= kWsCounterBytes) {
+  if (allow_split && !rowmin && d.split_k != 1 && static_cast<size_t>(m_tiles) * n_tiles * sizeof(int) <= kWsCounterBytes) {
     const int ctas = m_tiles * n_tiles;
     int want = d.split_k > 1 ? d.split_k : nsm / ctas;
     if (want > 16) want = 16;
@@ -911,6 +936,9 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   a.bias = d.bias;
   a.act = d.act;
   a.l2norm = (d.epilogue & YP_EPI_L2NORM) ? 1 : 0;
+  a.rowmin = (d.epilogue & YP_EPI_ROWMIN) ? 1 : 0;
+  a.row_key = d.row_key; a.n_rows = d.n_rows; a.n_cols = d.n_cols; a.col_off = d.col_off;
+  if (a.rowmin) YP_REQUIRE(in.B == 1 && in.H == 1, YP_ERR_SHAPE, "conv: YP_EPI_ROWMIN expects the descriptors of set 1 as a [1, 1, N1, D] view");
   if (d.residual.base) {
     YP_REQUIRE(d.residual.C == d.cout && d.residual.H == Ho && d.residual.W == Wo && d.residual.B == in.B, YP_ERR_SHAPE, "conv: residual geometry mismatch");
     YP_REQUIRE(d.residual.format == out_fmt, YP_ERR_SHAPE, "conv: residual format %d must equal the output format %d", d.residual.format, out_fmt);

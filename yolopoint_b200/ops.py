@@ -162,9 +162,52 @@ def match_finalize(row_key: torch.Tensor, n1: Optional[torch.Tensor], col_key: t
     return m, cnt
 
 
-def match_two_way(d1: torch.Tensor, n1, d2: torch.Tensor, n2, nn_thresh: float):
-    """Single-GPU two-way match of row-major descriptors."""
+def _rowmin_pass(q: torch.Tensor, nq: Optional[torch.Tensor], k: torch.Tensor, nk: Optional[torch.Tensor], keys: torch.Tensor, col_off: int = 0):
+    """keys[i] = min_j key(q_i, k_j) on the tcgen05 conv kernel (YP_EPI_ROWMIN): q [Nq,D] are the 'pixels' of a 1x1 conv whose
+    weights are the k [Nk,D] descriptors; 3xTF32 operands (hi/lo planes), the Nq x Nk similarity matrix is never written."""
+    from ._lib import YP_ACT_NONE, YP_ALGO_TCGEN05, YP_EPI_ROWMIN, YP_FMT_F32X2, YpConvDesc
+    from .engine import make_view, split_tf32
+    L = _lib.lib(require_device=True)
+    Nq, D = q.shape
+    Nk = k.shape[0]
+    Nkp = (Nk + 127) // 128 * 128                     # N tile of 128 output channels
+    qa = split_tf32(q).view(2, 1, 1, Nq, D).contiguous()
+    kw = torch.zeros((2, Nkp, D), dtype=torch.float32, device=k.device)
+    kw[:, :Nk] = split_tf32(k)
+    d = YpConvDesc()
+    d.in_ = make_view(qa, YP_FMT_F32X2, 0, D)
+    d.weight, d.bias = kw.data_ptr(), None
+    d.ksize, d.stride, d.cout, d.act, d.epilogue, d.n_out = 1, 1, Nkp, YP_ACT_NONE, YP_EPI_ROWMIN, 0
+    d.algo, d.tile_n, d.split_k = YP_ALGO_TCGEN05, 128, 1
+    d.row_key = keys.data_ptr()
+    d.n_rows = nq.data_ptr() if nq is not None else None
+    if nk is None:
+        nk = torch.tensor([Nk], dtype=torch.int32, device=k.device)
+    d.n_cols = nk.data_ptr()
+    d.col_off = int(col_off)
+    _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), _stream(q.device)))
+    return qa, kw, nk      # keep the operand buffers alive until the caller has synchronised / enqueued its consumer
+
+
+def match_partial_tc(d1: torch.Tensor, n1: Optional[torch.Tensor], d2: torch.Tensor, n2: Optional[torch.Tensor], col_off: int = 0):
+    """Tensor-core form of match_partial: two row-minimum passes (rows of d1 against d2, rows of d2 against d1)."""
+    _need_cuda(d1, "desc1")
+    assert d1.is_contiguous() and d2.is_contiguous() and d1.dtype == torch.float32 and d2.dtype == torch.float32
+    assert d1.shape[1] % 16 == 0, "descriptor dimension must be a multiple of 16"
+    rk = torch.full((d1.shape[0],), -1, dtype=torch.int64, device=d1.device)      # all ones = "no candidate"
+    ck = torch.full((d2.shape[0],), -1, dtype=torch.int64, device=d1.device)
+    keep = [_rowmin_pass(d1, n1, d2, n2, rk, col_off), _rowmin_pass(d2, n2, d1, n1, ck, 0)]
+    rk._yp_keep = keep
+    return rk, ck
+
+
+def match_two_way(d1: torch.Tensor, n1, d2: torch.Tensor, n2, nn_thresh: float, algo: str = "auto"):
+    """Single-GPU two-way match of row-major descriptors.  algo: "simt" = fused fp32 FMA kernel (yp_match_partial), "tc" = two
+    3xTF32 tcgen05 row-minimum passes (yp_conv2d_nhwc_fwd + YP_EPI_ROWMIN), "auto" = tc from 8192 descriptors per side on (measured
+    crossover on B200: 0.89 vs 1.12 ms at 8192, 2.72 vs 4.38 ms at 16384, D = 256; below that the operand split costs more than it saves)."""
     if nn_thresh < 0.0:
         raise ValueError("'nn_thresh' should be non-negative")
-    rk, ck = match_partial(d1, n1, d2, n2)
+    if algo == "auto":
+        algo = "tc" if min(d1.shape[0], d2.shape[0]) >= 8192 and d1.shape[1] % 16 == 0 else "simt"
+    rk, ck = match_partial_tc(d1, n1, d2, n2) if algo == "tc" else match_partial(d1, n1, d2, n2)
     return match_finalize(rk, n1, ck, nn_thresh)
