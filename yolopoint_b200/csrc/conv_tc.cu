@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);   // same value in every lane: lets the compiler keep MMA operands in uniform registers
   if (threadIdx.x == 0) stamp(1);
   if (a.ablate != 6) {   // 6 = launch + prologue only (timing experiment)
 
