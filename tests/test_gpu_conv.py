@@ -53,6 +53,12 @@ CASES = [
     dict(B=1, H=20, W=20, Cin=1024, Cout=512, k=1, s=1, split=4),
     dict(B=1, H=80, W=80, Cin=128, Cout=128, k=3, s=1, act=False, l2=True, plain=True, nobias=True, split=3),   # L2-norm head with split-K
     dict(B=1, H=40, W=40, Cin=128, Cout=128, k=3, s=1, res=True, split=4, tile=64),
+    # several waves of tiles: in bf16 these run on the persistent kernel (double-buffered TMEM accumulators)
+    dict(B=8, H=80, W=80, Cin=128, Cout=128, k=3, s=1, res=True),                  # patch mode, 432 tiles
+    dict(B=8, H=80, W=80, Cin=128, Cout=256, k=1, s=1),                            # 400 x 1 or 2 N tiles
+    dict(B=6, H=96, W=160, Cin=64, Cout=128, k=3, s=2, act=False, nobias=True),    # stride 2, 360 tiles
+    dict(B=5, H=72, W=72, Cin=64, Cout=80, k=1, s=1, act=False, plain=True),       # fp32 output, odd tile counts
+    dict(B=8, H=80, W=80, Cin=64, Cout=64, k=3, s=1, up=True),                     # two destinations (+ 2x upsample)
 ]
 
 

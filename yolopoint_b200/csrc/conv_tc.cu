@@ -65,6 +65,7 @@ struct ConvArgs {
   const void* res_base;
   long long res_pix, res_plane;
   int n_out_maps, out_planes, out_row_bytes, staging_set_bytes;
+  int persist, n_tiles_n, tiles_total, stg_off, buf_cols;   // persistent variant: tiles per CTA loop, staging offset, TMEM columns per accumulator buffer
   int ablate;      // debug (YP_CONV_ABLATE): 1 = issue no MMAs, 2 = issue no TMA loads (timing experiments; results are garbage)
   long long* dbg;  // optional timeline buffer (yp_debug_conv_timeline); CTA (0,0) records clock64 stamps
 };
@@ -552,6 +553,293 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant for layers with several waves of tiles (bf16; no split-K / L2-norm / row-min): one CTA per SM walks the
+// tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulators are double-buffered in TMEM (2 x 256 columns), so the
+// epilogue of tile i (warps 4-7: TMEM -> registers -> bias / SiLU / residual -> swizzled staging -> TMA store) runs under the
+// K loop of tile i+1 (warp 0 = TMA producer, warps 1-2 = MMA issuers, all continuing through the same mbarrier rings), and the
+// prologue (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM instead of once per tile.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int OUT_FMT, int UNITS, bool kTf32>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_persist_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int per_img = a.tiles_w * a.tiles_h;
+  const int num_kb = a.patch ? a.kb_per_tap : a.n_taps * a.kb_per_tap;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const uint32_t bar_base = smem_base + a.bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto accf_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };
+  auto acce_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 6 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 8);
+
+  if (warp == 0 && lane == 0) {
+    const int n_in = a.stride == 2 ? 4 : 1;
+    for (int i = 0; i < n_in; ++i) tma_prefetch_desc(&maps.in[i]);
+    tma_prefetch_desc(&maps.w);
+    for (int i = 0; i < a.n_out_maps; ++i) tma_prefetch_desc(&maps.out[i]);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), a.n_iss); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), a.n_iss);
+      mbar_init(accf_bar(s), a.n_iss); mbar_init(acce_bar(s), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  // tile t -> (image b, patch origin h0 / w0, first output channel n0); the N tiles of one patch are consecutive
+  auto decode = [&](int t, int& b, int& h0, int& w0, int& n0) {
+    const int nt = t % a.n_tiles_n, m = t / a.n_tiles_n;
+    b = m / per_img;
+    const int trem = m - b * per_img;
+    const int th = trem / a.tiles_w, tw = trem - th * a.tiles_w;
+    h0 = th * a.Ht; w0 = tw * a.Wt; n0 = nt * a.Nt;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    int s = 0, ph = 0, sa = 0, pha = 0;
+    for (int t = blockIdx.x; t < a.tiles_total; t += gridDim.x) {
+      int b, h0, w0, n0;
+      decode(t, b, h0, w0, n0);
+      if (a.patch) {
+        for (int cb = 0; cb < num_kb; ++cb) {
+          mbar_wait(aempty_bar(sa), pha ^ 1);
+          const uint32_t sta = smem_base + sa * a.a_stage_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(afull_bar(sa), a.a_tx);
+            tma_load_5d(sta, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 0);
+            if (a.in_planes == 2 && !a.a_split) tma_load_5d(sta + a.a_plane_off, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 1);
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(s), a.b_tx);
+              tma_load_3d(smem_base + a.b_ring_off + s * a.b_stage_bytes, &maps.w, full_bar(s), (tap * a.kb_per_tap + cb) * a.ck_elems, n0, 0);
+            }
+            if (++s == a.b_stages) { s = 0; ph ^= 1; }
+          }
+          if (++sa == 2) { sa = 0; pha ^= 1; }
+        }
+      } else {
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          int map = 0, dh = 0, dw = 0;
+          if (a.ksize == 3) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            if (a.stride == 1) { dh = kh - 1; dw = kw - 1; }
+            else { map = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1); dh = (kh == 0) ? -1 : 0; dw = (kw == 0) ? -1 : 0; }
+          } else if (a.ksize == 0) {
+            dh = static_cast<int>((a.tap_dh >> (4 * tap)) & 15ull) - 8;
+            dw = static_cast<int>((a.tap_dw >> (4 * tap)) & 15ull) - 8;
+          }
+          const uint32_t st = smem_base + s * a.stage_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), a.tx_bytes);
+            tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
+            if (a.in_planes == 2 && !a.a_split) tma_load_5d(st + a.a_plane_off, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 1);
+            tma_load_3d(st + a.a_region_bytes, &maps.w, full_bar(s), kb * a.ck_elems, n0, 0);
+          }
+          if (++cb == a.kb_per_tap) { cb = 0; ++tap; }
+          if (++s == a.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp - 1 < a.n_iss) {
+    // ===================== MMA issuers =====================
+    const int q = warp - 1;
+    const int ksteps = a.ck_bytes / 32;
+    const uint32_t b_plane = a.Nt * a.ck_bytes;
+    const int cnt = a.iss_cnt[q];
+    const uint32_t cstride = a.iss_stride[q], idesc = a.iss_idesc[q];
+    const int kstart = a.kstep_mod ? q : 0, kinc = a.kstep_mod ? a.kstep_mod : 1;
+    const uint32_t a_off0 = a.job_a[q][0] * a.a_plane_off, b_off0 = a.job_b[q][0] * b_plane;
+    const uint32_t a_off1 = a.job_a[q][1] * a.a_plane_off, b_off1 = a.job_b[q][1] * b_plane;
+    const bool two = a.n_jobs[q] == 2;
+    const uint32_t dhi = smem_desc_hi(a.ck_bytes);
+    int s = 0, ph = 0, sa = 0, pha = 0, it = 0;
+    for (int t = blockIdx.x; t < a.tiles_total; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(acce_bar(buf), ((it >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t col0 = tmem_base + buf * a.buf_cols + a.iss_col[q];
+      uint32_t used = 0;
+      int nxt = 0;
+      if (a.patch) {
+        for (int cb = 0; cb < num_kb; ++cb) {
+          mbar_wait(afull_bar(sa), pha);
+          tc_fence_after();
+          const uint32_t pa = smem_base + sa * a.a_stage_bytes;
+          uint32_t shift = 0;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sb = smem_base + a.b_ring_off + s * a.b_stage_bytes;
+            uint32_t al0 = smem_desc_lo(pa + a_off0 + shift) + 2 * kstart, bl0 = smem_desc_lo(sb + b_off0) + 2 * kstart;
+            uint32_t al1 = smem_desc_lo(pa + a_off1 + shift) + 2 * kstart, bl1 = smem_desc_lo(sb + b_off1) + 2 * kstart;
+            for (int k = kstart; k < ksteps; k += kinc) {
+              umma32<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
+              if (two) umma32<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
+              used |= 1u << nxt;
+              nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+              al0 += 2 * kinc; bl0 += 2 * kinc; al1 += 2 * kinc; bl1 += 2 * kinc;
+            }
+            umma_commit_elect(empty_bar(s));
+            if (++s == a.b_stages) { s = 0; ph ^= 1; }
+            shift += (tap % 3 == 2) ? (a.Wp - 2) * a.ck_bytes : a.ck_bytes;
+          }
+          umma_commit_elect(aempty_bar(sa));
+          if (++sa == 2) { sa = 0; pha ^= 1; }
+        }
+      } else {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sA = smem_base + s * a.stage_bytes;
+          const uint32_t sB = sA + a.a_region_bytes;
+          uint32_t al0 = smem_desc_lo(sA + a_off0) + 2 * kstart, bl0 = smem_desc_lo(sB + b_off0) + 2 * kstart;
+          uint32_t al1 = smem_desc_lo(sA + a_off1) + 2 * kstart, bl1 = smem_desc_lo(sB + b_off1) + 2 * kstart;
+          for (int k = kstart; k < ksteps; k += kinc) {
+            umma32<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
+            if (two) umma32<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
+            used |= 1u << nxt;
+            nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+            al0 += 2 * kinc; bl0 += 2 * kinc; al1 += 2 * kinc; bl1 += 2 * kinc;
+          }
+          umma_commit_elect(empty_bar(s));
+          if (++s == a.stages) { s = 0; ph ^= 1; }
+        }
+      }
+      umma_commit_elect(accf_bar(buf));                   // this issuer's MMAs of the tile have retired
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps, one per TMEM lane quarter) =====================
+    using TO = typename OutT<OUT_FMT>::type;
+    constexpr int CH = 16 * UNITS;
+    constexpr int ROWB = CH * (int)sizeof(TO);
+    constexpr int VP = 16 * (int)sizeof(TO) / 16;          // 16-byte vectors per 16-column unit
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rdiv = a.patch ? a.Wp : a.Wt;
+    const int rh = row / rdiv, rw = row - rh * rdiv;
+    const bool in_tile = rh < a.Ht && rw < a.Wt;
+    const int srow = in_tile ? rh * a.Wt + rw : 127;
+    const bool et0 = (threadIdx.x == 128);
+    const int n_chunks = a.Nt / CH;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    int it = 0, cg = 0;                                     // cg: running chunk counter (selects the staging set)
+    for (int t = blockIdx.x; t < a.tiles_total; t += gridDim.x, ++it) {
+      int b, h0, w0, n0;
+      decode(t, b, h0, w0, n0);
+      const int buf = it & 1;
+      const int oh = h0 + rh, ow = w0 + rw;
+      const bool valid = in_tile && oh < a.Ho && ow < a.Wo;
+      const bool has_res = a.res_base != nullptr && valid;
+      const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
+      const uint32_t taddr_row = tmem_base + buf * a.buf_cols + (static_cast<uint32_t>(q * 32) << 16);
+      mbar_wait(accf_bar(buf), (it >> 1) & 1);
+      tc_fence_after();
+      for (int c = 0; c < n_chunks; ++c, ++cg) {
+        const uint32_t stg = smem_base + a.stg_off + (cg & 1) * a.staging_set_bytes;
+        asm volatile("bar.sync 2, 128;" ::: "memory");      // staging set (cg & 1) was drained (et0 waited for the store of chunk cg-2)
+#pragma unroll 1
+        for (int ps = 0; ps < UNITS; ++ps) {
+          const int col0 = c * CH + ps * 16;
+          float v[16], r[16];
+          tmem_ld16(taddr_row + a.src_col[0] + col0, v);
+          if (a.n_src > 1) {
+            float t2[16];
+            tmem_ld16(taddr_row + a.src_col[1] + col0, t2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += t2[i];
+          } else {
+            tmem_ld_wait();
+          }
+          if (has_res) {
+            if (OUT_FMT == YP_FMT_BF16) {
+              const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_base) + res_off + col0);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 u = __ldg(p + j);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); r[j * 8 + 2 * e] = f.x; r[j * 8 + 2 * e + 1] = f.y; }
+              }
+            } else {
+              const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float4 f = __ldg(p + j); r[j * 4] = f.x; r[j * 4 + 1] = f.y; r[j * 4 + 2] = f.z; r[j * 4 + 3] = f.w; }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = 0.0f;
+          }
+          if (a.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + n0 + col0 + i);
+          }
+          if (a.act == YP_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = silu_fast(v[i]) + r[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          }
+          if (in_tile) {
+            if (OUT_FMT == YP_FMT_BF16) {
+#pragma unroll
+              for (int j = 0; j < VP; ++j) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, ps * VP + j, ROWB)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < VP; ++j)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, ps * VP + j, ROWB)), "f"(v[j * 4]), "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
+            }
+          }
+        }
+        if (c == n_chunks - 1) tc_fence_before();           // last TMEM read of this tile is done (tcgen05.wait::ld above)
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (et0) {
+          if (c == n_chunks - 1) mbar_arrive(acce_bar(buf)); // hand the accumulator buffer back to the issuers
+          for (int m = 0; m < a.n_out_maps; ++m) tma_store_5d(&maps.out[m], stg, n0 + c * CH, w0, h0, b, 0);
+          tma_store_commit();
+          tma_store_wait_read<1>();
+        }
+      }
+    }
+    if (et0) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
 long long* g_timeline = nullptr;
@@ -617,6 +905,25 @@ int launch(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t smem, cuda
   if (smem > configured) {
     YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
+  }
+  static const bool use_pdl = getenv("YP_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  YP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, a));
+  return YP_OK;
+}
+
+template <int OUT_FMT, int UNITS, bool kTf32>
+int launch_persist(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = conv_tc_persist_kernel<OUT_FMT, UNITS, kTf32>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
   }
   static const bool use_pdl = getenv("YP_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
@@ -791,7 +1098,12 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   // Layers with more CTAs than SMs run two CTAs per SM (the epilogue of one overlaps the main loop of the other): each CTA
   // then gets half of the shared memory and at most 256 TMEM columns.
   static const bool allow_dense = getenv("YP_CONV_NO_DENSE") == nullptr;
-  const bool dense = allow_dense && static_cast<long long>(m_tiles) * n_tiles * S > nsm;
+  // Several waves of tiles in bf16: the persistent kernel (one CTA per SM, double-buffered TMEM accumulators) instead of two
+  // independent CTAs per SM.  YP_CONV_PERSIST=0 switches it off.
+  static const bool allow_persist = getenv("YP_CONV_PERSIST") == nullptr || atoi(getenv("YP_CONV_PERSIST")) != 0;
+  const bool persist = allow_persist && !tf32 && S == 1 && !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && out_fmt != YP_FMT_F32X2 &&
+                       static_cast<long long>(m_tiles) * n_tiles > (getenv("YP_CONV_PERSIST_MIN") ? atoll(getenv("YP_CONV_PERSIST_MIN")) : 2LL * nsm);
+  const bool dense = (allow_dense && static_cast<long long>(m_tiles) * n_tiles * S > nsm) || persist;   // persist: 256 columns per accumulator buffer
   const int tmem_limit = dense ? 256 : 512;
 
   // ---- accumulator / issuer plan (see the kernel comment)
@@ -857,7 +1169,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   a.stage_bytes = a.a_region_bytes + b_region_bytes;
   // TMA counts the bytes of the boxes actually written: Ht*Wt (<= 128) rows per A plane, Nt rows per B plane
   a.tx_bytes = a.in_planes * (rows * a.ck_bytes + Nt * a.ck_bytes);
-  int budget = dense ? 104 * 1024 : 200 * 1024;
+  int budget = persist ? 198 * 1024 - 2 * a.staging_set_bytes : (dense ? 104 * 1024 : 200 * 1024);
   int region = 0;
   if (a.patch) {
     a.a_stage_bytes = a.in_planes * rows_alloc * a.ck_bytes;
@@ -882,12 +1194,25 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     a.stages = stages;
     region = stages * a.stage_bytes;
   }
-  if (region < 2 * a.staging_set_bytes) region = 2 * a.staging_set_bytes;
+  if (persist) {
+    // the staging sets may not alias the pipeline stages: the next tile's K loop runs under this tile's epilogue
+    region = (region + 1023) & ~1023;
+    a.stg_off = region;
+    region += 2 * a.staging_set_bytes;
+  } else if (region < 2 * a.staging_set_bytes) region = 2 * a.staging_set_bytes;
   region = (region + 1023) & ~1023;
   a.bar_off = region;
-  P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 6) + Nt * sizeof(float) + 16;
+  P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 10) + Nt * sizeof(float) + 16;
   YP_REQUIRE(P->smem <= 227 * 1024, YP_ERR_SHAPE, "conv: needs %zu bytes of shared memory", P->smem);
   P->grid = dim3(m_tiles, n_tiles, S);
+  a.persist = persist ? 1 : 0;
+  if (persist) {
+    YP_REQUIRE(a.n_src <= 2 && cols <= 256, YP_ERR_SHAPE, "conv(persist): accumulator plan needs %d sources / %d columns", a.n_src, cols);
+    a.n_tiles_n = n_tiles;
+    a.tiles_total = m_tiles * n_tiles;
+    a.buf_cols = 256;
+    P->grid = dim3(std::min(a.tiles_total, nsm), 1, 1);
+  }
   // The arrival counters live in a FIXED-size area at the start of the workspace: layers of one lane share the workspace,
   // and a per-layer counter area would overlap the partial sums an earlier (smaller) layer left behind.
   P->ws_counter_bytes = kWsCounterBytes;
@@ -978,6 +1303,12 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   const size_t smem = P.smem;
   const int units = P.units;
   const bool tf32 = P.tf32;
+#define YP_DISPATCH_P(FMT, U) return launch_persist<FMT, U, false>(maps, a, grid, smem, st)
+  if (a.persist) {
+    if (out_fmt == YP_FMT_BF16) { if (units == 4) YP_DISPATCH_P(YP_FMT_BF16, 4); if (units == 2) YP_DISPATCH_P(YP_FMT_BF16, 2); if (units == 1) YP_DISPATCH_P(YP_FMT_BF16, 1); }
+    else { if (units == 2) YP_DISPATCH_P(YP_FMT_F32, 2); if (units == 1) YP_DISPATCH_P(YP_FMT_F32, 1); }
+  }
+#undef YP_DISPATCH_P
 #define YP_DISPATCH(FMT, U, TF) return launch<FMT, U, TF>(maps, a, grid, smem, st)
   if (tf32) {
     if (out_fmt == YP_FMT_F32X2) { if (units == 2) YP_DISPATCH(YP_FMT_F32X2, 2, true); if (units == 1) YP_DISPATCH(YP_FMT_F32X2, 1, true); }
