@@ -73,6 +73,7 @@ struct ConvArgs {
 constexpr int kThreads = 256;   // 8 warps: warp 0 TMA producer, warps 1-2 MMA issuers, then all 8 run the epilogue
 constexpr size_t kWsCounterBytes = 64 * 1024;   // split-K arrival counters: one int per output tile, <= 16384 tiles
 constexpr int kMaxStages = 8;
+constexpr int kPersistThreads = 384;   // persistent variant: warp 0 producer, warps 1-2 issuers, warps 4-11 epilogue
 
 template <int OUT_FMT>
 struct OutT { using type = float; };
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------
 // Persistent variant for layers with several waves of tiles (bf16; no split-K / L2-norm / row-min): one CTA per SM walks the
 // tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulators are double-buffered in TMEM (2 x 256 columns), so the
-// epilogue of tile i (warps 4-7: TMEM -> registers -> bias / SiLU / residual -> swizzled staging -> TMA store) runs under the
+// epilogue of tile i (warps 4-11: TMEM -> registers -> bias / SiLU / residual -> swizzled staging -> TMA store) runs under the
 // K loop of tile i+1 (warp 0 = TMA producer, warps 1-2 = MMA issuers, all continuing through the same mbarrier rings), and the
 // prologue (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM instead of once per tile.
 // ---------------------------------------------------------------------------------------------
@@ -564,7 +565,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 template <int OUT_FMT, int UNITS, bool kTf32>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_persist_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+__global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -729,12 +730,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_persist_kernel(const __gr
       umma_commit_elect(accf_bar(buf));                   // this issuer's MMAs of the tile have retired
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps, one per TMEM lane quarter) =====================
+    // ===================== epilogue (8 warps: two per TMEM lane quarter, splitting the 16-column units) =====================
     using TO = typename OutT<OUT_FMT>::type;
     constexpr int CH = 16 * UNITS;
     constexpr int ROWB = CH * (int)sizeof(TO);
     constexpr int VP = 16 * (int)sizeof(TO) / 16;          // 16-byte vectors per 16-column unit
     const int q = warp & 3;
+    const int hf = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int rdiv = a.patch ? a.Wp : a.Wt;
     const int rh = row / rdiv, rw = row - rh * rdiv;
@@ -757,9 +759,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_persist_kernel(const __gr
       tc_fence_after();
       for (int c = 0; c < n_chunks; ++c, ++cg) {
         const uint32_t stg = smem_base + a.stg_off + (cg & 1) * a.staging_set_bytes;
-        asm volatile("bar.sync 2, 128;" ::: "memory");      // staging set (cg & 1) was drained (et0 waited for the store of chunk cg-2)
+        asm volatile("bar.sync 2, 256;" ::: "memory");      // staging set (cg & 1) was drained (et0 waited for the store of chunk cg-2)
 #pragma unroll 1
         for (int ps = 0; ps < UNITS; ++ps) {
+          if (((c * UNITS + ps) & 1) != hf) continue;     // the other warp of this lane quarter takes this unit
           const int col0 = c * CH + ps * 16;
           float v[16], r[16];
           tmem_ld16(taddr_row + a.src_col[0] + col0, v);
@@ -823,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_persist_kernel(const __gr
         }
         if (c == n_chunks - 1) tc_fence_before();           // last TMEM read of this tile is done (tcgen05.wait::ld above)
         fence_proxy_async_smem();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         if (et0) {
           if (c == n_chunks - 1) mbar_arrive(acce_bar(buf)); // hand the accumulator buffer back to the issuers
           for (int m = 0; m < a.n_out_maps; ++m) tma_store_5d(&maps.out[m], stg, n0 + c * CH, w0, h0, b, 0);
@@ -927,7 +930,7 @@ int launch_persist(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t sm
   }
   static const bool use_pdl = getenv("YP_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = grid; cfg.blockDim = dim3(kPersistThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;

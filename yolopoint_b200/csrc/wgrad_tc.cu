@@ -23,6 +23,7 @@
 #include <cudaTypedefs.h>
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace yp {
 namespace {
@@ -274,7 +275,10 @@ int wgrad_segment(const YpWgradDesc& d, int c0, int c1, cudaStream_t st) {
   a.n_strips = a.strips_per_img * x.B;
   const int tiles_y = ceil_div(a.Cout, 128) * ceil_div(a.Cin, 64 * a.NB);
   const int tiles_z = d.ksize == 3 ? 3 : 1;
-  int P = ceil_div(2 * sm_count(), tiles_y * tiles_z);
+  // One CTA per SM is resident (3 x ~50 KB stages): size the pixel split so that the grid is a whole number of waves -- rounding
+  // up (e.g. 99 x 3 = 297 CTAs on 148 SMs) would add a third, nearly empty wave.
+  static const int waves = getenv("YP_WGRAD_WAVES") ? atoi(getenv("YP_WGRAD_WAVES")) : 2;
+  int P = (waves * sm_count()) / (tiles_y * tiles_z);
   if (P > a.n_strips) P = a.n_strips;
   if (P < 1) P = 1;
   a.strips_per_cta = ceil_div(a.n_strips, P);
