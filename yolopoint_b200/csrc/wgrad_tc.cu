@@ -30,7 +30,7 @@ namespace {
 
 struct alignas(64) WgradMaps {
   CUtensorMap dy;      // (C, W, H, B) of dY
-  CUtensorMap x[2];    // X strips: [0] = stride 1 / even columns, [1] = odd columns (stride 2)
+  CUtensorMap x[4];    // X strips: stride 1: [0]; stride 2: [row parity * 2 + column parity] views of the input
 };
 
 struct WgradArgs {
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.dy);
-    for (int i = 0; i < a.n_box; ++i) tma_prefetch_desc(&maps.x[i]);
+    for (int i = 0; i < (a.stride == 2 ? 4 : 1); ++i) tma_prefetch_desc(&maps.x[i]);
     for (int s = 0; s < kWgMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         mbar_expect_tx(full_bar(s), a.tx_bytes);
         for (int j = 0; j < 2; ++j) tma_load_4d(st + j * a.dy_blk_bytes, &maps.dy, full_bar(s), co0 + 64 * j, 0, h0, b);
         for (int bx = 0; bx < a.n_box; ++bx) {
-          // stride 2: the tensor map of strip bx already selects (row parity, column parity); see the host code
-          const CUtensorMap* m = &maps.x[bx];
+          // stride 2: filter rows kh = 0 / 2 read the odd input rows, kh = 1 the even ones; strip bx = column parity
+          const CUtensorMap* m = &maps.x[(a.stride == 2 ? (kh == 1 ? 0 : 2) : 0) + bx];
           for (int j = 0; j < a.NB; ++j)
             tma_load_4d(st + x_off + bx * x_box_bytes + j * a.x_blk_bytes, m, full_bar(s), ci0 + 64 * j, a.x_w0[bx], h0 + x_dh, b);
         }
@@ -277,7 +277,9 @@ int wgrad_segment(const YpWgradDesc& d, int c0, int c1, cudaStream_t st) {
   const int tiles_z = d.ksize == 3 ? 3 : 1;
   // One CTA per SM is resident (3 x ~50 KB stages): size the pixel split so that the grid is a whole number of waves -- rounding
   // up (e.g. 99 x 3 = 297 CTAs on 148 SMs) would add a third, nearly empty wave.
-  static const int waves = getenv("YP_WGRAD_WAVES") ? atoi(getenv("YP_WGRAD_WAVES")) : 2;
+  // A single wave: every CTA pays one epilogue (128 x 384 fp32 reductions into dW); measured on the YOLOPoint-L layers, one wave of
+  // long CTAs beats two or three waves (3.20 vs 3.88 vs 4.71 ms per backward pass).
+  static const int waves = getenv("YP_WGRAD_WAVES") ? atoi(getenv("YP_WGRAD_WAVES")) : 1;
   int P = (waves * sm_count()) / (tiles_y * tiles_z);
   if (P > a.n_strips) P = a.n_strips;
   if (P < 1) P = 1;
@@ -297,19 +299,13 @@ int wgrad_segment(const YpWgradDesc& d, int c0, int c1, cudaStream_t st) {
   (void)Wfull;
   if (d.stride == 1) {
     if ((rc = encode_nhwc(&maps.x[0], x, 1, 0, 0, x_col0[0], Wx - x_col0[0], a.Wp, a.Ht)) != YP_OK) return rc;
-    wgrad_tc_kernel<<<dim3(P, tiles_y, tiles_z), kWgThreads, smem, st>>>(maps, a);
-    YP_LAUNCH_OK();
   } else {
-    // one launch per filter row: rows kh = 0 / 2 read the odd input rows, kh = 1 the even ones
-    for (int kh = 0; kh < 3; ++kh) {
-      const int ph = (kh == 1) ? 0 : 1;
-      if ((rc = encode_nhwc(&maps.x[0], x, 2, ph, 0, x_col0[0], Wx - x_col0[0], a.Wp, a.Ht)) != YP_OK) return rc;
-      if ((rc = encode_nhwc(&maps.x[1], x, 2, ph, 1, x_col0[1], Wx - x_col0[1], a.Wp, a.Ht)) != YP_OK) return rc;
-      a.kh0 = kh;
-      wgrad_tc_kernel<<<dim3(P, tiles_y, 1), kWgThreads, smem, st>>>(maps, a);
-      YP_LAUNCH_OK();
-    }
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        if ((rc = encode_nhwc(&maps.x[ph * 2 + pw], x, 2, ph, pw, x_col0[pw], Wx - x_col0[pw], a.Wp, a.Ht)) != YP_OK) return rc;
   }
+  wgrad_tc_kernel<<<dim3(P, tiles_y, tiles_z), kWgThreads, smem, st>>>(maps, a);
+  YP_LAUNCH_OK();
   return YP_OK;
 }
 
