@@ -97,22 +97,59 @@ def _launch_conv(x, wp, y, ksize, stride, n_taps=0, dh=(), dw=(), up=1, out_hw=N
     _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), _stream()))
 
 
-def conv_forward(x: torch.Tensor, w: torch.Tensor, stride: int) -> torch.Tensor:
+def _dgrad_operands(w: torch.Tensor, stride: int):
+    """Operand matrices of the data-gradient launches: stride 1 -> {"dgrad": [Ci, taps*Co]} (taps flipped, co/ci transposed);
+    stride 2 -> one [Ci, n_taps*Co] matrix per output parity class."""
+    Ci = w.shape[1]
+    if stride == 1:
+        return {"dgrad": w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, -1).to(torch.bfloat16).contiguous()}
+    out = {}
+    for ph in range(2):
+        for pw in range(2):
+            taps = [(kh, kw) for kh in ([1] if ph == 0 else [0, 2]) for kw in ([1] if pw == 0 else [0, 2])]
+            out[f"dgrad{ph}{pw}"] = torch.stack([w[:, :, kh, kw].t() for kh, kw in taps], 1).reshape(Ci, -1).to(torch.bfloat16).contiguous()
+    return out
+
+
+class WeightPack:
+    """bf16 operand copies of one conv weight (forward + data-gradient layouts) in persistent buffers, refreshed once per optimizer
+    step by ``refresh()`` -- outside the CUDA graphs of the forward / backward passes, which then contain no packing kernels (a
+    step uses every weight in two forward and two data-gradient passes)."""
+
+    def __init__(self, make_weight, stride: int, need_dgrad: bool):
+        self.make_weight, self.stride, self.need_dgrad, self.bufs = make_weight, stride, need_dgrad, None
+
+    @torch.no_grad()
+    def refresh(self):
+        w = self.make_weight()
+        new = {"fwd": pack_weight(w)}
+        if self.need_dgrad:
+            new.update(_dgrad_operands(w, self.stride))
+        if self.bufs is None:
+            self.bufs = {k: v.clone() for k, v in new.items()}
+        else:
+            for k, v in new.items():
+                self.bufs[k].copy_(v)
+
+
+def conv_forward(x: torch.Tensor, w: torch.Tensor, stride: int, pack: Optional[WeightPack] = None) -> torch.Tensor:
     B, Ci, H, W = x.shape
     Co, _, k, _ = w.shape
     y = torch.empty((B, Co, H // stride, W // stride), dtype=torch.bfloat16, device=x.device, memory_format=_CL)
-    _launch_conv(x, _cached("fwd", w, lambda: pack_weight(w)), y, k, stride)
+    wp = pack.bufs["fwd"] if pack is not None and pack.bufs is not None else _cached("fwd", w, lambda: pack_weight(w))
+    _launch_conv(x, wp, y, k, stride)
     return y
 
 
-def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, H: int, W: int) -> torch.Tensor:
+def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, H: int, W: int, pack: Optional[WeightPack] = None) -> torch.Tensor:
     """dx[b,ih,iw,ci] = sum_{kh,kw,co} dy[b,(ih+p-kh)/s,(iw+p-kw)/s,co] * w[co,ci,kh,kw]  (terms with integral indices)."""
     B, Co, Ho, Wo = dy.shape
     _, Ci, k, _ = w.shape
     dx = torch.empty((B, Ci, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=_CL)
     if stride == 1:
         # a forward conv over dy with the taps flipped and (co, ci) transposed
-        wt = _cached("dgrad", w, lambda: w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, -1).to(torch.bfloat16).contiguous())   # [Ci, taps*Co]
+        packed = pack.bufs if pack is not None and pack.bufs is not None and "dgrad" in pack.bufs else None
+        wt = packed["dgrad"] if packed else _cached("dgrad", w, lambda: _dgrad_operands(w, 1)["dgrad"])   # [Ci, taps*Co]
         _launch_conv(dy, wt, dx, k, 1)
         return dx
     assert k == 3 and stride == 2
@@ -123,8 +160,12 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, H: int, W: int) -
             taps = [(kh, kw) for kh in khs for kw in kws]
             dh = [(ph + 1 - kh) // 2 for kh, _ in taps]
             dw = [(pw + 1 - kw) // 2 for _, kw in taps]
-            wt = _cached(f"dgrad{ph}{pw}", w, lambda: torch.stack([w[:, :, kh, kw].t() for kh, kw in taps], 1).reshape(Ci, -1)
-                         .to(torch.bfloat16).contiguous())   # [Ci, n_taps*Co]
+            key = f"dgrad{ph}{pw}"
+            if pack is not None and pack.bufs is not None and key in pack.bufs:
+                wt = pack.bufs[key]
+            else:
+                wt = _cached(key, w, lambda: torch.stack([w[:, :, kh, kw].t() for kh, kw in taps], 1).reshape(Ci, -1)
+                             .to(torch.bfloat16).contiguous())   # [Ci, n_taps*Co]
             _launch_conv(dy, wt, dx, 0, 1, len(taps), dh, dw, up=YP_UP_PARITY + 2 * ph + pw, out_hw=(Ho, Wo))
     return dx
 
@@ -143,11 +184,11 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, stride: int) -> to
 
 class _Conv2dTC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, stride):
+    def forward(ctx, x, w, stride, pack=None):
         x = _cl(x)
         ctx.save_for_backward(x, w)
-        ctx.stride = stride
-        return conv_forward(x, w, stride)
+        ctx.stride, ctx.pack = stride, pack
+        return conv_forward(x, w, stride, pack)
 
     @staticmethod
     def backward(ctx, dy):
@@ -155,10 +196,10 @@ class _Conv2dTC(torch.autograd.Function):
         dy = _cl(dy)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = conv_dgrad(dy, w, ctx.stride, x.shape[2], x.shape[3])
+            dx = conv_dgrad(dy, w, ctx.stride, x.shape[2], x.shape[3], ctx.pack)
         if ctx.needs_input_grad[1]:
             dw = conv_wgrad(x, dy, w.shape[2], ctx.stride).to(w.dtype)
-        return dx, dw, None
+        return dx, dw, None, None
 
 
 def supported(w: torch.Tensor, stride: int, x: Optional[torch.Tensor] = None) -> bool:
@@ -169,7 +210,12 @@ def supported(w: torch.Tensor, stride: int, x: Optional[torch.Tensor] = None) ->
     return ok
 
 
-def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1) -> torch.Tensor:
+def _pad_weight(w: torch.Tensor) -> torch.Tensor:
+    pad_o, pad_i = (-w.shape[0]) % 16, (-w.shape[1]) % 16
+    return F.pad(w, (0, 0, 0, 0, 0, pad_i, 0, pad_o)) if (pad_o or pad_i) else w
+
+
+def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1, pack: Optional[WeightPack] = None) -> torch.Tensor:
     """Differentiable bias-free conv (pad = k // 2) on the tcgen05 kernels; x [B,Ci,H,W] (any float dtype, converted to
     channels-last bf16), w [Co,Ci,k,k] (fp32 master weights) -> bf16 channels-last [B,Co,H/s,W/s].  Channel counts that are
     not multiples of 16 (Detect: 255, ConvDet: 65) are zero-padded with differentiable torch ops around the kernel."""
@@ -179,7 +225,7 @@ def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
         x = F.pad(x, (0, 0, 0, 0, 0, pad_i))
     if pad_o or pad_i:
         w = F.pad(w, (0, 0, 0, 0, 0, pad_i, 0, pad_o))
-    y = _Conv2dTC.apply(x, w, stride)
+    y = _Conv2dTC.apply(x, w, stride, pack)
     if pad_o:
         y = y[:, :co]
     if bias is not None:
@@ -252,11 +298,12 @@ class TcConv2d(nn.Conv2d):
         w = self.weight
         if getattr(self, "_tc_cudnn", False):   # cross-check mode (tests): cuDNN on the same bf16 channels-last tensors
             return F.conv2d(_cl(x), w.to(torch.bfloat16), None if self.bias is None else self.bias.to(torch.bfloat16), self.stride, self.padding)
+        pack = getattr(self, "_yp_pack", None)
         if (k, s, p) == (6, 2, 2) and w.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
             xs, ws = _stem_s2d(x, w)
-            return conv2d_tc(xs, ws, self.bias, 1)
+            return conv2d_tc(xs, ws, self.bias, 1, pack)
         if p == k // 2 and supported(w, s, x):
-            return conv2d_tc(x, w, self.bias, s)
+            return conv2d_tc(x, w, self.bias, s, pack)
         # geometry outside the kernels' range (not used by any YOLOPoint layer): cuDNN on the same bf16 channels-last tensors
         y = F.conv2d(_cl(x), w.to(torch.bfloat16), None if self.bias is None else self.bias.to(torch.bfloat16), self.stride, self.padding)
         return y
@@ -269,6 +316,35 @@ def _conv_block_forward(self, x):
             and bn.track_running_stats and bn.weight is not None and bn.weight.shape[0] % 8 == 0 and isinstance(self.act, (nn.SiLU, nn.Identity))):
         return bn_act_tc(self.conv(x), bn, isinstance(self.act, nn.SiLU))
     return self._yp_plain_forward(x)
+
+
+def _stem_weight(w: torch.Tensor) -> torch.Tensor:
+    co, Cc = w.shape[0], w.shape[1]
+    return w.view(co, Cc, 3, 2, 3, 2).permute(0, 3, 5, 1, 2, 4).reshape(co, 4 * Cc, 3, 3)
+
+
+def attach_weight_packs(model: nn.Module):
+    """Give every TcConv2d a WeightPack (persistent pre-packed operands) and return the list; call ``refresh()`` on each after
+    every optimizer step (trainer.TrainStep does, from a CUDA graph).  The first convolution never needs a data gradient."""
+    packs = []
+    first = True
+    for mod in model.modules():
+        if isinstance(mod, TcConv2d):
+            k, s, p = mod.kernel_size[0], mod.stride[0], mod.padding[0]
+            stem = (k, s, p) == (6, 2, 2) and mod.weight.shape[1] == 3
+            if not stem and not (p == k // 2 and supported(mod.weight, s)):
+                continue
+            make = (lambda m=mod: _pad_weight(_stem_weight(m.weight.detach()))) if stem else (lambda m=mod: _pad_weight(m.weight.detach()))
+            mod._yp_pack = WeightPack(make, 1 if stem else s, need_dgrad=not (stem or first))
+            packs.append(mod._yp_pack)
+            first = False
+    return packs
+
+
+def detach_weight_packs(model: nn.Module):
+    for mod in model.modules():
+        if hasattr(mod, "_yp_pack"):
+            del mod._yp_pack
 
 
 def enable(model: nn.Module, cudnn_crosscheck: bool = False) -> nn.Module:

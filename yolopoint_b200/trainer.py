@@ -140,8 +140,23 @@ class TrainStep:
         self.opt = torch.optim.Adam(model.parameters(), lr=lr)
         self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lr_lambda=lambda e: (1 - e / epochs) * (1.0 - lrf) + lrf)
         self.graphed = None
+        self.packs, self.repack_graph = [], None
         if graph_sample is not None:
             model.train()
+            if getattr(model, "train_backend", None) == "b200":
+                # operand copies of the weights live in persistent buffers refreshed by one small graph per step, so that the
+                # graphs of the passes contain no packing kernels
+                from . import train as _train
+                _train.enable(model)
+                model._tc_train = "b200"
+                self.packs = _train.attach_weight_packs(model)
+                for pk in self.packs:
+                    pk.refresh()
+                torch.cuda.synchronize(self.device)
+                self.repack_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.repack_graph):
+                    for pk in self.packs:
+                        pk.refresh()
             bn_state = {k: v.clone() for k, v in model.state_dict().items() if "running_" in k or "num_batches" in k}
             passes = (_FlatOutputs(model), _FlatOutputs(model))
             x = graph_sample.detach().clone()
@@ -171,6 +186,8 @@ class TrainStep:
         """sample: dict as produced by the reference's data loader (src/train.py:196-205) with tensors on the model's device."""
         self.model.train()
         self.reducer.zero()
+        if self.repack_graph is not None:
+            self.repack_graph.replay()          # bf16 operand copies of the weights the optimizer just updated
         loss, _ = self.losses(sample)
         loss.backward()
         self.reducer.finish()
