@@ -68,10 +68,12 @@ class ComputeObjectLoss:
         self.gr, self.hyp = 1.0, config
         self.na, self.nc, self.nl, self.anchors, self.device = m.na, m.nc, m.nl, m.anchors, device
 
-    def __call__(self, p, targets):
+    def __call__(self, p, targets, built=None):
+        """``built`` = a precomputed ``build_targets(p, targets)`` (it only needs the shapes of ``p``, so a training step can run it
+        -- and its host synchronisations -- before the forward pass is launched)."""
         dev = self.device
         lcls, lbox, lobj = (torch.zeros(1, device=dev) for _ in range(3))
-        tcls, tbox, indices, anchors = self.build_targets(p, targets)
+        tcls, tbox, indices, anchors = built if built is not None else self.build_targets(p, targets)
         for i, pi in enumerate(p):
             b, a, gj, gi = indices[i]
             tobj = torch.zeros(pi.shape[:4], dtype=pi.dtype, device=dev)
@@ -182,32 +184,48 @@ def _warp_mask_nearest(mask, inv_h):
     return F.grid_sample(mask, grid, mode="nearest", align_corners=True, padding_mode="zeros")
 
 
+@torch.no_grad()
+def descriptor_pairs(mask_valid_warp, inv_homographies, B, Hc, Wc, num_samples_per_image=1500, num_masked_non_matches_per_match=120, cell_size=8,
+                     device="cpu"):
+    """The sampling half of descriptor_loss_sparse (loss_functions.py:374-427, 451-466): positive pairs (grid_sample coordinates in the
+    frame and in the warped frame) and the indices of the random negatives.  It depends on the masks / homographies only -- not on
+    the network outputs -- so a training step can run it (it synchronises with the host to size the sample pool) before the forward
+    passes are launched."""
+    ys, xs = torch.meshgrid(torch.arange(Hc, device=device), torch.arange(Wc, device=device), indexing="ij")
+    uv_a = torch.stack((xs.reshape(-1), ys.reshape(-1)), 1).float()
+    inv_h = inv_homographies.to(device).float()
+    valid = getMasks(_warp_mask_nearest(mask_valid_warp.to(device).float(), inv_h), device, cell_size)
+    valid = (valid == 1.0).flatten(1, -1)
+    trans = torch.tensor([[2.0 / Wc, 0.0, -1.0], [0.0, 2.0 / Hc, -1.0], [0.0, 0.0, 1.0]], dtype=torch.float32, device=device)
+    uv_b = _warp_points(uv_a, trans.inverse() @ inv_h @ trans).round_()
+    pool = min(num_samples_per_image, int(valid.sum(1).min()))
+    pa, pb = [], []
+    for b in range(B):
+        idx = valid[b].nonzero().squeeze(1)
+        idx = idx[torch.randperm(idx.shape[0], device=device)[:pool]]
+        pa.append(uv_a[idx])
+        pb.append(uv_b[b][idx])
+    scale = torch.tensor([Wc, Hc], dtype=torch.float32, device=device)
+    pa = torch.stack(pa) / scale * 2 - 1
+    pb = torch.stack(pb) / scale * 2 - 1
+    n, K = B * pool, num_masked_non_matches_per_match
+    rnd = torch.randint(0, n, (K, n), device=device)
+    same = rnd == torch.arange(n, device=device).unsqueeze(0)
+    rnd = torch.where(same, (rnd + 1 + torch.randint(0, max(n - 1, 1), (K, n), device=device)) % n, rnd)   # never the match itself
+    return pa, pb, rnd
+
+
 def descriptor_loss_sparse(descriptors, descriptors_warped, mask_valid_warp, inv_homographies, num_samples_per_image=1500,
-                           num_masked_non_matches_per_match=120, cell_size=8, device="cpu"):
+                           num_masked_non_matches_per_match=120, cell_size=8, device="cpu", pairs=None):
     """loss_functions.py:361-481.  Positive pairs: every valid cell centre of the frame and its (rounded) position in the warped
     frame, a random subset of equal size per image; loss = mean hinge (1 - <a,b>) over the pairs + mean over the violating ones
-    of the hinge (<a, b'> - 0.1) against random other warped samples."""
+    of the hinge (<a, b'> - 0.1) against random other warped samples.  ``pairs`` = a precomputed ``descriptor_pairs(...)`` result."""
     device = descriptors.device
     B, _, Hc, Wc = descriptors.shape
     assert Hc * Wc >= num_samples_per_image, "Number of samples per image must be greater than number of pixels in image"
-    with torch.no_grad():
-        ys, xs = torch.meshgrid(torch.arange(Hc, device=device), torch.arange(Wc, device=device), indexing="ij")
-        uv_a = torch.stack((xs.reshape(-1), ys.reshape(-1)), 1).float()
-        inv_h = inv_homographies.to(device).float()
-        valid = getMasks(_warp_mask_nearest(mask_valid_warp.to(device).float(), inv_h), device, cell_size)
-        valid = (valid == 1.0).flatten(1, -1)
-        trans = torch.tensor([[2.0 / Wc, 0.0, -1.0], [0.0, 2.0 / Hc, -1.0], [0.0, 0.0, 1.0]], dtype=torch.float32, device=device)
-        uv_b = _warp_points(uv_a, trans.inverse() @ inv_h @ trans).round_()
-        pool = min(num_samples_per_image, int(valid.sum(1).min()))
-        pa, pb = [], []
-        for b in range(B):
-            idx = valid[b].nonzero().squeeze(1)
-            idx = idx[torch.randperm(idx.shape[0], device=device)[:pool]]
-            pa.append(uv_a[idx])
-            pb.append(uv_b[b][idx])
-        scale = torch.tensor([Wc, Hc], dtype=torch.float32, device=device)
-        pa = torch.stack(pa) / scale * 2 - 1
-        pb = torch.stack(pb) / scale * 2 - 1
+    if pairs is None:
+        pairs = descriptor_pairs(mask_valid_warp, inv_homographies, B, Hc, Wc, num_samples_per_image, num_masked_non_matches_per_match, cell_size, device)
+    pa, pb, rnd = pairs
 
     def sample(desc, pts):
         return F.grid_sample(desc, pts.unsqueeze(1), mode="bilinear", align_corners=True).squeeze(2).transpose(1, 2)
@@ -217,11 +235,6 @@ def descriptor_loss_sparse(descriptors, descriptors_warped, mask_valid_warp, inv
     pos = (da * db).sum(-1).flatten()
     da, db = da.flatten(0, 1), db.flatten(0, 1)
     n = da.shape[0]
-    K = num_masked_non_matches_per_match
-    with torch.no_grad():
-        rnd = torch.randint(0, n, (K, n), device=device)
-        same = rnd == torch.arange(n, device=device).unsqueeze(0)
-        rnd = torch.where(same, (rnd + 1 + torch.randint(0, max(n - 1, 1), (K, n), device=device)) % n, rnd)   # never the match itself
     if da.is_cuda and n <= 40000:
         # The reference materialises db[rnd] as a [K, n, D] tensor (4.9 GB for 8 x 3000 samples, K = 200, D = 256) and multiplies it
         # by the broadcast queries (loss_functions.py:468-471).  The same K x n similarities are entries of the n x n matrix

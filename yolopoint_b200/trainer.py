@@ -173,12 +173,21 @@ class TrainStep:
 
     def losses(self, sample):
         m, dev = self.model, self.device
+        # Everything that depends on the labels only and synchronises with the host (target assignment, sample-pool sizes) runs
+        # first, so that the forward passes and the loss arithmetic can be enqueued back to back without the host waiting on them.
+        B, _, H, W = sample["image"].shape
+        det = getattr(m, "module", m).model.Detect
+        shapes = [torch.empty((B, det.na, H // int(s), W // int(s), det.no), device="meta") for s in (8, 16, 32)]
+        built = self.obj_loss.build_targets(shapes, sample["box_labels"])
+        pairs = Lz.descriptor_pairs(sample["warped_valid_mask"], sample["inv_homographies"], B, H // 8, W // 8, device=dev, **self.sparse_cfg)
+        lab, lab_w = Lz.labels2Dto3D(sample["labels_2D"]), Lz.labels2Dto3D(sample["warped_labels"])
+        msk, msk_w = Lz.getMasks(sample["valid_mask"], dev), Lz.getMasks(sample["warped_valid_mask"], dev)
         semi, desc, obj = self._forward(sample["image"], 0)
-        loss_obj, items = self.obj_loss(obj, sample["box_labels"])
-        loss_det = self.det_loss(semi, Lz.labels2Dto3D(sample["labels_2D"]), Lz.getMasks(sample["valid_mask"], dev))
         semi_w, desc_w, _ = self._forward(sample["warped_image"], 1)
-        loss_det_w = self.det_loss(semi_w, Lz.labels2Dto3D(sample["warped_labels"]), Lz.getMasks(sample["warped_valid_mask"], dev))
-        loss_desc = Lz.descriptor_loss_sparse(desc, desc_w, sample["warped_valid_mask"], sample["inv_homographies"], **self.sparse_cfg)
+        loss_obj, items = self.obj_loss(obj, sample["box_labels"], built)
+        loss_det = self.det_loss(semi, lab, msk)
+        loss_det_w = self.det_loss(semi_w, lab_w, msk_w)
+        loss_desc = Lz.descriptor_loss_sparse(desc, desc_w, sample["warped_valid_mask"], sample["inv_homographies"], pairs=pairs, **self.sparse_cfg)
         loss = loss_det + loss_det_w + LAMBDA_DESC * loss_desc + LAMBDA_OBJ * loss_obj
         return loss, dict(det=loss_det.detach(), det_warp=loss_det_w.detach(), desc=loss_desc.detach(), obj=loss_obj.detach())
 
