@@ -75,6 +75,22 @@ def test_forward_bf16_mode_is_close():
     assert e < 5e-2
 
 
+def test_forward_bf16_multiwave_layers_close():
+    """bf16 mode at a size where most layers have several waves of tiles, i.e. run on the persistent kernel (double-buffered TMEM
+    accumulators) with residuals, concat slices and 2x-upsampled destinations: same error bound as the small bf16 case, and the
+    non-persistent kernel (YP_CONV_PERSIST=0 is read once per process, so compare against the fp32 engine instead) agrees."""
+    m, sd = build("s", "bf16")
+    x = torch.from_numpy(np.random.RandomState(7).rand(4, 3, 384, 640).astype(np.float32))
+    out = m(x.cuda())
+    m32, _ = build("s")
+    ref = m32(x.cuda())
+    e_desc = float((out["desc"] - ref["desc"]).abs().max())
+    e_semi = float((out["semi"] - ref["semi"]).abs().max()) / float(ref["semi"].abs().max())
+    e_raw = max(float((a - b).abs().max()) / float(b.abs().max()) for a, b in zip(out["objects"][1], ref["objects"][1]))
+    print("bf16 multi-wave vs fp32 engine: desc", e_desc, "semi rel", e_semi, "raw rel", e_raw)
+    assert e_desc < 5e-2 and e_semi < 5e-2 and e_raw < 5e-2
+
+
 def test_pipeline_stages_bit_exact_on_same_inputs():
     """Feed the GPU's own network outputs to both the kernels and the oracle post-processing: indices bit-exact."""
     m, sd = build("s")
