@@ -67,7 +67,7 @@ _PACK_CACHE: dict = {}
 
 
 def _cached(kind: str, w: torch.Tensor, make):
-    if torch.cuda.is_current_stream_capturing() or not (w.is_leaf and isinstance(w, nn.Parameter)):
+    if not w.is_cuda or torch.cuda.is_current_stream_capturing() or not (w.is_leaf and isinstance(w, nn.Parameter)):
         # inside a CUDA graph the packing kernels must be part of the graph; temporaries (zero-padded / rearranged weights) get a
         # new allocation every call, whose address may later be reused by a different tensor -- never cache those
         return make()
