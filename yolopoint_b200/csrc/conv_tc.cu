@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     const bool two = a.n_jobs[q] == 2;
     const uint32_t dhi = smem_desc_hi(a.ck_bytes);
     const bool live = a.ablate != 1;
+    const bool fast4 = live && ksteps == 4 && kinc == 1 && !two && a.ablate != 8;   // YP_CONV_ABLATE=8: generic loop (A/B runs)
     uint32_t used = 0;                   // bit r set = accumulator r of this issuer already holds a partial sum
     int s = 0, ph = 0, nxt = 0;
     if (a.patch) {
@@ -262,6 +263,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
           const uint32_t sb = smem_base + a.b_ring_off + s * a.b_stage_bytes;
           uint32_t al0 = smem_desc_lo(pa + a_off0 + shift) + 2 * kstart, bl0 = smem_desc_lo(sb + b_off0) + 2 * kstart;
           uint32_t al1 = smem_desc_lo(pa + a_off1 + shift) + 2 * kstart, bl1 = smem_desc_lo(sb + b_off1) + 2 * kstart;
+          if (fast4) {
+            // common case (128-byte rows, one MMA per k-step, every k-step by this issuer): four MMAs fully unrolled so that the
+            // operand set-up of MMA k+1 overlaps the issue of MMA k
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma32<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
+              used |= 1u << nxt;
+              nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+            }
+          } else
           for (int k = kstart; k < ksteps && live; k += kinc) {
             umma32<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
             if (two) umma32<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
@@ -286,6 +297,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         const uint32_t sb = sa + a.a_region_bytes;
         uint32_t al0 = smem_desc_lo(sa + a_off0) + 2 * kstart, bl0 = smem_desc_lo(sb + b_off0) + 2 * kstart;
         uint32_t al1 = smem_desc_lo(sa + a_off1) + 2 * kstart, bl1 = smem_desc_lo(sb + b_off1) + 2 * kstart;
+        if (fast4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma32<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
+            used |= 1u << nxt;
+            nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+          }
+        } else
         for (int k = kstart; k < ksteps && live; k += kinc) {
           umma32<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
           if (two) umma32<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
