@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import sys
 
+os.environ.setdefault("YP_CONV_PERSIST", "0")   # the recorder lives in the one-tile-per-CTA kernel; the persistent variant is timed by tools/train_conv_times.py
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -43,6 +45,9 @@ def main():
             t = buf.cpu().numpy()
             rec = t[512:].reshape(-1, 3)
             rec = rec[rec[:, 1] > 0]
+            if len(rec) == 0:
+                print(f"\n== fmt={'bf16' if fmt == YP_FMT_BF16 else 'f32x2'} {c}: no per-CTA records (kernel without recorder)")
+                continue
             sm, st, en = rec[:, 0], rec[:, 1], rec[:, 2]
             t0 = st.min()
             life = (en - st) / 1e3
