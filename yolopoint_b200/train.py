@@ -19,6 +19,7 @@ that is not sm_100 the call raises.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional
 
 import torch
@@ -62,23 +63,24 @@ def pack_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 # Packed operand copies of the master weights (nn.Parameter leaves only), reused until the optimizer changes the parameter (tensor
-# version counter): a step uses every weight in two forward passes and two data-gradient passes.
+# version counter): a step uses every weight in two forward passes and two data-gradient passes.  An entry is only valid for the
+# very parameter object it was made from (weak reference): a freed parameter's address may be reused by another one.
 _PACK_CACHE: dict = {}
 
 
 def _cached(kind: str, w: torch.Tensor, make):
     if not w.is_cuda or torch.cuda.is_current_stream_capturing() or not (w.is_leaf and isinstance(w, nn.Parameter)):
         # inside a CUDA graph the packing kernels must be part of the graph; temporaries (zero-padded / rearranged weights) get a
-        # new allocation every call, whose address may later be reused by a different tensor -- never cache those
+        # new allocation every call -- never cache those
         return make()
-    key = (kind, w.data_ptr(), tuple(w.shape))
+    key = (kind, id(w))
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == w._version:
-        return hit[1]
+    if hit is not None and hit[0]() is w and hit[1] == w._version:
+        return hit[2]
     out = make()
     if len(_PACK_CACHE) > 4096:
         _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (w._version, out)
+    _PACK_CACHE[key] = (weakref.ref(w), w._version, out)
     return out
 
 
@@ -116,12 +118,23 @@ class WeightPack:
     step by ``refresh()`` -- outside the CUDA graphs of the forward / backward passes, which then contain no packing kernels (a
     step uses every weight in two forward and two data-gradient passes)."""
 
-    def __init__(self, make_weight, stride: int, need_dgrad: bool):
+    def __init__(self, make_weight, stride: int, need_dgrad: bool, src: Optional[torch.Tensor] = None):
         self.make_weight, self.stride, self.need_dgrad, self.bufs = make_weight, stride, need_dgrad, None
+        self.src, self.version = src, None      # the parameter the buffers were packed from and its version at that time
+
+    def usable(self) -> bool:
+        """True while the buffers hold the current weights.  Inside a captured graph the decision was taken at capture time (the
+        replayed refresh keeps the buffers current); an eager call after an optimizer step sees a newer parameter version and packs
+        on the fly instead of reading stale operands."""
+        if self.bufs is None:
+            return False
+        return self.src is None or torch.cuda.is_current_stream_capturing() or self.src._version == self.version
 
     @torch.no_grad()
     def refresh(self):
         w = self.make_weight()
+        if self.src is not None:
+            self.version = self.src._version
         new = {"fwd": pack_weight(w)}
         if self.need_dgrad:
             new.update(_dgrad_operands(w, self.stride))
@@ -136,7 +149,7 @@ def conv_forward(x: torch.Tensor, w: torch.Tensor, stride: int, pack: Optional[W
     B, Ci, H, W = x.shape
     Co, _, k, _ = w.shape
     y = torch.empty((B, Co, H // stride, W // stride), dtype=torch.bfloat16, device=x.device, memory_format=_CL)
-    wp = pack.bufs["fwd"] if pack is not None and pack.bufs is not None else _cached("fwd", w, lambda: pack_weight(w))
+    wp = pack.bufs["fwd"] if pack is not None and pack.usable() else _cached("fwd", w, lambda: pack_weight(w))
     _launch_conv(x, wp, y, k, stride)
     return y
 
@@ -148,7 +161,7 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, H: int, W: int, p
     dx = torch.empty((B, Ci, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=_CL)
     if stride == 1:
         # a forward conv over dy with the taps flipped and (co, ci) transposed
-        packed = pack.bufs if pack is not None and pack.bufs is not None and "dgrad" in pack.bufs else None
+        packed = pack.bufs if pack is not None and pack.usable() and "dgrad" in pack.bufs else None
         wt = packed["dgrad"] if packed else _cached("dgrad", w, lambda: _dgrad_operands(w, 1)["dgrad"])   # [Ci, taps*Co]
         _launch_conv(dy, wt, dx, k, 1)
         return dx
@@ -161,7 +174,7 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, stride: int, H: int, W: int, p
             dh = [(ph + 1 - kh) // 2 for kh, _ in taps]
             dw = [(pw + 1 - kw) // 2 for _, kw in taps]
             key = f"dgrad{ph}{pw}"
-            if pack is not None and pack.bufs is not None and key in pack.bufs:
+            if pack is not None and pack.usable() and key in pack.bufs:
                 wt = pack.bufs[key]
             else:
                 wt = _cached(key, w, lambda: torch.stack([w[:, :, kh, kw].t() for kh, kw in taps], 1).reshape(Ci, -1)
@@ -335,7 +348,7 @@ def attach_weight_packs(model: nn.Module):
             if not stem and not (p == k // 2 and supported(mod.weight, s)):
                 continue
             make = (lambda m=mod: _pad_weight(_stem_weight(m.weight.detach()))) if stem else (lambda m=mod: _pad_weight(m.weight.detach()))
-            mod._yp_pack = WeightPack(make, 1 if stem else s, need_dgrad=not (stem or first))
+            mod._yp_pack = WeightPack(make, 1 if stem else s, need_dgrad=not (stem or first), src=mod.weight)
             packs.append(mod._yp_pack)
             first = False
     return packs
