@@ -10,9 +10,11 @@
 // Numerics: YP_FMT_F32X2 operands are (hi, lo) TF32 pairs; the kernel issues A_lo*W_hi + A_hi*W_lo +
 // A_hi*W_hi into one fp32 TMEM accumulator ("3xTF32", ~fp32 accuracy); YP_FMT_BF16 issues one bf16 MMA.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
-// epilogue (TMEM -> registers -> bias/SiLU/residual/L2-norm -> swizzled smem -> TMA store to 1..8 maps:
-// channel-slice (concat) destinations and the four parity views of a 2x-upsampled destination).
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warp 2 = second MMA issuer; when their
+// loops are done all eight warps run the epilogue (TMEM -> registers -> bias/SiLU/residual/L2-norm -> swizzled smem -> TMA store
+// to 1..8 maps: channel-slice (concat) destinations and the four parity views of a 2x-upsampled destination), two warps per
+// TMEM lane quarter.  conv_tc_persist_kernel (bf16 layers with several waves of tiles) keeps producer / issuers / epilogue warps
+// separate and loops over tiles with double-buffered TMEM accumulators.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
