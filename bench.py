@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the YOLOPoint hot path on B200 (contract: see the task statement / DESIGN.md section "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload s640|n480|m1280|l640train] [--precision fp32|bf16]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload s640|n480|m1280|l640train|s640v52] [--precision fp32|bf16]
 
 A "step" is one pass of the whole per-frame hot path (uint8 frame -> network -> Detect decode -> box NMS -> heatmap ->
 keypoint NMS -> descriptor sampling -> two-way match with the previous frame) over one batch of synthetic frames.
@@ -33,10 +33,13 @@ WORKLOADS = {
     "n480": ("n", 480, 640, 1),     # configs[0] geometry (the reference's CPU case) on the GPU
     "m1280": ("m", 736, 1280, 4),   # configs[2]: 32 frames over 8 GPUs = 4 per GPU
     "l640train": ("l", 640, 640, 8),  # configs[4]: YOLOPoint-L bf16 training step, 64 samples over 8 GPUs = 8 per GPU
+    "s640v52": ("s", 640, 640, 1),  # YOLOPointv52-S (the model configs/kitti_inference.yaml names), configs[1] geometry
 }
+MODEL_NAME = {"s640v52": "YOLOPointv52"}   # every other workload runs the YOLOPoint (v5-style) network
 CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 7.27e6}   # profiles/r01_conv_tc_ncu_full.md: mean of the three YOLOPoint-S layer geometries captured
 NAMES = [str(i) for i in range(80)]
-CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398, "l640train": 135.526}   # SURVEY.md section 8a, per frame (forward)
+# SURVEY.md section 8a, per frame (forward); s640v52: conv-module hook count on the reference YOLOPointv52-S
+CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398, "l640train": 135.526, "s640v52": 21.363}
 
 
 def load_peaks():
@@ -47,11 +50,11 @@ def load_peaks():
     return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
 
 
-def build_weights(version):
+def build_weights(version, model_name="YOLOPoint"):
     from yolopoint_b200 import Model
     from yolopoint_b200.synth import perturb_state_dict
     torch.manual_seed(0)
-    m = Model(names=NAMES, version=version)
+    m = Model(names=NAMES, version=version, model_name=model_name)
     sd = perturb_state_dict(m.state_dict(), 0, version)
     m.load_state_dict(sd)
     return m, sd
@@ -98,14 +101,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_fps(version, H, W, steps, warmup, sd=None):
+def cpu_reference_fps(version, H, W, steps, warmup, sd=None, model_name="YOLOPoint"):
     """The reference's CPU path (oracle port: same torch-CPU convs / numpy post-processing) on all host threads."""
     from oracle import yolopoint_oracle as O
     from yolopoint_b200.synth import synthetic_frame
     if sd is None:
-        _, sd = build_weights(version)
+        _, sd = build_weights(version, model_name)
     torch.set_num_threads(os.cpu_count() or 1)
-    net = O.OracleNet(sd, version, 80)
+    net = O.OracleNet(sd, version, 80, model_name)
     frames = [synthetic_frame(H, W, s) for s in range(2)]
     prev = None
     times = []
@@ -219,13 +222,14 @@ def main():
     ap.add_argument("--train-graphs", type=int, default=1, help="l640train only: 1 = forward/backward passes replayed from CUDA graphs, 0 = eager launches")
     args = ap.parse_args()
     version, H, W, per_gpu = WORKLOADS[args.workload]
+    model_name = MODEL_NAME.get(args.workload, "YOLOPoint")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "l640train" and args.impl != "reference":
         return train_main(args, version, H, W, args.train_batch or per_gpu, world, rank, local_rank)
     K, Wm = args.steps, max(args.warmup, 3)
-    config = {"workload": f"YOLOPoint-{version.upper()} {W}x{H} batch={per_gpu}/GPU full per-frame pipeline (net+decode+boxNMS+heatmap+kpNMS+desc+match)",
+    config = {"workload": f"{model_name}-{version.upper()} {W}x{H} batch={per_gpu}/GPU full per-frame pipeline (net+decode+boxNMS+heatmap+kpNMS+desc+match)",
               "frames_per_gpu_per_step": per_gpu, "precision": args.precision, "parallelism": f"frames sharded over {world} GPU(s), no collective"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -233,7 +237,7 @@ def main():
         if rank != 0:
             return 0
         steps = min(K, 30)
-        fps, cores, med = cpu_reference_fps(version, H, W, steps, min(Wm, 3))
+        fps, cores, med = cpu_reference_fps(version, H, W, steps, min(Wm, 3), model_name=model_name)
         line = {"impl": "reference", "metric": "frames/sec end-to-end (backbone+heads+NMS+match)", "value": fps, "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": min(Wm, 3), "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -252,7 +256,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    model, sd = build_weights(version)
+    model, sd = build_weights(version, model_name)
     model.precision = args.precision
     model = model.to(dev).eval()
     NS = max(1, args.streams)
@@ -413,7 +417,7 @@ def main():
             "detail": {"net_only_ms": net_ms, "keypoints": kp_n, "boxes": box_n, "matches": match_n, "concurrent_camera_streams": multi}}
     if not args.no_cpu_baseline and world == 1:
         n = max(3, min(30, int(args.cpu_seconds / 0.3)))
-        cfps, cores, med = cpu_reference_fps(version, H, W, n, 2, sd)
+        cfps, cores, med = cpu_reference_fps(version, H, W, n, 2, sd, model_name)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} frames of the same workload (batch 1), median {med * 1e3:.1f} ms/frame"}
     print(json.dumps(line))

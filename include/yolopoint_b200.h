@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YP_ABI_VERSION 3
+#define YP_ABI_VERSION 4
 
 typedef enum {
   YP_OK = 0,
@@ -168,6 +168,11 @@ int yp_debug_conv_timeline(void* device_buf_i64);
 /* SPPF pooling: from slice 0 (C channels) of the [B,H,W,4C] concat buffer compute the 5x5, 9x9 and 13x13
  * stride-1 max pools (== three chained MaxPool2d(5,1,2), models/common.py:220-229) into slices 1..3. */
 int yp_sppf_pool(const YpView* cat4, void* stream);
+
+/* MaxPool2d(kernel 2, stride 2) from view `in` [B,H,W,C] to view `out` [B,H/2,W/2,C] of the same format (C % 8 == 0): the
+ * `descA = MaxPool(xa)` branch of the YOLOPointv52 descriptor head (models/YOLOPoint.py:287, 311).  `out` may be a channel slice of
+ * a concat buffer.  The operand planes of the winning element are copied unchanged. */
+int yp_maxpool2x2(const YpView* in, const YpView* out, void* stream);
 
 /* Input conversion.  Both produce the 2x2 space-to-depth NHWC operand of the stem conv:
  * out[b, h2, w2, (ph*2+pw)*3 + c] = x[b, c, 2*h2+ph, 2*w2+pw], channels 12..15 zero.

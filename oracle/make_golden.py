@@ -84,6 +84,8 @@ def main():
         save(f"e2e_{ver}_{H}x{W}.npz", pts0=res[0][0], desc0=res[0][1].astype(np.float32), boxes0=res[0][2],
              pts1=res[1][0], desc1=res[1][1].astype(np.float32), boxes1=res[1][2], matches=matches)
 
+    golden_v52(ns)
+
     # ---- 4. box NMS (src/utils/general_yolo.py:124-235) ---------------------------------------
     rs = np.random.RandomState(11)
     pred = clustered_pred(rs, 2, 600, 7)
@@ -157,6 +159,40 @@ def main():
          m03=ns.PointTracker.nn_match_two_way(d1, d2, 0.3))
 
 
+def golden_v52(ns=None):
+    """YOLOPointv52 (src/models/YOLOPoint.py:248-342): seeded state dict, network forward and the
+    whole-frame pipeline, all produced by the reference's own Model(model_name='YOLOPointv52') / YoloPointFrontend.process_img."""
+    ns = ns or ref_import.load()
+    name = "YOLOPointv52"
+    for ver in ("n", "s"):
+        torch.manual_seed(0)
+        m = ns.Model(names=NAMES80, version=ver, model_name=name)
+        sd = m.state_dict()
+        save(f"state_v52{ver}.npz", keys=np.array(list(sd.keys())), sums=np.array([float(v.double().sum()) for v in sd.values()]),
+             asums=np.array([float(v.double().abs().sum()) for v in sd.values()]), shapes=np.array([str(tuple(v.shape)) for v in sd.values()]),
+             param_names=np.array([n for n, _ in m.named_parameters()]), stride=m.model.Detect.stride.numpy(), anchors=m.model.Detect.anchors.numpy())
+    torch.manual_seed(0)
+    m = ns.Model(names=NAMES80, version="n", model_name=name)
+    m.load_state_dict(perturb_state_dict(m.state_dict(), 0, "n")); m.eval().fuse()
+    x = torch.from_numpy(np.random.RandomState(7).rand(2, 3, 64, 96).astype(np.float32))
+    with torch.no_grad():
+        o = m(x)
+    save("net_v52n_64x96.npz", x=x.numpy(), semi=o["semi"].numpy(), desc=o["desc"].numpy(), pred=o["objects"][0].numpy(),
+         raw0=o["objects"][1][0].numpy(), raw1=o["objects"][1][1].numpy(), raw2=o["objects"][1][2].numpy())
+    ver, (H, W) = "s", (640, 640)
+    torch.manual_seed(0)
+    m = ns.Model(names=NAMES80, version=ver, model_name=name)
+    m.load_state_dict(perturb_state_dict(m.state_dict(), 0, ver)); m.eval().fuse()
+    fe = ref_import.make_frontend(ns, m, O.DEFAULT_CFG)
+    res = []
+    for seed in (0, 1):
+        pts, desc, obj = fe.process_img(synthetic_frame(H, W, seed))
+        res.append((pts, desc, obj[0].numpy()))
+    matches = ns.PointTracker.nn_match_two_way(res[0][1], res[1][1], O.DEFAULT_CFG["nn_thresh"])
+    save(f"e2e_v52{ver}_{H}x{W}.npz", pts0=res[0][0], desc0=res[0][1].astype(np.float32), boxes0=res[0][2],
+         pts1=res[1][0], desc1=res[1][1].astype(np.float32), boxes1=res[1][2], matches=matches)
+
+
 def golden_losses():
     """Training losses (SURVEY.md section 8 row a11 consumers): the reference's own ComputeObjectLoss / ComputeDetectorLoss /
     descriptor_loss_sparse (src/utils/loss_functions.py:90-234, 600-619, 361-481) on seeded synthetic network outputs."""
@@ -198,6 +234,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "losses":
         os.makedirs(OUT, exist_ok=True)
         golden_losses()
+    elif len(sys.argv) > 1 and sys.argv[1] == "v52":
+        os.makedirs(OUT, exist_ok=True)
+        golden_v52()
     else:
         main()
         golden_losses()

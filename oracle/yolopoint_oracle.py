@@ -73,8 +73,9 @@ class OracleNet:
     ``sd`` is a reference-format state dict (keys ``model.Conv1.conv.weight`` ...).
     """
 
-    def __init__(self, sd: Dict[str, torch.Tensor], version: str, nc: int):
-        self.version, self.nc, self.no = version, nc, nc + 5
+    def __init__(self, sd: Dict[str, torch.Tensor], version: str, nc: int, model_name: str = "YOLOPoint"):
+        assert model_name in ("YOLOPoint", "YOLOPointv52"), model_name
+        self.version, self.nc, self.no, self.model_name = version, nc, nc + 5, model_name
         sd = {(k[len("model."):] if k.startswith("model.") else k): v.detach().cpu() for k, v in sd.items()}
         self.sd = sd
         (self.c1, self.c2, self.c3, self.c4, self.c5), (self.n1, self.n2, self.n3) = dims(version)
@@ -110,9 +111,58 @@ class OracleNet:
         y3 = F.max_pool2d(y2, 5, 1, 2)
         return self._conv(name + ".cv2", torch.cat((x, y1, y2, y3), 1), 1, 1)
 
+    def _c2f(self, name: str, x: torch.Tensor, n: int) -> torch.Tensor:
+        """models/common.py:151-165 with Bottleneckv8 (:91-103): two 3x3 convs, e=1.0, shortcut=False (C2f's default)."""
+        y = list(self._conv(name + ".cv1", x, 1, 1).chunk(2, 1))
+        for i in range(n):
+            y.append(self._conv(f"{name}.m.{i}.cv2", self._conv(f"{name}.m.{i}.cv1", y[-1], 3, 1), 3, 1))
+        return self._conv(name + ".cv2", torch.cat(y, 1), 1, 1)
+
+    def _detect(self, feats: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        """Detect.forward, eval branch (src/models/yolo.py:49-81)."""
+        raw = []
+        for i, t in enumerate(feats):
+            t = F.conv2d(t, self.sd[f"Detect.m.{i}.weight"].float(), self.sd[f"Detect.m.{i}.bias"].float())
+            bs, _, ny, nx = t.shape
+            raw.append(t.view(bs, 3, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous())
+        return detect_decode(raw, self.anchors, self.stride), raw
+
+    @torch.no_grad()
+    def forward_v52(self, x: torch.Tensor, keep: Optional[dict] = None) -> Dict[str, object]:
+        """YOLOPointv52.forward (src/models/YOLOPoint.py:295-342)."""
+        up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
+        x = self._conv("Conv1", x.float(), 6, 2, 2)
+        x = self._conv("Conv2", x, 3, 2)
+        xa = self._c2f("Bottleneck1", x, self.n1)
+        x = self._conv("Conv3", xa, 3, 2)
+        semi = self._c2f("BottleneckDet", x, self.n1)
+        xb = self._c2f("Bottleneck2", x, self.n2)
+        descA = F.max_pool2d(xa, 2, 2)
+        descB = up(self._conv("ConvDescB", xb, 3, 2, 1))
+        desc = self._c2f("BottleneckDesc", torch.cat((descA, descB), 1), self.n1)
+        dn = torch.norm(desc, p=2, dim=1)
+        desc = desc.div(torch.unsqueeze(dn, 1))
+        x = self._conv("Conv4", xb, 3, 2)
+        xc = self._c2f("Bottleneck3", x, self.n3)
+        x = self._conv("Conv5", xc, 3, 2)
+        x = self._c2f("Bottleneck4", x, self.n1)
+        xd = self._sppf("SPPooling", x)
+        xe = self._c2f("Bottleneck5", torch.cat((up(xd), xc), 1), self.n1)
+        xf = self._c2f("Bottleneck6", torch.cat((up(xe), xb), 1), self.n1)
+        x = self._conv("Conv8", xf, 3, 2, 1)
+        xg = self._c2f("Bottleneck7", torch.cat((x, xe), 1), self.n1)
+        x = self._conv("Conv9", xg, 3, 2, 1)
+        xh = self._c2f("Bottleneck8", torch.cat((x, xd), 1), self.n1)
+        if keep is not None:
+            keep.update(xa=xa, xb=xb, xc=xc, xd=xd, xe=xe, xf=xf, xg=xg, xh=xh)
+        pred, raw = self._detect((xf, xg, xh))
+        return {"semi": semi, "desc": desc, "objects": (pred, raw)}
+
     # -- network ---------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x: torch.Tensor, keep: Optional[dict] = None) -> Dict[str, object]:
+        if self.model_name == "YOLOPointv52":
+            return self.forward_v52(x, keep)
         sd = self.sd
         up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
         x = self._conv("Conv1", x.float(), 6, 2, 2)

@@ -1,14 +1,14 @@
 """CPU interpreter of the engine's launch plan (TEST INFRASTRUCTURE).
 
 Executes yolopoint_b200.engine.NetPlan op by op with torch-CPU arithmetic, following the *contract* of the C ABI
-(include/yolopoint_b200.h: channel-slice views, 2x-replicated stores, in-place residual, merged cv1||cv2, packed
+(include/yolopoint_b200.h: channel-slice views, 2x-replicated stores, in-place residual, merged cv1||cv2, 2x2 max-pool into a concat slice, packed
 weights incl. the space-to-depth stem, L2-norm epilogue, SPPF in the concat buffer).  It lets the CPU-only test
 suite prove that the plan + weight packing reproduce the oracle network before any kernel runs on a GPU.
 """
 import torch
 import torch.nn.functional as F
 
-from yolopoint_b200.engine import ConvOp, NetPlan, PoolOp, pack_conv
+from yolopoint_b200.engine import ConvOp, NetPlan, Pool2Op, PoolOp, pack_conv
 
 
 def run_plan(net: NetPlan, sd, x: torch.Tensor, quantize=None):
@@ -26,6 +26,10 @@ def run_plan(net: NetPlan, sd, x: torch.Tensor, quantize=None):
             for k in range(3):
                 y = F.max_pool2d(y, 5, 1, 2)
                 t[..., (k + 1) * c:(k + 2) * c] = y.permute(0, 2, 3, 1)
+            continue
+        if isinstance(op, Pool2Op):      # yp_maxpool2x2
+            y = F.max_pool2d(bufs[op.src.buf][..., op.src.c_off:op.src.c_off + op.src.C].permute(0, 3, 1, 2), 2, 2)
+            bufs[op.dst.buf][..., op.dst.c_off:op.dst.c_off + op.dst.C] = y.permute(0, 2, 3, 1)
             continue
         src = bufs[op.src.buf][..., op.src.c_off:op.src.c_off + op.src.C]
         w, b = pack_conv(sd, op, op.src.C, net.precision)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "yp_bn_act_bwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "yp_debug_conv_timeline": (_i32, [_vp]),
     "yp_sppf_pool": (_i32, [_PV, _vp]),
+    "yp_maxpool2x2": (_i32, [_PV, _PV, _vp]),
     "yp_nchw_to_s2d": (_i32, [_vp, _i32, _i32, _i32, _PV, _vp]),
     "yp_frame_to_s2d": (_i32, [_vp, _i32, _i32, _i32, _PV, _vp]),
     "yp_nhwc_to_nchw": (_i32, [_PV, _i32, _vp, _vp]),
@@ -104,7 +105,7 @@ def lib(require_device: bool = False):
                     except AttributeError as e:  # pragma: no cover
                         raise YoloPointB200Error(f"{LIB_PATH} does not export {name}") from e
                     fn.restype, fn.argtypes = res, args
-                if handle.yp_abi_version() != 3:
+                if handle.yp_abi_version() != 4:
                     raise YoloPointB200Error("ABI version mismatch between _lib.py and libyolopoint_b200.so")
                 _lib = handle
     if require_device:

@@ -1,5 +1,7 @@
 // Layout / pooling kernels: input conversion to the stem's space-to-depth NHWC operand, NHWC -> NCHW
 // export of network outputs, and the single-pass SPPF pooling.  All are HBM/L2-bound element movers.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace yp {
@@ -152,6 +154,67 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(YpView cat4, int C) {
   }
 }
 
+// MaxPool2d(kernel 2, stride 2) between two NHWC views of one format (YOLOPointv52 descriptor head, src/models/YOLOPoint.py:287, 311).
+// One thread owns 8 consecutive channels of one output pixel: 16-byte loads of the four window pixels (per operand plane), the
+// winner of each channel is chosen on its value (hi + lo for YP_FMT_F32X2) and its operand planes are copied unchanged, so the
+// stored elements are bit-identical to the source's.  Ties keep the first pixel in window raster order.
+template <int kFmt>
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(YpView in, YpView out, int groups) {
+  const int Ho = out.H, Wo = out.W;
+  const int64_t total = static_cast<int64_t>(out.B) * Ho * Wo * groups;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    const int64_t op = idx / groups;
+    const int wo = static_cast<int>(op % Wo);
+    const int ho = static_cast<int>((op / Wo) % Ho);
+    const int b = static_cast<int>(op / (static_cast<int64_t>(Wo) * Ho));
+    const int64_t dst = op * out.pix_stride + g * 8;
+    int64_t srcp[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      srcp[q] = ((static_cast<int64_t>(b) * in.H + 2 * ho + (q >> 1)) * in.W + 2 * wo + (q & 1)) * in.pix_stride + g * 8;
+    if (kFmt == YP_FMT_BF16) {
+      const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(in.base);
+      uint4 best = *reinterpret_cast<const uint4*>(f + srcp[0]);
+      __nv_bfloat16* bb = reinterpret_cast<__nv_bfloat16*>(&best);
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4*>(f + srcp[q]);
+        const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (__bfloat162float(vv[i]) > __bfloat162float(bb[i])) bb[i] = vv[i];
+      }
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out.base) + dst) = best;
+    } else {
+      const float* f = static_cast<const float*>(in.base);
+      const bool two = kFmt == YP_FMT_F32X2;
+      float hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(f + srcp[q] + 4 * i);
+          h[4 * i] = a.x; h[4 * i + 1] = a.y; h[4 * i + 2] = a.z; h[4 * i + 3] = a.w;
+          float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (two) c = *reinterpret_cast<const float4*>(f + in.plane_stride + srcp[q] + 4 * i);
+          l[4 * i] = c.x; l[4 * i + 1] = c.y; l[4 * i + 2] = c.z; l[4 * i + 3] = c.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (q == 0 || __fadd_rn(h[i], l[i]) > __fadd_rn(hi[i], lo[i])) { hi[i] = h[i]; lo[i] = l[i]; }
+      }
+      float* o = static_cast<float*>(out.base);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        *reinterpret_cast<float4*>(o + dst + 4 * i) = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+        if (two) *reinterpret_cast<float4*>(o + out.plane_stride + dst + 4 * i) = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace yp
 
@@ -187,6 +250,27 @@ extern "C" int yp_sppf_pool(const YpView* cat4, void* stream) {
     configured = 200 * 1024;
   }
   yp::sppf_pool_kernel<<<dim3(C / yp::SPPF_G, cat4->B), 256, smem, static_cast<cudaStream_t>(stream)>>>(*cat4, C);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+extern "C" int yp_maxpool2x2(const YpView* in, const YpView* out, void* stream) {
+  YP_REQUIRE(in && out && in->base && out->base, YP_ERR_ARG, "maxpool2x2: null view");
+  YP_REQUIRE(in->format == out->format && (in->format == YP_FMT_BF16 || in->format == YP_FMT_F32X2 || in->format == YP_FMT_F32), YP_ERR_SHAPE,
+             "maxpool2x2: formats %d -> %d unsupported", in->format, out->format);
+  YP_REQUIRE(in->H % 2 == 0 && in->W % 2 == 0 && out->B == in->B && out->H == in->H / 2 && out->W == in->W / 2 && out->C == in->C && in->C % 8 == 0 &&
+                 out->upsample <= 1, YP_ERR_SHAPE, "maxpool2x2: [%d,%d,%d,%d] -> [%d,%d,%d,%d] is not a 2x2 stride-2 pooling of 8-channel groups",
+             in->B, in->H, in->W, in->C, out->B, out->H, out->W, out->C);
+  const int es = yp::fmt_esize(in->format);
+  YP_REQUIRE(yp::aligned16(in->base) && yp::aligned16(out->base) && (in->pix_stride * es) % 16 == 0 && (out->pix_stride * es) % 16 == 0 &&
+                 (in->plane_stride * es) % 16 == 0 && (out->plane_stride * es) % 16 == 0, YP_ERR_ALIGN, "maxpool2x2: views not 16-byte aligned");
+  const int groups = in->C / 8;
+  const int64_t total = static_cast<int64_t>(out->B) * out->H * out->W * groups;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(yp::ceil_div64(total, 256), static_cast<int64_t>(yp::sm_count()) * 16));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in->format == YP_FMT_BF16) yp::maxpool2x2_kernel<YP_FMT_BF16><<<blocks, 256, 0, st>>>(*in, *out, groups);
+  else if (in->format == YP_FMT_F32X2) yp::maxpool2x2_kernel<YP_FMT_F32X2><<<blocks, 256, 0, st>>>(*in, *out, groups);
+  else yp::maxpool2x2_kernel<YP_FMT_F32><<<blocks, 256, 0, st>>>(*in, *out, groups);
   YP_LAUNCH_OK();
   return YP_OK;
 }

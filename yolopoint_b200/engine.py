@@ -29,6 +29,7 @@ from . import _lib
 from ._lib import YP_ACT_NONE, YP_ACT_SILU, YP_ALGO_TCGEN05, YP_EPI_L2NORM, YP_FMT_BF16, YP_FMT_F32, YP_FMT_F32X2, YpConvDesc, YpView
 
 BN_EPS = 1e-3
+MODEL_NAMES = ("YOLOPoint", "YOLOPointv52")
 VERSIONS = {"n": (0.33, 0.25), "s": (0.33, 0.5), "m": (0.67, 0.75), "l": (1.0, 1.0), "x": (1.33, 1.25)}
 
 
@@ -105,6 +106,14 @@ class PoolOp:
     buf: str
 
 
+@dataclass
+class Pool2Op:
+    """MaxPool2d(2, 2) from one buffer slice into a channel slice of a half-resolution buffer (YOLOPointv52 descriptor head)."""
+    src: SliceRef
+    dst: SliceRef
+    lane: int = 0
+
+
 def _pad16(c):
     return (c + 15) // 16 * 16
 
@@ -112,9 +121,11 @@ def _pad16(c):
 class NetPlan:
     """Shape-independent part: op list with symbolic buffers; instantiate() gives the buffer extents."""
 
-    def __init__(self, version: str, nc: int, precision: str = "fp32"):
+    def __init__(self, version: str, nc: int, precision: str = "fp32", model_name: str = "YOLOPoint"):
         assert precision in ("fp32", "bf16")
+        assert model_name in MODEL_NAMES, model_name
         self.version, self.nc, self.no = version, nc, nc + 5
+        self.model_name = model_name
         self.precision = precision
         self.act_fmt = YP_FMT_F32X2 if precision == "fp32" else YP_FMT_BF16
         (c1, c2, c3, c4, c5), (n1, n2, n3) = dims(version)
@@ -125,7 +136,7 @@ class NetPlan:
         self._lane = 0
         self.det_pad = _pad16(3 * self.no)
         self.semi_pad = _pad16(65)
-        self._build(c1, c2, c3, c4, c5, n1, n2, n3)
+        (self._build if model_name == "YOLOPoint" else self._build_v52)(c1, c2, c3, c4, c5, n1, n2, n3)
 
     # level L means spatial (H / 2**L, W / 2**L)
     def _buf(self, name, level, C_, fmt=None):
@@ -226,6 +237,87 @@ class NetPlan:
         self._c3("Bottleneck8", cat8, 5, c5, n1, xh)
         detect_head(2, xh, 5, 0)
 
+    def _c2f(self, name, src: SliceRef, level, cout, n, dst, cout_pad=None, l2norm=False):
+        """C2f (src/models/common.py:151-165): cv1 1x1 -> 2c channels, chunk(2); every Bottleneckv8 (3x3 -> 3x3, no shortcut:
+        C2f's default ``shortcut=False``) consumes the previous chunk and appends c channels; cv2 1x1 over all (2+n)c channels.
+        ``chunk`` and ``cat`` never run: cv1 stores into channels [0, 2c) of one (2+n)c-channel buffer, bottleneck i reads
+        slice [(1+i)c, (2+i)c) and stores into the next slice, cv2 reads the whole buffer."""
+        c = int(cout * 0.5)
+        assert c % 16 == 0, f"{name}: hidden width {c} is not a multiple of 16 channels"
+        Y = self._buf(name + ".Y", level, (2 + n) * c)
+        h = self._buf(name + ".h", level, c)
+        self._conv(name + ".cv1", src, SliceRef(Y.buf, 0, 2 * c), 1, 1, 2 * c)
+        for i in range(n):
+            self._conv(f"{name}.m.{i}.cv1", SliceRef(Y.buf, (1 + i) * c, c), h, 3, 1, c)
+            self._conv(f"{name}.m.{i}.cv2", h, SliceRef(Y.buf, (2 + i) * c, c), 3, 1, c)
+        self._conv(name + ".cv2", Y, dst, 1, 1, cout if cout_pad is None else cout_pad, l2norm=l2norm)
+
+    def _build_v52(self, c1, c2, c3, c4, c5, n1, n2, n3):
+        """YOLOPointv52 (src/models/YOLOPoint.py:248-342): C2f blocks, no Conv6 / Conv7 / ConvDet / ConvDesc / ConvDescA; ``semi``
+        and ``desc`` come straight out of a C2f (BN + SiLU, then the L2 normalisation for ``desc``); ``descA = MaxPool2d(2,2)(xa)``;
+        SPPF on c4 channels; Detect on (c3, c4, c4)."""
+        S = SliceRef
+        x0 = self._buf("in_s2d", 1, 16)
+        t1 = self._buf("t1", 1, c1)
+        t2 = self._buf("t2", 2, c2)
+        xa = self._buf("xa", 2, c2)
+        x3 = self._buf("x3", 3, c3)
+        cat6 = self._buf("cat6", 3, c4 + c3)     # up(xe) | xb
+        cat5 = self._buf("cat5", 4, 2 * c4)      # up(xd) | xc
+        cat7 = self._buf("cat7", 4, c3 + c4)     # Conv8(xf) | xe
+        cat8 = self._buf("cat8", 5, 2 * c4)      # Conv9(xg) | xd
+        catd = self._buf("catd", 3, 2 * c2)      # MaxPool(xa) | up(ConvDescB(xb))
+        xb = S("cat6", c4, c3)
+        xc = S("cat5", c4, c4)
+        # shared encoder
+        self._conv("Conv1", x0, t1, 3, 1, c1, stem=True)
+        self._conv("Conv2", t1, t2, 3, 2, c2)
+        self._c2f("Bottleneck1", t2, 2, c2, n1, xa)
+        self._conv("Conv3", xa, x3, 3, 2, c3)
+        # keypoint head (lane 1): semi = C2f(c3 -> 65) incl. BN + SiLU
+        self._lane = 1
+        semi = self._buf("semi", 3, self.semi_pad, YP_FMT_F32)
+        self._c2f("BottleneckDet", x3, 3, 65, n1, semi, cout_pad=self.semi_pad)
+        self._lane = 0
+        self._c2f("Bottleneck2", x3, 3, c3, n2, xb)
+        # descriptor head (lane 2)
+        self._lane = 2
+        self.ops.append(Pool2Op(xa, S("catd", 0, c2), self._lane))
+        self._conv("ConvDescB", xb, S("catd", c2, c2, upsample=2), 3, 2, c2)
+        desc = self._buf("desc", 3, c3, YP_FMT_F32)
+        self._c2f("BottleneckDesc", catd, 3, c3, n1, desc, l2norm=True)
+        # yolo encoder
+        self._lane = 0
+        x4 = self._buf("x4", 4, c4)
+        self._conv("Conv4", xb, x4, 3, 2, c4)
+        self._c2f("Bottleneck3", x4, 4, c4, n3, xc)
+        x5 = self._buf("x5", 5, c4)
+        self._conv("Conv5", xc, x5, 3, 2, c4)
+        x5b = self._buf("x5b", 5, c4)
+        self._c2f("Bottleneck4", x5, 5, c4, n1, x5b)
+        spp = self._buf("sppcat", 5, 2 * c4)     # x | y1 | y2 | y3, each c4/2
+        self._conv("SPPooling.cv1", x5b, S("sppcat", 0, c4 // 2), 1, 1, c4 // 2)
+        self.ops.append(PoolOp("sppcat"))
+        self._conv("SPPooling.cv2", spp, (S("cat8", c4, c4), S("cat5", 0, c4, upsample=2)), 1, 1, c4)          # xd
+        # neck
+        self._c2f("Bottleneck5", cat5, 4, c4, n1, (S("cat7", c3, c4), S("cat6", 0, c4, upsample=2)))           # xe
+
+        def detect_head(i, src, lvl):
+            det = self._buf(f"det{i}", lvl, self.det_pad, YP_FMT_F32)
+            self._conv(f"Detect.m.{i}", src, det, 1, 1, self.det_pad, act=False, bn=False)
+
+        xf = self._buf("xf", 3, c3)
+        self._c2f("Bottleneck6", cat6, 3, c3, n1, xf)
+        detect_head(0, xf, 3)
+        self._conv("Conv8", xf, S("cat7", 0, c3), 3, 2, c3)
+        xg = self._buf("xg", 4, c4)
+        self._c2f("Bottleneck7", cat7, 4, c4, n1, xg)
+        detect_head(1, xg, 4)
+        self._conv("Conv9", xg, S("cat8", 0, c4), 3, 2, c4)
+        xh = self._buf("xh", 5, c4)
+        self._c2f("Bottleneck8", cat8, 5, c4, n1, xh)
+        detect_head(2, xh, 5)
+
     def conv_ops(self):
         return [op for op in self.ops if isinstance(op, ConvOp)]
 
@@ -303,13 +395,14 @@ def pack_conv(sd, op: ConvOp, cin_view: int, precision: str) -> Tuple[torch.Tens
 TUNING_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning")
 
 
-def tuning_path(version: str, B: int, H: int, W: int, precision: str) -> str:
-    return os.path.join(TUNING_DIR, f"{version}_{B}x{H}x{W}_{precision}.json")
+def tuning_path(version: str, B: int, H: int, W: int, precision: str, model_name: str = "YOLOPoint") -> str:
+    tag = version if model_name == "YOLOPoint" else f"{model_name[len('YOLOPoint'):]}{version}"
+    return os.path.join(TUNING_DIR, f"{tag}_{B}x{H}x{W}_{precision}.json")
 
 
-def load_tuning(version: str, B: int, H: int, W: int, precision: str) -> Dict[str, Tuple[int, int]]:
+def load_tuning(version: str, B: int, H: int, W: int, precision: str, model_name: str = "YOLOPoint") -> Dict[str, Tuple[int, int]]:
     """Per-layer (tile_n, split_k) measured on a B200 by tools/tune_conv.py; absent file -> library heuristics."""
-    p = tuning_path(version, B, H, W, precision)
+    p = tuning_path(version, B, H, W, precision, model_name)
     if not os.path.exists(p):
         return {}
     with open(p) as f:
@@ -369,12 +462,17 @@ class ShapePlan:
         eng = self.eng
         need, descs = {}, []
         self.conv_descs = []
-        self.tuning = load_tuning(eng.net.version, self.B, self.H, self.W, eng.precision) if eng.use_tuning else {}
+        self.tuning = load_tuning(eng.net.version, self.B, self.H, self.W, eng.precision, eng.net.model_name) if eng.use_tuning else {}
         for op in eng.net.ops:
             if isinstance(op, PoolOp):
                 v = self.view(SliceRef(op.buf, 0, self.bufs[op.buf].shape[-1]))
                 self._keep.append(v)
                 self.launches.append((0, lambda st, v=v: _lib.check(L.yp_sppf_pool(C.byref(v), st))))
+                continue
+            if isinstance(op, Pool2Op):
+                vi, vo = self.view(op.src), self.view(op.dst)
+                self._keep += [vi, vo]
+                self.launches.append((op.lane, lambda st, vi=vi, vo=vo: _lib.check(L.yp_maxpool2x2(C.byref(vi), C.byref(vo), st))))
                 continue
             w, b = eng.weights[op.names]
             d = YpConvDesc()
@@ -493,10 +591,10 @@ class ShapePlan:
 
 class Engine:
     def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True,
-                 multi_stream: bool = True, split_k: bool = True, use_tuning: bool = True):
+                 multi_stream: bool = True, split_k: bool = True, use_tuning: bool = True, model_name: str = "YOLOPoint"):
         _lib.lib(require_device=True)
         self.device = torch.device(device)
-        self.net = NetPlan(version, nc, precision)
+        self.net = NetPlan(version, nc, precision, model_name)
         self.precision, self.algo, self.use_graphs, self.multi_stream, self.split_k = precision, algo, use_graphs, multi_stream, split_k
         self.use_tuning = use_tuning
         sd = {k: v.detach() for k, v in sd.items()}

@@ -77,6 +77,37 @@ class C3(nn.Module):
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
 
 
+class Bottleneckv8(nn.Module):
+    """cv2(cv1(x)) with two 3x3 convs, optional shortcut (src/models/common.py:91-103)."""
+
+    def __init__(self, c1, c2, shortcut=True, k=(3, 3), e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, k[0], 1)
+        self.cv2 = Conv(c_, c2, k[1], 1)
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x):
+        y = self.cv2(self.cv1(x))
+        return x + y if self.add else y
+
+
+class C2f(nn.Module):
+    """cv2(cat(chunk(cv1(x), 2) + [m_i(previous)])) (src/models/common.py:151-165); ``shortcut`` defaults to False."""
+
+    def __init__(self, c1, c2, n=1, shortcut=False, e=0.5):
+        super().__init__()
+        self.c = int(c2 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
+        self.cv2 = Conv((2 + n) * self.c, c2, 1)
+        self.m = nn.ModuleList(Bottleneckv8(self.c, self.c, shortcut, k=(3, 3), e=1.0) for _ in range(n))
+
+    def forward(self, x):
+        y = list(self.cv1(x).chunk(2, 1))
+        y.extend(m(y[-1]) for m in self.m)
+        return self.cv2(torch.cat(y, 1))
+
+
 class SPPF(nn.Module):
     """src/models/common.py:213-229."""
 
@@ -170,7 +201,51 @@ class YOLOPoint(nn.Module):
         return {"semi": semi, "desc": desc, "objects": self.Detect([xf, xg, xh])}
 
 
-_MODELS = {"YOLOPoint": YOLOPoint}
+class YOLOPointv52(nn.Module):
+    """Module tree of the reference's YOLOPointv52 in its construction order (src/models/YOLOPoint.py:248-293): C2f blocks, no
+    Conv6 / Conv7, ``semi`` and ``desc`` straight out of a C2f, ``descA = MaxPool2d(2, 2)(xa)``."""
+
+    def __init__(self, width_multiple=1.0, depth_multiple=1.0, inp_ch=3, nc=80, anchors=None):
+        super().__init__()
+        c1, c2, c3, c4, c5 = [make_divisible(2 ** k * width_multiple, 8) for k in range(6, 11)]
+        n1, n2, n3 = [max(round(k * depth_multiple), 1) for k in (3, 6, 9)]
+        self.dims = (c1, c2, c3, c4, c5)
+        self.depths = (n1, n2, n3)
+        spec = [
+            ("Conv1", lambda: Conv(inp_ch, c1, 6, 2, 2)), ("Conv2", lambda: Conv(c1, c2, 3, 2)),
+            ("Bottleneck1", lambda: C2f(c2, c2, n1)), ("Conv3", lambda: Conv(c2, c3, 3, 2)),
+            ("Bottleneck2", lambda: C2f(c3, c3, n2)), ("Conv4", lambda: Conv(c3, c4, 3, 2)),
+            ("Bottleneck3", lambda: C2f(c4, c4, n3)), ("Conv5", lambda: Conv(c4, c4, 3, 2)),
+            ("Bottleneck4", lambda: C2f(c4, c4, n1)), ("SPPooling", lambda: SPPF(c4, c4, 5)),
+            ("Bottleneck5", lambda: C2f(c5, c4, n1)), ("Bottleneck6", lambda: C2f(c4 + c3, c3, n1)),
+            ("Conv8", lambda: Conv(c3, c3, 3, 2, 1)), ("Bottleneck7", lambda: C2f(c4 + c3, c4, n1)),
+            ("Conv9", lambda: Conv(c4, c4, 3, 2, 1)), ("Bottleneck8", lambda: C2f(c5, c4, n1)),
+            ("Detect", lambda: Detect(nc, anchors=anchors, ch=(c3, c4, c4))),
+            ("BottleneckDet", lambda: C2f(c3, 65, n1)), ("ConvDescB", lambda: Conv(c3, c2, 3, 2, 1)),
+            ("MaxPool", lambda: nn.MaxPool2d(kernel_size=2, stride=2)),
+            ("ups", lambda: nn.Upsample(scale_factor=(2, 2), mode="nearest")),
+            ("BottleneckDesc", lambda: C2f(c3, c3, n1)),
+        ]
+        for name, make in spec:
+            setattr(self, name, make())
+
+    def forward(self, x):  # PyTorch path (training); dataflow of src/models/YOLOPoint.py:295-342
+        xa = self.Bottleneck1(self.Conv2(self.Conv1(x)))
+        x = self.Conv3(xa)
+        semi = self.BottleneckDet(x).float()
+        xb = self.Bottleneck2(x)
+        desc = self.BottleneckDesc(torch.cat((self.MaxPool(xa), self.ups(self.ConvDescB(xb))), 1)).float()
+        desc = desc.div(torch.unsqueeze(torch.norm(desc, p=2, dim=1), 1))
+        xc = self.Bottleneck3(self.Conv4(xb))
+        xd = self.SPPooling(self.Bottleneck4(self.Conv5(xc)))
+        xe = self.Bottleneck5(torch.cat((self.ups(xd), xc), 1))
+        xf = self.Bottleneck6(torch.cat((self.ups(xe), xb), 1))
+        xg = self.Bottleneck7(torch.cat((self.Conv8(xf), xe), 1))
+        xh = self.Bottleneck8(torch.cat((self.Conv9(xg), xd), 1))
+        return {"semi": semi, "desc": desc, "objects": self.Detect([xf, xg, xh])}
+
+
+_MODELS = {"YOLOPoint": YOLOPoint, "YOLOPointv52": YOLOPointv52}
 
 
 class Model(nn.Module):
@@ -184,12 +259,11 @@ class Model(nn.Module):
         if version not in VERSIONS:
             raise Exception(f"Version {version} is not a valid input. Choose one of n, s, m, l, x.")
         if model_name not in _MODELS:
-            raise NotImplementedError(f"model_name={model_name!r}: only {sorted(_MODELS)} is on the accelerated hot path "
-                                      f"(SURVEY.md section 8f lists YOLOPointv52 as the next row)")
+            raise NotImplementedError(f"model_name={model_name!r}: only {sorted(_MODELS)} are on the accelerated hot path")
         if inp_ch != 3:
             raise NotImplementedError("the B200 stem kernel is specialised for 3 input channels")
         dm, wm = VERSIONS[version]
-        self.version, self.nc, self.precision = version, nc, precision
+        self.version, self.nc, self.precision, self.model_name = version, nc, precision, model_name
         self.model = _MODELS[model_name](width_multiple=wm, depth_multiple=dm, inp_ch=inp_ch, nc=nc, anchors=anchors)
         m = self.model.Detect
         # The reference derives the strides with a 256x256 dummy forward in train mode (YOLOPoint.py:61-66).  The
@@ -249,7 +323,7 @@ class Model(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("yolopoint_b200.Model runs inference on a CUDA (sm_100a) device only: call .cuda() first; "
                                    "there is no CPU fallback")
-            self._engine = Engine(self.state_dict(), self.version, self.nc, dev, precision=self.precision)
+            self._engine = Engine(self.state_dict(), self.version, self.nc, dev, precision=self.precision, model_name=self.model_name)
         return self._engine
 
     def invalidate_engine(self):

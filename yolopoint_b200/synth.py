@@ -33,9 +33,21 @@ TUNING = {
 }
 
 
+# YOLOPointv52 (no ConvDet: the keypoint logits are a BN + SiLU output, peaked by scaling BottleneckDet.cv2's BN weight): same
+# columns, tuned the same way for the versions that have whole-frame fixtures / bench workloads (N, S); M / L keep the defaults.
+V52_SEMI_GAIN = 8.0
+TUNING_V52 = dict(TUNING, n=(2.5, 32.0, -3.3, 12.0, -3.0), s=(2.5, 40.0, -4.8, 12.0, -3.0))
+
+
 def perturb_state_dict(sd: Dict[str, torch.Tensor], seed: int = 0, version: str = "s", conv_gain=None,
-                       head_gain=None, obj_bias=None, det_gain=None, cls_bias=None) -> Dict[str, torch.Tensor]:
-    t = TUNING[version]
+                       head_gain=None, obj_bias=None, det_gain=None, cls_bias=None, semi_gain=None) -> Dict[str, torch.Tensor]:
+    """``semi_gain``: YOLOPointv52 has no ``ConvDet``; its keypoint logits are the BN + SiLU output of ``BottleneckDet.cv2``
+    (src/models/YOLOPoint.py:283, 303), so the softmax is peaked by scaling that BN's affine weight instead (auto-detected
+    from the keys when None; 1.0 for YOLOPoint)."""
+    v52 = not any(k.endswith("ConvDet.weight") for k in sd)
+    t = (TUNING_V52 if v52 else TUNING)[version]
+    if semi_gain is None:
+        semi_gain = V52_SEMI_GAIN if v52 else 1.0
     conv_gain = t[0] if conv_gain is None else conv_gain
     head_gain = t[1] if head_gain is None else head_gain
     obj_bias = t[2] if obj_bias is None else obj_bias
@@ -47,6 +59,8 @@ def perturb_state_dict(sd: Dict[str, torch.Tensor], seed: int = 0, version: str 
         v = v.detach().clone()
         if k.endswith(".bn.weight"):
             v = torch.empty_like(v).uniform_(0.8, 1.2, generator=g)
+            if semi_gain != 1.0 and k.endswith("BottleneckDet.cv2.bn.weight"):
+                v = v * semi_gain
         elif k.endswith(".bn.bias"):
             v = torch.empty_like(v).normal_(0.0, 0.1, generator=g)
         elif k.endswith(".bn.running_mean"):
