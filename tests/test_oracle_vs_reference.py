@@ -1,0 +1,85 @@
+"""Live check of the CPU oracle against the UNMODIFIED reference on fresh seeds (not the committed goldens).
+
+Runs only where the reference tree is present (the build container: /root/reference); skipped on the GPU box, where the
+committed fixtures under tests/golden/ (tests/test_oracle_golden.py) carry the pin.  TEST INFRASTRUCTURE."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_import
+from oracle import yolopoint_oracle as O
+from yolopoint_b200.synth import perturb_state_dict, synthetic_frame
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+NAMES = [str(i) for i in range(80)]
+
+
+@pytest.fixture(scope="module")
+def ns():
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return ref_import.load()
+
+
+@pytest.mark.parametrize("model_name,ver", [("YOLOPoint", "n"), ("YOLOPointv52", "n"), ("YOLOPointv52", "s")])
+def test_network_forward(ns, model_name, ver):
+    """OracleNet == the reference's fused eval forward (src/models/YOLOPoint.py:198-246 / :295-342) on a fresh seed."""
+    torch.manual_seed(5)
+    m = ns.Model(names=NAMES, version=ver, model_name=model_name)
+    sd = perturb_state_dict(m.state_dict(), 5, ver)
+    m.load_state_dict(sd)
+    m.eval().fuse()
+    x = torch.from_numpy(np.random.RandomState(21).rand(2, 3, 96, 128).astype(np.float32))
+    with torch.no_grad():
+        r = m(x)
+    o = O.OracleNet(sd, ver, 80, model_name).forward(x)
+    np.testing.assert_allclose(o["semi"].numpy(), r["semi"].numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(o["desc"].numpy(), r["desc"].numpy(), rtol=0, atol=2e-7)
+    np.testing.assert_allclose(o["objects"][0].numpy(), r["objects"][0].numpy(), rtol=1e-6, atol=1e-5)
+
+
+def test_post_processing_functions(ns):
+    rs = np.random.RandomState(99)
+    # box NMS (src/utils/general_yolo.py:124-235)
+    A, nc = 500, 5
+    centers = rs.uniform(30, 290, (20, 2))
+    xy = centers[rs.randint(0, 20, A)] + rs.normal(0, 5, (A, 2))
+    pred = np.concatenate((xy, rs.uniform(15, 70, (A, 2)), rs.uniform(0, 1, (A, 1)) ** 2, rs.uniform(0, 1, (A, nc)) ** 3), -1).astype(np.float32)[None]
+    for ct, it, ml, ag in ((0.25, 0.45, False, False), (0.4, 0.45, True, True), (0.3, 0.6, True, False)):
+        ref = ns.non_max_suppression(torch.from_numpy(pred.copy()), ct, it, agnostic=ag, multi_label=ml, max_det=300)[0].numpy()
+        got = O.non_max_suppression(pred, ct, it, agnostic=ag, multi_label=ml, max_det=300)[0]
+        np.testing.assert_array_equal(got, ref)
+    # heatmap (src/utils/utils.py:232-262)
+    semi = rs.normal(0, 3, (1, 65, 10, 14)).astype(np.float32)
+    np.testing.assert_allclose(O.flatten_detection(semi, variant="torch"), ns.flattenDetection(torch.from_numpy(semi)).numpy()[:, 0], rtol=0, atol=1e-7)
+    # keypoints (src/utils/utils.py:465-485, 118-182) on a tie-free heatmap
+    heat = (((rs.permutation(80 * 112) + 1.0) / (80 * 112 + 1.0)) ** 5).astype(np.float32).reshape(80, 112)
+    for thr, r in ((0.02, 4), (0.15, 8)):
+        np.testing.assert_array_equal(O.get_pts_from_heatmap(heat, thr, r), ns.getPtsFromHeatmap(heat, thr, r))
+    # descriptor sampling (src/evaluations/descriptor_evaluation.py:148-181)
+    coarse = rs.normal(0, 1, (1, 32, 10, 14)).astype(np.float32)
+    pts = np.stack((rs.randint(0, 112, 150), rs.randint(0, 80, 150), rs.uniform(0, 1, 150))).astype(np.float64)
+    np.testing.assert_allclose(O.sample_desc_from_points(coarse, pts), ns.sample_desc_from_points(torch.from_numpy(coarse), pts, "cpu"), rtol=0, atol=2e-7)
+    # two-way match (src/demo.py:300-341)
+    d1 = rs.normal(0, 1, (32, 200)).astype(np.float32)
+    d1 /= np.linalg.norm(d1, axis=0)
+    d2 = (d1[:, rs.permutation(200)[:170]] + 0.1 * rs.normal(0, 1, (32, 170))).astype(np.float32)
+    d2 /= np.linalg.norm(d2, axis=0)
+    np.testing.assert_array_equal(O.nn_match_two_way(d1, d2, 0.7), ns.PointTracker.nn_match_two_way(d1, d2, 0.7))
+
+
+def test_whole_frame(ns):
+    """process_frame == YoloPointFrontend.process_img (src/demo.py:125-230) on a frame seed the goldens do not use."""
+    torch.manual_seed(0)
+    m = ns.Model(names=NAMES, version="n")
+    sd = perturb_state_dict(m.state_dict(), 0, "n")
+    m.load_state_dict(sd)
+    m.eval().fuse()
+    fe = ref_import.make_frontend(ns, m, O.DEFAULT_CFG)
+    frame = synthetic_frame(256, 320, 9)
+    pts, desc, obj = fe.process_img(frame)
+    p2, d2, b2 = O.process_frame(O.OracleNet(sd, "n", 80), frame)
+    np.testing.assert_array_equal(p2, pts)
+    np.testing.assert_array_equal(b2, obj[0].numpy())
+    np.testing.assert_allclose(d2, desc, rtol=0, atol=1e-6)
