@@ -193,6 +193,104 @@ def golden_v52(ns=None):
          pts1=res[1][0], desc1=res[1][1].astype(np.float32), boxes1=res[1][2], matches=matches)
 
 
+def tracker_sequence(seed=0, frames=8, n0=160, D=32):
+    """Synthetic observation sequence for the tracker: a pool of unit descriptors with drifting positions; every frame sees a random
+    subset (plus a few new points), descriptors jittered; frame 3 is empty and frame 5 is a dropped frame (None)."""
+    rs = np.random.RandomState(seed)
+    pool = rs.normal(0, 1, (D, n0 + 40 * frames)).astype(np.float32)
+    pool /= np.linalg.norm(pool, axis=0)
+    xy = rs.uniform(8, 300, (2, pool.shape[1]))
+    seq = []
+    for f in range(frames):
+        if f == 3:
+            seq.append((np.zeros((3, 0)), np.zeros((D, 0), np.float32)))
+            continue
+        if f == 5:
+            seq.append((None, None))
+            continue
+        vis = np.sort(rs.permutation(n0 + 40 * f)[: n0 - 10 * f])
+        d = pool[:, vis] + 0.06 * rs.normal(0, 1, (D, vis.size)).astype(np.float32)
+        d = (d / np.linalg.norm(d, axis=0)).astype(np.float32)
+        p = np.vstack((np.rint(xy[:, vis] + f * 1.5), rs.uniform(0.1, 1.0, (1, vis.size))))
+        order = np.argsort(-p[2])
+        seq.append((p[:, order].astype(np.float64), d[:, order]))
+    return seq
+
+
+def ros_stub_modules():
+    """Import-time stand-ins for the ROS packages src/yolopoint_ros.py imports (rospy, rospkg, cv_bridge, message packages), so that
+    the reference's own ``to_ros_msg`` can run here; the message classes are plain attribute bags."""
+    import types
+
+    class Bag:
+        def __init__(self):
+            self.instances = []
+
+    mods = {}
+    for name in ("rospy", "rospkg", "cv_bridge", "sensor_msgs", "sensor_msgs.msg", "object_instance_msgs", "object_instance_msgs.msg",
+                 "keypoint_msg", "keypoint_msg.msg"):
+        mods[name] = types.ModuleType(name)
+    mods["sensor_msgs.msg"].Image = Bag
+    mods["cv_bridge"].CvBridge = Bag
+    mods["cv_bridge"].CvBridgeError = Exception
+    mods["object_instance_msgs.msg"].ObjectInstance2D = type("ObjectInstance2D", (Bag,), {})
+    mods["object_instance_msgs.msg"].ObjectInstance2DArray = type("ObjectInstance2DArray", (Bag,), {})
+    mods["keypoint_msg.msg"].KeypointArray = type("KeypointArray", (Bag,), {})
+    return mods
+
+
+def reference_to_ros_msg(pts, desc, obj_preds, names):
+    """Run the reference's YoloPointFrontendROS.to_ros_msg (src/yolopoint_ros.py:109-145) with stubbed ROS modules."""
+    import types
+    saved = {k: sys.modules.get(k) for k in ros_stub_modules()}
+    sys.modules.update(ros_stub_modules())
+    try:
+        import yolopoint_ros
+        fake = types.SimpleNamespace(names=names)
+        return yolopoint_ros.YoloPointFrontendROS.to_ros_msg(fake, pts, desc, obj_preds, "hdr")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def golden_tracker(ns=None):
+    """PointTracker.update / get_tracks (src/demo.py:358-441) over a synthetic sequence, and the KeypointArray / ObjectInstance2D
+    flattening of to_ros_msg (src/yolopoint_ros.py:109-145), both produced by the reference's own code."""
+    ns = ns or ref_import.load()
+    import contextlib
+    import io
+    arrs = {}
+    trk = ns.PointTracker(max_length=4, nn_thresh=0.7)
+    for f, (p, d) in enumerate(tracker_sequence()):
+        if p is not None:
+            arrs[f"pts{f}"], arrs[f"desc{f}"] = p, d
+            arrs[f"matches{f}"] = ns.PointTracker.nn_match_two_way(trk.last_desc if trk.last_desc is not None else np.zeros((d.shape[0], 0)), d, 0.7)
+        with contextlib.redirect_stdout(io.StringIO()):
+            trk.update(p, d)
+        arrs[f"tracks{f}"] = trk.tracks.copy()
+        arrs[f"count{f}"] = np.array(trk.track_count)
+        arrs[f"long{f}"] = trk.get_tracks(2)
+        arrs[f"offsets{f}"] = trk.get_offsets()
+    arrs["none_frames"] = np.array([f for f, (p, _) in enumerate(tracker_sequence()) if p is None])
+    # wire format
+    rs = np.random.RandomState(4)
+    pts = np.vstack((rs.randint(4, 636, 50), rs.randint(4, 476, 50), rs.uniform(0.1, 1, 50))).astype(np.float64)
+    desc = rs.normal(0, 1, (64, 50)).astype(np.float32)
+    det = torch.tensor([[10.7, 20.2, 110.9, 220.5, 0.91, 2.0], [300.1, 40.6, 420.4, 160.0, 0.55, 0.0], [5.5, 6.5, 7.5, 8.5, 0.41, 1.0]])
+    names = ["car", "person", "bike"]
+    km, am = reference_to_ros_msg(pts, desc, [det], names)
+    arrs.update(w_pts=pts, w_desc=desc, w_det=det.numpy(), w_x=km.x, w_y=km.y, w_score=km.score, w_desc_len=np.asarray(km.desc_len),
+                w_desc_flat=np.asarray(km.desc_flat), w_names=np.array(names),
+                w_obj_index=np.array([m.class_index for m in am.instances]), w_obj_name=np.array([m.class_name for m in am.instances]),
+                w_obj_prob=np.array([m.class_probabilities[0] for m in am.instances]),
+                w_obj_box=np.array([[m.bounding_box_min_x, m.bounding_box_min_y, m.bounding_box_max_x, m.bounding_box_max_y] for m in am.instances]),
+                w_obj_count=np.array([m.class_count for m in am.instances]))
+    save("tracker.npz", **arrs)
+
+
 def golden_losses():
     """Training losses (SURVEY.md section 8 row a11 consumers): the reference's own ComputeObjectLoss / ComputeDetectorLoss /
     descriptor_loss_sparse (src/utils/loss_functions.py:90-234, 600-619, 361-481) on seeded synthetic network outputs."""
@@ -237,6 +335,10 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "v52":
         os.makedirs(OUT, exist_ok=True)
         golden_v52()
+    elif len(sys.argv) > 1 and sys.argv[1] == "tracker":
+        os.makedirs(OUT, exist_ok=True)
+        golden_tracker()
     else:
         main()
         golden_losses()
+        golden_tracker()

@@ -1,0 +1,103 @@
+"""GPU parity of the streaming (HBM-bound) kernels' fast paths: vectorised NHWC heatmap, division-free Detect decode, two-pixel
+frame conversion.  Each is compared bit-exactly with the kernel's general path or with the oracle restatement
+(src/models/yolo.py:49-81, src/utils/utils.py:232-262, src/demo.py:130-132 of the reference)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolopoint_oracle as O
+from yolopoint_b200 import _lib, ops
+from yolopoint_b200._lib import YP_FMT_BF16, YP_FMT_F32X2
+from yolopoint_b200.engine import make_view, split_tf32
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("B,Hc,Wc", [(2, 12, 16), (1, 5, 7), (3, 9, 10), (1, 80, 80), (2, 23, 40)])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_heatmap_nhwc_vector_path_equals_nchw(B, Hc, Wc, variant):
+    """The engine's `semi` buffer is NHWC with 80-channel rows (float4 loads, paired-lane stores); the API path is NCHW (scalar
+    loads).  Same arithmetic, so the heatmaps must be bit-identical -- including odd Wc (unpaired stores) and a partial last CTA."""
+    g = torch.Generator().manual_seed(B * 100 + Wc)
+    semi = (torch.randn(B, 65, Hc, Wc, generator=g) * 3).cuda()
+    ref = ops.heatmap(semi, "nchw", variant=variant)
+    padded = torch.full((B, Hc, Wc, 80), 1e30, device="cuda")          # channels 65..79 must never be read into the softmax
+    padded[..., :65] = semi.permute(0, 2, 3, 1)
+    got = ops.heatmap(padded, "nhwc", variant=variant)
+    assert torch.equal(got, ref)
+    if variant == 0:
+        np.testing.assert_allclose(got.cpu().numpy(), O.flatten_detection(semi.cpu().numpy(), variant="torch"), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,ny,nx,nc,ldc", [(2, 5, 7, 80, 256), (1, 20, 20, 80, 256), (3, 4, 6, 1, 32), (1, 9, 3, 20, 80)])
+@pytest.mark.parametrize("want_raw", [True, False])
+def test_detect_decode_vs_oracle(B, ny, nx, nc, ldc, want_raw):
+    L = _lib.lib(require_device=True)
+    no, na = nc + 5, 3
+    g = torch.Generator().manual_seed(ny * nx + nc)
+    logits = torch.randn(B, ny, nx, ldc, generator=g) * 3
+    anchors_px = torch.tensor([[10., 13.], [16., 30.], [33., 23.]])
+    stride = 16.0
+    A_tot, row_off = 3 * ny * nx + 11, 5                       # rows of another level around this one stay untouched
+    pred = torch.full((B, A_tot, no), -7.0, device="cuda")
+    raw = torch.full((B, na, ny, nx, no), -7.0, device="cuda") if want_raw else None
+    dl = logits.cuda()
+    anc = (C.c_float * 6)(*anchors_px.flatten().tolist())
+    _lib.check(L.yp_detect_decode(dl.data_ptr(), B, ny, nx, ldc, na, no, stride, anc, raw.data_ptr() if want_raw else None, pred.data_ptr(), A_tot,
+                                  row_off, _st()))
+    torch.cuda.synchronize()
+    raw_ref = logits[..., :na * no].view(B, ny, nx, na, no).permute(0, 3, 1, 2, 4).contiguous()
+    ref = O.detect_decode([raw_ref], (anchors_px / stride)[None], torch.tensor([stride]))
+    if want_raw:
+        assert torch.equal(raw.cpu(), raw_ref)
+    got = pred.cpu()
+    assert float(got[:, :row_off].min()) == -7.0 and float(got[:, row_off + 3 * ny * nx:].max()) == -7.0
+    np.testing.assert_allclose(got[:, row_off:row_off + 3 * ny * nx].numpy(), ref.numpy(), rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("fmt", [YP_FMT_BF16, YP_FMT_F32X2])
+@pytest.mark.parametrize("B,H,W", [(2, 8, 36), (1, 6, 34), (1, 64, 96)])
+def test_frame_to_s2d(fmt, B, H, W):
+    """uint8 HWC frame -> 2x2 space-to-depth operand of the stem: W % 4 == 0 takes the two-pixel kernel, W = 34 the general one."""
+    L = _lib.lib(require_device=True)
+    frame = torch.from_numpy(np.random.RandomState(W).randint(0, 256, (B, H, W, 3)).astype(np.uint8)).cuda()
+    planes, dt = (1, torch.bfloat16) if fmt == YP_FMT_BF16 else (2, torch.float32)
+    out = torch.full((planes, B, H // 2, W // 2, 16), 9.0, dtype=dt, device="cuda")
+    v = make_view(out, fmt)
+    _lib.check(L.yp_frame_to_s2d(frame.data_ptr(), B, H, W, C.byref(v), _st()))
+    torch.cuda.synchronize()
+    x = torch.div(frame.float(), torch.full((), 255.0, device="cuda").expand(frame.shape))          # IEEE division (a python scalar divisor is a reciprocal multiply)
+    want = torch.zeros(B, H // 2, W // 2, 16, device="cuda")
+    want[..., :12] = x.view(B, H // 2, 2, W // 2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 2, W // 2, 12)
+    if fmt == YP_FMT_BF16:
+        assert torch.equal(out[0], want.to(torch.bfloat16))
+    else:
+        assert torch.equal(out, split_tf32(want))
+
+
+@pytest.mark.parametrize("D", [64, 96, 128, 192, 256, 320])
+def test_sample_desc_all_widths_and_out_of_range_points(D):
+    """Every descriptor width of the model family (compile-time channel-block counts 2/4/6/8, run-time path for 96 / 320) against
+    the oracle, with points left / right / above / below the image: out-of-bounds bilinear corners contribute zero (zeros padding
+    of grid_sample, src/evaluations/descriptor_evaluation.py:166-176) and must not be read as data."""
+    Hc, Wc, H, W = 12, 20, 96, 160
+    rs = np.random.RandomState(D)
+    coarse = rs.normal(0, 1, (1, D, Hc, Wc)).astype(np.float32)
+    coarse /= np.linalg.norm(coarse, axis=1, keepdims=True)
+    inside = np.stack((rs.randint(0, W, 300), rs.randint(0, H, 300)))
+    edge = np.array([[-5, W + 5, 30, 40, -3, W + 4, W, 0], [20, 30, -4, H + 6, -2, H + 3, H, 0]])
+    pts = np.concatenate((inside, edge), 1).astype(np.float64)
+    pts = np.vstack((pts, rs.uniform(0, 1, pts.shape[1])))
+    ref = O.sample_desc_from_points(coarse, pts, HW=(H, W))
+    nhwc = torch.from_numpy(coarse).cuda().permute(0, 2, 3, 1).contiguous()
+    p = torch.from_numpy(pts.T.astype(np.float32)).cuda()[None].contiguous()
+    got = ops.sample_desc(nhwc, p, None, (H, W), "nhwc")[0].T.cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-7)
+    got2 = ops.sample_desc(torch.from_numpy(coarse).cuda(), p, None, (H, W), "nchw")[0].T.cpu().numpy()      # strided (API) layout
+    np.testing.assert_array_equal(got2, got)

@@ -211,14 +211,3 @@ def extract_keypoints(semi, desc, conf_thresh=0.015, nms_dist=4, boxes=None):
     if n < 0:
         raise RuntimeError("keypoint buffer overflow")
     return (pts[0, :n].double().cpu().numpy().T.copy() if n else np.zeros((3, 0))), out[0, :n].T.contiguous().cpu().numpy()
-
-
-class PointTracker:
-    """Only the matching entry point of the reference tracker is on the hot path (src/demo.py:300-341); the
-    track bookkeeping (src/demo.py:358-422) is host logic listed as a later row in SURVEY.md section 8f."""
-
-    def __init__(self, max_length=4, nn_thresh=0.7):
-        self.maxl, self.nn_thresh = max_length, nn_thresh
-        self.last_desc = None
-
-    nn_match_two_way = staticmethod(nn_match_two_way)

@@ -10,9 +10,15 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxDPerLane = 16;  // D <= 512
 
-__global__ void sample_desc_kernel(const float* __restrict__ desc, int B, int D, int Hc, int Wc, long long sB, long long sD,
-                                   long long sH, long long sW, int img_h, int img_w, const float* __restrict__ pts,
-                                   const int* __restrict__ count, int pts_ld, float* __restrict__ out) {
+// K = channel blocks of 32 per descriptor (compile time, so that all 4*K corner loads are issued before the first use; K = 0: run
+// time, D <= 512).  The first version loaded inside `if (corner in bounds)` regions: the compiler kept every load in its own branch
+// region and each warp paid up to 24 serialised DRAM round trips (ncu: all stall samples on the multiply after each load, 31 % of
+// the HBM peak).  Out-of-bounds corners (zeros padding) now read a clamped, valid address and get weight 0: adding +-0 does not
+// change the sum, so the result is bit-identical to skipping the term.
+template <int K>
+__global__ void __launch_bounds__(256) sample_desc_kernel(const float* __restrict__ desc, int B, int D, int Hc, int Wc, long long sB, long long sD,
+                                                           long long sH, long long sW, int img_h, int img_w, const float* __restrict__ pts,
+                                                           const int* __restrict__ count, int pts_ld, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t wid = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   if (wid >= static_cast<int64_t>(B) * pts_ld) return;
@@ -28,24 +34,38 @@ __global__ void sample_desc_kernel(const float* __restrict__ desc, int B, int D,
   const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), static_cast<float>(Hc - 1));
   const float fx0 = floorf(ix), fy0 = floorf(iy);
   const float fx1 = __fadd_rn(fx0, 1.0f), fy1 = __fadd_rn(fy0, 1.0f);
-  const float wnw = __fmul_rn(__fsub_rn(fx1, ix), __fsub_rn(fy1, iy)), wne = __fmul_rn(__fsub_rn(ix, fx0), __fsub_rn(fy1, iy));
-  const float wsw = __fmul_rn(__fsub_rn(fx1, ix), __fsub_rn(iy, fy0)), wse = __fmul_rn(__fsub_rn(ix, fx0), __fsub_rn(iy, fy0));
   const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0), x1 = x0 + 1, y1 = y0 + 1;
   const bool okx0 = x0 >= 0 && x0 < Wc, okx1 = x1 >= 0 && x1 < Wc, oky0 = y0 >= 0 && y0 < Hc, oky1 = y1 >= 0 && y1 < Hc;
+  const float wnw = (okx0 && oky0) ? __fmul_rn(__fsub_rn(fx1, ix), __fsub_rn(fy1, iy)) : 0.0f;
+  const float wne = (okx1 && oky0) ? __fmul_rn(__fsub_rn(ix, fx0), __fsub_rn(fy1, iy)) : 0.0f;
+  const float wsw = (okx0 && oky1) ? __fmul_rn(__fsub_rn(fx1, ix), __fsub_rn(iy, fy0)) : 0.0f;
+  const float wse = (okx1 && oky1) ? __fmul_rn(__fsub_rn(ix, fx0), __fsub_rn(iy, fy0)) : 0.0f;
+  const int cx0 = min(max(x0, 0), Wc - 1), cx1 = min(max(x1, 0), Wc - 1), cy0 = min(max(y0, 0), Hc - 1), cy1 = min(max(y1, 0), Hc - 1);
   const float* base = desc + b * sB;
-  float v[kMaxDPerLane];
+  const float* pnw = base + cy0 * sH + cx0 * sW;
+  const float* pne = base + cy0 * sH + cx1 * sW;
+  const float* psw = base + cy1 * sH + cx0 * sW;
+  const float* pse = base + cy1 * sH + cx1 * sW;
+  constexpr int KK = K > 0 ? K : kMaxDPerLane;
+  float c[KK][4];
+#pragma unroll
+  for (int k = 0; k < KK; ++k) {
+    const int d = min(k * 32 + lane, D - 1);                       // lanes / blocks past D re-read the last channel, result unused
+    if (K > 0 || k * 32 < D) {
+      const long long off = d * sD;
+      c[k][0] = __ldg(pnw + off); c[k][1] = __ldg(pne + off); c[k][2] = __ldg(psw + off); c[k][3] = __ldg(pse + off);
+    }
+  }
+  float v[KK];
   float ss = 0.0f;
 #pragma unroll
-  for (int k = 0; k < kMaxDPerLane; ++k) {
-    const int d = k * 32 + lane;
+  for (int k = 0; k < KK; ++k) {
     v[k] = 0.0f;
-    if (d < D) {
-      const float* c = base + d * sD;
-      float acc = 0.0f;
-      if (okx0 && oky0) acc = __fadd_rn(acc, __fmul_rn(c[y0 * sH + x0 * sW], wnw));
-      if (okx1 && oky0) acc = __fadd_rn(acc, __fmul_rn(c[y0 * sH + x1 * sW], wne));
-      if (okx0 && oky1) acc = __fadd_rn(acc, __fmul_rn(c[y1 * sH + x0 * sW], wsw));
-      if (okx1 && oky1) acc = __fadd_rn(acc, __fmul_rn(c[y1 * sH + x1 * sW], wse));
+    if ((K > 0 || k * 32 < D) && k * 32 + lane < D) {
+      float acc = __fadd_rn(0.0f, __fmul_rn(c[k][0], wnw));
+      acc = __fadd_rn(acc, __fmul_rn(c[k][1], wne));
+      acc = __fadd_rn(acc, __fmul_rn(c[k][2], wsw));
+      acc = __fadd_rn(acc, __fmul_rn(c[k][3], wse));
       v[k] = acc;
       ss = fmaf(acc, acc, ss);
     }
@@ -55,9 +75,9 @@ __global__ void sample_desc_kernel(const float* __restrict__ desc, int B, int D,
   const float nrm = sqrtf(ss);
   float* o = out + (static_cast<int64_t>(b) * pts_ld + i) * D;
 #pragma unroll
-  for (int k = 0; k < kMaxDPerLane; ++k) {
+  for (int k = 0; k < KK; ++k) {
     const int d = k * 32 + lane;
-    if (d < D) o[d] = __fdiv_rn(v[k], nrm);
+    if ((K > 0 || k * 32 < D) && d < D) o[d] = __fdiv_rn(v[k], nrm);
   }
 }
 
@@ -196,8 +216,18 @@ extern "C" int yp_sample_desc(const float* desc, int32_t B, int32_t D, int32_t H
   YP_REQUIRE(desc && pts && out, YP_ERR_ARG, "sample_desc: null pointer");
   YP_REQUIRE(B > 0 && D > 0 && D <= 32 * yp::kMaxDPerLane && Hc > 0 && Wc > 0 && pts_ld > 0, YP_ERR_SHAPE, "sample_desc: bad shape (D=%d)", D);
   const int64_t warps = static_cast<int64_t>(B) * pts_ld;
-  yp::sample_desc_kernel<<<static_cast<unsigned>(yp::ceil_div64(warps * 32, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      desc, B, D, Hc, Wc, sB, sD, sH, sW, img_h, img_w, pts, count, pts_ld, out);
+  const unsigned blocks = static_cast<unsigned>(yp::ceil_div64(warps * 32, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define YP_SAMPLE(KB) yp::sample_desc_kernel<KB><<<blocks, 256, 0, st>>>(desc, B, D, Hc, Wc, sB, sD, sH, sW, img_h, img_w, pts, count, pts_ld, out)
+  switch ((D + 31) / 32) {   // descriptor widths of the model family: 64 / 128 / 192 / 256 (N / S / M / L), 320 (X)
+    case 1: YP_SAMPLE(1); break;
+    case 2: YP_SAMPLE(2); break;
+    case 4: YP_SAMPLE(4); break;
+    case 6: YP_SAMPLE(6); break;
+    case 8: YP_SAMPLE(8); break;
+    default: YP_SAMPLE(0); break;
+  }
+#undef YP_SAMPLE
   YP_LAUNCH_OK();
   return YP_OK;
 }

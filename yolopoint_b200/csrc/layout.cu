@@ -64,6 +64,70 @@ __global__ void to_s2d_kernel(const void* __restrict__ src, int B, int H, int W,
   }
 }
 
+// uint8 HWC frame -> space-to-depth operand, staged through shared memory so that both sides are coalesced: a CTA owns a strip of
+// S2D_PIX output pixels of one output row, i.e. two input row segments of 6 * S2D_PIX contiguous bytes, which it reads as aligned
+// 32-bit words (W % 4 == 0, 4-byte aligned frame); then consecutive threads emit consecutive 16-byte vectors of the output rows
+// (4 fp32 channels per plane, or 8 bf16 channels).  Output channel ch = (ph*2 + pw)*3 + c of pixel px is byte 6*px + ch % 6 of
+// input row ph = ch / 6.  Same values as to_s2d_kernel<true>: byte / 255 in round-to-nearest division, taken from a 256-entry table
+// the CTA builds once (one IEEE division per thread instead of 12-16 per pixel: ncu showed the kernel bound by instruction issue,
+// 88 % issue-slot utilisation, with the divisions' FFMA / FCHK / branch sequences on top).  A thread per output pixel with byte
+// loads and 32-/64-byte stores per thread reached 39 % (bf16) / 64 % (fp32 pairs) of the HBM peak.
+constexpr int S2D_PIX = 512;
+
+template <int kFmt>
+__global__ void __launch_bounds__(256) frame_to_s2d_staged_kernel(const uint8_t* __restrict__ frame, int B, int H, int W, YpView out) {
+  __shared__ uint32_t raw[2][S2D_PIX * 6 / 4];
+  __shared__ float lut[256];
+  lut[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), 255.0f);      // blockDim.x == 256
+  const int W2 = W / 2, H2 = H / 2;
+  const int strips = (W2 + S2D_PIX - 1) / S2D_PIX;
+  const int strip = blockIdx.x % strips, row = blockIdx.x / strips;
+  const int h2 = row % H2, b = row / H2;
+  const int w0 = strip * S2D_PIX;
+  const int npx = min(S2D_PIX, W2 - w0);
+  const int nwords = npx * 6 / 4;                       // W2 and w0 are even, so npx is
+  for (int t = threadIdx.x; t < 2 * nwords; t += blockDim.x) {
+    const int ph = t >= nwords ? 1 : 0, k = t - ph * nwords;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(frame + ((static_cast<int64_t>(b) * H + 2 * h2 + ph) * W + 2 * w0) * 3);
+    raw[ph][k] = __ldg(src + k);
+  }
+  __syncthreads();
+  const uint8_t* rb = reinterpret_cast<const uint8_t*>(&raw[0][0]);
+  const int64_t pix0 = (static_cast<int64_t>(b) * H2 + h2) * W2 + w0;
+  auto value = [&](int px, int ch) -> float {          // ch < 12
+    const int ph = ch >= 6 ? 1 : 0;
+    return lut[rb[ph * (S2D_PIX * 6) + 6 * px + (ch - 6 * ph)]];
+  };
+  if (kFmt == YP_FMT_BF16) {
+    for (int t = threadIdx.x; t < npx * 2; t += blockDim.x) {
+      const int px = t >> 1, half = t & 1;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const int ch = half * 8 + e; v[e] = ch < 12 ? value(px, ch) : 0.0f; }
+      uint4 pk;
+      __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out.base) + (pix0 + px) * out.pix_stride + half * 8) = pk;
+    }
+  } else {
+    for (int t = threadIdx.x; t < npx * 4; t += blockDim.x) {
+      const int px = t >> 2, q = t & 3;
+      float hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ch = q * 4 + e;
+        const float x = ch < 12 ? value(px, ch) : 0.0f;
+        hi[e] = kFmt == YP_FMT_F32X2 ? tf32_round(x) : x;
+        lo[e] = tf32_round(x - hi[e]);
+      }
+      float* o = static_cast<float*>(out.base) + (pix0 + px) * out.pix_stride + q * 4;
+      *reinterpret_cast<float4*>(o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      if (kFmt == YP_FMT_F32X2) *reinterpret_cast<float4*>(o + out.plane_stride) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 int to_s2d(const void* src, bool frame, int B, int H, int W, const YpView* out, cudaStream_t st) {
   YP_REQUIRE(src && out && out->base, YP_ERR_ARG, "to_s2d: null pointer");
   YP_REQUIRE(H % 2 == 0 && W % 2 == 0 && B > 0, YP_ERR_SHAPE, "to_s2d: H=%d W=%d must be even", H, W);
@@ -72,7 +136,14 @@ int to_s2d(const void* src, bool frame, int B, int H, int W, const YpView* out, 
   YP_REQUIRE(aligned16(out->base) && out->pix_stride % 8 == 0 && out->plane_stride % 4 == 0, YP_ERR_ALIGN, "to_s2d: output not 16-byte aligned");
   const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2);
   const unsigned blocks = static_cast<unsigned>(ceil_div64(total, 256));
-  if (frame) to_s2d_kernel<true><<<blocks, 256, 0, st>>>(src, B, H, W, *out);
+  if (frame && W % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 3u) == 0) {
+    const int64_t ctas = static_cast<int64_t>(B) * (H / 2) * ceil_div(W / 2, S2D_PIX);
+    YP_REQUIRE(ctas < (1ll << 31), YP_ERR_SHAPE, "to_s2d: frame batch too large");
+    const uint8_t* f = static_cast<const uint8_t*>(src);
+    if (out->format == YP_FMT_BF16) frame_to_s2d_staged_kernel<YP_FMT_BF16><<<static_cast<unsigned>(ctas), 256, 0, st>>>(f, B, H, W, *out);
+    else if (out->format == YP_FMT_F32X2) frame_to_s2d_staged_kernel<YP_FMT_F32X2><<<static_cast<unsigned>(ctas), 256, 0, st>>>(f, B, H, W, *out);
+    else frame_to_s2d_staged_kernel<YP_FMT_F32><<<static_cast<unsigned>(ctas), 256, 0, st>>>(f, B, H, W, *out);
+  } else if (frame) to_s2d_kernel<true><<<blocks, 256, 0, st>>>(src, B, H, W, *out);
   else to_s2d_kernel<false><<<blocks, 256, 0, st>>>(src, B, H, W, *out);
   YP_LAUNCH_OK();
   return YP_OK;
