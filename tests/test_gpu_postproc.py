@@ -179,3 +179,26 @@ def test_match_full_size_properties():
     assert float(m[:, 2].max()) < 3e-3   # sqrt(2-2*d) with d = 1 - O(1e-7): self-distance noise is O(1e-3)
     m2, cnt2 = ops.match_two_way(d2, None, d1, None, 0.7)
     assert int(cnt2.item()) == N and torch.equal(m2[:, 1].long(), perm)
+
+
+def test_point_tracker_with_cuda_match_equals_reference(golden, capsys):
+    """PointTracker.update with its own match (the CUDA two-way match instead of the reference's numpy one) reproduces the track
+    matrices the reference's tracker produced over the synthetic sequence (src/demo.py:358-441), bit for bit in the ids; the running
+    mean score column agrees to the match-score tolerance (1e-4 abs)."""
+    g = golden("tracker.npz")
+    none = set(int(i) for i in g["none_frames"])
+    trk = yp.PointTracker(max_length=4, nn_thresh=0.7)
+    f = 0
+    while f"tracks{f}" in g.files:
+        if f in none:
+            trk.update(None, None)
+        else:
+            trk.update(g[f"pts{f}"], g[f"desc{f}"])
+        ref = g[f"tracks{f}"]
+        assert trk.tracks.shape == ref.shape, f
+        np.testing.assert_array_equal(trk.tracks[:, 0], ref[:, 0])
+        np.testing.assert_array_equal(trk.tracks[:, 2:], ref[:, 2:])
+        np.testing.assert_allclose(trk.tracks[:, 1], ref[:, 1], rtol=0, atol=1e-4)
+        assert trk.track_count == int(g[f"count{f}"])
+        f += 1
+    capsys.readouterr()

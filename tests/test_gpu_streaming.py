@@ -1,6 +1,7 @@
 """GPU parity of the streaming (HBM-bound) kernels' fast paths: vectorised NHWC heatmap, division-free Detect decode, two-pixel
 frame conversion.  Each is compared bit-exactly with the kernel's general path or with the oracle restatement
 (src/models/yolo.py:49-81, src/utils/utils.py:232-262, src/demo.py:130-132 of the reference)."""
+import ctypes
 import ctypes as C
 
 import numpy as np
@@ -101,3 +102,16 @@ def test_sample_desc_all_widths_and_out_of_range_points(D):
     np.testing.assert_allclose(got, ref, rtol=0, atol=2e-7)
     got2 = ops.sample_desc(torch.from_numpy(coarse).cuda(), p, None, (H, W), "nchw")[0].T.cpu().numpy()      # strided (API) layout
     np.testing.assert_array_equal(got2, got)
+
+
+@pytest.mark.parametrize("B,H,W,Ct,c_off,Cv,C", [(2, 5, 7, 80, 0, 80, 65), (1, 12, 20, 192, 0, 192, 192), (3, 9, 9, 96, 32, 64, 64), (1, 4, 8, 16, 0, 16, 16)])
+def test_nhwc_to_nchw_export(B, H, W, Ct, c_off, Cv, C):
+    """fp32 NHWC view (channel slice of a wider buffer, padded channel count) -> dense NCHW of the first C channels."""
+    from yolopoint_b200._lib import YP_FMT_F32
+    L = _lib.lib(require_device=True)
+    t = torch.randn(1, B, H, W, Ct, device="cuda")
+    v = make_view(t, YP_FMT_F32, c_off, Cv)
+    out = torch.full((B, C, H, W), -3.0, device="cuda")
+    _lib.check(L.yp_nhwc_to_nchw(ctypes.byref(v), C, out.data_ptr(), _st()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, t[0, ..., c_off:c_off + C].permute(0, 3, 1, 2))

@@ -171,6 +171,35 @@ __global__ void nhwc_to_nchw_kernel(YpView in, int C, float* __restrict__ out) {
   }
 }
 
+// Fast path of the export for plain fp32 views with 16-byte aligned pixels: a CTA moves 32 pixels x 64 channels; every lane reads a
+// float4 (16 lanes = one pixel's 64 channels, a warp = two pixels), the tile is transposed in shared memory and written back as
+// 128-byte pixel runs per channel.  The element-wise kernel above spent ~70 instructions per warp-element on index arithmetic and
+// reached 50 % of the HBM peak (instruction issue 80 % busy).
+__global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(YpView in, int C, float* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int64_t HW = static_cast<int64_t>(in.H) * in.W;
+  const int b = blockIdx.z, c0 = blockIdx.y * 64;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = static_cast<const float*>(in.base) + (static_cast<int64_t>(b) * HW + p0) * in.pix_stride + c0;
+  const int cl = (lane & 15) * 4, ph = lane >> 4;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int p = warp * 4 + it * 2 + ph;                      // pixel of the tile this lane loads
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p0 + p < HW && c0 + cl < in.C) v = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(p) * in.pix_stride + cl));
+    tile[cl][p] = v.x; tile[cl + 1][p] = v.y; tile[cl + 2][p] = v.z; tile[cl + 3][p] = v.w;
+  }
+  __syncthreads();
+  float* dst = out + (static_cast<int64_t>(b) * C + c0) * HW + p0 + lane;
+  const bool pix_ok = p0 + lane < HW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = warp * 8 + j;
+    if (pix_ok && c0 + c < C) dst[static_cast<int64_t>(c) * HW] = tile[c][lane];
+  }
+}
+
 // SPPF: three chained 5x5 stride-1 max pools (padding = -inf, i.e. clipped windows), all in shared memory.
 // One CTA owns G channels of one image: stage the (value, source pixel) pairs of the whole map, run the three
 // pooling passes ping-pong between two shared buffers and copy the operand planes of the winning source pixel into
@@ -301,8 +330,13 @@ extern "C" int yp_nhwc_to_nchw(const YpView* in, int32_t C, float* out, void* st
   YP_REQUIRE(in && in->base && out, YP_ERR_ARG, "nhwc_to_nchw: null pointer");
   YP_REQUIRE(C > 0 && C <= in->C, YP_ERR_SHAPE, "nhwc_to_nchw: C=%d exceeds view channels %d", C, in->C);
   const int64_t HW = static_cast<int64_t>(in->H) * in->W;
-  dim3 grid(static_cast<unsigned>(yp::ceil_div64(HW, 32)), yp::ceil_div(C, 32), in->B);
-  yp::nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(*in, C, out);
+  if (in->format == YP_FMT_F32 && in->C % 4 == 0 && in->pix_stride % 4 == 0 && yp::aligned16(in->base)) {
+    dim3 grid(static_cast<unsigned>(yp::ceil_div64(HW, 32)), yp::ceil_div(C, 64), in->B);
+    yp::nhwc_to_nchw_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*in, C, out);
+  } else {
+    dim3 grid(static_cast<unsigned>(yp::ceil_div64(HW, 32)), yp::ceil_div(C, 32), in->B);
+    yp::nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(*in, C, out);
+  }
   YP_LAUNCH_OK();
   return YP_OK;
 }
