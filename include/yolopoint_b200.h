@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YP_ABI_VERSION 4
+#define YP_ABI_VERSION 5
 
 typedef enum {
   YP_OK = 0,
@@ -125,6 +125,11 @@ typedef struct {
 int yp_conv2d_nhwc_fwd(const YpConvDesc* desc, void* stream);
 /* Bytes of split-K workspace yp_conv2d_nhwc_fwd would like for this descriptor (0 = it will not split). */
 size_t yp_conv2d_workspace_bytes(const YpConvDesc* desc);
+/* Dry run of yp_conv2d_nhwc_fwd's host side for this descriptor: format / shape / tile / shared-memory / TMEM planning without
+ * touching the device or the pointers (works on a machine without a GPU).  Returns the status the launch would fail with before any
+ * tensor map is encoded, YP_OK otherwise; yp_last_error() describes the failure.  Lets a caller validate a whole launch plan (every
+ * layer of a model at a given input shape) ahead of time. */
+int yp_conv2d_plan_check(const YpConvDesc* desc);
 
 /*
  * yp_conv2d_nhwc_wgrad -- weight gradient of a Conv2d (bias-free, pad = k/2) for the training step: what autograd computes

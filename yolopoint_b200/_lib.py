@@ -55,6 +55,7 @@ SIGNATURES = {
     "yp_check_device": (_i32, []),
     "yp_conv2d_nhwc_fwd": (_i32, [_PC, _vp]),
     "yp_conv2d_workspace_bytes": (_sz, [_PC]),
+    "yp_conv2d_plan_check": (_i32, [_PC]),
     "yp_conv2d_nhwc_wgrad": (_i32, [C.POINTER(YpWgradDesc), _vp]),
     "yp_bn_act_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _vp]),
     "yp_bn_act_bwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -105,7 +106,7 @@ def lib(require_device: bool = False):
                     except AttributeError as e:  # pragma: no cover
                         raise YoloPointB200Error(f"{LIB_PATH} does not export {name}") from e
                     fn.restype, fn.argtypes = res, args
-                if handle.yp_abi_version() != 4:
+                if handle.yp_abi_version() != 5:
                     raise YoloPointB200Error("ABI version mismatch between _lib.py and libyolopoint_b200.so")
                 _lib = handle
     if require_device:

@@ -29,6 +29,7 @@ int sm_count() {
 
 int conv_tc_forward(const YpConvDesc& d, cudaStream_t st);
 size_t conv_tc_workspace_bytes(const YpConvDesc& d);
+int conv_tc_plan_check(const YpConvDesc& d);
 int conv_simt_forward(const YpConvDesc& d, cudaStream_t st);
 void set_conv_timeline(long long* p);
 int wgrad_tc(const YpWgradDesc& d, cudaStream_t st);
@@ -70,6 +71,12 @@ extern "C" int yp_debug_conv_timeline(void* device_buf_i64) {
 extern "C" size_t yp_conv2d_workspace_bytes(const YpConvDesc* d) {
   if (!d || d->algo != YP_ALGO_TCGEN05) return 0;
   return yp::conv_tc_workspace_bytes(*d);
+}
+
+extern "C" int yp_conv2d_plan_check(const YpConvDesc* d) {
+  YP_REQUIRE(d, YP_ERR_ARG, "conv: null descriptor");
+  YP_REQUIRE(d->algo == YP_ALGO_TCGEN05, YP_ERR_ARG, "conv: plan check is defined for the tcgen05 algorithm only (algo %d)", d->algo);
+  return yp::conv_tc_plan_check(*d);
 }
 
 extern "C" int yp_conv2d_nhwc_wgrad(const YpWgradDesc* d, void* stream) {

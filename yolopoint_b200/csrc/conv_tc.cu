@@ -1261,6 +1261,12 @@ size_t conv_tc_workspace_bytes(const YpConvDesc& d) {
   return P.ws_bytes;
 }
 
+// Shape / alignment / resource checks and tile planning only (host code, no CUDA calls): what yp_conv2d_plan_check returns.
+int conv_tc_plan_check(const YpConvDesc& d) {
+  ConvPlan P;
+  return plan_conv(d, &P, true);
+}
+
 int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   YP_REQUIRE(get_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   ConvPlan P;

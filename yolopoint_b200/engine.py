@@ -134,6 +134,11 @@ class NetPlan:
         self.bufs: Dict[str, Tuple[int, int, int]] = {}   # name -> (stride level, C, fmt)
         self.ops: List[object] = []
         self._lane = 0
+        if self.D > 256:
+            # the descriptor L2 normalisation runs in the epilogue of the last descriptor-head conv, which needs all D channels of a
+            # pixel in one accumulator tile (<= 256 TMEM columns): version "x" (D = 320) is not supported by the inference engine
+            raise NotImplementedError(f"version {version!r}: descriptor width {self.D} > 256 is not supported by the B200 inference engine "
+                                      f"(train mode runs; see DESIGN.md section 8)")
         self.det_pad = _pad16(3 * self.no)
         self.semi_pad = _pad16(65)
         (self._build if model_name == "YOLOPoint" else self._build_v52)(c1, c2, c3, c4, c5, n1, n2, n3)
@@ -336,6 +341,42 @@ class NetPlan:
                 co, ci, k = weights_meta[n]
                 total += 2.0 * ho * wo * co * ci * k * k
         return total
+
+
+def check_plan(net: "NetPlan", B: int, H: int, W: int) -> List[Tuple[str, str]]:
+    """Dry run of every convolution launch of ``net`` at input shape [B,3,H,W] through the library's host-side planner
+    (``yp_conv2d_plan_check``: formats, channel / tile geometry, shared memory and TMEM budgets).  Needs the shared library but no
+    GPU and no weights: pointers are placeholders with the alignment real buffers have.  Returns ``[(layer, error message), ...]``
+    (empty = every launch plans)."""
+    L = _lib.lib()
+    bad = []
+
+    def view(ref: SliceRef) -> YpView:
+        lvl, ctot, fmt = net.bufs[ref.buf]
+        es = 2 if fmt == YP_FMT_BF16 else 4
+        h, w = H >> lvl, W >> lvl
+        v = YpView()
+        v.base = 0x10000000 + ref.c_off * es
+        v.B, v.C = B, ref.C
+        v.H, v.W = (h // 2, w // 2) if ref.upsample == 2 else (h, w)
+        v.pix_stride, v.plane_stride, v.format, v.upsample = ctot, B * h * w * ctot, fmt, ref.upsample
+        return v
+
+    for op in net.conv_ops():
+        d = YpConvDesc()
+        d.in_ = view(op.src)
+        d.weight = 0x20000000
+        d.ksize, d.stride, d.cout, d.act = op.k, op.s, op.cout, op.act
+        d.epilogue = YP_EPI_L2NORM if op.l2norm else 0
+        if op.residual is not None:
+            d.residual = view(op.residual)
+        d.n_out = len(op.dst)
+        for i, ds in enumerate(op.dst):
+            d.out[i] = view(ds)
+        d.algo, d.split_k = YP_ALGO_TCGEN05, 0
+        if L.yp_conv2d_plan_check(C.byref(d)) != 0:
+            bad.append(("+".join(op.names), L.yp_last_error().decode("utf-8", "replace")))
+    return bad
 
 
 # --------------------------------------------------------------------------------------------------
