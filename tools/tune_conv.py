@@ -1,6 +1,6 @@
 """Per-layer autotuning of the tcgen05 conv launch parameters (N tile, split-K factor) on the GPU box.
 
-  python tools/tune_conv.py [--version s] [--size 640 640] [--batch 1] [--precision fp32]
+  python tools/tune_conv.py [--version s] [--size 640 640] [--batch 1] [--precision fp32] [--model-name YOLOPoint|YOLOPointv52]
 
 Times every conv layer of the network (real buffers / weights of a ShapePlan) for each valid (tile_n, split_k) with
 CUDA events over a captured graph of back-to-back launches and writes yolopoint_b200/tuning/<cfg>.json, which the engine
@@ -53,12 +53,13 @@ def main():
     ap.add_argument("--size", type=int, nargs=2, default=[640, 640])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--model-name", default="YOLOPoint", choices=["YOLOPoint", "YOLOPointv52"])
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     H, W = args.size
     L = _lib.lib(require_device=True)
     torch.manual_seed(0)
-    m = Model(names=[str(i) for i in range(80)], version=args.version, precision=args.precision)
+    m = Model(names=[str(i) for i in range(80)], version=args.version, precision=args.precision, model_name=args.model_name)
     m.load_state_dict(perturb_state_dict(m.state_dict(), 0, args.version))
     m = m.cuda().eval()
     eng = m.engine()
@@ -95,7 +96,7 @@ def main():
     tot_base = sum(r[1] for r in report)
     tot_best = sum(r[2][0] for r in report)
     print(f"distinct shapes {len(report)}; sum heuristic {tot_base:.1f} us, sum tuned {tot_best:.1f} us")
-    out = args.out or tuning_path(args.version, args.batch, H, W, args.precision)
+    out = args.out or tuning_path(args.version, args.batch, H, W, args.precision, args.model_name)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as f:
         json.dump({"device": torch.cuda.get_device_name(0), "config": vars(args), "layers": table}, f, indent=1)
