@@ -123,3 +123,32 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.yp_abi_version() == 5
     # struct layouts must agree with the header (sizes only; offsets follow from the C rules both sides use)
     assert ctypes.sizeof(_lib.YpView) == 48 and ctypes.sizeof(_lib.YpNmsParams) == 40
+
+
+def test_frontend_host_side_without_gpu():
+    """preprocess / restore_coords / template_filter of YoloPointFrontend are pure host code (src/demo.py:97-123, 187-195, 217-228)."""
+    import yolopoint_b200 as yp
+    rs = np.random.RandomState(0)
+    fe = yp.YoloPointFrontend(None)
+    frame = rs.randint(0, 256, (490, 651, 3)).astype(np.uint8)
+    img, cth, ctw, fac = fe.preprocess(frame)
+    assert img.shape == (480, 640, 3) and (cth, ctw, fac) == (5, 6, 1.0)          # ceil(10/2), ceil(11/2)
+    np.testing.assert_array_equal(img, frame[5:485, 6:646])
+    fe2 = yp.YoloPointFrontend(None, {"crop_resize": [10, 410, 20, 820, 640], "model": {"superpoint": {"nms": 4}}})
+    assert fe2.cfg["nms"] == 4
+    img2, cth2, ctw2, fac2 = fe2.preprocess(rs.randint(0, 256, (480, 960, 3)).astype(np.uint8))
+    assert img2.shape == (320, 640, 3) and fac2 == 0.8 and (cth2, ctw2) == (0, 0)   # 480x960 is a multiple of 32: no second crop
+    pts = np.array([[10., 20., 30.], [40., 50., 60.], [.9, .8, .7]])
+    boxes = torch.tensor([[8., 16., 24., 32., .5, 1.]])
+    p, b = fe2.restore_coords(pts.copy(), boxes.clone(), 0, 0, 0.8)
+    # x / y rows divided by the resize factor; then the reference's crop offsets land on the first two POINTS (all rows)
+    np.testing.assert_allclose(p, np.array([[12.5 + 20, 25. + 10, 37.5], [50. + 20, 62.5 + 10, 75.], [.9 + 20, .8 + 10, .7]]))
+    np.testing.assert_allclose(b[0, :4].numpy(), np.array([10. + 20, 20. + 10, 30. + 20, 40. + 10]))
+    fe.templates["front"] = np.ones((480, 640))
+    fe.templates["front"][:, 320:] = 0
+    q = np.array([[100., 400., 319., 320.], [10., 20., 30., 40.], [.9, .8, .7, .6]])
+    d = np.arange(8, dtype=np.float32).reshape(2, 4)
+    fp, fd, dropped = fe.template_filter(q, d, "front")
+    np.testing.assert_array_equal(fp, q[:, [0, 2]])
+    np.testing.assert_array_equal(fd, d[:, [0, 2]])
+    assert dropped

@@ -83,3 +83,47 @@ def test_whole_frame(ns):
     np.testing.assert_array_equal(p2, pts)
     np.testing.assert_array_equal(b2, obj[0].numpy())
     np.testing.assert_allclose(d2, desc, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,crop_resize", [((490, 650), None), ((480, 640), None), ((1216, 1936), [200, 1000, 300, 1900, 1280]),
+                                               ((1210, 1930), [100, 900, 50, 1650, 800])])
+def test_frontend_host_logic(ns, shape, crop_resize):
+    """YoloPointFrontend.preprocess / coordinate restore / template filter (host side of src/demo.py:97-123, 178-228) against the
+    reference's own methods on the same frame."""
+    import yolopoint_b200 as yp
+    rs = np.random.RandomState(shape[0])
+    frame = rs.randint(0, 256, shape + (3,)).astype(np.uint8)
+    ref = ref_import.make_frontend(ns, None, O.DEFAULT_CFG)
+    ref.crop_resize = crop_resize
+    ours = yp.YoloPointFrontend(None, {"crop_resize": crop_resize} if crop_resize else None)
+    a, b = ref.preprocess(frame), ours.preprocess(frame)
+    np.testing.assert_array_equal(a[0], b[0])
+    assert tuple(a[1:]) == tuple(b[1:])
+    # coordinate restore: the tail of the reference's process_img (src/demo.py:217-228), restated verbatim on copies
+    img, cth, ctw, fac = a
+    H, W = img.shape[:2]
+    pts = np.vstack((rs.randint(4, W - 4, 40), rs.randint(4, H - 4, 40), rs.uniform(0, 1, 40))).astype(np.float64)
+    boxes = torch.tensor(rs.uniform(0, 300, (5, 6)).astype(np.float32))
+    rp, rb = pts.copy().transpose(), boxes.clone()
+    rp[:, 0] = (rp[:, 0] + ctw) / fac
+    rp[:, 1] = (rp[:, 1] + cth) / fac
+    rp = rp.transpose()
+    rb[:, :4] = (rb[:, :4] + torch.tensor([ctw, cth, ctw, cth])) / fac
+    if crop_resize:
+        rp[:, 0] += crop_resize[2]
+        rp[:, 1] += crop_resize[0]
+        rb[:, :4] += torch.tensor([crop_resize[2], crop_resize[0], crop_resize[2], crop_resize[0]])
+    gp, gb = ours.restore_coords(pts.copy(), boxes.clone(), cth, ctw, fac)
+    np.testing.assert_array_equal(gp, rp)
+    assert torch.equal(gb, rb)
+    # template filter: mask semantics of the reference closure (ones * template == 1)
+    template = (rs.rand(H, W) > 0.3).astype(np.float64)
+    ours.templates["cam"] = template
+    desc = rs.normal(0, 1, (16, 40)).astype(np.float32)
+    mask = np.ones((H, W)) * template
+    keep = mask[pts[1].astype(int), pts[0].astype(int)] == 1
+    fp, fd, dropped = ours.template_filter(pts.copy(), desc, "cam")
+    np.testing.assert_array_equal(fp, pts[:, keep])
+    np.testing.assert_array_equal(fd, desc[:, keep])
+    assert dropped == (not keep.all())
+    assert ours.template_filter(pts, desc, "other")[2] is False          # unknown camera: warn and keep everything

@@ -193,31 +193,75 @@ class FramePipeline:
 class YoloPointFrontend:
     """Drop-in for the reference frontend's per-frame call (src/demo.py:15-230) around an already-built model.
 
-    ``process_img(img)`` takes a uint8 HxWx3 frame and returns ``(pts [3,N] float64, desc [D,N] float32, [boxes [n,6]])``
-    exactly like the reference (crop to multiples of 32 included; ``crop_resize`` is not supported)."""
+    ``process_img(img, rostpc=None)`` takes a uint8 HxWx3 frame and returns ``(pts [3,N] float64, desc [D,N] float32, [boxes [n,6]])``
+    exactly like the reference: crop to multiples of 32, the optional ``crop_resize`` window of the config (crop + ``cv2.resize`` on the
+    host, as the reference does it) and the optional per-camera template mask (``self.templates[rostpc]``, src/demo.py:187-192) included.
+    """
 
     def __init__(self, model, config: Optional[dict] = None, filter_pts: bool = True, max_pts: int = 4096, nms_cap: int = 4096):
         self.model = model
         cfg = dict(DEFAULT_CFG)
+        self.crop_resize = None
         if config:
             m = config.get("model", config)
             cfg.update({k: v for k, v in m.get("superpoint", {}).items() if k in cfg})
             cfg.update({k: v for k, v in m.get("yolo", {}).items() if k in cfg})
             cfg.update({k: v for k, v in config.items() if k in cfg})
+            self.crop_resize = config.get("crop_resize")        # src/demo.py:52
         self.cfg, self.filter_pts, self.max_pts, self.nms_cap = cfg, filter_pts, max_pts, nms_cap
         self.cell, self.border_remove = 8, 4
+        self.templates: Dict[str, np.ndarray] = {}              # camera name -> [H,W] mask, 1 = keep (src/demo.py:94)
         self._pipes: Dict[Tuple[int, int], FramePipeline] = {}
         self.last_matches = None
 
-    def preprocess(self, img):  # src/demo.py:97-123 without crop_resize
-        h0, w0 = img.shape[:2]
+    def preprocess(self, img, interpolation=None):
+        """src/demo.py:97-123: optional crop + resize to width ``crop_resize[4]``, then a centred crop to multiples of 32 (decided,
+        like the reference, on the shape of the frame as it came in).  -> (img, cut_h0, cut_w0, resize_fac)"""
+        shape0 = img.shape[:2]
+        resize_fac = 1.0
         cut_h0 = cut_w0 = 0
-        if h0 % 32 or w0 % 32:
+        if self.crop_resize:
+            import cv2
+            cr = self.crop_resize
+            w1 = cr[4]
+            img = img[cr[0]:cr[1], cr[2]:cr[3]]
+            h0, w0 = img.shape[:2]
+            resize_fac = w1 / w0
+            img = cv2.resize(img, (w1, round(h0 * resize_fac)), interpolation=cv2.INTER_LINEAR if interpolation is None else interpolation)
+        if shape0[0] % 32 or shape0[1] % 32:
+            h0, w0 = img.shape[:2]
             cut_h, cut_w = (h0 % 32) / 2, (w0 % 32) / 2
             cut_h0, cut_h1 = int(np.ceil(cut_h)), int(np.floor(cut_h))
             cut_w0, cut_w1 = int(np.ceil(cut_w)), int(np.floor(cut_w))
             img = img[cut_h0:h0 - cut_h1, cut_w0:w0 - cut_w1]
-        return img, cut_h0, cut_w0, 1.0
+        return img, cut_h0, cut_w0, resize_fac
+
+    def template_filter(self, pts: np.ndarray, desc: np.ndarray, rostpc):
+        """Second half of the reference's ``filter_points`` closure (src/demo.py:187-195): keep the points whose pixel of the camera's
+        template mask equals 1.  Descriptor sampling is per point, so dropping columns afterwards equals filtering before sampling."""
+        try:
+            template = self.templates[rostpc]
+        except KeyError:
+            print(f"Template for {rostpc} not found.")
+            return pts, desc, False
+        keep = (np.ones(template.shape[:2]) * template)[pts[1].astype(int), pts[0].astype(int)] == 1
+        if keep.all():
+            return pts, desc, False
+        return pts[:, keep], (desc[:, keep] if keep.any() else np.zeros((desc.shape[0], 0))), True
+
+    def restore_coords(self, pts: np.ndarray, boxes: torch.Tensor, cth: int, ctw: int, resize_fac: float):
+        """src/demo.py:217-228: back to the coordinates of the frame as it came in.  With ``crop_resize`` the reference then adds the
+        crop offsets through ``pts[:, 0] += cr[2]; pts[:, 1] += cr[0]`` on the [3,N] array, i.e. to the first two POINTS (all three
+        rows) rather than to the x / y rows; reproduced as is so that results stay identical."""
+        pts[0] = (pts[0] + ctw) / resize_fac
+        pts[1] = (pts[1] + cth) / resize_fac
+        boxes[:, :4] = (boxes[:, :4] + torch.tensor([ctw, cth, ctw, cth], dtype=boxes.dtype)) / resize_fac
+        if self.crop_resize:
+            cr = self.crop_resize
+            pts[:, 0] += cr[2]
+            pts[:, 1] += cr[0]
+            boxes[:, :4] += torch.tensor([cr[2], cr[0], cr[2], cr[0]], dtype=boxes.dtype)
+        return pts, boxes
 
     def pipeline(self, H: int, W: int) -> FramePipeline:
         if (H, W) not in self._pipes:
@@ -226,14 +270,16 @@ class YoloPointFrontend:
 
     @torch.no_grad()
     def process_img(self, img, rostpc=None):
-        img, cth, ctw, _ = self.preprocess(img)
+        img, cth, ctw, resize_fac = self.preprocess(img)
         H, W, _ = img.shape
         pts, desc, boxes, matches = self.pipeline(H, W).step_host(img[None])[0]
         self.last_matches = matches
         obj = torch.from_numpy(boxes)
         if pts.shape[1] == 0:
             return np.zeros((3, 0)), None, None  # src/demo.py:152-153
-        pts[0] += ctw
-        pts[1] += cth
-        obj[:, :4] += torch.tensor([ctw, cth, ctw, cth], dtype=obj.dtype)
+        if self.filter_pts and rostpc:
+            pts, desc, dropped = self.template_filter(pts, desc, rostpc)
+            if dropped:
+                self.last_matches = None          # the device-side matches index the unfiltered sets
+        pts, obj = self.restore_coords(pts, obj, cth, ctw, resize_fac)
         return pts, desc, [obj]
