@@ -291,6 +291,36 @@ def golden_tracker(ns=None):
     save("tracker.npz", **arrs)
 
 
+def homography_batch(seed=0, B=6):
+    """Normalised inverse homographies (rotation, scale, translation, perspective terms; the first one is the identity)."""
+    rs = np.random.RandomState(seed)
+    Hs = []
+    for _ in range(B):
+        a, sc = rs.uniform(-0.25, 0.25), rs.uniform(0.8, 1.2)
+        Hs.append(np.array([[sc * np.cos(a), -sc * np.sin(a), rs.uniform(-.2, .2)], [sc * np.sin(a), sc * np.cos(a), rs.uniform(-.2, .2)],
+                            [rs.uniform(-.15, .15), rs.uniform(-.15, .15), 1.0]], np.float32))
+    Hs = np.stack(Hs)
+    Hs[0] = np.eye(3)
+    return Hs
+
+
+def golden_homography(ns=None):
+    """SURVEY.md section 8f rank 2 (contract pinned ahead of the kernel): warp_image_batch / compute_valid_mask (src/utils/utils.py:
+    296-376) and the aggregation of src/export_homography.py:97-128, run by the reference's own functions."""
+    ns = ns or ref_import.load()
+    from utils.utils import compute_valid_mask, warp_image_batch
+    B, H, W = 6, 48, 64
+    rs = np.random.RandomState(5)
+    heat = rs.rand(B, 1, H, W).astype(np.float32) ** 4
+    Hs = homography_batch(0, B)
+    th, tH = torch.from_numpy(heat), torch.from_numpy(Hs)
+    mask = compute_valid_mask(torch.tensor([H, W]), tH)[:, None]
+    wb = warp_image_batch(th, tH, mode="bilinear")
+    wn = warp_image_batch(th, tH, mode="nearest")
+    agg = torch.sum(warp_image_batch(th * mask, tH), dim=0) / torch.sum(warp_image_batch(mask, tH), dim=0)
+    save("homography.npz", heat=heat, inv_homographies=Hs, mask=mask.numpy(), warp_bilinear=wb.numpy(), warp_nearest=wn.numpy(), aggregated=agg.numpy()[0])
+
+
 def golden_losses():
     """Training losses (SURVEY.md section 8 row a11 consumers): the reference's own ComputeObjectLoss / ComputeDetectorLoss /
     descriptor_loss_sparse (src/utils/loss_functions.py:90-234, 600-619, 361-481) on seeded synthetic network outputs."""
@@ -335,6 +365,9 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "v52":
         os.makedirs(OUT, exist_ok=True)
         golden_v52()
+    elif len(sys.argv) > 1 and sys.argv[1] == "homography":
+        os.makedirs(OUT, exist_ok=True)
+        golden_homography()
     elif len(sys.argv) > 1 and sys.argv[1] == "tracker":
         os.makedirs(OUT, exist_ok=True)
         golden_tracker()
@@ -342,3 +375,4 @@ if __name__ == "__main__":
         main()
         golden_losses()
         golden_tracker()
+        golden_homography()

@@ -463,6 +463,62 @@ def nn_match_two_way(desc1: np.ndarray, desc2: np.ndarray, nn_thresh: float) -> 
 # Whole-frame pipeline (src/demo.py:125-230 without crop/resize bookkeeping)
 # ----------------------------------------------------------------------------------------------
 
+# ----------------------------------------------------------------------------------------------
+# Homography adaptation (the next row; restated ahead of its kernel so that the contract is pinned)
+# src/utils/utils.py:274-291 (warp_points), :333-376 (warp_image_batch); src/export_homography.py:92-128 (combine)
+# ----------------------------------------------------------------------------------------------
+
+def warp_image_batch(img: np.ndarray, mat_homo_inv: np.ndarray, mode: str = "bilinear") -> np.ndarray:
+    """Inverse warp of a batch [B,C,H,W] by normalised homographies [B,3,3] (zeros padding, align_corners=True).
+
+    Output pixel (y, x) samples the source at ``p = Hinv_b . (xn, yn, 1)``, ``(u, v) = p[:2] / p[2]`` in normalised coordinates,
+    ``xn = linspace(-1, 1, W)[x]``, ``yn = linspace(-1, 1, H)[y]`` (torch.linspace values), i.e. source pixel
+    ``ix = (u + 1) / 2 * (W - 1)``, ``iy = (v + 1) / 2 * (H - 1)``; bilinear weights and the four-term sum in ATen's order
+    (nw, ne, sw, se), out-of-range corners contribute zero; ``mode='nearest'`` rounds half to even like ``nearbyint``."""
+    img = np.asarray(img, np.float32)
+    Hm = np.asarray(mat_homo_inv, np.float32).reshape(-1, 3, 3)
+    B, Cc, H, W = img.shape
+    xs = torch.linspace(-1, 1, W).numpy()
+    ys = torch.linspace(-1, 1, H).numpy()
+    xn, yn = np.meshgrid(xs, ys)                                   # [H,W] each
+    pts = np.stack((xn.ravel(), yn.ravel(), np.ones(H * W, np.float32)), 0).astype(np.float32)   # [3, H*W]
+    out = np.zeros_like(img)
+    for b in range(B):
+        p = (Hm[b] @ pts).astype(np.float32)
+        u = (p[0] / p[2]).reshape(H, W)
+        v = (p[1] / p[2]).reshape(H, W)
+        ix = ((u + np.float32(1)) / np.float32(2)) * np.float32(W - 1)
+        iy = ((v + np.float32(1)) / np.float32(2)) * np.float32(H - 1)
+        if mode == "nearest":
+            xi, yi = np.rint(ix).astype(np.int64), np.rint(iy).astype(np.int64)
+            ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H) & np.isfinite(ix) & np.isfinite(iy)
+            out[b] = np.where(ok, img[b][:, np.clip(yi, 0, H - 1), np.clip(xi, 0, W - 1)], np.float32(0))
+            continue
+        x0, y0 = np.floor(ix), np.floor(iy)
+        x1, y1 = x0 + 1, y0 + 1
+        terms = ((x0, y0, (x1 - ix) * (y1 - iy)), (x1, y0, (ix - x0) * (y1 - iy)), (x0, y1, (x1 - ix) * (iy - y0)), (x1, y1, (ix - x0) * (iy - y0)))
+        acc = np.zeros((Cc, H, W), np.float32)
+        with np.errstate(invalid="ignore"):
+            for xq, yq, w in terms:
+                fin = np.isfinite(xq) & np.isfinite(yq)
+                xi = np.where(fin, xq, -1).astype(np.int64)
+                yi = np.where(fin, yq, -1).astype(np.int64)
+                ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+                acc += np.where(ok, img[b][:, np.clip(yi, 0, H - 1), np.clip(xi, 0, W - 1)] * w.astype(np.float32), np.float32(0))
+        out[b] = acc
+    return out
+
+
+def homography_adaptation(heat: np.ndarray, valid_mask: np.ndarray, inv_homographies: np.ndarray) -> np.ndarray:
+    """src/export_homography.py:97-128 without the letterbox slicing: heat [B,1,H,W] of the B warped copies of one image, valid masks
+    [B,1,H,W], inverse homographies [B,3,3] -> the aggregated heatmap [H,W] = sum_b warp(heat_b * mask_b) / sum_b warp(mask_b)
+    (0/0 = NaN where no copy covers a pixel, as in the reference)."""
+    h = warp_image_batch(np.asarray(heat, np.float32) * np.asarray(valid_mask, np.float32), inv_homographies)
+    m = warp_image_batch(valid_mask, inv_homographies)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (h.sum(0, dtype=np.float32) / m.sum(0, dtype=np.float32))[0]
+
+
 DEFAULT_CFG = dict(  # configs/kitti_inference.yaml:5-16
     detection_threshold=0.12, nms=8, nn_thresh=0.7, conf_thres_box=0.4, iou_thres_box=0.45, max_det=1000,
 )

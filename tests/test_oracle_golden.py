@@ -96,3 +96,17 @@ def test_e2e_n(golden):
         np.testing.assert_allclose(boxes, g[f"boxes{i}"], rtol=0, atol=1e-3)
     m = O.nn_match_two_way(res[0][1], res[1][1], 0.7)
     np.testing.assert_array_equal(m[:2], g["matches"][:2])
+
+
+def test_homography_adaptation_contract(golden):
+    """warp_image_batch (bilinear / nearest) and the heatmap aggregation of the homography-adaptation export (SURVEY.md section 8f
+    rank 2) against the reference's own functions: the contract the next kernel is built to."""
+    g = golden("homography.npz")
+    np.testing.assert_allclose(O.warp_image_batch(g["heat"], g["inv_homographies"]), g["warp_bilinear"], rtol=0, atol=5e-7)
+    wn = O.warp_image_batch(g["heat"], g["inv_homographies"], mode="nearest")
+    assert (wn != g["warp_nearest"]).mean() < 1e-3            # a source coordinate within 1 ulp of x.5 may round the other way
+    # identity homography: linspace coordinates are not exact integers in fp32, so the warp is the identity only to ~1e-5 (reference too)
+    np.testing.assert_allclose(O.warp_image_batch(g["heat"][:1], g["inv_homographies"][:1]), g["heat"][:1], rtol=0, atol=2e-5)
+    agg = O.homography_adaptation(g["heat"], g["mask"], g["inv_homographies"])
+    assert np.array_equal(np.isnan(agg), np.isnan(g["aggregated"]))
+    np.testing.assert_allclose(np.nan_to_num(agg), np.nan_to_num(g["aggregated"]), rtol=0, atol=1e-6)
