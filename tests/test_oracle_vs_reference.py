@@ -127,3 +127,19 @@ def test_frontend_host_logic(ns, shape, crop_resize):
     np.testing.assert_array_equal(fd, desc[:, keep])
     assert dropped == (not keep.all())
     assert ours.template_filter(pts, desc, "other")[2] is False          # unknown camera: warn and keep everything
+
+
+@pytest.mark.parametrize("model_name", ["YOLOPoint", "YOLOPointv52"])
+def test_fuse_matches_reference(ns, model_name):
+    """Model.fuse(): same state-dict keys and folded values as the reference's fuse (src/models/YOLOPoint.py:84-90)."""
+    import yolopoint_b200 as yp
+    torch.manual_seed(3)
+    ref = ns.Model(names=NAMES, version="n", model_name=model_name)
+    sd = perturb_state_dict(ref.state_dict(), 3, "n")
+    ref.load_state_dict(sd)
+    ours = yp.Model(names=NAMES, version="n", model_name=model_name)
+    ours.load_state_dict(sd)
+    a, b = ref.eval().fuse().state_dict(), ours.eval().fuse().state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        np.testing.assert_allclose(b[k].numpy(), a[k].numpy(), rtol=1e-6, atol=1e-7, err_msg=k)

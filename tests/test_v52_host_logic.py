@@ -130,3 +130,29 @@ def test_plan_structure(ver):
 def test_unknown_model_name_raises():
     with pytest.raises(NotImplementedError):
         Model(names=NAMES, version="n", model_name="YOLOPointM")
+
+
+def test_fuse_partial_load_and_cpu_training_path():
+    """Wrapper behaviour for the v52 tree: fuse() folds every Conv block's BN (src/models/YOLOPoint.py:84-90), a checkpoint with another
+    class count loads positionally except Detect (:102-135), and the train-mode module tree backpropagates to every parameter on the
+    CPU (plain PyTorch path: the reference's own way of running it)."""
+    torch.manual_seed(0)
+    m = Model(names=NAMES, version="n", model_name=V52)
+    sd = m.state_dict()
+    m2 = Model(names=["a", "b", "c"], version="n", model_name=V52)
+    m2.load_state_dict(sd, strict=True)
+    assert torch.equal(m2.state_dict()["model.Bottleneck1.m.0.cv2.conv.weight"], sd["model.Bottleneck1.m.0.cv2.conv.weight"])
+    assert m2.state_dict()["model.Detect.m.0.bias"].shape[0] == 3 * 8
+    m.train()
+    x = torch.rand(2, 3, 64, 96)
+    out = m(x)
+    assert out["semi"].shape == (2, 65, 8, 12) and out["desc"].shape == (2, 64, 8, 12) and len(out["objects"]) == 3
+    loss = out["semi"].square().mean() + out["desc"][:, ::2].mean() + sum(r.square().mean() for r in out["objects"])
+    loss.backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+    assert len(list(m.parameters())) == 174
+    m.eval().fuse()
+    keys = list(m.state_dict().keys())
+    assert "model.BottleneckDet.cv2.conv.bias" in keys and not any(".bn." in k for k in keys)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64))      # eval-mode inference on CPU must fail loudly
