@@ -233,6 +233,9 @@ int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, const YpNmsP
  * semi: logits, element (b,c,hc,wc) at b*sB + c*sC + hc*sH + wc*sW (so NCHW and NHWC both work).
  * heat [B, 8*Hc, 8*Wc] fp32: heat[8hc+i, 8wc+j] = softmax_c(semi)[8i+j]; channel 64 (dustbin) dropped.
  * variant 0: torch.softmax (max-subtracted).  variant 1: demo.py's exp(x)/(sum+1e-5).
+ * The normalisation is one correctly rounded reciprocal of the sum per cell and a multiply per pixel (<= 1 ulp from the quotient; the
+ * two layouts give bit-identical results).  Rows whose channels are contiguous and 16-byte aligned (sC == 1, sW % 4 == 0) take
+ * vector loads.
  * ---------------------------------------------------------------------------------------------- */
 int yp_heatmap(const float* semi, int32_t B, int32_t Hc, int32_t Wc, int64_t sB, int64_t sC, int64_t sH, int64_t sW,
                int32_t variant, float* heat, void* stream);
