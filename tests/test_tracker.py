@@ -68,3 +68,16 @@ def test_wire_format_matches_reference(golden):
                                   g["w_obj_box"])
     np.testing.assert_array_equal(np.array([o["class_probabilities"][0] for o in objs]), g["w_obj_prob"])
     assert all(o["class_count"] == 3 and o["is_instance"] for o in objs)
+
+
+def test_wire_descriptor_width_256_wraps_like_the_uint8_field():
+    pts = np.array([[5., 6.], [7., 8.], [.5, .25]])
+    desc = np.arange(512, dtype=np.float32).reshape(256, 2)
+    w = keypoints_to_wire(pts, desc)
+    assert w["desc_len"].dtype == np.uint8 and int(w["desc_len"]) == 0 and w["desc_flat"].shape == (512,)
+    p2, d2 = keypoints_from_wire(w)
+    np.testing.assert_array_equal(d2, desc.astype(float))
+    np.testing.assert_array_equal(p2, pts)
+    e = keypoints_to_wire(np.zeros((3, 0)), np.zeros((64, 0)))
+    p3, d3 = keypoints_from_wire(e)
+    assert p3.shape == (3, 0) and d3.shape == (64, 0)

@@ -129,7 +129,9 @@ def keypoints_to_wire(pts: np.ndarray, desc: np.ndarray) -> dict:
         "x": pts[1, :].astype(np.uint16),
         "y": pts[0, :].astype(np.uint16),
         "score": pts[2, :].astype(np.float32),
-        "desc_len": np.array(desc.shape[0], dtype=np.uint8),
+        # the message field is uint8: D = 256 (YOLOPoint-L) does not fit and wraps to 0 (what numpy < 2 did for the reference's
+        # np.array(256, dtype=np.uint8); numpy >= 2 raises there) -- consumers recover D from len(desc_flat) / len(x)
+        "desc_len": np.array(desc.shape[0] & 0xFF, dtype=np.uint8),
         "desc_flat": desc.flatten().astype(float),
     }
 
