@@ -143,3 +143,28 @@ def test_fuse_matches_reference(ns, model_name):
     assert list(a.keys()) == list(b.keys())
     for k in a:
         np.testing.assert_allclose(b[k].numpy(), a[k].numpy(), rtol=1e-6, atol=1e-7, err_msg=k)
+
+
+@pytest.mark.parametrize("seed,maxl", [(1, 2), (2, 4), (3, 6)])
+def test_tracker_against_live_reference(ns, seed, maxl, capsys):
+    """PointTracker.update / get_tracks against the reference tracker on fresh random sequences and window lengths (the committed
+    golden covers one sequence at max_length 4)."""
+    import contextlib
+    import io
+    import yolopoint_b200 as yp
+    from oracle.make_golden import tracker_sequence
+    ref = ns.PointTracker(max_length=maxl, nn_thresh=0.7)
+    ours = yp.PointTracker(max_length=maxl, nn_thresh=0.7)
+    for p, d in tracker_sequence(seed=seed, frames=10, n0=90, D=16):
+        m = None
+        if p is not None:
+            prev = ref.last_desc if ref.last_desc is not None else np.zeros((d.shape[0], 0))
+            m = O.nn_match_two_way(prev, d, 0.7)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref.update(p, d)
+        ours.update(p, d, matches=m)
+        np.testing.assert_array_equal(ours.tracks, ref.tracks)
+        assert ours.track_count == ref.track_count
+        for k in (1, 2, maxl):
+            np.testing.assert_array_equal(ours.get_tracks(k), ref.get_tracks(k))
+    capsys.readouterr()
