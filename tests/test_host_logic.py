@@ -152,3 +152,32 @@ def test_frontend_host_side_without_gpu():
     np.testing.assert_array_equal(fp, q[:, [0, 2]])
     np.testing.assert_array_equal(fd, d[:, [0, 2]])
     assert dropped
+
+
+def test_load_model_signature_and_compat_on_stand_in_modules():
+    """load_model keeps the reference's calling convention (src/utils/utils.py:55-57); compat.install() rebinds whatever of the
+    reference's modules is importable -- exercised here on stand-in modules, against the live reference in test_oracle_vs_reference.py."""
+    import sys
+    import types
+    import yolopoint_b200 as yp
+    import yolopoint_b200.compat as compat
+    m = yp.load_model(inp_ch=3, names=NAMES, version="n", model_name="YOLOPointv52")
+    assert isinstance(m, Model) and m.model_name == "YOLOPointv52"
+    with pytest.raises(NotImplementedError):
+        yp.load_model(meta_model=False, model_name="SuperPointNet")
+    fake_models, fake_utils = types.ModuleType("models"), types.ModuleType("utils.utils")
+    fake_models.Model = object
+    fake_utils.nms_fast = len
+    saved = {k: sys.modules.get(k) for k in ("models", "utils.utils")}
+    sys.modules["models"], sys.modules["utils.utils"] = fake_models, fake_utils
+    try:
+        done = compat.install(modules=("models", "utils.utils"))
+        assert done == ["models.Model", "utils.utils.nms_fast"] and fake_models.Model is yp.Model and fake_utils.nms_fast is yp.nms_fast
+        compat.uninstall()
+        assert fake_models.Model is object and fake_utils.nms_fast is len
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -168,3 +168,27 @@ def test_tracker_against_live_reference(ns, seed, maxl, capsys):
         for k in (1, 2, maxl):
             np.testing.assert_array_equal(ours.get_tracks(k), ref.get_tracks(k))
     capsys.readouterr()
+
+
+def test_compat_install_switches_the_reference_seam(ns):
+    """yolopoint_b200.compat.install() rebinds the names the reference scripts resolve at run time; the reference's own load_model
+    (src/utils/utils.py:55-57) then builds yolopoint_b200.Model with the reference's state dict, for both model families."""
+    import yolopoint_b200 as yp
+    import yolopoint_b200.compat as compat
+    import utils.utils as ru
+    import demo
+    torch.manual_seed(0)
+    ref_sd = ns.Model(names=NAMES, version="n", model_name="YOLOPointv52").state_dict()
+    done = compat.install()
+    try:
+        assert {"models.Model", "utils.utils.nms_fast", "utils.general_yolo.non_max_suppression", "demo.PointTracker"} <= set(done)
+        m = ru.load_model(inp_ch=3, names=NAMES, version="n", model_name="YOLOPointv52")        # the call of src/demo.py:45
+        assert isinstance(m, yp.Model) and type(m.model).__name__ == "YOLOPointv52"
+        m.load_state_dict(ref_sd, strict=True)
+        assert demo.PointTracker is yp.PointTracker and ru.getPtsFromHeatmap is yp.getPtsFromHeatmap
+        bare = yp.load_model(meta_model=False, model_name="YOLOPoint", width_multiple=0.25, depth_multiple=0.33, inp_ch=3, nc=80,
+                             anchors=yp.model.ANCHORS_DEFAULT)
+        assert type(bare).__name__ == "YOLOPoint"
+    finally:
+        compat.uninstall()
+    assert ru.nms_fast is ns.nms_fast and demo.PointTracker is ns.PointTracker

@@ -390,8 +390,13 @@ class Model(nn.Module):
                 param.requires_grad = False
 
 
-def load_model(model_name="YOLOPoint", **kwargs):
-    """src/utils/utils.py:55-57 for the names this package provides."""
-    if model_name == "Model":
+def load_model(meta_model=True, **kwargs):
+    """src/utils/utils.py:55-57: ``meta_model=True`` (the way every reference script calls it) builds the ``Model`` wrapper from
+    ``names / version / inp_ch / anchors / model_name``; ``meta_model=False`` builds the bare network class named by ``model_name``
+    from ``width_multiple / depth_multiple / inp_ch / nc / anchors`` (what the wrapper itself does, src/models/YOLOPoint.py:47-53)."""
+    if meta_model:
         return Model(**kwargs)
-    return Model(model_name=model_name, **kwargs)
+    name = kwargs.pop("model_name")
+    if name not in _MODELS:
+        raise NotImplementedError(f"model_name={name!r}: only {sorted(_MODELS)} are on the accelerated hot path")
+    return _MODELS[name](**kwargs)
