@@ -321,6 +321,21 @@ def golden_homography(ns=None):
     save("homography.npz", heat=heat, inv_homographies=Hs, mask=mask.numpy(), warp_bilinear=wb.numpy(), warp_nearest=wn.numpy(), aggregated=agg.numpy()[0])
 
 
+def golden_infonce():
+    """The descriptor loss of the reference's training script (src/train.py:8: infonce, src/utils/loss_functions.py:484-597) on the
+    descriptor maps of losses.npz: 16 draws of its random pair / negative sampling."""
+    ref_import.load()
+    from utils.loss_functions import infonce
+    g = np.load(os.path.join(OUT, "losses.npz"))
+    d1, d2, mask, Hm = (torch.from_numpy(g[k]) for k in ("d1", "d2", "mask", "Hm"))
+    np.random.seed(0)
+    torch.manual_seed(0)
+    vals = np.array([infonce(d1, d2, mask, Hm, num_samples_per_image=200, num_masked_non_matches_per_match=50).item() for _ in range(16)], np.float32)
+    eye, ones = torch.eye(3).repeat(d1.shape[0], 1, 1), torch.ones_like(mask)
+    same = np.array([infonce(d1, d1, ones, eye, num_samples_per_image=200, num_masked_non_matches_per_match=50).item() for _ in range(4)], np.float32)
+    save("infonce.npz", linfonce=vals, linfonce_same=same)
+
+
 def golden_losses():
     """Training losses (SURVEY.md section 8 row a11 consumers): the reference's own ComputeObjectLoss / ComputeDetectorLoss /
     descriptor_loss_sparse (src/utils/loss_functions.py:90-234, 600-619, 361-481) on seeded synthetic network outputs."""
@@ -365,6 +380,8 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "v52":
         os.makedirs(OUT, exist_ok=True)
         golden_v52()
+    elif len(sys.argv) > 1 and sys.argv[1] == "infonce":
+        golden_infonce()
     elif len(sys.argv) > 1 and sys.argv[1] == "homography":
         os.makedirs(OUT, exist_ok=True)
         golden_homography()
@@ -376,3 +393,4 @@ if __name__ == "__main__":
         golden_losses()
         golden_tracker()
         golden_homography()
+        golden_infonce()

@@ -98,7 +98,7 @@ def _train_worker(rank, world, port, q):
     ref_step = TrainStep.__new__(TrainStep)
     ref_step.model, ref_step.device = m2, torch.device("cpu")
     ref_step.obj_loss, ref_step.det_loss = Lz.ComputeObjectLoss(m2, LOSS_CFG, "cpu"), Lz.ComputeDetectorLoss("cpu")
-    ref_step.sparse_cfg, ref_step.graphed = ts.sparse_cfg, None
+    ref_step.sparse_cfg, ref_step.graphed, ref_step.desc_loss = ts.sparse_cfg, None, ts.desc_loss
     torch.manual_seed(100 + rank)
     l2, _ = ref_step.losses(sample)
     l2.backward()

@@ -47,3 +47,25 @@ def test_sparse_descriptor_loss_matches_reference_statistically(golden):
     same = Lz.descriptor_loss_sparse(d1, d1, ones, eye, num_samples_per_image=200, num_masked_non_matches_per_match=50)
     diff = Lz.descriptor_loss_sparse(d1, -d1, ones, eye, num_samples_per_image=200, num_masked_non_matches_per_match=50)
     assert float(diff) > float(same) + 0.5
+
+
+def test_infonce_matches_reference_statistically(golden):
+    """The descriptor loss the reference's training script uses (src/train.py:8 imports ``infonce`` as its descriptor loss;
+    src/utils/loss_functions.py:484-597): (1 + K)-way cross entropy of every sampled match against K random non-matches at tau = 0.07.
+    Random sampling as in the hinge form, so means over repeated draws are compared (reference std 0.014 on this input)."""
+    g, r = golden("losses.npz"), golden("infonce.npz")
+    torch.manual_seed(1)
+    d1, d2, mask, Hm = (torch.from_numpy(g[k]) for k in ("d1", "d2", "mask", "Hm"))
+    vals = np.array([Lz.infonce(d1, d2, mask, Hm, num_samples_per_image=200, num_masked_non_matches_per_match=50).item() for _ in range(16)])
+    assert abs(vals.mean() - r["linfonce"].mean()) < 2e-2, (vals.mean(), r["linfonce"].mean())
+    eye, ones = torch.eye(3).repeat(d1.shape[0], 1, 1), torch.ones_like(mask)
+    same = np.array([Lz.infonce(d1, d1, ones, eye, num_samples_per_image=200, num_masked_non_matches_per_match=50).item() for _ in range(4)])
+    assert abs(same.mean() - r["linfonce_same"].mean()) < 2e-2, (same.mean(), r["linfonce_same"].mean())
+    # one draw of pairs shared by both forms: the logits are the same similarities the hinge form thresholds; gradients reach both maps
+    pairs = Lz.descriptor_pairs(mask, Hm, d1.shape[0], d1.shape[2], d1.shape[3], 200, 50)
+    a, b = d1.clone().requires_grad_(True), d2.clone().requires_grad_(True)
+    loss = Lz.infonce(a, b, mask, Hm, 200, 50, pairs=pairs)
+    loss.backward()
+    pos, neg = Lz._pair_similarities(d1, d2, pairs)
+    want = -torch.log_softmax(torch.cat((pos[:, None], neg.t()), 1) / 0.07, 1)[:, 0].mean()
+    assert abs(float(loss) - float(want)) < 1e-6 and float(a.grad.abs().sum()) > 0 and float(b.grad.abs().sum()) > 0

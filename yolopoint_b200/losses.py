@@ -215,16 +215,9 @@ def descriptor_pairs(mask_valid_warp, inv_homographies, B, Hc, Wc, num_samples_p
     return pa, pb, rnd
 
 
-def descriptor_loss_sparse(descriptors, descriptors_warped, mask_valid_warp, inv_homographies, num_samples_per_image=1500,
-                           num_masked_non_matches_per_match=120, cell_size=8, device="cpu", pairs=None):
-    """loss_functions.py:361-481.  Positive pairs: every valid cell centre of the frame and its (rounded) position in the warped
-    frame, a random subset of equal size per image; loss = mean hinge (1 - <a,b>) over the pairs + mean over the violating ones
-    of the hinge (<a, b'> - 0.1) against random other warped samples.  ``pairs`` = a precomputed ``descriptor_pairs(...)`` result."""
-    device = descriptors.device
-    B, _, Hc, Wc = descriptors.shape
-    assert Hc * Wc >= num_samples_per_image, "Number of samples per image must be greater than number of pixels in image"
-    if pairs is None:
-        pairs = descriptor_pairs(mask_valid_warp, inv_homographies, B, Hc, Wc, num_samples_per_image, num_masked_non_matches_per_match, cell_size, device)
+def _pair_similarities(descriptors, descriptors_warped, pairs):
+    """Cosine similarities of the sampled pairs: pos [n] (a_i . b_i) and neg [K, n] (a_i . b_{rnd[k, i]}), n = B * pool
+    (loss_functions.py:429-471 / 553-591: the part the two descriptor losses share)."""
     pa, pb, rnd = pairs
 
     def sample(desc, pts):
@@ -237,7 +230,7 @@ def descriptor_loss_sparse(descriptors, descriptors_warped, mask_valid_warp, inv
     n = da.shape[0]
     if da.is_cuda and n <= 40000:
         # The reference materialises db[rnd] as a [K, n, D] tensor (4.9 GB for 8 x 3000 samples, K = 200, D = 256) and multiplies it
-        # by the broadcast queries (loss_functions.py:468-471).  The same K x n similarities are entries of the n x n matrix
+        # by the broadcast queries (loss_functions.py:468-471, 587-591).  The same K x n similarities are entries of the n x n matrix
         # da @ db^T: one GEMM (TF32 tensor cores, 2.3 GB result) + a gather, ~5x less memory traffic forward and backward.
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -247,6 +240,37 @@ def descriptor_loss_sparse(descriptors, descriptors_warped, mask_valid_warp, inv
             torch.backends.cuda.matmul.allow_tf32 = prev
     else:
         neg = (da.unsqueeze(0) * db[rnd]).sum(-1)
+    return pos, neg
+
+
+def descriptor_loss_sparse(descriptors, descriptors_warped, mask_valid_warp, inv_homographies, num_samples_per_image=1500,
+                           num_masked_non_matches_per_match=120, cell_size=8, device="cpu", pairs=None):
+    """loss_functions.py:361-481 (the hinge form; the training script itself uses ``infonce`` below).  Positive pairs: every valid cell
+    centre of the frame and its (rounded) position in the warped frame, a random subset of equal size per image; loss = mean hinge
+    (1 - <a,b>) over the pairs + mean over the violating ones of the hinge (<a, b'> - 0.1) against random other warped samples.
+    ``pairs`` = a precomputed ``descriptor_pairs(...)`` result."""
+    device = descriptors.device
+    B, _, Hc, Wc = descriptors.shape
+    assert Hc * Wc >= num_samples_per_image, "Number of samples per image must be greater than number of pixels in image"
+    if pairs is None:
+        pairs = descriptor_pairs(mask_valid_warp, inv_homographies, B, Hc, Wc, num_samples_per_image, num_masked_non_matches_per_match, cell_size, device)
+    pos, neg = _pair_similarities(descriptors, descriptors_warped, pairs)
     neg = torch.clamp(neg - 0.1, min=0).flatten()
     neg_loss = neg.sum() / (torch.count_nonzero(neg) + 1)
     return torch.clamp(1 - pos, min=0).mean() + neg_loss
+
+
+def infonce(descriptors, descriptors_warped, mask_valid_warp, inv_homographies, num_samples_per_image=1500, num_masked_non_matches_per_match=120,
+            cell_size=8, device="cpu", tau=0.07, pairs=None):
+    """loss_functions.py:484-597 -- the descriptor loss the reference's training script uses (src/train.py:8: ``from
+    utils.loss_functions import infonce as descriptor_loss_sparse``).  Same sampled pairs as the hinge form; every match is one
+    (1 + K)-way classification: logits = [<a_i, b_i>, <a_i, b_rnd(1,i)>, ..., <a_i, b_rnd(K,i)>] / tau, loss = mean cross entropy
+    of the match against its K random non-matches."""
+    device = descriptors.device
+    B, _, Hc, Wc = descriptors.shape
+    assert Hc * Wc >= num_samples_per_image, "Number of samples per image must be greater than number of pixels in image"
+    if pairs is None:
+        pairs = descriptor_pairs(mask_valid_warp, inv_homographies, B, Hc, Wc, num_samples_per_image, num_masked_non_matches_per_match, cell_size, device)
+    pos, neg = _pair_similarities(descriptors, descriptors_warped, pairs)
+    logits = torch.cat((pos.unsqueeze(1), neg.t()), dim=1) / tau
+    return -F.log_softmax(logits, dim=1)[:, 0].mean()

@@ -1,7 +1,7 @@
 """One training step of the reference (src/train.py:196-250) on the B200 path, data parallel over the GPUs of one box.
 
   step = forward(image) + forward(warped image)                    (tcgen05 convs, train.py)
-       + object loss + 2 x detector loss + sparse descriptor loss   (losses.py; train.py:212-241 of the reference)
+       + object loss + 2 x detector loss + InfoNCE descriptor loss  (losses.py; train.py:8, 212-241 of the reference)
        + backward                                                   (tcgen05 dgrad / wgrad)
        + gradient all-reduce (mean over ranks)                      (NCCL over NVLink; gloo in the CPU tests)
        + Adam step (lr 1e-3 over all parameters, src/train.py:88) and the linear LambdaLR schedule (:91-93)
@@ -121,12 +121,17 @@ class _FlatOutputs(torch.nn.Module):
 
 class TrainStep:
     def __init__(self, model, epochs: int = 100, lr: float = 1e-3, lrf: float = 0.01, sparse_cfg: Optional[dict] = None, group=None,
-                 bucket_bytes: int = 32 << 20, graph_sample: Optional[torch.Tensor] = None):
+                 bucket_bytes: int = 32 << 20, graph_sample: Optional[torch.Tensor] = None, desc_loss: str = "infonce"):
         """``graph_sample``: an image batch [B,3,H,W] on the model's device.  When given, the two forward passes of a step and
         their backward passes are captured into CUDA graphs (torch.cuda.make_graphed_callables: one forward + one backward graph
         per pass, shared parameters), so that the ~10^4 kernel launches of a step replay from four graph launches instead of
         being issued one by one from Python; the batch shape is then fixed.  BatchNorm statistics, the losses, the gradient
-        all-reduce and Adam are unchanged."""
+        all-reduce and Adam are unchanged.  ``desc_loss``: "infonce" = the descriptor loss of the reference's training script
+        (src/train.py:8 imports ``infonce`` under the name ``descriptor_loss_sparse``), "hinge" = the older
+        ``descriptor_loss_sparse`` of src/utils/loss_functions.py:361-481 (same sampled pairs, same similarities)."""
+        if desc_loss not in ("infonce", "hinge"):
+            raise ValueError(f"desc_loss={desc_loss!r}: expected 'infonce' or 'hinge'")
+        self.desc_loss = Lz.infonce if desc_loss == "infonce" else Lz.descriptor_loss_sparse
         self.model = model
         self.device = next(model.parameters()).device
         if self.device.type == "cuda":
@@ -187,7 +192,7 @@ class TrainStep:
         loss_obj, items = self.obj_loss(obj, sample["box_labels"], built)
         loss_det = self.det_loss(semi, lab, msk)
         loss_det_w = self.det_loss(semi_w, lab_w, msk_w)
-        loss_desc = Lz.descriptor_loss_sparse(desc, desc_w, sample["warped_valid_mask"], sample["inv_homographies"], pairs=pairs, **self.sparse_cfg)
+        loss_desc = self.desc_loss(desc, desc_w, sample["warped_valid_mask"], sample["inv_homographies"], pairs=pairs, **self.sparse_cfg)
         loss = loss_det + loss_det_w + LAMBDA_DESC * loss_desc + LAMBDA_OBJ * loss_obj
         return loss, dict(det=loss_det.detach(), det_warp=loss_det_w.detach(), desc=loss_desc.detach(), obj=loss_obj.detach())
 
