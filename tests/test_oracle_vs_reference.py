@@ -192,3 +192,11 @@ def test_compat_install_switches_the_reference_seam(ns):
     finally:
         compat.uninstall()
     assert ru.nms_fast is ns.nms_fast and demo.PointTracker is ns.PointTracker
+    import utils.loss_functions as rl
+    ref_infonce = rl.infonce
+    done = compat.install(losses=True)
+    try:
+        assert "utils.loss_functions.infonce" in done and rl.infonce is yp.losses.infonce and ru.getMasks is yp.losses.getMasks
+    finally:
+        compat.uninstall()
+    assert rl.infonce is ref_infonce

@@ -31,12 +31,33 @@ BINDINGS: Dict[str, Dict[str, str]] = {
 }
 
 
-def install(modules=None) -> List[str]:
+# training-side names (src/train.py:7-8, 12-13): opt-in, the inference switch does not need them
+LOSS_BINDINGS: Dict[str, Dict[str, str]] = {
+    "utils.loss_functions": {"ComputeObjectLoss": "losses.ComputeObjectLoss", "ComputeDetectorLoss": "losses.ComputeDetectorLoss",
+                             "infonce": "losses.infonce", "descriptor_loss_sparse": "losses.descriptor_loss_sparse"},
+    "utils.utils": {"labels2Dto3D": "losses.labels2Dto3D", "getMasks": "losses.getMasks"},
+}
+
+
+def _resolve(root, dotted: str):
+    obj = root
+    for part in dotted.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+def install(modules=None, losses: bool = False) -> List[str]:
     """Rebind the hot-path names of the (importable) reference modules to their yolopoint_b200 counterparts.  Modules that cannot be
-    imported in this environment (missing optional dependencies of the reference) are skipped.  Returns the rebound names."""
+    imported in this environment (missing optional dependencies of the reference) are skipped.  ``losses=True`` also rebinds the
+    training losses / target helpers.  Returns the rebound names."""
     import yolopoint_b200 as yp
+    from . import losses as _losses  # noqa: F401  (makes yp.losses resolvable)
     done = []
-    for mod_name, names in BINDINGS.items():
+    table = {k: dict(v) for k, v in BINDINGS.items()}
+    if losses:
+        for k, v in LOSS_BINDINGS.items():
+            table.setdefault(k, {}).update(v)
+    for mod_name, names in table.items():
         if modules is not None and mod_name not in modules:
             continue
         try:
@@ -46,7 +67,7 @@ def install(modules=None) -> List[str]:
         for attr, ours in names.items():
             if hasattr(mod, attr):
                 _SAVED.append((mod, attr, getattr(mod, attr)))
-                setattr(mod, attr, getattr(yp, ours))
+                setattr(mod, attr, _resolve(yp, ours))
                 done.append(f"{mod_name}.{attr}")
     return done
 
