@@ -69,3 +69,27 @@ def test_infonce_matches_reference_statistically(golden):
     pos, neg = Lz._pair_similarities(d1, d2, pairs)
     want = -torch.log_softmax(torch.cat((pos[:, None], neg.t()), 1) / 0.07, 1)[:, 0].mean()
     assert abs(float(loss) - float(want)) < 1e-6 and float(a.grad.abs().sum()) > 0 and float(b.grad.abs().sum()) > 0
+
+
+def test_train_step_options_on_cpu():
+    """TrainStep wiring on the CPU (plain PyTorch convolutions): both descriptor losses, the optional gradient clipping of
+    src/train.py:249-250 (total gradient norm <= max_norm before Adam), and rejection of an unknown loss name."""
+    import pytest
+    from yolopoint_b200 import Model
+    from yolopoint_b200.trainer import TrainStep, synthetic_sample
+    smp = synthetic_sample(2, 64, 96, 3)
+    cfg = dict(num_samples_per_image=40, num_masked_non_matches_per_match=10)
+    vals = {}
+    for name in ("infonce", "hinge"):
+        torch.manual_seed(0)
+        m = Model(names=[str(i) for i in range(80)], version="n").train()
+        ts = TrainStep(m, sparse_cfg=cfg, desc_loss=name, gradclip=0.5)
+        torch.manual_seed(5)
+        _, parts = ts.losses(smp)
+        vals[name] = float(parts["desc"])
+        torch.manual_seed(5)
+        assert np.isfinite(float(ts.step(smp)))
+        assert float(ts.reducer.flat.norm()) <= 0.5 * 1.001
+    assert vals["infonce"] > 1.5 and vals["hinge"] < 1.5           # ln(1 + 10) = 2.4 at random init vs a hinge of order 1
+    with pytest.raises(ValueError):
+        TrainStep(m, desc_loss="triplet")

@@ -121,7 +121,8 @@ class _FlatOutputs(torch.nn.Module):
 
 class TrainStep:
     def __init__(self, model, epochs: int = 100, lr: float = 1e-3, lrf: float = 0.01, sparse_cfg: Optional[dict] = None, group=None,
-                 bucket_bytes: int = 32 << 20, graph_sample: Optional[torch.Tensor] = None, desc_loss: str = "infonce"):
+                 bucket_bytes: int = 32 << 20, graph_sample: Optional[torch.Tensor] = None, desc_loss: str = "infonce",
+                 gradclip: Optional[float] = None):
         """``graph_sample``: an image batch [B,3,H,W] on the model's device.  When given, the two forward passes of a step and
         their backward passes are captured into CUDA graphs (torch.cuda.make_graphed_callables: one forward + one backward graph
         per pass, shared parameters), so that the ~10^4 kernel launches of a step replay from four graph launches instead of
@@ -132,6 +133,7 @@ class TrainStep:
         if desc_loss not in ("infonce", "hinge"):
             raise ValueError(f"desc_loss={desc_loss!r}: expected 'infonce' or 'hinge'")
         self.desc_loss = Lz.infonce if desc_loss == "infonce" else Lz.descriptor_loss_sparse
+        self.gradclip = gradclip                # src/train.py:249-250: clip_grad_norm_ on the (averaged) gradients before the optimizer step
         self.model = model
         self.device = next(model.parameters()).device
         if self.device.type == "cuda":
@@ -205,5 +207,7 @@ class TrainStep:
         loss, _ = self.losses(sample)
         loss.backward()
         self.reducer.finish()
+        if self.gradclip:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.gradclip)
         self.opt.step()
         return loss.detach()
