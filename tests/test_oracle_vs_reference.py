@@ -200,3 +200,30 @@ def test_compat_install_switches_the_reference_seam(ns):
     finally:
         compat.uninstall()
     assert rl.infonce is ref_infonce
+
+
+def test_tracker_evaluation_variant(ns, capsys):
+    """The tracker of src/models/model_wrap.py:410-597 (export_descriptor.py uses it with max_length 2): same tracks, plus get_matches()
+    (raw rows for the first pair, then matched coordinates) and clear_desc()."""
+    import contextlib
+    import io
+    import models.model_wrap as mw
+    import yolopoint_b200 as yp
+    from oracle.make_golden import tracker_sequence
+    ref, ours = mw.PointTracker(max_length=2, nn_thresh=0.7), yp.PointTracker(max_length=2, nn_thresh=0.7)
+    for f, (p, d) in enumerate(tracker_sequence(seed=7, frames=7, n0=80, D=16)):
+        m = None
+        if p is not None:
+            prev = ref.last_desc if ref.last_desc is not None else np.zeros((d.shape[0], 0))
+            m = O.nn_match_two_way(prev, d, 0.7)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref.update(p, d)
+        ours.update(p, d, matches=m)
+        np.testing.assert_array_equal(ours.tracks, ref.tracks)
+        if p is not None:
+            np.testing.assert_array_equal(ours.get_matches(), ref.get_matches())
+        if f == 4:
+            ref.clear_desc()
+            ours.clear_desc()
+    np.testing.assert_array_equal(ours.get_mscores(), ref.get_mscores())
+    capsys.readouterr()

@@ -27,6 +27,7 @@ BINDINGS: Dict[str, Dict[str, str]] = {
                     "nms_fast": "nms_fast"},
     "utils.general_yolo": {"non_max_suppression": "non_max_suppression"},
     "evaluations.descriptor_evaluation": {"sample_desc_from_points": "sample_desc_from_points"},
+    "models.model_wrap": {"PointTracker": "PointTracker"},
     "demo": {"PointTracker": "PointTracker", "non_max_suppression": "non_max_suppression", "nms_fast": "nms_fast"},
 }
 

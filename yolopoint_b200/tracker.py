@@ -35,6 +35,10 @@ class PointTracker:
         self.tracks = np.zeros((0, self.maxl + 2))
         self.track_count = 0
         self.max_score = MAX_SCORE
+        # state of the evaluation variant of the tracker (src/models/model_wrap.py:410-432, used by src/export_descriptor.py:72-132)
+        self.matches = None
+        self.last_pts = None
+        self.mscores = None
 
     @staticmethod
     def nn_match_two_way(desc1, desc2, nn_thresh):
@@ -45,6 +49,19 @@ class PointTracker:
         """Start of every stored frame in the concatenated point numbering (the newest frame's size is not needed)."""
         sizes = [0] + [p.shape[1] for p in self.all_pts[:-1]]
         return np.cumsum(np.array(sizes))
+
+    def get_matches(self):
+        """src/models/model_wrap.py:494: after ``update``: the [3,L] match rows of the first frame pair, afterwards the [4,L]
+        coordinates (x1, y1, x2, y2) of the matched points in the previous / current frame."""
+        return self.matches
+
+    def get_mscores(self):
+        """The raw [3,L] match rows (index in the previous frame, index in this frame, score) of the last update."""
+        return self.mscores
+
+    def clear_desc(self):
+        """src/models/model_wrap.py:500: forget the previous descriptors (the next update starts new tracks only)."""
+        self.last_desc = None
 
     def update(self, pts, desc, matches: Optional[np.ndarray] = None):
         """Add the observations of a new frame: pts [3,N] (x, y, conf), desc [D,N].  ``matches`` ([3,L] rows (index in the previous
@@ -67,6 +84,9 @@ class PointTracker:
         if matches is None:
             matches = self.nn_match_two_way(self.last_desc, desc, self.nn_thresh)
         matches = np.asarray(matches, dtype=np.float64).reshape(3, -1)
+        self.matches = self.mscores = matches            # model_wrap.py:475 keeps the raw [3,L] rows (with scores) as ``mscores``
+        if self.last_pts is not None:                       # src/models/model_wrap.py:536-541
+            self.matches = np.concatenate((self.last_pts[:, matches[0].astype(int)], pts[:2, matches[1].astype(int)]), axis=0)
         N = pts.shape[1]
         matched = np.zeros(N, dtype=bool)
         if matches.shape[1] and T:
@@ -98,6 +118,7 @@ class PointTracker:
         self.track_count += new_ids.shape[0]
         self.tracks = tracks[np.any(tracks[:, 2:] >= 0, axis=1), :]
         self.last_desc = desc.copy()
+        self.last_pts = pts[:2, :].copy()
 
     def get_tracks(self, min_length):
         """Tracks with at least ``min_length`` observations and one in the newest frame ([M, 2 + maxl] copy)."""
