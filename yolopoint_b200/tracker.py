@@ -84,7 +84,9 @@ class PointTracker:
         if matches is None:
             matches = self.nn_match_two_way(self.last_desc, desc, self.nn_thresh)
         matches = np.asarray(matches, dtype=np.float64).reshape(3, -1)
-        self.matches = self.mscores = matches            # model_wrap.py:475 keeps the raw [3,L] rows (with scores) as ``mscores``
+        self.matches = matches
+        if self.last_desc.shape[1] and desc.shape[1]:     # model_wrap.py:475 keeps the raw [3,L] rows of the last non-trivial match
+            self.mscores = matches
         if self.last_pts is not None:                       # src/models/model_wrap.py:536-541
             self.matches = np.concatenate((self.last_pts[:, matches[0].astype(int)], pts[:2, matches[1].astype(int)]), axis=0)
         N = pts.shape[1]
