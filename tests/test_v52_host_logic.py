@@ -156,3 +156,22 @@ def test_fuse_partial_load_and_cpu_training_path():
     assert "model.BottleneckDet.cv2.conv.bias" in keys and not any(".bn." in k for k in keys)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 64, 64))      # eval-mode inference on CPU must fail loudly
+
+
+def test_synthetic_weights_and_tuning_tables_are_model_specific():
+    """perturb_state_dict detects the v52 key set (no ConvDet) and peaks the keypoint logits through BottleneckDet.cv2's BN weight;
+    tuning tables of the two model families never alias (a YOLOPoint table names layers of other shapes)."""
+    from yolopoint_b200.engine import load_tuning, tuning_path
+    from yolopoint_b200.synth import TUNING, TUNING_V52, V52_SEMI_GAIN
+    torch.manual_seed(0)
+    sd = Model(names=NAMES, version="n", model_name=V52).state_dict()
+    a, b = perturb_state_dict(sd, 0, "n"), perturb_state_dict(sd, 0, "n")
+    assert all(torch.equal(a[k], b[k]) for k in a)                                   # deterministic
+    plain = perturb_state_dict(sd, 0, "n", semi_gain=1.0)
+    k = "model.BottleneckDet.cv2.bn.weight"
+    assert torch.allclose(a[k], plain[k] * V52_SEMI_GAIN) and all(torch.equal(a[j], plain[j]) for j in a if j != k)
+    assert TUNING_V52["n"] != TUNING["n"] and TUNING_V52["m"] == TUNING["m"]
+    p5, p52 = tuning_path("s", 1, 640, 640, "fp32"), tuning_path("s", 1, 640, 640, "fp32", V52)
+    assert p5 != p52 and p52.endswith("v52s_1x640x640_fp32.json")
+    assert load_tuning("s", 1, 640, 640, "fp32", V52) == {}                          # no table yet: library heuristics
+    assert len(load_tuning("s", 1, 640, 640, "fp32")) > 0
