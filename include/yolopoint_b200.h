@@ -207,8 +207,13 @@ int yp_detect_decode(const float* logits, int32_t B, int32_t ny, int32_t nx, int
  * (class_mask: 32-bit words, bit c set = keep class c; NULL = all); stable sort by conf desc, cap max_nms;
  * greedy IoU (> iou_thres suppresses; boxes offset by cls*max_wh unless agnostic); cap max_det.
  * out_boxes [B,max_det,6] (x1,y1,x2,y2,conf,cls), out_count int32 [B].
- * workspace: yp_box_nms_workspace_bytes(B, A, no, cap) bytes; cap = per-image candidate capacity
- * (candidates beyond cap set out_count[b] = -1 - n_candidates so the caller can detect overflow).
+ * workspace: yp_box_nms_workspace_bytes(B, A, no, cap) bytes (~(2A + 7 cap) * 4 B per image; no n x n matrix);
+ * cap = per-image candidate capacity, a multiple of 64.  With cap >= max_nms (e.g. 30016 for the reference's 30000) ANY
+ * number of candidates is handled the way the reference does: the max_nms most confident are kept (exact radix select,
+ * ties in candidate order) and the call never reports overflow.  Only with cap < max_nms can a frame overflow; then
+ * out_count[b] = -1 - n_candidates so that the caller can grow cap.  The first 4 int32 per image of the workspace hold
+ * statistics of the last call: rows passing objectness, candidates found, candidates that entered the NMS, path
+ * (0 = shared memory, 1 = workspace arrays, 2 = top-max_nms select, 3 = overflow reported).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   float conf_thres, iou_thres;

@@ -151,7 +151,7 @@ def test_frame_pipeline_vs_golden(golden):
     H = W = 640
     g = golden("e2e_v52s_640x640.npz")
     m, _ = build("s")
-    pipe = FramePipeline(m, 1, H, W, max_pts=4096, nms_cap=4096)
+    pipe = FramePipeline(m, 1, H, W)
     res = [pipe.step_host(synthetic_frame(H, W, s)[None])[0] for s in (0, 1)]
     for i, (pts, desc, boxes, matches) in enumerate(res):
         rp, rd, rb = g[f"pts{i}"], g[f"desc{i}"], g[f"boxes{i}"]

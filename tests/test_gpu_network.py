@@ -123,7 +123,7 @@ def test_frame_pipeline_vs_golden(golden, ver, H, W):
     """Whole-frame pipeline from uint8 frames (host buffers) against what the unmodified reference produced."""
     g = golden(f"e2e_{ver}_{H}x{W}.npz")
     m, _ = build(ver)
-    pipe = FramePipeline(m, 1, H, W, max_pts=4096, nms_cap=4096)
+    pipe = FramePipeline(m, 1, H, W)
     res = [pipe.step_host(synthetic_frame(H, W, s)[None])[0] for s in (0, 1)]
     for i, (pts, desc, boxes, matches) in enumerate(res):
         rp, rd, rb = g[f"pts{i}"], g[f"desc{i}"], g[f"boxes{i}"]

@@ -18,7 +18,7 @@ from yolopoint_b200.synth import synthetic_frame  # noqa: E402
 
 model, sd = bench.build_weights("s")
 model = model.cuda().eval()
-pipe = FramePipeline(model, 1, 640, 640, max_pts=4096, nms_cap=4096)
+pipe = FramePipeline(model, 1, 640, 640)
 for s in range(3):
     pipe.step_host(synthetic_frame(640, 640, s)[None])
 L, p = _lib.lib(), pipe.plan
@@ -36,8 +36,8 @@ def stage_nms():
     ldc = (C.c_int32 * 3)(*[d.shape[4] for d in dets])
     strd = (C.c_float * 3)(*[float(v) for v in pipe.eng.stride])
     anc = (C.c_float * 18)(*[float(v) for row in pipe.eng.anchors_px for v in row])
-    _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, pipe.eng.net.no, C.byref(pipe.nms_params), pipe.nms_cap, pipe.boxes.data_ptr(),
-                               pipe.bcount.data_ptr(), pipe.ws_nms.data_ptr(), pipe.ws_nms.numel(), st()))
+    _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, pipe.eng.net.no, C.byref(pipe.nms_params), pipe.nms_cap, pipe.boxes[0].data_ptr(),
+                               pipe.bcount[0].data_ptr(), pipe.ws_nms.data_ptr(), pipe.ws_nms.numel(), st()))
 
 
 def stage_heat_kpnms():
@@ -65,5 +65,5 @@ def time_graph(fn, reps=20):
     return best
 
 
-for name, fn in (("Detect decode + box NMS (5 kernels)", stage_nms), ("heatmap + keypoint NMS rounds (side lane)", stage_heat_kpnms)):
+for name, fn in (("Detect decode + box NMS (1 kernel)", stage_nms), ("heatmap + keypoint NMS rounds (side lane)", stage_heat_kpnms)):
     print(f"{name:45s} {time_graph(fn):8.2f} us")

@@ -57,20 +57,18 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     src_dev = prediction.device if isinstance(prediction, torch.Tensor) else torch.device("cpu")
     pred = _to_dev(prediction)
     B, A, no = pred.shape
-    cap = cap or 4096
+    cap = cap or 30016   # >= the reference's max_nms = 30000: the kernel then handles any candidate count like the reference does
     while True:
         boxes, count = ops.box_nms(pred, conf_thres, iou_thres, multi_label, agnostic, max_det, classes, cap=cap)
         cnt = count.cpu().numpy()
         if (cnt >= 0).all():
             break
-        # a candidate list overflowed: grow to what the kernel reported (up to max_nms, like the reference) and redo
+        # only reachable with an explicit cap < max_nms: grow to what the kernel reported and redo (never truncate silently)
         need = int((-1 - cnt[cnt < 0]).max())
-        if cap >= 30016:
-            break  # more than max_nms candidates: the reference keeps the 30000 best; see DESIGN.md (known limit)
         cap = min(30016, max(2 * cap, (need + 63) // 64 * 64))
     out = []
     for b in range(B):
-        n = int(cnt[b]) if cnt[b] >= 0 else max_det
+        n = int(cnt[b])
         out.append(boxes[b, :n].clone().to(src_dev) if src_dev.type == "cuda" else boxes[b, :n].cpu())
     return out
 

@@ -78,286 +78,375 @@ __global__ void __launch_bounds__(256) detect_decode_kernel(const DecodeArgs a, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// NMS stage 1: candidates.  One warp per prediction row.
+// Box NMS: ONE kernel, one 1024-thread CTA per image (general_yolo.py:124-235 + torchvision.ops.nms).
+//
+//   A  scan the objectness of all A rows, list the rows with obj > conf_thres            (general_yolo.py:146, 168)
+//   B  evaluate conf = cls * obj of the listed rows, one (row, class) pair per thread step; every candidate is ONE 64-bit key
+//      (conf bits << 32 | ~ord), ord = row * nc + class = the reference's row-major (box, class) order   (:184-196)
+//   C  more candidates than the buffer holds (cap >= max_nms): exact radix select of the max_nms largest keys over re-scans of
+//      the listed rows -- the reference's `argsort(descending=True)[:max_nms]` (:210-211), never an error
+//   D  bitonic sort of the keys, descending = confidence descending, ties in candidate order  (:211-213)
+//   E  boxes of the sorted candidates are re-derived from their rows (+ class offset unless agnostic, :216-217)
+//   F  greedy suppression in chunks of 64 sorted boxes: the chunk's 64 x 64 IoU bits, a sequential resolve of the chunk by one
+//      thread, then the chunk's kept boxes clear all later boxes in parallel.  IoU work is kept x n instead of n^2 / 2 and no
+//      n x n bit matrix exists, so 30 000 candidates need 1 MB of scratch, not 113 MB.
+//
+// Up to kSmemCap candidates everything lives in shared memory (the usual frame: 10^2..10^3 candidates, ~10 us); beyond that the
+// same code runs on arrays in the caller's workspace (L2).  The five-kernel pipeline this replaces (candidates / counts / rank /
+// mask / scan) cost 77 us of launch + dependency latency per frame and aborted above `cap` candidates.
 // ------------------------------------------------------------------------------------------------
+constexpr int kNmsThreads = 1024;
+constexpr int kSmemCap = 4096;      // candidates whose keys + boxes fit in shared memory
+constexpr int kPassSmem = 4096;     // objectness survivors listed in shared memory (the rest spill to the workspace)
+
 struct NmsWs {
-  int* n_cand;          // [B]  candidates found (may exceed cap); slots are handed out with atomicAdd
-  int* n_sorted;        // [B]  min(n_cand, cap, max_nms)
-  unsigned int* ord;    // [B][cap]  position of the candidate in the reference's row-major (box, class) order
-  float* cand;          // [B][cap][6]  x1,y1,x2,y2,conf,cls in arbitrary (slot) order
-  float* sorted;        // [B][cap][6]  confidence-descending (stable)
-  unsigned long long* mask;  // [B][cap][cap/64]
+  int* stats;                  // [B][4]  rows passing objectness, candidates found, candidates sorted, path (0 smem, 1 workspace, 2 select)
+  unsigned int* pass_row;      // [B][A]
+  float* pass_obj;             // [B][A]
+  unsigned long long* key;     // [B][cap_p2]
+  float4* box;                 // [B][cap]   NMS boxes (class offset applied) in sorted order
+  unsigned long long* removed; // [B][cap_p2 / 64]
 };
 
 __device__ __forceinline__ bool class_ok(const uint32_t* class_mask, int c) {
   return class_mask == nullptr || ((class_mask[c >> 5] >> (c & 31)) & 1u);
 }
 
-// Candidate emission shared by the two front ends (decoded `pred` rows, or raw Detect logits).
-// x,y,w,h,obj and a class-score accessor cls(c) are already sigmoid-decoded values.
-template <typename ClsFn>
-__device__ __forceinline__ void emit_candidates(float bx, float by, float bw, float bh, float obj, int nc, ClsFn cls, unsigned int row,
-                                                const YpNmsParams& p, int cap, int b, const NmsWs& ws) {
-  auto put = [&](float conf, int c, unsigned int ord) {
-    const int slot = atomicAdd(&ws.n_cand[b], 1);
-    if (slot < cap) {
-      float* o = ws.cand + (static_cast<int64_t>(b) * cap + slot) * 6;
-      o[0] = __fsub_rn(bx, __fdiv_rn(bw, 2.0f)); o[1] = __fsub_rn(by, __fdiv_rn(bh, 2.0f));   // xywh2xyxy, general_yolo.py:623-630
-      o[2] = __fadd_rn(bx, __fdiv_rn(bw, 2.0f)); o[3] = __fadd_rn(by, __fdiv_rn(bh, 2.0f));
-      o[4] = conf; o[5] = static_cast<float>(c);
-      ws.ord[static_cast<int64_t>(b) * cap + slot] = ord;
-    }
-  };
-  if (p.multi_label && nc > 1) {  // one candidate per (row, class) with conf > thr, general_yolo.py:191-193
-    for (int c = 0; c < nc; ++c) {
-      const float conf = __fmul_rn(cls(c), obj);
-      if (conf > p.conf_thres && class_ok(p.class_mask, c)) put(conf, c, row * static_cast<unsigned int>(nc) + c);
-    }
-  } else {                        // best class only (first maximum), general_yolo.py:195-196
-    float best = -INFINITY;
-    int bc = 0;
-    for (int c = 0; c < nc; ++c) {
-      const float conf = __fmul_rn(cls(c), obj);
-      if (conf > best) { best = conf; bc = c; }
-    }
-    if (best > p.conf_thres && class_ok(p.class_mask, bc)) put(best, bc, row);
+__device__ __forceinline__ float sigmoid_rn(float v) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v))); }
+
+// xywh -> xyxy exactly as general_yolo.py:623-630
+__device__ __forceinline__ float4 xywh2xyxy_rn(float bx, float by, float bw, float bh) {
+  return make_float4(__fsub_rn(bx, __fdiv_rn(bw, 2.0f)), __fsub_rn(by, __fdiv_rn(bh, 2.0f)), __fadd_rn(bx, __fdiv_rn(bw, 2.0f)),
+                     __fadd_rn(by, __fdiv_rn(bh, 2.0f)));
+}
+
+// front end 1: decoded predictions [B, A, no]
+struct PredRows {
+  const float* pred;
+  long long A;
+  int no;
+  __device__ __forceinline__ const float* row(int b, unsigned int r) const { return pred + (static_cast<int64_t>(b) * A + r) * no; }
+  __device__ __forceinline__ float obj(int b, unsigned int r) const { return __ldg(row(b, r) + 4); }
+  __device__ __forceinline__ float cls(int b, unsigned int r, int c) const { return __ldg(row(b, r) + 5 + c); }
+  __device__ __forceinline__ float4 box(int b, unsigned int r) const {
+    const float* p = row(b, r);
+    return xywh2xyxy_rn(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
   }
-}
+};
 
-// front end 1: decoded predictions [B,A,no]; one thread per row (objectness survivors are rare)
-__global__ void nms_candidates_pred_kernel(const float* __restrict__ pred, int B, long long A, int no, YpNmsParams p, int cap, NmsWs ws) {
-  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (row >= static_cast<int64_t>(B) * A) return;
-  const int b = static_cast<int>(row / A);
-  const float* r = pred + row * no;
-  const float obj = r[4];
-  if (!(obj > p.conf_thres)) return;  // strict, general_yolo.py:146
-  emit_candidates(r[0], r[1], r[2], r[3], obj, no - 5, [&](int c) { return r[5 + c]; }, static_cast<unsigned int>(row - b * A), p, cap, b, ws);
-}
-
-// front end 2: raw Detect logits of the three levels (NHWC, channel a*no+o): decode (models/yolo.py:60-68) only the rows
-// whose objectness passes, so `pred` is never materialised in the whole-frame pipeline.
+// front end 2: raw Detect logits of the three levels (NHWC, channel a*no+o): decode (models/yolo.py:60-68) only what the NMS
+// looks at, so `pred` is never materialised in the whole-frame pipeline.
 struct DetLevels {
   const float* logits[3];
   int ny[3], nx[3], ldc[3];
   float stride[3];
   float anchor[3][6];
   long long row_off[3];
+  long long A;
   int na, no;
+  __device__ __forceinline__ const float* row(int b, unsigned int r, int* l_, int* an_, int* y_, int* x_) const {
+    const int l = r >= row_off[2] ? 2 : (r >= row_off[1] ? 1 : 0);
+    unsigned int cell = r - static_cast<unsigned int>(row_off[l]);   // (anchor, y, x) order, models/yolo.py:56
+    const int x = cell % nx[l]; cell /= nx[l];
+    const int y = cell % ny[l];
+    const int an = cell / ny[l];
+    *l_ = l; *an_ = an; *y_ = y; *x_ = x;
+    return logits[l] + ((static_cast<int64_t>(b) * ny[l] + y) * nx[l] + x) * ldc[l] + an * no;
+  }
+  __device__ __forceinline__ float obj(int b, unsigned int r) const {
+    int l, an, y, x;
+    return sigmoid_rn(__ldg(row(b, r, &l, &an, &y, &x) + 4));
+  }
+  __device__ __forceinline__ float cls(int b, unsigned int r, int c) const {
+    int l, an, y, x;
+    return sigmoid_rn(__ldg(row(b, r, &l, &an, &y, &x) + 5 + c));
+  }
+  __device__ __forceinline__ float4 box(int b, unsigned int r) const {
+    int l, an, y, x;
+    const float* p = row(b, r, &l, &an, &y, &x);
+    const float sx = sigmoid_rn(__ldg(p)), sy = sigmoid_rn(__ldg(p + 1)), sw = sigmoid_rn(__ldg(p + 2)), sh = sigmoid_rn(__ldg(p + 3));
+    const float bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), static_cast<float>(x)), stride[l]);
+    const float by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), static_cast<float>(y)), stride[l]);
+    const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
+    return xywh2xyxy_rn(bx, by, __fmul_rn(__fmul_rn(tw, tw), anchor[l][an * 2]), __fmul_rn(__fmul_rn(th, th), anchor[l][an * 2 + 1]));
+  }
 };
 
-__device__ __forceinline__ float sigmoid_rn(float v) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v))); }
-
-__global__ void nms_candidates_logits_kernel(const DetLevels lv, int B, long long A, YpNmsParams p, int cap, NmsWs ws) {
-  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (idx >= static_cast<int64_t>(B) * A) return;
-  const int b = static_cast<int>(idx / A);
-  const long long row = idx - b * A;
-  const int l = row >= lv.row_off[2] ? 2 : (row >= lv.row_off[1] ? 1 : 0);
-  const int ny = lv.ny[l], nx = lv.nx[l];
-  long long cell = row - lv.row_off[l];                 // (anchor, y, x) order, models/yolo.py:56
-  const int x = static_cast<int>(cell % nx); cell /= nx;
-  const int y = static_cast<int>(cell % ny);
-  const int an = static_cast<int>(cell / ny);
-  const float* r = lv.logits[l] + ((static_cast<int64_t>(b) * ny + y) * nx + x) * lv.ldc[l] + an * lv.no;
-  const float obj = sigmoid_rn(r[4]);
-  if (!(obj > p.conf_thres)) return;
-  const float sx = sigmoid_rn(r[0]), sy = sigmoid_rn(r[1]), sw = sigmoid_rn(r[2]), sh = sigmoid_rn(r[3]);
-  const float bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), static_cast<float>(x)), lv.stride[l]);
-  const float by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), static_cast<float>(y)), lv.stride[l]);
-  const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
-  const float bw = __fmul_rn(__fmul_rn(tw, tw), lv.anchor[l][an * 2]);
-  const float bh = __fmul_rn(__fmul_rn(th, th), lv.anchor[l][an * 2 + 1]);
-  emit_candidates(bx, by, bw, bh, obj, lv.no - 5, [&](int c) { return sigmoid_rn(r[5 + c]); }, static_cast<unsigned int>(row), p, cap, b, ws);
-}
-
-__global__ void nms_counts_kernel(int B, int cap, int max_nms, NmsWs ws) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int n = min(ws.n_cand[b], cap);
-  ws.n_sorted[b] = min(n, max_nms);
-}
-
-// descending rank sort, ties in the reference's candidate order: rank(i) = #{j : conf_j > conf_i or (conf_j == conf_i and ord_j < ord_i)}
-__global__ void nms_rank_kernel(int cap, NmsWs ws) {
-  __shared__ float tile[256];
-  __shared__ unsigned int tord[256];
-  const int b = blockIdx.y;
-  const int n = min(ws.n_cand[b], cap);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x * blockDim.x >= n) return;
-  const float* cand = ws.cand + static_cast<int64_t>(b) * cap * 6;
-  const unsigned int* ord = ws.ord + static_cast<int64_t>(b) * cap;
-  const float ci = i < n ? cand[i * 6 + 4] : 0.0f;
-  const unsigned int oi = i < n ? ord[i] : 0u;
-  int rank = 0;
-  for (int j0 = 0; j0 < n; j0 += 256) {
-    const int j = j0 + threadIdx.x;
-    tile[threadIdx.x] = j < n ? cand[j * 6 + 4] : -INFINITY;
-    tord[threadIdx.x] = j < n ? ord[j] : 0xffffffffu;
-    __syncthreads();
-    const int lim = min(256, n - j0);
-    for (int k = 0; k < lim; ++k) {
-      const float cj = tile[k];
-      rank += (cj > ci || (cj == ci && tord[k] < oi)) ? 1 : 0;
-    }
-    __syncthreads();
-  }
-  if (i < n && rank < ws.n_sorted[b]) {
-    float* o = ws.sorted + (static_cast<int64_t>(b) * cap + rank) * 6;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) o[k] = cand[i * 6 + k];
-  }
-}
-
-// torchvision nms_kernel semantics: suppress j (> i in sorted order) iff inter / (area_i + area_j - inter) > thr
-__device__ __forceinline__ bool iou_gt(const float* a, const float* b, float thr) {
-  const float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
-  const float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
-  const float w = fmaxf(__fsub_rn(right, left), 0.0f), h = fmaxf(__fsub_rn(bottom, top), 0.0f);
+// torchvision nms_kernel semantics: suppress j (after i in sorted order) iff inter / (area_i + area_j - inter) > thr.
+// inter == 0 can never exceed thr >= 0 (0 / x is 0, -0 or NaN), so disjoint pairs skip the division.
+__device__ __forceinline__ bool iou_gt(const float4& a, const float4& b, float thr) {
+  const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+  const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+  if (!(w > 0.0f && h > 0.0f)) return false;
   const float inter = __fmul_rn(w, h);
-  const float sa = __fmul_rn(__fsub_rn(a[2], a[0]), __fsub_rn(a[3], a[1]));
-  const float sb = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
+  const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
 }
 
-// 64x64 blocks of the upper-triangular suppression bit matrix; persistent over block pairs
-__global__ void nms_mask_kernel(int cap, float iou_thres, int agnostic, float max_wh, NmsWs ws) {
-  __shared__ float colbox[64][4];
-  const int b = blockIdx.y;
-  const int n = ws.n_sorted[b];
-  const int nb = (n + 63) >> 6;
-  const int words = cap >> 6;
-  const float* sorted = ws.sorted + static_cast<int64_t>(b) * cap * 6;
-  unsigned long long* mask = ws.mask + static_cast<int64_t>(b) * cap * words;
-  for (int t = blockIdx.x; t < nb * nb; t += gridDim.x) {
-    const int rb = t / nb, cb = t - rb * nb;
-    if (cb < rb) continue;
-    __syncthreads();
-    {
-      const int j = cb * 64 + threadIdx.x;
-      if (j < n) {
-        const float off = agnostic ? 0.0f : __fmul_rn(sorted[j * 6 + 5], max_wh);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) colbox[threadIdx.x][k] = __fadd_rn(sorted[j * 6 + k], off);
-      }
-    }
-    __syncthreads();
-    const int i = rb * 64 + threadIdx.x;
-    if (i < n) {
-      float me[4];
-      const float off = agnostic ? 0.0f : __fmul_rn(sorted[i * 6 + 5], max_wh);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) me[k] = __fadd_rn(sorted[i * 6 + k], off);
-      unsigned long long bits = 0;
-      const int lim = min(64, n - cb * 64);
-      const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-      for (int k = start; k < lim; ++k)
-        if (iou_gt(me, colbox[k], iou_thres)) bits |= 1ull << k;
-      mask[static_cast<int64_t>(i) * words + cb] = bits;
-    }
-  }
+__device__ __forceinline__ unsigned long long cand_key(float conf, unsigned int ord) {
+  return (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xffffffffu - ord);   // conf > 0: bits are monotone
 }
 
-// ordered scan over the bit matrix; one block per image.  The upper-triangular part of the matrix that the scan touches
-// (n rows x ceil(n/64) words) is staged in shared memory when it fits, the 64-step dependent scan of a chunk runs in one
-// warp on registers (diagonal words exchanged by shuffles), and the suppression rows of the kept boxes are folded in
-// parallel.
-constexpr int kScanSmemBytes = 160 * 1024;
+struct NmsSmem {
+  unsigned int pass_row[kPassSmem];
+  float pass_obj[kPassSmem];
+  unsigned long long key[kSmemCap];
+  float4 box[kSmemCap];
+  unsigned long long removed[kSmemCap / 64];
+  unsigned long long diag[64];
+  float4 kbox[64];
+  unsigned int hist[256];
+  unsigned long long keep_bits, prefix;
+  int n_pass, n_emit, n_keep, k_rem;
+};
 
-__global__ void __launch_bounds__(256) nms_scan_keep_kernel(int cap, int max_det, NmsWs ws, float* __restrict__ out_boxes, int* __restrict__ out_count,
-                                                            int stage_words) {
-  extern __shared__ unsigned long long scan_smem[];   // removed[cap/64] then (optionally) the staged matrix
-  __shared__ unsigned long long keep_bits;
-  __shared__ int n_keep;
-  const int b = blockIdx.x;
-  const int n = ws.n_sorted[b];
-  const int nb = (n + 63) >> 6;
-  const int words = cap >> 6;
-  unsigned long long* removed = scan_smem;
-  unsigned long long* staged = scan_smem + words;
-  const bool in_smem = static_cast<long long>(n) * nb <= stage_words;
-  const float* sorted = ws.sorted + static_cast<int64_t>(b) * cap * 6;
-  const unsigned long long* mask = ws.mask + static_cast<int64_t>(b) * cap * words;
-  float* out = out_boxes + static_cast<int64_t>(b) * max_det * 6;
-  for (int w = threadIdx.x; w < nb; w += blockDim.x) removed[w] = 0;
-  if (in_smem)
-    for (int t = threadIdx.x; t < n * nb; t += blockDim.x) {
-      const int i = t / nb, w = t - i * nb;
-      staged[t] = w >= (i >> 6) ? mask[static_cast<int64_t>(i) * words + w] : 0ull;   // words left of the diagonal are never written
-    }
-  if (threadIdx.x == 0) n_keep = 0;
+template <class FE>
+__global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, int B, YpNmsParams p, int cap, int cap_p2, NmsWs ws,
+                                                                 float* __restrict__ out_boxes, int* __restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char nms_smem_raw[];
+  NmsSmem& sm = *reinterpret_cast<NmsSmem*>(nms_smem_raw);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int A = static_cast<int>(fe.A), nc = fe.no - 5;
+  const bool multi = p.multi_label && nc > 1;
+  unsigned int* g_pass_row = ws.pass_row + static_cast<int64_t>(b) * A;
+  float* g_pass_obj = ws.pass_obj + static_cast<int64_t>(b) * A;
+  if (tid == 0) { sm.n_pass = 0; sm.n_emit = 0; sm.n_keep = 0; }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // the logits are the previous kernels' output
   __syncthreads();
-  auto row_word = [&](int i, int w) -> unsigned long long {
-    return in_smem ? staged[i * nb + w] : mask[static_cast<int64_t>(i) * words + w];
-  };
-  for (int wc = 0; wc < nb; ++wc) {
-    if (n_keep >= max_det) break;  // uniform: n_keep only changes between barriers
-    const int lim = min(64, n - wc * 64);
-    const int base = n_keep;
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      const unsigned long long d0 = lane < lim ? row_word(wc * 64 + lane, wc) : 0ull;
-      const unsigned long long d1 = lane + 32 < lim ? row_word(wc * 64 + 32 + lane, wc) : 0ull;
-      unsigned long long rem = removed[wc], kb = 0;
-      int nk = base;
-      for (int k = 0; k < lim && nk < max_det; ++k) {
-        const unsigned long long dk = __shfl_sync(0xffffffffu, k < 32 ? d0 : d1, k & 31);
-        if (!((rem >> k) & 1ull)) { kb |= 1ull << k; rem |= dk; ++nk; }
-      }
-      if (lane == 0) keep_bits = kb;
-    }
-    __syncthreads();
-    const unsigned long long kb = keep_bits;
-    if (threadIdx.x < 64 && ((kb >> threadIdx.x) & 1ull)) {   // kept rows, in order
-      const int pos = base + __popcll(kb & ((1ull << threadIdx.x) - 1ull));
-      const float* sr = sorted + static_cast<int64_t>(wc * 64 + threadIdx.x) * 6;
+
+  // ---- A: objectness scan (strict >, general_yolo.py:146)
+  for (int r0 = tid; r0 < A; r0 += 4 * kNmsThreads) {
+    float o[4];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) out[pos * 6 + k] = sr[k];
-    }
-    // fold the suppression rows of the kept boxes into `removed`: one (row, word) pair per thread
-    const int later = nb - (wc + 1);
-    for (int t = threadIdx.x; t < 64 * later; t += blockDim.x) {
-      const int k = t / later, w = wc + 1 + (t - k * later);
-      if ((kb >> k) & 1ull) {
-        const unsigned long long m = row_word(wc * 64 + k, w);
-        if (m) atomicOr(&removed[w], m);
+    for (int u = 0; u < 4; ++u) { const int r = r0 + u * kNmsThreads; o[u] = r < A ? fe.obj(b, r) : -1.0f; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (o[u] > p.conf_thres) {
+        const int slot = atomicAdd(&sm.n_pass, 1);
+        const unsigned int r = r0 + u * kNmsThreads;
+        if (slot < kPassSmem) { sm.pass_row[slot] = r; sm.pass_obj[slot] = o[u]; }
+        else { g_pass_row[slot] = r; g_pass_obj[slot] = o[u]; }
       }
     }
+  }
+  __syncthreads();
+  const int n_pass = sm.n_pass;
+  auto pass_row = [&](int i) { return i < kPassSmem ? sm.pass_row[i] : g_pass_row[i]; };
+  auto pass_obj = [&](int i) { return i < kPassSmem ? sm.pass_obj[i] : g_pass_obj[i]; };
+
+  // ---- B: candidates.  f(key) is called once per candidate (any order).
+  auto for_each_candidate = [&](auto&& f) {
+    if (multi) {  // one candidate per (row, class) with conf > thr, general_yolo.py:191-193
+      const int total = n_pass * nc;
+      for (int idx = tid; idx < total; idx += kNmsThreads) {
+        const int pi = idx / nc, c = idx - pi * nc;
+        const unsigned int r = pass_row(pi);
+        const float conf = __fmul_rn(fe.cls(b, r, c), pass_obj(pi));
+        if (conf > p.conf_thres && class_ok(p.class_mask, c)) f(cand_key(conf, r * static_cast<unsigned int>(nc) + c));
+      }
+    } else {      // best class only (first maximum), general_yolo.py:195-196
+      for (int pi = tid; pi < n_pass; pi += kNmsThreads) {
+        const unsigned int r = pass_row(pi);
+        const float obj = pass_obj(pi);
+        float best = -INFINITY;
+        int bc = 0;
+        for (int c = 0; c < nc; ++c) {
+          const float conf = __fmul_rn(fe.cls(b, r, c), obj);
+          if (conf > best) { best = conf; bc = c; }
+        }
+        if (best > p.conf_thres && class_ok(p.class_mask, bc)) f(cand_key(best, r * static_cast<unsigned int>(nc) + bc));
+      }
+    }
+  };
+  unsigned long long* g_key = ws.key + static_cast<int64_t>(b) * cap_p2;
+  for_each_candidate([&](unsigned long long k) {
+    const int slot = atomicAdd(&sm.n_emit, 1);
+    if (slot < kSmemCap) sm.key[slot] = k;
+  });
+  __syncthreads();
+  const int n_cand = sm.n_emit;
+  int path = 0, n = n_cand;
+  unsigned long long* key = sm.key;
+  float4* box = sm.box;
+  unsigned long long* removed = sm.removed;
+  if (n_cand > kSmemCap) {
+    key = g_key; box = ws.box + static_cast<int64_t>(b) * cap; removed = ws.removed + static_cast<int64_t>(b) * (cap_p2 / 64);
     __syncthreads();
-    if (threadIdx.x == 0) n_keep = base + __popcll(kb);
+    if (tid == 0) sm.n_emit = 0;
+    __syncthreads();
+    if (n_cand <= cap) {
+      path = 1;
+      for_each_candidate([&](unsigned long long k) { key[atomicAdd(&sm.n_emit, 1)] = k; });
+    } else if (cap >= p.max_nms) {
+      // ---- C: radix select (8 bits per pass, most significant first) of the max_nms-th largest key; keys are unique
+      path = 2;
+      if (tid == 0) { sm.prefix = 0ull; sm.k_rem = p.max_nms; }
+      for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        if (tid < 256) sm.hist[tid] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = sm.prefix;
+        for_each_candidate([&](unsigned long long k) {
+          if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&sm.hist[(k >> shift) & 255ull], 1u);
+        });
+        __syncthreads();
+        if (tid == 0) {
+          int cum = 0, d = 255;
+          for (; d > 0; --d) {
+            if (cum + static_cast<int>(sm.hist[d]) >= sm.k_rem) break;
+            cum += sm.hist[d];
+          }
+          sm.k_rem -= cum;
+          sm.prefix = (prefix << 8) | static_cast<unsigned long long>(d);
+        }
+        __syncthreads();
+      }
+      const unsigned long long kstar = sm.prefix;
+      for_each_candidate([&](unsigned long long k) { if (k >= kstar) key[atomicAdd(&sm.n_emit, 1)] = k; });
+    } else {
+      // the caller's buffer is smaller than max_nms and overflowed: report, the host grows `cap` (never silently truncated)
+      if (tid == 0) {
+        out_count[b] = -1 - n_cand;
+        ws.stats[b * 4] = n_pass; ws.stats[b * 4 + 1] = n_cand; ws.stats[b * 4 + 2] = 0; ws.stats[b * 4 + 3] = 3;
+      }
+      return;
+    }
+    __syncthreads();
+    n = sm.n_emit;
+  }
+
+  // ---- D: bitonic sort, descending; padding keys are 0 (< every candidate key)
+  int n_p2 = 64;
+  while (n_p2 < n) n_p2 <<= 1;
+  for (int i = n + tid; i < n_p2; i += kNmsThreads) key[i] = 0ull;
+  __syncthreads();
+  for (int k = 2; k <= n_p2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (n_p2 >> 1); t += kNmsThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+        const int l = i | j;
+        const unsigned long long a = key[i], c = key[l];
+        const bool desc = (i & k) == 0;
+        if (desc ? a < c : a > c) { key[i] = c; key[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const int n_sorted = min(n, p.max_nms);
+
+  // ---- E: NMS boxes of the sorted candidates (class offset unless agnostic, general_yolo.py:216-217)
+  for (int i = tid; i < n_sorted; i += kNmsThreads) {
+    const unsigned int ord = 0xffffffffu - static_cast<unsigned int>(key[i]);
+    const unsigned int r = ord / nc, c = ord - r * nc;
+    float4 bx = fe.box(b, r);
+    if (!p.agnostic) {
+      const float off = __fmul_rn(static_cast<float>(c), p.max_wh);
+      bx = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+    }
+    box[i] = bx;
+  }
+  for (int w = tid; w < (n_p2 >> 6); w += kNmsThreads) removed[w] = 0ull;
+  __syncthreads();
+
+  // ---- F: chunked greedy suppression
+  float* out = out_boxes + static_cast<int64_t>(b) * p.max_det * 6;
+  const int n_chunks = (n_sorted + 63) >> 6;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int base = ch << 6;
+    const int lim = min(64, n_sorted - base);
+    const int n_keep = sm.n_keep;
+    if (n_keep >= p.max_det) break;   // uniform: n_keep only changes between barriers
+    {
+      // 64 x 64 IoU bits of the chunk: thread (i, g) tests box i against boxes 4g..4g+3; 16 lanes OR their nibbles
+      const int i = tid >> 4, g = tid & 15;
+      unsigned long long bits = 0ull;
+      if (i < lim) {
+        const float4 me = box[base + i];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * g + e;
+          if (j > i && j < lim && iou_gt(me, box[base + j], p.iou_thres)) bits |= 1ull << j;
+        }
+      }
+#pragma unroll
+      for (int sft = 8; sft > 0; sft >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, sft);
+      if (g == 0) sm.diag[i] = bits;
+    }
+    __syncthreads();
+    if (tid == 0) {   // the sequential part: the reference's scan restricted to one chunk
+      unsigned long long rem = removed[ch] | (lim < 64 ? ~0ull << lim : 0ull), kb = 0ull;
+      int nk = n_keep;
+      while (~rem != 0ull && nk < p.max_det) {
+        const int k = __ffsll(static_cast<long long>(~rem)) - 1;
+        kb |= 1ull << k;
+        rem |= sm.diag[k] | (1ull << k);
+        ++nk;
+      }
+      sm.keep_bits = kb;
+      sm.n_keep = nk;
+    }
+    __syncthreads();
+    const unsigned long long kb = sm.keep_bits;
+    const int nk_chunk = __popcll(kb);
+    if (tid < 64 && ((kb >> tid) & 1ull)) {   // kept rows, in order: output (un-offset box, conf, cls) and the chunk's kept list
+      const int q = __popcll(kb & ((1ull << tid) - 1ull));
+      const unsigned long long k = key[base + tid];
+      const unsigned int ord = 0xffffffffu - static_cast<unsigned int>(k);
+      const unsigned int r = ord / nc, c = ord - r * nc;
+      const float4 bx = fe.box(b, r);
+      float* o = out + static_cast<int64_t>(n_keep + q) * 6;
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = __uint_as_float(static_cast<unsigned int>(k >> 32)); o[5] = static_cast<float>(c);
+      sm.kbox[q] = box[base + tid];
+    }
+    __syncthreads();
+    if (nk_chunk && ch + 1 < n_chunks) {
+      for (int j = base + 64 + tid; j < n_sorted; j += kNmsThreads) {
+        if ((removed[j >> 6] >> (j & 63)) & 1ull) continue;
+        const float4 bj = box[j];
+        bool hit = false;
+        for (int q = 0; q < nk_chunk && !hit; ++q) hit = iou_gt(sm.kbox[q], bj, p.iou_thres);
+        if (hit) atomicOr(&removed[j >> 6], 1ull << (j & 63));
+      }
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const int nc = ws.n_cand[b];
-    out_count[b] = nc > cap ? -1 - nc : n_keep;
+  if (tid == 0) {
+    out_count[b] = sm.n_keep;
+    ws.stats[b * 4] = n_pass; ws.stats[b * 4 + 1] = n_cand; ws.stats[b * 4 + 2] = n_sorted; ws.stats[b * 4 + 3] = path;
   }
 }
 
 size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
+int pow2_at_least(int v) { int p = 64; while (p < v) p <<= 1; return p; }
+
 size_t carve(NmsWs* ws, char* base, int B, long long A, int cap) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
-  (void)A;
-  ws->n_cand = reinterpret_cast<int*>(take(sizeof(int) * B));
-  ws->n_sorted = reinterpret_cast<int*>(take(sizeof(int) * B));
-  ws->ord = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * B * cap));
-  ws->cand = reinterpret_cast<float*>(take(sizeof(float) * 6 * B * cap));
-  ws->sorted = reinterpret_cast<float*>(take(sizeof(float) * 6 * B * cap));
-  ws->mask = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * cap * (cap / 64)));
+  const int cap_p2 = pow2_at_least(cap);
+  ws->stats = reinterpret_cast<int*>(take(sizeof(int) * 4 * B));
+  ws->pass_row = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * B * A));
+  ws->pass_obj = reinterpret_cast<float*>(take(sizeof(float) * B * A));
+  ws->key = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * cap_p2));
+  ws->box = reinterpret_cast<float4*>(take(sizeof(float4) * B * cap));
+  ws->removed = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * (cap_p2 / 64)));
   return off;
 }
 
-int nms_tail(int B, int cap, const YpNmsParams& p, const NmsWs& ws, float* out_boxes, int32_t* out_count, cudaStream_t st) {
-  nms_counts_kernel<<<ceil_div(B, 128), 128, 0, st>>>(B, cap, p.max_nms, ws);
-  nms_rank_kernel<<<dim3(cap / 256 + (cap % 256 ? 1 : 0), B), 256, 0, st>>>(cap, ws);
-  nms_mask_kernel<<<dim3(2 * sm_count(), B), 64, 0, st>>>(cap, p.iou_thres, p.agnostic, p.max_wh, ws);
+template <class FE>
+int launch_box_nms(const FE& fe, int B, const YpNmsParams& p, int cap, const NmsWs& ws, float* out_boxes, int32_t* out_count, cudaStream_t st) {
+  auto kern = box_nms_kernel<FE>;
   static thread_local bool raised = false;
-  if (!raised) { YP_CUDA_OK(cudaFuncSetAttribute(nms_scan_keep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes)); raised = true; }
-  const int stage_words = (kScanSmemBytes - static_cast<int>(sizeof(unsigned long long)) * (cap / 64)) / static_cast<int>(sizeof(unsigned long long));
-  nms_scan_keep_kernel<<<B, 256, kScanSmemBytes, st>>>(cap, p.max_det, ws, out_boxes, out_count, stage_words > 0 ? stage_words : 0);
-  YP_LAUNCH_OK();
+  if (!raised) { YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem)))); raised = true; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B); cfg.blockDim = dim3(kNmsThreads); cfg.dynamicSmemBytes = sizeof(NmsSmem); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  YP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, fe, B, p, cap, pow2_at_least(cap), ws, out_boxes, out_count));
   return YP_OK;
 }
 
@@ -389,22 +478,27 @@ extern "C" size_t yp_box_nms_workspace_bytes(int32_t B, int64_t A, int32_t no, i
   return yp::carve(&ws, nullptr, B, A, cap);
 }
 
+static int nms_check_params(const char* who, const YpNmsParams* p, int32_t cap) {
+  YP_REQUIRE(cap > 0 && cap % 64 == 0, YP_ERR_SHAPE, "%s: cap=%d must be a positive multiple of 64", who, cap);
+  YP_REQUIRE(p->conf_thres >= 0.f && p->conf_thres <= 1.f, YP_ERR_ARG, "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", p->conf_thres);
+  YP_REQUIRE(p->iou_thres >= 0.f && p->iou_thres <= 1.f, YP_ERR_ARG, "Invalid IoU %g, valid values are between 0.0 and 1.0", p->iou_thres);
+  YP_REQUIRE(p->max_det > 0 && p->max_nms > 0, YP_ERR_ARG, "%s: max_det/max_nms must be positive", who);
+  return YP_OK;
+}
+
 extern "C" int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, const YpNmsParams* p, int32_t cap,
                           float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
   YP_REQUIRE(pred && p && out_boxes && out_count && workspace, YP_ERR_ARG, "box_nms: null pointer");
   YP_REQUIRE(B > 0 && A > 0 && no >= 6, YP_ERR_SHAPE, "box_nms: B=%d A=%lld no=%d", B, (long long)A, no);
-  YP_REQUIRE(cap > 0 && cap % 64 == 0, YP_ERR_SHAPE, "box_nms: cap=%d must be a positive multiple of 64", cap);
-  YP_REQUIRE(p->conf_thres >= 0.f && p->conf_thres <= 1.f, YP_ERR_ARG, "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", p->conf_thres);
-  YP_REQUIRE(p->iou_thres >= 0.f && p->iou_thres <= 1.f, YP_ERR_ARG, "Invalid IoU %g, valid values are between 0.0 and 1.0", p->iou_thres);
-  YP_REQUIRE(p->max_det > 0 && p->max_nms > 0, YP_ERR_ARG, "box_nms: max_det/max_nms must be positive");
+  YP_REQUIRE(A * (no - 5) < (1ll << 31), YP_ERR_SHAPE, "box_nms: A * nc = %lld exceeds 2^31", (long long)(A * (no - 5)));
+  int rc = nms_check_params("box_nms", p, cap);
+  if (rc != YP_OK) return rc;
   yp::NmsWs ws;
   const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, A, cap);
   YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "box_nms: workspace %zu < %zu bytes", workspace_bytes, need);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t rows = static_cast<int64_t>(B) * A;
-  YP_CUDA_OK(cudaMemsetAsync(ws.n_cand, 0, sizeof(int) * B, st));
-  yp::nms_candidates_pred_kernel<<<static_cast<unsigned>(yp::ceil_div64(rows, 256)), 256, 0, st>>>(pred, B, A, no, *p, cap, ws);
-  return yp::nms_tail(B, cap, *p, ws, out_boxes, out_count, st);
+  yp::PredRows fe;
+  fe.pred = pred; fe.A = A; fe.no = no;
+  return yp::launch_box_nms(fe, B, *p, cap, ws, out_boxes, out_count, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int yp_detect_nms(const float* const* logits3, const int32_t* ny3, const int32_t* nx3, const int32_t* ldc3, const float* stride3,
@@ -412,10 +506,8 @@ extern "C" int yp_detect_nms(const float* const* logits3, const int32_t* ny3, co
                              float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
   YP_REQUIRE(logits3 && ny3 && nx3 && ldc3 && stride3 && anchors_px_host && p && out_boxes && out_count && workspace, YP_ERR_ARG, "detect_nms: null pointer");
   YP_REQUIRE(B > 0 && na == 3 && no >= 6, YP_ERR_SHAPE, "detect_nms: B=%d na=%d no=%d (na must be 3)", B, na, no);
-  YP_REQUIRE(cap > 0 && cap % 64 == 0, YP_ERR_SHAPE, "detect_nms: cap=%d must be a positive multiple of 64", cap);
-  YP_REQUIRE(p->conf_thres >= 0.f && p->conf_thres <= 1.f, YP_ERR_ARG, "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", p->conf_thres);
-  YP_REQUIRE(p->iou_thres >= 0.f && p->iou_thres <= 1.f, YP_ERR_ARG, "Invalid IoU %g, valid values are between 0.0 and 1.0", p->iou_thres);
-  YP_REQUIRE(p->max_det > 0 && p->max_nms > 0, YP_ERR_ARG, "detect_nms: max_det/max_nms must be positive");
+  int rc = nms_check_params("detect_nms", p, cap);
+  if (rc != YP_OK) return rc;
   yp::DetLevels lv;
   long long A = 0;
   for (int l = 0; l < 3; ++l) {
@@ -425,14 +517,10 @@ extern "C" int yp_detect_nms(const float* const* logits3, const int32_t* ny3, co
     lv.row_off[l] = A;
     A += static_cast<long long>(na) * ny3[l] * nx3[l];
   }
-  lv.na = na; lv.no = no;
+  lv.na = na; lv.no = no; lv.A = A;
+  YP_REQUIRE(A * (no - 5) < (1ll << 31), YP_ERR_SHAPE, "detect_nms: A * nc = %lld exceeds 2^31", (long long)(A * (no - 5)));
   yp::NmsWs ws;
   const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, A, cap);
   YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "detect_nms: workspace %zu < %zu bytes", workspace_bytes, need);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  YP_CUDA_OK(cudaMemsetAsync(ws.n_cand, 0, sizeof(int) * B, st));
-  yp::nms_candidates_logits_kernel<<<static_cast<unsigned>(yp::ceil_div64(static_cast<int64_t>(B) * A, 256)), 256, 0, st>>>(lv, B, A, *p, cap, ws);
-  return yp::nms_tail(B, cap, *p, ws, out_boxes, out_count, st);
+  return yp::launch_box_nms(lv, B, *p, cap, ws, out_boxes, out_count, static_cast<cudaStream_t>(stream));
 }
-
-

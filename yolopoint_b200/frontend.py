@@ -19,6 +19,8 @@ from . import _lib
 from ._lib import YpNmsParams
 from .engine import SliceRef
 
+NMS_CAP = 30016     # >= the reference's max_nms = 30000 (src/utils/general_yolo.py:155), multiple of 64
+
 DEFAULT_CFG = dict(  # configs/kitti_inference.yaml:5-16 of the reference
     detection_threshold=0.12, nms=8, nn_thresh=0.7, conf_thres_box=0.4, iou_thres_box=0.45, max_det=1000,
 )
@@ -27,40 +29,67 @@ DEFAULT_CFG = dict(  # configs/kitti_inference.yaml:5-16 of the reference
 class FramePipeline:
     """Static buffers + graphs for frames of one shape.  All results stay on the device until ``fetch``."""
 
-    def __init__(self, model, B: int, H: int, W: int, cfg: Optional[dict] = None, filter_pts: bool = True, max_pts: int = 4096,
-                 nms_cap: int = 4096, heat_variant: int = 1, do_match: bool = True, slot: int = 0):
+    def __init__(self, model, B: int, H: int, W: int, cfg: Optional[dict] = None, filter_pts: bool = True, max_pts: Optional[int] = None,
+                 nms_cap: int = NMS_CAP, heat_variant: int = 1, do_match: bool = True, slot: int = 0):
+        """``max_pts`` / ``nms_cap`` are buffer capacities, not semantics.  The defaults cannot overflow: ``max_pts=None`` is the
+        geometric bound of the keypoint NMS (survivors are more than ``nms`` pixels apart) and ``nms_cap`` = 30016 covers the
+        reference's ``max_nms`` = 30000 candidates, beyond which the kernel keeps the 30000 most confident like the reference
+        (src/utils/general_yolo.py:155, 210-211).  Smaller explicit values save memory; a frame that exceeds them makes the
+        pipeline grow to the defaults and re-run the frame -- valid input never raises."""
         self.cfg = dict(DEFAULT_CFG, **(cfg or {}))
         self.eng = model.engine() if hasattr(model, "engine") else model
         self.plan = self.eng.plan(B, H, W, slot)
         self.B, self.H, self.W = B, H, W
-        self.filter_pts, self.max_pts, self.nms_cap, self.heat_variant, self.do_match = filter_pts, max_pts, (nms_cap + 63) // 64 * 64, heat_variant, do_match
-        dev, D = self.eng.device, self.eng.net.D
-        self.D = D
+        self.filter_pts, self.heat_variant, self.do_match = filter_pts, heat_variant, do_match
+        self.max_pts = min(int(max_pts), self.max_pts_bound()) if max_pts else self.max_pts_bound()
+        self.nms_cap = (min(int(nms_cap), NMS_CAP) + 63) // 64 * 64
+        self.D = self.eng.net.D
+        self.parity = 0
+        self._n_submit = self._n_collect = 0
+        self.regrown = 0      # how many times a frame exceeded an explicit capacity (diagnostics)
+        self._alloc()
+
+    def max_pts_bound(self) -> int:
+        """Keypoints that can survive nms_fast with radius r on an H x W frame: survivors are >= r+1 pixels apart (Chebyshev)."""
+        r = int(self.cfg["nms"]) + 1
+        return (-(-self.H // r) * -(-self.W // r) + 63) // 64 * 64
+
+    def _alloc(self, old: Optional[dict] = None):
+        """(Re)allocate every capacity-dependent buffer; ``old`` carries the previous frames' keypoints / descriptors over."""
+        B, H, W, D = self.B, self.H, self.W, self.D
+        max_pts = self.max_pts
+        dev = self.eng.device
         L = _lib.lib(require_device=True)
         md = self.cfg["max_det"]
         z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)
-        self.boxes, self.bcount = z(B, md, 6), z(B, dt=torch.int32)
+        two = lambda f: [f(), f()]
+        # every result buffer exists once per frame parity: frame i+1 is computed while frame i's results are read back
+        self.boxes, self.bcount = two(lambda: z(B, md, 6)), two(lambda: z(B, dt=torch.int32))
         self.heat = z(B, H, W)
-        self.pts = [z(B, max_pts, 3), z(B, max_pts, 3)]
-        self.kcount = [z(B, dt=torch.int32), z(B, dt=torch.int32)]
-        self.descs = [z(B, max_pts, D), z(B, max_pts, D)]
+        self.pts, self.kcount = two(lambda: z(B, max_pts, 3)), two(lambda: z(B, dt=torch.int32))
+        self.descs = two(lambda: z(B, max_pts, D))
         self.row_key, self.col_key = z(B, max_pts, dt=torch.int64), z(B, max_pts, dt=torch.int64)
-        self.matches, self.mcount = z(B, max_pts, 3), z(B, dt=torch.int32)
+        self.matches, self.mcount = two(lambda: z(B, max_pts, 3)), two(lambda: z(B, dt=torch.int32))
+        self.d_counts = two(lambda: z(3, B, dt=torch.int32))
         self.ws_nms = torch.empty(L.yp_box_nms_workspace_bytes(B, self.plan.A, self.eng.net.no, self.nms_cap), dtype=torch.uint8, device=dev)
         self.ws_kp = torch.empty(L.yp_keypoints_workspace_bytes(B, H, W, max_pts), dtype=torch.uint8, device=dev)
         self.nms_params = YpNmsParams(float(self.cfg["conf_thres_box"]), float(self.cfg["iou_thres_box"]), 1, 1, int(md), 30000, 7680.0, None)
-        self.parity = 0
-        # pinned host mirrors for the single read-back, double-buffered so that one frame can be staged / unpacked on the host
-        # while the previous one is still on the GPU (submit_host may run one frame ahead of collect)
+        # host boundary: frames go up on a copy stream into a device staging buffer, results come back on another copy stream
+        # (counts first, then exactly `count` rows of each result), so that neither transfer sits between two frames' kernels
+        if old is None:
+            self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self.d_frame = two(lambda: torch.zeros((B, H, W, 3), dtype=torch.uint8, device=dev))
+            self._host = [dict(frame=torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True),
+                               counts=torch.empty((3, B), dtype=torch.int32, pin_memory=True), k=0, ev_counts=None, ev_read=None) for _ in range(2)]
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        self.d_counts = z(3, B, dt=torch.int32)
-        self._host = [dict(frame=torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True),
-                           counts=torch.empty((3, B), dtype=torch.int32, pin_memory=True), pts=pin(self.pts[0]), boxes=pin(self.boxes),
-                           desc=pin(self.descs[0]), matches=pin(self.matches), done=None) for _ in range(2)]
-        self.h_frame, self.h_counts = self._host[0]["frame"], self._host[0]["counts"]
-        self.h_pts, self.h_boxes, self.h_desc, self.h_matches = (self._host[0][k] for k in ("pts", "boxes", "desc", "matches"))
-        self._n_submit = self._n_collect = 0
+        for h in self._host:
+            h.update(pts=pin(self.pts[0]), boxes=pin(self.boxes[0]), desc=pin(self.descs[0]), matches=pin(self.matches[0]))
         self.graphs = {}   # graphs bake THIS pipeline's buffer addresses, so they are owned here, not by the shared plan
+        self._d2h_bytes = 0
+        if old is not None:   # the previous frame's results are the match partner of the next frame
+            n = old["pts"][0].shape[1]
+            for k in range(2):
+                self.pts[k][:, :n].copy_(old["pts"][k]); self.descs[k][:, :n].copy_(old["descs"][k]); self.kcount[k].copy_(old["kcount"][k])
 
     # ---- device work ---------------------------------------------------------------------------
     def _enqueue(self, k: int, from_frame: bool = True):
@@ -78,17 +107,18 @@ class FramePipeline:
                                           self.ws_kp.data_ptr(), self.ws_kp.numel(), stp))
 
         p.run_net(tails={1: kp_tail})
-        # Detect decode fused into the NMS front end: pred [B,A,85] is never materialised here
+        # Detect decode fused into the box NMS kernel: pred [B,A,85] is never materialised here
         dets = [p.bufs[f"det{i}"] for i in range(3)]
         lg = (C.c_void_p * 3)(*[d.data_ptr() for d in dets])
         ny = (C.c_int32 * 3)(*[d.shape[2] for d in dets]); nx = (C.c_int32 * 3)(*[d.shape[3] for d in dets])
         ldc = (C.c_int32 * 3)(*[d.shape[4] for d in dets])
         strd = (C.c_float * 3)(*[float(v) for v in self.eng.stride])
         anc = (C.c_float * 18)(*[float(v) for row in self.eng.anchors_px for v in row])
+        boxes, bcount = self.boxes[k], self.bcount[k]
         _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, self.eng.net.no, C.byref(self.nms_params), self.nms_cap,
-                                   self.boxes.data_ptr(), self.bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), st))
-        _lib.check(L.yp_keypoints_collect(self.heat.data_ptr(), B, H, W, 4, self.boxes.data_ptr() if self.filter_pts else None,
-                                          self.bcount.data_ptr() if self.filter_pts else None, self.boxes.shape[1] if self.filter_pts else 0,
+                                   boxes.data_ptr(), bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), st))
+        _lib.check(L.yp_keypoints_collect(self.heat.data_ptr(), B, H, W, 4, boxes.data_ptr() if self.filter_pts else None,
+                                          bcount.data_ptr() if self.filter_pts else None, boxes.shape[1] if self.filter_pts else 0,
                                           self.pts[k].data_ptr(), self.kcount[k].data_ptr(), self.max_pts, self.ws_kp.data_ptr(),
                                           self.ws_kp.numel(), st))
         desc = p.bufs["desc"][0]   # [B,Hc,Wc,D] fp32 NHWC, unit norm
@@ -101,17 +131,16 @@ class FramePipeline:
                                               self.descs[k][b].data_ptr(), self.kcount[k][b:].data_ptr(), self.max_pts, self.D, 0,
                                               self.row_key[b].data_ptr(), self.col_key[b].data_ptr(), st))
                 _lib.check(L.yp_match_finalize(self.row_key[b].data_ptr(), self.kcount[1 - k][b:].data_ptr(), self.max_pts,
-                                               self.col_key[b].data_ptr(), self.max_pts, float(cfg["nn_thresh"]), self.matches[b].data_ptr(),
-                                               self.mcount[b:].data_ptr(), st))
-        self.d_counts[0].copy_(self.kcount[k]); self.d_counts[1].copy_(self.bcount); self.d_counts[2].copy_(self.mcount)
+                                               self.col_key[b].data_ptr(), self.max_pts, float(cfg["nn_thresh"]), self.matches[k][b].data_ptr(),
+                                               self.mcount[k][b:].data_ptr(), st))
+        dc = self.d_counts[k]
+        dc[0].copy_(self.kcount[k]); dc[1].copy_(bcount); dc[2].copy_(self.mcount[k])
 
     def n_launches(self) -> int:
         """Kernels of this library launched per frame batch (for bench.py's gpu_launches)."""
         net_launches = len(self.plan.launches)
-        # input + net + fused decode/NMS (candidates, counts, rank, mask, scan) + heatmap + keypoints (nms, collect, emit) + sample + match
-        # keypoints = 8 NMS rounds + 1 sweep + collect + emit (see csrc/keypoints.cu)
-        per = 1 + net_launches + 5 + 1 + 11 + 1 + (self.B * 3 if self.do_match else 0)
-        return per
+        # input + net + fused decode/box NMS (1) + heatmap + keypoints (8 NMS rounds + sweep + collect + emit) + sample + match (3 per image)
+        return 1 + net_launches + 1 + 1 + 11 + 1 + (self.B * 3 if self.do_match else 0)
 
     def step_device(self, from_frame: bool = True):
         """Process the frame already resident in plan.frame_in / plan.x_in; flips the parity."""
@@ -137,40 +166,81 @@ class FramePipeline:
             c.zero_()
         self.parity = 0
 
+    def nms_stats(self) -> np.ndarray:
+        """[B,4] int32 of the last frame's box NMS: rows passing objectness, candidates, candidates sorted, path (see the header)."""
+        return self.ws_nms[: 16 * self.B].view(torch.int32).view(self.B, 4).cpu().numpy()
+
     # ---- host boundary -------------------------------------------------------------------------
     def submit_host(self, frames_u8: np.ndarray):
-        """Enqueue (on the current stream) H2D of the frames, the whole pipeline and the D2H of the compact results.  At most two
-        submissions may be outstanding (double-buffered pinned host memory): ``submit(i+1)`` before ``collect(i)`` lets the host
-        stage / unpack one frame while the GPU works on the other."""
+        """Stage the frames in pinned memory and enqueue H2D (copy stream) -> the whole pipeline (current stream) -> D2H of the result
+        counts (second copy stream).  At most two submissions may be outstanding: ``submit(i+1)`` before ``collect(i)`` lets the
+        host stage / unpack one frame while the GPU works on the other, and lets the transfers overlap the kernels."""
         if self._n_submit - self._n_collect >= 2:
             raise RuntimeError("FramePipeline: two frames already in flight; call collect() first")
         dev = self.eng.device
-        h = self._host[self._n_submit % 2]
+        slot = self._n_submit % 2
+        h = self._host[slot]
+        cur = torch.cuda.current_stream(dev)
         h["frame"].copy_(torch.from_numpy(np.ascontiguousarray(frames_u8)).view(self.B, self.H, self.W, 3))
-        self.plan.frame_in.copy_(h["frame"], non_blocking=True)
+        with torch.cuda.stream(self.s_in):
+            if h["ev_read"] is not None:
+                self.s_in.wait_event(h["ev_read"])          # the staging buffer's previous frame has been consumed
+            self.d_frame[slot].copy_(h["frame"], non_blocking=True)
+            ev_in = torch.cuda.Event(); ev_in.record(self.s_in)
+        cur.wait_event(ev_in)
+        self.plan.frame_in.copy_(self.d_frame[slot])
+        h["ev_read"] = torch.cuda.Event(); h["ev_read"].record(cur)
         k = self.step_device(True)
-        h["counts"].copy_(self.d_counts, non_blocking=True)
-        h["pts"].copy_(self.pts[k], non_blocking=True)
-        h["boxes"].copy_(self.boxes, non_blocking=True)
-        h["desc"].copy_(self.descs[k], non_blocking=True)
-        h["matches"].copy_(self.matches, non_blocking=True)
-        h["done"] = torch.cuda.Event()
-        h["done"].record(torch.cuda.current_stream(dev))
+        ev_done = torch.cuda.Event(); ev_done.record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(ev_done)
+            h["counts"].copy_(self.d_counts[k], non_blocking=True)
+            h["ev_counts"] = torch.cuda.Event(); h["ev_counts"].record(self.s_out)
+        h["k"] = k
         self._n_submit += 1
+
+    def _regrow_and_rerun(self):
+        """A frame exceeded an explicitly reduced capacity: grow to the defaults that cannot overflow and redo the frames in
+        flight (their host copies are still staged).  The previous frame's keypoints / descriptors are carried over."""
+        torch.cuda.synchronize(self.eng.device)
+        pending = [(self._host[i % 2]["frame"].numpy().copy(), self._host[i % 2]["k"]) for i in range(self._n_collect, self._n_submit)]
+        old = dict(pts=self.pts, descs=self.descs, kcount=self.kcount)
+        self.max_pts, self.nms_cap = self.max_pts_bound(), NMS_CAP
+        self._alloc(old)
+        self.regrown += 1
+        self._n_submit = self._n_collect
+        self.parity = pending[0][1]
+        for frame, _ in pending:
+            self.submit_host(frame)
 
     def collect(self):
         """Wait for the oldest outstanding submit_host and unpack per-image (pts[3,N] f64, desc[D,N] f32, boxes[n,6] f32,
-        matches[3,L] f64)."""
+        matches[3,L] f64).  Reads back exactly the rows the counts name."""
         if self._n_collect >= self._n_submit:
             raise RuntimeError("FramePipeline.collect() without a matching submit_host()")
         h = self._host[self._n_collect % 2]
+        h["ev_counts"].synchronize()
+        if int(h["counts"][:2].min()) < 0:                  # keypoint or box buffer smaller than this frame needs
+            self._regrow_and_rerun()
+            h = self._host[self._n_collect % 2]
+            h["ev_counts"].synchronize()
         self._n_collect += 1
-        h["done"].synchronize()
+        k = h["k"]
+        cnt = h["counts"].numpy()
+        nbytes = cnt.nbytes
+        with torch.cuda.stream(self.s_out):
+            for b in range(self.B):
+                nk, nb, nm = (int(v) for v in cnt[:, b])
+                for name, src, n in (("pts", self.pts[k], nk), ("desc", self.descs[k], nk), ("boxes", self.boxes[k], nb), ("matches", self.matches[k], nm)):
+                    if n > 0:
+                        h[name][b, :n].copy_(src[b, :n], non_blocking=True)
+                        nbytes += n * src.shape[2] * 4
+            done = torch.cuda.Event(); done.record(self.s_out)
+        done.synchronize()
+        self._d2h_bytes = nbytes
         out = []
         for b in range(self.B):
-            nk, nb, nm = (int(v) for v in h["counts"][:, b])
-            if nk < 0 or nb < 0:
-                raise RuntimeError(f"buffer overflow (keypoints {nk}, boxes {nb}): raise max_pts / nms_cap")
+            nk, nb, nm = (int(v) for v in cnt[:, b])
             pts = h["pts"][b, :nk].numpy().astype(np.float64).T.copy()
             desc = h["desc"][b, :nk].numpy().T.copy()
             boxes = h["boxes"][b, :nb].numpy().copy()
@@ -179,15 +249,16 @@ class FramePipeline:
         return out
 
     def step_host(self, frames_u8: np.ndarray):
-        """frames [B,H,W,3] uint8 on the host -> per-image (pts, desc, boxes, matches); one H2D, one D2H, one sync."""
+        """frames [B,H,W,3] uint8 on the host -> per-image (pts, desc, boxes, matches)."""
         self.submit_host(frames_u8)
         return self.collect()
 
     def d2h_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.h_counts, self.h_pts, self.h_boxes, self.h_desc, self.h_matches))
+        """Bytes the last collect() read back (counts + exactly the result rows)."""
+        return self._d2h_bytes
 
     def h2d_bytes(self) -> int:
-        return self.h_frame.numel()
+        return self._host[0]["frame"].numel()
 
 
 class YoloPointFrontend:
@@ -198,7 +269,7 @@ class YoloPointFrontend:
     host, as the reference does it) and the optional per-camera template mask (``self.templates[rostpc]``, src/demo.py:187-192) included.
     """
 
-    def __init__(self, model, config: Optional[dict] = None, filter_pts: bool = True, max_pts: int = 4096, nms_cap: int = 4096):
+    def __init__(self, model, config: Optional[dict] = None, filter_pts: bool = True, max_pts: Optional[int] = None, nms_cap: int = NMS_CAP):
         self.model = model
         cfg = dict(DEFAULT_CFG)
         self.crop_resize = None

@@ -21,9 +21,14 @@ def _stream(dev) -> C.c_void_p:
 
 
 def _workspace(dev, kind: str, nbytes: int) -> torch.Tensor:
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), kind)
+    """Scratch buffer per (device, kind, stream): calls on different streams never share scratch, and a buffer that is replaced
+    by a larger one is kept alive by the caching allocator until the work already enqueued on its stream has finished."""
+    stream = torch.cuda.current_stream(dev)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), kind, stream.cuda_stream)
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            t.record_stream(stream)
         t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
         _ws_cache[key] = t
     return t
@@ -46,9 +51,10 @@ def class_mask_tensor(classes: Optional[Sequence[int]], nc: int, dev) -> Optiona
 
 
 def box_nms(pred: torch.Tensor, conf_thres: float, iou_thres: float, multi_label: bool, agnostic: bool, max_det: int,
-            classes: Optional[Sequence[int]] = None, cap: int = 4096, max_nms: int = 30000, max_wh: float = 7680.0,
+            classes: Optional[Sequence[int]] = None, cap: int = 30016, max_nms: int = 30000, max_wh: float = 7680.0,
             out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, class_mask: Optional[torch.Tensor] = None):
-    """pred [B,A,no] fp32 -> (boxes [B,max_det,6], count int32 [B]).  count < 0 means -1-n candidates overflowed `cap`."""
+    """pred [B,A,no] fp32 -> (boxes [B,max_det,6], count int32 [B]).  With cap >= max_nms any number of candidates is handled like
+    the reference (the max_nms most confident enter the NMS); count < 0 (= -1-n) only with an explicit cap < max_nms that overflowed."""
     _need_cuda(pred, "prediction")
     L = _lib.lib(require_device=True)
     pred = pred.contiguous().float()
