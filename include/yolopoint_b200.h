@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YP_ABI_VERSION 5
+#define YP_ABI_VERSION 6
 
 typedef enum {
   YP_OK = 0,
@@ -44,6 +44,10 @@ int yp_abi_version(void);
 const char* yp_last_error(void);
 /* 0 if the current device can run this library (compute capability 10.x). */
 int yp_check_device(void);
+/* Stream-ordered copy between device and/or pinned host buffers (cudaMemcpyDefault); used by the host boundary of the whole-frame
+ * pipeline (frame upload, count-bounded result read-back).  The reference moves the same data with tensor.to(device) /
+ * .cpu().numpy() (src/demo.py:132, 138, 214). */
+int yp_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Activation views.  Activations live in HBM as NHWC tensors [planes][B][H][W][C_total]; a view is a

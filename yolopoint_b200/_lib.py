@@ -53,6 +53,7 @@ SIGNATURES = {
     "yp_abi_version": (_i32, []),
     "yp_last_error": (C.c_char_p, []),
     "yp_check_device": (_i32, []),
+    "yp_memcpy_async": (_i32, [_vp, _vp, _sz, _vp]),
     "yp_conv2d_nhwc_fwd": (_i32, [_PC, _vp]),
     "yp_conv2d_workspace_bytes": (_sz, [_PC]),
     "yp_conv2d_plan_check": (_i32, [_PC]),
@@ -106,7 +107,7 @@ def lib(require_device: bool = False):
                     except AttributeError as e:  # pragma: no cover
                         raise YoloPointB200Error(f"{LIB_PATH} does not export {name}") from e
                     fn.restype, fn.argtypes = res, args
-                if handle.yp_abi_version() != 5:
+                if handle.yp_abi_version() != 6:
                     raise YoloPointB200Error("ABI version mismatch between _lib.py and libyolopoint_b200.so")
                 _lib = handle
     if require_device:

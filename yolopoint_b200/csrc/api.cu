@@ -83,3 +83,12 @@ extern "C" int yp_conv2d_nhwc_wgrad(const YpWgradDesc* d, void* stream) {
   YP_REQUIRE(d && d->x.base && d->dy.base && d->dw, YP_ERR_ARG, "wgrad: null pointer in descriptor");
   return yp::wgrad_tc(*d, static_cast<cudaStream_t>(stream));
 }
+
+// Stream-ordered copy between any two of {device, pinned host} buffers (cudaMemcpyDefault): the host boundary of the whole-frame
+// pipeline issues its H2D / D2H transfers through this so that a frame costs a handful of driver calls, not framework dispatches.
+extern "C" int yp_memcpy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  YP_REQUIRE(dst && src, YP_ERR_ARG, "memcpy_async: null pointer");
+  if (bytes == 0) return YP_OK;
+  YP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return YP_OK;
+}

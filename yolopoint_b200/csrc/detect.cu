@@ -101,7 +101,7 @@ constexpr int kPassSmem = 4096;     // objectness survivors listed in shared mem
 
 struct NmsWs {
   int* stats;                  // [B][4]  rows passing objectness, candidates found, candidates sorted, path (0 smem, 1 workspace, 2 select)
-  unsigned int* pass_row;      // [B][A]
+  unsigned long long* pass_row; // [B][A]  row handles
   float* pass_obj;             // [B][A]
   unsigned long long* key;     // [B][cap_p2]
   float4* box;                 // [B][cap]   NMS boxes (class offset applied) in sorted order
@@ -120,22 +120,38 @@ __device__ __forceinline__ float4 xywh2xyxy_rn(float bx, float by, float bw, flo
                      __fadd_rn(by, __fdiv_rn(bh, 2.0f)));
 }
 
+// A front end enumerates the rows of one image as (segment, position) pairs without integer division by run-time values, hands
+// out a 64-bit row handle (what the later phases need to find the row again) and answers three questions about a row:
+// objectness, class score c, decoded box.  `*_may_pass` are cheap conservative pre-tests on the raw value (no false negatives):
+// the exact test `value > thr` is only evaluated where they hold.
+//
 // front end 1: decoded predictions [B, A, no]
 struct PredRows {
   const float* pred;
   long long A;
   int no;
-  __device__ __forceinline__ const float* row(int b, unsigned int r) const { return pred + (static_cast<int64_t>(b) * A + r) * no; }
-  __device__ __forceinline__ float obj(int b, unsigned int r) const { return __ldg(row(b, r) + 4); }
-  __device__ __forceinline__ float cls(int b, unsigned int r, int c) const { return __ldg(row(b, r) + 5 + c); }
-  __device__ __forceinline__ float4 box(int b, unsigned int r) const {
-    const float* p = row(b, r);
+  float thr;
+  __device__ __forceinline__ int segments() const { return 1; }
+  __device__ __forceinline__ int seg_rows(int) const { return static_cast<int>(A); }
+  __device__ __forceinline__ unsigned long long handle(int, int i) const { return static_cast<unsigned long long>(i); }
+  __device__ __forceinline__ unsigned int row_of(unsigned long long h) const { return static_cast<unsigned int>(h); }
+  __device__ __forceinline__ unsigned long long handle_of_row(unsigned int r) const { return r; }
+  __device__ __forceinline__ const float* row(int b, unsigned long long h) const { return pred + (static_cast<int64_t>(b) * A + static_cast<int64_t>(h)) * no; }
+  __device__ __forceinline__ float obj_raw(int b, unsigned long long h) const { return __ldg(row(b, h) + 4); }
+  __device__ __forceinline__ bool obj_may_pass(float raw) const { return raw > thr; }
+  __device__ __forceinline__ float obj(float raw) const { return raw; }
+  __device__ __forceinline__ float cls_raw(int b, unsigned long long h, int c) const { return __ldg(row(b, h) + 5 + c); }
+  __device__ __forceinline__ bool cls_may_pass(float raw, float) const { return true; }
+  __device__ __forceinline__ float cls(float raw) const { return raw; }
+  __device__ __forceinline__ float4 box(int b, unsigned long long h) const {
+    const float* p = row(b, h);
     return xywh2xyxy_rn(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
   }
 };
 
 // front end 2: raw Detect logits of the three levels (NHWC, channel a*no+o): decode (models/yolo.py:60-68) only what the NMS
-// looks at, so `pred` is never materialised in the whole-frame pipeline.
+// looks at, so `pred` is never materialised in the whole-frame pipeline.  Segment = level, position = pixel * 3 + anchor
+// (consecutive threads read the three objectness logits of consecutive pixels); handle = level | anchor | y | x | row.
 struct DetLevels {
   const float* logits[3];
   int ny[3], nx[3], ldc[3];
@@ -144,26 +160,42 @@ struct DetLevels {
   long long row_off[3];
   long long A;
   int na, no;
-  __device__ __forceinline__ const float* row(int b, unsigned int r, int* l_, int* an_, int* y_, int* x_) const {
+  float logit_thr;   // log(thr / (1 - thr)) - margin: sigmoid(v) > thr implies v > logit_thr
+  __device__ __forceinline__ int segments() const { return 3; }
+  __device__ __forceinline__ int seg_rows(int l) const { return 3 * ny[l] * nx[l]; }
+  __device__ __forceinline__ unsigned long long handle(int l, int i) const {
+    const int pix = i / 3, an = i - pix * 3;
+    const int y = pix / nx[l], x = pix - y * nx[l];
+    const unsigned int r = static_cast<unsigned int>(row_off[l]) + static_cast<unsigned int>((an * ny[l] + y) * nx[l] + x);   // models/yolo.py:56
+    return (static_cast<unsigned long long>(l) << 62) | (static_cast<unsigned long long>(an) << 60) | (static_cast<unsigned long long>(y) << 46) |
+           (static_cast<unsigned long long>(x) << 32) | r;
+  }
+  __device__ __forceinline__ unsigned int row_of(unsigned long long h) const { return static_cast<unsigned int>(h); }
+  __device__ __forceinline__ unsigned long long handle_of_row(unsigned int r) const {
     const int l = r >= row_off[2] ? 2 : (r >= row_off[1] ? 1 : 0);
-    unsigned int cell = r - static_cast<unsigned int>(row_off[l]);   // (anchor, y, x) order, models/yolo.py:56
-    const int x = cell % nx[l]; cell /= nx[l];
-    const int y = cell % ny[l];
-    const int an = cell / ny[l];
-    *l_ = l; *an_ = an; *y_ = y; *x_ = x;
+    unsigned int cell = r - static_cast<unsigned int>(row_off[l]);
+    const unsigned int x = cell % nx[l]; cell /= nx[l];
+    const unsigned int y = cell % ny[l], an = cell / ny[l];
+    return (static_cast<unsigned long long>(l) << 62) | (static_cast<unsigned long long>(an) << 60) | (static_cast<unsigned long long>(y) << 46) |
+           (static_cast<unsigned long long>(x) << 32) | r;
+  }
+  __device__ __forceinline__ const float* row(int b, unsigned long long h) const {
+    const int l = static_cast<int>(h >> 62), an = static_cast<int>(h >> 60) & 3, y = static_cast<int>(h >> 46) & 0x3fff, x = static_cast<int>(h >> 32) & 0x3fff;
     return logits[l] + ((static_cast<int64_t>(b) * ny[l] + y) * nx[l] + x) * ldc[l] + an * no;
   }
-  __device__ __forceinline__ float obj(int b, unsigned int r) const {
-    int l, an, y, x;
-    return sigmoid_rn(__ldg(row(b, r, &l, &an, &y, &x) + 4));
+  // position i of segment l without building the handle: pixel-major NHWC, 3 anchors per pixel
+  __device__ __forceinline__ float obj_raw_at(int b, int l, int i) const {
+    const int pix = i / 3, an = i - pix * 3;
+    return __ldg(logits[l] + (static_cast<int64_t>(b) * ny[l] * nx[l] + pix) * ldc[l] + an * no + 4);
   }
-  __device__ __forceinline__ float cls(int b, unsigned int r, int c) const {
-    int l, an, y, x;
-    return sigmoid_rn(__ldg(row(b, r, &l, &an, &y, &x) + 5 + c));
-  }
-  __device__ __forceinline__ float4 box(int b, unsigned int r) const {
-    int l, an, y, x;
-    const float* p = row(b, r, &l, &an, &y, &x);
+  __device__ __forceinline__ bool obj_may_pass(float raw) const { return raw > logit_thr; }
+  __device__ __forceinline__ float obj(float raw) const { return sigmoid_rn(raw); }
+  __device__ __forceinline__ float cls_raw(int b, unsigned long long h, int c) const { return __ldg(row(b, h) + 5 + c); }
+  __device__ __forceinline__ bool cls_may_pass(float raw, float) const { return raw > logit_thr; }   // conf = cls * obj <= cls
+  __device__ __forceinline__ float cls(float raw) const { return sigmoid_rn(raw); }
+  __device__ __forceinline__ float4 box(int b, unsigned long long h) const {
+    const int l = static_cast<int>(h >> 62), an = static_cast<int>(h >> 60) & 3, y = static_cast<int>(h >> 46) & 0x3fff, x = static_cast<int>(h >> 32) & 0x3fff;
+    const float* p = row(b, h);
     const float sx = sigmoid_rn(__ldg(p)), sy = sigmoid_rn(__ldg(p + 1)), sw = sigmoid_rn(__ldg(p + 2)), sh = sigmoid_rn(__ldg(p + 3));
     const float bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), static_cast<float>(x)), stride[l]);
     const float by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), static_cast<float>(y)), stride[l]);
@@ -171,6 +203,8 @@ struct DetLevels {
     return xywh2xyxy_rn(bx, by, __fmul_rn(__fmul_rn(tw, tw), anchor[l][an * 2]), __fmul_rn(__fmul_rn(th, th), anchor[l][an * 2 + 1]));
   }
 };
+template <class FE> __device__ __forceinline__ float fe_obj_raw_at(const FE& fe, int b, int l, int i) { return fe.obj_raw(b, fe.handle(l, i)); }
+template <> __device__ __forceinline__ float fe_obj_raw_at<DetLevels>(const DetLevels& fe, int b, int l, int i) { return fe.obj_raw_at(b, l, i); }
 
 // torchvision nms_kernel semantics: suppress j (after i in sorted order) iff inter / (area_i + area_j - inter) > thr.
 // inter == 0 can never exceed thr >= 0 (0 / x is 0, -0 or NaN), so disjoint pairs skip the division.
@@ -189,16 +223,15 @@ __device__ __forceinline__ unsigned long long cand_key(float conf, unsigned int 
 }
 
 struct NmsSmem {
-  unsigned int pass_row[kPassSmem];
+  unsigned long long pass_row[kPassSmem];   // row handles of the objectness survivors
   float pass_obj[kPassSmem];
   unsigned long long key[kSmemCap];
   float4 box[kSmemCap];
   unsigned long long removed[kSmemCap / 64];
-  unsigned long long diag[64];
-  float4 kbox[64];
+  unsigned long long diag[2][64];
   unsigned int hist[256];
   unsigned long long keep_bits, prefix;
-  int n_pass, n_emit, n_keep, k_rem;
+  int n_pass, n_emit, n_keep[2], k_rem;   // n_keep[ch & 1]: boxes kept before chunk ch (double-buffered: written during the previous chunk)
 };
 
 template <class FE>
@@ -206,28 +239,33 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
                                                                  float* __restrict__ out_boxes, int* __restrict__ out_count) {
   extern __shared__ __align__(16) unsigned char nms_smem_raw[];
   NmsSmem& sm = *reinterpret_cast<NmsSmem*>(nms_smem_raw);
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = static_cast<int>(fe.A), nc = fe.no - 5;
   const bool multi = p.multi_label && nc > 1;
-  unsigned int* g_pass_row = ws.pass_row + static_cast<int64_t>(b) * A;
+  unsigned long long* g_pass_row = ws.pass_row + static_cast<int64_t>(b) * A;
   float* g_pass_obj = ws.pass_obj + static_cast<int64_t>(b) * A;
-  if (tid == 0) { sm.n_pass = 0; sm.n_emit = 0; sm.n_keep = 0; }
+  if (tid == 0) { sm.n_pass = 0; sm.n_emit = 0; sm.n_keep[0] = 0; sm.n_keep[1] = 0; }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");   // the logits are the previous kernels' output
   __syncthreads();
 
-  // ---- A: objectness scan (strict >, general_yolo.py:146)
-  for (int r0 = tid; r0 < A; r0 += 4 * kNmsThreads) {
-    float o[4];
+  // ---- A: objectness scan (strict >, general_yolo.py:146); four independent loads in flight per thread
+  for (int l = 0; l < fe.segments(); ++l) {
+    const int rows = fe.seg_rows(l);
+    for (int i0 = tid; i0 < rows; i0 += 4 * kNmsThreads) {
+      float raw[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int r = r0 + u * kNmsThreads; o[u] = r < A ? fe.obj(b, r) : -1.0f; }
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * kNmsThreads; raw[u] = i < rows ? fe_obj_raw_at(fe, b, l, i) : -INFINITY; }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (o[u] > p.conf_thres) {
-        const int slot = atomicAdd(&sm.n_pass, 1);
-        const unsigned int r = r0 + u * kNmsThreads;
-        if (slot < kPassSmem) { sm.pass_row[slot] = r; sm.pass_obj[slot] = o[u]; }
-        else { g_pass_row[slot] = r; g_pass_obj[slot] = o[u]; }
+      for (int u = 0; u < 4; ++u) {
+        if (!fe.obj_may_pass(raw[u])) continue;
+        const float o = fe.obj(raw[u]);
+        if (o > p.conf_thres) {
+          const int slot = atomicAdd(&sm.n_pass, 1);
+          const unsigned long long h = fe.handle(l, i0 + u * kNmsThreads);
+          if (slot < kPassSmem) { sm.pass_row[slot] = h; sm.pass_obj[slot] = o; }
+          else { g_pass_row[slot] = h; g_pass_obj[slot] = o; }
+        }
       }
     }
   }
@@ -236,27 +274,35 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
   auto pass_row = [&](int i) { return i < kPassSmem ? sm.pass_row[i] : g_pass_row[i]; };
   auto pass_obj = [&](int i) { return i < kPassSmem ? sm.pass_obj[i] : g_pass_obj[i]; };
 
-  // ---- B: candidates.  f(key) is called once per candidate (any order).
+  // ---- B: candidates.  One warp per surviving row, lanes over the classes (coalesced logits); f(key) once per candidate.
   auto for_each_candidate = [&](auto&& f) {
-    if (multi) {  // one candidate per (row, class) with conf > thr, general_yolo.py:191-193
-      const int total = n_pass * nc;
-      for (int idx = tid; idx < total; idx += kNmsThreads) {
-        const int pi = idx / nc, c = idx - pi * nc;
-        const unsigned int r = pass_row(pi);
-        const float conf = __fmul_rn(fe.cls(b, r, c), pass_obj(pi));
-        if (conf > p.conf_thres && class_ok(p.class_mask, c)) f(cand_key(conf, r * static_cast<unsigned int>(nc) + c));
-      }
-    } else {      // best class only (first maximum), general_yolo.py:195-196
-      for (int pi = tid; pi < n_pass; pi += kNmsThreads) {
-        const unsigned int r = pass_row(pi);
-        const float obj = pass_obj(pi);
+    for (int pi = warp; pi < n_pass; pi += kNmsThreads / 32) {
+      const unsigned long long h = pass_row(pi);
+      const float obj = pass_obj(pi);
+      const unsigned int ord0 = fe.row_of(h) * static_cast<unsigned int>(nc);
+      if (multi) {  // one candidate per (row, class) with conf > thr, general_yolo.py:191-193
+        for (int c = lane; c < nc; c += 32) {
+          const float raw = fe.cls_raw(b, h, c);
+          if (!fe.cls_may_pass(raw, obj)) continue;
+          const float conf = __fmul_rn(fe.cls(raw), obj);
+          if (conf > p.conf_thres && class_ok(p.class_mask, c)) f(cand_key(conf, ord0 + c));
+        }
+      } else {      // best class only (first maximum), general_yolo.py:195-196
         float best = -INFINITY;
         int bc = 0;
-        for (int c = 0; c < nc; ++c) {
-          const float conf = __fmul_rn(fe.cls(b, r, c), obj);
+        for (int c = lane; c < nc; c += 32) {
+          const float raw = fe.cls_raw(b, h, c);
+          if (!fe.cls_may_pass(raw, obj)) continue;   // cannot exceed the threshold, so it cannot be a maximum that matters
+          const float conf = __fmul_rn(fe.cls(raw), obj);
           if (conf > best) { best = conf; bc = c; }
         }
-        if (best > p.conf_thres && class_ok(p.class_mask, bc)) f(cand_key(best, r * static_cast<unsigned int>(nc) + bc));
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, sft);
+          const int oc = __shfl_xor_sync(0xffffffffu, bc, sft);
+          if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+        }
+        if (lane == 0 && best > p.conf_thres && class_ok(p.class_mask, bc)) f(cand_key(best, ord0 + bc));
       }
     }
   };
@@ -340,7 +386,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
   for (int i = tid; i < n_sorted; i += kNmsThreads) {
     const unsigned int ord = 0xffffffffu - static_cast<unsigned int>(key[i]);
     const unsigned int r = ord / nc, c = ord - r * nc;
-    float4 bx = fe.box(b, r);
+    float4 bx = fe.box(b, fe.handle_of_row(r));
     if (!p.agnostic) {
       const float off = __fmul_rn(static_cast<float>(c), p.max_wh);
       bx = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
@@ -350,70 +396,75 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
   for (int w = tid; w < (n_p2 >> 6); w += kNmsThreads) removed[w] = 0ull;
   __syncthreads();
 
-  // ---- F: chunked greedy suppression
+  // ---- F: chunked greedy suppression, two barriers per chunk:
+  //   (1) thread 0 resolves chunk ch sequentially from its 64 x 64 IoU bits (the reference's scan restricted to one chunk);
+  //   (2) everybody: the chunk's kept boxes are written out and clear all later boxes; the IoU bits of chunk ch+1 are computed.
   float* out = out_boxes + static_cast<int64_t>(b) * p.max_det * 6;
   const int n_chunks = (n_sorted + 63) >> 6;
-  for (int ch = 0; ch < n_chunks; ++ch) {
+  // 64 x 64 IoU bits of a chunk: thread (i, g) tests box i against boxes 4g..4g+3 of the chunk; 16 lanes OR their nibbles
+  auto chunk_bits = [&](int ch) {
+    const int base = ch << 6, lim = min(64, n_sorted - base);
+    const int i = tid >> 4, g = tid & 15;
+    unsigned long long bits = 0ull;
+    if (i < lim) {
+      const float4 me = box[base + i];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * g + e;
+        if (j > i && j < lim && iou_gt(me, box[base + j], p.iou_thres)) bits |= 1ull << j;
+      }
+    }
+#pragma unroll
+    for (int sft = 8; sft > 0; sft >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, sft);
+    if (g == 0) sm.diag[ch & 1][i] = bits;
+  };
+  if (n_chunks) chunk_bits(0);
+  __syncthreads();
+  int ch = 0;
+  for (; ch < n_chunks; ++ch) {
     const int base = ch << 6;
     const int lim = min(64, n_sorted - base);
-    const int n_keep = sm.n_keep;
-    if (n_keep >= p.max_det) break;   // uniform: n_keep only changes between barriers
-    {
-      // 64 x 64 IoU bits of the chunk: thread (i, g) tests box i against boxes 4g..4g+3; 16 lanes OR their nibbles
-      const int i = tid >> 4, g = tid & 15;
-      unsigned long long bits = 0ull;
-      if (i < lim) {
-        const float4 me = box[base + i];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = 4 * g + e;
-          if (j > i && j < lim && iou_gt(me, box[base + j], p.iou_thres)) bits |= 1ull << j;
-        }
-      }
-#pragma unroll
-      for (int sft = 8; sft > 0; sft >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, sft);
-      if (g == 0) sm.diag[i] = bits;
-    }
-    __syncthreads();
-    if (tid == 0) {   // the sequential part: the reference's scan restricted to one chunk
+    const int n_keep = sm.n_keep[ch & 1];
+    if (n_keep >= p.max_det) break;   // uniform: slot ch & 1 was written during the previous chunk, before a barrier
+    if (tid == 0) {
       unsigned long long rem = removed[ch] | (lim < 64 ? ~0ull << lim : 0ull), kb = 0ull;
       int nk = n_keep;
       while (~rem != 0ull && nk < p.max_det) {
         const int k = __ffsll(static_cast<long long>(~rem)) - 1;
         kb |= 1ull << k;
-        rem |= sm.diag[k] | (1ull << k);
+        rem |= sm.diag[ch & 1][k] | (1ull << k);
         ++nk;
       }
       sm.keep_bits = kb;
-      sm.n_keep = nk;
+      sm.n_keep[(ch + 1) & 1] = nk;
     }
     __syncthreads();
     const unsigned long long kb = sm.keep_bits;
-    const int nk_chunk = __popcll(kb);
-    if (tid < 64 && ((kb >> tid) & 1ull)) {   // kept rows, in order: output (un-offset box, conf, cls) and the chunk's kept list
+    if (tid < 64 && ((kb >> tid) & 1ull)) {   // kept rows, in order: (un-offset box, conf, cls)
       const int q = __popcll(kb & ((1ull << tid) - 1ull));
       const unsigned long long k = key[base + tid];
       const unsigned int ord = 0xffffffffu - static_cast<unsigned int>(k);
       const unsigned int r = ord / nc, c = ord - r * nc;
-      const float4 bx = fe.box(b, r);
+      const float4 bx = fe.box(b, fe.handle_of_row(r));
       float* o = out + static_cast<int64_t>(n_keep + q) * 6;
       o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = __uint_as_float(static_cast<unsigned int>(k >> 32)); o[5] = static_cast<float>(c);
-      sm.kbox[q] = box[base + tid];
     }
-    __syncthreads();
-    if (nk_chunk && ch + 1 < n_chunks) {
-      for (int j = base + 64 + tid; j < n_sorted; j += kNmsThreads) {
-        if ((removed[j >> 6] >> (j & 63)) & 1ull) continue;
-        const float4 bj = box[j];
-        bool hit = false;
-        for (int q = 0; q < nk_chunk && !hit; ++q) hit = iou_gt(sm.kbox[q], bj, p.iou_thres);
-        if (hit) atomicOr(&removed[j >> 6], 1ull << (j & 63));
+    if (ch + 1 < n_chunks) {
+      if (kb) {
+        for (int j = base + 64 + tid; j < n_sorted; j += kNmsThreads) {
+          if ((removed[j >> 6] >> (j & 63)) & 1ull) continue;
+          const float4 bj = box[j];
+          bool hit = false;
+          for (unsigned long long m = kb; m && !hit; m &= m - 1ull) hit = iou_gt(box[base + __ffsll(static_cast<long long>(m)) - 1], bj, p.iou_thres);
+          if (hit) atomicOr(&removed[j >> 6], 1ull << (j & 63));
+        }
       }
+      chunk_bits(ch + 1);
     }
     __syncthreads();
   }
   if (tid == 0) {
-    out_count[b] = sm.n_keep;
+    out_count[b] = sm.n_keep[ch & 1];   // after a break or the last chunk, slot ch & 1 holds the total
     ws.stats[b * 4] = n_pass; ws.stats[b * 4 + 1] = n_cand; ws.stats[b * 4 + 2] = n_sorted; ws.stats[b * 4 + 3] = path;
   }
 }
@@ -427,7 +478,7 @@ size_t carve(NmsWs* ws, char* base, int B, long long A, int cap) {
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
   const int cap_p2 = pow2_at_least(cap);
   ws->stats = reinterpret_cast<int*>(take(sizeof(int) * 4 * B));
-  ws->pass_row = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * B * A));
+  ws->pass_row = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * A));
   ws->pass_obj = reinterpret_cast<float*>(take(sizeof(float) * B * A));
   ws->key = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * cap_p2));
   ws->box = reinterpret_cast<float4*>(take(sizeof(float4) * B * cap));
@@ -497,7 +548,7 @@ extern "C" int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, c
   const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, A, cap);
   YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "box_nms: workspace %zu < %zu bytes", workspace_bytes, need);
   yp::PredRows fe;
-  fe.pred = pred; fe.A = A; fe.no = no;
+  fe.pred = pred; fe.A = A; fe.no = no; fe.thr = p->conf_thres;
   return yp::launch_box_nms(fe, B, *p, cap, ws, out_boxes, out_count, static_cast<cudaStream_t>(stream));
 }
 
@@ -518,6 +569,11 @@ extern "C" int yp_detect_nms(const float* const* logits3, const int32_t* ny3, co
     A += static_cast<long long>(na) * ny3[l] * nx3[l];
   }
   lv.na = na; lv.no = no; lv.A = A;
+  // sigmoid(v) > thr  =>  v > log(thr / (1 - thr)); the margin covers the rounding of expf / the division
+  {
+    const double t = static_cast<double>(p->conf_thres) * (1.0 - 1e-4) - 1e-30;   // a threshold strictly below the real one
+    lv.logit_thr = t <= 0.0 ? -INFINITY : static_cast<float>(log(t / (1.0 - t)) - 1e-4);
+  }
   YP_REQUIRE(A * (no - 5) < (1ll << 31), YP_ERR_SHAPE, "detect_nms: A * nc = %lld exceeds 2^31", (long long)(A * (no - 5)));
   yp::NmsWs ws;
   const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, A, cap);

@@ -549,11 +549,12 @@ class ShapePlan:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.eng.device).cuda_stream)
 
-    def run_input(self, frame: bool):
+    def run_input(self, frame: bool, src: Optional[torch.Tensor] = None):
+        """Input conversion into the stem's operand buffer; ``src`` = another uint8 [B,H,W,3] device buffer than ``frame_in``."""
         L = _lib.lib()
         v = self.view(SliceRef("in_s2d", 0, 16))
         if frame:
-            _lib.check(L.yp_frame_to_s2d(self.frame_in.data_ptr(), self.B, self.H, self.W, C.byref(v), self._stream()))
+            _lib.check(L.yp_frame_to_s2d((self.frame_in if src is None else src).data_ptr(), self.B, self.H, self.W, C.byref(v), self._stream()))
         else:
             _lib.check(L.yp_nchw_to_s2d(self.x_in.data_ptr(), self.B, self.H, self.W, C.byref(v), self._stream()))
 

@@ -80,10 +80,13 @@ class FramePipeline:
             self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self.d_frame = two(lambda: torch.zeros((B, H, W, 3), dtype=torch.uint8, device=dev))
             self._host = [dict(frame=torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True),
-                               counts=torch.empty((3, B), dtype=torch.int32, pin_memory=True), k=0, ev_counts=None, ev_read=None) for _ in range(2)]
+                               counts=torch.zeros((3, B), dtype=torch.int32, pin_memory=True), k=0, used=False,
+                               ev_in=torch.cuda.Event(), ev_read=torch.cuda.Event(), ev_counts=torch.cuda.Event(), ev_done=torch.cuda.Event())
+                          for _ in range(2)]
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         for h in self._host:
             h.update(pts=pin(self.pts[0]), boxes=pin(self.boxes[0]), desc=pin(self.descs[0]), matches=pin(self.matches[0]))
+            h.update({n + "_np": h[n].numpy() for n in ("frame", "counts", "pts", "boxes", "desc", "matches")})
         self.graphs = {}   # graphs bake THIS pipeline's buffer addresses, so they are owned here, not by the shared plan
         self._d2h_bytes = 0
         if old is not None:   # the previous frame's results are the match partner of the next frame
@@ -92,12 +95,14 @@ class FramePipeline:
                 self.pts[k][:, :n].copy_(old["pts"][k]); self.descs[k][:, :n].copy_(old["descs"][k]); self.kcount[k].copy_(old["kcount"][k])
 
     # ---- device work ---------------------------------------------------------------------------
-    def _enqueue(self, k: int, from_frame: bool = True):
-        """Everything for the frame currently in plan.frame_in (or plan.x_in), results into parity-k buffers."""
+    def _enqueue(self, k: int, from_frame: bool = True, with_input: bool = True):
+        """Everything for the frame currently in plan.frame_in (or plan.x_in), results into parity-k buffers.  ``with_input=False``:
+        the stem's operand buffer has already been filled (the host path converts straight from its staging buffer)."""
         L, p, dev = _lib.lib(), self.plan, self.eng.device
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         B, H, W, cfg = self.B, self.H, self.W, self.cfg
-        p.run_input(from_frame)
+        if with_input:
+            p.run_input(from_frame)
         semi = p.bufs["semi"][0]   # [B,Hc,Wc,80] fp32 NHWC
         sB, sH, sW, sC = semi.stride()
 
@@ -142,18 +147,22 @@ class FramePipeline:
         # input + net + fused decode/box NMS (1) + heatmap + keypoints (8 NMS rounds + sweep + collect + emit) + sample + match (3 per image)
         return 1 + net_launches + 1 + 1 + 11 + 1 + (self.B * 3 if self.do_match else 0)
 
-    def step_device(self, from_frame: bool = True):
-        """Process the frame already resident in plan.frame_in / plan.x_in; flips the parity."""
+    def step_device(self, from_frame: bool = True, frame_src: Optional[torch.Tensor] = None):
+        """Process the frame already resident in plan.frame_in / plan.x_in (or in ``frame_src``, a uint8 [B,H,W,3] device buffer
+        that the input conversion then reads directly, launched in front of the graph); flips the parity."""
         k = self.parity
-        key = (k, bool(from_frame))
+        ext = frame_src is not None
+        if ext:
+            self.plan.run_input(True, frame_src)
+        key = (k, "ext" if ext else bool(from_frame))
         g = self.graphs.get(key)
         if g is None:
-            self._enqueue(k, from_frame)            # eager first run: sets function attributes, fills caches
+            self._enqueue(k, from_frame, not ext)   # eager first run: sets function attributes, fills caches
             torch.cuda.synchronize(self.eng.device)
             if self.eng.use_graphs:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._enqueue(k, from_frame)
+                    self._enqueue(k, from_frame, not ext)
                 self.graphs[key] = g
                 # the eager run already produced this frame's results; replaying is idempotent (same inputs)
         else:
@@ -177,26 +186,22 @@ class FramePipeline:
         host stage / unpack one frame while the GPU works on the other, and lets the transfers overlap the kernels."""
         if self._n_submit - self._n_collect >= 2:
             raise RuntimeError("FramePipeline: two frames already in flight; call collect() first")
-        dev = self.eng.device
+        L, dev = _lib.lib(), self.eng.device
         slot = self._n_submit % 2
         h = self._host[slot]
         cur = torch.cuda.current_stream(dev)
-        h["frame"].copy_(torch.from_numpy(np.ascontiguousarray(frames_u8)).view(self.B, self.H, self.W, 3))
-        with torch.cuda.stream(self.s_in):
-            if h["ev_read"] is not None:
-                self.s_in.wait_event(h["ev_read"])          # the staging buffer's previous frame has been consumed
-            self.d_frame[slot].copy_(h["frame"], non_blocking=True)
-            ev_in = torch.cuda.Event(); ev_in.record(self.s_in)
-        cur.wait_event(ev_in)
-        self.plan.frame_in.copy_(self.d_frame[slot])
-        h["ev_read"] = torch.cuda.Event(); h["ev_read"].record(cur)
-        k = self.step_device(True)
-        ev_done = torch.cuda.Event(); ev_done.record(cur)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(ev_done)
-            h["counts"].copy_(self.d_counts[k], non_blocking=True)
-            h["ev_counts"] = torch.cuda.Event(); h["ev_counts"].record(self.s_out)
-        h["k"] = k
+        np.copyto(h["frame_np"], np.asarray(frames_u8).reshape(h["frame_np"].shape))
+        if h["used"]:
+            self.s_in.wait_event(h["ev_read"])              # the staging buffer's previous frame has been consumed
+        _lib.check(L.yp_memcpy_async(self.d_frame[slot].data_ptr(), h["frame"].data_ptr(), h["frame"].numel(), C.c_void_p(self.s_in.cuda_stream)))
+        h["ev_in"].record(self.s_in)
+        cur.wait_event(h["ev_in"])
+        k = self.step_device(True, self.d_frame[slot])
+        h["ev_read"].record(cur)                            # (conservative: the conversion kernel is the only reader)
+        self.s_out.wait_event(h["ev_read"])
+        _lib.check(L.yp_memcpy_async(h["counts"].data_ptr(), self.d_counts[k].data_ptr(), 12 * self.B, C.c_void_p(self.s_out.cuda_stream)))
+        h["ev_counts"].record(self.s_out)
+        h["k"], h["used"] = k, True
         self._n_submit += 1
 
     def _regrow_and_rerun(self):
@@ -220,32 +225,32 @@ class FramePipeline:
             raise RuntimeError("FramePipeline.collect() without a matching submit_host()")
         h = self._host[self._n_collect % 2]
         h["ev_counts"].synchronize()
-        if int(h["counts"][:2].min()) < 0:                  # keypoint or box buffer smaller than this frame needs
+        cnt = h["counts_np"]
+        if cnt[:2].min() < 0:                               # keypoint or box buffer smaller than this frame needs
             self._regrow_and_rerun()
             h = self._host[self._n_collect % 2]
             h["ev_counts"].synchronize()
+            cnt = h["counts_np"]
         self._n_collect += 1
-        k = h["k"]
-        cnt = h["counts"].numpy()
+        L, k, D = _lib.lib(), h["k"], self.D
+        so = C.c_void_p(self.s_out.cuda_stream)
         nbytes = cnt.nbytes
-        with torch.cuda.stream(self.s_out):
-            for b in range(self.B):
-                nk, nb, nm = (int(v) for v in cnt[:, b])
-                for name, src, n in (("pts", self.pts[k], nk), ("desc", self.descs[k], nk), ("boxes", self.boxes[k], nb), ("matches", self.matches[k], nm)):
-                    if n > 0:
-                        h[name][b, :n].copy_(src[b, :n], non_blocking=True)
-                        nbytes += n * src.shape[2] * 4
-            done = torch.cuda.Event(); done.record(self.s_out)
-        done.synchronize()
+        for b in range(self.B):
+            nk, nb, nm = int(cnt[0, b]), int(cnt[1, b]), int(cnt[2, b])
+            for name, src, n, w in (("pts", self.pts[k], nk, 3), ("desc", self.descs[k], nk, D), ("boxes", self.boxes[k], nb, 6), ("matches", self.matches[k], nm, 3)):
+                if n > 0:
+                    row = src.shape[1] * w * 4 * b
+                    _lib.check(L.yp_memcpy_async(h[name].data_ptr() + row, src.data_ptr() + row, n * w * 4, so))
+                    nbytes += n * w * 4
+        h["ev_done"].record(self.s_out)
+        h["ev_done"].synchronize()
         self._d2h_bytes = nbytes
         out = []
         for b in range(self.B):
-            nk, nb, nm = (int(v) for v in cnt[:, b])
-            pts = h["pts"][b, :nk].numpy().astype(np.float64).T.copy()
-            desc = h["desc"][b, :nk].numpy().T.copy()
-            boxes = h["boxes"][b, :nb].numpy().copy()
-            matches = h["matches"][b, :max(nm, 0)].numpy().astype(np.float64).T.copy()
-            out.append((pts, desc, boxes, matches))
+            nk, nb, nm = int(cnt[0, b]), int(cnt[1, b]), max(int(cnt[2, b]), 0)
+            pts = h["pts_np"][b, :nk].astype(np.float64).T
+            desc = h["desc_np"][b, :nk].copy().T            # [D, N] view of a fresh [N, D] copy (same values / shape as the reference's)
+            out.append((pts, desc, h["boxes_np"][b, :nb].copy(), h["matches_np"][b, :nm].astype(np.float64).T))
         return out
 
     def step_host(self, frames_u8: np.ndarray):
