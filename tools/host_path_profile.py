@@ -42,6 +42,56 @@ for i in range(50):
 e1.record(); torch.cuda.synchronize()
 print(f"e2e {N / tot:.1f} frames/s | submit_host {1e6 * np.median(ts):.0f} us, collect {1e6 * np.median(tc):.0f} us (median wall time per frame) | "
       f"device step {e0.elapsed_time(e1) / 50 * 1e3:.0f} us | d2h bytes {pipe.d2h_bytes()}")
+# device-side picture of the same loop: per frame, time from the first kernel to the last (busy) and from one frame's end to the
+# next frame's start (gap), from timing events recorded on the compute stream around step_device
+orig = pipe.step_device
+marks = []
+
+
+def timed_step(*a, **kw):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    k = orig(*a, **kw)
+    e1.record()
+    marks.append((e0, e1))
+    return k
+
+
+pipe.step_device = timed_step
+pipe.submit_host(frames[0])
+for i in range(60):
+    pipe.submit_host(frames[(i + 1) % 4])
+    pipe.collect()
+pipe.collect()
+torch.cuda.synchronize()
+busy = [a.elapsed_time(b) * 1e3 for a, b in marks[5:]]
+gap = [marks[i][1].elapsed_time(marks[i + 1][0]) * 1e3 for i in range(5, len(marks) - 1)]
+print(f"device: busy {np.median(busy):.0f} us per frame (min {min(busy):.0f}, max {max(busy):.0f}), gap between frames {np.median(gap):.0f} us (max {max(gap):.0f})")
+# the same picture for the device-resident loop (bench.py's `value`): frame already in HBM, host far ahead
+marks.clear()
+pool = [torch.from_numpy(f).cuda() for f in frames]
+for i in range(60):
+    pipe.plan.frame_in.copy_(pool[i % 4])
+    timed_step(True)
+torch.cuda.synchronize()
+busy = [a.elapsed_time(b) * 1e3 for a, b in marks[5:]]
+gap = [marks[i][1].elapsed_time(marks[i + 1][0]) * 1e3 for i in range(5, len(marks) - 1)]
+print(f"device loop: busy {np.median(busy):.0f} us per frame, gap {np.median(gap):.0f} us (max {max(gap):.0f})")
+# and for the host loop with the host TWO frames ahead is impossible (two staging slots); instead: host loop without reading results
+marks.clear()
+t0 = time.perf_counter()
+for i in range(60):
+    h = pipe._host[i % 2]
+    if pipe._n_submit - pipe._n_collect >= 2:
+        pipe._host[pipe._n_collect % 2]["ev_counts"].synchronize(); pipe._n_collect += 1
+    pipe.step_device = timed_step
+    pipe.submit_host(frames[i % 4])
+torch.cuda.synchronize()
+pipe._n_collect = pipe._n_submit
+busy = [a.elapsed_time(b) * 1e3 for a, b in marks[5:]]
+gap = [marks[i][1].elapsed_time(marks[i + 1][0]) * 1e3 for i in range(5, len(marks) - 1)]
+print(f"host loop, counts only: busy {np.median(busy):.0f} us per frame, gap {np.median(gap):.0f} us (max {max(gap):.0f}), {60 / (time.perf_counter() - t0):.0f} frames/s")
+pipe.step_device = orig
 import cProfile, pstats  # noqa: E402
 pr = cProfile.Profile()
 pr.enable()

@@ -77,7 +77,10 @@ class FramePipeline:
         # host boundary: frames go up on a copy stream into a device staging buffer, results come back on another copy stream
         # (counts first, then exactly `count` rows of each result), so that neither transfer sits between two frames' kernels
         if old is None:
-            self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            # three copy streams: frames up, counts down, result rows down.  The rows of frame i are requested (collect) after the
+            # counts of frame i+1 were enqueued (submit), so they need their own stream -- on a shared in-order stream they
+            # would wait for frame i+1 to finish (measured: a 200 us hole between frames)
+            self.s_in, self.s_out, self.s_res = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self.d_frame = two(lambda: torch.zeros((B, H, W, 3), dtype=torch.uint8, device=dev))
             self._host = [dict(frame=torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True),
                                counts=torch.zeros((3, B), dtype=torch.int32, pin_memory=True), k=0, used=False,
@@ -233,7 +236,7 @@ class FramePipeline:
             cnt = h["counts_np"]
         self._n_collect += 1
         L, k, D = _lib.lib(), h["k"], self.D
-        so = C.c_void_p(self.s_out.cuda_stream)
+        so = C.c_void_p(self.s_res.cuda_stream)       # frame i is complete (its counts arrived): no device-side dependency needed
         nbytes = cnt.nbytes
         for b in range(self.B):
             nk, nb, nm = int(cnt[0, b]), int(cnt[1, b]), int(cnt[2, b])
@@ -242,7 +245,7 @@ class FramePipeline:
                     row = src.shape[1] * w * 4 * b
                     _lib.check(L.yp_memcpy_async(h[name].data_ptr() + row, src.data_ptr() + row, n * w * 4, so))
                     nbytes += n * w * 4
-        h["ev_done"].record(self.s_out)
+        h["ev_done"].record(self.s_res)
         h["ev_done"].synchronize()
         self._d2h_bytes = nbytes
         out = []
