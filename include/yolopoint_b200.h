@@ -260,6 +260,19 @@ int yp_heatmap(const float* semi, int32_t B, int32_t Hc, int32_t Wc, int64_t sB,
  * out_pts [B,max_pts,3] fp32 (x, y, conf), out_count int32 [B] (-1-n on overflow of max_pts).
  * ---------------------------------------------------------------------------------------------- */
 size_t yp_keypoints_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t max_pts);
+/* Whole-frame pipeline pieces (src/demo.py:151-198 split so that only the in-box filter waits for the box NMS):
+ *   yp_keypoints_collect with boxes == NULL builds the confidence-ordered list of NMS survivors inside the border while the
+ *   detection branch is still running; yp_keypoints_filter then removes the points inside the boxes as an order-preserving
+ *   compaction: out_pts [B,max_pts,3], out_sel [B,max_pts] (index of each kept point in pts_all), out_count [B].  If row_key is
+ *   given it also initialises the keys of the two-way match that follows (rows: n_prev[b] points of the previous frame, columns:
+ *   the kept points).  yp_keypoints_threshold_count copies, per image, the number of pixels with heat >= conf_thresh seen by
+ *   the last yp_keypoints_nms on this workspace (demo.py:152-153 returns early only when that number is 0). */
+int yp_keypoints_filter(const float* pts_all, const int32_t* n_all, int32_t B, int32_t max_pts, int32_t H, int32_t W,
+                        const float* boxes, const int32_t* box_count, int32_t box_ld, float* out_pts, int32_t* out_sel,
+                        int32_t* out_count, const int32_t* n_prev, unsigned long long* row_key, unsigned long long* col_key,
+                        void* stream);
+int yp_keypoints_threshold_count(const void* workspace, size_t workspace_bytes, int32_t B, int32_t H, int32_t W, int32_t max_pts,
+                                 int32_t* out_count, void* stream);
 /* The two halves of yp_keypoints, so that a pipeline can run the NMS (which only needs the heatmap) on another stream
  * while the boxes are still being computed, and collect (border + in-box filters, sort, emit) afterwards. */
 int yp_keypoints_nms(const float* heat, int32_t B, int32_t H, int32_t W, float conf_thresh, int32_t nms_dist, int32_t max_pts,
@@ -298,6 +311,16 @@ int yp_match_partial(const float* d1, const int32_t* n1, int32_t n1_cap, const f
 int yp_match_finalize(const unsigned long long* row_key, const int32_t* n1, int32_t n1_cap,
                       const unsigned long long* col_key, int32_t n2_total, float nn_thresh, float* matches,
                       int32_t* match_count, void* stream);
+/* Whole-frame pipeline form of the two-way match (src/demo.py:300-341 between consecutive frames), all B images in two launches
+ * whose grids do not depend on the buffer capacity: descriptor i of set 1 / 2 of image b is row sel1[b*cap+i] / sel2[b*cap+i] of
+ * d1 / d2 (each [B,cap,D]; sel == NULL: row i), n1 / n2 [B] are device-side counts, row_key / col_key [B,cap] must hold ~0 in their
+ * first n1 / n2 entries (yp_keypoints_filter does that).  matches [B,cap,3], match_count [B].  counts3 (optional, [3,B]): the
+ * frame's result counts (kcount, bcount, match_count) gathered for a single read-back.  yp_gather_rows: dst[b,i,:] = src[b,sel[b,i],:]
+ * for i < count[b] (the compact descriptor block the host reads back). */
+int yp_match_frames(const float* d1, const int32_t* sel1, const int32_t* n1, const float* d2, const int32_t* sel2, const int32_t* n2,
+                    int32_t B, int32_t cap, int32_t D, unsigned long long* row_key, unsigned long long* col_key, float nn_thresh,
+                    float* matches, int32_t* match_count, const int32_t* kcount, const int32_t* bcount, int32_t* counts3, void* stream);
+int yp_gather_rows(const float* src, const int32_t* sel, const int32_t* count, int32_t B, int32_t cap, int32_t D, float* dst, void* stream);
 
 #ifdef __cplusplus
 }

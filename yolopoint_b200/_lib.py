@@ -75,6 +75,10 @@ SIGNATURES = {
     "yp_keypoints_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "yp_keypoints_nms": (_i32, [_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _sz, _vp]),
     "yp_keypoints_collect": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "yp_keypoints_filter": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yp_keypoints_threshold_count": (_i32, [_vp, _sz, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "yp_match_frames": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yp_gather_rows": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "yp_keypoints": (_i32, [_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
     "yp_sample_desc": (_i32, [_vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "yp_match_partial": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),

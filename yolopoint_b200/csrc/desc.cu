@@ -1,5 +1,7 @@
 // Descriptor sampling (bilinear grid_sample + L2 normalise) and brute-force two-way matching
 // (demo.py:200-215, 300-341; evaluations/descriptor_evaluation.py:148-181 of the reference).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace yp {
@@ -94,18 +96,13 @@ __global__ void match_init_kernel(unsigned long long* row_key, int n1_cap, unsig
   if (i < n2_cap) col_key[i] = ~0ull;
 }
 
-__global__ void __launch_bounds__(256) match_tile_kernel(const float* __restrict__ d1, const int* __restrict__ n1p, int n1_cap,
-                                                          const float* __restrict__ d2, const int* __restrict__ n2p, int n2_cap,
-                                                          int D, int col_off, unsigned long long* __restrict__ row_key,
-                                                          unsigned long long* __restrict__ col_key) {
-  __shared__ float As[TK][TM + 4];
-  __shared__ float Bs[TK][TN + 4];
-  __shared__ unsigned long long rmin[TM];
-  __shared__ unsigned long long cmin[TN];
-  const int n1 = n1p ? min(*n1p, n1_cap) : n1_cap;
-  const int n2 = n2p ? min(*n2p, n2_cap) : n2_cap;
-  const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
-  if (i0 >= n1 || j0 >= n2) return;
+// One 64x64 tile of d1 . d2^T (rows i0.., columns j0..) with fused distances and minima.  sel1 / sel2 (optional): row r of the
+// operand is row sel[r] of the buffer (the whole-frame pipeline matches the box-filtered subset of the sampled descriptors
+// without compacting them first).
+__device__ __forceinline__ void match_tile(const float* __restrict__ d1, const int* __restrict__ sel1, int n1, const float* __restrict__ d2,
+                                           const int* __restrict__ sel2, int n2, int D, int col_off, int i0, int j0,
+                                           unsigned long long* __restrict__ row_key, unsigned long long* __restrict__ col_key,
+                                           float (*As)[TM + 4], float (*Bs)[TN + 4], unsigned long long* rmin, unsigned long long* cmin) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4x4 outputs each
   float acc[4][4];
 #pragma unroll
@@ -114,13 +111,16 @@ __global__ void __launch_bounds__(256) match_tile_kernel(const float* __restrict
     for (int c = 0; c < 4; ++c) acc[a][c] = 0.0f;
   if (threadIdx.x < TM) rmin[threadIdx.x] = ~0ull;
   if (threadIdx.x < TN) cmin[threadIdx.x] = ~0ull;
+  const int r = threadIdx.x >> 2, kq = (threadIdx.x & 3) * 4;
+  const bool va_ok = i0 + r < n1, vb_ok = j0 + r < n2;
+  const float* pa = d1 + static_cast<int64_t>(va_ok ? (sel1 ? sel1[i0 + r] : i0 + r) : 0) * D + kq;
+  const float* pb = d2 + static_cast<int64_t>(vb_ok ? (sel2 ? sel2[j0 + r] : j0 + r) : 0) * D + kq;
   for (int k0 = 0; k0 < D; k0 += TK) {
     // 64 rows x 16 k: each thread loads one float4 of A and one of B (rows are D-contiguous)
     {
-      const int r = threadIdx.x >> 2, kq = (threadIdx.x & 3) * 4;
       float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-      if (i0 + r < n1 && k0 + kq < D) va = *reinterpret_cast<const float4*>(d1 + static_cast<int64_t>(i0 + r) * D + k0 + kq);
-      if (j0 + r < n2 && k0 + kq < D) vb = *reinterpret_cast<const float4*>(d2 + static_cast<int64_t>(j0 + r) * D + k0 + kq);
+      if (va_ok && k0 + kq < D) va = *reinterpret_cast<const float4*>(pa + k0);
+      if (vb_ok && k0 + kq < D) vb = *reinterpret_cast<const float4*>(pb + k0);
       As[kq][r] = va.x; As[kq + 1][r] = va.y; As[kq + 2][r] = va.z; As[kq + 3][r] = va.w;
       Bs[kq][r] = vb.x; Bs[kq + 1][r] = vb.y; Bs[kq + 2][r] = vb.z; Bs[kq + 3][r] = vb.w;
     }
@@ -159,15 +159,75 @@ __global__ void __launch_bounds__(256) match_tile_kernel(const float* __restrict
   __syncthreads();
   if (threadIdx.x < TM && i0 + threadIdx.x < n1) atomicMin(&row_key[i0 + threadIdx.x], rmin[threadIdx.x]);
   if (threadIdx.x >= TM && threadIdx.x < TM + TN && j0 + (threadIdx.x - TM) < n2) atomicMin(&col_key[j0 + threadIdx.x - TM], cmin[threadIdx.x - TM]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) match_tile_kernel(const float* __restrict__ d1, const int* __restrict__ n1p, int n1_cap,
+                                                          const float* __restrict__ d2, const int* __restrict__ n2p, int n2_cap,
+                                                          int D, int col_off, unsigned long long* __restrict__ row_key,
+                                                          unsigned long long* __restrict__ col_key) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  __shared__ unsigned long long rmin[TM];
+  __shared__ unsigned long long cmin[TN];
+  const int n1 = n1p ? min(*n1p, n1_cap) : n1_cap;
+  const int n2 = n2p ? min(*n2p, n2_cap) : n2_cap;
+  const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
+  if (i0 >= n1 || j0 >= n2) return;
+  match_tile(d1, nullptr, n1, d2, nullptr, n2, D, col_off, i0, j0, row_key, col_key, As, Bs, rmin, cmin);
+}
+
+// Whole-frame pipeline form: blockIdx.y = image, a fixed number of CTAs per image walk the tiles the device-side counts call for
+// (the grid does not depend on the buffer capacity), operands are rows sel[r] of the per-image descriptor buffers, keys were
+// initialised by kp_filter_kernel.
+__global__ void __launch_bounds__(256) match_frames_kernel(const float* __restrict__ d1, const int* __restrict__ sel1, const int* __restrict__ n1p,
+                                                            const float* __restrict__ d2, const int* __restrict__ sel2, const int* __restrict__ n2p,
+                                                            int cap, int D, unsigned long long* __restrict__ row_key,
+                                                            unsigned long long* __restrict__ col_key) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  __shared__ unsigned long long rmin[TM];
+  __shared__ unsigned long long cmin[TN];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int b = blockIdx.y;
+  const int n1 = min(max(n1p[b], 0), cap), n2 = min(max(n2p[b], 0), cap);
+  const int nt2 = (n2 + TN - 1) / TN, tiles = ((n1 + TM - 1) / TM) * nt2;
+  const int64_t off = static_cast<int64_t>(b) * cap;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int ti = t / nt2, tj = t - ti * nt2;
+    match_tile(d1 + off * D, sel1 ? sel1 + off : nullptr, n1, d2 + off * D, sel2 ? sel2 + off : nullptr, n2, D, 0, ti * TM, tj * TN,
+               row_key + off, col_key + off, As, Bs, rmin, cmin);
+  }
+}
+
+// rows sel[i] (i < count) of src -> consecutive rows of dst; one warp per row, float4 lanes (D % 4 == 0)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ sel, const int* __restrict__ count,
+                                                           int cap, int D, float* __restrict__ dst) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int n = min(max(count[b], 0), cap);
+  const int64_t off = static_cast<int64_t>(b) * cap;
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+    const float4* s = reinterpret_cast<const float4*>(src + (off + sel[off + i]) * D);
+    float4* d = reinterpret_cast<float4*>(dst + (off + i) * D);
+    for (int k = lane; k < D / 4; k += 32) d[k] = __ldg(s + k);
+  }
 }
 
 // ascending-i compaction of mutual nearest neighbours below the threshold (single block)
+// blockIdx.x = image (strides img_keys / img_matches elements; 0 for the single-image API).  counts3 (optional, [3][B]): the
+// frame's result counts (keypoints, boxes, matches) gathered into one array for a single read-back.
 __global__ void match_finalize_kernel(const unsigned long long* __restrict__ row_key, const int* __restrict__ n1p, int n1_cap,
                                       const unsigned long long* __restrict__ col_key, int n2_total, float thr,
-                                      float* __restrict__ matches, int* __restrict__ match_count) {
+                                      float* __restrict__ matches, int* __restrict__ match_count, long long img_keys, long long img_matches,
+                                      const int* __restrict__ kcount, const int* __restrict__ bcount, int* __restrict__ counts3) {
   __shared__ int warp_excl[32];
   __shared__ int block_total;
-  const int n1 = n1p ? min(*n1p, n1_cap) : n1_cap;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int bimg = blockIdx.x, nimg = gridDim.x;
+  row_key += bimg * img_keys; col_key += bimg * img_keys; matches += bimg * img_matches; match_count += bimg;
+  if (n1p) n1p += bimg;
+  const int n1 = n1p ? min(max(*n1p, 0), n1_cap) : n1_cap;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int carry = 0;
   for (int base = 0; base < n1; base += blockDim.x) {
@@ -204,7 +264,10 @@ __global__ void match_finalize_kernel(const unsigned long long* __restrict__ row
     }
     carry += block_total;
   }
-  if (threadIdx.x == 0) *match_count = carry;
+  if (threadIdx.x == 0) {
+    *match_count = carry;
+    if (counts3) { counts3[bimg] = kcount[bimg]; counts3[nimg + bimg] = bcount[bimg]; counts3[2 * nimg + bimg] = carry; }
+  }
 }
 
 }  // namespace
@@ -252,7 +315,48 @@ extern "C" int yp_match_finalize(const unsigned long long* row_key, const int32_
   YP_REQUIRE(nn_thresh >= 0.0f, YP_ERR_ARG, "'nn_thresh' should be non-negative");
   YP_REQUIRE(n1_cap > 0 && n2_total >= 0, YP_ERR_SHAPE, "match_finalize: bad sizes");
   yp::match_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(row_key, n1, n1_cap, col_key, n2_total, nn_thresh, matches,
-                                                                               match_count);
+                                                                               match_count, 0, 0, nullptr, nullptr, nullptr);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+namespace {
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  YP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+  return YP_OK;
+}
+}  // namespace
+
+extern "C" int yp_match_frames(const float* d1, const int32_t* sel1, const int32_t* n1, const float* d2, const int32_t* sel2, const int32_t* n2,
+                               int32_t B, int32_t cap, int32_t D, unsigned long long* row_key, unsigned long long* col_key, float nn_thresh,
+                               float* matches, int32_t* match_count, const int32_t* kcount, const int32_t* bcount, int32_t* counts3,
+                               void* stream) {
+  YP_REQUIRE(d1 && d2 && n1 && n2 && row_key && col_key && matches && match_count, YP_ERR_ARG, "match_frames: null pointer");
+  YP_REQUIRE(B > 0 && cap > 0 && D > 0 && D % 4 == 0, YP_ERR_SHAPE, "match_frames: B=%d cap=%d D=%d (D must be a multiple of 4)", B, cap, D);
+  YP_REQUIRE(yp::aligned16(d1) && yp::aligned16(d2), YP_ERR_ALIGN, "match_frames: descriptors not 16-byte aligned");
+  YP_REQUIRE(nn_thresh >= 0.0f, YP_ERR_ARG, "'nn_thresh' should be non-negative");
+  YP_REQUIRE(!counts3 || (kcount && bcount), YP_ERR_ARG, "match_frames: counts3 needs kcount and bcount");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int per_img = std::max(1, 2 * yp::sm_count() / B);
+  int rc = launch_pdl(yp::match_frames_kernel, dim3(per_img, B), dim3(256), st, d1, sel1, n1, d2, sel2, n2, cap, D, row_key, col_key);
+  if (rc != YP_OK) return rc;
+  return launch_pdl(yp::match_finalize_kernel, dim3(B), dim3(1024), st, static_cast<const unsigned long long*>(row_key), n1, cap,
+                    static_cast<const unsigned long long*>(col_key), cap, nn_thresh, matches, match_count, static_cast<long long>(cap),
+                    static_cast<long long>(cap) * 3, kcount, bcount, counts3);
+}
+
+extern "C" int yp_gather_rows(const float* src, const int32_t* sel, const int32_t* count, int32_t B, int32_t cap, int32_t D, float* dst, void* stream) {
+  YP_REQUIRE(src && sel && count && dst, YP_ERR_ARG, "gather_rows: null pointer");
+  YP_REQUIRE(B > 0 && cap > 0 && D > 0 && D % 4 == 0, YP_ERR_SHAPE, "gather_rows: B=%d cap=%d D=%d", B, cap, D);
+  YP_REQUIRE(yp::aligned16(src) && yp::aligned16(dst), YP_ERR_ALIGN, "gather_rows: buffers not 16-byte aligned");
+  yp::gather_rows_kernel<<<dim3(std::max(1, 2 * yp::sm_count() / B), B), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, sel, count, cap, D, dst);
   YP_LAUNCH_OK();
   return YP_OK;
 }

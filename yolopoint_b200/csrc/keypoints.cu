@@ -74,6 +74,7 @@ struct KpWs {
   unsigned int* tile_undecided;  // [B * tiles]
   unsigned int* round_total;     // [KP_ROUNDS] undecided candidates left after each round
   int* n_list;                 // [B]
+  int* n_thresh;               // [B]  pixels with heat >= conf_thresh (candidates before the NMS), right behind n_list
   unsigned long long* list;    // [B][max_pts]  (ordered_conf << 32) | raster index
 };
 
@@ -97,9 +98,20 @@ constexpr int KT = 32;       // tile edge
 constexpr int KR_MAX = 16;   // largest supported nms_dist
 constexpr int KP_ROUNDS = 8; // parallel rounds before the sequential sweep (dense noise needs ~7)
 
+constexpr int kWinSteps = ((2 * KR_MAX + 1) * (2 * KR_MAX + 1) + 31) / 32;
+
 struct KpTileSmem {
   float* sheat; unsigned long long* keys; unsigned short* cand; unsigned short* sorted; unsigned char* sstate; int* n_list;
+  const short* win_off;   // [kWinSteps * 32] cell offsets of the (2r+1)^2 window positions, see kp_window_offsets
 };
+
+// window position idx (row-major over the (2r+1)^2 window) -> offset in the (KT + 2r)-wide shared-memory tile; 0 for the centre
+// and for the padding positions >= (2r+1)^2.  Computed once per kernel by the whole CTA.
+__device__ __forceinline__ void kp_window_offsets(short* tab, int r) {
+  const int win = 2 * r + 1, RW = KT + 2 * r;
+  for (int idx = threadIdx.x; idx < kWinSteps * 32; idx += blockDim.x)
+    tab[idx] = idx < win * win ? static_cast<short>((idx / win - r) * RW + (idx % win - r)) : static_cast<short>(0);
+}
 
 // One round for tile t.  Returns (to thread 0 only... every thread gets its partial) the number of still-undecided
 // interior candidates counted by this thread.
@@ -140,6 +152,7 @@ __device__ unsigned int kp_process_tile(const float* __restrict__ heat, int B, i
   }
   __syncthreads();
   const int n = *sm.n_list;
+  if (first && threadIdx.x == 0 && n) atomicAdd(&ws.n_thresh[b], n);   // round 0 sees every pixel >= threshold of its tile exactly once
   for (int i = threadIdx.x; i < n; i += blockDim.x) {  // rank sort, descending priority (keys are unique)
     const unsigned long long ki = sm.keys[i];
     int rank = 0;
@@ -148,25 +161,39 @@ __device__ unsigned int kp_process_tile(const float* __restrict__ heat, int B, i
   }
   __syncthreads();
   if (warp == 0) {
+    // Sequential resolve of the tile's undecided candidates in priority order by ONE warp (inside a tile this is the reference's
+    // scan).  The (2r+1)^2 window is walked in 32-cell steps whose cell offsets are computed once per kernel (the first version
+    // divided by the window width for every cell of every candidate: ~3000 cycles per candidate, 60 us per round); a candidate
+    // that an earlier kept one already marked suppressed costs one shared-memory read; a kept candidate marks its window, which
+    // is what nms_fast does (utils/utils.py:165-170).  Priority between two cells of one tile: confidence, then the smaller cell
+    // index (= the smaller raster index: both orders are row-major over the same rows and columns).
+    const int steps = (win * win + 31) / 32;
+    const short* off = sm.win_off + lane;      // off[32 t]: cell offset of window position lane + 32 t (0 = the candidate itself / padding)
     for (int i = 0; i < n; ++i) {
       const int p = sm.sorted[i];
-      const int py = p / RW, px = p - py * RW;
+      if (sm.sstate[p] != 1) continue;          // suppressed by a candidate kept earlier in this round (uniform: same address)
       const float hp = sm.sheat[p];
-      const int gp = (y0 + py) * W + (x0 + px);
       bool kept = false, pend = false;
-      for (int idx = lane; idx < win * win; idx += 32) {
-        const int dy = idx / win - r, dx = idx % win - r;
-        const int q = (py + dy) * RW + (px + dx);
-        const unsigned char sq = sm.sstate[q];
-        if (sq == 2) kept = true;
-        else if (sq == 1 && q != p) {
-          const float hq = sm.sheat[q];
-          const int gq = (y0 + py + dy) * W + (x0 + px + dx);
-          if (hq > hp || (hq == hp && gq < gp)) pend = true;
+      for (int t = 0; t < steps; ++t) {
+        const int o = off[32 * t];
+        if (o != 0) {
+          const int q = p + o;
+          const unsigned char sq = sm.sstate[q];
+          if (sq == 2) kept = true;               // a kept candidate of a neighbouring tile (or of an earlier round)
+          else if (sq == 1) {
+            const float hq = sm.sheat[q];
+            if (hq > hp || (hq == hp && q < p)) pend = true;
+          }
         }
       }
       kept = __any_sync(0xffffffffu, kept);
       pend = __any_sync(0xffffffffu, pend);
+      if (!kept && !pend) {                      // keep p: everything still undecided in its window loses to it
+        for (int t = 0; t < steps; ++t) {
+          const int o = off[32 * t];
+          if (o != 0 && sm.sstate[p + o] == 1) sm.sstate[p + o] = 3;
+        }
+      }
       if (lane == 0) sm.sstate[p] = kept ? 3 : (pend ? 1 : 2);
       __syncwarp();
     }
@@ -195,7 +222,7 @@ __device__ unsigned int kp_process_tile(const float* __restrict__ heat, int B, i
   return undecided;
 }
 
-__device__ __forceinline__ KpTileSmem kp_carve(unsigned char* base, int r, int* n_list) {
+__device__ __forceinline__ KpTileSmem kp_carve(unsigned char* base, int r, int* n_list, const short* win_off) {
   const int RW = KT + 2 * r, RN = RW * RW;
   KpTileSmem sm;
   sm.sheat = reinterpret_cast<float*>(base);
@@ -204,6 +231,7 @@ __device__ __forceinline__ KpTileSmem kp_carve(unsigned char* base, int r, int* 
   sm.sorted = sm.cand + KT * KT;
   sm.sstate = reinterpret_cast<unsigned char*>(sm.sorted + KT * KT);
   sm.n_list = n_list;
+  sm.win_off = win_off;
   return sm;
 }
 
@@ -212,9 +240,11 @@ __global__ void __launch_bounds__(256) kp_round_kernel(const float* __restrict__
   extern __shared__ unsigned char kp_smem[];
   __shared__ int n_list;
   __shared__ unsigned int total;
+  __shared__ short win_off[kWinSteps * 32];
   const int t = blockIdx.x;
   if (!first && ws.tile_undecided[t] == 0) return;
-  const KpTileSmem sm = kp_carve(kp_smem, r, &n_list);
+  kp_window_offsets(win_off, r);
+  const KpTileSmem sm = kp_carve(kp_smem, r, &n_list, win_off);
   if (threadIdx.x == 0) total = 0;
   unsigned int u = kp_process_tile(heat, B, H, W, thr, r, ws, t, first != 0, sm);
 #pragma unroll
@@ -232,8 +262,10 @@ __global__ void __launch_bounds__(256) kp_sweep_kernel(const float* __restrict__
   extern __shared__ unsigned char kp_smem[];
   __shared__ int n_list;
   __shared__ unsigned int total, any;
+  __shared__ short win_off[kWinSteps * 32];
   if (ws.round_total[KP_ROUNDS - 1] == 0) return;   // the parallel rounds finished everything (the usual case)
-  const KpTileSmem sm = kp_carve(kp_smem, r, &n_list);
+  kp_window_offsets(win_off, r);
+  const KpTileSmem sm = kp_carve(kp_smem, r, &n_list, win_off);
   for (;;) {
     if (threadIdx.x == 0) any = 0;
     __syncthreads();
@@ -324,6 +356,78 @@ __global__ void kp_emit_kernel(int W, int max_pts, KpWs ws, float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Whole-frame pipeline, critical path after the box NMS: the keypoint list (NMS survivors inside the border, confidence
+// descending) was built while the detection branch was still running; what is left is the in-box filter (demo.py:178-198) as an
+// ORDER-PRESERVING compaction.  One CTA per image: box slices in shared memory, a block-wide exclusive scan per 1024 points.
+// Also initialises the keys of the two-way match that follows (previous frame x this frame).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) kp_filter_kernel(const float* __restrict__ pts_all, const int* __restrict__ n_all, int max_pts, int H, int W,
+                                                         const float* __restrict__ boxes, const int* __restrict__ box_count, int box_ld,
+                                                         float* __restrict__ out_pts, int* __restrict__ out_sel, int* __restrict__ out_count,
+                                                         const int* __restrict__ n_prev, unsigned long long* __restrict__ row_key,
+                                                         unsigned long long* __restrict__ col_key) {
+  extern __shared__ int sbox[];  // [nb][4] slice bounds x0,x1,y0,y1
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  int nb = 0;
+  if (boxes) {
+    nb = min(max(box_count[b], 0), box_ld);
+    for (int i = tid; i < nb; i += blockDim.x) {
+      const float* bx = boxes + (static_cast<int64_t>(b) * box_ld + i) * 6;
+      int sx, ex, sy, ey;
+      py_slice(static_cast<int>(rintf(bx[0])), static_cast<int>(rintf(bx[2])), W, &sx, &ex);
+      py_slice(static_cast<int>(rintf(bx[1])), static_cast<int>(rintf(bx[3])), H, &sy, &ey);
+      sbox[4 * i] = sx; sbox[4 * i + 1] = ex; sbox[4 * i + 2] = sy; sbox[4 * i + 3] = ey;
+    }
+  }
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  const int n = min(max(n_all[b], 0), max_pts);
+  const float* pin = pts_all + static_cast<int64_t>(b) * max_pts * 3;
+  float* pout = out_pts + static_cast<int64_t>(b) * max_pts * 3;
+  int* sel = out_sel + static_cast<int64_t>(b) * max_pts;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + tid;
+    bool keep = false;
+    float px = 0.f, py = 0.f, pc = 0.f;
+    if (i < n) {
+      px = pin[i * 3]; py = pin[i * 3 + 1]; pc = pin[i * 3 + 2];
+      const int x = static_cast<int>(px), y = static_cast<int>(py);
+      keep = true;
+      for (int j = 0; j < nb && keep; ++j) keep = !(x >= sbox[4 * j] && x < sbox[4 * j + 1] && y >= sbox[4 * j + 2] && y < sbox[4 * j + 3]);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_sum[warp] = __popc(m);
+    __syncthreads();
+    const int carry = carry_s;
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_sum[w];
+    if (keep) {
+      const int pos = carry + before + __popc(m & ((1u << lane) - 1u));
+      pout[pos * 3] = px; pout[pos * 3 + 1] = py; pout[pos * 3 + 2] = pc;
+      sel[pos] = i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < (blockDim.x >> 5); ++w) tot += warp_sum[w];
+      carry_s = carry + tot;
+    }
+    __syncthreads();
+  }
+  const int kept = carry_s;
+  if (tid == 0) out_count[b] = n_all[b] < 0 ? n_all[b] : kept;   // an overflowed list stays flagged
+  if (row_key) {
+    const int np = n_prev ? min(max(n_prev[b], 0), max_pts) : 0;
+    for (int i = tid; i < np; i += blockDim.x) row_key[static_cast<int64_t>(b) * max_pts + i] = ~0ull;
+    for (int i = tid; i < kept; i += blockDim.x) col_key[static_cast<int64_t>(b) * max_pts + i] = ~0ull;
+  }
+}
+
 size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 size_t carve(KpWs* ws, char* base, int B, int H, int W, int max_pts) {
@@ -332,7 +436,8 @@ size_t carve(KpWs* ws, char* base, int B, int H, int W, int max_pts) {
   ws->state = reinterpret_cast<unsigned char*>(take(static_cast<size_t>(B) * H * W));
   ws->tile_undecided = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * B * ((H + 31) / 32) * ((W + 31) / 32)));
   ws->round_total = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 16));
-  ws->n_list = reinterpret_cast<int*>(take(sizeof(int) * B));
+  ws->n_list = reinterpret_cast<int*>(take(sizeof(int) * 2 * B));
+  ws->n_thresh = ws->n_list ? ws->n_list + B : nullptr;
   ws->list = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * max_pts));
   return off;
 }
@@ -379,8 +484,7 @@ extern "C" int yp_keypoints_nms(const float* heat, int32_t B, int32_t H, int32_t
     raised = true;
   }
   const int tiles = B * yp::ceil_div(H, yp::KT) * yp::ceil_div(W, yp::KT);
-  YP_CUDA_OK(cudaMemsetAsync(ws.n_list, 0, sizeof(int) * B, st));
-  YP_CUDA_OK(cudaMemsetAsync(ws.round_total, 0, sizeof(unsigned int) * 16, st));
+  YP_CUDA_OK(cudaMemsetAsync(ws.round_total, 0, yp::align_up(sizeof(unsigned int) * 16) + sizeof(int) * 2 * B, st));   // round_total, n_list, n_thresh (adjacent)
   for (int round = 0; round < yp::KP_ROUNDS; ++round)
     yp::kp_round_kernel<<<tiles, 256, nms_smem, st>>>(heat, B, H, W, conf_thresh, nms_dist, ws, round == 0 ? 1 : 0, round);
   yp::kp_sweep_kernel<<<1, 256, nms_smem, st>>>(heat, B, H, W, conf_thresh, nms_dist, ws, tiles);
@@ -418,4 +522,38 @@ extern "C" int yp_keypoints(const float* heat, int32_t B, int32_t H, int32_t W, 
   const int rc = yp_keypoints_nms(heat, B, H, W, conf_thresh, nms_dist, max_pts, workspace, workspace_bytes, stream);
   if (rc != YP_OK) return rc;
   return yp_keypoints_collect(heat, B, H, W, border, boxes, box_count, box_ld, out_pts, out_count, max_pts, workspace, workspace_bytes, stream);
+}
+
+extern "C" int yp_keypoints_filter(const float* pts_all, const int32_t* n_all, int32_t B, int32_t max_pts, int32_t H, int32_t W,
+                                   const float* boxes, const int32_t* box_count, int32_t box_ld, float* out_pts, int32_t* out_sel,
+                                   int32_t* out_count, const int32_t* n_prev, unsigned long long* row_key, unsigned long long* col_key,
+                                   void* stream) {
+  YP_REQUIRE(pts_all && n_all && out_pts && out_sel && out_count, YP_ERR_ARG, "keypoints_filter: null pointer");
+  YP_REQUIRE(B > 0 && max_pts > 0 && H > 0 && W > 0, YP_ERR_SHAPE, "keypoints_filter: bad shape");
+  YP_REQUIRE(!boxes || (box_count && box_ld > 0 && box_ld <= 8192), YP_ERR_ARG, "keypoints_filter: boxes need box_count and 0 < box_ld <= 8192");
+  YP_REQUIRE(!row_key || col_key, YP_ERR_ARG, "keypoints_filter: row_key needs col_key");
+  const size_t smem = boxes ? sizeof(int) * 4 * box_ld : 0;
+  if (smem > 40 * 1024) {
+    static thread_local bool raised = false;
+    if (!raised) { YP_CUDA_OK(cudaFuncSetAttribute(yp::kp_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024)); raised = true; }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  YP_CUDA_OK(cudaLaunchKernelEx(&cfg, yp::kp_filter_kernel, pts_all, n_all, max_pts, H, W, boxes, box_count, box_ld, out_pts, out_sel, out_count,
+                                n_prev, row_key, col_key));
+  return YP_OK;
+}
+
+extern "C" int yp_keypoints_threshold_count(const void* workspace, size_t workspace_bytes, int32_t B, int32_t H, int32_t W, int32_t max_pts,
+                                            int32_t* out_count, void* stream) {
+  YP_REQUIRE(workspace && out_count, YP_ERR_ARG, "keypoints_threshold_count: null pointer");
+  yp::KpWs ws;
+  const size_t need = yp::carve(&ws, static_cast<char*>(const_cast<void*>(workspace)), B, H, W, max_pts);
+  YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "keypoints_threshold_count: workspace %zu < %zu bytes", workspace_bytes, need);
+  YP_CUDA_OK(cudaMemcpyAsync(out_count, ws.n_thresh, sizeof(int) * B, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return YP_OK;
 }

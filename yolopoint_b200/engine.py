@@ -558,6 +558,11 @@ class ShapePlan:
         else:
             _lib.check(L.yp_nchw_to_s2d(self.x_in.data_ptr(), self.B, self.H, self.W, C.byref(v), self._stream()))
 
+    def side_stream(self, lane: int) -> "torch.cuda.Stream":
+        if self._side is None:
+            self._side = {ln: torch.cuda.Stream(self.eng.device) for ln in (1, 2, 3, 4)}
+        return self._side[lane]
+
     def run_net(self, tails=None):
         """Launch list; the keypoint and descriptor heads run on side streams that fork from / join the current stream
         (also under graph capture), so their small grids overlap the detection branch.  ``tails`` maps a lane to a
@@ -572,8 +577,7 @@ class ShapePlan:
             for lane in sorted(tails):
                 tails[lane](st)
             return
-        if self._side is None:
-            self._side = {lane: torch.cuda.Stream(dev) for lane in (1, 2, 3, 4)}
+        self.side_stream(1)
         started = {}
         ptr = {0: C.c_void_p(main.cuda_stream)}
         for lane, f in self.launches:
@@ -584,7 +588,7 @@ class ShapePlan:
                 started[lane] = True
                 ptr[lane] = C.c_void_p(self._side[lane].cuda_stream)
             f(ptr[lane])
-        for lane in started:
+        for lane in started:   # in the order the lanes started (a later lane's tail may wait for an earlier lane's event)
             if lane in tails:
                 tails[lane](ptr[lane])
             ev = torch.cuda.Event()

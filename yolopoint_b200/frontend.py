@@ -67,10 +67,14 @@ class FramePipeline:
         self.boxes, self.bcount = two(lambda: z(B, md, 6)), two(lambda: z(B, dt=torch.int32))
         self.heat = z(B, H, W)
         self.pts, self.kcount = two(lambda: z(B, max_pts, 3)), two(lambda: z(B, dt=torch.int32))
-        self.descs = two(lambda: z(B, max_pts, D))
+        self.descs = two(lambda: z(B, max_pts, D))                       # box-filtered descriptors, compact (what the host reads)
+        # NMS survivors inside the border BEFORE the in-box filter and their descriptors: built while the detection branch is still
+        # running; `sel` = indices of the points that passed the filter.  The match reads rows sel[i] of descs_all directly.
+        self.pts_all, self.n_all = z(B, max_pts, 3), z(B, dt=torch.int32)
+        self.descs_all, self.sel = two(lambda: z(B, max_pts, D)), two(lambda: z(B, max_pts, dt=torch.int32))
         self.row_key, self.col_key = z(B, max_pts, dt=torch.int64), z(B, max_pts, dt=torch.int64)
         self.matches, self.mcount = two(lambda: z(B, max_pts, 3)), two(lambda: z(B, dt=torch.int32))
-        self.d_counts = two(lambda: z(3, B, dt=torch.int32))
+        self.d_counts = two(lambda: z(4, B, dt=torch.int32))            # keypoints, boxes, matches, pixels >= detection threshold
         self.ws_nms = torch.empty(L.yp_box_nms_workspace_bytes(B, self.plan.A, self.eng.net.no, self.nms_cap), dtype=torch.uint8, device=dev)
         self.ws_kp = torch.empty(L.yp_keypoints_workspace_bytes(B, H, W, max_pts), dtype=torch.uint8, device=dev)
         self.nms_params = YpNmsParams(float(self.cfg["conf_thres_box"]), float(self.cfg["iou_thres_box"]), 1, 1, int(md), 30000, 7680.0, None)
@@ -83,7 +87,7 @@ class FramePipeline:
             self.s_in, self.s_out, self.s_res = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self.d_frame = two(lambda: torch.zeros((B, H, W, 3), dtype=torch.uint8, device=dev))
             self._host = [dict(frame=torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True),
-                               counts=torch.zeros((3, B), dtype=torch.int32, pin_memory=True), k=0, used=False,
+                               counts=torch.zeros((4, B), dtype=torch.int32, pin_memory=True), k=0, used=False,
                                ev_in=torch.cuda.Event(), ev_read=torch.cuda.Event(), ev_counts=torch.cuda.Event(), ev_done=torch.cuda.Event())
                           for _ in range(2)]
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -93,9 +97,9 @@ class FramePipeline:
         self.graphs = {}   # graphs bake THIS pipeline's buffer addresses, so they are owned here, not by the shared plan
         self._d2h_bytes = 0
         if old is not None:   # the previous frame's results are the match partner of the next frame
-            n = old["pts"][0].shape[1]
+            n = old["sel"][0].shape[1]
             for k in range(2):
-                self.pts[k][:, :n].copy_(old["pts"][k]); self.descs[k][:, :n].copy_(old["descs"][k]); self.kcount[k].copy_(old["kcount"][k])
+                self.descs_all[k][:, :n].copy_(old["descs_all"][k]); self.sel[k][:, :n].copy_(old["sel"][k]); self.kcount[k].copy_(old["kcount"][k])
 
     # ---- device work ---------------------------------------------------------------------------
     def _enqueue(self, k: int, from_frame: bool = True, with_input: bool = True):
@@ -109,12 +113,29 @@ class FramePipeline:
         semi = p.bufs["semi"][0]   # [B,Hc,Wc,80] fp32 NHWC
         sB, sH, sW, sC = semi.stride()
 
-        def kp_tail(stp):   # runs on the keypoint head's stream, overlapping the detection branch
+        desc = p.bufs["desc"][0]   # [B,Hc,Wc,D] fp32 NHWC, unit norm
+        dB, dH, dW, dD = desc.stride()
+        multi = self.eng.multi_stream   # False: every launch on the current stream, already ordered
+        ev_kp = torch.cuda.Event() if multi else None
+        nthr = self.d_counts[k][3]
+
+        def kp_tail(stp):   # keypoint head's stream, under the detection branch: heatmap, NMS, border filter, confidence order
             _lib.check(L.yp_heatmap(semi.data_ptr(), B, H // 8, W // 8, sB, sC, sH, sW, self.heat_variant, self.heat.data_ptr(), stp))
             _lib.check(L.yp_keypoints_nms(self.heat.data_ptr(), B, H, W, float(cfg["detection_threshold"]), int(cfg["nms"]), self.max_pts,
                                           self.ws_kp.data_ptr(), self.ws_kp.numel(), stp))
+            _lib.check(L.yp_keypoints_collect(self.heat.data_ptr(), B, H, W, 4, None, None, 0, self.pts_all.data_ptr(), self.n_all.data_ptr(),
+                                              self.max_pts, self.ws_kp.data_ptr(), self.ws_kp.numel(), stp))
+            _lib.check(L.yp_keypoints_threshold_count(self.ws_kp.data_ptr(), self.ws_kp.numel(), B, H, W, self.max_pts, nthr.data_ptr(), stp))
+            if multi:
+                ev_kp.record(p.side_stream(1))
 
-        p.run_net(tails={1: kp_tail})
+        def desc_tail(stp):  # descriptor head's stream: sample every listed point (the in-box filter only drops points later)
+            if multi:
+                p.side_stream(2).wait_event(ev_kp)
+            _lib.check(L.yp_sample_desc(desc.data_ptr(), B, self.D, H // 8, W // 8, dB, dD, dH, dW, H, W, self.pts_all.data_ptr(),
+                                        self.n_all.data_ptr(), self.max_pts, self.descs_all[k].data_ptr(), stp))
+
+        p.run_net(tails={1: kp_tail, 2: desc_tail})
         # Detect decode fused into the box NMS kernel: pred [B,A,85] is never materialised here
         dets = [p.bufs[f"det{i}"] for i in range(3)]
         lg = (C.c_void_p * 3)(*[d.data_ptr() for d in dets])
@@ -125,30 +146,36 @@ class FramePipeline:
         boxes, bcount = self.boxes[k], self.bcount[k]
         _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, self.eng.net.no, C.byref(self.nms_params), self.nms_cap,
                                    boxes.data_ptr(), bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), st))
-        _lib.check(L.yp_keypoints_collect(self.heat.data_ptr(), B, H, W, 4, boxes.data_ptr() if self.filter_pts else None,
-                                          bcount.data_ptr() if self.filter_pts else None, boxes.shape[1] if self.filter_pts else 0,
-                                          self.pts[k].data_ptr(), self.kcount[k].data_ptr(), self.max_pts, self.ws_kp.data_ptr(),
-                                          self.ws_kp.numel(), st))
-        desc = p.bufs["desc"][0]   # [B,Hc,Wc,D] fp32 NHWC, unit norm
-        dB, dH, dW, dD = desc.stride()
-        _lib.check(L.yp_sample_desc(desc.data_ptr(), B, self.D, H // 8, W // 8, dB, dD, dH, dW, H, W, self.pts[k].data_ptr(),
-                                    self.kcount[k].data_ptr(), self.max_pts, self.descs[k].data_ptr(), st))
-        if self.do_match:
-            for b in range(B):  # previous frame (parity 1-k) is desc1, current is desc2, as PointTracker.update does
-                _lib.check(L.yp_match_partial(self.descs[1 - k][b].data_ptr(), self.kcount[1 - k][b:].data_ptr(), self.max_pts,
-                                              self.descs[k][b].data_ptr(), self.kcount[k][b:].data_ptr(), self.max_pts, self.D, 0,
-                                              self.row_key[b].data_ptr(), self.col_key[b].data_ptr(), st))
-                _lib.check(L.yp_match_finalize(self.row_key[b].data_ptr(), self.kcount[1 - k][b:].data_ptr(), self.max_pts,
-                                               self.col_key[b].data_ptr(), self.max_pts, float(cfg["nn_thresh"]), self.matches[k][b].data_ptr(),
-                                               self.mcount[k][b:].data_ptr(), st))
+        # critical path after the box NMS: in-box filter (order-preserving compaction) -> match with the previous frame
+        fp = self.filter_pts
+        _lib.check(L.yp_keypoints_filter(self.pts_all.data_ptr(), self.n_all.data_ptr(), B, self.max_pts, H, W, boxes.data_ptr() if fp else None,
+                                         bcount.data_ptr() if fp else None, boxes.shape[1] if fp else 0, self.pts[k].data_ptr(),
+                                         self.sel[k].data_ptr(), self.kcount[k].data_ptr(), self.kcount[1 - k].data_ptr(),
+                                         self.row_key.data_ptr(), self.col_key.data_ptr(), st))
+        main = torch.cuda.current_stream(dev)
+        side = p.side_stream(2) if multi else main
+        if multi:   # the compact descriptor block is only needed by the host: gather it beside the match
+            ev_f = torch.cuda.Event(); ev_f.record(main); side.wait_event(ev_f)
+        _lib.check(L.yp_gather_rows(self.descs_all[k].data_ptr(), self.sel[k].data_ptr(), self.kcount[k].data_ptr(), B, self.max_pts, self.D,
+                                    self.descs[k].data_ptr(), C.c_void_p(side.cuda_stream)))
         dc = self.d_counts[k]
-        dc[0].copy_(self.kcount[k]); dc[1].copy_(bcount); dc[2].copy_(self.mcount[k])
+        if self.do_match:   # previous frame (parity 1-k) is desc1, current is desc2, as PointTracker.update does
+            _lib.check(L.yp_match_frames(self.descs_all[1 - k].data_ptr(), self.sel[1 - k].data_ptr(), self.kcount[1 - k].data_ptr(),
+                                         self.descs_all[k].data_ptr(), self.sel[k].data_ptr(), self.kcount[k].data_ptr(), B, self.max_pts,
+                                         self.D, self.row_key.data_ptr(), self.col_key.data_ptr(), float(cfg["nn_thresh"]),
+                                         self.matches[k].data_ptr(), self.mcount[k].data_ptr(), self.kcount[k].data_ptr(), bcount.data_ptr(),
+                                         dc.data_ptr(), st))
+        else:
+            dc[0].copy_(self.kcount[k]); dc[1].copy_(bcount); dc[2].zero_()
+        if multi:
+            ev_g = torch.cuda.Event(); ev_g.record(side); main.wait_event(ev_g)
 
     def n_launches(self) -> int:
         """Kernels of this library launched per frame batch (for bench.py's gpu_launches)."""
         net_launches = len(self.plan.launches)
-        # input + net + fused decode/box NMS (1) + heatmap + keypoints (8 NMS rounds + sweep + collect + emit) + sample + match (3 per image)
-        return 1 + net_launches + 1 + 1 + 11 + 1 + (self.B * 3 if self.do_match else 0)
+        # input + net + fused decode / box NMS (1) + heatmap + keypoints (8 NMS rounds + sweep + collect + emit) + sample + in-box filter +
+        # descriptor gather + match (tiles + finalize, all images)
+        return 1 + net_launches + 1 + 1 + 11 + 1 + 1 + 1 + (2 if self.do_match else 0)
 
     def step_device(self, from_frame: bool = True, frame_src: Optional[torch.Tensor] = None):
         """Process the frame already resident in plan.frame_in / plan.x_in (or in ``frame_src``, a uint8 [B,H,W,3] device buffer
@@ -202,7 +229,7 @@ class FramePipeline:
         k = self.step_device(True, self.d_frame[slot])
         h["ev_read"].record(cur)                            # (conservative: the conversion kernel is the only reader)
         self.s_out.wait_event(h["ev_read"])
-        _lib.check(L.yp_memcpy_async(h["counts"].data_ptr(), self.d_counts[k].data_ptr(), 12 * self.B, C.c_void_p(self.s_out.cuda_stream)))
+        _lib.check(L.yp_memcpy_async(h["counts"].data_ptr(), self.d_counts[k].data_ptr(), 16 * self.B, C.c_void_p(self.s_out.cuda_stream)))
         h["ev_counts"].record(self.s_out)
         h["k"], h["used"] = k, True
         self._n_submit += 1
@@ -212,7 +239,7 @@ class FramePipeline:
         flight (their host copies are still staged).  The previous frame's keypoints / descriptors are carried over."""
         torch.cuda.synchronize(self.eng.device)
         pending = [(self._host[i % 2]["frame"].numpy().copy(), self._host[i % 2]["k"]) for i in range(self._n_collect, self._n_submit)]
-        old = dict(pts=self.pts, descs=self.descs, kcount=self.kcount)
+        old = dict(descs_all=self.descs_all, sel=self.sel, kcount=self.kcount)
         self.max_pts, self.nms_cap = self.max_pts_bound(), NMS_CAP
         self._alloc(old)
         self.regrown += 1
@@ -248,6 +275,7 @@ class FramePipeline:
         h["ev_done"].record(self.s_res)
         h["ev_done"].synchronize()
         self._d2h_bytes = nbytes
+        self.last_threshold_counts = cnt[3].copy()          # pixels >= detection threshold per image (before the NMS)
         out = []
         for b in range(self.B):
             nk, nb, nm = int(cnt[0, b]), int(cnt[1, b]), max(int(cnt[2, b]), 0)
@@ -337,8 +365,9 @@ class YoloPointFrontend:
         boxes[:, :4] = (boxes[:, :4] + torch.tensor([ctw, cth, ctw, cth], dtype=boxes.dtype)) / resize_fac
         if self.crop_resize:
             cr = self.crop_resize
-            pts[:, 0] += cr[2]
-            pts[:, 1] += cr[0]
+            if pts.shape[1] >= 2:    # (the reference indexes the first two POINTS here and raises IndexError with fewer)
+                pts[:, 0] += cr[2]
+                pts[:, 1] += cr[0]
             boxes[:, :4] += torch.tensor([cr[2], cr[0], cr[2], cr[0]], dtype=boxes.dtype)
         return pts, boxes
 
@@ -354,8 +383,11 @@ class YoloPointFrontend:
         pts, desc, boxes, matches = self.pipeline(H, W).step_host(img[None])[0]
         self.last_matches = matches
         obj = torch.from_numpy(boxes)
-        if pts.shape[1] == 0:
-            return np.zeros((3, 0)), None, None  # src/demo.py:152-153
+        if int(self.pipeline(H, W).last_threshold_counts[0]) == 0:
+            return np.zeros((3, 0)), None, None  # src/demo.py:152-153: no heat-map pixel reaches the detection threshold
+        if pts.shape[1] == 0:                    # the border / in-box filters removed every point: src/demo.py:202-203
+            pts, obj = self.restore_coords(pts, obj, cth, ctw, resize_fac)
+            return pts, np.zeros((self.pipeline(H, W).D, 0)), [obj]
         if self.filter_pts and rostpc:
             pts, desc, dropped = self.template_filter(pts, desc, rostpc)
             if dropped:
