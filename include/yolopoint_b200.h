@@ -233,7 +233,15 @@ size_t yp_box_nms_workspace_bytes(int32_t B, int64_t A, int32_t no, int32_t cap)
  * (level, anchor, w/h) in pixels.  Same outputs / workspace as yp_box_nms with A = sum_l na*ny*nx. */
 int yp_detect_nms(const float* const* logits3_host, const int32_t* ny3_host, const int32_t* nx3_host, const int32_t* ldc3_host,
                   const float* stride3_host, const float* anchors_px_host, int32_t B, int32_t na, int32_t no, const YpNmsParams* p,
-                  int32_t cap, float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+                  int32_t cap, float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, int32_t prescanned_levels,
+                  void* stream);
+/* Optional: list the candidates of ONE level ahead of yp_detect_nms, e.g. on a side stream as soon as that level's Detect
+ * convolution is done (levels 0 / 1 hold 95 % of the rows and finish long before level 2).  yp_detect_nms then gets the bit mask of
+ * the levels listed this way (prescanned_levels, 0 = none) and only scans the others.  Same arguments / workspace as yp_detect_nms;
+ * the workspace must be zero-filled once before the first use (the calls leave its counters zero again). */
+int yp_detect_prescan(const float* const* logits3_host, const int32_t* ny3_host, const int32_t* nx3_host, const int32_t* ldc3_host,
+                      const float* stride3_host, const float* anchors_px_host, int32_t B, int32_t na, int32_t no, const YpNmsParams* p,
+                      int32_t cap, int32_t level, void* workspace, size_t workspace_bytes, void* stream);
 int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, const YpNmsParams* p, int32_t cap,
                float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -53,7 +53,7 @@ def main():
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     convs = iter(plan.conv_descs)
     bad = 0
-    for op, (lane, f) in zip(eng.net.ops, plan.launches):
+    for op, (lane, f, _name) in zip(eng.net.ops, plan.launches):
         if not isinstance(op, ConvOp):
             f(st)
             continue

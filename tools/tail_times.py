@@ -37,7 +37,7 @@ def stage_nms():
     strd = (C.c_float * 3)(*[float(v) for v in pipe.eng.stride])
     anc = (C.c_float * 18)(*[float(v) for row in pipe.eng.anchors_px for v in row])
     _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, pipe.eng.net.no, C.byref(pipe.nms_params), pipe.nms_cap, pipe.boxes[0].data_ptr(),
-                               pipe.bcount[0].data_ptr(), pipe.ws_nms.data_ptr(), pipe.ws_nms.numel(), st()))
+                               pipe.bcount[0].data_ptr(), pipe.ws_nms.data_ptr(), pipe.ws_nms.numel(), 0, st()))
 
 
 def stage_heat_kpnms():
@@ -65,5 +65,20 @@ def time_graph(fn, reps=20):
     return best
 
 
-for name, fn in (("Detect decode + box NMS (1 kernel)", stage_nms), ("heatmap + keypoint NMS rounds (side lane)", stage_heat_kpnms)):
-    print(f"{name:45s} {time_graph(fn):8.2f} us")
+def stage_nms_prescanned():
+    dets = [p.bufs[f"det{i}"] for i in range(3)]
+    lg = (C.c_void_p * 3)(*[d.data_ptr() for d in dets])
+    ny = (C.c_int32 * 3)(*[d.shape[2] for d in dets]); nx = (C.c_int32 * 3)(*[d.shape[3] for d in dets])
+    ldc = (C.c_int32 * 3)(*[d.shape[4] for d in dets])
+    strd = (C.c_float * 3)(*[float(v) for v in pipe.eng.stride])
+    anc = (C.c_float * 18)(*[float(v) for row in pipe.eng.anchors_px for v in row])
+    for lvl in (0, 1):
+        _lib.check(L.yp_detect_prescan(lg, ny, nx, ldc, strd, anc, B, 3, pipe.eng.net.no, C.byref(pipe.nms_params), pipe.nms_cap, lvl,
+                                       pipe.ws_nms.data_ptr(), pipe.ws_nms.numel(), st()))
+    _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, pipe.eng.net.no, C.byref(pipe.nms_params), pipe.nms_cap, pipe.boxes[0].data_ptr(),
+                               pipe.bcount[0].data_ptr(), pipe.ws_nms.data_ptr(), pipe.ws_nms.numel(), 3, st()))
+
+
+for name, fn in (("Detect decode + box NMS (1 kernel, scans all levels)", stage_nms), ("prescan levels 0, 1 (2 kernels) + box NMS", stage_nms_prescanned),
+                 ("heatmap + keypoint NMS rounds (side lane)", stage_heat_kpnms)):
+    print(f"{name:55s} {time_graph(fn):8.2f} us")

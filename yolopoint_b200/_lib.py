@@ -70,7 +70,9 @@ SIGNATURES = {
     "yp_box_nms_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32]),
     "yp_box_nms": (_i32, [_vp, _i32, _i64, _i32, _PN, _i32, _vp, _vp, _vp, _sz, _vp]),
     "yp_detect_nms": (_i32, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
-                             C.POINTER(C.c_float), _i32, _i32, _i32, _PN, _i32, _vp, _vp, _vp, _sz, _vp]),
+                             C.POINTER(C.c_float), _i32, _i32, _i32, _PN, _i32, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "yp_detect_prescan": (_i32, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float), _i32, _i32, _i32, _PN, _i32, _i32, _vp, _sz, _vp]),
     "yp_heatmap": (_i32, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "yp_keypoints_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "yp_keypoints_nms": (_i32, [_vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _sz, _vp]),

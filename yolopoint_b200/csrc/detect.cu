@@ -106,6 +106,8 @@ struct NmsWs {
   unsigned long long* key;     // [B][cap_p2]
   float4* box;                 // [B][cap]   NMS boxes (class offset applied) in sorted order
   unsigned long long* removed; // [B][cap_p2 / 64]
+  int* pre_n;                  // [B][2]  prescan: candidates emitted / true number of (row, class) pairs; zero between frames
+  unsigned long long* pre_key; // [B][kSmemCap]  prescan: candidate keys of the levels scanned ahead of the NMS kernel
 };
 
 __device__ __forceinline__ bool class_ok(const uint32_t* class_mask, int c) {
@@ -222,6 +224,76 @@ __device__ __forceinline__ unsigned long long cand_key(float conf, unsigned int 
   return (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xffffffffu - ord);   // conf > 0: bits are monotone
 }
 
+
+// The candidates of ONE objectness survivor, evaluated by one warp (lanes over the classes: coalesced logits).  f(key) is called
+// once per candidate; returns (to every lane) how many (row, class) pairs exceed the threshold.
+//
+// `dedupe` (agnostic multi-label NMS, iou_thres < 1): the candidates of one row share one box, so their mutual IoU is exactly 1
+// (inter == area_i == area_j bit for bit, (a + a) - a == a in fp32) and only the most confident one can ever be kept: it
+// precedes the others in the sort, suppresses them if it is kept, and whatever suppresses it (a kept box of higher confidence
+// with IoU > thr) suppresses them too -- same box, same IoU.  Emitting only that candidate leaves the output unchanged and cuts
+// the sort / suppression work by the number of classes per row (5.5 on the benchmark frames).  Boxes without a finite positive
+// area are exempt (their IoU is 0 or NaN, nothing is suppressed).  The caller must fall back to all candidates when their true
+// number exceeds max_nms (the reference's top-max_nms cut is taken over all of them).
+template <class FE, class F>
+__device__ __forceinline__ int warp_row_candidates(const FE& fe, int b, unsigned long long h, float obj, const YpNmsParams& p, int nc,
+                                                   bool multi, bool dedupe, int lane, F&& f) {
+  const unsigned int ord0 = fe.row_of(h) * static_cast<unsigned int>(nc);
+  float best = -INFINITY;
+  int bc = 0, cnt = 0;
+  if (multi && !dedupe) {   // one candidate per (row, class) with conf > thr, general_yolo.py:191-193
+    for (int c = lane; c < nc; c += 32) {
+      const float raw = fe.cls_raw(b, h, c);
+      if (!fe.cls_may_pass(raw, obj)) continue;
+      const float conf = __fmul_rn(fe.cls(raw), obj);
+      if (conf > p.conf_thres && class_ok(p.class_mask, c)) { f(cand_key(conf, ord0 + c)); ++cnt; }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, sft);
+    return cnt;
+  }
+  // best class (first maximum); in dedupe mode only over the classes that are candidates themselves
+  for (int c = lane; c < nc; c += 32) {
+    const float raw = fe.cls_raw(b, h, c);
+    if (!fe.cls_may_pass(raw, obj)) continue;   // cannot exceed the threshold, so it cannot be a maximum that matters
+    const float conf = __fmul_rn(fe.cls(raw), obj);
+    if (multi && !(conf > p.conf_thres && class_ok(p.class_mask, c))) continue;
+    if (multi) ++cnt;
+    if (conf > best) { best = conf; bc = c; }
+  }
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, sft);
+    const int oc = __shfl_xor_sync(0xffffffffu, bc, sft);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, sft);
+    if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+  }
+  if (!multi) {             // best class only, general_yolo.py:195-196
+    const bool ok = best > p.conf_thres && class_ok(p.class_mask, bc);
+    if (lane == 0 && ok) f(cand_key(best, ord0 + bc));
+    return ok ? 1 : 0;
+  }
+  if (cnt >= 2) {
+    int ok = 0;
+    if (lane == 0) {
+      const float4 bx = fe.box(b, h);
+      const float w = __fsub_rn(bx.z, bx.x), hh = __fsub_rn(bx.w, bx.y);
+      ok = (w > 0.0f && hh > 0.0f && __fmul_rn(w, hh) < 1e37f) ? 1 : 0;
+    }
+    if (!__shfl_sync(0xffffffffu, ok, 0)) {   // degenerate box: every class stays a candidate
+      for (int c = lane; c < nc; c += 32) {
+        const float raw = fe.cls_raw(b, h, c);
+        if (!fe.cls_may_pass(raw, obj)) continue;
+        const float conf = __fmul_rn(fe.cls(raw), obj);
+        if (conf > p.conf_thres && class_ok(p.class_mask, c)) f(cand_key(conf, ord0 + c));
+      }
+      return cnt;
+    }
+  }
+  if (lane == 0 && cnt >= 1) f(cand_key(best, ord0 + bc));
+  return cnt;
+}
+
 struct NmsSmem {
   unsigned long long pass_row[kPassSmem];   // row handles of the objectness survivors
   float pass_obj[kPassSmem];
@@ -231,12 +303,12 @@ struct NmsSmem {
   unsigned long long diag[2][64];
   unsigned int hist[256];
   unsigned long long keep_bits, prefix;
-  int n_pass, n_emit, n_keep[2], k_rem;   // n_keep[ch & 1]: boxes kept before chunk ch (double-buffered: written during the previous chunk)
+  int n_pass, n_emit, n_real, n_keep[2], k_rem;   // n_keep[ch & 1]: boxes kept before chunk ch (double-buffered: written during the previous chunk)
 };
 
 template <class FE>
 __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, int B, YpNmsParams p, int cap, int cap_p2, NmsWs ws,
-                                                                 float* __restrict__ out_boxes, int* __restrict__ out_count) {
+                                                                 float* __restrict__ out_boxes, int* __restrict__ out_count, int prescanned) {
   extern __shared__ __align__(16) unsigned char nms_smem_raw[];
   NmsSmem& sm = *reinterpret_cast<NmsSmem*>(nms_smem_raw);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -244,66 +316,60 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
   const bool multi = p.multi_label && nc > 1;
   unsigned long long* g_pass_row = ws.pass_row + static_cast<int64_t>(b) * A;
   float* g_pass_obj = ws.pass_obj + static_cast<int64_t>(b) * A;
-  if (tid == 0) { sm.n_pass = 0; sm.n_emit = 0; sm.n_keep[0] = 0; sm.n_keep[1] = 0; }
+  if (tid == 0) { sm.n_pass = 0; sm.n_emit = 0; sm.n_real = 0; sm.n_keep[0] = 0; sm.n_keep[1] = 0; }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");   // the logits are the previous kernels' output
   __syncthreads();
+  bool dedupe = multi && p.agnostic && p.iou_thres < 1.0f;   // see warp_row_candidates
+
+  // Segments (Detect levels) whose candidates nms_prescan_kernel already listed while the rest of the network was still running:
+  // take the list if it is complete, else scan everything here.
+  int have = 0;
+  if (prescanned) {
+    const int pn = ws.pre_n[2 * b], pr = ws.pre_n[2 * b + 1];
+    if (pn <= kSmemCap && pr <= p.max_nms) {
+      have = prescanned;
+      for (int i = tid; i < pn; i += kNmsThreads) sm.key[i] = ws.pre_key[static_cast<int64_t>(b) * kSmemCap + i];
+      if (tid == 0) { sm.n_emit = pn; sm.n_real = pr; }
+    }
+    __syncthreads();
+    if (tid == 0) { ws.pre_n[2 * b] = 0; ws.pre_n[2 * b + 1] = 0; }   // ready for the next frame
+  }
 
   // ---- A: objectness scan (strict >, general_yolo.py:146); four independent loads in flight per thread
-  for (int l = 0; l < fe.segments(); ++l) {
-    const int rows = fe.seg_rows(l);
-    for (int i0 = tid; i0 < rows; i0 += 4 * kNmsThreads) {
-      float raw[4];
+  auto scan_objectness = [&](int skip_mask) {
+    for (int l = 0; l < fe.segments(); ++l) {
+      if ((skip_mask >> l) & 1) continue;
+      const int rows = fe.seg_rows(l);
+      for (int i0 = tid; i0 < rows; i0 += 4 * kNmsThreads) {
+        float raw[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const int i = i0 + u * kNmsThreads; raw[u] = i < rows ? fe_obj_raw_at(fe, b, l, i) : -INFINITY; }
+        for (int u = 0; u < 4; ++u) { const int i = i0 + u * kNmsThreads; raw[u] = i < rows ? fe_obj_raw_at(fe, b, l, i) : -INFINITY; }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (!fe.obj_may_pass(raw[u])) continue;
-        const float o = fe.obj(raw[u]);
-        if (o > p.conf_thres) {
-          const int slot = atomicAdd(&sm.n_pass, 1);
-          const unsigned long long h = fe.handle(l, i0 + u * kNmsThreads);
-          if (slot < kPassSmem) { sm.pass_row[slot] = h; sm.pass_obj[slot] = o; }
-          else { g_pass_row[slot] = h; g_pass_obj[slot] = o; }
+        for (int u = 0; u < 4; ++u) {
+          if (!fe.obj_may_pass(raw[u])) continue;
+          const float o = fe.obj(raw[u]);
+          if (o > p.conf_thres) {
+            const int slot = atomicAdd(&sm.n_pass, 1);
+            const unsigned long long h = fe.handle(l, i0 + u * kNmsThreads);
+            if (slot < kPassSmem) { sm.pass_row[slot] = h; sm.pass_obj[slot] = o; }
+            else { g_pass_row[slot] = h; g_pass_obj[slot] = o; }
+          }
         }
       }
     }
-  }
+  };
+  scan_objectness(have);
   __syncthreads();
-  const int n_pass = sm.n_pass;
+  int n_pass = sm.n_pass;
   auto pass_row = [&](int i) { return i < kPassSmem ? sm.pass_row[i] : g_pass_row[i]; };
   auto pass_obj = [&](int i) { return i < kPassSmem ? sm.pass_obj[i] : g_pass_obj[i]; };
 
-  // ---- B: candidates.  One warp per surviving row, lanes over the classes (coalesced logits); f(key) once per candidate.
+  // ---- B: candidates.  One warp per surviving row; f(key) once per candidate.
   auto for_each_candidate = [&](auto&& f) {
     for (int pi = warp; pi < n_pass; pi += kNmsThreads / 32) {
-      const unsigned long long h = pass_row(pi);
-      const float obj = pass_obj(pi);
-      const unsigned int ord0 = fe.row_of(h) * static_cast<unsigned int>(nc);
-      if (multi) {  // one candidate per (row, class) with conf > thr, general_yolo.py:191-193
-        for (int c = lane; c < nc; c += 32) {
-          const float raw = fe.cls_raw(b, h, c);
-          if (!fe.cls_may_pass(raw, obj)) continue;
-          const float conf = __fmul_rn(fe.cls(raw), obj);
-          if (conf > p.conf_thres && class_ok(p.class_mask, c)) f(cand_key(conf, ord0 + c));
-        }
-      } else {      // best class only (first maximum), general_yolo.py:195-196
-        float best = -INFINITY;
-        int bc = 0;
-        for (int c = lane; c < nc; c += 32) {
-          const float raw = fe.cls_raw(b, h, c);
-          if (!fe.cls_may_pass(raw, obj)) continue;   // cannot exceed the threshold, so it cannot be a maximum that matters
-          const float conf = __fmul_rn(fe.cls(raw), obj);
-          if (conf > best) { best = conf; bc = c; }
-        }
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) {
-          const float ob = __shfl_xor_sync(0xffffffffu, best, sft);
-          const int oc = __shfl_xor_sync(0xffffffffu, bc, sft);
-          if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
-        }
-        if (lane == 0 && best > p.conf_thres && class_ok(p.class_mask, bc)) f(cand_key(best, ord0 + bc));
-      }
+      const int cnt = warp_row_candidates(fe, b, pass_row(pi), pass_obj(pi), p, nc, multi, dedupe, lane, f);
+      if (lane == 0 && cnt) atomicAdd(&sm.n_real, cnt);
     }
   };
   unsigned long long* g_key = ws.key + static_cast<int64_t>(b) * cap_p2;
@@ -312,7 +378,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
     if (slot < kSmemCap) sm.key[slot] = k;
   });
   __syncthreads();
-  const int n_cand = sm.n_emit;
+  const int n_real = sm.n_real;                 // (row, class) pairs above the threshold = the reference's candidate count
+  int n_cand = sm.n_emit;                       // candidates that enter the sort (fewer than n_real with dedupe)
+  if (dedupe && n_real > p.max_nms) { dedupe = false; n_cand = n_real; }   // the top-max_nms cut is over ALL candidates
   int path = 0, n = n_cand;
   unsigned long long* key = sm.key;
   float4* box = sm.box;
@@ -320,6 +388,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
   if (n_cand > kSmemCap) {
     key = g_key; box = ws.box + static_cast<int64_t>(b) * cap; removed = ws.removed + static_cast<int64_t>(b) * (cap_p2 / 64);
     __syncthreads();
+    if (have) {                                 // the prescan list is being dropped: list the rows of its segments as well
+      scan_objectness(~have);
+      __syncthreads();
+      n_pass = sm.n_pass;
+    }
     if (tid == 0) sm.n_emit = 0;
     __syncthreads();
     if (n_cand <= cap) {
@@ -355,7 +428,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
       // the caller's buffer is smaller than max_nms and overflowed: report, the host grows `cap` (never silently truncated)
       if (tid == 0) {
         out_count[b] = -1 - n_cand;
-        ws.stats[b * 4] = n_pass; ws.stats[b * 4 + 1] = n_cand; ws.stats[b * 4 + 2] = 0; ws.stats[b * 4 + 3] = 3;
+        ws.stats[b * 4] = n_pass; ws.stats[b * 4 + 1] = n_real; ws.stats[b * 4 + 2] = 0; ws.stats[b * 4 + 3] = 3;
       }
       return;
     }
@@ -465,8 +538,43 @@ __global__ void __launch_bounds__(kNmsThreads, 1) box_nms_kernel(const FE fe, in
   }
   if (tid == 0) {
     out_count[b] = sm.n_keep[ch & 1];   // after a break or the last chunk, slot ch & 1 holds the total
-    ws.stats[b * 4] = n_pass; ws.stats[b * 4 + 1] = n_cand; ws.stats[b * 4 + 2] = n_sorted; ws.stats[b * 4 + 3] = path;
+    ws.stats[b * 4] = n_pass; ws.stats[b * 4 + 1] = n_real; ws.stats[b * 4 + 2] = n_sorted; ws.stats[b * 4 + 3] = path;
   }
+}
+
+// Candidates of one segment (Detect level), listed ahead of the NMS kernel: grid-wide, one thread per row for the objectness test,
+// then the warp evaluates the classes of its surviving rows one row at a time.  Levels 0 and 1 hold 95 % of the rows and are
+// complete long before the last Detect convolution, so this runs under the rest of the network and the NMS kernel on the
+// critical path starts from a finished list.  Emission order is irrelevant (the keys are sorted later); the counters are the only
+// shared state and the NMS kernel zeroes them again.
+template <class FE>
+__global__ void __launch_bounds__(256) nms_prescan_kernel(const FE fe, int seg, YpNmsParams p, NmsWs ws) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int nc = fe.no - 5;
+  const bool multi = p.multi_label && nc > 1;
+  const bool dedupe = multi && p.agnostic && p.iou_thres < 1.0f;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int rows = fe.seg_rows(seg);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float o = 0.0f;
+  bool pass = false;
+  if (i < rows) {
+    const float raw = fe_obj_raw_at(fe, b, seg, i);
+    if (fe.obj_may_pass(raw)) { o = fe.obj(raw); pass = o > p.conf_thres; }
+  }
+  unsigned m = __ballot_sync(0xffffffffu, pass);
+  int real = 0;
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int ri = __shfl_sync(0xffffffffu, i, src);
+    const float ro = __shfl_sync(0xffffffffu, o, src);
+    real += warp_row_candidates(fe, b, fe.handle(seg, ri), ro, p, nc, multi, dedupe, lane, [&](unsigned long long k) {
+      const int slot = atomicAdd(&ws.pre_n[2 * b], 1);
+      if (slot < kSmemCap) ws.pre_key[static_cast<int64_t>(b) * kSmemCap + slot] = k;
+    });
+  }
+  if (lane == 0 && real) atomicAdd(&ws.pre_n[2 * b + 1], real);
 }
 
 size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -483,11 +591,14 @@ size_t carve(NmsWs* ws, char* base, int B, long long A, int cap) {
   ws->key = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * cap_p2));
   ws->box = reinterpret_cast<float4*>(take(sizeof(float4) * B * cap));
   ws->removed = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * (cap_p2 / 64)));
+  ws->pre_n = reinterpret_cast<int*>(take(sizeof(int) * 2 * B));
+  ws->pre_key = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * B * kSmemCap));
   return off;
 }
 
 template <class FE>
-int launch_box_nms(const FE& fe, int B, const YpNmsParams& p, int cap, const NmsWs& ws, float* out_boxes, int32_t* out_count, cudaStream_t st) {
+int launch_box_nms(const FE& fe, int B, const YpNmsParams& p, int cap, const NmsWs& ws, float* out_boxes, int32_t* out_count, int prescanned,
+                   cudaStream_t st) {
   auto kern = box_nms_kernel<FE>;
   static thread_local bool raised = false;
   if (!raised) { YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(NmsSmem)))); raised = true; }
@@ -497,7 +608,7 @@ int launch_box_nms(const FE& fe, int B, const YpNmsParams& p, int cap, const Nms
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  YP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, fe, B, p, cap, pow2_at_least(cap), ws, out_boxes, out_count));
+  YP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, fe, B, p, cap, pow2_at_least(cap), ws, out_boxes, out_count, prescanned));
   return YP_OK;
 }
 
@@ -549,34 +660,61 @@ extern "C" int yp_box_nms(const float* pred, int32_t B, int64_t A, int32_t no, c
   YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "box_nms: workspace %zu < %zu bytes", workspace_bytes, need);
   yp::PredRows fe;
   fe.pred = pred; fe.A = A; fe.no = no; fe.thr = p->conf_thres;
-  return yp::launch_box_nms(fe, B, *p, cap, ws, out_boxes, out_count, static_cast<cudaStream_t>(stream));
+  return yp::launch_box_nms(fe, B, *p, cap, ws, out_boxes, out_count, 0, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int yp_detect_nms(const float* const* logits3, const int32_t* ny3, const int32_t* nx3, const int32_t* ldc3, const float* stride3,
-                             const float* anchors_px_host, int32_t B, int32_t na, int32_t no, const YpNmsParams* p, int32_t cap,
-                             float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
-  YP_REQUIRE(logits3 && ny3 && nx3 && ldc3 && stride3 && anchors_px_host && p && out_boxes && out_count && workspace, YP_ERR_ARG, "detect_nms: null pointer");
-  YP_REQUIRE(B > 0 && na == 3 && no >= 6, YP_ERR_SHAPE, "detect_nms: B=%d na=%d no=%d (na must be 3)", B, na, no);
-  int rc = nms_check_params("detect_nms", p, cap);
+static int det_levels(const char* who, const float* const* logits3, const int32_t* ny3, const int32_t* nx3, const int32_t* ldc3, const float* stride3,
+                      const float* anchors_px_host, int32_t B, int32_t na, int32_t no, const YpNmsParams* p, int32_t cap, yp::DetLevels* out) {
+  YP_REQUIRE(logits3 && ny3 && nx3 && ldc3 && stride3 && anchors_px_host && p, YP_ERR_ARG, "%s: null pointer", who);
+  YP_REQUIRE(B > 0 && na == 3 && no >= 6, YP_ERR_SHAPE, "%s: B=%d na=%d no=%d (na must be 3)", who, B, na, no);
+  int rc = nms_check_params(who, p, cap);
   if (rc != YP_OK) return rc;
-  yp::DetLevels lv;
+  yp::DetLevels& lv = *out;
   long long A = 0;
   for (int l = 0; l < 3; ++l) {
-    YP_REQUIRE(logits3[l] && na * no <= ldc3[l], YP_ERR_SHAPE, "detect_nms: level %d logits missing or ldc too small", l);
+    YP_REQUIRE(logits3[l] && na * no <= ldc3[l], YP_ERR_SHAPE, "%s: level %d logits missing or ldc too small", who, l);
+    YP_REQUIRE(ny3[l] > 0 && nx3[l] > 0 && ny3[l] < 16384 && nx3[l] < 16384, YP_ERR_SHAPE, "%s: level %d is %d x %d", who, l, ny3[l], nx3[l]);
     lv.logits[l] = logits3[l]; lv.ny[l] = ny3[l]; lv.nx[l] = nx3[l]; lv.ldc[l] = ldc3[l]; lv.stride[l] = stride3[l];
     for (int i = 0; i < 6; ++i) lv.anchor[l][i] = anchors_px_host[l * 6 + i];
     lv.row_off[l] = A;
     A += static_cast<long long>(na) * ny3[l] * nx3[l];
   }
   lv.na = na; lv.no = no; lv.A = A;
-  // sigmoid(v) > thr  =>  v > log(thr / (1 - thr)); the margin covers the rounding of expf / the division
   {
     const double t = static_cast<double>(p->conf_thres) * (1.0 - 1e-4) - 1e-30;   // a threshold strictly below the real one
     lv.logit_thr = t <= 0.0 ? -INFINITY : static_cast<float>(log(t / (1.0 - t)) - 1e-4);
   }
-  YP_REQUIRE(A * (no - 5) < (1ll << 31), YP_ERR_SHAPE, "detect_nms: A * nc = %lld exceeds 2^31", (long long)(A * (no - 5)));
+  YP_REQUIRE(A * (no - 5) < (1ll << 31), YP_ERR_SHAPE, "%s: A * nc = %lld exceeds 2^31", who, (long long)(A * (no - 5)));
+  return YP_OK;
+}
+
+extern "C" int yp_detect_prescan(const float* const* logits3, const int32_t* ny3, const int32_t* nx3, const int32_t* ldc3, const float* stride3,
+                                 const float* anchors_px_host, int32_t B, int32_t na, int32_t no, const YpNmsParams* p, int32_t cap,
+                                 int32_t level, void* workspace, size_t workspace_bytes, void* stream) {
+  yp::DetLevels lv;
+  int rc = det_levels("detect_prescan", logits3, ny3, nx3, ldc3, stride3, anchors_px_host, B, na, no, p, cap, &lv);
+  if (rc != YP_OK) return rc;
+  YP_REQUIRE(workspace && level >= 0 && level < 3, YP_ERR_ARG, "detect_prescan: level %d / workspace", level);
   yp::NmsWs ws;
-  const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, A, cap);
+  const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, lv.A, cap);
+  YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "detect_prescan: workspace %zu < %zu bytes", workspace_bytes, need);
+  const int rows = 3 * ny3[level] * nx3[level];
+  yp::nms_prescan_kernel<yp::DetLevels><<<dim3(yp::ceil_div(rows, 256), B), 256, 0, static_cast<cudaStream_t>(stream)>>>(lv, level, *p, ws);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+extern "C" int yp_detect_nms(const float* const* logits3, const int32_t* ny3, const int32_t* nx3, const int32_t* ldc3, const float* stride3,
+                             const float* anchors_px_host, int32_t B, int32_t na, int32_t no, const YpNmsParams* p, int32_t cap,
+                             float* out_boxes, int32_t* out_count, void* workspace, size_t workspace_bytes, int32_t prescanned_levels,
+                             void* stream) {
+  YP_REQUIRE(out_boxes && out_count && workspace, YP_ERR_ARG, "detect_nms: null pointer");
+  YP_REQUIRE(prescanned_levels >= 0 && prescanned_levels < 8, YP_ERR_ARG, "detect_nms: prescanned_levels=%d", prescanned_levels);
+  yp::DetLevels lv;
+  int rc = det_levels("detect_nms", logits3, ny3, nx3, ldc3, stride3, anchors_px_host, B, na, no, p, cap, &lv);
+  if (rc != YP_OK) return rc;
+  yp::NmsWs ws;
+  const size_t need = yp::carve(&ws, static_cast<char*>(workspace), B, lv.A, cap);
   YP_REQUIRE(workspace_bytes >= need, YP_ERR_CAPACITY, "detect_nms: workspace %zu < %zu bytes", workspace_bytes, need);
-  return yp::launch_box_nms(lv, B, *p, cap, ws, out_boxes, out_count, static_cast<cudaStream_t>(stream));
+  return yp::launch_box_nms(lv, B, *p, cap, ws, out_boxes, out_count, prescanned_levels, static_cast<cudaStream_t>(stream));
 }

@@ -160,42 +160,62 @@ __device__ unsigned int kp_process_tile(const float* __restrict__ heat, int B, i
     sm.sorted[rank] = sm.cand[i];
   }
   __syncthreads();
-  if (warp == 0) {
-    // Sequential resolve of the tile's undecided candidates in priority order by ONE warp (inside a tile this is the reference's
-    // scan).  The (2r+1)^2 window is walked in 32-cell steps whose cell offsets are computed once per kernel (the first version
-    // divided by the window width for every cell of every candidate: ~3000 cycles per candidate, 60 us per round); a candidate
-    // that an earlier kept one already marked suppressed costs one shared-memory read; a kept candidate marks its window, which
-    // is what nms_fast does (utils/utils.py:165-170).  Priority between two cells of one tile: confidence, then the smaller cell
-    // index (= the smaller raster index: both orders are row-major over the same rows and columns).
+  {
+    // Resolve the tile's undecided candidates: warp w walks candidates w, w + nwarps, ... of the priority-sorted list, so the whole
+    // CTA sweeps the list roughly in priority order; sweeps repeat until one of them decides nothing (tile-local fixed point; what
+    // is left depends on an undecided halo candidate of a neighbouring tile and waits for the next round).  Each decision is the
+    // sequential algorithm's decision whatever the interleaving: p is SUPPRESSED iff a kept candidate lies in its window, KEPT iff
+    // every higher-priority candidate in its window is decided and none is kept -- both are final, so a stale read of a
+    // neighbour's state can only postpone a decision to the next sweep.  A kept candidate marks the undecided cells of its window
+    // suppressed (nms_fast's own step, utils/utils.py:165-170; they all have lower priority, or p could not have been kept), so
+    // most candidates cost one shared-memory read.  The (2r+1)^2 window is walked in 32-cell steps through a table of cell
+    // offsets built once per kernel.  (The first version resolved with ONE warp and divided by the window width per cell: 60 us
+    // per round; ncu showed the other seven warps waiting at the barrier for 73 % of the kernel.)
+    // Priority between two cells of one tile: confidence, then the smaller cell index (= the smaller raster index).
     const int steps = (win * win + 31) / 32;
+    const int nwarps = blockDim.x >> 5;
     const short* off = sm.win_off + lane;      // off[32 t]: cell offset of window position lane + 32 t (0 = the candidate itself / padding)
-    for (int i = 0; i < n; ++i) {
-      const int p = sm.sorted[i];
-      if (sm.sstate[p] != 1) continue;          // suppressed by a candidate kept earlier in this round (uniform: same address)
-      const float hp = sm.sheat[p];
-      bool kept = false, pend = false;
-      for (int t = 0; t < steps; ++t) {
-        const int o = off[32 * t];
-        if (o != 0) {
-          const int q = p + o;
-          const unsigned char sq = sm.sstate[q];
-          if (sq == 2) kept = true;               // a kept candidate of a neighbouring tile (or of an earlier round)
-          else if (sq == 1) {
-            const float hq = sm.sheat[q];
-            if (hq > hp || (hq == hp && q < p)) pend = true;
-          }
-        }
-      }
-      kept = __any_sync(0xffffffffu, kept);
-      pend = __any_sync(0xffffffffu, pend);
-      if (!kept && !pend) {                      // keep p: everything still undecided in its window loses to it
+    volatile unsigned char* vstate = sm.sstate;
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) *sm.n_list = 0;    // reused as "this sweep decided something"
+      __syncthreads();
+      bool progress = false;
+      for (int i = warp; i < n; i += nwarps) {
+        const int p = sm.sorted[i];
+        if (vstate[p] != 1) continue;           // decided (uniform: same address)
+        const float hp = sm.sheat[p];
+        bool kept = false, pend = false;
         for (int t = 0; t < steps; ++t) {
           const int o = off[32 * t];
-          if (o != 0 && sm.sstate[p + o] == 1) sm.sstate[p + o] = 3;
+          if (o != 0) {
+            const int q = p + o;
+            const unsigned char sq = vstate[q];
+            if (sq == 2) kept = true;
+            else if (sq == 1) {
+              const float hq = sm.sheat[q];
+              if (hq > hp || (hq == hp && q < p)) pend = true;
+            }
+          }
         }
+        kept = __any_sync(0xffffffffu, kept);
+        pend = __any_sync(0xffffffffu, pend);
+        if (kept) {
+          if (lane == 0) vstate[p] = 3;
+          progress = true;
+        } else if (!pend) {                      // keep p: everything still undecided in its window loses to it
+          if (lane == 0) vstate[p] = 2;
+          for (int t = 0; t < steps; ++t) {
+            const int o = off[32 * t];
+            if (o != 0 && vstate[p + o] == 1) vstate[p + o] = 3;
+          }
+          progress = true;
+        }
+        __syncwarp();
       }
-      if (lane == 0) sm.sstate[p] = kept ? 3 : (pend ? 1 : 2);
-      __syncwarp();
+      if (progress && lane == 0) *sm.n_list = 1;
+      __syncthreads();
+      if (*sm.n_list == 0) break;
     }
   }
   __syncthreads();

@@ -491,7 +491,7 @@ class ShapePlan:
         self.raw = [torch.empty((B, 3, Hc >> i, Wc >> i, net.no), dtype=torch.float32, device=dev) for i in range(3)]
         self._side = None
         self._keep = []      # ctypes objects referenced by the launch closures
-        self.launches = []   # callables (stream_ptr) -> None
+        self.launches = []   # (lane, callable(stream_ptr) -> None, layer name)
         self._compile()
         self.graphs = {}
 
@@ -508,12 +508,12 @@ class ShapePlan:
             if isinstance(op, PoolOp):
                 v = self.view(SliceRef(op.buf, 0, self.bufs[op.buf].shape[-1]))
                 self._keep.append(v)
-                self.launches.append((0, lambda st, v=v: _lib.check(L.yp_sppf_pool(C.byref(v), st))))
+                self.launches.append((0, lambda st, v=v: _lib.check(L.yp_sppf_pool(C.byref(v), st)), "sppf_pool"))
                 continue
             if isinstance(op, Pool2Op):
                 vi, vo = self.view(op.src), self.view(op.dst)
                 self._keep += [vi, vo]
-                self.launches.append((op.lane, lambda st, vi=vi, vo=vo: _lib.check(L.yp_maxpool2x2(C.byref(vi), C.byref(vo), st))))
+                self.launches.append((op.lane, lambda st, vi=vi, vo=vo: _lib.check(L.yp_maxpool2x2(C.byref(vi), C.byref(vo), st)), "maxpool2x2"))
                 continue
             w, b = eng.weights[op.names]
             d = YpConvDesc()
@@ -536,7 +536,7 @@ class ShapePlan:
             need[op.lane] = max(need.get(op.lane, 0), int(L.yp_conv2d_workspace_bytes(C.byref(d)))) if eng.split_k else 0
             descs.append((op.lane, d))
             self._keep.append(d)
-            self.launches.append((op.lane, lambda st, d=d: _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), st))))
+            self.launches.append((op.lane, lambda st, d=d: _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), st)), "+".join(op.names)))
         # split-K scratch: one zero-initialised buffer per lane (lanes may run concurrently; launches of one lane are
         # stream-ordered and the arrival counters reset themselves)
         self.workspaces = {lane: torch.zeros(max(n, 16), dtype=torch.uint8, device=eng.device) for lane, n in need.items() if n > 0}
@@ -563,36 +563,59 @@ class ShapePlan:
             self._side = {ln: torch.cuda.Stream(self.eng.device) for ln in (1, 2, 3, 4)}
         return self._side[lane]
 
-    def run_net(self, tails=None):
+    def run_net(self, tails=None, after=None):
         """Launch list; the keypoint and descriptor heads run on side streams that fork from / join the current stream
         (also under graph capture), so their small grids overlap the detection branch.  ``tails`` maps a lane to a
-        callable(stream_ptr) enqueued on that lane's stream after its last layer (e.g. heatmap + keypoint NMS)."""
+        callable(stream_ptr) enqueued on that lane's stream after its last layer (e.g. heatmap + keypoint NMS).  ``after`` maps a
+        layer name to a callable(stream_ptr) that only needs that layer's output: it is enqueued on its own side stream right
+        behind the layer and joined at the end (e.g. the box-NMS candidate scan of a Detect level)."""
         tails = tails or {}
+        after = after or {}
         dev = self.eng.device
         main = torch.cuda.current_stream(dev)
         if not self.eng.multi_stream:
             st = C.c_void_p(main.cuda_stream)
-            for _, f in self.launches:
+            for _, f, name in self.launches:
                 f(st)
+                if name in after:
+                    after[name](st)
             for lane in sorted(tails):
                 tails[lane](st)
             return
         self.side_stream(1)
         started = {}
+        hooks = []
+        streams = {0: main}
         ptr = {0: C.c_void_p(main.cuda_stream)}
-        for lane, f in self.launches:
+        free_hook_lanes = [ln for ln in (3, 4) if not any(l == ln for l, _, _ in self.launches)]
+        for lane, f, name in self.launches:
             if lane and lane not in started:
                 ev = torch.cuda.Event()
                 ev.record(main)
                 self._side[lane].wait_event(ev)
                 started[lane] = True
+                streams[lane] = self._side[lane]
                 ptr[lane] = C.c_void_p(self._side[lane].cuda_stream)
             f(ptr[lane])
+            if name in after:
+                if free_hook_lanes:
+                    hs = self._side[free_hook_lanes.pop(0)]
+                    ev = torch.cuda.Event()
+                    ev.record(streams[lane])
+                    hs.wait_event(ev)
+                    after[name](C.c_void_p(hs.cuda_stream))
+                    hooks.append(hs)
+                else:
+                    after[name](ptr[lane])
         for lane in started:   # in the order the lanes started (a later lane's tail may wait for an earlier lane's event)
             if lane in tails:
                 tails[lane](ptr[lane])
             ev = torch.cuda.Event()
             ev.record(self._side[lane])
+            main.wait_event(ev)
+        for hs in hooks:
+            ev = torch.cuda.Event()
+            ev.record(hs)
             main.wait_event(ev)
 
     def run_decode(self, want_raw: bool = True):

@@ -75,7 +75,7 @@ class FramePipeline:
         self.row_key, self.col_key = z(B, max_pts, dt=torch.int64), z(B, max_pts, dt=torch.int64)
         self.matches, self.mcount = two(lambda: z(B, max_pts, 3)), two(lambda: z(B, dt=torch.int32))
         self.d_counts = two(lambda: z(4, B, dt=torch.int32))            # keypoints, boxes, matches, pixels >= detection threshold
-        self.ws_nms = torch.empty(L.yp_box_nms_workspace_bytes(B, self.plan.A, self.eng.net.no, self.nms_cap), dtype=torch.uint8, device=dev)
+        self.ws_nms = torch.zeros(L.yp_box_nms_workspace_bytes(B, self.plan.A, self.eng.net.no, self.nms_cap), dtype=torch.uint8, device=dev)
         self.ws_kp = torch.empty(L.yp_keypoints_workspace_bytes(B, H, W, max_pts), dtype=torch.uint8, device=dev)
         self.nms_params = YpNmsParams(float(self.cfg["conf_thres_box"]), float(self.cfg["iou_thres_box"]), 1, 1, int(md), 30000, 7680.0, None)
         # host boundary: frames go up on a copy stream into a device staging buffer, results come back on another copy stream
@@ -135,17 +135,25 @@ class FramePipeline:
             _lib.check(L.yp_sample_desc(desc.data_ptr(), B, self.D, H // 8, W // 8, dB, dD, dH, dW, H, W, self.pts_all.data_ptr(),
                                         self.n_all.data_ptr(), self.max_pts, self.descs_all[k].data_ptr(), stp))
 
-        p.run_net(tails={1: kp_tail, 2: desc_tail})
-        # Detect decode fused into the box NMS kernel: pred [B,A,85] is never materialised here
+        # Detect decode fused into the box NMS: pred [B,A,85] is never materialised here.  The candidates of levels 0 / 1 (95 % of
+        # the rows) are listed on side streams as soon as their Detect convolution is done; the NMS kernel after the last layer
+        # scans level 2 only and starts from that list.
         dets = [p.bufs[f"det{i}"] for i in range(3)]
         lg = (C.c_void_p * 3)(*[d.data_ptr() for d in dets])
         ny = (C.c_int32 * 3)(*[d.shape[2] for d in dets]); nx = (C.c_int32 * 3)(*[d.shape[3] for d in dets])
         ldc = (C.c_int32 * 3)(*[d.shape[4] for d in dets])
         strd = (C.c_float * 3)(*[float(v) for v in self.eng.stride])
         anc = (C.c_float * 18)(*[float(v) for row in self.eng.anchors_px for v in row])
+        self._keep_alive = (lg, ny, nx, ldc, strd, anc)
+
+        def prescan(level):
+            return lambda stp: _lib.check(L.yp_detect_prescan(lg, ny, nx, ldc, strd, anc, B, 3, self.eng.net.no, C.byref(self.nms_params),
+                                                              self.nms_cap, level, self.ws_nms.data_ptr(), self.ws_nms.numel(), stp))
+
+        p.run_net(tails={1: kp_tail, 2: desc_tail}, after={"Detect.m.0": prescan(0), "Detect.m.1": prescan(1)})
         boxes, bcount = self.boxes[k], self.bcount[k]
         _lib.check(L.yp_detect_nms(lg, ny, nx, ldc, strd, anc, B, 3, self.eng.net.no, C.byref(self.nms_params), self.nms_cap,
-                                   boxes.data_ptr(), bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), st))
+                                   boxes.data_ptr(), bcount.data_ptr(), self.ws_nms.data_ptr(), self.ws_nms.numel(), 3, st))
         # critical path after the box NMS: in-box filter (order-preserving compaction) -> match with the previous frame
         fp = self.filter_pts
         _lib.check(L.yp_keypoints_filter(self.pts_all.data_ptr(), self.n_all.data_ptr(), B, self.max_pts, H, W, boxes.data_ptr() if fp else None,
@@ -173,9 +181,9 @@ class FramePipeline:
     def n_launches(self) -> int:
         """Kernels of this library launched per frame batch (for bench.py's gpu_launches)."""
         net_launches = len(self.plan.launches)
-        # input + net + fused decode / box NMS (1) + heatmap + keypoints (8 NMS rounds + sweep + collect + emit) + sample + in-box filter +
+        # input + net + box-NMS candidate prescan of Detect levels 0 / 1 (2) + fused decode / box NMS (1) + heatmap + keypoints (8 NMS rounds + sweep + collect + emit) + sample + in-box filter +
         # descriptor gather + match (tiles + finalize, all images)
-        return 1 + net_launches + 1 + 1 + 11 + 1 + 1 + 1 + (2 if self.do_match else 0)
+        return 1 + net_launches + 2 + 1 + 1 + 11 + 1 + 1 + 1 + (2 if self.do_match else 0)
 
     def step_device(self, from_frame: bool = True, frame_src: Optional[torch.Tensor] = None):
         """Process the frame already resident in plan.frame_in / plan.x_in (or in ``frame_src``, a uint8 [B,H,W,3] device buffer
