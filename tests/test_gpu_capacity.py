@@ -81,14 +81,14 @@ def test_box_nms_ties_keep_candidate_order_beyond_max_nms():
 
 def test_box_nms_small_cap_reports_and_api_grows():
     pred = torch.from_numpy(crowded_pred(6000, seed=1)).cuda()
-    _, count = ops.box_nms(pred, 0.4, 0.45, True, True, 1000, cap=1024)
+    _, count = ops.box_nms(pred, 0.4, 0.45, True, False, 1000, cap=1024)   # class-aware: every (row, class) pair is a candidate
     # explicit cap < max_nms and more candidates than cap AND than the kernel's shared-memory list (4096): overflow is reported,
     # never truncated; the reference-named API grows the buffer and redoes the call
     assert int(count[0]) == -1 - 6000
     _, count = ops.box_nms(torch.from_numpy(crowded_pred(3000, seed=1)).cuda(), 0.4, 0.45, True, True, 1000, cap=1024)
     assert int(count[0]) >= 0                             # fits the shared-memory list: cap is irrelevant
-    ref = O.non_max_suppression(pred.cpu().numpy(), 0.4, 0.45, multi_label=True, agnostic=True, max_det=1000)[0]
-    got = yp.non_max_suppression(pred, 0.4, 0.45, multi_label=True, agnostic=True, max_det=1000, cap=1024)[0].cpu().numpy()
+    ref = O.non_max_suppression(pred.cpu().numpy(), 0.4, 0.45, multi_label=True, agnostic=False, max_det=1000)[0]
+    got = yp.non_max_suppression(pred, 0.4, 0.45, multi_label=True, agnostic=False, max_det=1000, cap=1024)[0].cpu().numpy()
     np.testing.assert_array_equal(got, ref)
 
 

@@ -115,16 +115,18 @@ __device__ __forceinline__ void match_tile(const float* __restrict__ d1, const i
   const bool va_ok = i0 + r < n1, vb_ok = j0 + r < n2;
   const float* pa = d1 + static_cast<int64_t>(va_ok ? (sel1 ? sel1[i0 + r] : i0 + r) : 0) * D + kq;
   const float* pb = d2 + static_cast<int64_t>(vb_ok ? (sel2 ? sel2[j0 + r] : j0 + r) : 0) * D + kq;
+  // 64 rows x 16 k per step: each thread loads one float4 of A and one of B (rows are D-contiguous).  The loads of step k+1 are
+  // issued before the FMAs of step k (the first version waited for an L2 round trip in front of every step).
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 va = (va_ok && kq < D) ? *reinterpret_cast<const float4*>(pa) : zero4;
+  float4 vb = (vb_ok && kq < D) ? *reinterpret_cast<const float4*>(pb) : zero4;
   for (int k0 = 0; k0 < D; k0 += TK) {
-    // 64 rows x 16 k: each thread loads one float4 of A and one of B (rows are D-contiguous)
-    {
-      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-      if (va_ok && k0 + kq < D) va = *reinterpret_cast<const float4*>(pa + k0);
-      if (vb_ok && k0 + kq < D) vb = *reinterpret_cast<const float4*>(pb + k0);
-      As[kq][r] = va.x; As[kq + 1][r] = va.y; As[kq + 2][r] = va.z; As[kq + 3][r] = va.w;
-      Bs[kq][r] = vb.x; Bs[kq + 1][r] = vb.y; Bs[kq + 2][r] = vb.z; Bs[kq + 3][r] = vb.w;
-    }
+    As[kq][r] = va.x; As[kq + 1][r] = va.y; As[kq + 2][r] = va.z; As[kq + 3][r] = va.w;
+    Bs[kq][r] = vb.x; Bs[kq + 1][r] = vb.y; Bs[kq + 2][r] = vb.z; Bs[kq + 3][r] = vb.w;
     __syncthreads();
+    const int kn = k0 + TK + kq;
+    va = (va_ok && kn < D) ? *reinterpret_cast<const float4*>(pa + k0 + TK) : zero4;
+    vb = (vb_ok && kn < D) ? *reinterpret_cast<const float4*>(pb + k0 + TK) : zero4;
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
