@@ -72,7 +72,7 @@ struct ConvArgs {
   long long* dbg;  // optional timeline buffer (yp_debug_conv_timeline); CTA (0,0) records clock64 stamps
 };
 
-constexpr int kThreads = 256;   // 8 warps: warp 0 TMA producer, warps 1-2 MMA issuers, then all 8 run the epilogue
+// CTA size: 256 threads (8 warps: warp 0 TMA producer, warps 1-2 MMA issuers, then all run the epilogue; two CTAs per SM) or 512 (one CTA per SM)
 constexpr size_t kWsCounterBytes = 64 * 1024;   // split-K arrival counters: one int per output tile, <= 16384 tiles
 constexpr int kMaxStages = 8;
 constexpr int kPersistThreads = 384;   // persistent variant: warp 0 producer, warps 1-2 issuers, warps 4-11 epilogue
@@ -103,8 +103,8 @@ __device__ __forceinline__ float silu_fast(float v) {
 // `n_small` (<= 2) more take the two cross terms (A_lo*W_hi, A_hi*W_lo), whose partial sums are ~2^-11 of the
 // result so that their truncation error is negligible.
 // ---------------------------------------------------------------------------------------------
-template <int OUT_FMT, int UNITS, bool kTf32>
-__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+template <int OUT_FMT, int UNITS, bool kTf32, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
-  for (int i = threadIdx.x; i < a.Nt; i += kThreads) bias_s[i] = a.bias ? a.bias[n0 + i] : 0.0f;
+  for (int i = threadIdx.x; i < a.Nt; i += NT) bias_s[i] = a.bias ? a.bias[n0 + i] : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -324,14 +324,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   __syncwarp();
   {
     // ===================== epilogue =====================
-    // All eight warps take part (the producer and issuer warps join when their loops are done): two warps per TMEM lane
-    // quarter, which split the 16-column units of the tile between them (hf = 0 / 1 takes the even / odd units).  With one
-    // warp per scheduler the epilogue was bound by single-warp instruction latency (~4 cycles per instruction).
+    // All warps take part (the producer and issuer warps join when their loops are done): NG = NT / 128 warps per TMEM lane
+    // quarter, which split the 16-column units of the tile between them (warp group hf takes the units u with u % NG == hf).
+    // With one warp per scheduler the epilogue was bound by single-warp instruction latency (~4 cycles per instruction);
+    // layers that cannot fill the GPU anyway (one CTA per SM) run 16 warps = four per quarter, which halves it again.
     using TO = typename OutT<OUT_FMT>::type;
     constexpr int CH = 16 * UNITS;                 // elements per staging row
     constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
+    constexpr int NG = NT / 128;                   // warp groups (2 or 4)
+    constexpr int G = NG > UNITS ? NG / UNITS : 1; // staging chunks worked on at the same time (every warp group has a unit)
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int hf = warp >> 2;                      // which half of the column units this warp handles
+    const int hf = warp >> 2;                      // warp group
     const int row = q * 32 + lane;               // accumulator row (TMEM lane) of this thread
     const int rdiv = a.patch ? a.Wp : a.Wt;      // patch mode: rows index the padded patch, halo columns are dropped
     const int rh = row / rdiv, rw = row - rh * rdiv;
@@ -434,6 +437,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
 
     float res[PE];
     asm volatile("griddepcontrol.wait;" ::: "memory");     // the residual may be the previous kernel's output
+    // The residual of this thread's first unit is fetched while the main loop is still running (it cost 0.4 us of exposed
+    // latency in front of every pass).  Unit u (16 columns) of the tile = columns [16 u, 16 u + 16); this thread's first is u = hf.
+    const bool res_pre = hf * 16 < a.Nt && a.split_k == 1 && !a.rowmin && !a.l2norm;
+    if (res_pre) load_res(hf * 16, res);
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (et0) stamp(2);
@@ -442,21 +449,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
     if (S > 1 && a.ablate != 7) {
       // publish this CTA's partial tile, then the last CTA to arrive (per tile) reduces all of them and finishes
       float* mine = a.ws_partial + ((blockIdx.z * n_tiles_all + tile_id) * 128 + row) * a.Nt;
-      for (int u = hf; u < a.Nt / 16; u += 2) {
+      for (int u = hf; u < a.Nt / 16; u += NG) {
         float v[16];
         tmem_acc16(u * 16, v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) __stcg(reinterpret_cast<float4*>(mine + u * 16) + j, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
       }
       __threadfence();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
       if (et0) {
         const int old = atomicAdd(a.ws_counter + tile_id, 1);
         const int last = old == S - 1;
         if (last) a.ws_counter[tile_id] = 0;   // ready for the next launch that uses this workspace
         *split_flag = last;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
       run_epilogue = *split_flag != 0;
       __threadfence();
     }
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       const int n_rows = a.n_rows ? min(*a.n_rows, a.Wo) : a.Wo;
       const int n_cols = a.n_cols ? *a.n_cols : (int)(gridDim.y * a.Nt);
       unsigned long long best = ~0ull;
-      for (int u = hf; u < a.Nt / 16; u += 2) {
+      for (int u = hf; u < a.Nt / 16; u += NG) {
         float v[16];
         load_acc16(u * 16, v);
 #pragma unroll
@@ -493,17 +500,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       inv_norm = 1.0f / sqrtf(ss);
     }
 
-    for (int c = 0; c < n_chunks; ++c) {
-      const uint32_t stg = smem_base + (c & 1) * a.staging_set_bytes;
-      // staging set (c & 1) must have been drained by the TMA store of chunk c-2 (thread et0 waited)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et0 && c == 0) stamp(320);
+    // Chunks (one staging row = CH columns each) are processed G at a time so that every warp group has a 16-column unit; the
+    // 2 G staging sets alternate between consecutive groups of chunks (the TMA stores of one group drain under the next).
+    for (int cg = 0; cg < n_chunks; cg += G) {
+      const int set0 = ((cg / G) & 1) * G;
+      // the staging sets of this group were drained by the TMA stores committed two groups ago (thread et0 waited)
+      asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+      if (et0 && cg == 0) stamp(320);
 #pragma unroll 1
-      for (int ps = 0; ps < NP; ++ps) {
-      if (((c * NP + ps) & 1) != hf) continue;       // the other warp of this lane quarter takes this unit
+      for (int it = hf; it < G * NP; it += NG) {     // this warp group's units of the G chunks
+      const int gi = it / NP, ps = it - gi * NP;
+      const int c = cg + gi;
+      if (c >= n_chunks) break;
+      const uint32_t stg = smem_base + (set0 + gi) * a.staging_set_bytes;
       float v[PE];
       const int col0 = c * CH + ps * PE;
-      load_res(col0, res);
+      if (!(res_pre && col0 == hf * 16)) load_res(col0, res);
       if (et0 && c == 0 && ps == 0) stamp(321);
       if (a.ablate != 3) load_acc16(col0, v);
       if (et0 && c == 0 && ps == 0) stamp(322);
@@ -544,17 +556,18 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j0 + j, ROWB)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
       }
-      }  // passes
+      }  // units
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et0 && c < 8) stamp(301 + 4 * c);
+      asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+      if (et0 && cg < 8) stamp(301 + 4 * cg);
       if (et0 && a.ablate != 5) {
-        for (int m = 0; m < a.n_out_maps; ++m)
-          for (int pl = 0; pl < a.out_planes; ++pl)
-            tma_store_5d(&maps.out[m], stg + pl * 128 * ROWB, n0 + c * CH, w0, h0, b, pl);
+        for (int gi = 0; gi < G && cg + gi < n_chunks; ++gi)
+          for (int m = 0; m < a.n_out_maps; ++m)
+            for (int pl = 0; pl < a.out_planes; ++pl)
+              tma_store_5d(&maps.out[m], smem_base + (set0 + gi) * a.staging_set_bytes + pl * 128 * ROWB, n0 + (cg + gi) * CH, w0, h0, b, pl);
         tma_store_commit();
         tma_store_wait_read<1>();  // everything but the group just committed has finished reading smem
-        if (c < 8) stamp(302 + 4 * c);
+        if (cg < 8) stamp(302 + 4 * cg);
       }
     }
     if (et0) { tma_store_wait_read<0>(); stamp(3); }
@@ -922,9 +935,9 @@ int encode_weight(CUtensorMap* tm, const void* w, int fmt, int Ktot, int cout, i
   return YP_OK;
 }
 
-template <int OUT_FMT, int UNITS, bool kTf32>
+template <int OUT_FMT, int UNITS, bool kTf32, int NT>
 int launch(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = conv_tc_kernel<OUT_FMT, UNITS, kTf32>;
+  auto kern = conv_tc_kernel<OUT_FMT, UNITS, kTf32, NT>;
   static thread_local size_t configured = 0;  // per (instantiation, thread): raise the dynamic smem limit once per size
   if (smem > configured) {
     YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -932,7 +945,7 @@ int launch(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t smem, cuda
   }
   static const bool use_pdl = getenv("YP_NO_PDL") == nullptr;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -999,6 +1012,7 @@ struct ConvPlan {
   size_t smem, ws_bytes, ws_counter_bytes;
   int out_fmt, units, chunk_elems;
   bool tf32;
+  int nt;   // threads per CTA: 256 (two CTAs per SM) or 512 (one CTA per SM, four epilogue warps per TMEM lane quarter)
 };
 
 // Everything that does not need device pointers: tile shapes, accumulator plan, split-K factor, workspace need.
@@ -1218,12 +1232,17 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     a.stages = stages;
     region = stages * a.stage_bytes;
   }
+  // Layers that cannot fill the GPU (at most one CTA per SM) run 512-thread CTAs: 16 epilogue warps instead of 8.
+  static const bool allow_wide = getenv("YP_CONV_WIDE") == nullptr || atoi(getenv("YP_CONV_WIDE")) != 0;
+  P->nt = (allow_wide && !dense && !persist) ? 512 : 256;
+  const int n_groups = P->nt / 128;
+  const int staging_sets = 2 * (n_groups > P->units ? n_groups / P->units : 1);
   if (persist) {
     // the staging sets may not alias the pipeline stages: the next tile's K loop runs under this tile's epilogue
     region = (region + 1023) & ~1023;
     a.stg_off = region;
     region += 2 * a.staging_set_bytes;
-  } else if (region < 2 * a.staging_set_bytes) region = 2 * a.staging_set_bytes;
+  } else if (region < staging_sets * a.staging_set_bytes) region = staging_sets * a.staging_set_bytes;
   region = (region + 1023) & ~1023;
   a.bar_off = region;
   P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 10) + Nt * sizeof(float) + 16;
@@ -1339,7 +1358,7 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
     else { if (units == 2) YP_DISPATCH_P(YP_FMT_F32, 2); if (units == 1) YP_DISPATCH_P(YP_FMT_F32, 1); }
   }
 #undef YP_DISPATCH_P
-#define YP_DISPATCH(FMT, U, TF) return launch<FMT, U, TF>(maps, a, grid, smem, st)
+#define YP_DISPATCH(FMT, U, TF) return P.nt == 512 ? launch<FMT, U, TF, 512>(maps, a, grid, smem, st) : launch<FMT, U, TF, 256>(maps, a, grid, smem, st)
   if (tf32) {
     if (out_fmt == YP_FMT_F32X2) { if (units == 2) YP_DISPATCH(YP_FMT_F32X2, 2, true); if (units == 1) YP_DISPATCH(YP_FMT_F32X2, 1, true); }
     else { if (units == 2) YP_DISPATCH(YP_FMT_F32, 2, true); if (units == 1) YP_DISPATCH(YP_FMT_F32, 1, true); }
