@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   if (threadIdx.x == 0) stamp(1);
   if (a.ablate != 6) {   // 6 = launch + prologue only (timing experiment)
 
-  if (warp == 0) {
-    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+  if (warp == 0 && elect_one()) {
+    // ===================== TMA producer (one elected lane runs the whole loop) =====================
     asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
     const bool load = a.ablate != 2;
     if (a.patch) {
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
         const int cb = kb0 + cbi;
         mbar_wait(aempty_bar(sa), pha ^ 1);
         const uint32_t sta = smem_base + sa * a.a_stage_bytes;
-        if (elect_one()) {
+        {
           mbar_expect_tx(afull_bar(sa), load ? a.a_tx : 0);
           if (load) {
             tma_load_5d(sta, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 0);
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
         }
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(empty_bar(sb), phb ^ 1);
-          if (elect_one()) {
+          {
             mbar_expect_tx(full_bar(sb), load ? a.b_tx : 0);
             if (load) tma_load_3d(smem_base + a.b_ring_off + sb * a.b_stage_bytes, &maps.w, full_bar(sb), (tap * a.kb_per_tap + cb) * a.ck_elems, n0, 0);
           }
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
           dw = static_cast<int>((a.tap_dw >> (4 * tap)) & 15ull) - 8;
         }
         const uint32_t st = smem_base + s * a.stage_bytes;
-        if (elect_one()) {
+        {
           mbar_expect_tx(full_bar(s), load ? a.tx_bytes : 0);
           if (load) {
             tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   // instruction) with 32-bit descriptor arithmetic: tcgen05.mma / tcgen05.commit take uniform-register operands, and code
   // under a `lane == 0` branch makes the compiler move every operand through an elect / R2UR loop and 64-bit adds -- measured
   // ~450 cycles of issue overhead per MMA, several times the 64-128 cycles the MMA occupies the tensor pipe.
-  if (warp >= 1 && warp - 1 < a.n_iss) {
+  if (warp >= 1 && warp - 1 < a.n_iss && elect_one()) {   // ONE lane runs the whole issue loop (see umma32_one)
     const int q = warp - 1;
     const int ksteps = a.ck_bytes / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
     const uint32_t b_plane = a.Nt * a.ck_bytes;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
       for (int cbi = 0; cbi < num_kb; ++cbi) {
         mbar_wait(afull_bar(sa), pha);
         tc_fence_after();
-        if (q == 0 && cbi < 96 && lane == 0) stamp(104 + cbi);
+        if (q == 0 && cbi < 96) stamp(104 + cbi);
         const uint32_t pa = smem_base + sa * a.a_stage_bytes;
         uint32_t shift = 0;               // byte offset of the tap's window inside the patch: (kh * Wp + kw) rows
         for (int tap = 0; tap < 9; ++tap) {
@@ -270,31 +270,31 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
             // operand set-up of MMA k+1 overlaps the issue of MMA k
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma32<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
+              umma32_one<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
               used |= 1u << nxt;
               nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
             }
           } else
           for (int k = kstart; k < ksteps && live; k += kinc) {
-            umma32<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
-            if (two) umma32<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
+            umma32_one<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
+            if (two) umma32_one<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
             used |= 1u << nxt;
             nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
             al0 += 2 * kinc; bl0 += 2 * kinc; al1 += 2 * kinc; bl1 += 2 * kinc;
           }
-          umma_commit_elect(empty_bar(s));
+          umma_commit(empty_bar(s));
           if (++s == a.b_stages) { s = 0; ph ^= 1; }
           shift += (tap % 3 == 2) ? (a.Wp - 2) * a.ck_bytes : a.ck_bytes;
         }
-        umma_commit_elect(aempty_bar(sa));
-        if (q == 0 && cbi < 96 && lane == 0) stamp(200 + cbi);
+        umma_commit(aempty_bar(sa));
+        if (q == 0 && cbi < 96) stamp(200 + cbi);
         if (++sa == 2) { sa = 0; pha ^= 1; }
       }
     } else {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        if (q == 0 && kb < 96 && lane == 0) stamp(104 + kb);
+        if (q == 0 && kb < 96) stamp(104 + kb);
         const uint32_t sa = smem_base + s * a.stage_bytes;
         const uint32_t sb = sa + a.a_region_bytes;
         uint32_t al0 = smem_desc_lo(sa + a_off0) + 2 * kstart, bl0 = smem_desc_lo(sb + b_off0) + 2 * kstart;
@@ -302,24 +302,24 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
         if (fast4) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma32<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
+            umma32_one<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
             used |= 1u << nxt;
             nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
           }
         } else
         for (int k = kstart; k < ksteps && live; k += kinc) {
-          umma32<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
-          if (two) umma32<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
+          umma32_one<kTf32>(col0 + nxt * cstride, al0, bl0, dhi, idesc, (used >> nxt) & 1u);
+          if (two) umma32_one<kTf32>(col0 + nxt * cstride, al1, bl1, dhi, idesc, 1u);
           used |= 1u << nxt;
           nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
           al0 += 2 * kinc; bl0 += 2 * kinc; al1 += 2 * kinc; bl1 += 2 * kinc;
         }
-        umma_commit_elect(empty_bar(s));  // one arrival per issuer: the stage is free when all their MMAs have retired
-        if (q == 0 && kb < 96 && lane == 0) stamp(200 + kb);
+        umma_commit(empty_bar(s));  // one arrival per issuer: the stage is free when all their MMAs have retired
+        if (q == 0 && kb < 96) stamp(200 + kb);
         if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
-    umma_commit_elect(accum_bar);
+    umma_commit(accum_bar);
   }
   __syncwarp();
   {
@@ -1233,7 +1233,10 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     region = stages * a.stage_bytes;
   }
   // Layers that cannot fill the GPU (at most one CTA per SM) run 512-thread CTAs: 16 epilogue warps instead of 8.
-  static const bool allow_wide = getenv("YP_CONV_WIDE") == nullptr || atoi(getenv("YP_CONV_WIDE")) != 0;
+  // Measured on B200 (YOLOPoint-S 640x640 batch 1, fp32): 0.786 ms per network pass with it, 0.777 ms without -- a 512-thread CTA owns the
+  // whole register file of its SM, so the next layer's CTAs can no longer start under this layer's tail (programmatic dependent launch).
+  // Off unless YP_CONV_WIDE=1.
+  static const bool allow_wide = getenv("YP_CONV_WIDE") != nullptr && atoi(getenv("YP_CONV_WIDE")) != 0;
   P->nt = (allow_wide && !dense && !persist) ? 512 : 256;
   const int n_groups = P->nt / 128;
   const int staging_sets = 2 * (n_groups > P->units ? n_groups / P->units : 1);

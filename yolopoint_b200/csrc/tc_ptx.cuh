@@ -167,6 +167,25 @@ __device__ __forceinline__ void umma32(uint32_t tmem_d, uint32_t a_lo, uint32_t 
     }
   }
 }
+// Same without the election, for code that already runs on one elected lane (a whole issue loop inside `if (elect_one())`: the
+// loop-carried descriptor halves, accumulator addresses and predicates then stay in uniform registers across iterations instead of
+// being moved there by eight R2UR per MMA -- SASS of the per-MMA election: ELECT, BSSY, 8 x R2UR, 6 uniform ops, UTCHMMA, BSYNC).
+template <bool kTf32>
+__device__ __forceinline__ void umma32_one(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accum) {
+  if (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   if (elect_one()) umma_commit(bar);
 }
