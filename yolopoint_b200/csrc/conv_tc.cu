@@ -166,6 +166,71 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   if (threadIdx.x == 0) stamp(1);
   if (a.ablate != 6) {   // 6 = launch + prologue only (timing experiment)
 
+  // ---- epilogue geometry of this thread (needed before the roles start: the residual of the thread's first unit is fetched NOW,
+  // under the main loop -- it cost 0.4-0.8 us of exposed latency in front of the first epilogue barrier, longest for the producer /
+  // issuer warps, which only reach the epilogue when their loops are done).  Unit u = columns [16 u, 16 u + 16); first unit = hf.
+  using TO = typename OutT<OUT_FMT>::type;
+  constexpr int CH = 16 * UNITS;                 // elements per staging row
+  constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
+  constexpr int NG = NT / 128;                   // warp groups (2 or 4)
+  constexpr int G = NG > UNITS ? NG / UNITS : 1; // staging chunks worked on at the same time (every warp group has a unit)
+  const int q = warp & 3;                        // TMEM lane quarter this warp may access
+  const int hf = warp >> 2;                      // warp group
+  const int row = q * 32 + lane;               // accumulator row (TMEM lane) of this thread
+  const int rdiv = a.patch ? a.Wp : a.Wt;      // patch mode: rows index the padded patch, halo columns are dropped
+  const int rh = row / rdiv, rw = row - rh * rdiv;
+  const int oh = h0 + rh, ow = w0 + rw;
+  const bool in_tile = rh < a.Ht && rw < a.Wt;
+  const bool valid = in_tile && (oh < a.Ho) && (ow < a.Wo);
+  const int srow = in_tile ? rh * a.Wt + rw : 127;   // row of the (compact Ht x Wt) staging tile this thread fills
+  const bool et0 = (threadIdx.x == 64);
+  const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  const int n_chunks = a.Nt / CH;
+  const bool has_res = a.res_base != nullptr && valid;
+  const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
+
+  // A chunk (one staging row, CH columns) is computed in passes of 16 columns by a rolled loop: few live registers (two
+  // CTAs per SM, so that one CTA's epilogue overlaps the other's main loop) and a loop body that stays in the instruction
+  // cache -- the unrolled epilogue ran once per CTA from cold code and spent ~40 % of its issue slots waiting for
+  // instruction fetch (ncu source view, stall_no_inst).
+  constexpr int PU = 1;                          // 16-column units per pass
+  constexpr int PE = 16 * PU;                    // columns per pass
+  constexpr int NP = UNITS / PU;                 // passes per chunk
+  // residual of columns [col0, col0 + PE) for this thread's pixel, planes summed (residual format == output format family)
+  auto load_res = [&](int col0, float* r) {
+    if (!has_res) {
+#pragma unroll
+      for (int i = 0; i < PE; ++i) r[i] = 0.0f;
+      return;
+    }
+    if (OUT_FMT == YP_FMT_BF16) {
+      const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_base) + res_off + col0);
+#pragma unroll
+      for (int j = 0; j < PE / 8; ++j) {
+        const uint4 u = __ldg(p + j);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); r[j * 8 + 2 * e] = f.x; r[j * 8 + 2 * e + 1] = f.y; }
+      }
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + col0);
+      const float4* pl = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + a.res_plane + col0);
+#pragma unroll
+      for (int j = 0; j < PE / 4; ++j) {
+        const float4 hi = __ldg(p + j);
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (OUT_FMT == YP_FMT_F32X2) lo = __ldg(pl + j);
+        r[j * 4] = hi.x + lo.x; r[j * 4 + 1] = hi.y + lo.y; r[j * 4 + 2] = hi.z + lo.z; r[j * 4 + 3] = hi.w + lo.w;
+      }
+    }
+  };
+  float res[PE];
+  const bool res_pre = hf * 16 < a.Nt && a.split_k == 1 && !a.rowmin && !a.l2norm;
+  if (res_pre) {
+    if (a.res_base) asm volatile("griddepcontrol.wait;" ::: "memory");   // the residual may be the previous kernel's output
+    load_res(hf * 16, res);
+  }
+
   if (warp == 0 && elect_one()) {
     // ===================== TMA producer (one elected lane runs the whole loop) =====================
     asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
@@ -328,61 +393,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
     // quarter, which split the 16-column units of the tile between them (warp group hf takes the units u with u % NG == hf).
     // With one warp per scheduler the epilogue was bound by single-warp instruction latency (~4 cycles per instruction);
     // layers that cannot fill the GPU anyway (one CTA per SM) run 16 warps = four per quarter, which halves it again.
-    using TO = typename OutT<OUT_FMT>::type;
-    constexpr int CH = 16 * UNITS;                 // elements per staging row
-    constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
-    constexpr int NG = NT / 128;                   // warp groups (2 or 4)
-    constexpr int G = NG > UNITS ? NG / UNITS : 1; // staging chunks worked on at the same time (every warp group has a unit)
-    const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int hf = warp >> 2;                      // warp group
-    const int row = q * 32 + lane;               // accumulator row (TMEM lane) of this thread
-    const int rdiv = a.patch ? a.Wp : a.Wt;      // patch mode: rows index the padded patch, halo columns are dropped
-    const int rh = row / rdiv, rw = row - rh * rdiv;
-    const int oh = h0 + rh, ow = w0 + rw;
-    const bool in_tile = rh < a.Ht && rw < a.Wt;
-    const bool valid = in_tile && (oh < a.Ho) && (ow < a.Wo);
-    const int srow = in_tile ? rh * a.Wt + rw : 127;   // row of the (compact Ht x Wt) staging tile this thread fills
-    const bool et0 = (threadIdx.x == 64);
-    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int n_chunks = a.Nt / CH;
-    const bool has_res = a.res_base != nullptr && valid;
-    const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
-
-    // A chunk (one staging row, CH columns) is computed in passes of 16 columns by a rolled loop: few live registers (two
-    // CTAs per SM, so that one CTA's epilogue overlaps the other's main loop) and a loop body that stays in the instruction
-    // cache -- the unrolled epilogue ran once per CTA from cold code and spent ~40 % of its issue slots waiting for
-    // instruction fetch (ncu source view, stall_no_inst).
-    constexpr int PU = 1;                          // 16-column units per pass
-    constexpr int PE = 16 * PU;                    // columns per pass
-    constexpr int NP = UNITS / PU;                 // passes per chunk
-    // residual of columns [col0, col0 + PE) for this thread's pixel, planes summed (residual format == output format family)
-    auto load_res = [&](int col0, float* r) {
-      if (!has_res) {
-#pragma unroll
-        for (int i = 0; i < PE; ++i) r[i] = 0.0f;
-        return;
-      }
-      if (OUT_FMT == YP_FMT_BF16) {
-        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_base) + res_off + col0);
-#pragma unroll
-        for (int j = 0; j < PE / 8; ++j) {
-          const uint4 u = __ldg(p + j);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); r[j * 8 + 2 * e] = f.x; r[j * 8 + 2 * e + 1] = f.y; }
-        }
-      } else {
-        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + col0);
-        const float4* pl = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + a.res_plane + col0);
-#pragma unroll
-        for (int j = 0; j < PE / 4; ++j) {
-          const float4 hi = __ldg(p + j);
-          float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (OUT_FMT == YP_FMT_F32X2) lo = __ldg(pl + j);
-          r[j * 4] = hi.x + lo.x; r[j * 4 + 1] = hi.y + lo.y; r[j * 4 + 2] = hi.z + lo.z; r[j * 4 + 3] = hi.w + lo.w;
-        }
-      }
-    };
     // accumulator columns [col, col+16) of this thread's row: sum of all TMEM sources (main products first)
     auto tmem_acc16 = [&](int col, float* v) {
       float t[4][16];
@@ -435,12 +445,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
       return v + res;
     };
 
-    float res[PE];
-    asm volatile("griddepcontrol.wait;" ::: "memory");     // the residual may be the previous kernel's output
-    // The residual of this thread's first unit is fetched while the main loop is still running (it cost 0.4 us of exposed
-    // latency in front of every pass).  Unit u (16 columns) of the tile = columns [16 u, 16 u + 16); this thread's first is u = hf.
-    const bool res_pre = hf * 16 < a.Nt && a.split_k == 1 && !a.rowmin && !a.l2norm;
-    if (res_pre) load_res(hf * 16, res);
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // residual / split-K workspace may be the previous kernel's output
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (et0) stamp(2);
