@@ -46,10 +46,12 @@ struct ConvArgs {
   int Nt, stages, stage_bytes, a_region_bytes, bar_off, tx_bytes;
   // MMA issuers (see kernel comment).  Issuer q emits, per 32-byte k-step, n_jobs[q] MMAs (A plane ja, W plane jb) with
   // instruction descriptor iss_idesc[q] into accumulator (iss_col[q] + r * iss_stride[q]), r rotating over iss_cnt[q].
-  int n_iss, kstep_mod;            // kstep_mod: 0 = every issuer takes every k-step, else issuer q takes k % kstep_mod == q
-  int n_jobs[2], job_a[2][2], job_b[2][2];
-  int iss_col[2], iss_stride[2], iss_cnt[2];
-  uint32_t iss_idesc[2];
+  // Issuer q (warp 1 + q) takes the k-steps kstart[q], kstart[q] + kinc[q], ... of every k-block.
+  int n_iss;
+  int kstart[4], kinc[4];
+  int n_jobs[4], job_a[4][2], job_b[4][2];
+  int iss_col[4], iss_stride[4], iss_cnt[4];
+  uint32_t iss_idesc[4];
   int n_src, src_col[16];          // TMEM column bases whose sum is the result (main products first)
   int split_k, kb_per_split;       // grid.z CTAs share one output tile, each reducing a slice of K
   // patch mode (3x3 stride 1): one (Ht+2) x (Wt+2) input patch per channel block stays in shared memory and the nine taps
@@ -307,13 +309,14 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
     const uint32_t b_plane = a.Nt * a.ck_bytes;
     const int cnt = a.iss_cnt[q];
     const uint32_t col0 = tmem_base + a.iss_col[q], cstride = a.iss_stride[q], idesc = a.iss_idesc[q];
-    const int kstart = a.kstep_mod ? q : 0, kinc = a.kstep_mod ? a.kstep_mod : 1;
+    const int kstart = a.kstart[q], kinc = a.kinc[q];
     const uint32_t a_off0 = a.job_a[q][0] * a.a_plane_off, b_off0 = a.job_b[q][0] * b_plane;
     const uint32_t a_off1 = a.job_a[q][1] * a.a_plane_off, b_off1 = a.job_b[q][1] * b_plane;
     const bool two = a.n_jobs[q] == 2;
     const uint32_t dhi = smem_desc_hi(a.ck_bytes);
     const bool live = a.ablate != 1;
     const bool fast4 = live && ksteps == 4 && kinc == 1 && !two && a.ablate != 8;   // YP_CONV_ABLATE=8: generic loop (A/B runs)
+    const bool fast2 = live && ksteps == 4 && kinc == 2 && !two && a.ablate != 8;   // two issuers share a stream: every other k-step
     uint32_t used = 0;                   // bit r set = accumulator r of this issuer already holds a partial sum
     int s = 0, ph = 0, nxt = 0;
     if (a.patch) {
@@ -335,6 +338,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
             // operand set-up of MMA k+1 overlaps the issue of MMA k
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+              umma32_one<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
+              used |= 1u << nxt;
+              nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+            }
+          } else if (fast2) {
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
               umma32_one<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
               used |= 1u << nxt;
               nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
@@ -367,6 +377,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
         if (fast4) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            umma32_one<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
+            used |= 1u << nxt;
+            nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+          }
+        } else if (fast2) {
+#pragma unroll
+          for (int k = 0; k < 4; k += 2) {
             umma32_one<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
             used |= 1u << nxt;
             nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
@@ -708,7 +725,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
     const uint32_t b_plane = a.Nt * a.ck_bytes;
     const int cnt = a.iss_cnt[q];
     const uint32_t cstride = a.iss_stride[q], idesc = a.iss_idesc[q];
-    const int kstart = a.kstep_mod ? q : 0, kinc = a.kstep_mod ? a.kstep_mod : 1;
+    const int kstart = a.kstart[q], kinc = a.kinc[q];
     const uint32_t a_off0 = a.job_a[q][0] * a.a_plane_off, b_off0 = a.job_b[q][0] * b_plane;
     const uint32_t a_off1 = a.job_a[q][1] * a.a_plane_off, b_off1 = a.job_b[q][1] * b_plane;
     const bool two = a.n_jobs[q] == 2;
@@ -1164,9 +1181,33 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     if (n_p > mmas_min) n_p = mmas_min;
     if (n_s > mmas_min) n_s = mmas_min;
     YP_REQUIRE(n_p >= 1 && n_s >= 1, YP_ERR_SHAPE, "conv: no accumulator plan for Nt=%d", Nt);
-    a.n_iss = 2; a.kstep_mod = 0;
-    a.n_jobs[0] = 1; a.job_a[0][0] = 0; a.job_b[0][0] = 0; a.iss_col[0] = 0; a.iss_stride[0] = 2 * Nt; a.iss_cnt[0] = n_p; a.iss_idesc[0] = idesc(2 * Nt);
-    a.n_jobs[1] = 1; a.job_a[1][0] = 1; a.job_b[1][0] = 0; a.iss_col[1] = n_p * 2 * Nt; a.iss_stride[1] = Nt; a.iss_cnt[1] = n_s; a.iss_idesc[1] = idesc(Nt);
+    // Issue rate: one thread sustains one small MMA per ~120 cycles (descriptor / accumulator bookkeeping), the tensor core needs
+    // 2 Nt / 2 + Nt / 2 cycles for the two MMAs of a k-step (48 for Nt = 32), so each of the two MMA streams is dealt to TWO
+    // threads (even / odd k-steps of every k-block, each with its own accumulators) when it has the accumulators and k-steps.
+    static const bool four = getenv("YP_CONV_ISSUERS4") == nullptr || atoi(getenv("YP_CONV_ISSUERS4")) != 0;
+    const int per_blk = a.ck_bytes / 32;
+    const bool split_main = four && per_blk >= 2 && n_p >= 2 && mmas_min >= 2 * n_p;
+    const bool split_cross = four && per_blk >= 2 && n_s >= 2 && mmas_min >= 2 * n_s;
+    int qn = 0;
+    auto add_iss = [&](int ja, int col, int stride, int cnt, int n, int ks, int ki) {
+      a.n_jobs[qn] = 1; a.job_a[qn][0] = ja; a.job_b[qn][0] = 0; a.iss_col[qn] = col; a.iss_stride[qn] = stride; a.iss_cnt[qn] = cnt;
+      a.iss_idesc[qn] = idesc(n); a.kstart[qn] = ks; a.kinc[qn] = ki;
+      ++qn;
+    };
+    if (split_main) {
+      const int h0n = (n_p + 1) / 2;
+      add_iss(0, 0, 2 * Nt, h0n, 2 * Nt, 0, 2);
+      add_iss(0, h0n * 2 * Nt, 2 * Nt, n_p - h0n, 2 * Nt, 1, 2);
+    } else {
+      add_iss(0, 0, 2 * Nt, n_p, 2 * Nt, 0, 1);
+    }
+    if (split_cross) {
+      add_iss(1, n_p * 2 * Nt, Nt, 1, Nt, 0, 2);
+      add_iss(1, n_p * 2 * Nt + Nt, Nt, n_s - 1, Nt, 1, 2);
+    } else {
+      add_iss(1, n_p * 2 * Nt, Nt, n_s, Nt, 0, 1);
+    }
+    a.n_iss = qn;
     int k = 0;
     for (int j = 0; j < n_p; ++j) a.src_col[k++] = j * 2 * Nt;               // main products first
     for (int j = 0; j < n_p; ++j) a.src_col[k++] = j * 2 * Nt + Nt;          // A_hi x W_lo
@@ -1175,7 +1216,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     cols = n_p * 2 * Nt + n_s * Nt;
   } else if (tf32) {
     // Nt in (128, 256] (L2-norm head of wide models): main accumulator + one accumulator for both cross terms
-    a.n_iss = 2; a.kstep_mod = 0;
+    a.n_iss = 2; a.kstart[0] = a.kstart[1] = 0; a.kinc[0] = a.kinc[1] = 1;
     a.n_jobs[0] = 1; a.job_a[0][0] = 0; a.job_b[0][0] = 0; a.iss_col[0] = 0; a.iss_stride[0] = 0; a.iss_cnt[0] = 1; a.iss_idesc[0] = idesc(Nt);
     a.n_jobs[1] = 2; a.job_a[1][0] = 1; a.job_b[1][0] = 0; a.job_a[1][1] = 0; a.job_b[1][1] = 1;
     a.iss_col[1] = Nt; a.iss_stride[1] = 0; a.iss_cnt[1] = 1; a.iss_idesc[1] = idesc(Nt);
@@ -1185,11 +1226,10 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     const int total = (tmem_limit / Nt) >= 1 ? tmem_limit / Nt : 512 / Nt;
     static const int max_iss = getenv("YP_CONV_ISSUERS") ? atoi(getenv("YP_CONV_ISSUERS")) : 2;
     a.n_iss = (total >= 2 && ksteps >= 2 && max_iss >= 2) ? 2 : 1;
-    a.kstep_mod = a.n_iss == 2 ? 2 : 0;
     // one accumulator per issuer: every accumulator costs a 128-lane TMEM read in the epilogue; short K loops (<= 16
     // k-steps, the 1x1 layers) are issued by a single thread into a single accumulator
     if (mmas_min <= 16) a.n_iss = 1;
-    if (a.n_iss == 1) a.kstep_mod = 0;
+    for (int q = 0; q < 2; ++q) { a.kstart[q] = a.n_iss == 2 ? q : 0; a.kinc[q] = a.n_iss == 2 ? 2 : 1; }
     int each = 1;
     const int per = mmas_min / a.n_iss;
     if (each > per) each = per;
