@@ -54,13 +54,14 @@ def dims(version: str) -> Tuple[Tuple[int, ...], Tuple[int, ...]]:
     return cs, ns
 
 
-def _fold(sd: Dict[str, torch.Tensor], name: str) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Conv+BN folding exactly as src/utils/torch_utils_yolo.py:194-214 (fp32)."""
-    w = sd[name + ".conv.weight"].float()
+def _fold(sd: Dict[str, torch.Tensor], name: str, dtype=torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Conv+BN folding exactly as src/utils/torch_utils_yolo.py:194-214 (fp32; ``dtype=torch.float64`` evaluates the same
+    expressions in double precision, see OracleNet)."""
+    w = sd[name + ".conv.weight"].to(dtype)
     if name + ".bn.weight" not in sd:  # already fused state dict
-        return w, sd[name + ".conv.bias"].float()
-    g, b = sd[name + ".bn.weight"].float(), sd[name + ".bn.bias"].float()
-    mu, var = sd[name + ".bn.running_mean"].float(), sd[name + ".bn.running_var"].float()
+        return w, sd[name + ".conv.bias"].to(dtype)
+    g, b = sd[name + ".bn.weight"].to(dtype), sd[name + ".bn.bias"].to(dtype)
+    mu, var = sd[name + ".bn.running_mean"].to(dtype), sd[name + ".bn.running_var"].to(dtype)
     scale = g.div(torch.sqrt(BN_EPS + var))
     wf = torch.mm(torch.diag(scale), w.view(w.shape[0], -1)).view(w.shape)
     bf = b - g.mul(mu).div(torch.sqrt(var + BN_EPS))
@@ -70,24 +71,26 @@ def _fold(sd: Dict[str, torch.Tensor], name: str) -> Tuple[torch.Tensor, torch.T
 class OracleNet:
     """Functional, BN-folded, eval-mode YOLOPoint forward (src/models/YOLOPoint.py:198-246).
 
-    ``sd`` is a reference-format state dict (keys ``model.Conv1.conv.weight`` ...).
+    ``sd`` is a reference-format state dict (keys ``model.Conv1.conv.weight`` ...).  ``dtype=torch.float64`` evaluates the same
+    graph on the same fp32 weights in double precision: the yardstick that tells how far ANY fp32 evaluation (the reference's
+    own included) is from the exact result, used by the tests to set the float tolerances.
     """
 
-    def __init__(self, sd: Dict[str, torch.Tensor], version: str, nc: int, model_name: str = "YOLOPoint"):
+    def __init__(self, sd: Dict[str, torch.Tensor], version: str, nc: int, model_name: str = "YOLOPoint", dtype=torch.float32):
         assert model_name in ("YOLOPoint", "YOLOPointv52"), model_name
-        self.version, self.nc, self.no, self.model_name = version, nc, nc + 5, model_name
+        self.version, self.nc, self.no, self.model_name, self.dtype = version, nc, nc + 5, model_name, dtype
         sd = {(k[len("model."):] if k.startswith("model.") else k): v.detach().cpu() for k, v in sd.items()}
         self.sd = sd
         (self.c1, self.c2, self.c3, self.c4, self.c5), (self.n1, self.n2, self.n3) = dims(version)
         self._folded: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
-        self.anchors = sd["Detect.anchors"].float()  # (3,3,2), already divided by stride
-        self.stride = torch.tensor(STRIDES)
+        self.anchors = sd["Detect.anchors"].to(dtype)  # (3,3,2), already divided by stride
+        self.stride = torch.tensor(STRIDES, dtype=dtype)
 
     # -- building blocks -------------------------------------------------------------------
     def _conv(self, name: str, x: torch.Tensor, k: int, s: int, p: Optional[int] = None) -> torch.Tensor:
         """models/common.py:22-34 forward_fuse: act(conv(x)) with SiLU."""
         if name not in self._folded:
-            self._folded[name] = _fold(self.sd, name)
+            self._folded[name] = _fold(self.sd, name, self.dtype)
         w, b = self._folded[name]
         p = k // 2 if p is None else p
         return F.silu(F.conv2d(x, w, b, stride=s, padding=p))
@@ -122,7 +125,7 @@ class OracleNet:
         """Detect.forward, eval branch (src/models/yolo.py:49-81)."""
         raw = []
         for i, t in enumerate(feats):
-            t = F.conv2d(t, self.sd[f"Detect.m.{i}.weight"].float(), self.sd[f"Detect.m.{i}.bias"].float())
+            t = F.conv2d(t, self.sd[f"Detect.m.{i}.weight"].to(self.dtype), self.sd[f"Detect.m.{i}.bias"].to(self.dtype))
             bs, _, ny, nx = t.shape
             raw.append(t.view(bs, 3, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous())
         return detect_decode(raw, self.anchors, self.stride), raw
@@ -131,7 +134,7 @@ class OracleNet:
     def forward_v52(self, x: torch.Tensor, keep: Optional[dict] = None) -> Dict[str, object]:
         """YOLOPointv52.forward (src/models/YOLOPoint.py:295-342)."""
         up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
-        x = self._conv("Conv1", x.float(), 6, 2, 2)
+        x = self._conv("Conv1", x.to(self.dtype), 6, 2, 2)
         x = self._conv("Conv2", x, 3, 2)
         xa = self._c2f("Bottleneck1", x, self.n1)
         x = self._conv("Conv3", xa, 3, 2)
@@ -165,17 +168,17 @@ class OracleNet:
             return self.forward_v52(x, keep)
         sd = self.sd
         up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
-        x = self._conv("Conv1", x.float(), 6, 2, 2)
+        x = self._conv("Conv1", x.to(self.dtype), 6, 2, 2)
         x = self._conv("Conv2", x, 3, 2)
         xa = self._c3("Bottleneck1", x, self.n1)
         x = self._conv("Conv3", xa, 3, 2)
         semi = self._c3("BottleneckDet", x, self.n1)
-        semi = F.conv2d(semi, sd["ConvDet.weight"].float())
+        semi = F.conv2d(semi, sd["ConvDet.weight"].to(self.dtype))
         xb = self._c3("Bottleneck2", x, self.n2)
         descA = self._conv("ConvDescA", xa, 3, 2, 1)
         descB = up(self._conv("ConvDescB", xb, 3, 2, 1))
         desc = self._c3("BottleneckDesc", torch.cat((descA, descB), 1), self.n1)
-        desc = F.conv2d(desc, sd["ConvDesc.weight"].float(), padding=1)
+        desc = F.conv2d(desc, sd["ConvDesc.weight"].to(self.dtype), padding=1)
         dn = torch.norm(desc, p=2, dim=1)
         desc = desc.div(torch.unsqueeze(dn, 1))
         x = self._conv("Conv4", xb, 3, 2)
@@ -195,7 +198,7 @@ class OracleNet:
             keep.update(xa=xa, xb=xb, xc=xc, xd=xd, xe=xe, xf=xf, xg=xg, xh=xh)
         raw = []
         for i, t in enumerate((xf, xg, xh)):
-            t = F.conv2d(t, sd[f"Detect.m.{i}.weight"].float(), sd[f"Detect.m.{i}.bias"].float())
+            t = F.conv2d(t, sd[f"Detect.m.{i}.weight"].to(self.dtype), sd[f"Detect.m.{i}.bias"].to(self.dtype))
             bs, _, ny, nx = t.shape
             raw.append(t.view(bs, 3, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous())
         pred = detect_decode(raw, self.anchors, self.stride)
@@ -212,8 +215,8 @@ def detect_decode(raw: Sequence[torch.Tensor], anchors: torch.Tensor, stride: to
     for i, x in enumerate(raw):
         bs, na, ny, nx, no = x.shape
         yv, xv = torch.meshgrid(torch.arange(ny), torch.arange(nx), indexing="ij")
-        grid = torch.stack((xv, yv), 2).expand(1, na, ny, nx, 2).float()
-        ag = (anchors[i].clone() * stride[i]).view(1, na, 1, 1, 2).expand(1, na, ny, nx, 2).float()
+        grid = torch.stack((xv, yv), 2).expand(1, na, ny, nx, 2).to(x.dtype)
+        ag = (anchors[i].clone() * stride[i]).view(1, na, 1, 1, 2).expand(1, na, ny, nx, 2).to(x.dtype)
         y = x.sigmoid()
         xy = (y[..., 0:2] * 2 - 0.5 + grid) * stride[i]
         wh = (y[..., 2:4] * 2) ** 2 * ag

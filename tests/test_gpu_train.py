@@ -137,13 +137,15 @@ def test_bn_act_matches_torch(shape, act):
     assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
 
 
-def test_model_train_step_matches_torch():
-    """One train-mode forward/backward of YOLOPoint-N through the B200 conv kernels vs the PyTorch fp32 path on the same
+# ("l", 2, 640, 640): the model and resolution of BASELINE.json configs[4] (YOLOPoint-L training step), small batch
+@pytest.mark.parametrize("ver,B,H,W", [("n", 4, 192, 256), ("l", 2, 640, 640)])
+def test_model_train_step_matches_torch(ver, B, H, W):
+    """One train-mode forward/backward of YOLOPoint through the B200 conv kernels vs the PyTorch fp32 path on the same
     parameters: outputs within bf16 noise, every parameter receives a gradient that points the same way."""
     torch.manual_seed(0)
     names = [str(i) for i in range(80)]
-    m = Model(names=names, version="n").cuda().train()
-    x = torch.rand(4, 3, 192, 256, device="cuda")
+    m = Model(names=names, version=ver).cuda().train()
+    x = torch.rand(B, 3, H, W, device="cuda")
 
     def run(backend):
         m.train_backend = backend

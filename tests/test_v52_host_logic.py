@@ -173,5 +173,7 @@ def test_synthetic_weights_and_tuning_tables_are_model_specific():
     assert TUNING_V52["n"] != TUNING["n"] and TUNING_V52["m"] == TUNING["m"]
     p5, p52 = tuning_path("s", 1, 640, 640, "fp32"), tuning_path("s", 1, 640, 640, "fp32", V52)
     assert p5 != p52 and p52.endswith("v52s_1x640x640_fp32.json")
-    assert load_tuning("s", 1, 640, 640, "fp32", V52) == {}                          # no table yet: library heuristics
+    t52, t5 = load_tuning("s", 1, 640, 640, "fp32", V52), load_tuning("s", 1, 640, 640, "fp32")
+    assert t52 and "BottleneckDet.cv2" in t52 and "ConvDet" not in t52 and "ConvDet" in t5   # each family has its own measured table
+    assert load_tuning("l", 1, 640, 640, "fp32", V52) == {}                          # no table: library heuristics
     assert len(load_tuning("s", 1, 640, 640, "fp32")) > 0
