@@ -36,7 +36,7 @@ WORKLOADS = {
     "s640v52": ("s", 640, 640, 1),  # YOLOPointv52-S (the model configs/kitti_inference.yaml names), configs[1] geometry
 }
 MODEL_NAME = {"s640v52": "YOLOPointv52"}   # every other workload runs the YOLOPoint (v5-style) network
-CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 7.27e6}   # profiles/r01_conv_tc_ncu_full.md: mean of the three YOLOPoint-S layer geometries captured
+CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 7.27e6}   # profiles/r01_conv_tc_ncu_full.md: mean of the three YOLOPoint-S layer geometries captured (cold L2)
 NAMES = [str(i) for i in range(80)]
 # SURVEY.md section 8a, per frame (forward); s640v52: conv-module hook count on the reference YOLOPointv52-S
 CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398, "l640train": 135.526, "s640v52": 21.363}
@@ -138,6 +138,64 @@ def cpu_reference_fps(version, H, W, steps, warmup, sd=None, model_name="YOLOPoi
     return len(times) / sum(times), best, float(np.median(times)), {str(k): round(v, 2) for k, v in sweep.items()}
 
 
+def torch_eager_net_ms(model, B, H, W, dev):
+    """The network alone through eager PyTorch on the same GPU: this repo's module tree (the reference's layer-for-layer graph, BN
+    folded like the reference's `.eval().fuse()`) on cuDNN / ATen kernels -- what the reference itself would run on a CUDA device
+    (SURVEY.md section 2b).  Two settings: PyTorch's default (cuDNN may use plain TF32 for fp32 convolutions) and true fp32."""
+    import copy
+    tm = copy.deepcopy(model).fuse().eval()
+    x = torch.rand(B, 3, H, W, device=dev)
+    out = {}
+    prev = torch.backends.cudnn.allow_tf32
+    try:
+        for key, allow in (("ms_cudnn_default_tf32_allowed", True), ("ms_cudnn_fp32", False)):
+            torch.backends.cudnn.allow_tf32 = allow
+            with torch.no_grad():
+                for _ in range(5):
+                    tm.model(x)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    tm.model(x)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            out[key] = e0.elapsed_time(e1) / 20
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    out["what"] = "network forward only (no decode / NMS / keypoints / match), eager launches, batch as in config.workload"
+    return out
+
+
+def other_configs():
+    """Short, bounded runs of the other BASELINE.json configs in child processes (their full JSON lines are kept under profiles/):
+    configs[2] YOLOPoint-M 1280x736 batch 4 per GPU (bf16 and fp32), configs[3] descriptor match sweep, configs[4] YOLOPoint-L
+    training step batch 8 per GPU."""
+    import subprocess
+    res = {}
+
+    def child(tag, cmd, pick, timeout=420):
+        try:
+            r = subprocess.run([sys.executable] + cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+            lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+            res[tag] = pick(lines) if lines else {"error": (r.stderr or "no output")[-300:]}
+        except Exception as e:  # pragma: no cover
+            res[tag] = {"error": str(e)[:300]}
+
+    short = ["--steps", "20", "--warmup", "5", "--no-cpu-baseline", "--no-other-configs", "--also-streams", "0"]
+    frames = lambda ls: {"frames_per_s": ls[-1]["value"], "e2e_frames_per_s": ls[-1]["e2e"]["value"], "ms_per_step": ls[-1]["ms_per_step"],
+                         "net_only_ms": ls[-1]["detail"]["net_only_ms"], "conv_tflops": ls[-1]["roofline"]["achieved"],
+                         "roofline_frac": ls[-1]["roofline"]["frac"], "workload": ls[-1]["config"]["workload"]}
+    child("m1280_bf16", [os.path.join(ROOT, "bench.py"), "--workload", "m1280", "--precision", "bf16"] + short, frames)
+    child("m1280_fp32", [os.path.join(ROOT, "bench.py"), "--workload", "m1280", "--precision", "fp32"] + short, frames)
+    child("l640train_bf16", [os.path.join(ROOT, "bench.py"), "--workload", "l640train", "--steps", "5", "--warmup", "3"],
+          lambda ls: {"samples_per_s": ls[-1]["value"], "ms_per_step": ls[-1]["ms_per_step"], "conv_tflops": ls[-1]["roofline"]["achieved"],
+                      "roofline_frac": ls[-1]["roofline"]["frac"], "workload": ls[-1]["config"]["workload"]})
+    child("match_sweep_d256", [os.path.join(ROOT, "tools", "bench_match.py")],
+          lambda ls: [{"n": int(l["workload"].split("=")[2].split()[0]), "ms": l["ms"], "tflops_fp32_equiv": l["tflops_fp32"], "matches": l["matches"]} for l in ls])
+    return res
+
+
 def train_main(args, version, H, W, per_gpu, world, rank, local_rank):
     """configs[4]: one training step = 2 forwards + 3 losses + backward + gradient all-reduce + Adam (yolopoint_b200/trainer.py).
     value = samples/s over all ranks with the synthetic batch resident in HBM; e2e = the same step fed from pinned host memory
@@ -234,6 +292,7 @@ def main():
     ap.add_argument("--train-backend", default="b200", choices=["b200", "cudnn_bf16", "torch"], help="l640train only: conv kernels used by the step")
     ap.add_argument("--train-batch", type=int, default=0, help="l640train only: samples per GPU (default 8)")
     ap.add_argument("--train-graphs", type=int, default=1, help="l640train only: 1 = forward/backward passes replayed from CUDA graphs, 0 = eager launches")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of BASELINE configs 3-5 and of eager PyTorch reported under detail")
     args = ap.parse_args()
     version, H, W, per_gpu = WORKLOADS[args.workload]
     model_name = MODEL_NAME.get(args.workload, "YOLOPoint")
@@ -435,6 +494,9 @@ def main():
                          "launches_per_step": n_conv, "avg_launch_us": net_ms * 1e3 / n_conv, "algorithmic_gflop_per_step": flops_step / 1e9,
                          "note": "achieved = SURVEY 8a conv FLOPs per frame x frames per step / live CUDA-event time of the conv launches of one step"},
             "detail": {"net_only_ms": net_ms, "keypoints": kp_n, "boxes": box_n, "matches": match_n, "concurrent_camera_streams": multi}}
+    if world == 1 and not args.no_other_configs and args.workload == "s640":
+        line["detail"]["torch_eager_gpu"] = torch_eager_net_ms(model, per_gpu, H, W, dev)
+        line["detail"]["other_configs"] = other_configs()
     if not args.no_cpu_baseline and world == 1:
         n = max(3, min(30, int(args.cpu_seconds / 0.3)))
         cfps, cores, med, sweep = cpu_reference_fps(version, H, W, n, 2, sd, model_name)
