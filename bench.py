@@ -138,12 +138,14 @@ def cpu_reference_fps(version, H, W, steps, warmup, sd=None, model_name="YOLOPoi
     return len(times) / sum(times), best, float(np.median(times)), {str(k): round(v, 2) for k, v in sweep.items()}
 
 
-def torch_eager_net_ms(model, B, H, W, dev):
+def torch_eager_net_ms(sd, version, model_name, B, H, W, dev):
     """The network alone through eager PyTorch on the same GPU: this repo's module tree (the reference's layer-for-layer graph, BN
     folded like the reference's `.eval().fuse()`) on cuDNN / ATen kernels -- what the reference itself would run on a CUDA device
     (SURVEY.md section 2b).  Two settings: PyTorch's default (cuDNN may use plain TF32 for fp32 convolutions) and true fp32."""
-    import copy
-    tm = copy.deepcopy(model).fuse().eval()
+    from yolopoint_b200 import Model
+    tm = Model(names=NAMES, version=version, model_name=model_name)
+    tm.load_state_dict(sd)
+    tm = tm.to(dev).fuse().eval()
     x = torch.rand(B, 3, H, W, device=dev)
     out = {}
     prev = torch.backends.cudnn.allow_tf32
@@ -495,7 +497,7 @@ def main():
                          "note": "achieved = SURVEY 8a conv FLOPs per frame x frames per step / live CUDA-event time of the conv launches of one step"},
             "detail": {"net_only_ms": net_ms, "keypoints": kp_n, "boxes": box_n, "matches": match_n, "concurrent_camera_streams": multi}}
     if world == 1 and not args.no_other_configs and args.workload == "s640":
-        line["detail"]["torch_eager_gpu"] = torch_eager_net_ms(model, per_gpu, H, W, dev)
+        line["detail"]["torch_eager_gpu"] = torch_eager_net_ms(sd, version, model_name, per_gpu, H, W, dev)
         line["detail"]["other_configs"] = other_configs()
     if not args.no_cpu_baseline and world == 1:
         n = max(3, min(30, int(args.cpu_seconds / 0.3)))
