@@ -330,6 +330,20 @@ int yp_match_frames(const float* d1, const int32_t* sel1, const int32_t* n1, con
                     float* matches, int32_t* match_count, const int32_t* kcount, const int32_t* bcount, int32_t* counts3, void* stream);
 int yp_gather_rows(const float* src, const int32_t* sel, const int32_t* count, int32_t B, int32_t cap, int32_t D, float* dst, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Homography adaptation (export path).
+ * yp_warp_image_batch = utils/utils.py:333-376 (warp_image_batch): img [B,C,H,W] fp32 -> out [B,C,H,W], sampled at the inverse
+ * homography hinv [B,3,3] of every output pixel's normalised coordinate; xs [W] / ys [H] are torch.linspace(-1, 1, n) (passed in so
+ * that the coordinates are bit-identical to the reference's); nearest = 0: bilinear, 1: nearest; align_corners = True, zeros padding.
+ * yp_homography_adaptation = export_homography.py:97-128: heat, mask [B,H,W] (the B warped copies of ONE image and their valid
+ * masks) -> agg [H,W] = sum_b warp(heat_b * mask_b) / sum_b warp(mask_b) in one pass (0/0 = NaN like the reference);
+ * sum_heat / sum_mask [H,W] optionally receive numerator and denominator.
+ * ---------------------------------------------------------------------------------------------- */
+int yp_warp_image_batch(const float* img, const float* hinv, const float* xs, const float* ys, int32_t B, int32_t C, int32_t H, int32_t W,
+                        int32_t nearest, float* out, void* stream);
+int yp_homography_adaptation(const float* heat, const float* mask, const float* hinv, const float* xs, const float* ys, int32_t B,
+                             int32_t H, int32_t W, float* sum_heat, float* sum_mask, float* agg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

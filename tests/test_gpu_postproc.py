@@ -202,3 +202,44 @@ def test_point_tracker_with_cuda_match_equals_reference(golden, capsys):
         assert trk.track_count == int(g[f"count{f}"])
         f += 1
     capsys.readouterr()
+
+
+def test_warp_image_batch_and_homography_adaptation_golden(golden):
+    """SURVEY.md section 8f rank 2 against what the unmodified reference produced (tests/golden/homography.npz): the bilinear warp to
+    1e-6 abs, the nearest warp identical except where a source coordinate sits within an ulp of x.5, the fused aggregation
+    (product, two warps, two sums, division in one kernel) to 1e-6 abs with the same NaN pattern."""
+    g = golden("homography.npz")
+    heat, mask, hinv = (torch.from_numpy(g[k]).cuda() for k in ("heat", "mask", "inv_homographies"))
+    wb = yp.warp_image_batch(heat, hinv, mode="bilinear")
+    np.testing.assert_allclose(wb.cpu().numpy(), g["warp_bilinear"], rtol=0, atol=1e-6)
+    wn = yp.warp_image_batch(heat, hinv, mode="nearest").cpu().numpy()
+    assert (wn != g["warp_nearest"]).mean() < 1e-3
+    agg = yp.homography_adaptation(heat, mask, hinv)[0].cpu().numpy()
+    assert np.array_equal(np.isnan(agg), np.isnan(g["aggregated"]))
+    np.testing.assert_allclose(np.nan_to_num(agg), np.nan_to_num(g["aggregated"]), rtol=0, atol=1e-6)
+    # host input -> host output, 2-D / RGB forms of the reference's signature
+    one = yp.warp_image_batch(g["heat"][0, 0], g["inv_homographies"][0])
+    assert not one.is_cuda and one.shape == (1, 1, 48, 64)
+    np.testing.assert_allclose(one.numpy()[0, 0], g["warp_bilinear"][0, 0], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,H,W", [(100, 120, 160), (7, 33, 57)])
+def test_homography_adaptation_vs_oracle_random(B, H, W):
+    """The export's real shape class (100 warped copies per image): random perspective homographies, random masks with holes."""
+    rs = np.random.RandomState(B + H)
+    heat = rs.rand(B, 1, H, W).astype(np.float32)
+    mask = (rs.rand(B, 1, H, W) > 0.2).astype(np.float32)
+    hinv = np.tile(np.eye(3, dtype=np.float32), (B, 1, 1))
+    hinv[:, :2, :2] += rs.uniform(-0.25, 0.25, (B, 2, 2)).astype(np.float32)
+    hinv[:, :2, 2] += rs.uniform(-0.3, 0.3, (B, 2)).astype(np.float32)
+    hinv[:, 2, :2] += rs.uniform(-0.15, 0.15, (B, 2)).astype(np.float32)
+    ref = O.homography_adaptation(heat, mask, hinv)
+    got = yp.homography_adaptation(torch.from_numpy(heat).cuda(), torch.from_numpy(mask).cuda(), torch.from_numpy(hinv).cuda())[0].cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(ref), rtol=0, atol=2e-6)
+    wref = O.warp_image_batch(heat[:5], hinv[:5])
+    wgot = yp.warp_image_batch(torch.from_numpy(heat[:5]).cuda(), torch.from_numpy(hinv[:5]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(wgot, wref, rtol=0, atol=2e-6)
+    # letterbox slicing as the reference applies it
+    padded = yp.homography_adaptation(torch.from_numpy(heat).cuda(), torch.from_numpy(mask).cuda(), torch.from_numpy(hinv).cuda(), pad=(4, 6, 3, 5))
+    assert padded.shape == (1, len(range(H)[4:W - 6]), len(range(W)[3:H - 5]))       # (:103-109 bound the rows by the WIDTH and vice versa)

@@ -9,6 +9,8 @@ behaviour as the reference's Python functions), executed by the B200 kernels.
   nms_fast                 src/utils/utils.py:118-182
   sample_desc_from_points  src/evaluations/descriptor_evaluation.py:148-181
   nn_match_two_way         src/demo.py:300-341 (PointTracker.nn_match_two_way)
+  warp_image_batch         src/utils/utils.py:333-376
+  homography_adaptation    src/export_homography.py:97-128 (heat-map aggregation over the warped copies of one image)
   detect / extract_keypoints / match   convenience names requested by BASELINE.json north_star
 
 numpy in -> numpy out where the reference does so; every call moves data to the current CUDA device, runs
@@ -209,3 +211,45 @@ def extract_keypoints(semi, desc, conf_thresh=0.015, nms_dist=4, boxes=None):
     if n < 0:
         raise RuntimeError("keypoint buffer overflow")
     return (pts[0, :n].double().cpu().numpy().T.copy() if n else np.zeros((3, 0))), out[0, :n].T.contiguous().cpu().numpy()
+
+
+def warp_image_batch(img, mat_homo_inv, device="cpu", mode="bilinear", padding_mode="zeros"):
+    """Inverse warp of a batch of images (src/utils/utils.py:333-376): ``img`` [B,1,H,W] / [B,C,H,W], [H,W,3] (RGB), [B,H,W,3] or
+    [H,W]; ``mat_homo_inv`` [B,3,3] or [3,3].  ``device`` is accepted for signature compatibility; the warp always runs on the
+    current CUDA device and the result comes back where the input was."""
+    if padding_mode != "zeros":
+        raise NotImplementedError("the reference only ever warps with padding_mode='zeros'")
+    src_dev = img.device if isinstance(img, torch.Tensor) else torch.device("cpu")
+    t = _to_dev(img)
+    transposed = False
+    if t.shape[-1] == 3 and t.dim() == 3:       # the reference unsqueezes and hands [1,H,W,3] to grid_sample as [N,C,H,W] = [1,H,W,3]
+        t = t.unsqueeze(0)
+    elif t.shape[-1] == 3 and t.dim() == 4:
+        transposed = True
+        t = t.transpose(1, 3).transpose(2, 3)
+    elif t.dim() in (2, 3):
+        t = t.reshape(1, 1, t.shape[-2], t.shape[-1]) if t.dim() == 2 else t.reshape(1, 1, t.shape[0], t.shape[1])
+    hm = _to_dev(mat_homo_inv).reshape(-1, 3, 3)
+    out = ops.warp_batch(t.contiguous(), hm, mode)
+    if transposed:
+        out = out.transpose(1, 3).transpose(1, 2)
+    return out if src_dev.type == "cuda" else out.cpu()
+
+
+def homography_adaptation(heatmap, mask_2D, inv_homographies, pad=None):
+    """The aggregation step of the homography-adaptation export (src/export_homography.py:97-128): ``heatmap`` [B,1,H,W] =
+    flattenDetection(semi) of the B warped copies of one image, ``mask_2D`` [B,1,H,W] their valid masks, ``inv_homographies``
+    [B,3,3] -> ``sum_b warp(heatmap_b * mask_b) / sum_b warp(mask_b)`` as [1,H',W'] (``outputs`` of the reference; NaN where no copy
+    covers a pixel), fused into one kernel.  ``pad`` = the sample's letterbox tuple: the reference's slicing (:103-109, including its
+    use of the WIDTH for the row bound) is applied to the result, which is equivalent because the aggregation is per pixel."""
+    src_dev = heatmap.device if isinstance(heatmap, torch.Tensor) else torch.device("cpu")
+    h, m = _to_dev(heatmap), _to_dev(mask_2D)
+    B, H, W = h.shape[0], h.shape[-2], h.shape[-1]
+    out = ops.homography_adapt(h.reshape(B, H, W), m.reshape(B, H, W), _to_dev(inv_homographies).reshape(-1, 3, 3)).unsqueeze(0)
+    if pad:
+        height, width = H, W
+        if pad[1]:
+            out = out[:, int(pad[0]):width - int(pad[1]), :]
+        if pad[3]:
+            out = out[:, :, int(pad[2]):height - int(pad[3])]
+    return out if src_dev.type == "cuda" else out.cpu()

@@ -217,3 +217,46 @@ def match_two_way(d1: torch.Tensor, n1, d2: torch.Tensor, n2, nn_thresh: float, 
         algo = "tc" if min(d1.shape[0], d2.shape[0]) >= 8192 and d1.shape[1] % 16 == 0 else "simt"
     rk, ck = match_partial_tc(d1, n1, d2, n2) if algo == "tc" else match_partial(d1, n1, d2, n2)
     return match_finalize(rk, n1, ck, nn_thresh)
+
+
+def _linspace_pair(H: int, W: int, dev):
+    """torch.linspace(-1, 1, n) for the columns / rows, exactly the values warp_image_batch builds its grid from."""
+    return torch.linspace(-1, 1, W).to(dev), torch.linspace(-1, 1, H).to(dev)
+
+
+def warp_batch(img: torch.Tensor, hinv: torch.Tensor, mode: str = "bilinear", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """img [B,C,H,W] fp32, hinv [B,3,3] -> [B,C,H,W] sampled at the inverse-homography position of every output pixel
+    (utils/utils.py:333-376: align_corners=True, zeros padding)."""
+    _need_cuda(img, "img")
+    L = _lib.lib(require_device=True)
+    assert mode in ("bilinear", "nearest"), mode
+    img = img.contiguous().float()
+    B, Cc, H, W = img.shape
+    hinv = hinv.to(img.device).float().contiguous().view(-1, 3, 3)
+    assert hinv.shape[0] == B, (hinv.shape, B)
+    xs, ys = _linspace_pair(H, W, img.device)
+    if out is None:
+        out = torch.empty_like(img)
+    _lib.check(L.yp_warp_image_batch(img.data_ptr(), hinv.data_ptr(), xs.data_ptr(), ys.data_ptr(), B, Cc, H, W, int(mode == "nearest"),
+                                     out.data_ptr(), _stream(img.device)))
+    return out
+
+
+def homography_adapt(heat: torch.Tensor, mask: torch.Tensor, hinv: torch.Tensor, want_sums: bool = False):
+    """heat, mask [B,H,W] fp32 (B warped copies of one image, their valid masks), hinv [B,3,3] -> aggregated heatmap [H,W]
+    = sum_b warp(heat_b * mask_b) / sum_b warp(mask_b) in one kernel (export_homography.py:97-128)."""
+    _need_cuda(heat, "heatmap")
+    L = _lib.lib(require_device=True)
+    heat, mask = heat.contiguous().float(), mask.to(heat.device).contiguous().float()
+    B, H, W = heat.shape
+    assert mask.shape == heat.shape
+    hinv = hinv.to(heat.device).float().contiguous().view(-1, 3, 3)
+    assert hinv.shape[0] == B
+    xs, ys = _linspace_pair(H, W, heat.device)
+    agg = torch.empty((H, W), dtype=torch.float32, device=heat.device)
+    sh = torch.empty_like(agg) if want_sums else None
+    sm = torch.empty_like(agg) if want_sums else None
+    _lib.check(L.yp_homography_adaptation(heat.data_ptr(), mask.data_ptr(), hinv.data_ptr(), xs.data_ptr(), ys.data_ptr(), B, H, W,
+                                          sh.data_ptr() if want_sums else None, sm.data_ptr() if want_sums else None, agg.data_ptr(),
+                                          _stream(heat.device)))
+    return (agg, sh, sm) if want_sums else agg
