@@ -344,6 +344,17 @@ int yp_warp_image_batch(const float* img, const float* hinv, const float* xs, co
 int yp_homography_adaptation(const float* heat, const float* mask, const float* hinv, const float* xs, const float* ys, int32_t B,
                              int32_t H, int32_t W, float* sum_heat, float* sum_mask, float* agg, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Keypoint-detector loss of the training step, forward and backward fused:
+ * labels2Dto3D + getMasks (utils/utils.py:184-209, 103-116) + ComputeDetectorLoss (utils/loss_functions.py:600-619).
+ * semi: logits [B,65,Hc,Wc] fp32 with element strides (sB, sC, sH, sW); labels2d, mask2d: [B,8Hc,8Wc] fp32 contiguous.
+ * dsemi (same strides as semi) receives d loss / d semi; out2[0] = loss, out2[1] = number of valid cells (sum of the cell mask).
+ * workspace: yp_detector_loss_workspace_bytes(B, Hc, Wc).  Reductions run in a fixed order (bit-reproducible).
+ * ---------------------------------------------------------------------------------------------- */
+size_t yp_detector_loss_workspace_bytes(int32_t B, int32_t Hc, int32_t Wc);
+int yp_detector_loss(const float* semi, int64_t sB, int64_t sC, int64_t sH, int64_t sW, const float* labels2d, const float* mask2d,
+                     int32_t B, int32_t Hc, int32_t Wc, float* dsemi, float* out2, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,3 +218,31 @@ def test_graphed_training_step_tracks_eager():
     assert eager[3] < eager[0] and graphed[3] < graphed[0]            # Adam makes progress on the fixed batch
     for a, b in zip(eager, graphed):
         assert abs(a - b) < 0.1 * abs(a), (eager, graphed)
+
+
+def test_fused_detector_loss_matches_reference_golden_and_autograd(golden):
+    """csrc/loss.cu (labels2Dto3D + getMasks + ComputeDetectorLoss, forward and backward in one kernel) against the vectors of the
+    UNMODIFIED reference (loss 1e-6 relative, gradient 1e-5 relative) and against PyTorch autograd on a channels-last batch with
+    partly invalid cells, empty cells (dustbin) and several keypoints per cell."""
+    from yolopoint_b200 import losses as Lz
+    g = golden("losses.npz")
+    semi = torch.from_numpy(g["semi"]).cuda().requires_grad_(True)
+    det = Lz.ComputeDetectorLoss("cuda")
+    loss = det.from_2d(semi, torch.from_numpy(g["labels"]).cuda(), torch.from_numpy(g["mask"]).cuda())
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), g["ldet"], rtol=1e-6)
+    np.testing.assert_allclose(semi.grad.cpu().numpy(), g["gsemi"], rtol=1e-5, atol=1e-9)
+    gen = torch.Generator().manual_seed(5)
+    B, Hc, Wc = 3, 12, 20
+    x = (torch.randn(B, 65, Hc, Wc, generator=gen) * 3).cuda().contiguous(memory_format=torch.channels_last)
+    lab = (torch.rand(B, 1, Hc * 8, Wc * 8, generator=gen) < 0.01).float().cuda()
+    msk = torch.ones(B, 1, Hc * 8, Wc * 8).cuda()
+    msk[:, :, :20, :30] = 0
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    la = det.from_2d(xa, lab, msk)
+    lb = det(xb, Lz.labels2Dto3D(lab), Lz.getMasks(msk, "cuda"))
+    (la * 1.7).backward()
+    (lb * 1.7).backward()
+    assert abs(la.item() - lb.item()) < 1e-6 * abs(lb.item())
+    assert _rel(xa.grad, xb.grad.double()) < 1e-5
+    assert torch.equal(det.from_2d(x, lab, msk), det.from_2d(x, lab, msk))      # fixed-order reductions: bit-reproducible

@@ -85,6 +85,8 @@ SIGNATURES = {
     "yp_sample_desc": (_i32, [_vp, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "yp_warp_image_batch": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "yp_homography_adaptation": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "yp_detector_loss_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "yp_detector_loss": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "yp_match_partial": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "yp_match_finalize": (_i32, [_vp, _vp, _i32, _vp, _i32, _f32, _vp, _vp, _vp]),
 }

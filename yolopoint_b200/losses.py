@@ -5,8 +5,9 @@ reference as well (row f3 lists fusing them into kernels as later work), so they
 device the network outputs live on.  Same names / arguments / return values as the reference, so ``train.py`` can import
 them from here:
 
-  ComputeObjectLoss     src/utils/loss_functions.py:90-234   (YOLOv5 box / objectness / class loss, CIoU)
-  bbox_iou              src/utils/metrics_yolo.py:202-240
+  ComputeObjectLoss     src/utils/loss_functions.py:90-234   (YOLOv5 box / objectness / class loss, CIoU) -- re-designed without
+                        boolean indexing: fixed-shape masked candidates, no host synchronisation (see the class docstring)
+  bbox_iou, ciou_xywh   src/utils/metrics_yolo.py:202-240
   ComputeDetectorLoss   src/utils/loss_functions.py:600-619  (65-way cell classification, BCE on the softmax)
   labels2Dto3D/getMasks src/utils/utils.py:184-209, 103-116
   descriptor_loss_sparse src/utils/loss_functions.py:361-481 (sampled hinge loss between frame / warped-frame descriptors)
@@ -19,123 +20,156 @@ are gathered from one ``da @ db^T`` GEMM instead of a materialised ``[K, n, D]``
 from __future__ import annotations
 
 import math
+from typing import Optional
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 
+def ciou_xywh(p: torch.Tensor, t: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """Complete-IoU of row-aligned centre-format boxes p, t [..., 4] = (x, y, w, h) -> [...].
+
+    CIoU = IoU - rho^2 / c^2 - alpha v (Zheng et al. 2020, the form src/utils/metrics_yolo.py:202-240 evaluates with CIoU=True):
+    rho = centre distance, c = diagonal of the smallest enclosing box, v = (4 / pi^2)(atan(w_t / h_t) - atan(w_p / h_p))^2,
+    alpha = v / (v - IoU + 1 + eps) treated as a constant in the backward pass.  ``eps`` enters where the reference adds it
+    (union, c^2, the two aspect ratios, alpha), so the values agree to rounding."""
+    px, py, pw, ph = p.unbind(-1)
+    tx, ty, tw, th = t.unbind(-1)
+    p_l, p_r, p_t, p_b = px - pw / 2, px + pw / 2, py - ph / 2, py + ph / 2
+    t_l, t_r, t_t, t_b = tx - tw / 2, tx + tw / 2, ty - th / 2, ty + th / 2
+    inter = (torch.minimum(p_r, t_r) - torch.maximum(p_l, t_l)).clamp(0) * (torch.minimum(p_b, t_b) - torch.maximum(p_t, t_t)).clamp(0)
+    iou = inter / (pw * ph + tw * th - inter + eps)
+    diag2 = (torch.maximum(p_r, t_r) - torch.minimum(p_l, t_l)) ** 2 + (torch.maximum(p_b, t_b) - torch.minimum(p_t, t_t)) ** 2 + eps
+    rho2 = ((t_l + t_r - p_l - p_r) ** 2 + (t_t + t_b - p_t - p_b) ** 2) / 4
+    v = (4 / math.pi ** 2) * (torch.atan(tw / (th + eps)) - torch.atan(pw / (ph + eps))) ** 2
+    alpha = (v / (v - iou + (1 + eps))).detach()
+    return iou - (rho2 / diag2 + v * alpha)
+
+
 def bbox_iou(box1, box2, xywh=True, CIoU=False, eps=1e-7):
-    """IoU / complete-IoU of row-aligned boxes [n,4] (metrics_yolo.py:202-240)."""
-    if xywh:
-        (x1, y1, w1, h1), (x2, y2, w2, h2) = box1.chunk(4, 1), box2.chunk(4, 1)
-        b1x1, b1x2, b1y1, b1y2 = x1 - w1 / 2, x1 + w1 / 2, y1 - h1 / 2, y1 + h1 / 2
-        b2x1, b2x2, b2y1, b2y2 = x2 - w2 / 2, x2 + w2 / 2, y2 - h2 / 2, y2 + h2 / 2
-    else:
-        b1x1, b1y1, b1x2, b1y2 = box1.chunk(4, 1)
-        b2x1, b2y1, b2x2, b2y2 = box2.chunk(4, 1)
-        w1, h1, w2, h2 = b1x2 - b1x1, b1y2 - b1y1, b2x2 - b2x1, b2y2 - b2y1
-    inter = (torch.min(b1x2, b2x2) - torch.max(b1x1, b2x1)).clamp(0) * (torch.min(b1y2, b2y2) - torch.max(b1y1, b2y1)).clamp(0)
-    union = w1 * h1 + w2 * h2 - inter + eps
-    iou = inter / union
-    if not CIoU:
-        return iou
-    cw = torch.max(b1x2, b2x2) - torch.min(b1x1, b2x1)
-    ch = torch.max(b1y2, b2y2) - torch.min(b1y1, b2y1)
-    c2 = cw ** 2 + ch ** 2 + eps
-    rho2 = ((b2x1 + b2x2 - b1x1 - b1x2) ** 2 + (b2y1 + b2y2 - b1y1 - b1y2) ** 2) / 4
-    v = (4 / math.pi ** 2) * torch.pow(torch.atan(w2 / (h2 + eps)) - torch.atan(w1 / (h1 + eps)), 2)
-    with torch.no_grad():
-        alpha = v / (v - iou + (1 + eps))
-    return iou - (rho2 / c2 + v * alpha)
+    """Reference-named entry point (src/utils/metrics_yolo.py:202-240) for the two forms the hot path uses: row-aligned [n,4]
+    boxes -> [n,1] IoU or CIoU."""
+    if not xywh:
+        (l1, t1, r1, b1), (l2, t2, r2, b2) = box1.unbind(-1), box2.unbind(-1)
+        box1 = torch.stack(((l1 + r1) / 2, (t1 + b1) / 2, r1 - l1, b1 - t1), -1)
+        box2 = torch.stack(((l2 + r2) / 2, (t2 + b2) / 2, r2 - l2, b2 - t2), -1)
+    if CIoU:
+        return ciou_xywh(box1, box2, eps).unsqueeze(-1)
+    px, py, pw, ph = box1.unbind(-1)
+    tx, ty, tw, th = box2.unbind(-1)
+    inter = (torch.minimum(px + pw / 2, tx + tw / 2) - torch.maximum(px - pw / 2, tx - tw / 2)).clamp(0) * \
+            (torch.minimum(py + ph / 2, ty + th / 2) - torch.maximum(py - ph / 2, ty - th / 2)).clamp(0)
+    return (inter / (pw * ph + tw * th - inter + eps)).unsqueeze(-1)
 
 
-def smooth_BCE(eps=0.1):
-    return 1.0 - 0.5 * eps, 0.5 * eps
+class TargetPlan:
+    """Everything ``ComputeObjectLoss`` needs from the labels, per Detect level, as FIXED-SHAPE tensors over all
+    E = 5 x anchors x targets assignment candidates with a validity mask (no boolean indexing, so building and using it never
+    waits for the device): flat cell index of the candidate, the target box relative to its cell, its anchor, its class."""
+
+    def __init__(self, levels):
+        self.levels = levels      # list of dicts: valid [E] bool, cell [E] long (b, a, gj, gi flattened), tbox [E,4], anchor [E,2], cls [E] long
 
 
 class ComputeObjectLoss:
-    """loss_functions.py:90-234 (focal loss / autobalance variants are configuration the shipped YAMLs leave off)."""
+    """YOLOv5's box / objectness / class loss as the reference configures it (src/utils/loss_functions.py:90-234: CIoU box loss, BCE
+    objectness against the detached CIoU, BCE classes; label smoothing, focal loss and autobalance are options the shipped YAMLs
+    leave off).
+
+    Target assignment (the rule of :120-234): a target is a candidate for an anchor of a level when no side of the target is more
+    than ``anchor_t`` times longer or shorter than the anchor's; it is assigned to the cell that contains its centre and to the
+    (up to two) neighbouring cells its centre is closest to.  The reference expresses this with boolean indexing, which on a GPU
+    makes the host wait for the device five times per level; here all 5 x na x nt candidates are kept with a validity mask and the
+    sums are masked, which gives the same loss values (tests/test_losses.py, against vectors of the reference) without any
+    synchronisation, so the whole loss can be enqueued behind the forward pass.  Where several targets claim one (image, anchor,
+    cell), the reference's ``tobj[b, a, gj, gi] = iou`` keeps the last one in its candidate order (offset variant, anchor,
+    target); the same order decides here."""
 
     def __init__(self, model, config, device, autobalance=False):
-        if config.get("fl_gamma", 0.0) > 0:
-            raise NotImplementedError("fl_gamma > 0 (focal loss) is not used by the reference configs")
-        self.BCEcls = nn.BCEWithLogitsLoss(pos_weight=torch.tensor([config["cls_pw"]], device=device))
-        self.BCEobj = nn.BCEWithLogitsLoss(pos_weight=torch.tensor([config["obj_pw"]], device=device))
-        self.cp, self.cn = smooth_BCE(eps=config.get("label_smoothing", 0.0))
-        m = getattr(model, "module", model).model.Detect
-        self.balance = {3: [4.0, 1.0, 0.4]}.get(m.nl, [4.0, 1.0, 0.25, 0.06, 0.02])
-        self.gr, self.hyp = 1.0, config
-        self.na, self.nc, self.nl, self.anchors, self.device = m.na, m.nc, m.nl, m.anchors, device
+        if config.get("fl_gamma", 0.0) > 0 or autobalance:
+            raise NotImplementedError("focal loss / autobalance are not used by the reference configs")
+        self.hyp, self.device = config, device
+        self.cls_pw = torch.tensor([config["cls_pw"]], device=device)
+        self.obj_pw = torch.tensor([config["obj_pw"]], device=device)
+        smooth = config.get("label_smoothing", 0.0)
+        self.cp, self.cn = 1.0 - 0.5 * smooth, 0.5 * smooth        # positive / negative class targets
+        det = getattr(model, "module", model).model.Detect
+        self.na, self.nc, self.nl, self.anchors = det.na, det.nc, det.nl, det.anchors
+        self.balance = [4.0, 1.0, 0.4] if det.nl == 3 else [4.0, 1.0, 0.25, 0.06, 0.02]
+        self.gr = 1.0
 
-    def __call__(self, p, targets, built=None):
-        """``built`` = a precomputed ``build_targets(p, targets)`` (it only needs the shapes of ``p``, so a training step can run it
-        -- and its host synchronisations -- before the forward pass is launched)."""
-        dev = self.device
-        lcls, lbox, lobj = (torch.zeros(1, device=dev) for _ in range(3))
-        tcls, tbox, indices, anchors = built if built is not None else self.build_targets(p, targets)
-        for i, pi in enumerate(p):
-            b, a, gj, gi = indices[i]
-            tobj = torch.zeros(pi.shape[:4], dtype=pi.dtype, device=dev)
-            n = b.shape[0]
-            if n:
-                pxy, pwh, _, pcls = pi[b, a, gj, gi].split((2, 2, 1, self.nc), 1)
-                pxy = pxy.sigmoid() * 2 - 0.5
-                pwh = (pwh.sigmoid() * 2) ** 2 * anchors[i]
-                iou = bbox_iou(torch.cat((pxy, pwh), 1), tbox[i], CIoU=True).squeeze()
-                lbox = lbox + (1.0 - iou).mean()
-                iou = iou.detach().clamp(0).type(tobj.dtype)
-                if self.gr < 1:
-                    iou = (1.0 - self.gr) + self.gr * iou
-                tobj[b, a, gj, gi] = iou
-                if self.nc > 1:
-                    t = torch.full_like(pcls, self.cn, device=dev)
-                    t[range(n), tcls[i]] = self.cp
-                    lcls = lcls + self.BCEcls(pcls, t)
-            lobj = lobj + self.BCEobj(pi[..., 4], tobj) * self.balance[i]
-        lbox = lbox * self.hyp["box"]
-        lobj = lobj * self.hyp["obj"]
-        lcls = lcls * self.hyp["cls"]
-        return (lbox + lobj + lcls), torch.cat((lbox, lobj, lcls)).detach()
-
-    def build_targets(self, p, targets):
-        """targets [n,6] = (image, class, x, y, w, h) normalised -> per level (class, box, indices, anchors): every target is
-        assigned to the anchors within ratio anchor_t and to the cell it falls in plus its two nearest neighbours."""
-        dev = self.device
-        na, nt = self.na, targets.shape[0]
-        tcls, tbox, indices, anch = [], [], [], []
-        gain = torch.ones(7, device=dev)
-        ai = torch.arange(na, device=dev).float().view(na, 1).repeat(1, nt)
-        targets = torch.cat((targets.repeat(na, 1, 1), ai[..., None]), 2)
-        g = 0.5
-        off = torch.tensor([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1]], device=dev).float() * g
+    # -- labels only ---------------------------------------------------------------------------
+    def build_targets(self, p, targets) -> TargetPlan:
+        """``p``: the per-level predictions [B, na, ny, nx, no] (only their shapes are used; meta tensors are fine);
+        ``targets`` [nt, 6] = (image, class, x, y, w, h), box normalised to [0, 1]."""
+        dev, na = self.device, self.na
+        targets = targets.to(dev).float()
+        nt = targets.shape[0]
+        img, cls = targets[:, 0].long(), targets[:, 1].long()
+        half = torch.tensor([[0.0, 0.0], [0.5, 0.0], [0.0, 0.5], [-0.5, 0.0], [0.0, -0.5]], device=dev)     # centre, left, up, right, down
+        levels = []
         for i in range(self.nl):
-            anchors, shape = self.anchors[i], p[i].shape
-            gain[2:6] = torch.tensor(shape)[[3, 2, 3, 2]]
-            t = targets * gain
-            if nt:
-                r = t[..., 4:6] / anchors[:, None]
-                j = torch.max(r, 1 / r).max(2)[0] < self.hyp["anchor_t"]
-                t = t[j]
-                gxy = t[:, 2:4]
-                gxi = gain[[2, 3]] - gxy
-                j, k = ((gxy % 1 < g) & (gxy > 1)).T
-                l, m = ((gxi % 1 < g) & (gxi > 1)).T
-                j = torch.stack((torch.ones_like(j), j, k, l, m))
-                t = t.repeat((5, 1, 1))[j]
-                offsets = (torch.zeros_like(gxy)[None] + off[:, None])[j]
-            else:
-                t = targets[0]
-                offsets = 0
-            bc, gxy, gwh, a = t.chunk(4, 1)
-            a, (b, c) = a.long().view(-1), bc.long().T
-            gij = (gxy - offsets).long()
-            gi, gj = gij.T
-            indices.append((b, a, gj.clamp_(0, shape[2] - 1), gi.clamp_(0, shape[3] - 1)))
-            tbox.append(torch.cat((gxy - gij, gwh), 1))
-            anch.append(anchors[a])
-            tcls.append(c)
-        return tcls, tbox, indices, anch
+            B, _, ny, nx, _ = p[i].shape
+            size = torch.tensor([nx, ny], device=dev, dtype=torch.float32)
+            anchors = self.anchors[i].to(dev).float()                                   # [na, 2] in cells
+            gxy, gwh = targets[:, 2:4] * size, targets[:, 4:6] * size                  # [nt, 2] in cells
+            ratio = gwh[None] / anchors[:, None]                                       # [na, nt, 2]
+            shape_ok = torch.maximum(ratio, 1 / ratio).amax(2) < self.hyp["anchor_t"]  # [na, nt]
+            low = (gxy % 1 < 0.5) & (gxy > 1)                                          # centre in the left / upper half of its cell
+            inv = size - gxy
+            high = (inv % 1 < 0.5) & (inv > 1)                                         # ... in the right / lower half
+            near = torch.stack((torch.ones(nt, dtype=torch.bool, device=dev), low[:, 0], low[:, 1], high[:, 0], high[:, 1]))   # [5, nt]
+            valid = near[:, None, :] & shape_ok[None]                                  # [5, na, nt]
+            cell = (gxy[None] - half[:, None]).long()                                  # [5, nt, 2] (x, y), truncation like the reference
+            gi, gj = cell[..., 0].clamp(0, nx - 1), cell[..., 1].clamp(0, ny - 1)
+            a_idx = torch.arange(na, device=dev)
+            flat = ((img[None, None] * na + a_idx[None, :, None]) * ny + gj[:, None]) * nx + gi[:, None]      # [5, na, nt]
+            tbox = torch.cat((gxy[None] - cell.float(), gwh[None].expand(5, nt, 2)), 2)  # [5, nt, 4] relative to the UNclamped cell
+            E = 5 * na * nt
+            levels.append(dict(valid=valid.reshape(E), cell=flat.reshape(E), tbox=tbox[:, None].expand(5, na, nt, 4).reshape(E, 4),
+                               anchor=anchors[None, :, None].expand(5, na, nt, 2).reshape(E, 2), cls=cls[None, None].expand(5, na, nt).reshape(E),
+                               cells=B * na * ny * nx))
+        return TargetPlan(levels)
+
+    # -- predictions -----------------------------------------------------------------------------
+    def __call__(self, p, targets, built: Optional[TargetPlan] = None):
+        """-> (loss [1], detached (box, obj, cls) terms [3]).  ``built`` = a precomputed ``build_targets(p, targets)``."""
+        dev = self.device
+        plan = built if built is not None else self.build_targets(p, targets)
+        lbox = torch.zeros(1, device=dev)
+        lobj = torch.zeros(1, device=dev)
+        lcls = torch.zeros(1, device=dev)
+        for i, pi in enumerate(p):
+            lv = plan.levels[i]
+            valid, w = lv["valid"], lv["valid"].to(pi.dtype)
+            rows = pi.reshape(-1, pi.shape[-1])
+            obj_logit = rows[:, 4]
+            tobj = torch.zeros(lv["cells"] + 1, dtype=pi.dtype, device=dev)          # last slot swallows the invalid candidates
+            if valid.numel():
+                n = w.sum()
+                q = rows[lv["cell"]]                                                  # [E, no] (invalid candidates read a real row; masked below)
+                xy = q[:, 0:2].sigmoid() * 2 - 0.5
+                wh = (q[:, 2:4].sigmoid() * 2) ** 2 * lv["anchor"]
+                ciou = ciou_xywh(torch.cat((xy, wh), 1), lv["tbox"])
+                lbox = lbox + ((1.0 - ciou) * w).sum() / n.clamp(min=1)
+                score = ciou.detach().clamp(0).to(tobj.dtype)
+                if self.gr < 1:
+                    score = (1.0 - self.gr) + self.gr * score
+                # the last valid candidate of a cell (in candidate order) sets its objectness target
+                order = torch.arange(valid.numel(), device=dev)
+                slot = torch.where(valid, lv["cell"], torch.full_like(lv["cell"], lv["cells"]))
+                owner = torch.full((lv["cells"] + 1,), -1, dtype=torch.long, device=dev).scatter_reduce(0, slot, order, "amax")
+                mine = valid & (owner[slot] == order)
+                tobj = tobj.scatter(0, torch.where(mine, slot, torch.full_like(slot, lv["cells"])), torch.where(mine, score, torch.zeros_like(score)))
+                if self.nc > 1:
+                    tcls = torch.full_like(q[:, 5:], self.cn)
+                    tcls.scatter_(1, lv["cls"][:, None], self.cp)
+                    bce = F.binary_cross_entropy_with_logits(q[:, 5:], tcls, pos_weight=self.cls_pw, reduction="none")
+                    lcls = lcls + (bce * w[:, None]).sum() / (n * self.nc).clamp(min=1)
+            lobj = lobj + F.binary_cross_entropy_with_logits(obj_logit, tobj[:-1], pos_weight=self.obj_pw) * self.balance[i]
+        lbox, lobj, lcls = lbox * self.hyp["box"], lobj * self.hyp["obj"], lcls * self.hyp["cls"]
+        return lbox + lobj + lcls, torch.cat((lbox, lobj, lcls)).detach()
 
 
 def labels2Dto3D(labels, cell_size=8, add_dustbin=True):
@@ -155,8 +189,40 @@ def getMasks(mask_2D, device, cell_size=8):
     return torch.prod(labels2Dto3D(mask_2D.to(device), cell_size=cell_size, add_dustbin=False).float(), 1)
 
 
+class _DetectorLossFused(torch.autograd.Function):
+    """labels2Dto3D + getMasks + ComputeDetectorLoss, forward and backward in one pass over the logits (csrc/loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, semi, labels_2D, mask_2D):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib(require_device=True)
+        B, Cc, Hc, Wc = semi.shape
+        assert Cc == 65 and semi.dtype == torch.float32, (semi.shape, semi.dtype)
+        lab = labels_2D.to(semi.device).float().contiguous().view(B, Hc * 8, Wc * 8)
+        msk = mask_2D.to(semi.device).float().contiguous().view(B, Hc * 8, Wc * 8)
+        dsemi = torch.empty_like(semi)                       # same memory format as the logits (channels-last in the training step)
+        assert dsemi.stride() == semi.stride()
+        out2 = torch.empty(2, dtype=torch.float32, device=semi.device)
+        ws = torch.empty(L.yp_detector_loss_workspace_bytes(B, Hc, Wc), dtype=torch.uint8, device=semi.device)
+        sB, sC, sH, sW = semi.stride()
+        _lib.check(L.yp_detector_loss(semi.data_ptr(), sB, sC, sH, sW, lab.data_ptr(), msk.data_ptr(), B, Hc, Wc, dsemi.data_ptr(), out2.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), C.c_void_p(torch.cuda.current_stream(semi.device).cuda_stream)))
+        ctx.save_for_backward(dsemi)
+        return out2[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dsemi,) = ctx.saved_tensors
+        return dsemi * grad_out, None, None
+
+
 class ComputeDetectorLoss:
-    """loss_functions.py:600-619: BCE between softmax(semi) and the 65-channel labels, summed over channels, masked mean."""
+    """loss_functions.py:600-619: BCE between softmax(semi) and the 65-channel labels, summed over channels, masked mean.
+
+    ``__call__(inp, target, mask)`` is the reference's call on prepared [B,65,Hc,Wc] labels / [B,Hc,Wc] cell masks (PyTorch ops, any
+    device).  ``from_2d(inp, labels_2D, mask_2D)`` takes the [B,1,H,W] keypoint map and valid mask the data loader delivers and, on a
+    CUDA device, runs label preparation, loss and its gradient as one fused kernel (same value, tests/test_gpu_train.py)."""
 
     def __init__(self, device):
         self.device = device
@@ -165,6 +231,11 @@ class ComputeDetectorLoss:
         loss = F.binary_cross_entropy(torch.softmax(inp, dim=1), target, reduction="none")
         loss = (loss.sum(dim=1) * mask).sum()
         return loss / (mask.sum() + 1e-10)
+
+    def from_2d(self, inp, labels_2D, mask_2D):
+        if inp.is_cuda:
+            return _DetectorLossFused.apply(inp.float(), labels_2D, mask_2D)
+        return self(inp, labels2Dto3D(labels_2D.to(inp.device)), getMasks(mask_2D, inp.device))
 
 
 def _warp_points(points, homographies):

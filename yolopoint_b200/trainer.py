@@ -136,10 +136,8 @@ class TrainStep:
         self.gradclip = gradclip                # src/train.py:249-250: clip_grad_norm_ on the (averaged) gradients before the optimizer step
         self.model = model
         self.device = next(model.parameters()).device
-        if self.device.type == "cuda":
-            # the sampled-similarity GEMM of the descriptor loss (losses.py) and its two backward GEMMs (24000 x 24000 x 256) run on
-            # TF32 tensor cores instead of the fp32 SIMT path (10.7 ms -> 1 ms per step); the network itself computes in bf16
-            torch.backends.cuda.matmul.allow_tf32 = True
+        # (the sampled-similarity GEMM of the descriptor loss runs on TF32 tensor cores: losses._pair_similarities switches
+        # torch.backends.cuda.matmul.allow_tf32 on around that one matmul and restores it; nothing global is changed here)
         self.obj_loss = Lz.ComputeObjectLoss(model, LOSS_CFG, self.device)
         self.det_loss = Lz.ComputeDetectorLoss(self.device)
         self.sparse_cfg = dict(SPARSE_CFG if sparse_cfg is None else sparse_cfg)
@@ -187,16 +185,20 @@ class TrainStep:
         shapes = [torch.empty((B, det.na, H // int(s), W // int(s), det.no), device="meta") for s in (8, 16, 32)]
         built = self.obj_loss.build_targets(shapes, sample["box_labels"])
         pairs = Lz.descriptor_pairs(sample["warped_valid_mask"], sample["inv_homographies"], B, H // 8, W // 8, device=dev, **self.sparse_cfg)
-        lab, lab_w = Lz.labels2Dto3D(sample["labels_2D"]), Lz.labels2Dto3D(sample["warped_labels"])
-        msk, msk_w = Lz.getMasks(sample["valid_mask"], dev), Lz.getMasks(sample["warped_valid_mask"], dev)
         semi, desc, obj = self._forward(sample["image"], 0)
         semi_w, desc_w, _ = self._forward(sample["warped_image"], 1)
         loss_obj, items = self.obj_loss(obj, sample["box_labels"], built)
-        loss_det = self.det_loss(semi, lab, msk)
-        loss_det_w = self.det_loss(semi_w, lab_w, msk_w)
+        # label layout + cell masks + loss + gradient of the detector loss: one fused kernel per pass on CUDA (csrc/loss.cu)
+        loss_det = self.det_loss.from_2d(semi, sample["labels_2D"], sample["valid_mask"])
+        loss_det_w = self.det_loss.from_2d(semi_w, sample["warped_labels"], sample["warped_valid_mask"])
         loss_desc = self.desc_loss(desc, desc_w, sample["warped_valid_mask"], sample["inv_homographies"], pairs=pairs, **self.sparse_cfg)
         loss = loss_det + loss_det_w + LAMBDA_DESC * loss_desc + LAMBDA_OBJ * loss_obj
         return loss, dict(det=loss_det.detach(), det_warp=loss_det_w.detach(), desc=loss_desc.detach(), obj=loss_obj.detach())
+
+    def epoch_end(self):
+        """Advance the linear learning-rate schedule (src/train.py:91-93, stepped once per epoch at :289): the caller's epoch loop
+        calls this; ``step`` itself never touches the schedule."""
+        self.sched.step()
 
     def step(self, sample) -> torch.Tensor:
         """sample: dict as produced by the reference's data loader (src/train.py:196-205) with tensors on the model's device."""
