@@ -286,6 +286,31 @@ def descriptor_pairs(mask_valid_warp, inv_homographies, B, Hc, Wc, num_samples_p
     return pa, pb, rnd
 
 
+class _SimilarityTF32(torch.autograd.Function):
+    """a @ b^T with TF32 tensor cores for the forward GEMM AND the two backward GEMMs (24000 x 24000 x 256 each in the training
+    step: 10.7 ms on the fp32 SIMT path, 1 ms on tensor cores), with ``torch.backends.cuda.matmul.allow_tf32`` switched on only
+    around these three matmuls -- the process-wide setting is left as the caller had it."""
+
+    @staticmethod
+    def _mm(x, y):
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return x @ y
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return _SimilarityTF32._mm(a, b.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return _SimilarityTF32._mm(g, b), _SimilarityTF32._mm(g.t(), a)
+
+
 def _pair_similarities(descriptors, descriptors_warped, pairs):
     """Cosine similarities of the sampled pairs: pos [n] (a_i . b_i) and neg [K, n] (a_i . b_{rnd[k, i]}), n = B * pool
     (loss_functions.py:429-471 / 553-591: the part the two descriptor losses share)."""
@@ -303,12 +328,7 @@ def _pair_similarities(descriptors, descriptors_warped, pairs):
         # The reference materialises db[rnd] as a [K, n, D] tensor (4.9 GB for 8 x 3000 samples, K = 200, D = 256) and multiplies it
         # by the broadcast queries (loss_functions.py:468-471, 587-591).  The same K x n similarities are entries of the n x n matrix
         # da @ db^T: one GEMM (TF32 tensor cores, 2.3 GB result) + a gather, ~5x less memory traffic forward and backward.
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            neg = (da @ db.t()).gather(1, rnd.t()).t()
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+        neg = _SimilarityTF32.apply(da, db).gather(1, rnd.t()).t()
     else:
         neg = (da.unsqueeze(0) * db[rnd]).sum(-1)
     return pos, neg
