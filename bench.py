@@ -290,6 +290,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=1, help="independent camera streams (frame pipelines) in flight per GPU")
+    ap.add_argument("--in-flight", type=int, default=3, help="frames of the one camera stream in flight per GPU (software pipelining; 1 = one frame at a time)")
     ap.add_argument("--also-streams", type=int, default=3, help="extra (untimed-for-value) run with this many camera streams, reported under detail")
     ap.add_argument("--train-backend", default="b200", choices=["b200", "cudnn_bf16", "torch"], help="l640train only: conv kernels used by the step")
     ap.add_argument("--train-batch", type=int, default=0, help="l640train only: samples per GPU (default 8)")
@@ -337,11 +338,13 @@ def main():
     model.precision = args.precision
     model = model.to(dev).eval()
     NS = max(1, args.streams)
-    pipes = [FramePipeline(model, per_gpu, H, W, slot=i) for i in range(NS)]
+    pipes = [FramePipeline(model, per_gpu, H, W, slot=i, frames_in_flight=args.in_flight) for i in range(NS)]
     cuda_streams = [torch.cuda.Stream(dev) for _ in range(NS)]
     pipe = pipes[0]
     plan = pipe.plan
     config["streams_per_gpu"] = NS
+    config["frames_in_flight"] = (f"{args.in_flight}: consecutive frames of the one camera stream are software-pipelined, each a batch-{per_gpu} pass; "
+                                  "only the in-box filter + match of frame i+1 wait for frame i") if args.in_flight > 1 else 1
 
     # input pool larger than L2 (126 MB): every step reads a different frame batch from HBM
     frame_bytes = per_gpu * H * W * 3
@@ -365,7 +368,7 @@ def main():
     def step(i):
         """One step = every camera stream processes its next frame batch (independent graphs on independent CUDA streams)."""
         if NS == 1:
-            plan.frame_in.copy_(pool[(i + 7 * rank) % n_pool])
+            pipe.plan.frame_in.copy_(pool[(i + 7 * rank) % n_pool])
             pipe.step_device(True)
             return
         cur = torch.cuda.current_stream(dev)
@@ -387,6 +390,8 @@ def main():
     e0.record()
     for i in range(K):
         step(Wm + i)
+    for pp in pipes:
+        pp.join()          # frames in flight on the pipelines' own streams end inside the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -398,7 +403,7 @@ def main():
     multi = None
     if NS == 1 and args.also_streams > 1:
         M = args.also_streams
-        xp = [pipe] + [FramePipeline(model, per_gpu, H, W, slot=i) for i in range(1, M)]
+        xp = [FramePipeline(model, per_gpu, H, W, slot=8 + i) for i in range(M)]
         xs = [torch.cuda.Stream(dev) for _ in range(M)]
 
         def mstep(i):
@@ -464,10 +469,12 @@ def main():
     # H2D + pipeline + D2H while frame i is on the GPU, then unpacks frame i).  Every step's H2D and D2H are inside the timed region.
     t0 = time.perf_counter()
     Ke = min(K, 100)
-    host_submit(0)
+    ahead = max(1, args.in_flight)      # frames the host keeps submitted beyond the one it collects
+    for j in range(min(ahead, Ke)):
+        host_submit(j)
     for i in range(Ke):
-        if i + 1 < Ke:
-            host_submit(i + 1)
+        if i + ahead < Ke:
+            host_submit(i + ahead)
         res = host_collect()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YP_ABI_VERSION 6
+#define YP_ABI_VERSION 7
 
 typedef enum {
   YP_OK = 0,
@@ -134,6 +134,42 @@ size_t yp_conv2d_workspace_bytes(const YpConvDesc* desc);
  * tensor map is encoded, YP_OK otherwise; yp_last_error() describes the failure.  Lets a caller validate a whole launch plan (every
  * layer of a model at a given input shape) ahead of time. */
 int yp_conv2d_plan_check(const YpConvDesc* desc);
+
+/*
+ * Layer chains -- a segment of the network (the Conv / Bottleneck / C3 / SPPF sequence of YOLOPoint.forward,
+ * models/YOLOPoint.py:198-246, models/common.py:22-34, 79-89, 124-135, 213-229) executed by ONE persistent kernel instead of one
+ * launch per layer: one CTA per SM walks the operations in the given order; every operation is cut into the same work items a
+ * stand-alone launch would run as CTAs (item i of an operation goes to CTA (offset + i) mod #CTAs, the offsets rotating so that
+ * consecutive small layers land on different SMs), and an item starts as soon as the operations it depends on have published
+ * their completion counters in global memory (release / acquire at GPU scope, proxy fences around the TMA transfers).  TMEM
+ * allocation, tensor-map prefetch, launch latency and the grid-completion gap are paid once per segment, and independent layers
+ * that are adjacent in the list (different branches of the network) run concurrently on different SMs.
+ *
+ * ops[i].deps lists the operations (indices < i of the same chain) whose output ops[i] reads or overwrites (read-after-write,
+ * write-after-read and write-after-write on activation buffers); the caller derives them from its buffer plan
+ * (yolopoint_b200/engine.py: chain_dependencies).  The order of `ops` must be a valid sequential order.  Split-K layers get their
+ * own workspace inside the chain object (conv.workspace is ignored).  Chains longer than the kernel-parameter space allows are cut
+ * into several kernels launched back to back.  Supported: YP_ALGO_TCGEN05 convolutions with F32X2 operands (the parity mode) and
+ * the SPPF pooling; anything else returns YP_ERR_SHAPE and the caller keeps launching layer by layer.
+ * A chain object may be launched on one stream at a time (its completion counters and workspaces are per object).
+ */
+typedef struct {
+  int32_t type;        /* 0 = convolution (conv), 1 = SPPF pooling in place on the 4-slice concat buffer `pool` (see yp_sppf_pool) */
+  YpConvDesc conv;
+  YpView pool;
+  int32_t n_deps;
+  int32_t deps[8];
+} YpChainOp;
+int yp_conv_chain_create(const YpChainOp* ops, int32_t n_ops, void** chain);
+int yp_conv_chain_launch(void* chain, void* stream);
+int yp_conv_chain_destroy(void* chain);
+/* Number of kernels yp_conv_chain_launch enqueues (1 unless the chain was cut), and the work items / shared memory of the chain. */
+int yp_conv_chain_info(void* chain, int32_t* n_kernels, int32_t* n_items, int32_t* smem_bytes);
+/* Debug aid (chains created while the environment variable YP_CHAIN_DEBUG is set): device pointer of kernel `kernel`'s timeline,
+ * [n_ops][n_ctas][16] int64 %globaltimer stamps of the last item each CTA ran per operation (0 item start, 6 dependencies met,
+ * 1 prologue done, 8 first TMA load issued, 9 first operands landed, 10 first k-block issued, 11 all MMAs issued, 2 accumulators
+ * complete, 3 stores complete, 4 item end, 7 completion published); NULL when not recording. */
+int yp_debug_conv_chain_timeline(void* chain, int32_t kernel, void** device_buf_i64, int32_t* n_ops, int32_t* n_ctas);
 
 /*
  * yp_conv2d_nhwc_wgrad -- weight gradient of a Conv2d (bias-free, pad = k/2) for the training step: what autograd computes

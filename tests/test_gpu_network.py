@@ -231,3 +231,76 @@ def test_frontend_process_img_contract():
     big = np.zeros((490, 650, 3), np.uint8); big[5:485, 5:645] = frame
     pts2, _, _ = fe.process_img(big)
     np.testing.assert_array_equal(pts2[:2] - np.array([[5.0], [5.0]]), pts[:2])
+
+
+@pytest.mark.parametrize("ver,B,H,W", [("s", 1, 640, 640), ("n", 2, 96, 160)])
+def test_layer_chains_equal_per_layer_launches(ver, B, H, W):
+    """The network as layer chains (one persistent kernel per segment, device-side completion counters between layers;
+    yp_conv_chain_*) against the per-layer launch list: same kernels' arithmetic, so the outputs agree to fp32 rounding of the
+    accumulator plan (chained items always plan as one CTA per SM), replays are bit-identical (the counters reset themselves),
+    and the chained network meets the oracle tolerances."""
+    from yolopoint_b200.engine import Engine
+    _, sd = build(ver)
+    torch.manual_seed(3)
+    x = torch.rand(B, 3, H, W)
+    outs = {}
+    for chain in (False, True):
+        eng = Engine(sd, ver, 80, torch.device("cuda:0"), chain=chain)
+        p = eng.plan(B, H, W)
+        assert bool(p.chain) == chain
+        o1 = eng.forward(x.cuda())
+        o2 = eng.forward(x.cuda())
+        assert torch.equal(o1["semi"], o2["semi"]) and torch.equal(o1["desc"], o2["desc"]) and torch.equal(o1["objects"][0], o2["objects"][0])
+        outs[chain] = o1
+        if chain:
+            assert p.n_net_launches() <= 8 and sum(len(sg["ops"]) for sg in p.chain) == len(eng.net.ops)
+    a, b = outs[False], outs[True]
+    assert float((a["semi"] - b["semi"]).abs().max()) <= 1e-5 * max(1.0, float(a["semi"].abs().max()))
+    assert float((a["desc"] - b["desc"]).abs().max()) <= 1e-5
+    ref = O.OracleNet(sd, ver, 80).forward(x)
+    check_outputs(b, ref, f"chain {ver} {B}x{H}x{W}")
+
+
+@pytest.mark.parametrize("F", [2, 3])
+def test_frames_in_flight_equal_one_at_a_time(F):
+    """FramePipeline(frames_in_flight=F): consecutive frames of one camera stream overlap on the GPU (own context, stream and graphs
+    per frame in flight; only the in-box filter + match wait for the previous frame) -- the results of every frame, matches
+    against the previous frame included, are bit-identical to processing the frames one at a time, through the host path
+    (submit F ahead, collect in order) and through the device path (step_device + join)."""
+    m, _ = build("n")
+    H, W = 192, 256
+    frames = [synthetic_frame(H, W, s)[None] for s in range(9)]
+    ref_pipe = FramePipeline(m, 1, H, W)
+    ref = [ref_pipe.step_host(f)[0] for f in frames]
+    pipe = FramePipeline(m, 1, H, W, slot=3, frames_in_flight=F)
+    got = []
+    for j in range(F):
+        pipe.submit_host(frames[j])
+    for i in range(len(frames)):
+        if i + F < len(frames):
+            pipe.submit_host(frames[i + F])
+        got.append(pipe.collect()[0])
+    assert sum(r[3].shape[1] for r in ref) > 0 and sum(r[0].shape[1] for r in ref) > 0
+    for i, (r, g) in enumerate(zip(ref, got)):
+        for a, b, name in zip(r, g, ("pts", "desc", "boxes", "matches")):
+            assert a.shape == b.shape, (i, name, a.shape, b.shape)
+            np.testing.assert_array_equal(a, b, err_msg=f"frame {i} {name}")
+    # device path: frames resident on the GPU, results read from the context buffers after join()
+    pipe.reset_tracking()
+    ref_pipe.reset_tracking()
+    dev = torch.device("cuda:0")
+    ks = []
+    for f in frames[:5]:
+        pipe.plan.frame_in.copy_(torch.from_numpy(f).to(dev))
+        ks.append(pipe.step_device(True))
+    pipe.join()
+    torch.cuda.synchronize()
+    got_counts = [pipe.d_counts[k].cpu().numpy().copy() for k in ks[-pipe.nctx:]]
+    ref_counts = []
+    for f in frames[:5]:
+        ref_pipe.plan.frame_in.copy_(torch.from_numpy(f).to(dev))
+        k = ref_pipe.step_device(True)
+        torch.cuda.synchronize()
+        ref_counts.append(ref_pipe.d_counts[k].cpu().numpy().copy())
+    for a, b in zip(ref_counts[-pipe.nctx:], got_counts):
+        np.testing.assert_array_equal(a[:3], b[:3])

@@ -120,7 +120,7 @@ def test_c_abi_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.yp_abi_version() == 6
+    assert L.yp_abi_version() == 7
     # struct layouts must agree with the header (sizes only; offsets follow from the C rules both sides use)
     assert ctypes.sizeof(_lib.YpView) == 48 and ctypes.sizeof(_lib.YpNmsParams) == 40
 
@@ -181,3 +181,38 @@ def test_load_model_signature_and_compat_on_stand_in_modules():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_chain_dependencies_and_schedule():
+    """Layer-chain host logic (engine.chain_dependencies / chain_schedule): every read-after-write, write-after-read and
+    write-after-write pair of the launch list is ordered by the (transitively reduced) dependency lists, the schedule is a valid
+    sequential order, and the segment cuts sit right behind the milestone layers."""
+    from yolopoint_b200.engine import ConvOp, NetPlan, _op_reads_writes, _overlap, chain_dependencies, chain_schedule
+    for model_name, ver in (("YOLOPoint", "s"), ("YOLOPoint", "l"), ("YOLOPointv52", "n")):
+        net = NetPlan(ver, 80, "fp32", model_name)
+        ops = net.ops
+        deps = chain_dependencies(ops)
+        # transitive closure of the reduced lists
+        anc = []
+        for j, d in enumerate(deps):
+            a = set(d)
+            for i in d:
+                assert i < j
+                a |= anc[i]
+            anc.append(a)
+        rw = [_op_reads_writes(op) for op in ops]
+        for j in range(len(ops)):
+            for i in range(j):
+                hazard = _overlap(rw[i][1], rw[j][0]) or _overlap(rw[i][1], rw[j][1]) or _overlap(rw[i][0], rw[j][1])
+                if hazard:
+                    assert i in anc[j], (model_name, ver, i, j)
+        assert max(len(d) for d in deps) <= 6
+        names = ["+".join(op.names) if isinstance(op, ConvOp) else "other" for op in ops]
+        ms = [names.index("Detect.m.0"), names.index("Detect.m.1")]
+        order, cuts = chain_schedule(ops, ms)
+        assert sorted(order) == list(range(len(ops))) and cuts[-1] == len(ops)
+        pos = {j: k for k, j in enumerate(order)}
+        for j, d in enumerate(deps):
+            assert all(pos[i] < pos[j] for i in d)
+        for m in ms:
+            assert pos[m] + 1 in cuts

@@ -36,6 +36,10 @@ class YpConvDesc(C.Structure):
                 ("row_key", C.c_void_p), ("n_rows", C.c_void_p), ("n_cols", C.c_void_p), ("col_off", C.c_int32)]
 
 
+class YpChainOp(C.Structure):
+    _fields_ = [("type", C.c_int32), ("conv", YpConvDesc), ("pool", YpView), ("n_deps", C.c_int32), ("deps", C.c_int32 * 8)]
+
+
 class YpWgradDesc(C.Structure):
     _fields_ = [("x", YpView), ("dy", YpView), ("ksize", C.c_int32), ("stride", C.c_int32), ("dw", C.c_void_p)]
 
@@ -57,6 +61,11 @@ SIGNATURES = {
     "yp_conv2d_nhwc_fwd": (_i32, [_PC, _vp]),
     "yp_conv2d_workspace_bytes": (_sz, [_PC]),
     "yp_conv2d_plan_check": (_i32, [_PC]),
+    "yp_conv_chain_create": (_i32, [C.POINTER(YpChainOp), _i32, C.POINTER(C.c_void_p)]),
+    "yp_conv_chain_launch": (_i32, [_vp, _vp]),
+    "yp_conv_chain_destroy": (_i32, [_vp]),
+    "yp_conv_chain_info": (_i32, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "yp_debug_conv_chain_timeline": (_i32, [_vp, _i32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "yp_conv2d_nhwc_wgrad": (_i32, [C.POINTER(YpWgradDesc), _vp]),
     "yp_bn_act_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _vp]),
     "yp_bn_act_bwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -117,7 +126,7 @@ def lib(require_device: bool = False):
                     except AttributeError as e:  # pragma: no cover
                         raise YoloPointB200Error(f"{LIB_PATH} does not export {name}") from e
                     fn.restype, fn.argtypes = res, args
-                if handle.yp_abi_version() != 6:
+                if handle.yp_abi_version() != 7:
                     raise YoloPointB200Error("ABI version mismatch between _lib.py and libyolopoint_b200.so")
                 _lib = handle
     if require_device:

@@ -30,6 +30,11 @@ int sm_count() {
 int conv_tc_forward(const YpConvDesc& d, cudaStream_t st);
 size_t conv_tc_workspace_bytes(const YpConvDesc& d);
 int conv_tc_plan_check(const YpConvDesc& d);
+int conv_chain_create(const YpChainOp* ops, int n_ops, void** out);
+int conv_chain_launch(void* chain, cudaStream_t st);
+int conv_chain_destroy(void* chain);
+int conv_chain_info(void* chain, int* n_kernels, int* n_items, int* smem);
+int conv_chain_debug(void* chain, int k, void** dbg, int* n_ops, int* n_ctas);
 int conv_simt_forward(const YpConvDesc& d, cudaStream_t st);
 void set_conv_timeline(long long* p);
 int wgrad_tc(const YpWgradDesc& d, cudaStream_t st);
@@ -77,6 +82,32 @@ extern "C" int yp_conv2d_plan_check(const YpConvDesc* d) {
   YP_REQUIRE(d, YP_ERR_ARG, "conv: null descriptor");
   YP_REQUIRE(d->algo == YP_ALGO_TCGEN05, YP_ERR_ARG, "conv: plan check is defined for the tcgen05 algorithm only (algo %d)", d->algo);
   return yp::conv_tc_plan_check(*d);
+}
+
+extern "C" int yp_conv_chain_create(const YpChainOp* ops, int32_t n_ops, void** chain) {
+  YP_REQUIRE(ops && chain && n_ops >= 1, YP_ERR_ARG, "chain: null pointer or empty operation list");
+  *chain = nullptr;
+  return yp::conv_chain_create(ops, n_ops, chain);
+}
+
+extern "C" int yp_conv_chain_launch(void* chain, void* stream) {
+  YP_REQUIRE(chain, YP_ERR_ARG, "chain: null handle");
+  return yp::conv_chain_launch(chain, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int yp_conv_chain_destroy(void* chain) {
+  if (!chain) return YP_OK;
+  return yp::conv_chain_destroy(chain);
+}
+
+extern "C" int yp_conv_chain_info(void* chain, int32_t* n_kernels, int32_t* n_items, int32_t* smem_bytes) {
+  YP_REQUIRE(chain, YP_ERR_ARG, "chain: null handle");
+  return yp::conv_chain_info(chain, n_kernels, n_items, smem_bytes);
+}
+
+extern "C" int yp_debug_conv_chain_timeline(void* chain, int32_t kernel, void** device_buf_i64, int32_t* n_ops, int32_t* n_ctas) {
+  YP_REQUIRE(chain && device_buf_i64 && n_ops && n_ctas, YP_ERR_ARG, "chain: null pointer");
+  return yp::conv_chain_debug(chain, kernel, device_buf_i64, n_ops, n_ctas);
 }
 
 extern "C" int yp_conv2d_nhwc_wgrad(const YpWgradDesc* d, void* stream) {

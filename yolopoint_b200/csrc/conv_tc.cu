@@ -17,11 +17,14 @@
 // separate and loops over tiles with double-buffered TMEM accumulators.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "sppf.cuh"
 
 #include <cudaTypedefs.h>
 
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
+#include <vector>
 #include <stdlib.h>
 
 namespace yp {
@@ -68,7 +71,7 @@ struct ConvArgs {
   const int* n_cols;
   const void* res_base;
   long long res_pix, res_plane;
-  int n_out_maps, out_planes, out_row_bytes, staging_set_bytes;
+  int n_out_maps, out_planes, out_row_bytes, staging_set_bytes, out_fmt;
   int persist, n_tiles_n, tiles_total, stg_off, buf_cols;   // persistent variant: tiles per CTA loop, staging offset, TMEM columns per accumulator buffer
   int ablate;      // debug (YP_CONV_ABLATE): 1 = issue no MMAs, 2 = issue no TMA loads (timing experiments; results are garbage)
   long long* dbg;  // optional timeline buffer (yp_debug_conv_timeline); CTA (0,0) records clock64 stamps
@@ -105,28 +108,51 @@ __device__ __forceinline__ float silu_fast(float v) {
 // `n_small` (<= 2) more take the two cross terms (A_lo*W_hi, A_hi*W_lo), whose partial sums are ~2^-11 of the
 // result so that their truncation error is negligible.
 // ---------------------------------------------------------------------------------------------
-template <int OUT_FMT, int UNITS, bool kTf32, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+// Chain mode reads the layer's arguments from an element of an array in the kernel-parameter space (dynamic constant-bank index):
+// the compiler then re-loads loop-invariant fields inside the single-thread producer / issuer loops (LDC / LDCU + R2UR per
+// k-block) where the stand-alone kernel has immediate constant operands.  `held` pins such a value in a register before the loop.
+template <bool kHold>
+__device__ __forceinline__ uint32_t held(uint32_t v) {
+  if (kHold) asm volatile("" : "+r"(v));
+  return v;
+}
+
+// One work item = what one CTA of the stand-alone launch does (bx, by, bz = its blockIdx; gx, gy = the launch's grid.x / grid.y).
+// kChain: the item runs inside conv_chain_kernel (a persistent CTA walking the layers of a network segment): TMEM is allocated once
+// per CTA (chain_tmem), the mbarriers are re-initialised per item, there is no programmatic dependent launch, `dep_wait` blocks until
+// the layers this one reads from have completed, and the item ends with all of its global writes complete (the caller publishes the
+// layer's completion counter).
+template <int OUT_FMT, int UNITS, bool kTf32, int NT, bool kChain, class WaitFn>
+__device__ __forceinline__ void conv_tile(const ConvMaps& maps, const ConvArgs& a, const int bx, const int by, const int bz, const int gx, const int gy,
+                                          uint8_t* smem_raw, const uint32_t chain_tmem, const bool chain_first, WaitFn&& dep_wait,
+                                          long long* chain_dbg = nullptr, const int chain_variant = 0) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index as a warp-uniform value
   const int per_img = a.tiles_w * a.tiles_h;
-  const int b = blockIdx.x / per_img;
-  const int trem = blockIdx.x - b * per_img;
+  const int b = bx / per_img;
+  const int trem = bx - b * per_img;
   const int th = trem / a.tiles_w, tw = trem - th * a.tiles_w;
   const int h0 = th * a.Ht, w0 = tw * a.Wt;
-  const int n0 = blockIdx.y * a.Nt;
+  const int n0 = by * a.Nt;
   const int num_kb_all = a.patch ? a.kb_per_tap : a.n_taps * a.kb_per_tap;   // K-loop units (patch mode: channel blocks)
-  const int kb0 = blockIdx.z * a.kb_per_split;                       // this CTA's slice of the K loop (split-K)
+  const int kb0 = bz * a.kb_per_split;                       // this CTA's slice of the K loop (split-K)
   const int num_kb = min(num_kb_all, kb0 + a.kb_per_split) - kb0;
-  long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
-  auto stamp = [&](int slot) { if (dbg) dbg[slot] = clock64(); };   // callers restrict it to one lane
+  long long* dbg = kChain ? chain_dbg : ((a.dbg && bx == 0 && by == 0 && bz == 0) ? a.dbg : nullptr);
+  auto stamp = [&](int slot) {   // callers restrict it to one lane; chain mode: 8 slots per item, nanoseconds
+    if (!dbg) return;
+    if (kChain) {   // 8 first TMA issued, 9 first operands landed, 10 first k-block issued, 11 all MMAs issued
+      const int idx = slot < 6 ? slot : (slot == 8 ? 8 : (slot == 104 ? 9 : (slot == 200 ? 10 : (slot == 400 ? 11 : -1))));
+      if (idx >= 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[idx] = static_cast<long long>(t); }
+    } else {
+      dbg[slot] = clock64();
+    }
+  };
   if (threadIdx.x == 0) stamp(0);
   // whole-grid occupancy picture: every CTA records (SM id, start, end) in nanoseconds at dbg[512 + 3 * linear CTA index]
-  const long long cta_lin = (static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  if (a.dbg && threadIdx.x == 0 && cta_lin < 20000) {
+  const long long cta_lin = (static_cast<long long>(bz) * gy + by) * gx + bx;
+  if (!kChain && a.dbg && threadIdx.x == 0 && cta_lin < 20000) {
     unsigned smid; unsigned long long t;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -134,7 +160,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   }
   // Programmatic dependent launch: let the next kernel of the stream start its prologue (barrier init, TMEM allocation,
   // descriptor prefetch) now; it blocks in griddepcontrol.wait until this grid has completed and flushed.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!kChain) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // barriers + tmem slot + bias live after the pipeline/staging region
   const uint32_t bar_base = smem_base + a.bar_off;
@@ -152,18 +178,23 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
     for (int i = 0; i < n_in; ++i) tma_prefetch_desc(&maps.in[i]);
     tma_prefetch_desc(&maps.w);
     for (int i = 0; i < a.n_out_maps; ++i) tma_prefetch_desc(&maps.out[i]);
+    if (kChain && !chain_first) {   // the previous item's barriers: every arrival on them has happened (see the end of the item)
+      for (int s = 0; s < 2 * kMaxStages + 1; ++s) mbar_inval(bar_base + 8u * s);
+      for (int s = 0; s < 4; ++s) mbar_inval(bar_base + 8u * (2 * kMaxStages + 2 + s));
+    }
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), a.n_iss); }
     for (int s = 0; s < 2; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), a.n_iss); }
     mbar_init(accum_bar, a.n_iss);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (!kChain && warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (kChain) dep_wait();   // one thread spins on the completion counters of the producer layers (under the barrier set-up of the others)
   for (int i = threadIdx.x; i < a.Nt; i += NT) bias_s[i] = a.bias ? a.bias[n0 + i] : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  uint32_t tmem_base = chain_tmem;
+  if (!kChain) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);   // same value in every lane: lets the compiler keep MMA operands in uniform registers
   if (threadIdx.x == 0) stamp(1);
   if (a.ablate != 6) {   // 6 = launch + prologue only (timing experiment)
@@ -171,11 +202,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   // ---- epilogue geometry of this thread (needed before the roles start: the residual of the thread's first unit is fetched NOW,
   // under the main loop -- it cost 0.4-0.8 us of exposed latency in front of the first epilogue barrier, longest for the producer /
   // issuer warps, which only reach the epilogue when their loops are done).  Unit u = columns [16 u, 16 u + 16); first unit = hf.
-  using TO = typename OutT<OUT_FMT>::type;
-  constexpr int CH = 16 * UNITS;                 // elements per staging row
-  constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
   constexpr int NG = NT / 128;                   // warp groups (2 or 4)
-  constexpr int G = NG > UNITS ? NG / UNITS : 1; // staging chunks worked on at the same time (every warp group has a unit)
   const int q = warp & 3;                        // TMEM lane quarter this warp may access
   const int hf = warp >> 2;                      // warp group
   const int row = q * 32 + lane;               // accumulator row (TMEM lane) of this thread
@@ -187,7 +214,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   const int srow = in_tile ? rh * a.Wt + rw : 127;   // row of the (compact Ht x Wt) staging tile this thread fills
   const bool et0 = (threadIdx.x == 64);
   const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-  const int n_chunks = a.Nt / CH;
   const bool has_res = a.res_base != nullptr && valid;
   const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
 
@@ -197,15 +223,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   // instruction fetch (ncu source view, stall_no_inst).
   constexpr int PU = 1;                          // 16-column units per pass
   constexpr int PE = 16 * PU;                    // columns per pass
-  constexpr int NP = UNITS / PU;                 // passes per chunk
-  // residual of columns [col0, col0 + PE) for this thread's pixel, planes summed (residual format == output format family)
-  auto load_res = [&](int col0, float* r) {
+  // residual of columns [col0, col0 + PE) for this thread's pixel, planes summed (residual format == output format family `fmt`:
+  // a compile-time constant in the stand-alone kernel, the layer's a.out_fmt for the early fetch of a chained item)
+  auto load_res = [&](int fmt, int col0, float* r) {
     if (!has_res) {
 #pragma unroll
       for (int i = 0; i < PE; ++i) r[i] = 0.0f;
       return;
     }
-    if (OUT_FMT == YP_FMT_BF16) {
+    if (fmt == YP_FMT_BF16) {
       const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_base) + res_off + col0);
 #pragma unroll
       for (int j = 0; j < PE / 8; ++j) {
@@ -221,7 +247,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
       for (int j = 0; j < PE / 4; ++j) {
         const float4 hi = __ldg(p + j);
         float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (OUT_FMT == YP_FMT_F32X2) lo = __ldg(pl + j);
+        if (fmt == YP_FMT_F32X2) lo = __ldg(pl + j);
         r[j * 4] = hi.x + lo.x; r[j * 4 + 1] = hi.y + lo.y; r[j * 4 + 2] = hi.z + lo.z; r[j * 4 + 3] = hi.w + lo.w;
       }
     }
@@ -229,65 +255,69 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   float res[PE];
   const bool res_pre = hf * 16 < a.Nt && a.split_k == 1 && !a.rowmin && !a.l2norm;
   if (res_pre) {
-    if (a.res_base) asm volatile("griddepcontrol.wait;" ::: "memory");   // the residual may be the previous kernel's output
-    load_res(hf * 16, res);
+    if (!kChain && a.res_base) asm volatile("griddepcontrol.wait;" ::: "memory");   // the residual may be the previous kernel's output
+    load_res(kChain ? a.out_fmt : OUT_FMT, hf * 16, res);
   }
 
   if (warp == 0 && elect_one()) {
     // ===================== TMA producer (one elected lane runs the whole loop) =====================
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
+    if (!kChain) asm volatile("griddepcontrol.wait;" ::: "memory");   // inputs are written by the previous kernel(s) of the stream
     const bool load = a.ablate != 2;
+    const uint32_t p_a_stage = held<kChain>(a.a_stage_bytes), p_a_tx = held<kChain>(a.a_tx), p_ck = held<kChain>(a.ck_elems), p_b_tx = held<kChain>(a.b_tx);
+    const uint32_t p_b_ring = held<kChain>(a.b_ring_off), p_b_stage = held<kChain>(a.b_stage_bytes), p_kbt = held<kChain>(a.kb_per_tap);
+    const uint32_t p_b_stages = held<kChain>(a.b_stages), p_plane_off = held<kChain>(a.a_plane_off), p_two = held<kChain>(a.in_planes == 2 && !a.a_split);
+    const uint32_t p_stage = held<kChain>(a.stage_bytes), p_tx = held<kChain>(a.tx_bytes), p_stages = held<kChain>(a.stages), p_ks = held<kChain>(a.ksize), p_st = held<kChain>(a.stride);
     if (a.patch) {
       // K order = (channel block, tap): one patch load per channel block, nine weight tiles streamed through the B ring
       int sa = 0, pha = 0, sb = 0, phb = 0;
       for (int cbi = 0; cbi < num_kb; ++cbi) {
         const int cb = kb0 + cbi;
         mbar_wait(aempty_bar(sa), pha ^ 1);
-        const uint32_t sta = smem_base + sa * a.a_stage_bytes;
+        const uint32_t sta = smem_base + sa * p_a_stage;
         {
-          mbar_expect_tx(afull_bar(sa), load ? a.a_tx : 0);
+          mbar_expect_tx(afull_bar(sa), load ? p_a_tx : 0);
           if (load) {
-            tma_load_5d(sta, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 0);
-            if (a.in_planes == 2 && !a.a_split) tma_load_5d(sta + a.a_plane_off, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 1);
+            tma_load_5d(sta, &maps.in[0], afull_bar(sa), cb * p_ck, w0 - 1, h0 - 1, b, 0);
+            if (p_two) tma_load_5d(sta + p_plane_off, &maps.in[0], afull_bar(sa), cb * p_ck, w0 - 1, h0 - 1, b, 1);
           }
           if (cbi < 96) stamp(8 + cbi);
         }
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(empty_bar(sb), phb ^ 1);
           {
-            mbar_expect_tx(full_bar(sb), load ? a.b_tx : 0);
-            if (load) tma_load_3d(smem_base + a.b_ring_off + sb * a.b_stage_bytes, &maps.w, full_bar(sb), (tap * a.kb_per_tap + cb) * a.ck_elems, n0, 0);
+            mbar_expect_tx(full_bar(sb), load ? p_b_tx : 0);
+            if (load) tma_load_3d(smem_base + p_b_ring + sb * p_b_stage, &maps.w, full_bar(sb), (tap * p_kbt + cb) * p_ck, n0, 0);
           }
-          if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+          if (++sb == static_cast<int>(p_b_stages)) { sb = 0; phb ^= 1; }
         }
         if (++sa == 2) { sa = 0; pha ^= 1; }
       }
     } else {
       int s = 0, ph = 0, tap = kb0 / a.kb_per_tap, cb = kb0 - tap * a.kb_per_tap;
-      const uint32_t b_off = a.a_region_bytes;
+      const uint32_t b_off = held<kChain>(a.a_region_bytes);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1);
         int map = 0, dh = 0, dw = 0;
-        if (a.ksize == 3) {
+        if (p_ks == 3) {
           const int kh = tap / 3, kw = tap - kh * 3;
-          if (a.stride == 1) { dh = kh - 1; dw = kw - 1; }
+          if (p_st == 1) { dh = kh - 1; dw = kw - 1; }
           else { map = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1); dh = (kh == 0) ? -1 : 0; dw = (kw == 0) ? -1 : 0; }
-        } else if (a.ksize == 0) {
+        } else if (p_ks == 0) {
           dh = static_cast<int>((a.tap_dh >> (4 * tap)) & 15ull) - 8;
           dw = static_cast<int>((a.tap_dw >> (4 * tap)) & 15ull) - 8;
         }
-        const uint32_t st = smem_base + s * a.stage_bytes;
+        const uint32_t st = smem_base + s * p_stage;
         {
-          mbar_expect_tx(full_bar(s), load ? a.tx_bytes : 0);
+          mbar_expect_tx(full_bar(s), load ? p_tx : 0);
           if (load) {
-            tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
-            if (a.in_planes == 2 && !a.a_split) tma_load_5d(st + a.a_plane_off, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 1);
-            tma_load_3d(st + b_off, &maps.w, full_bar(s), (kb0 + kb) * a.ck_elems, n0, 0);   // box covers both weight planes
+            tma_load_5d(st, &maps.in[map], full_bar(s), cb * p_ck, w0 + dw, h0 + dh, b, 0);
+            if (p_two) tma_load_5d(st + p_plane_off, &maps.in[map], full_bar(s), cb * p_ck, w0 + dw, h0 + dh, b, 1);
+            tma_load_3d(st + b_off, &maps.w, full_bar(s), (kb0 + kb) * p_ck, n0, 0);   // box covers both weight planes
           }
           if (kb < 96) stamp(8 + kb);
         }
-        if (++cb == a.kb_per_tap) { cb = 0; ++tap; }
-        if (++s == a.stages) { s = 0; ph ^= 1; }
+        if (++cb == static_cast<int>(p_kbt)) { cb = 0; ++tap; }
+        if (++s == static_cast<int>(p_stages)) { s = 0; ph ^= 1; }
       }
     }
   }
@@ -305,18 +335,22 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
   // ~450 cycles of issue overhead per MMA, several times the 64-128 cycles the MMA occupies the tensor pipe.
   if (warp >= 1 && warp - 1 < a.n_iss && elect_one()) {   // ONE lane runs the whole issue loop (see umma32_one)
     const int q = warp - 1;
-    const int ksteps = a.ck_bytes / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
-    const uint32_t b_plane = a.Nt * a.ck_bytes;
-    const int cnt = a.iss_cnt[q];
-    const uint32_t col0 = tmem_base + a.iss_col[q], cstride = a.iss_stride[q], idesc = a.iss_idesc[q];
-    const int kstart = a.kstart[q], kinc = a.kinc[q];
-    const uint32_t a_off0 = a.job_a[q][0] * a.a_plane_off, b_off0 = a.job_b[q][0] * b_plane;
-    const uint32_t a_off1 = a.job_a[q][1] * a.a_plane_off, b_off1 = a.job_b[q][1] * b_plane;
-    const bool two = a.n_jobs[q] == 2;
-    const uint32_t dhi = smem_desc_hi(a.ck_bytes);
+    const uint32_t i_ck = held<kChain>(a.ck_bytes);
+    const int ksteps = i_ck / 32;  // one UMMA consumes 32 bytes of K per row (8 tf32 / 16 bf16)
+    const uint32_t b_plane = a.Nt * i_ck;
+    const int cnt = held<kChain>(a.iss_cnt[q]);
+    const uint32_t col0 = held<kChain>(tmem_base + a.iss_col[q]), cstride = held<kChain>(a.iss_stride[q]), idesc = held<kChain>(a.iss_idesc[q]);
+    const int kstart = held<kChain>(a.kstart[q]), kinc = held<kChain>(a.kinc[q]);
+    const uint32_t a_off0 = held<kChain>(a.job_a[q][0] * a.a_plane_off), b_off0 = held<kChain>(a.job_b[q][0] * b_plane);
+    const uint32_t a_off1 = held<kChain>(a.job_a[q][1] * a.a_plane_off), b_off1 = held<kChain>(a.job_b[q][1] * b_plane);
+    const bool two = held<kChain>(a.n_jobs[q] == 2) != 0;
+    const uint32_t dhi = held<kChain>(smem_desc_hi(i_ck));
+    const uint32_t i_a_stage = held<kChain>(a.a_stage_bytes), i_b_ring = held<kChain>(a.b_ring_off), i_b_stage = held<kChain>(a.b_stage_bytes);
+    const int i_b_stages = held<kChain>(a.b_stages), i_stages = held<kChain>(a.stages);
+    const uint32_t i_row_step = held<kChain>((a.Wp - 2) * i_ck), i_stage = held<kChain>(a.stage_bytes), i_a_region = held<kChain>(a.a_region_bytes);
     const bool live = a.ablate != 1;
-    const bool fast4 = live && ksteps == 4 && kinc == 1 && !two && a.ablate != 8;   // YP_CONV_ABLATE=8: generic loop (A/B runs)
-    const bool fast2 = live && ksteps == 4 && kinc == 2 && !two && a.ablate != 8;   // two issuers share a stream: every other k-step
+    const bool fast4 = held<kChain>(live && ksteps == 4 && kinc == 1 && !two && a.ablate != 8) != 0;   // YP_CONV_ABLATE=8: generic loop (A/B runs)
+    const bool fast2 = held<kChain>(live && ksteps == 4 && kinc == 2 && !two && a.ablate != 8) != 0;   // two issuers share a stream: every other k-step
     uint32_t used = 0;                   // bit r set = accumulator r of this issuer already holds a partial sum
     int s = 0, ph = 0, nxt = 0;
     if (a.patch) {
@@ -325,12 +359,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
         mbar_wait(afull_bar(sa), pha);
         tc_fence_after();
         if (q == 0 && cbi < 96) stamp(104 + cbi);
-        const uint32_t pa = smem_base + sa * a.a_stage_bytes;
+        const uint32_t pa = smem_base + sa * i_a_stage;
         uint32_t shift = 0;               // byte offset of the tap's window inside the patch: (kh * Wp + kw) rows
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sb = smem_base + a.b_ring_off + s * a.b_stage_bytes;
+          const uint32_t sb = smem_base + i_b_ring + s * i_b_stage;
           uint32_t al0 = smem_desc_lo(pa + a_off0 + shift) + 2 * kstart, bl0 = smem_desc_lo(sb + b_off0) + 2 * kstart;
           uint32_t al1 = smem_desc_lo(pa + a_off1 + shift) + 2 * kstart, bl1 = smem_desc_lo(sb + b_off1) + 2 * kstart;
           if (fast4) {
@@ -358,8 +392,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
             al0 += 2 * kinc; bl0 += 2 * kinc; al1 += 2 * kinc; bl1 += 2 * kinc;
           }
           umma_commit(empty_bar(s));
-          if (++s == a.b_stages) { s = 0; ph ^= 1; }
-          shift += (tap % 3 == 2) ? (a.Wp - 2) * a.ck_bytes : a.ck_bytes;
+          if (++s == i_b_stages) { s = 0; ph ^= 1; }
+          shift += (tap % 3 == 2) ? i_row_step : i_ck;
         }
         umma_commit(aempty_bar(sa));
         if (q == 0 && cbi < 96) stamp(200 + cbi);
@@ -370,8 +404,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         if (q == 0 && kb < 96) stamp(104 + kb);
-        const uint32_t sa = smem_base + s * a.stage_bytes;
-        const uint32_t sb = sa + a.a_region_bytes;
+        const uint32_t sa = smem_base + s * i_stage;
+        const uint32_t sb = sa + i_a_region;
         uint32_t al0 = smem_desc_lo(sa + a_off0) + 2 * kstart, bl0 = smem_desc_lo(sb + b_off0) + 2 * kstart;
         uint32_t al1 = smem_desc_lo(sa + a_off1) + 2 * kstart, bl1 = smem_desc_lo(sb + b_off1) + 2 * kstart;
         if (fast4) {
@@ -398,13 +432,25 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
         }
         umma_commit(empty_bar(s));  // one arrival per issuer: the stage is free when all their MMAs have retired
         if (q == 0 && kb < 96) stamp(200 + kb);
-        if (++s == a.stages) { s = 0; ph ^= 1; }
+        if (++s == i_stages) { s = 0; ph ^= 1; }
       }
     }
     umma_commit(accum_bar);
+    if (kChain && q == 0) stamp(400);
   }
   __syncwarp();
-  {
+  // The epilogue is the only part that depends on the output format / store-chunk width: a generic lambda, instantiated once by the
+  // stand-alone kernel (its template arguments) and once per (format, units) combination by a chained item, which selects it at run
+  // time -- the chain kernel then carries ONE copy of the set-up / producer / issuer code (instruction-cache footprint).
+  auto epilogue = [&](auto fmt_tag, auto units_tag) {
+    constexpr int OUT_FMT_ = decltype(fmt_tag)::value;
+    constexpr int UNITS_ = decltype(units_tag)::value;
+    using TO = typename OutT<OUT_FMT_>::type;
+    constexpr int CH = 16 * UNITS_;                // elements per staging row
+    constexpr int ROWB = CH * (int)sizeof(TO);     // bytes per staging row (128 / 64 / 32)
+    constexpr int G = NG > UNITS_ ? NG / UNITS_ : 1; // staging chunks worked on at the same time (every warp group has a unit)
+    constexpr int NP = UNITS_ / PU;                // passes per chunk
+    const int n_chunks = a.Nt / CH;
     // ===================== epilogue =====================
     // All warps take part (the producer and issuer warps join when their loops are done): NG = NT / 128 warps per TMEM lane
     // quarter, which split the 16-column units of the tile between them (warp group hf takes the units u with u % NG == hf).
@@ -432,8 +478,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
       tmem_ld_wait();
     };
     const int S = a.split_k;
-    const long long tile_id = static_cast<long long>(blockIdx.x) * gridDim.y + blockIdx.y;
-    const long long n_tiles_all = static_cast<long long>(gridDim.x) * gridDim.y;
+    const long long tile_id = static_cast<long long>(bx) * gy + by;
+    const long long n_tiles_all = static_cast<long long>(gx) * gy;
     // split-K: partial sums of the S CTAs of a tile, read back in fixed order z = 0..S-1 (deterministic)
     auto load_acc16 = [&](int col, float* v) {
       if (S == 1) { tmem_acc16(col, v); return; }
@@ -462,7 +508,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
       return v + res;
     };
 
-    asm volatile("griddepcontrol.wait;" ::: "memory");     // residual / split-K workspace may be the previous kernel's output
+    if (!kChain) asm volatile("griddepcontrol.wait;" ::: "memory");     // residual / split-K workspace may be the previous kernel's output
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (et0) stamp(2);
@@ -470,7 +516,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
     bool run_epilogue = a.ablate != 7;   // 7 = main loop only (timing experiment)
     if (S > 1 && a.ablate != 7) {
       // publish this CTA's partial tile, then the last CTA to arrive (per tile) reduces all of them and finishes
-      float* mine = a.ws_partial + ((blockIdx.z * n_tiles_all + tile_id) * 128 + row) * a.Nt;
+      float* mine = a.ws_partial + ((bz * n_tiles_all + tile_id) * 128 + row) * a.Nt;
       for (int u = hf; u < a.Nt / 16; u += NG) {
         float v[16];
         tmem_acc16(u * 16, v);
@@ -492,7 +538,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
     if (run_epilogue && a.rowmin) {
       // descriptor matching: key(i, j) = bits(sqrt(2 - 2 clip(<d1_i, d2_j>))) << 32 | j, integer MIN over this tile's columns
       const int n_rows = a.n_rows ? min(*a.n_rows, a.Wo) : a.Wo;
-      const int n_cols = a.n_cols ? *a.n_cols : (int)(gridDim.y * a.Nt);
+      const int n_cols = a.n_cols ? *a.n_cols : (int)(gy * a.Nt);
       unsigned long long best = ~0ull;
       for (int u = hf; u < a.Nt / 16; u += NG) {
         float v[16];
@@ -537,7 +583,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
       const uint32_t stg = smem_base + (set0 + gi) * a.staging_set_bytes;
       float v[PE];
       const int col0 = c * CH + ps * PE;
-      if (!(res_pre && col0 == hf * 16)) load_res(col0, res);
+      if (!(res_pre && col0 == hf * 16)) load_res(OUT_FMT_, col0, res);
       if (et0 && c == 0 && ps == 0) stamp(321);
       if (a.ablate != 3) load_acc16(col0, v);
       if (et0 && c == 0 && ps == 0) stamp(322);
@@ -553,7 +599,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
       const int j0 = ps * VP;
       if (!in_tile || a.ablate == 4) {
         // halo / padding row: nothing to stage
-      } else if (OUT_FMT == YP_FMT_F32X2) {
+      } else if (OUT_FMT_ == YP_FMT_F32X2) {
 #pragma unroll
         for (int j = 0; j < VP; ++j) {
           float hi[4], lo[4];
@@ -562,7 +608,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j0 + j, ROWB)), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg + 128 * ROWB, srow, j0 + j, ROWB)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
         }
-      } else if (OUT_FMT == YP_FMT_F32) {
+      } else if (OUT_FMT_ == YP_FMT_F32) {
 #pragma unroll
         for (int j = 0; j < VP; ++j)
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, j0 + j, ROWB)), "f"(v[j * 4]), "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
@@ -592,21 +638,41 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __
         if (cg < 8) stamp(302 + 4 * cg);
       }
     }
-    if (et0) { tma_store_wait_read<0>(); stamp(3); }
+    if (et0) {
+      if (kChain) tma_store_wait_all();   // the stores have been written, not only read out of the staging buffers
+      else tma_store_wait_read<0>();
+      stamp(3);
+    }
     }  // run_epilogue
+  };
+  if constexpr (kChain) {
+    switch (chain_variant) {
+      case 0: epilogue(std::integral_constant<int, YP_FMT_F32X2>{}, std::integral_constant<int, 2>{}); break;
+      case 1: epilogue(std::integral_constant<int, YP_FMT_F32X2>{}, std::integral_constant<int, 1>{}); break;
+      case 2: epilogue(std::integral_constant<int, YP_FMT_F32>{}, std::integral_constant<int, 2>{}); break;
+      default: epilogue(std::integral_constant<int, YP_FMT_F32>{}, std::integral_constant<int, 1>{}); break;
+    }
+  } else {
+    epilogue(std::integral_constant<int, OUT_FMT>{}, std::integral_constant<int, UNITS>{});
   }
 
   }  // ablate != 6
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) stamp(4);
-  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (!kChain && warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
   if (threadIdx.x == 32) stamp(5);
-  if (a.dbg && threadIdx.x == 0 && cta_lin < 20000) {
+  if (!kChain && a.dbg && threadIdx.x == 0 && cta_lin < 20000) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     a.dbg[514 + 3 * cta_lin] = static_cast<long long>(t);
   }
+}
+
+template <int OUT_FMT, int UNITS, bool kTf32, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  conv_tile<OUT_FMT, UNITS, kTf32, NT, false>(maps, a, blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, smem_raw, 0u, true, [] {});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -899,6 +965,106 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Layer chain: one persistent kernel for a segment of the network (yp_conv_chain_*, see the header).  Batch-1 inference is a chain
+// of ~60 small dependent layers; launched one by one each pays launch latency, TMEM allocation, descriptor prefetch and the
+// grid-completion gap, and the GPU idles while the slowest CTA of a layer finishes.  Here one CTA per SM walks the operations in
+// order; item i of operation l runs on CTA (cta_off_l + i) mod #CTAs exactly as conv_tile() would run it as a CTA of its own launch.
+// Ordering between operations: done[l] counts the completed items of operation l (red.release.gpu after the item's stores have
+// completed); an item first waits (ld.acquire.gpu, one thread, under the barrier set-up of the others) until every operation in its
+// dependency list has reached its item count, then fences the async proxy (the data arrive through TMA).  Deadlock freedom: every
+// CTA processes its items in list order, the list is a valid sequential order and all CTAs are co-resident (cooperative launch,
+// grid = #SMs, one CTA per SM).  The last CTA to leave the kernel resets the counters for the next launch.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxChain = 40;      // operations per kernel (bounded by the 32 KB kernel-parameter space)
+constexpr int kMaxChainDeps = 6;
+
+struct ChainMeta {
+  int type;                        // 0 = convolution, 1 = SPPF pooling
+  int variant;                     // convolution: epilogue instantiation; pooling: index into ChainParams::pool
+  int gx, gy, n_items, cta_off;
+  int n_deps;
+  int dep[kMaxChainDeps], dep_target[kMaxChainDeps];
+};
+struct ChainPool { YpView cat4; int C; int groups; };
+struct ChainParams {
+  int n_ops;
+  long long* dbg;                  // optional per-item timeline (YP_CHAIN_DEBUG): [n_ops][#CTAs][16] globaltimer stamps
+  ChainMeta meta[kMaxChain];
+  ConvArgs args[kMaxChain];
+  ChainPool pool[2];
+};
+static_assert(sizeof(ChainParams) <= 32000, "ChainParams exceeds the kernel parameter space");
+
+__device__ __forceinline__ void chain_spin(const unsigned* p, unsigned target) {
+  unsigned v;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= target) break;
+    if (clock64() - t0 > 4000000000LL) mbar_timeout_trap();
+  }
+}
+
+template <bool kTf32, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) conv_chain_kernel(const __grid_constant__ ChainParams P, const ConvMaps* __restrict__ maps, unsigned* done) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_slot_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot_s;
+  const int G = gridDim.x;
+  bool first = true;
+  for (int l = 0; l < P.n_ops; ++l) {
+    const ChainMeta& m = P.meta[l];
+    int it = static_cast<int>(blockIdx.x) - m.cta_off;
+    if (it < 0) it += G;
+    for (; it < m.n_items; it += G) {
+      long long* idbg = P.dbg ? P.dbg + (static_cast<long long>(l) * G + blockIdx.x) * 16 : nullptr;
+      auto gstamp = [&](int slot) { if (idbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); idbg[slot] = static_cast<long long>(t); } };
+      auto dep_wait = [&] {
+        if (threadIdx.x == 64) {
+          for (int k = 0; k < m.n_deps; ++k) chain_spin(done + m.dep[k], static_cast<unsigned>(m.dep_target[k]));
+          asm volatile("fence.proxy.async;" ::: "memory");   // the producers wrote through TMA; this CTA reads through TMA
+          gstamp(6);
+        }
+      };
+      if (m.type == 0) {
+        const ConvArgs& a = P.args[l];
+        const int bx = it % m.gx, t2 = it / m.gx, by = t2 % m.gy, bz = t2 / m.gy;
+        conv_tile<YP_FMT_F32X2, 2, kTf32, NT, true>(maps[l], a, bx, by, bz, m.gx, m.gy, smem_raw, tmem_base, first, dep_wait, idbg, m.variant);
+        first = false;
+      } else {
+        const ChainPool& pp = P.pool[m.variant];
+        dep_wait();
+        __syncthreads();
+        sppf_pool_item(pp.cat4, pp.C, it % pp.groups, it / pp.groups, smem_raw);   // ends with __syncthreads()
+      }
+      // every global write of the item has been performed (TMA stores: wait_group 0 by their issuing thread before the item's last
+      // barrier; generic stores of the other threads: ordered before this release by that barrier)
+      if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done + l) : "memory");
+        gstamp(7);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(done + kMaxChain, 1u);
+    if (old == static_cast<unsigned>(G - 1)) {   // every CTA has finished all of its items: nobody reads the counters any more
+      for (int l = 0; l <= kMaxChain; ++l) done[l] = 0;
+      __threadfence();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
 long long* g_timeline = nullptr;
@@ -1028,6 +1194,11 @@ void pick_patch_padded(int Ho, int Wo, int* Ht, int* Wt) {
 
 namespace {
 
+// > 0 while plan_conv() plans an operation of a layer chain (conv_chain_kernel): shared-memory budget in bytes for the pipeline /
+// staging region; the plan is then the one-CTA-per-SM kind (up to 512 TMEM columns, no persistent variant, kChainThreads threads).
+thread_local int g_chain_budget = 0;
+constexpr int kChainThreads = 256;
+
 struct ConvPlan {
   ConvArgs a;
   dim3 grid;
@@ -1101,6 +1272,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
              "conv: output format %d incompatible with input format %d", out_fmt, in_fmt);
   const int oes = fmt_esize(out_fmt);
   a.out_planes = fmt_planes(out_fmt);
+  a.out_fmt = out_fmt;
   const int cout_bytes = d.cout * oes;
   a.out_row_bytes = cout_bytes % 128 == 0 ? 128 : (cout_bytes % 64 == 0 ? 64 : 32);
   const int chunk_elems = a.out_row_bytes / oes;
@@ -1161,9 +1333,10 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   // Several waves of tiles in bf16: the persistent kernel (one CTA per SM, double-buffered TMEM accumulators) instead of two
   // independent CTAs per SM.  YP_CONV_PERSIST=0 switches it off.
   static const bool allow_persist = getenv("YP_CONV_PERSIST") == nullptr || atoi(getenv("YP_CONV_PERSIST")) != 0;
-  const bool persist = allow_persist && !tf32 && S == 1 && !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && out_fmt != YP_FMT_F32X2 &&
+  const bool chain = g_chain_budget > 0;
+  const bool persist = allow_persist && !chain && !tf32 && S == 1 && !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && out_fmt != YP_FMT_F32X2 &&
                        static_cast<long long>(m_tiles) * n_tiles > (getenv("YP_CONV_PERSIST_MIN") ? atoll(getenv("YP_CONV_PERSIST_MIN")) : 2LL * nsm);
-  const bool dense = (allow_dense && static_cast<long long>(m_tiles) * n_tiles * S > nsm) || persist;   // persist: 256 columns per accumulator buffer
+  const bool dense = !chain && ((allow_dense && static_cast<long long>(m_tiles) * n_tiles * S > nsm) || persist);   // persist: 256 columns per accumulator buffer
   const int tmem_limit = dense ? 256 : 512;
 
   // ---- accumulator / issuer plan (see the kernel comment)
@@ -1252,7 +1425,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   a.stage_bytes = a.a_region_bytes + b_region_bytes;
   // TMA counts the bytes of the boxes actually written: Ht*Wt (<= 128) rows per A plane, Nt rows per B plane
   a.tx_bytes = a.in_planes * (rows * a.ck_bytes + Nt * a.ck_bytes);
-  int budget = persist ? 198 * 1024 - 2 * a.staging_set_bytes : (dense ? 104 * 1024 : 200 * 1024);
+  int budget = chain ? g_chain_budget : (persist ? 198 * 1024 - 2 * a.staging_set_bytes : (dense ? 104 * 1024 : 200 * 1024));
   int region = 0;
   if (a.patch) {
     a.a_stage_bytes = a.in_planes * rows_alloc * a.ck_bytes;
@@ -1282,7 +1455,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   // whole register file of its SM, so the next layer's CTAs can no longer start under this layer's tail (programmatic dependent launch).
   // Off unless YP_CONV_WIDE=1.
   static const bool allow_wide = getenv("YP_CONV_WIDE") != nullptr && atoi(getenv("YP_CONV_WIDE")) != 0;
-  P->nt = (allow_wide && !dense && !persist) ? 512 : 256;
+  P->nt = chain ? kChainThreads : ((allow_wide && !dense && !persist) ? 512 : 256);
   const int n_groups = P->nt / 128;
   const int staging_sets = 2 * (n_groups > P->units ? n_groups / P->units : 1);
   if (persist) {
@@ -1334,23 +1507,20 @@ int conv_tc_plan_check(const YpConvDesc& d) {
   return plan_conv(d, &P, true);
 }
 
-int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
-  YP_REQUIRE(get_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  ConvPlan P;
-  int rc = plan_conv(d, &P, d.workspace != nullptr);
-  if (rc != YP_OK) return rc;
-  if (P.ws_bytes > d.workspace_bytes) {   // workspace too small for the split the planner wants: run unsplit
-    if ((rc = plan_conv(d, &P, false)) != YP_OK) return rc;
-  }
+namespace {
+
+// Runtime half of a planned launch: pointers of the descriptor into the kernel arguments, tensor maps of the operand / destination
+// views.  `workspace` (split-K plans only): P.ws_bytes bytes, counters zero-initialised.
+int prepare_conv(const YpConvDesc& d, ConvPlan& P, void* workspace, ConvMaps& maps) {
+  int rc = YP_OK;
   ConvArgs& a = P.a;
   const YpView& in = d.in;
   const int Ho = a.Ho, Wo = a.Wo, Nt = a.Nt, out_fmt = P.out_fmt, chunk_elems = P.chunk_elems;
   if (a.split_k > 1) {
-    YP_REQUIRE(aligned16(d.workspace), YP_ERR_ALIGN, "conv: workspace not 16-byte aligned");
-    a.ws_counter = static_cast<int*>(d.workspace);
-    a.ws_partial = reinterpret_cast<float*>(static_cast<char*>(d.workspace) + P.ws_counter_bytes);
+    YP_REQUIRE(aligned16(workspace), YP_ERR_ALIGN, "conv: workspace not 16-byte aligned");
+    a.ws_counter = static_cast<int*>(workspace);
+    a.ws_partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + P.ws_counter_bytes);
   }
-  ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
 
   a.dbg = g_timeline;
@@ -1395,7 +1565,23 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
     }
   }
   a.n_out_maps = nm;
+  return YP_OK;
+}
 
+}  // namespace
+
+int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
+  YP_REQUIRE(get_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  ConvPlan P;
+  int rc = plan_conv(d, &P, d.workspace != nullptr);
+  if (rc != YP_OK) return rc;
+  if (P.ws_bytes > d.workspace_bytes) {   // workspace too small for the split the planner wants: run unsplit
+    if ((rc = plan_conv(d, &P, false)) != YP_OK) return rc;
+  }
+  ConvMaps maps;
+  if ((rc = prepare_conv(d, P, d.workspace, maps)) != YP_OK) return rc;
+  const ConvArgs& a = P.a;
+  const int out_fmt = P.out_fmt;
   const dim3 grid = P.grid;
   const size_t smem = P.smem;
   const int units = P.units;
@@ -1417,6 +1603,196 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
 #undef YP_DISPATCH
   set_error("conv: no kernel instantiation for out_fmt=%d units=%d", out_fmt, units);
   return YP_ERR_SHAPE;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layer chains (host side)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct ChainKernel {
+  ChainParams params;
+  ConvMaps* d_maps = nullptr;      // [n_ops]
+  unsigned* d_done = nullptr;      // [kMaxChain + 1] completion counters + exit counter
+};
+struct Chain {
+  std::vector<ChainKernel*> kernels;
+  std::vector<void*> allocs;
+  size_t smem = 0;
+  int n_items = 0, grid = 0, device = 0;
+  ~Chain() {
+    for (void* p : allocs) cudaFree(p);
+    for (ChainKernel* k : kernels) delete k;
+  }
+};
+
+int chain_variant(int out_fmt, int units) {
+  if (out_fmt == YP_FMT_F32X2) return units == 2 ? 0 : (units == 1 ? 1 : -1);
+  if (out_fmt == YP_FMT_F32) return units == 2 ? 2 : (units == 1 ? 3 : -1);
+  return -1;
+}
+
+int chain_build(const YpChainOp* ops, int n_ops, Chain* ch) {
+  YP_REQUIRE(get_encode() != nullptr, YP_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  YP_CUDA_OK(cudaGetDevice(&ch->device));
+  static const int budget_kb = getenv("YP_CHAIN_SMEM_KB") ? atoi(getenv("YP_CHAIN_SMEM_KB")) : 160;
+  const int G = sm_count();
+  ch->grid = G;
+  // ---- plan every operation (chain mode: one CTA per SM, common barrier offset)
+  std::vector<ConvPlan> plans(n_ops);
+  int bar_off = 0, max_nt = 16;
+  size_t ws_total = 0, pool_smem = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    const YpChainOp& op = ops[i];
+    YP_REQUIRE(op.n_deps >= 0 && op.n_deps <= 8, YP_ERR_ARG, "chain: op %d has %d dependencies", i, op.n_deps);
+    for (int k = 0; k < op.n_deps; ++k) YP_REQUIRE(op.deps[k] >= 0 && op.deps[k] < i, YP_ERR_ARG, "chain: op %d depends on op %d (not earlier in the list)", i, op.deps[k]);
+    if (op.type == 1) {
+      const YpView& v = op.pool;
+      YP_REQUIRE(v.base && v.C % 4 == 0 && (v.C / 4) % SPPF_G == 0 && v.H * v.W <= 65535, YP_ERR_SHAPE, "chain: op %d: SPPF view unsupported", i);
+      pool_smem = std::max(pool_smem, sppf_smem_bytes(v.H * v.W));
+      continue;
+    }
+    YP_REQUIRE(op.type == 0, YP_ERR_ARG, "chain: op %d has unknown type %d", i, op.type);
+    const YpConvDesc& d = op.conv;
+    YP_REQUIRE(d.in.base && d.weight && d.n_out >= 1 && d.out[0].base, YP_ERR_ARG, "chain: op %d: null pointer in descriptor", i);
+    YP_REQUIRE(d.algo == YP_ALGO_TCGEN05 && d.in.format == YP_FMT_F32X2 && !(d.epilogue & YP_EPI_ROWMIN), YP_ERR_SHAPE,
+               "chain: op %d: only tcgen05 convolutions with F32X2 operands can be chained", i);
+    g_chain_budget = budget_kb * 1024;
+    const int rc = plan_conv(d, &plans[i], true);
+    g_chain_budget = 0;
+    if (rc != YP_OK) return rc;
+    ConvPlan& P = plans[i];
+    YP_REQUIRE(chain_variant(P.out_fmt, P.units) >= 0, YP_ERR_SHAPE, "chain: op %d: no epilogue instantiation for out_fmt=%d units=%d", i, P.out_fmt, P.units);
+    bar_off = std::max(bar_off, P.a.bar_off);
+    max_nt = std::max(max_nt, P.a.Nt);
+    ws_total += (P.ws_bytes + 255) & ~static_cast<size_t>(255);
+  }
+  ch->smem = 1024 + bar_off + 8 * (2 * kMaxStages + 10) + max_nt * sizeof(float) + 16;
+  ch->smem = std::max(ch->smem, pool_smem + 16);
+  YP_REQUIRE(ch->smem <= 225 * 1024, YP_ERR_SHAPE, "chain: needs %zu bytes of shared memory", ch->smem);
+  char* ws = nullptr;
+  if (ws_total) {
+    YP_CUDA_OK(cudaMalloc(&ws, ws_total));
+    ch->allocs.push_back(ws);
+    YP_CUDA_OK(cudaMemset(ws, 0, ws_total));
+  }
+  // ---- kernels of <= kMaxChain operations
+  int cta_off = 0;
+  for (int k0 = 0; k0 < n_ops; k0 += kMaxChain) {
+    const int n = std::min(kMaxChain, n_ops - k0);
+    ChainKernel* K = new ChainKernel();
+    ch->kernels.push_back(K);
+    memset(&K->params, 0, sizeof(K->params));
+    K->params.n_ops = n;
+    if (getenv("YP_CHAIN_DEBUG")) {
+      const size_t bytes = static_cast<size_t>(n) * G * 16 * sizeof(long long);
+      YP_CUDA_OK(cudaMalloc(&K->params.dbg, bytes));
+      ch->allocs.push_back(K->params.dbg);
+      YP_CUDA_OK(cudaMemset(K->params.dbg, 0, bytes));
+    }
+    std::vector<ConvMaps> maps(n);
+    int n_pool = 0;
+    for (int j = 0; j < n; ++j) {
+      const int i = k0 + j;
+      const YpChainOp& op = ops[i];
+      ChainMeta& m = K->params.meta[j];
+      m.type = op.type;
+      if (op.type == 1) {
+        YP_REQUIRE(n_pool < 2, YP_ERR_SHAPE, "chain: more than two SPPF poolings in one kernel");
+        ChainPool& pp = K->params.pool[n_pool];
+        pp.cat4 = op.pool; pp.C = op.pool.C / 4; pp.groups = pp.C / SPPF_G;
+        m.variant = n_pool++;
+        m.gx = pp.groups; m.gy = op.pool.B;
+        m.n_items = pp.groups * op.pool.B;
+        memset(&maps[j], 0, sizeof(ConvMaps));
+      } else {
+        ConvPlan& P = plans[i];
+        P.a.bar_off = bar_off;
+        void* w = nullptr;
+        if (P.ws_bytes) { w = ws; ws += (P.ws_bytes + 255) & ~static_cast<size_t>(255); }
+        const int rc = prepare_conv(op.conv, P, w, maps[j]);
+        if (rc != YP_OK) return rc;
+        P.a.dbg = nullptr; P.a.ablate = 0;
+        K->params.args[j] = P.a;
+        m.variant = chain_variant(P.out_fmt, P.units);
+        m.gx = P.grid.x; m.gy = P.grid.y;
+        m.n_items = P.grid.x * P.grid.y * P.grid.z;
+      }
+      m.cta_off = cta_off;
+      cta_off = (cta_off + m.n_items) % G;
+      ch->n_items += m.n_items;
+      m.n_deps = 0;
+      for (int k = 0; k < op.n_deps; ++k) {
+        const int dj = op.deps[k] - k0;
+        if (dj < 0) continue;                       // produced by an earlier kernel of the chain: ordered by the stream
+        YP_REQUIRE(m.n_deps < kMaxChainDeps, YP_ERR_SHAPE, "chain: op %d has more than %d dependencies inside one kernel", i, kMaxChainDeps);
+        m.dep[m.n_deps] = dj;
+        m.dep_target[m.n_deps] = K->params.meta[dj].n_items;
+        ++m.n_deps;
+      }
+    }
+    YP_CUDA_OK(cudaMalloc(&K->d_maps, n * sizeof(ConvMaps)));
+    ch->allocs.push_back(K->d_maps);
+    YP_CUDA_OK(cudaMemcpy(K->d_maps, maps.data(), n * sizeof(ConvMaps), cudaMemcpyHostToDevice));
+    YP_CUDA_OK(cudaMalloc(&K->d_done, (kMaxChain + 1) * sizeof(unsigned)));
+    ch->allocs.push_back(K->d_done);
+    YP_CUDA_OK(cudaMemset(K->d_done, 0, (kMaxChain + 1) * sizeof(unsigned)));
+  }
+  YP_CUDA_OK(cudaDeviceSynchronize());
+  return YP_OK;
+}
+
+}  // namespace
+
+int conv_chain_create(const YpChainOp* ops, int n_ops, void** out) {
+  Chain* ch = new Chain();
+  const int rc = chain_build(ops, n_ops, ch);
+  if (rc != YP_OK) { delete ch; return rc; }
+  *out = ch;
+  return YP_OK;
+}
+
+int conv_chain_launch(void* chain, cudaStream_t st) {
+  Chain* ch = static_cast<Chain*>(chain);
+  auto kern = conv_chain_kernel<true, kChainThreads>;
+  static thread_local size_t configured = 0;
+  if (ch->smem > configured) {   // the kernel also has ~1 KB of static shared memory: ask for what the chain needs, not for the maximum
+    YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ch->smem)));
+    configured = ch->smem;
+  }
+  static const bool coop = getenv("YP_CHAIN_NO_COOP") == nullptr;
+  for (ChainKernel* K : ch->kernels) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ch->grid); cfg.blockDim = dim3(kChainThreads); cfg.dynamicSmemBytes = ch->smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the in-kernel waits cannot starve an unscheduled CTA
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = coop ? 1 : 0;
+    YP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, K->params, static_cast<const ConvMaps*>(K->d_maps), K->d_done));
+  }
+  return YP_OK;
+}
+
+// debug: device pointer of kernel k's timeline ([n_ops][#CTAs][16] int64 nanosecond stamps: 0 item start, 6 dependencies met, 1 prologue
+// done, 2 accumulators complete, 3 stores complete, 4 item end, 7 completion published), its op count and the CTA count
+int conv_chain_debug(void* chain, int k, void** dbg, int* n_ops, int* n_ctas) {
+  Chain* ch = static_cast<Chain*>(chain);
+  YP_REQUIRE(k >= 0 && k < static_cast<int>(ch->kernels.size()), YP_ERR_ARG, "chain: kernel index %d out of range", k);
+  *dbg = ch->kernels[k]->params.dbg; *n_ops = ch->kernels[k]->params.n_ops; *n_ctas = ch->grid;
+  return YP_OK;
+}
+
+int conv_chain_destroy(void* chain) {
+  delete static_cast<Chain*>(chain);
+  return YP_OK;
+}
+
+int conv_chain_info(void* chain, int* n_kernels, int* n_items, int* smem) {
+  Chain* ch = static_cast<Chain*>(chain);
+  if (n_kernels) *n_kernels = static_cast<int>(ch->kernels.size());
+  if (n_items) *n_items = ch->n_items;
+  if (smem) *smem = static_cast<int>(ch->smem);
+  return YP_OK;
 }
 
 }  // namespace yp

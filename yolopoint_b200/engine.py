@@ -26,7 +26,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import YP_ACT_NONE, YP_ACT_SILU, YP_ALGO_TCGEN05, YP_EPI_L2NORM, YP_FMT_BF16, YP_FMT_F32, YP_FMT_F32X2, YpConvDesc, YpView
+from ._lib import YP_ACT_NONE, YP_ACT_SILU, YP_ALGO_TCGEN05, YP_EPI_L2NORM, YP_FMT_BF16, YP_FMT_F32, YP_FMT_F32X2, YpChainOp, YpConvDesc, YpView
 
 BN_EPS = 1e-3
 MODEL_NAMES = ("YOLOPoint", "YOLOPointv52")
@@ -343,6 +343,61 @@ class NetPlan:
         return total
 
 
+# --------------------------------------------------------------------------------------------------
+# layer chains: dependency analysis and segment order (host logic, CPU-testable)
+# --------------------------------------------------------------------------------------------------
+def _op_reads_writes(op) -> Tuple[List[Tuple[str, int, int]], List[Tuple[str, int, int]]]:
+    """(reads, writes) of an op as (buffer, first channel, end channel) ranges."""
+    if isinstance(op, PoolOp):
+        return [(op.buf, 0, 1 << 30)], [(op.buf, 0, 1 << 30)]
+    if isinstance(op, Pool2Op):
+        return [(op.src.buf, op.src.c_off, op.src.c_off + op.src.C)], [(op.dst.buf, op.dst.c_off, op.dst.c_off + op.dst.C)]
+    reads = [(op.src.buf, op.src.c_off, op.src.c_off + op.src.C)]
+    if op.residual is not None:
+        reads.append((op.residual.buf, op.residual.c_off, op.residual.c_off + op.residual.C))
+    return reads, [(d.buf, d.c_off, d.c_off + d.C) for d in op.dst]
+
+
+def _overlap(a, b) -> bool:
+    return any(x[0] == y[0] and x[1] < y[2] and y[1] < x[2] for x in a for y in b)
+
+
+def chain_dependencies(ops: Sequence[object]) -> List[List[int]]:
+    """For every op of a sequentially valid list: the earlier ops it must wait for -- read-after-write, write-after-read and
+    write-after-write on channel ranges of the activation buffers -- transitively reduced (a dependency implied by another one is
+    dropped).  This is what lets ``conv_chain_kernel`` run independent branches of the network (keypoint head, descriptor head,
+    detection branch; src/models/YOLOPoint.py:198-246) concurrently and reorder them."""
+    rw = [_op_reads_writes(op) for op in ops]
+    anc: List[set] = []
+    deps: List[List[int]] = []
+    for j, (rj, wj) in enumerate(rw):
+        direct = [i for i in range(j) if _overlap(rw[i][1], rj) or _overlap(rw[i][1], wj) or _overlap(rw[i][0], wj)]
+        keep = [d for d in direct if not any(d in anc[e] for e in direct if e != d)]
+        a = set(direct)
+        for d in direct:
+            a |= anc[d]
+        anc.append(a)
+        deps.append(keep)
+    return deps
+
+
+def chain_schedule(ops: Sequence[object], milestones: Sequence[int]) -> Tuple[List[int], List[int]]:
+    """Order and segment boundaries for the chained execution of ``ops``.
+
+    The order sorts the ops by dependency depth (ops of the same depth are independent: the branches of the network interleave, so
+    consecutive items of the chain rarely wait for each other).  ``milestones`` are indices of ops after which work outside the chain
+    may start (the last layer of a head, a Detect level): the sorted list is cut right behind each of them.
+    Returns (order, cuts): ``order`` = op indices in execution order, ``cuts`` = segment end positions (exclusive) in ``order``."""
+    deps = chain_dependencies(ops)
+    depth = []
+    for j, d in enumerate(deps):
+        depth.append(1 + max((depth[i] for i in d), default=0))
+    order = sorted(range(len(ops)), key=lambda j: (depth[j], j))
+    pos = {j: k for k, j in enumerate(order)}
+    cuts = sorted({pos[m] + 1 for m in milestones} | {len(order)})
+    return order, cuts
+
+
 def check_plan(net: "NetPlan", B: int, H: int, W: int) -> List[Tuple[str, str]]:
     """Dry run of every convolution launch of ``net`` at input shape [B,3,H,W] through the library's host-side planner
     (``yp_conv2d_plan_check``: formats, channel / tile geometry, shared memory and TMEM budgets).  Needs the shared library but no
@@ -503,16 +558,19 @@ class ShapePlan:
         eng = self.eng
         need, descs = {}, []
         self.conv_descs = []
+        self.op_records = []   # per op of net.ops: ("conv", YpConvDesc) / ("pool", YpView) / ("pool2", None): input of the layer chains
         self.tuning = load_tuning(eng.net.version, self.B, self.H, self.W, eng.precision, eng.net.model_name) if eng.use_tuning else {}
         for op in eng.net.ops:
             if isinstance(op, PoolOp):
                 v = self.view(SliceRef(op.buf, 0, self.bufs[op.buf].shape[-1]))
                 self._keep.append(v)
+                self.op_records.append(("pool", v))
                 self.launches.append((0, lambda st, v=v: _lib.check(L.yp_sppf_pool(C.byref(v), st)), "sppf_pool"))
                 continue
             if isinstance(op, Pool2Op):
                 vi, vo = self.view(op.src), self.view(op.dst)
                 self._keep += [vi, vo]
+                self.op_records.append(("pool2", None))
                 self.launches.append((op.lane, lambda st, vi=vi, vo=vo: _lib.check(L.yp_maxpool2x2(C.byref(vi), C.byref(vo), st)), "maxpool2x2"))
                 continue
             w, b = eng.weights[op.names]
@@ -533,6 +591,7 @@ class ShapePlan:
             if tuned and eng.split_k:
                 d.tile_n, d.split_k = int(tuned[0]), int(tuned[1])
             self.conv_descs.append((op, d))
+            self.op_records.append(("conv", d))
             need[op.lane] = max(need.get(op.lane, 0), int(L.yp_conv2d_workspace_bytes(C.byref(d)))) if eng.split_k else 0
             descs.append((op.lane, d))
             self._keep.append(d)
@@ -544,6 +603,75 @@ class ShapePlan:
             if lane in self.workspaces:
                 d.workspace = self.workspaces[lane].data_ptr()
                 d.workspace_bytes = self.workspaces[lane].numel()
+        self.chain = None
+        if eng.chain:
+            self._build_chain()
+
+    def _build_chain(self):
+        """Layer chains (yp_conv_chain_*): the launch list reordered by dependency depth and cut behind the layers that work outside
+        the network waits for (last layer of the keypoint / descriptor head, Detect levels 0 and 1); every segment is one persistent
+        kernel.  Falls back to the per-layer launch list when an op cannot be chained (YOLOPointv52's 2x2 max pool, bf16 operands)."""
+        L, ops = _lib.lib(), self.eng.net.ops
+        if any(kind == "pool2" for kind, _ in self.op_records) or self.eng.precision != "fp32" or self.eng.algo != YP_ALGO_TCGEN05:
+            return
+        names = ["+".join(op.names) if isinstance(op, ConvOp) else "sppf_pool" for op in ops]
+        lanes = [getattr(op, "lane", 0) for op in ops]
+        milestones = {}
+        for lane in (1, 2):
+            idx = [i for i, ln in enumerate(lanes) if ln == lane]
+            if idx:
+                milestones[max(idx)] = ("lane", lane)
+        for nm in os.environ.get("YP_CHAIN_HOOK_CUTS", "Detect.m.0,Detect.m.1").split(","):
+            if nm in names:
+                milestones[names.index(nm)] = ("hook", nm)
+        deps = chain_dependencies(ops)
+        order, cuts = chain_schedule(ops, list(milestones))
+        segs, k0 = [], 0
+        for c in cuts:
+            seg_ops = order[k0:c]
+            local = {j: i for i, j in enumerate(seg_ops)}
+            arr = (YpChainOp * len(seg_ops))()
+            for i, j in enumerate(seg_ops):
+                kind, rec = self.op_records[j]
+                arr[i].type = 0 if kind == "conv" else 1
+                if kind == "conv":
+                    arr[i].conv = rec
+                else:
+                    arr[i].pool = rec
+                dl = [local[d] for d in deps[j] if d in local]   # dependencies on earlier segments are ordered by the stream
+                arr[i].n_deps = len(dl)
+                for q, d in enumerate(dl):
+                    arr[i].deps[q] = d
+            handle = C.c_void_p()
+            rc = L.yp_conv_chain_create(arr, len(seg_ops), C.byref(handle))
+            if rc != 0:
+                for sg in segs:
+                    L.yp_conv_chain_destroy(sg["handle"])
+                if os.environ.get("YP_CHAIN", "") == "require":
+                    _lib.check(rc)
+                return
+            nk, ni, sm = C.c_int32(), C.c_int32(), C.c_int32()
+            _lib.check(L.yp_conv_chain_info(handle, C.byref(nk), C.byref(ni), C.byref(sm)))
+            segs.append({"handle": handle, "ops": seg_ops, "names": [names[j] for j in seg_ops], "kernels": nk.value, "items": ni.value, "smem": sm.value,
+                         "lanes": [v for j in seg_ops if j in milestones for k_, v in [milestones[j]] if k_ == "lane"],
+                         "hooks": [v for j in seg_ops if j in milestones for k_, v in [milestones[j]] if k_ == "hook"]})
+            k0 = c
+        self.chain = segs
+
+    def __del__(self):
+        try:
+            if getattr(self, "chain", None):
+                L = _lib.lib()
+                for sg in self.chain:
+                    L.yp_conv_chain_destroy(sg["handle"])
+        except Exception:
+            pass
+
+    def n_net_launches(self) -> int:
+        """Kernels one pass over the network launches (per-layer list, or the kernels of the layer chains)."""
+        if self.chain:
+            return sum(sg["kernels"] for sg in self.chain)
+        return len(self.launches)
 
     # ---- pieces -------------------------------------------------------------------------------
     def _stream(self):
@@ -573,6 +701,8 @@ class ShapePlan:
         after = after or {}
         dev = self.eng.device
         main = torch.cuda.current_stream(dev)
+        if self.chain:
+            return self._run_net_chain(tails, after, main)
         if not self.eng.multi_stream:
             st = C.c_void_p(main.cuda_stream)
             for _, f, name in self.launches:
@@ -618,6 +748,54 @@ class ShapePlan:
             ev.record(hs)
             main.wait_event(ev)
 
+    def _run_net_chain(self, tails, after, main):
+        """The network as layer chains: the segments run back to back on the current stream; a lane's tail / a layer's hook is
+        enqueued on a side stream behind the segment that ends with that lane / layer, under the following segments."""
+        L = _lib.lib()
+        st = C.c_void_p(main.cuda_stream)
+        multi = self.eng.multi_stream
+        if multi:
+            self.side_stream(1)
+        joins = []
+        free_hook_lanes = [3, 4]
+        pending_hooks = dict(after)
+        for sg in self.chain:
+            _lib.check(L.yp_conv_chain_launch(sg["handle"], st))
+            for lane in sorted(sg["lanes"]):
+                if lane not in tails:
+                    continue
+                if not multi:
+                    tails[lane](st)
+                    continue
+                side = self._side[lane]
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                tails[lane](C.c_void_p(side.cuda_stream))
+                joins.append(side)
+            for nm in sg["hooks"]:
+                if nm not in pending_hooks:
+                    continue
+                hook = pending_hooks.pop(nm)
+                if not multi or not free_hook_lanes:
+                    hook(st)
+                    continue
+                hs = self._side[free_hook_lanes.pop(0)]
+                ev = torch.cuda.Event()
+                ev.record(main)
+                hs.wait_event(ev)
+                hook(C.c_void_p(hs.cuda_stream))
+                joins.append(hs)
+        for nm, hook in pending_hooks.items():   # hooks of layers that are not segment ends
+            hook(st)
+        for lane in sorted(tails):               # tails of lanes without a milestone (none in the shipped plans)
+            if not any(lane in sg["lanes"] for sg in self.chain):
+                tails[lane](st)
+        for side in joins:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
+
     def run_decode(self, want_raw: bool = True):
         L, net, st = _lib.lib(), self.eng.net, self._stream()
         row = 0
@@ -660,12 +838,17 @@ class ShapePlan:
 
 class Engine:
     def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True,
-                 multi_stream: bool = True, split_k: bool = True, use_tuning: bool = True, model_name: str = "YOLOPoint"):
+                 multi_stream: bool = True, split_k: bool = True, use_tuning: bool = True, model_name: str = "YOLOPoint", chain: Optional[bool] = None):
         _lib.lib(require_device=True)
         self.device = torch.device(device)
         self.net = NetPlan(version, nc, precision, model_name)
         self.precision, self.algo, self.use_graphs, self.multi_stream, self.split_k = precision, algo, use_graphs, multi_stream, split_k
         self.use_tuning = use_tuning
+        # layer chains (one persistent kernel per network segment, yp_conv_chain_*): opt-in (chain=True or YP_CHAIN=1).  Measured on
+        # B200 (YOLOPoint-S 640x640 batch 1, profiles/r02_chain.md): 1.005 ms per pass against 0.722 ms for the per-layer launch list
+        # (CUDA graph + programmatic dependent launch) -- the per-layer cost is the CTA's own latency (first TMA, K loop, epilogue,
+        # store drain), which a chain does not shorten, and multi-wave layers lose the two-CTAs-per-SM overlap.
+        self.chain = (os.environ.get("YP_CHAIN", "0") not in ("0", "")) if chain is None else bool(chain)
         sd = {k: v.detach() for k, v in sd.items()}
         self.anchors = _get(sd, "Detect.anchors").float().cpu()
         self.stride = torch.tensor([8.0, 16.0, 32.0])
