@@ -588,7 +588,15 @@ class ShapePlan:
             d.algo = eng.algo
             d.split_k = 0 if eng.split_k else 1
             tuned = self.tuning.get("+".join(op.names))
-            if tuned and eng.split_k:
+            if eng.tile_policy == "wide":
+                # throughput plan: the widest N tile (fewest re-reads of the activation tile, fewest MMAs per FLOP), K never split --
+                # a layer then occupies few SMs, which is what several frames in flight want
+                step = 32 if (op.cout * 4) % 128 == 0 else 16
+                nmax = 128 if eng.precision == "fp32" else 256
+                if not op.l2norm:
+                    d.tile_n = max((n for n in range(step, min(op.cout, nmax) + 1, step) if op.cout % n == 0), default=0)
+                d.split_k = 1
+            elif tuned and eng.split_k:
                 d.tile_n, d.split_k = int(tuned[0]), int(tuned[1])
             self.conv_descs.append((op, d))
             self.op_records.append(("conv", d))
@@ -838,12 +846,16 @@ class ShapePlan:
 
 class Engine:
     def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True,
-                 multi_stream: bool = True, split_k: bool = True, use_tuning: bool = True, model_name: str = "YOLOPoint", chain: Optional[bool] = None):
+                 multi_stream: bool = True, split_k: bool = True, use_tuning: bool = True, model_name: str = "YOLOPoint", chain: Optional[bool] = None,
+                 tile_policy: Optional[str] = None):
         _lib.lib(require_device=True)
         self.device = torch.device(device)
         self.net = NetPlan(version, nc, precision, model_name)
         self.precision, self.algo, self.use_graphs, self.multi_stream, self.split_k = precision, algo, use_graphs, multi_stream, split_k
         self.use_tuning = use_tuning
+        # "latency" = per-layer (tile_n, split_k) from the measured tables (smallest time of ONE pass); "wide" = widest N tile, no split-K
+        self.tile_policy = tile_policy or os.environ.get("YP_TILE_POLICY", "latency")
+        assert self.tile_policy in ("latency", "wide"), self.tile_policy
         # layer chains (one persistent kernel per network segment, yp_conv_chain_*): opt-in (chain=True or YP_CHAIN=1).  Measured on
         # B200 (YOLOPoint-S 640x640 batch 1, profiles/r02_chain.md): 1.005 ms per pass against 0.722 ms for the per-layer launch list
         # (CUDA graph + programmatic dependent launch) -- the per-layer cost is the CTA's own latency (first TMA, K loop, epilogue,

@@ -275,6 +275,21 @@ class FramePipeline:
         self.parity = nxt
         return k
 
+    def prepare(self, host: bool = True):
+        """Capture the CUDA graphs of every frame context (device path, and the host path's variant that reads the staging buffer)
+        by running each context once on whatever its input buffers hold; the tracking state is reset afterwards.  Set-up, not work:
+        without it the first ``nctx`` frames pay an eager run + capture each."""
+        for _ in range(self.nctx):
+            self.step_device(True)
+        self.join()
+        if host:
+            zero = np.zeros((self.B, self.H, self.W, 3), np.uint8)
+            for _ in range(self.nctx):
+                self.submit_host(zero)
+                self.collect()
+        torch.cuda.synchronize(self.eng.device)
+        self.reset_tracking()
+
     def join(self):
         """Make the current stream wait for every frame in flight (no-op with ``frames_in_flight`` = 1: same stream)."""
         if self.F > 1:

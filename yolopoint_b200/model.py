@@ -323,7 +323,8 @@ class Model(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("yolopoint_b200.Model runs inference on a CUDA (sm_100a) device only: call .cuda() first; "
                                    "there is no CPU fallback")
-            self._engine = Engine(self.state_dict(), self.version, self.nc, dev, precision=self.precision, model_name=self.model_name)
+            self._engine = Engine(self.state_dict(), self.version, self.nc, dev, precision=self.precision, model_name=self.model_name,
+                                  tile_policy=getattr(self, "tile_policy", None))
         return self._engine
 
     def invalidate_engine(self):
