@@ -76,6 +76,7 @@ typedef struct {
 
 typedef enum { YP_ACT_NONE = 0, YP_ACT_SILU = 1 } YpAct;
 typedef enum { YP_ALGO_TCGEN05 = 0, YP_ALGO_SIMT = 1 } YpConvAlgo;
+#define YP_TILE_WIDE (-1)
 #define YP_EPI_L2NORM 1u /* divide each output pixel by its L2 norm over all `cout` channels */
 #define YP_EPI_NO_PATCH 2u /* planner hint: do not use the shared-memory patch formulation of 3x3 stride-1 convs */
 #define YP_EPI_ROWMIN 4u   /* descriptor matching on the tensor cores: nothing is stored; for every input pixel i (a descriptor of set 1, the
@@ -109,7 +110,8 @@ typedef struct {
   int32_t n_out;          /* 1 or 2 */
   YpView out[2];
   int32_t algo;           /* YpConvAlgo */
-  int32_t tile_n;         /* 0 = library heuristic; else the N (output-channel) tile: a divisor of cout, multiple of 16, <= 128 (fp32) / 256 (bf16) */
+  int32_t tile_n;         /* 0 = library heuristic; YP_TILE_WIDE = throughput plan (widest tile whose accumulator plan keeps fp32-grade accuracy; split_k
+                             is then chosen by the library); else the N (output-channel) tile: a divisor of cout, multiple of 16, <= 128 (fp32) / 256 (bf16) */
   int32_t split_k;        /* 0 = let the library slice K over several CTAs when the layer cannot fill the GPU, 1 = never, n = n slices */
   void* workspace;        /* split-K scratch (zero-initialised once by the caller, reusable by later launches on the same
                              stream; launches that may run concurrently need distinct workspaces); NULL -> never split */

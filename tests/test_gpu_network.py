@@ -304,3 +304,42 @@ def test_frames_in_flight_equal_one_at_a_time(F):
         ref_counts.append(ref_pipe.d_counts[k].cpu().numpy().copy())
     for a, b in zip(ref_counts[-pipe.nctx:], got_counts):
         np.testing.assert_array_equal(a[:3], b[:3])
+
+
+@pytest.mark.parametrize("ver,B,H,W", [("s", 1, 640, 640), ("n", 1, 480, 640)])
+def test_wide_tile_policy_meets_oracle_tolerances(ver, B, H, W):
+    """The throughput plan of bench.py's headline line (Engine(tile_policy="wide") -> YP_TILE_WIDE: the widest N tile whose accumulator
+    plan chains at most 48 truncating tensor-core accumulations, K split only where that bound asks for it) is a different summation
+    order of the same arithmetic; it is held to the same tolerances against the oracle as the latency-tuned plan."""
+    from yolopoint_b200.engine import Engine
+    _, sd = build(ver)
+    torch.manual_seed(4)
+    x = torch.rand(B, 3, H, W)
+    eng = Engine(sd, ver, 80, torch.device("cuda:0"), tile_policy="wide")
+    out = eng.forward(x.cuda())
+    ref = O.OracleNet(sd, ver, 80).forward(x)
+    check_outputs(out, ref, f"wide {ver} {B}x{H}x{W}")
+
+
+def test_wide_policy_pipeline_equals_latency_policy_indices():
+    """Whole-frame pipeline under the wide tile policy with 8 frames in flight (the configuration bench.py times) against the
+    latency-tuned pipeline processing one frame at a time: the keypoint sets agree to >= 99 %, box counts within 2 % (the two plans
+    differ by fp32 summation order only, which may flip a handful of threshold decisions)."""
+    from yolopoint_b200.engine import Engine
+    m, sd = build("s")
+    H = W = 640
+    frames = [synthetic_frame(H, W, s)[None] for s in range(4)]
+    ref_pipe = FramePipeline(m, 1, H, W)
+    ref = [ref_pipe.step_host(f)[0] for f in frames]
+    eng = Engine(sd, "s", 80, torch.device("cuda:0"), tile_policy="wide")
+    pipe = FramePipeline(eng, 1, H, W, frames_in_flight=8)
+    for f in frames:
+        pipe.submit_host(f)
+    got = [pipe.collect()[0] for _ in frames]
+    for i, (r, g) in enumerate(zip(ref, got)):
+        rs = {(int(x), int(y)) for x, y in zip(r[0][0], r[0][1])}
+        gs = {(int(x), int(y)) for x, y in zip(g[0][0], g[0][1])}
+        assert len(rs & gs) >= 0.99 * len(rs) and len(gs) <= 1.01 * len(rs) + 1, (i, len(rs), len(gs), len(rs & gs))
+        assert abs(r[2].shape[0] - g[2].shape[0]) <= max(1, r[2].shape[0] // 50)
+        if i:
+            assert abs(r[3].shape[1] - g[3].shape[1]) <= max(3, r[3].shape[1] // 10)

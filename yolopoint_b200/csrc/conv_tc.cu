@@ -351,6 +351,7 @@ __device__ __forceinline__ void conv_tile(const ConvMaps& maps, const ConvArgs& 
     const bool live = a.ablate != 1;
     const bool fast4 = held<kChain>(live && ksteps == 4 && kinc == 1 && !two && a.ablate != 8) != 0;   // YP_CONV_ABLATE=8: generic loop (A/B runs)
     const bool fast2 = held<kChain>(live && ksteps == 4 && kinc == 2 && !two && a.ablate != 8) != 0;   // two issuers share a stream: every other k-step
+    const bool fast4two = held<kChain>(live && ksteps == 4 && kinc == 1 && two && cnt == 1 && a.ablate != 8) != 0;   // both cross terms of the un-stacked wide plan
     uint32_t used = 0;                   // bit r set = accumulator r of this issuer already holds a partial sum
     int s = 0, ph = 0, nxt = 0;
     if (a.patch) {
@@ -382,6 +383,13 @@ __device__ __forceinline__ void conv_tile(const ConvMaps& maps, const ConvArgs& 
               umma32_one<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
               used |= 1u << nxt;
               nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+            }
+          } else if (fast4two) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma32_one<kTf32>(col0, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, used);
+              umma32_one<kTf32>(col0, al1 + 2 * k, bl1 + 2 * k, dhi, idesc, 1u);
+              used = 1u;
             }
           } else
           for (int k = kstart; k < ksteps && live; k += kinc) {
@@ -421,6 +429,13 @@ __device__ __forceinline__ void conv_tile(const ConvMaps& maps, const ConvArgs& 
             umma32_one<kTf32>(col0 + nxt * cstride, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, (used >> nxt) & 1u);
             used |= 1u << nxt;
             nxt = (nxt + 1 == cnt) ? 0 : nxt + 1;
+          }
+        } else if (fast4two) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma32_one<kTf32>(col0, al0 + 2 * k, bl0 + 2 * k, dhi, idesc, used);
+            umma32_one<kTf32>(col0, al1 + 2 * k, bl1 + 2 * k, dhi, idesc, 1u);
+            used = 1u;
           }
         } else
         for (int k = kstart; k < ksteps && live; k += kinc) {
@@ -1286,9 +1301,42 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   const int m_tiles = a.tiles_w * a.tiles_h * in.B;
   const int nsm = sm_count();
   int Nt = 0;
+  int split_req = d.split_k;           // 0 = heuristic, 1 = never, n = n slices
   if (d.epilogue & YP_EPI_L2NORM) {
     YP_REQUIRE(d.cout <= 256, YP_ERR_SHAPE, "conv: L2-norm epilogue needs Cout <= 256 (got %d)", d.cout);
     Nt = d.cout;
+  } else if (d.tile_n == YP_TILE_WIDE) {
+    // Throughput plan: the widest N tile (fewest re-reads of the activation tile, fewest MMAs per FLOP) whose accumulator plan still
+    // keeps the fp32-grade accuracy of the 3xTF32 mode.  The tensor core adds into an fp32 accumulator with truncation, so the error
+    // grows with the number of MMAs chained on one accumulator: a wide tile leaves TMEM room for fewer accumulators to rotate over
+    // (Nt = 128: three main accumulators beside one for both cross terms -- the un-stacked plan below --, 64: three [main | cross]
+    // pairs, 32: six).  Every candidate tile is charged the K split that keeps its chains <= kMaxChain main MMAs (each slice has its
+    // own accumulators; partial tiles are summed in fp32 with rounding).
+    static const int kMaxChain = getenv("YP_CONV_MAX_CHAIN") ? atoi(getenv("YP_CONV_MAX_CHAIN")) : 24;
+    const int total_steps = num_kb * ksteps;
+    auto n_main = [&](int nt) {
+      if (!tf32) return 1 << 20;       // bf16 operands: the accumulator plan is not the accuracy limit
+      if (nt == 128) return 3;
+      const int lim = (static_cast<long long>(m_tiles) * (d.cout / nt) > nsm) ? 256 : 512;
+      int n_s = 2, n_p = (lim - n_s * nt) / (2 * nt);
+      if (n_p < 1) { n_s = 1; n_p = (lim - nt) / (2 * nt); }
+      if (n_p < 1) n_p = (512 - nt) / (2 * nt);
+      return std::max(1, std::min(n_p, 6));
+    };
+    // Candidates from wide to narrow; the first that needs no K split wins.  When every tile needs a split: a layer that fills the GPU
+    // anyway takes the tile with the fewest slices (split-K partial tiles are pure overhead there), a small layer the widest tile
+    // (its extra CTAs only cost their fixed set-up, the tensor time per FLOP is what the wide tile saves).
+    int best_split = 1 << 20, widest = 0, widest_split = 1;
+    for (int n = tf32 ? 128 : 256; n >= chunk_elems; n -= 16) {
+      if (d.cout % n || n % chunk_elems) continue;
+      int need = ceil_div(total_steps, n_main(n) * kMaxChain);          // K slices that bound the chains of this tile
+      if (need > num_kb) need = num_kb;
+      if (!widest) { widest = n; widest_split = need; }
+      if (need < best_split) { Nt = n; best_split = need; }
+      if (n <= 32 || best_split == 1) break;
+    }
+    if (best_split > 1 && static_cast<long long>(m_tiles) * (d.cout / widest) < nsm / 2) { Nt = widest; best_split = widest_split; }
+    split_req = std::max(1, best_split);
   } else if (d.tile_n > 0) {
     YP_REQUIRE(d.tile_n % chunk_elems == 0 && d.cout % d.tile_n == 0 && d.tile_n <= (tf32 ? 128 : 256), YP_ERR_SHAPE,
                "conv: tile_n=%d invalid for Cout=%d (store chunk %d)", d.tile_n, d.cout, chunk_elems);
@@ -1310,11 +1358,11 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
 
   // ---- split-K: deep layers on small feature maps occupy few CTAs; slice K over grid.z so that ~#SM CTAs are busy.
   int S = 1;
-  if (allow_split && !rowmin && d.split_k != 1 && static_cast<size_t>(m_tiles) * n_tiles * sizeof(int) <= kWsCounterBytes) {
+  if (allow_split && !rowmin && split_req != 1 && static_cast<size_t>(m_tiles) * n_tiles * sizeof(int) <= kWsCounterBytes) {
     const int ctas = m_tiles * n_tiles;
-    int want = d.split_k > 1 ? d.split_k : nsm / ctas;
+    int want = split_req > 1 ? split_req : nsm / ctas;
     if (want > 16) want = 16;
-    if (d.split_k <= 1) {                         // heuristic: at most 8 slices of >= 4 k-blocks (>= 1 channel block in patch mode)
+    if (split_req <= 1) {                         // heuristic: at most 8 slices of >= 4 k-blocks (>= 1 channel block in patch mode)
       if (want > 8) want = 8;
       const int lim = a.patch ? num_kb : num_kb / 4;
       if (want > lim) want = lim;
@@ -1336,7 +1384,9 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   const bool chain = g_chain_budget > 0;
   const bool persist = allow_persist && !chain && !tf32 && S == 1 && !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && out_fmt != YP_FMT_F32X2 &&
                        static_cast<long long>(m_tiles) * n_tiles > (getenv("YP_CONV_PERSIST_MIN") ? atoll(getenv("YP_CONV_PERSIST_MIN")) : 2LL * nsm);
-  const bool dense = !chain && ((allow_dense && static_cast<long long>(m_tiles) * n_tiles * S > nsm) || persist);   // persist: 256 columns per accumulator buffer
+  static const bool force_dense = getenv("YP_CONV_FORCE_DENSE") != nullptr && atoi(getenv("YP_CONV_FORCE_DENSE")) != 0;
+  const bool unstacked = d.tile_n == YP_TILE_WIDE && tf32 && Nt == 128 && !(d.epilogue & YP_EPI_L2NORM);   // needs all 512 TMEM columns
+  const bool dense = !chain && !unstacked && ((allow_dense && (force_dense || static_cast<long long>(m_tiles) * n_tiles * S > nsm)) || persist);   // persist: 256 columns per accumulator buffer
   const int tmem_limit = dense ? 256 : 512;
 
   // ---- accumulator / issuer plan (see the kernel comment)
@@ -1345,7 +1395,19 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     return (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
   };
   int cols = 0;
-  if (tf32 && Nt <= 128) {
+  if (unstacked) {
+    // Wide throughput tile: the main product A_hi x W_hi rotates over three accumulators (issuer 0), both cross terms go into a fourth
+    // (issuer 1, two MMAs per k-step; their partial sums are ~2^-11 of the result, so their truncation error is negligible).
+    const int n_p = std::min(3, std::max(1, mmas_min));
+    a.n_iss = 2; a.kstart[0] = a.kstart[1] = 0; a.kinc[0] = a.kinc[1] = 1;
+    a.n_jobs[0] = 1; a.job_a[0][0] = 0; a.job_b[0][0] = 0; a.iss_col[0] = 0; a.iss_stride[0] = Nt; a.iss_cnt[0] = n_p; a.iss_idesc[0] = idesc(Nt);
+    a.n_jobs[1] = 2; a.job_a[1][0] = 1; a.job_b[1][0] = 0; a.job_a[1][1] = 0; a.job_b[1][1] = 1;
+    a.iss_col[1] = n_p * Nt; a.iss_stride[1] = 0; a.iss_cnt[1] = 1; a.iss_idesc[1] = idesc(Nt);
+    for (int j = 0; j < n_p; ++j) a.src_col[j] = j * Nt;
+    a.src_col[n_p] = n_p * Nt;
+    a.n_src = n_p + 1;
+    cols = (n_p + 1) * Nt;
+  } else if (tf32 && Nt <= 128) {
     // issuer 0: A_hi x [W_hi; W_lo]  (N = 2 Nt)  -> pairs [main | cross2];  issuer 1: A_lo x W_hi (N = Nt) -> cross1
     int n_s = 2, n_p = (tmem_limit - n_s * Nt) / (2 * Nt);
     if (n_p < 1) { n_s = 1; n_p = (tmem_limit - Nt) / (2 * Nt); }

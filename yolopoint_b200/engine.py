@@ -589,13 +589,11 @@ class ShapePlan:
             d.split_k = 0 if eng.split_k else 1
             tuned = self.tuning.get("+".join(op.names))
             if eng.tile_policy == "wide":
-                # throughput plan: the widest N tile (fewest re-reads of the activation tile, fewest MMAs per FLOP), K never split --
-                # a layer then occupies few SMs, which is what several frames in flight want
-                step = 32 if (op.cout * 4) % 128 == 0 else 16
-                nmax = 128 if eng.precision == "fp32" else 256
+                # throughput plan (YP_TILE_WIDE): the widest N tile whose accumulator plan keeps the fp32-grade accuracy, K split only
+                # where the accuracy bound asks for it -- a layer then occupies few SMs, which is what several frames in flight want
                 if not op.l2norm:
-                    d.tile_n = max((n for n in range(step, min(op.cout, nmax) + 1, step) if op.cout % n == 0), default=0)
-                d.split_k = 1
+                    d.tile_n = -1
+                d.split_k = 0
             elif tuned and eng.split_k:
                 d.tile_n, d.split_k = int(tuned[0]), int(tuned[1])
             self.conv_descs.append((op, d))
