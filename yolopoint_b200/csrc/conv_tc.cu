@@ -1316,7 +1316,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     const int total_steps = num_kb * ksteps;
     auto n_main = [&](int nt) {
       if (!tf32) return 1 << 20;       // bf16 operands: the accumulator plan is not the accuracy limit
-      if (nt == 128) return 3;
+      if (nt == 128 && m_tiles < nsm) return 3;     // un-stacked plan (single-wave layers only: it needs all 512 TMEM columns, one CTA per SM)
       const int lim = (static_cast<long long>(m_tiles) * (d.cout / nt) > nsm) ? 256 : 512;
       int n_s = 2, n_p = (lim - n_s * nt) / (2 * nt);
       if (n_p < 1) { n_s = 1; n_p = (lim - nt) / (2 * nt); }
@@ -1385,7 +1385,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   const bool persist = allow_persist && !chain && !tf32 && S == 1 && !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && out_fmt != YP_FMT_F32X2 &&
                        static_cast<long long>(m_tiles) * n_tiles > (getenv("YP_CONV_PERSIST_MIN") ? atoll(getenv("YP_CONV_PERSIST_MIN")) : 2LL * nsm);
   static const bool force_dense = getenv("YP_CONV_FORCE_DENSE") != nullptr && atoi(getenv("YP_CONV_FORCE_DENSE")) != 0;
-  const bool unstacked = d.tile_n == YP_TILE_WIDE && tf32 && Nt == 128 && !(d.epilogue & YP_EPI_L2NORM);   // needs all 512 TMEM columns
+  const bool unstacked = d.tile_n == YP_TILE_WIDE && m_tiles < nsm && tf32 && Nt == 128 && !(d.epilogue & YP_EPI_L2NORM);   // needs all 512 TMEM columns
   const bool dense = !chain && !unstacked && ((allow_dense && (force_dense || static_cast<long long>(m_tiles) * n_tiles * S > nsm)) || persist);   // persist: 256 columns per accumulator buffer
   const int tmem_limit = dense ? 256 : 512;
 
