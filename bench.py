@@ -313,6 +313,18 @@ def main():
     K, Wm = args.steps, max(args.warmup, 3)
     config = {"workload": f"{model_name}-{version.upper()} {W}x{H} batch={per_gpu}/GPU full per-frame pipeline (net+decode+boxNMS+heatmap+kpNMS+desc+match)",
               "frames_per_gpu_per_step": per_gpu, "precision": args.precision, "parallelism": f"frames sharded over {world} GPU(s), no collective"}
+    # execution parameters of the B200 arm; the reference arm prints the same `config` (it names the line it is compared with)
+    if args.in_flight <= 0:
+        args.in_flight = 8 if per_gpu == 1 else 2
+    policy = args.tile_policy if args.tile_policy != "auto" else ("wide" if (args.in_flight >= 4 and per_gpu == 1) else "latency")
+    NS = max(1, args.streams)
+    frame_bytes = per_gpu * H * W * 3
+    n_pool = max(8, int(160e6 // frame_bytes) + 1)
+    config["streams_per_gpu"] = NS
+    config["conv_tile_policy"] = policy
+    config["frames_in_flight"] = (f"{args.in_flight}: consecutive frames of the one camera stream are software-pipelined, each a batch-{per_gpu} pass; "
+                                  "only the in-box filter + match of frame i+1 wait for frame i") if args.in_flight > 1 else 1
+    config["l2"] = f"inputs larger than L2: pool of {n_pool} frame batches ({n_pool * frame_bytes / 1e6:.0f} MB) cycled, weights stay L2-resident"
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -342,26 +354,16 @@ def main():
     peaks = load_peaks()
     model, sd = build_weights(version, model_name)
     model.precision = args.precision
-    if args.in_flight <= 0:
-        args.in_flight = 8 if per_gpu == 1 else 2
-    policy = args.tile_policy if args.tile_policy != "auto" else ("wide" if (args.in_flight >= 4 and per_gpu == 1) else "latency")
     model.tile_policy = policy
     model = model.to(dev).eval()
-    NS = max(1, args.streams)
     pipes = [FramePipeline(model, per_gpu, H, W, slot=i, frames_in_flight=args.in_flight) for i in range(NS)]
     cuda_streams = [torch.cuda.Stream(dev) for _ in range(NS)]
     for pp in pipes:
         pp.prepare()       # graph capture of every frame context (set-up; the W warm-up steps below then run the replay path)
     pipe = pipes[0]
     plan = pipe.plan
-    config["streams_per_gpu"] = NS
-    config["conv_tile_policy"] = policy
-    config["frames_in_flight"] = (f"{args.in_flight}: consecutive frames of the one camera stream are software-pipelined, each a batch-{per_gpu} pass; "
-                                  "only the in-box filter + match of frame i+1 wait for frame i") if args.in_flight > 1 else 1
 
     # input pool larger than L2 (126 MB): every step reads a different frame batch from HBM
-    frame_bytes = per_gpu * H * W * 3
-    n_pool = max(8, int(160e6 // frame_bytes) + 1)
     # Weak scaling: every rank processes the SAME set of synthetic frames (identical work per GPU), each starting at a different
     # offset of the pool so that the ranks are not in lockstep.  (r01 seeded the frames by rank; the work per frame -- box
     # candidates 300 .. 7000 -- then differed between ranks, which measures the frames, not the scaling.  Frames of every rank
@@ -371,7 +373,6 @@ def main():
     for i in range(n_pool):
         for b in range(per_gpu):
             pool[i, b] = torch.from_numpy(np.roll(base[(i + b) % 4], shift=(3 * i) % W, axis=1)).to(dev)
-    config["l2"] = f"inputs larger than L2: pool of {n_pool} frame batches ({n_pool * frame_bytes / 1e6:.0f} MB) cycled, weights stay L2-resident"
 
     def barrier():
         if world > 1:

@@ -1,0 +1,24 @@
+"""Eager network passes of YOLOPoint-S 640x640 batch 1 for an ncu capture of every conv launch under a tile policy:
+   ncu --set full --clock-control none -k regex:conv_tc_kernel -s 130 -c 65 -o gpurun_out/x python tools/prof_net_pass.py [latency|wide]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from yolopoint_b200 import Model  # noqa: E402
+from yolopoint_b200.engine import Engine  # noqa: E402
+from yolopoint_b200.synth import perturb_state_dict  # noqa: E402
+
+policy = sys.argv[1] if len(sys.argv) > 1 else "wide"
+torch.manual_seed(0)
+m = Model(names=[str(i) for i in range(80)], version="s")
+sd = perturb_state_dict(m.state_dict(), 0, "s")
+eng = Engine(sd, "s", 80, torch.device("cuda:0"), tile_policy=policy, use_graphs=False, multi_stream=False)
+p = eng.plan(1, 640, 640)
+p.frame_in.copy_(torch.randint(0, 256, p.frame_in.shape, dtype=torch.uint8, device="cuda"))
+for _ in range(4):
+    p.run_input(True)
+    p.run_net()
+torch.cuda.synchronize()
+print("conv launches per pass:", len(eng.net.conv_ops()))

@@ -283,9 +283,11 @@ class FramePipeline:
             self.step_device(True)
         self.join()
         if host:
-            zero = np.zeros((self.B, self.H, self.W, 3), np.uint8)
+            # (noise, not a constant image: a flat heat map is the worst case of the keypoint NMS -- every pixel a candidate, one
+            # priority chain over the whole frame -- and costs ~30 ms per frame in the single-CTA sweep)
+            noise = np.random.RandomState(0).randint(0, 256, (self.B, self.H, self.W, 3)).astype(np.uint8)
             for _ in range(self.nctx):
-                self.submit_host(zero)
+                self.submit_host(noise)
                 self.collect()
         torch.cuda.synchronize(self.eng.device)
         self.reset_tracking()
