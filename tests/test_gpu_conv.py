@@ -167,3 +167,29 @@ def test_split_k_layers_share_one_workspace():
     more = dict(B=2, H=48, W=80, Cin=384, Cout=384, k=1, s=1, split=12, tile=64)       # 60 x 6 tiles
     for c in (few, many, few, more, many):
         run_case(c, YP_FMT_F32X2, YP_ALGO_TCGEN05, shared_ws=ws)
+
+
+# Throughput plan (tile_n = YP_TILE_WIDE = -1): 3xTF32 layers with 128-byte store chunks run on conv_tc_drain_kernel (persistent,
+# accumulators drained into registers every 16 MMAs); the others take the chain-bounded wide plans of conv_tc_kernel.
+WIDE_CASES = [
+    dict(B=1, H=16, W=16, Cin=32, Cout=32, k=1, s=1),                              # one tile, one round
+    dict(B=1, H=80, W=80, Cin=128, Cout=128, k=1, s=1),                            # Nt = 128, 50 tiles
+    dict(B=2, H=20, W=20, Cin=64, Cout=64, k=3, s=1, res=True),                    # patch mode + residual
+    dict(B=1, H=20, W=20, Cin=256, Cout=256, k=3, s=1, res=True),                  # deep K (288 k-steps = 18 rounds), two N tiles
+    dict(B=1, H=40, W=40, Cin=128, Cout=128, k=3, s=2),                            # stride 2 (parity views)
+    dict(B=1, H=20, W=20, Cin=1024, Cout=512, k=1, s=1),                           # 32 k-blocks, four N tiles
+    dict(B=1, H=20, W=20, Cin=256, Cout=128, k=1, s=1, up=True),                   # two destinations (+ 2x upsample)
+    dict(B=1, H=8, W=8, Cin=512, Cout=256, k=1, s=1, act=False, plain=True),       # fp32 output
+    dict(B=8, H=80, W=80, Cin=128, Cout=128, k=3, s=1, res=True),                  # 400+ tiles: several tiles per persistent CTA
+    dict(B=6, H=96, W=160, Cin=64, Cout=96, k=3, s=2, act=False, nobias=True),     # Nt = 96, 360 tiles
+    dict(B=1, H=320, W=320, Cin=16, Cout=32, k=3, s=1),                            # the stem's geometry: 64-byte K rows, 856 tiles
+    dict(B=1, H=80, W=80, Cin=128, Cout=80, k=1, s=1, act=False, plain=True, nobias=True),   # 64-byte store chunks: not drained (conv_tc_kernel)
+    dict(B=1, H=80, W=80, Cin=128, Cout=128, k=3, s=1, act=False, l2=True, plain=True),      # L2-norm head: not drained
+]
+
+
+@pytest.mark.parametrize("ci", range(len(WIDE_CASES)))
+def test_conv_wide_plan(ci):
+    c = dict(WIDE_CASES[ci], tile=-1)
+    err = run_case(c, YP_FMT_F32X2, YP_ALGO_TCGEN05)
+    print(f"wide plan case {ci}: rel err {err:.2e}")

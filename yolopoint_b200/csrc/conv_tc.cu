@@ -72,6 +72,7 @@ struct ConvArgs {
   const void* res_base;
   long long res_pix, res_plane;
   int n_out_maps, out_planes, out_row_bytes, staging_set_bytes, out_fmt;
+  int drain_units;   // conv_tc_drain_kernel (persist == 2): pipeline units per accumulation round
   int persist, n_tiles_n, tiles_total, stg_off, buf_cols;   // persistent variant: tiles per CTA loop, staging offset, TMEM columns per accumulator buffer
   int ablate;      // debug (YP_CONV_ABLATE): 1 = issue no MMAs, 2 = issue no TMA loads (timing experiments; results are garbage)
   long long* dbg;  // optional timeline buffer (yp_debug_conv_timeline); CTA (0,0) records clock64 stamps
@@ -980,6 +981,330 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
 }
 
 // ---------------------------------------------------------------------------------------------
+// 3xTF32 variant with DRAINED accumulators (a.persist == 2; the throughput plan, YP_TILE_WIDE).
+//
+// The tensor core adds into its fp32 accumulator with truncation, so the error of a tile grows with the number of MMAs chained on one
+// accumulator; conv_tile() bounds the chains by rotating over many TMEM accumulators, which caps the N tile (TMEM columns) and forces
+// split-K on deep layers.  Here the chains are bounded at ANY tile width: the main product A_hi x W_hi accumulates for one ROUND
+// (a.drain_units pipeline units = ~16 MMAs) into one of two TMEM buffers; the epilogue warps -- idle during the main loop anyway --
+// then pull the buffer into registers (tcgen05.ld) and add it to their running fp32 sums with round-to-nearest, while the issuer fills
+// the other buffer.  The two cross terms (A_lo x W_hi, A_hi x W_lo; ~2^-11 of the result, their truncation error is negligible)
+// accumulate over the whole K in a third accumulator that is read once per tile.  TMEM: main 2 x Nt + cross 2 x Nt columns
+// (the cross accumulator alternates between two buffers per TILE), Nt <= 128.
+//
+// Like conv_tc_persist_kernel the CTA is persistent (one per SM, tiles t = blockIdx.x, +gridDim.x, ...): warp 0 = TMA producer,
+// warp 1 = main issuer, warp 2 = cross issuer, warps 4-11 = drain + epilogue (two per TMEM lane quarter; the warp pair splits the
+// 16-column units of the tile by parity, so a thread keeps Nt / 2 running sums in registers).  The epilogue of tile i (bias / SiLU /
+// residual / (hi, lo) split / staging / TMA stores) overlaps the first rounds of tile i+1.
+// ---------------------------------------------------------------------------------------------
+template <int OUT_FMT>
+__global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_drain_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int per_img = a.tiles_w * a.tiles_h;
+  const int num_kb = a.patch ? a.kb_per_tap : a.n_taps * a.kb_per_tap;
+  const int units_per_tile = a.patch ? 9 * num_kb : num_kb;      // pipeline units (one weight stage each) of a tile
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const uint32_t bar_base = smem_base + a.bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+  auto accf_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 4 + s); };
+  auto acce_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 6 + s); };
+  auto crossf_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 8 + s); };
+  auto crosse_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 10 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 12);
+
+  if (warp == 0 && lane == 0) {
+    const int n_in = a.stride == 2 ? 4 : 1;
+    for (int i = 0; i < n_in; ++i) tma_prefetch_desc(&maps.in[i]);
+    tma_prefetch_desc(&maps.w);
+    for (int i = 0; i < a.n_out_maps; ++i) tma_prefetch_desc(&maps.out[i]);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 2); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 2);
+      mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 8);
+      mbar_init(crossf_bar(s), 1); mbar_init(crosse_bar(s), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  auto decode = [&](int t, int& b, int& h0, int& w0, int& n0) {
+    const int nt = t % a.n_tiles_n, m = t / a.n_tiles_n;
+    b = m / per_img;
+    const int trem = m - b * per_img;
+    const int th = trem / a.tiles_w, tw = trem - th * a.tiles_w;
+    h0 = th * a.Ht; w0 = tw * a.Wt; n0 = nt * a.Nt;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (as in conv_tc_persist_kernel) =====================
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    int s = 0, ph = 0, sa = 0, pha = 0;
+    for (int t = blockIdx.x; t < a.tiles_total; t += gridDim.x) {
+      int b, h0, w0, n0;
+      decode(t, b, h0, w0, n0);
+      if (a.patch) {
+        for (int cb = 0; cb < num_kb; ++cb) {
+          mbar_wait(aempty_bar(sa), pha ^ 1);
+          const uint32_t sta = smem_base + sa * a.a_stage_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(afull_bar(sa), a.a_tx);
+            tma_load_5d(sta, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 0);
+            tma_load_5d(sta + a.a_plane_off, &maps.in[0], afull_bar(sa), cb * a.ck_elems, w0 - 1, h0 - 1, b, 1);
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(s), a.b_tx);
+              tma_load_3d(smem_base + a.b_ring_off + s * a.b_stage_bytes, &maps.w, full_bar(s), (tap * a.kb_per_tap + cb) * a.ck_elems, n0, 0);
+            }
+            if (++s == a.b_stages) { s = 0; ph ^= 1; }
+          }
+          if (++sa == 2) { sa = 0; pha ^= 1; }
+        }
+      } else {
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          int map = 0, dh = 0, dw = 0;
+          if (a.ksize == 3) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            if (a.stride == 1) { dh = kh - 1; dw = kw - 1; }
+            else { map = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1); dh = (kh == 0) ? -1 : 0; dw = (kw == 0) ? -1 : 0; }
+          }
+          const uint32_t st = smem_base + s * a.stage_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(s), a.tx_bytes);
+            tma_load_5d(st, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 0);
+            if (!a.a_split) tma_load_5d(st + a.a_plane_off, &maps.in[map], full_bar(s), cb * a.ck_elems, w0 + dw, h0 + dh, b, 1);
+            tma_load_3d(st + a.a_region_bytes, &maps.w, full_bar(s), kb * a.ck_elems, n0, 0);
+          }
+          if (++cb == a.kb_per_tap) { cb = 0; ++tap; }
+          if (++s == a.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if ((warp == 1 || warp == 2) && elect_one()) {
+    // ===================== MMA issuers: warp 1 = main product (rounds, two TMEM buffers), warp 2 = both cross terms =====================
+    const bool is_main = warp == 1;
+    const int ksteps = a.ck_bytes / 32;
+    const uint32_t b_plane = a.Nt * a.ck_bytes;
+    const uint32_t idesc = a.iss_idesc[0];
+    const uint32_t dhi = smem_desc_hi(a.ck_bytes);
+    const uint32_t main_col = tmem_base, cross_col = tmem_base + 2 * a.Nt;
+    int s = 0, ph = 0, sa = 0, pha = 0, tile_it = 0;
+    int rc = 0;          // rounds issued so far (main issuer); buffer = rc & 1
+    for (int t = blockIdx.x; t < a.tiles_total; t += gridDim.x, ++tile_it) {
+      const int tb = tile_it & 1;
+      uint32_t acc = 0;                       // accumulate flag of the next MMA of this issuer's current accumulator
+      int u_in_round = 0;
+      if (!is_main) {
+        if (tile_it >= 2) { mbar_wait(crosse_bar(tb), ((tile_it >> 1) - 1) & 1); tc_fence_after(); }
+      }
+      auto begin_round = [&]() {
+        const int buf = rc & 1;
+        if (rc >= 2) { mbar_wait(acce_bar(buf), ((rc >> 1) - 1) & 1); tc_fence_after(); }
+        acc = 0;
+      };
+      auto issue_unit = [&](uint32_t sa_addr, uint32_t sb_addr, bool last_unit) {
+        if (is_main) {
+          if (u_in_round == 0) begin_round();
+          const uint32_t col = main_col + (rc & 1) * a.Nt;
+          const uint32_t al = smem_desc_lo(sa_addr), bl = smem_desc_lo(sb_addr);
+          for (int k = 0; k < ksteps; ++k) { umma32_one<true>(col, al + 2 * k, bl + 2 * k, dhi, idesc, acc); acc = 1u; }
+          if (++u_in_round == a.drain_units || last_unit) { umma_commit(accf_bar(rc & 1)); ++rc; u_in_round = 0; }
+        } else {
+          const uint32_t col = cross_col + tb * a.Nt;
+          const uint32_t al_hi = smem_desc_lo(sa_addr), al_lo = smem_desc_lo(sa_addr + a.a_plane_off);
+          const uint32_t bl_hi = smem_desc_lo(sb_addr), bl_lo = smem_desc_lo(sb_addr + b_plane);
+          for (int k = 0; k < ksteps; ++k) {
+            umma32_one<true>(col, al_lo + 2 * k, bl_hi + 2 * k, dhi, idesc, acc);
+            umma32_one<true>(col, al_hi + 2 * k, bl_lo + 2 * k, dhi, idesc, 1u);
+            acc = 1u;
+          }
+          if (last_unit) umma_commit(crossf_bar(tb));
+        }
+      };
+      int unit = 0;
+      if (a.patch) {
+        for (int cb = 0; cb < num_kb; ++cb) {
+          mbar_wait(afull_bar(sa), pha);
+          tc_fence_after();
+          const uint32_t pa = smem_base + sa * a.a_stage_bytes;
+          uint32_t shift = 0;
+          for (int tap = 0; tap < 9; ++tap, ++unit) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            issue_unit(pa + shift, smem_base + a.b_ring_off + s * a.b_stage_bytes, unit + 1 == units_per_tile);
+            umma_commit(empty_bar(s));
+            if (++s == a.b_stages) { s = 0; ph ^= 1; }
+            shift += (tap % 3 == 2) ? (a.Wp - 2) * a.ck_bytes : a.ck_bytes;
+          }
+          umma_commit(aempty_bar(sa));
+          if (++sa == 2) { sa = 0; pha ^= 1; }
+        }
+      } else {
+        for (int kb = 0; kb < num_kb; ++kb, ++unit) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sA = smem_base + s * a.stage_bytes;
+          issue_unit(sA, sA + a.a_region_bytes, unit + 1 == units_per_tile);
+          umma_commit(empty_bar(s));
+          if (++s == a.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== drain + epilogue (8 warps: two per TMEM lane quarter, units split by parity) =====================
+    using TO = typename OutT<OUT_FMT>::type;
+    constexpr int CH = 32;                                   // UNITS = 2: one staging row = 32 fp32 columns = 128 bytes
+    constexpr int ROWB = CH * (int)sizeof(TO);
+    const int q = warp & 3;
+    const int hf = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int rdiv = a.patch ? a.Wp : a.Wt;
+    const int rh = row / rdiv, rw = row - rh * rdiv;
+    const bool in_tile = rh < a.Ht && rw < a.Wt;
+    const int srow = in_tile ? rh * a.Wt + rw : 127;
+    const bool et0 = (threadIdx.x == 128);
+    const int n_chunks = a.Nt / CH;                          // <= 4; this thread owns unit 2 c + hf of chunk c
+    const int rounds_per_tile = (units_per_tile + a.drain_units - 1) / a.drain_units;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    int tile_it = 0, cg = 0, rc = 0;
+    for (int t = blockIdx.x; t < a.tiles_total; t += gridDim.x, ++tile_it) {
+      int b, h0, w0, n0;
+      decode(t, b, h0, w0, n0);
+      const int tb = tile_it & 1;
+      float sums[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sums[c][i] = 0.0f;
+      // ---- drain the rounds of this tile
+      for (int r = 0; r < rounds_per_tile; ++r, ++rc) {
+        const int buf = rc & 1;
+        mbar_wait(accf_bar(buf), (rc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t base = tmem_base + lane_off + buf * a.Nt + hf * 16;
+#pragma unroll
+        for (int c0 = 0; c0 < 4; c0 += 2) {      // two units in flight (register budget: 64 running sums + 32 in flight)
+          if (c0 < n_chunks) {
+            float tv[2][16];
+            tmem_ld16(base + c0 * CH, tv[0]);
+            if (c0 + 1 < n_chunks) tmem_ld16(base + (c0 + 1) * CH, tv[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sums[c0][i] += tv[0][i];
+            if (c0 + 1 < n_chunks) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sums[c0 + 1][i] += tv[1][i];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce_bar(buf));
+      }
+      // ---- cross terms of the tile
+      mbar_wait(crossf_bar(tb), (tile_it >> 1) & 1);
+      tc_fence_after();
+      {
+        const uint32_t base = tmem_base + lane_off + 2 * a.Nt + tb * a.Nt + hf * 16;
+#pragma unroll
+        for (int c0 = 0; c0 < 4; c0 += 2) {
+          if (c0 < n_chunks) {
+            float tv[2][16];
+            tmem_ld16(base + c0 * CH, tv[0]);
+            if (c0 + 1 < n_chunks) tmem_ld16(base + (c0 + 1) * CH, tv[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sums[c0][i] += tv[0][i];
+            if (c0 + 1 < n_chunks) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sums[c0 + 1][i] += tv[1][i];
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(crosse_bar(tb));
+      }
+      // ---- epilogue: bias, SiLU, residual, operand split, staging, TMA stores
+      const int oh = h0 + rh, ow = w0 + rw;
+      const bool valid = in_tile && oh < a.Ho && ow < a.Wo;
+      const bool has_res = a.res_base != nullptr && valid;
+      const long long res_off = ((static_cast<long long>(b) * a.Ho + oh) * a.Wo + ow) * a.res_pix + n0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < n_chunks) {
+          const uint32_t stg = smem_base + a.stg_off + (cg & 1) * a.staging_set_bytes;
+          asm volatile("bar.sync 2, 256;" ::: "memory");      // staging set (cg & 1) was drained (et0 waited for the stores of chunk cg-2)
+          const int col0 = c * CH + hf * 16;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = sums[c][i] + (a.bias ? __ldg(a.bias + n0 + col0 + i) : 0.0f);
+          if (a.act == YP_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = silu_fast(v[i]);
+          }
+          if (has_res) {
+            const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + col0);
+            const float4* pl = reinterpret_cast<const float4*>(static_cast<const float*>(a.res_base) + res_off + a.res_plane + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 hi = __ldg(p + j);
+              float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (OUT_FMT == YP_FMT_F32X2) lo = __ldg(pl + j);
+              v[j * 4] += hi.x + lo.x; v[j * 4 + 1] += hi.y + lo.y; v[j * 4 + 2] += hi.z + lo.z; v[j * 4 + 3] += hi.w + lo.w;
+            }
+          }
+          if (in_tile) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (OUT_FMT == YP_FMT_F32X2) {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { hi[e] = tf32_round(v[j * 4 + e]); lo[e] = tf32_round(v[j * 4 + e] - hi[e]); }
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, hf * 4 + j, ROWB)), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg + 128 * ROWB, srow, hf * 4 + j, ROWB)), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+              } else {
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(swz_addr(stg, srow, hf * 4 + j, ROWB)), "f"(v[j * 4]), "f"(v[j * 4 + 1]), "f"(v[j * 4 + 2]), "f"(v[j * 4 + 3]) : "memory");
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (et0) {
+            for (int m = 0; m < a.n_out_maps; ++m)
+              for (int pl = 0; pl < a.out_planes; ++pl)
+                tma_store_5d(&maps.out[m], stg + pl * 128 * ROWB, n0 + c * CH, w0, h0, b, pl);
+            tma_store_commit();
+            tma_store_wait_read<1>();
+          }
+          ++cg;
+        }
+      }
+    }
+    if (et0) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Layer chain: one persistent kernel for a segment of the network (yp_conv_chain_*, see the header).  Batch-1 inference is a chain
 // of ~60 small dependent layers; launched one by one each pays launch latency, TMEM allocation, descriptor prefetch and the
 // grid-completion gap, and the GPU idles while the slowest CTA of a layer finishes.  Here one CTA per SM walks the operations in
@@ -1176,6 +1501,25 @@ int launch_persist(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t sm
   return YP_OK;
 }
 
+template <int OUT_FMT>
+int launch_drain(const ConvMaps& maps, const ConvArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = conv_tc_drain_kernel<OUT_FMT>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    YP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  static const bool use_pdl = getenv("YP_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kPersistThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  YP_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, a));
+  return YP_OK;
+}
+
 }  // namespace
 
 void set_conv_timeline(long long* p) { g_timeline = p; }
@@ -1302,9 +1646,19 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   const int nsm = sm_count();
   int Nt = 0;
   int split_req = d.split_k;           // 0 = heuristic, 1 = never, n = n slices
+  // Throughput plan on the drained-accumulator kernel (YP_CONV_DRAIN=0 switches it off): 3xTF32, 128-byte store chunks, no L2-norm /
+  // row-min epilogue, no custom tap list, not inside a layer chain.
+  static const bool allow_drain = getenv("YP_CONV_DRAIN") == nullptr || atoi(getenv("YP_CONV_DRAIN")) != 0;
+  const bool drain = allow_drain && d.tile_n == YP_TILE_WIDE && tf32 && g_chain_budget == 0 && d.ksize != 0 && chunk_elems == 32 && d.cout % 32 == 0 &&
+                     !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && (out_fmt == YP_FMT_F32X2 || out_fmt == YP_FMT_F32);
   if (d.epilogue & YP_EPI_L2NORM) {
     YP_REQUIRE(d.cout <= 256, YP_ERR_SHAPE, "conv: L2-norm epilogue needs Cout <= 256 (got %d)", d.cout);
     Nt = d.cout;
+  } else if (drain) {
+    // drained accumulators (conv_tc_drain_kernel): chains are bounded at any width -> the widest tile, K never split
+    for (int n = 128; n >= 32; n -= 32)
+      if (d.cout % n == 0) { Nt = n; break; }
+    split_req = 1;
   } else if (d.tile_n == YP_TILE_WIDE) {
     // Throughput plan: the widest N tile (fewest re-reads of the activation tile, fewest MMAs per FLOP) whose accumulator plan still
     // keeps the fp32-grade accuracy of the 3xTF32 mode.  The tensor core adds into an fp32 accumulator with truncation, so the error
@@ -1385,8 +1739,8 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   const bool persist = allow_persist && !chain && !tf32 && S == 1 && !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && out_fmt != YP_FMT_F32X2 &&
                        static_cast<long long>(m_tiles) * n_tiles > (getenv("YP_CONV_PERSIST_MIN") ? atoll(getenv("YP_CONV_PERSIST_MIN")) : 2LL * nsm);
   static const bool force_dense = getenv("YP_CONV_FORCE_DENSE") != nullptr && atoi(getenv("YP_CONV_FORCE_DENSE")) != 0;
-  const bool unstacked = d.tile_n == YP_TILE_WIDE && m_tiles < nsm && tf32 && Nt == 128 && !(d.epilogue & YP_EPI_L2NORM);   // needs all 512 TMEM columns
-  const bool dense = !chain && !unstacked && ((allow_dense && (force_dense || static_cast<long long>(m_tiles) * n_tiles * S > nsm)) || persist);   // persist: 256 columns per accumulator buffer
+  const bool unstacked = !drain && d.tile_n == YP_TILE_WIDE && m_tiles < nsm && tf32 && Nt == 128 && !(d.epilogue & YP_EPI_L2NORM);   // needs all 512 TMEM columns
+  const bool dense = !chain && !unstacked && !drain && ((allow_dense && (force_dense || static_cast<long long>(m_tiles) * n_tiles * S > nsm)) || persist);   // persist: 256 columns per accumulator buffer
   const int tmem_limit = dense ? 256 : 512;
 
   // ---- accumulator / issuer plan (see the kernel comment)
@@ -1395,7 +1749,15 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     return (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
   };
   int cols = 0;
-  if (unstacked) {
+  if (drain) {
+    // conv_tc_drain_kernel: main product in two round buffers, both cross terms in one accumulator per tile (two tile buffers)
+    a.n_iss = 2;
+    a.iss_idesc[0] = idesc(Nt);
+    a.n_src = 0;
+    cols = 4 * Nt;
+    static const int drain_steps = getenv("YP_CONV_DRAIN_STEPS") ? atoi(getenv("YP_CONV_DRAIN_STEPS")) : 16;   // MMAs chained per round
+    a.drain_units = std::max(1, drain_steps / (a.ck_bytes / 32));
+  } else if (unstacked) {
     // Wide throughput tile: the main product A_hi x W_hi rotates over three accumulators (issuer 0), both cross terms go into a fourth
     // (issuer 1, two MMAs per k-step; their partial sums are ~2^-11 of the result, so their truncation error is negligible).
     const int n_p = std::min(3, std::max(1, mmas_min));
@@ -1487,7 +1849,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   a.stage_bytes = a.a_region_bytes + b_region_bytes;
   // TMA counts the bytes of the boxes actually written: Ht*Wt (<= 128) rows per A plane, Nt rows per B plane
   a.tx_bytes = a.in_planes * (rows * a.ck_bytes + Nt * a.ck_bytes);
-  int budget = chain ? g_chain_budget : (persist ? 198 * 1024 - 2 * a.staging_set_bytes : (dense ? 104 * 1024 : 200 * 1024));
+  int budget = chain ? g_chain_budget : ((persist || drain) ? 198 * 1024 - 2 * a.staging_set_bytes : (dense ? 104 * 1024 : 200 * 1024));
   int region = 0;
   if (a.patch) {
     a.a_stage_bytes = a.in_planes * rows_alloc * a.ck_bytes;
@@ -1495,7 +1857,10 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     a.b_stage_bytes = b_region_bytes;
     a.b_tx = b_region_bytes;
     a.b_ring_off = 2 * a.a_stage_bytes;
-    if (2 * a.a_stage_bytes + 2 * a.b_stage_bytes > budget) budget = 200 * 1024;
+    if (2 * a.a_stage_bytes + 2 * a.b_stage_bytes > budget) {
+      if (drain) { *patch_no_fit = true; return YP_ERR_SHAPE; }   // the staging sets live beside the pipeline: re-plan with per-tap loads
+      budget = 200 * 1024;
+    }
     int bs = (budget - 2 * a.a_stage_bytes) / a.b_stage_bytes;
     if (bs > kMaxStages) bs = kMaxStages;
     if (bs < 2) { *patch_no_fit = true; return YP_ERR_SHAPE; }   // caller re-plans with per-tap loads
@@ -1503,7 +1868,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     a.stages = bs;
     region = 2 * a.a_stage_bytes + bs * a.b_stage_bytes;
   } else {
-    if (a.stage_bytes * 2 > budget) budget = 200 * 1024;   // keep at least two stages
+    if (a.stage_bytes * 2 > budget && !drain) budget = 200 * 1024;   // keep at least two stages
     int stages = budget / a.stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > a.kb_per_split) stages = a.kb_per_split;
@@ -1517,10 +1882,10 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   // whole register file of its SM, so the next layer's CTAs can no longer start under this layer's tail (programmatic dependent launch).
   // Off unless YP_CONV_WIDE=1.
   static const bool allow_wide = getenv("YP_CONV_WIDE") != nullptr && atoi(getenv("YP_CONV_WIDE")) != 0;
-  P->nt = chain ? kChainThreads : ((allow_wide && !dense && !persist) ? 512 : 256);
+  P->nt = chain ? kChainThreads : (drain ? kPersistThreads : ((allow_wide && !dense && !persist) ? 512 : 256));
   const int n_groups = P->nt / 128;
   const int staging_sets = 2 * (n_groups > P->units ? n_groups / P->units : 1);
-  if (persist) {
+  if (persist || drain) {
     // the staging sets may not alias the pipeline stages: the next tile's K loop runs under this tile's epilogue
     region = (region + 1023) & ~1023;
     a.stg_off = region;
@@ -1528,10 +1893,15 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   } else if (region < staging_sets * a.staging_set_bytes) region = staging_sets * a.staging_set_bytes;
   region = (region + 1023) & ~1023;
   a.bar_off = region;
-  P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 10) + Nt * sizeof(float) + 16;
+  P->smem = 1024 /*alignment slack*/ + region + 8 * (2 * kMaxStages + 14) + Nt * sizeof(float) + 16;
   YP_REQUIRE(P->smem <= 227 * 1024, YP_ERR_SHAPE, "conv: needs %zu bytes of shared memory", P->smem);
   P->grid = dim3(m_tiles, n_tiles, S);
-  a.persist = persist ? 1 : 0;
+  a.persist = persist ? 1 : (drain ? 2 : 0);
+  if (drain) {
+    a.n_tiles_n = n_tiles;
+    a.tiles_total = m_tiles * n_tiles;
+    P->grid = dim3(std::min(a.tiles_total, nsm), 1, 1);
+  }
   if (persist) {
     YP_REQUIRE(a.n_src <= 2 && cols <= 256, YP_ERR_SHAPE, "conv(persist): accumulator plan needs %d sources / %d columns", a.n_src, cols);
     a.n_tiles_n = n_tiles;
@@ -1648,6 +2018,7 @@ int conv_tc_forward(const YpConvDesc& d, cudaStream_t st) {
   const size_t smem = P.smem;
   const int units = P.units;
   const bool tf32 = P.tf32;
+  if (a.persist == 2) return out_fmt == YP_FMT_F32X2 ? launch_drain<YP_FMT_F32X2>(maps, a, grid, smem, st) : launch_drain<YP_FMT_F32>(maps, a, grid, smem, st);
 #define YP_DISPATCH_P(FMT, U) return launch_persist<FMT, U, false>(maps, a, grid, smem, st)
   if (a.persist) {
     if (out_fmt == YP_FMT_BF16) { if (units == 4) YP_DISPATCH_P(YP_FMT_BF16, 4); if (units == 2) YP_DISPATCH_P(YP_FMT_BF16, 2); if (units == 1) YP_DISPATCH_P(YP_FMT_BF16, 1); }
