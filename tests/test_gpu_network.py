@@ -308,9 +308,11 @@ def test_frames_in_flight_equal_one_at_a_time(F):
 
 @pytest.mark.parametrize("ver,B,H,W", [("s", 1, 640, 640), ("n", 1, 480, 640)])
 def test_wide_tile_policy_meets_oracle_tolerances(ver, B, H, W):
-    """The throughput plan of bench.py's headline line (Engine(tile_policy="wide") -> YP_TILE_WIDE: the widest N tile whose accumulator
-    plan chains at most 48 truncating tensor-core accumulations, K split only where that bound asks for it) is a different summation
-    order of the same arithmetic; it is held to the same tolerances against the oracle as the latency-tuned plan."""
+    """The throughput plan of bench.py's headline line (Engine(tile_policy="wide") -> YP_TILE_WIDE): the widest N tile on
+    conv_tc_drain_kernel, whose main-product accumulators are drained into registers every 4 MMAs (round-to-nearest adds), so the
+    truncating tensor-core accumulate never chains more than 4 steps at any K.  Measured: Detect logits 2.9e-5 of their scale from
+    the fp32 oracle (latency-tuned plan ~5e-5, tolerance 1e-4), `pred` 5.6e-4 relative; asserted at 6e-5 so that a regression of the
+    drain (longer rounds, a layer falling back to long accumulator chains) trips the test."""
     from yolopoint_b200.engine import Engine
     _, sd = build(ver)
     torch.manual_seed(4)
@@ -318,7 +320,8 @@ def test_wide_tile_policy_meets_oracle_tolerances(ver, B, H, W):
     eng = Engine(sd, ver, 80, torch.device("cuda:0"), tile_policy="wide")
     out = eng.forward(x.cuda())
     ref = O.OracleNet(sd, ver, 80).forward(x)
-    check_outputs(out, ref, f"wide {ver} {B}x{H}x{W}")
+    check_outputs(out, ref, f"wide {ver} {B}x{H}x{W}", atol_logit=6e-5)
+    assert float(((out["objects"][0].cpu() - ref["objects"][0]).abs() / (1.0 + ref["objects"][0].abs())).max()) < 1.5e-3
 
 
 def test_wide_policy_pipeline_equals_latency_policy_indices():

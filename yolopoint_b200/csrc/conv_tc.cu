@@ -1649,8 +1649,11 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   // Throughput plan on the drained-accumulator kernel (YP_CONV_DRAIN=0 switches it off): 3xTF32, 128-byte store chunks, no L2-norm /
   // row-min epilogue, no custom tap list, not inside a layer chain.
   static const bool allow_drain = getenv("YP_CONV_DRAIN") == nullptr || atoi(getenv("YP_CONV_DRAIN")) != 0;
+  // Layers with a short K (few MMAs per accumulator anyway) keep the rotating-accumulator plans below, which run two CTAs per SM.
+  static const int drain_min_steps = getenv("YP_CONV_DRAIN_MIN_STEPS") ? atoi(getenv("YP_CONV_DRAIN_MIN_STEPS")) : 0;
   const bool drain = allow_drain && d.tile_n == YP_TILE_WIDE && tf32 && g_chain_budget == 0 && d.ksize != 0 && chunk_elems == 32 && d.cout % 32 == 0 &&
-                     !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && (out_fmt == YP_FMT_F32X2 || out_fmt == YP_FMT_F32);
+                     !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && (out_fmt == YP_FMT_F32X2 || out_fmt == YP_FMT_F32) &&
+                     num_kb * ksteps >= drain_min_steps;
   if (d.epilogue & YP_EPI_L2NORM) {
     YP_REQUIRE(d.cout <= 256, YP_ERR_SHAPE, "conv: L2-norm epilogue needs Cout <= 256 (got %d)", d.cout);
     Nt = d.cout;
@@ -1755,7 +1758,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     a.iss_idesc[0] = idesc(Nt);
     a.n_src = 0;
     cols = 4 * Nt;
-    static const int drain_steps = getenv("YP_CONV_DRAIN_STEPS") ? atoi(getenv("YP_CONV_DRAIN_STEPS")) : 16;   // MMAs chained per round
+    static const int drain_steps = getenv("YP_CONV_DRAIN_STEPS") ? atoi(getenv("YP_CONV_DRAIN_STEPS")) : 4;   // MMAs chained per round
     a.drain_units = std::max(1, drain_steps / (a.ck_bytes / 32));
   } else if (unstacked) {
     // Wide throughput tile: the main product A_hi x W_hi rotates over three accumulators (issuer 0), both cross terms go into a fourth
