@@ -990,7 +990,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
 // then pull the buffer into registers (tcgen05.ld) and add it to their running fp32 sums with round-to-nearest, while the issuer fills
 // the other buffer.  The two cross terms (A_lo x W_hi, A_hi x W_lo; ~2^-11 of the result, their truncation error is negligible)
 // accumulate over the whole K in a third accumulator that is read once per tile.  TMEM: main 2 x Nt + cross 2 x Nt columns
-// (the cross accumulator alternates between two buffers per TILE), Nt <= 128.
+// (the cross accumulator alternates between two buffers per TILE), Nt <= 128; for Nt <= 64 the round buffers are 2 Nt wide and also
+// take the A_hi x W_lo cross term (one stacked MMA of N = 2 Nt, see the issuer).
 //
 // Like conv_tc_persist_kernel the CTA is persistent (one per SM, tiles t = blockIdx.x, +gridDim.x, ...): warp 0 = TMA producer,
 // warp 1 = main issuer, warp 2 = cross issuer, warps 4-11 = drain + epilogue (two per TMEM lane quarter; the warp pair splits the
@@ -1100,9 +1101,14 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_drain_kernel(const
     const bool is_main = warp == 1;
     const int ksteps = a.ck_bytes / 32;
     const uint32_t b_plane = a.Nt * a.ck_bytes;
-    const uint32_t idesc = a.iss_idesc[0];
+    // a.buf_cols = columns of one round buffer: Nt (main product only; both cross terms go to the cross accumulator) or, for
+    // Nt <= 64, 2 Nt: the two weight planes are adjacent in shared memory, so A_hi x [W_hi; W_lo] is ONE MMA of N = 2 Nt that yields
+    // the main product and one cross term side by side (both are drained into the same running sums), and the cross issuer is left
+    // with A_lo x W_hi -- two MMAs per k-step instead of three (small MMAs cost ~64 cycles whatever their N).
+    const bool stacked = a.buf_cols == 2 * a.Nt;
+    const uint32_t idesc = a.iss_idesc[is_main ? 0 : 1];
     const uint32_t dhi = smem_desc_hi(a.ck_bytes);
-    const uint32_t main_col = tmem_base, cross_col = tmem_base + 2 * a.Nt;
+    const uint32_t main_col = tmem_base, cross_col = tmem_base + 2 * a.buf_cols;
     int s = 0, ph = 0, sa = 0, pha = 0, tile_it = 0;
     int rc = 0;          // rounds issued so far (main issuer); buffer = rc & 1
     for (int t = blockIdx.x; t < a.tiles_total; t += gridDim.x, ++tile_it) {
@@ -1120,7 +1126,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_drain_kernel(const
       auto issue_unit = [&](uint32_t sa_addr, uint32_t sb_addr, bool last_unit) {
         if (is_main) {
           if (u_in_round == 0) begin_round();
-          const uint32_t col = main_col + (rc & 1) * a.Nt;
+          const uint32_t col = main_col + (rc & 1) * a.buf_cols;
           const uint32_t al = smem_desc_lo(sa_addr), bl = smem_desc_lo(sb_addr);
           for (int k = 0; k < ksteps; ++k) { umma32_one<true>(col, al + 2 * k, bl + 2 * k, dhi, idesc, acc); acc = 1u; }
           if (++u_in_round == a.drain_units || last_unit) { umma_commit(accf_bar(rc & 1)); ++rc; u_in_round = 0; }
@@ -1130,7 +1136,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_drain_kernel(const
           const uint32_t bl_hi = smem_desc_lo(sb_addr), bl_lo = smem_desc_lo(sb_addr + b_plane);
           for (int k = 0; k < ksteps; ++k) {
             umma32_one<true>(col, al_lo + 2 * k, bl_hi + 2 * k, dhi, idesc, acc);
-            umma32_one<true>(col, al_hi + 2 * k, bl_lo + 2 * k, dhi, idesc, 1u);
+            if (!stacked) umma32_one<true>(col, al_hi + 2 * k, bl_lo + 2 * k, dhi, idesc, 1u);
             acc = 1u;
           }
           if (last_unit) umma_commit(crossf_bar(tb));
@@ -1197,19 +1203,22 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_drain_kernel(const
         const int buf = rc & 1;
         mbar_wait(accf_bar(buf), (rc >> 1) & 1);
         tc_fence_after();
-        const uint32_t base = tmem_base + lane_off + buf * a.Nt + hf * 16;
+        const uint32_t base = tmem_base + lane_off + buf * a.buf_cols + hf * 16;
+        const int halves = a.buf_cols == 2 * a.Nt ? 2 : 1;      // stacked round buffer: [main | A_hi x W_lo], both added to the same sums
+        for (int hv = 0; hv < halves; ++hv) {
 #pragma unroll
-        for (int c0 = 0; c0 < 4; c0 += 2) {      // two units in flight (register budget: 64 running sums + 32 in flight)
-          if (c0 < n_chunks) {
-            float tv[2][16];
-            tmem_ld16(base + c0 * CH, tv[0]);
-            if (c0 + 1 < n_chunks) tmem_ld16(base + (c0 + 1) * CH, tv[1]);
-            tmem_ld_wait();
+          for (int c0 = 0; c0 < 4; c0 += 2) {      // two units in flight (register budget: 64 running sums + 32 in flight)
+            if (c0 < n_chunks) {
+              float tv[2][16];
+              tmem_ld16(base + hv * a.Nt + c0 * CH, tv[0]);
+              if (c0 + 1 < n_chunks) tmem_ld16(base + hv * a.Nt + (c0 + 1) * CH, tv[1]);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sums[c0][i] += tv[0][i];
-            if (c0 + 1 < n_chunks) {
+              for (int i = 0; i < 16; ++i) sums[c0][i] += tv[0][i];
+              if (c0 + 1 < n_chunks) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sums[c0 + 1][i] += tv[1][i];
+                for (int i = 0; i < 16; ++i) sums[c0 + 1][i] += tv[1][i];
+              }
             }
           }
         }
@@ -1221,7 +1230,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_drain_kernel(const
       mbar_wait(crossf_bar(tb), (tile_it >> 1) & 1);
       tc_fence_after();
       {
-        const uint32_t base = tmem_base + lane_off + 2 * a.Nt + tb * a.Nt + hf * 16;
+        const uint32_t base = tmem_base + lane_off + 2 * a.buf_cols + tb * a.Nt + hf * 16;
 #pragma unroll
         for (int c0 = 0; c0 < 4; c0 += 2) {
           if (c0 < n_chunks) {
@@ -1755,9 +1764,12 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   if (drain) {
     // conv_tc_drain_kernel: main product in two round buffers, both cross terms in one accumulator per tile (two tile buffers)
     a.n_iss = 2;
-    a.iss_idesc[0] = idesc(Nt);
+    static const bool drain_stack = getenv("YP_CONV_DRAIN_STACK") == nullptr || atoi(getenv("YP_CONV_DRAIN_STACK")) != 0;
+    a.buf_cols = (drain_stack && Nt <= 64) ? 2 * Nt : Nt;      // stacked round buffers need 6 Nt <= 512 TMEM columns
+    a.iss_idesc[0] = idesc(a.buf_cols);
+    a.iss_idesc[1] = idesc(Nt);
     a.n_src = 0;
-    cols = 4 * Nt;
+    cols = 2 * a.buf_cols + 2 * Nt;
     static const int drain_steps = getenv("YP_CONV_DRAIN_STEPS") ? atoi(getenv("YP_CONV_DRAIN_STEPS")) : 4;   // MMAs chained per round
     a.drain_units = std::max(1, drain_steps / (a.ck_bytes / 32));
   } else if (unstacked) {
