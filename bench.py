@@ -320,6 +320,12 @@ def main():
     NS = max(1, args.streams)
     frame_bytes = per_gpu * H * W * 3
     n_pool = max(8, int(160e6 // frame_bytes) + 1)
+    # One step = one pipeline window = `frames_in_flight` consecutive frame batches of the camera stream (each its own batch-1 pass):
+    # the contract's barrier + synchronize in front of the timed region empties the pipeline, so a step of a single frame would time
+    # the fill / drain ramp of the window (K = 20: 27 frame slots for 20 frames), not the stream.
+    FPS = args.in_flight
+    config["frames_per_gpu_per_step"] = per_gpu * FPS
+    config["step"] = f"{FPS} consecutive frame batch(es) of {per_gpu} frame(s): one pipeline window of the camera stream"
     config["streams_per_gpu"] = NS
     config["conv_tile_policy"] = policy
     config["frames_in_flight"] = (f"{args.in_flight}: consecutive frames of the one camera stream are software-pipelined, each a batch-{per_gpu} pass; "
@@ -382,15 +388,17 @@ def main():
     def step(i):
         """One step = every camera stream processes its next frame batch (independent graphs on independent CUDA streams)."""
         if NS == 1:
-            pipe.plan.frame_in.copy_(pool[(i + 7 * rank) % n_pool])
-            pipe.step_device(True)
+            for j in range(FPS):
+                pipe.plan.frame_in.copy_(pool[(i * FPS + j + 7 * rank) % n_pool])
+                pipe.step_device(True)
             return
         cur = torch.cuda.current_stream(dev)
         for s_i, (pp, cs) in enumerate(zip(pipes, cuda_streams)):
             cs.wait_stream(cur)
             with torch.cuda.stream(cs):
-                pp.plan.frame_in.copy_(pool[(i * NS + s_i + 7 * rank) % n_pool])
-                pp.step_device(True)
+                for j in range(FPS):
+                    pp.plan.frame_in.copy_(pool[((i * FPS + j) * NS + s_i + 7 * rank) % n_pool])
+                    pp.step_device(True)
         for cs in cuda_streams:
             cur.wait_stream(cs)
 
@@ -411,7 +419,7 @@ def main():
     ms = e0.elapsed_time(e1)
     sampler.stop_flag = True
     sampler.join()
-    launches = K * NS * (pipe.n_launches())
+    launches = K * FPS * NS * (pipe.n_launches())
 
     # ---- informational: several independent camera streams in flight (each batch 1), reported under detail only
     multi = None
@@ -460,7 +468,7 @@ def main():
     # conv FLOPs of the K timed steps / duration of the timed region (CUDA events): with several frames in flight the conv launches of
     # different frames overlap, so their rate over the region is the honest figure (it also holds the non-conv kernels, all overlapped);
     # with one frame in flight it is the rate over the conv launches of one pass, timed alone (net_only_ms)
-    achieved_tf = (flops_step * NS * K / (ms * 1e-3) / 1e12) if pipe.F > 1 else (flops_step / (net_ms * 1e-3) / 1e12)
+    achieved_tf = (flops_step * NS * K * FPS / (ms * 1e-3) / 1e12) if pipe.F > 1 else (flops_step / (net_ms * 1e-3) / 1e12)
 
     # ---- end to end through the public host API
     host_frames = [np.stack([np.roll(base[(i + b) % 4], (5 * i) % W, axis=1) for b in range(per_gpu)]) for i in range(8)]
@@ -485,7 +493,7 @@ def main():
     # One camera stream, frames in order; the host runs one frame ahead (stages frame i+1 into pinned memory and enqueues its
     # H2D + pipeline + D2H while frame i is on the GPU, then unpacks frame i).  Every step's H2D and D2H are inside the timed region.
     t0 = time.perf_counter()
-    Ke = min(K, 100)
+    Ke = min(K * FPS, 400)             # frame batches of the end-to-end loop (the same K steps, bounded)
     ahead = max(1, args.in_flight)      # frames the host keeps submitted beyond the one it collects
     for j in range(min(ahead, Ke)):
         host_submit(j)
@@ -506,19 +514,19 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    fps = K * NS * per_gpu * world / (ms * 1e-3)
+    fps = K * FPS * NS * per_gpu * world / (ms * 1e-3)
     line = {"metric": "frames/sec end-to-end (backbone+heads+NMS+match)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (3xTF32 tensor-core MMA, fp32 accumulate)" if args.precision == "fp32" else "bf16",
             "data": "synthetic", "config": config, "clocks": sampler.summary(), "gpu_launches": launches,
-            "e2e": {"value": Ke * NS * per_gpu * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": NS * pipe.h2d_bytes(),
-                    "d2h_bytes_per_step": NS * pipe.d2h_bytes(), "steps": Ke},
+            "e2e": {"value": Ke * NS * per_gpu * world / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": FPS * NS * pipe.h2d_bytes(),
+                    "d2h_bytes_per_step": FPS * NS * pipe.d2h_bytes(), "steps": Ke / FPS},
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved_tf, "peak": peaks["tf"],
                          "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": CONV_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                          "traffic_note": "dram__bytes_read+write per conv launch, mean over the layers in profiles/r01_conv_tc_ncu_full.md (ncu, cold L2)",
                          "peak_source": f"{peaks['src']} bf16 sustained",
-                         "launches_per_step": plan.n_net_launches(), "avg_launch_us": (ms / K if pipe.F > 1 else net_ms) * 1e3 / plan.n_net_launches(),
-                         "algorithmic_gflop_per_step": flops_step / 1e9, "single_pass_ms": net_ms,
+                         "launches_per_step": FPS * plan.n_net_launches(), "avg_launch_us": (ms / (K * FPS) if pipe.F > 1 else net_ms) * 1e3 / plan.n_net_launches(),
+                         "algorithmic_gflop_per_step": FPS * flops_step / 1e9, "single_pass_ms": net_ms,
                          "note": ("achieved = SURVEY 8a conv FLOPs per frame x frames of the timed region / CUDA-event duration of the timed region (frames overlap: "
                                   "the conv launches of several frames run concurrently); single_pass_ms = the conv launches of ONE frame timed alone")
                                  if pipe.F > 1 else
