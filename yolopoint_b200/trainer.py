@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -119,6 +121,29 @@ class _FlatOutputs(torch.nn.Module):
         return (out["semi"], out["desc"], *out["objects"])
 
 
+class _LossHead(torch.nn.Module):
+    """The three losses of a step as one callable over tensors only (network outputs of both passes, labels, the precomputed target
+    plan and descriptor pairs), so that torch.cuda.make_graphed_callables can capture its forward and backward: ~700 small kernels
+    (target gather, CIoU, BCE terms, sampling, similarity GEMM, log-softmax and their gradients) replay from two graph launches
+    instead of being issued one by one from Python."""
+
+    def __init__(self, ts: "TrainStep", cells):
+        super().__init__()
+        self.ts, self.cells = [ts], list(cells)      # (list: keep the TrainStep out of nn.Module's attribute registry)
+
+    def forward(self, semi, semi_w, desc, desc_w, p0, p1, p2, labels_2D, valid_mask, warped_labels, warped_valid_mask, inv_h, pa, pb, rnd, *plan):
+        ts = self.ts[0]
+        levels = [dict(valid=plan[5 * i], cell=plan[5 * i + 1], tbox=plan[5 * i + 2], anchor=plan[5 * i + 3], cls=plan[5 * i + 4], cells=self.cells[i])
+                  for i in range(len(self.cells))]
+        loss_obj, _ = ts.obj_loss([p0, p1, p2], None, Lz.TargetPlan(levels))
+        loss_det = ts.det_loss.from_2d(semi, labels_2D, valid_mask)
+        loss_det_w = ts.det_loss.from_2d(semi_w, warped_labels, warped_valid_mask)
+        loss_desc = ts.desc_loss(desc, desc_w, warped_valid_mask, inv_h, pairs=(pa, pb, rnd), **ts.sparse_cfg)
+        loss = loss_det + loss_det_w + LAMBDA_DESC * loss_desc + LAMBDA_OBJ * loss_obj
+        return loss.reshape(1), torch.stack((loss_det.detach().reshape(()), loss_det_w.detach().reshape(()), loss_desc.detach().reshape(()),
+                                             loss_obj.detach().reshape(())))
+
+
 class TrainStep:
     def __init__(self, model, epochs: int = 100, lr: float = 1e-3, lrf: float = 0.01, sparse_cfg: Optional[dict] = None, group=None,
                  bucket_bytes: int = 32 << 20, graph_sample: Optional[torch.Tensor] = None, desc_loss: str = "infonce",
@@ -145,6 +170,8 @@ class TrainStep:
         self.opt = torch.optim.Adam(model.parameters(), lr=lr)
         self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lr_lambda=lambda e: (1 - e / epochs) * (1.0 - lrf) + lrf)
         self.graphed = None
+        self.loss_heads = {}                    # shape key -> graphed _LossHead (or None when the capture failed: eager losses)
+        self.graph_losses = graph_sample is not None and os.environ.get("YP_TRAIN_GRAPH_LOSSES", "1") != "0"
         self.packs, self.repack_graph = [], None
         if graph_sample is not None:
             model.train()
@@ -187,6 +214,10 @@ class TrainStep:
         pairs = Lz.descriptor_pairs(sample["warped_valid_mask"], sample["inv_homographies"], B, H // 8, W // 8, device=dev, **self.sparse_cfg)
         semi, desc, obj = self._forward(sample["image"], 0)
         semi_w, desc_w, _ = self._forward(sample["warped_image"], 1)
+        if self.graph_losses and len(obj) == 3:
+            res = self._graphed_losses(sample, semi, semi_w, desc, desc_w, obj, built, pairs)
+            if res is not None:
+                return res
         loss_obj, items = self.obj_loss(obj, sample["box_labels"], built)
         # label layout + cell masks + loss + gradient of the detector loss: one fused kernel per pass on CUDA (csrc/loss.cu)
         loss_det = self.det_loss.from_2d(semi, sample["labels_2D"], sample["valid_mask"])
@@ -194,6 +225,32 @@ class TrainStep:
         loss_desc = self.desc_loss(desc, desc_w, sample["warped_valid_mask"], sample["inv_homographies"], pairs=pairs, **self.sparse_cfg)
         loss = loss_det + loss_det_w + LAMBDA_DESC * loss_desc + LAMBDA_OBJ * loss_obj
         return loss, dict(det=loss_det.detach(), det_warp=loss_det_w.detach(), desc=loss_desc.detach(), obj=loss_obj.detach())
+
+    def _graphed_losses(self, sample, semi, semi_w, desc, desc_w, obj, built, pairs):
+        """The loss head through a CUDA graph captured per shape signature (number of targets, size of the descriptor sample pool,
+        batch geometry): a data loader delivers a handful of distinct signatures when its label lists are padded to a bucket size;
+        a signature whose capture fails runs the eager losses (returns None)."""
+        dev = self.device
+        f32 = lambda t: t.to(dev).float().contiguous()
+        plan = [lv[k] if k != "valid" else lv[k] for lv in built.levels for k in ("valid", "cell", "tbox", "anchor", "cls")]
+        plan = [t.contiguous() for t in plan]
+        args = [semi, semi_w, desc, desc_w, obj[0], obj[1], obj[2], f32(sample["labels_2D"]), f32(sample["valid_mask"]), f32(sample["warped_labels"]),
+                f32(sample["warped_valid_mask"]), f32(sample["inv_homographies"]), pairs[0].contiguous(), pairs[1].contiguous(), pairs[2].contiguous()] + plan
+        key = tuple((tuple(t.shape), t.dtype) for t in args)
+        if key not in self.loss_heads:
+            head = _LossHead(self, [lv["cells"] for lv in built.levels])
+            try:
+                samples = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in args)
+                self.loss_heads[key] = torch.cuda.make_graphed_callables(head, samples, num_warmup_iters=2)
+            except Exception as e:      # pragma: no cover  (e.g. an op of a custom loss configuration that cannot be captured)
+                import warnings
+                warnings.warn(f"TrainStep: loss head not captured ({type(e).__name__}: {e}); running the losses eagerly")
+                self.loss_heads[key] = None
+        head = self.loss_heads[key]
+        if head is None:
+            return None
+        loss, parts = head(*args)
+        return loss[0], dict(det=parts[0], det_warp=parts[1], desc=parts[2], obj=parts[3])
 
     def epoch_end(self):
         """Advance the linear learning-rate schedule (src/train.py:91-93, stepped once per epoch at :289): the caller's epoch loop
