@@ -212,6 +212,11 @@ int yp_bn_act_bwd(const void* dout, const void* y, int64_t P, int32_t C, const f
  * (see tools/conv_timeline.py); NULL switches it off.  Not thread safe. */
 int yp_debug_conv_timeline(void* device_buf_i64);
 
+/* desc / ||desc||_2 over the channels of every pixel of a plain fp32 (YP_FMT_F32) NHWC view, in place -- the descriptor normalisation of
+ * models/YOLOPoint.py:219-220 for descriptor widths that do not fit one accumulator tile (version "x", D = 320); narrower heads have it
+ * fused into the last convolution's epilogue (YP_EPI_L2NORM). */
+int yp_l2norm_nhwc(const YpView* view, void* stream);
+
 /* SPPF pooling: from slice 0 (C channels) of the [B,H,W,4C] concat buffer compute the 5x5, 9x9 and 13x13
  * stride-1 max pools (== three chained MaxPool2d(5,1,2), models/common.py:220-229) into slices 1..3. */
 int yp_sppf_pool(const YpView* cat4, void* stream);

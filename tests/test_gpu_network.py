@@ -54,8 +54,9 @@ def test_forward_golden_n(golden):
 
 
 # the last two are the shapes of BASELINE.json configs[2] (one GPU's shard: YOLOPoint-M, 4 x 736 x 1280) and configs[4] (YOLOPoint-L 640 x 640)
+# ... and version "x" (descriptor width 320: the last descriptor convolution runs without the fused L2 norm, yp_l2norm_nhwc behind it)
 @pytest.mark.parametrize("ver,B,H,W", [("n", 1, 480, 640), ("s", 1, 640, 640), ("s", 3, 96, 160), ("m", 1, 128, 160), ("m", 4, 736, 1280),
-                                       ("l", 1, 640, 640)])
+                                       ("l", 1, 640, 640), ("x", 1, 128, 160)])
 def test_forward_vs_oracle(ver, B, H, W):
     m, sd = build(ver)
     x = torch.from_numpy(np.random.RandomState(H + W).rand(B, 3, H, W).astype(np.float32))
@@ -346,3 +347,24 @@ def test_wide_policy_pipeline_equals_latency_policy_indices():
         assert abs(r[2].shape[0] - g[2].shape[0]) <= max(1, r[2].shape[0] // 50)
         if i:
             assert abs(r[3].shape[1] - g[3].shape[1]) <= max(3, r[3].shape[1] // 10)
+
+
+def test_version_x_whole_frame_pipeline():
+    """Version "x" (c3 = 320 descriptor channels) through the whole-frame pipeline: descriptors of width 320 are unit-norm rows, the
+    stage-by-stage results equal the oracle's post-processing of the engine's own network outputs."""
+    H, W = 192, 256
+    m, sd = build("x")
+    pipe = FramePipeline(m, 1, H, W)
+    assert pipe.D == 320
+    frame = synthetic_frame(H, W, 0)
+    pts, desc, boxes, matches = pipe.step_host(frame[None])[0]
+    x = torch.from_numpy(frame.transpose(2, 0, 1).astype(np.float32) / 255.)[None].cuda()
+    out = m(x)
+    assert out["desc"].shape[1] == 320
+    np.testing.assert_allclose(out["desc"].norm(dim=1).cpu().numpy(), 1.0, atol=1e-5)
+    outs_cpu = dict(semi=out["semi"].cpu(), desc=out["desc"].cpu(), objects=(out["objects"][0].cpu(), None))
+    pts_ref, desc_ref, boxes_ref = O.process_outputs(outs_cpu, H, W, O.DEFAULT_CFG, True, heat_variant="demo")
+    np.testing.assert_array_equal(boxes, boxes_ref)
+    if pts.shape == pts_ref.shape and np.array_equal(pts[:2], pts_ref[:2]) and pts.shape[1]:
+        assert desc.shape == (320, pts.shape[1])
+        np.testing.assert_allclose(desc, desc_ref, rtol=0, atol=1e-5)

@@ -37,7 +37,12 @@ def test_planner_reports_what_is_wrong():
 
 
 @pytest.mark.parametrize("model_name", MODEL_NAMES)
-def test_version_x_fails_loudly(model_name):
-    """D = 320 exceeds the single-tile L2-norm epilogue: the engine refuses at plan time instead of failing at the first launch."""
-    with pytest.raises(NotImplementedError, match="descriptor width 320"):
-        NetPlan("x", 80, "fp32", model_name)
+def test_version_x_plans_with_a_separate_l2norm(model_name):
+    """D = 320 exceeds the single-tile L2-norm epilogue: the last descriptor convolution is planned without it, followed by the
+    in-place row normalisation (yp_l2norm_nhwc); every launch of the plan passes the library's dry run."""
+    from yolopoint_b200.engine import L2NormOp
+    net = NetPlan("x", 80, "fp32", model_name)
+    assert net.D == 320 and not net.fused_l2norm
+    assert sum(isinstance(op, L2NormOp) for op in net.ops) == 1 and not any(op.l2norm for op in net.conv_ops())
+    assert check_plan(net, 1, 640, 640) == []
+    assert NetPlan("l", 80, "fp32", model_name).fused_l2norm

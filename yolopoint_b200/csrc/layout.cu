@@ -201,6 +201,33 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(YpView in, int C,
   }
 }
 
+// desc / ||desc||_2 over the channels of every pixel of a plain fp32 NHWC view, in place (models/YOLOPoint.py:219-220: the
+// normalisation of the descriptor head).  The conv kernel does this in its epilogue when all D channels of a pixel sit in one
+// accumulator tile (D <= 256); version "x" (D = 320) runs the last descriptor convolution without it and this kernel after it.
+// One warp per pixel, float4 lanes; HBM-bound: reads and writes D floats per pixel.
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(YpView v, int64_t n_pix) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = v.C >> 2;
+  for (int64_t p = warp0; p < n_pix; p += n_warps) {
+    float4* row = reinterpret_cast<float4*>(static_cast<float*>(v.base) + p * v.pix_stride);
+    float ss = 0.0f;
+    for (int j = lane; j < nv; j += 32) {
+      const float4 f = row[j];
+      ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); ss = fmaf(f.z, f.z, ss); ss = fmaf(f.w, f.w, ss);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    const float inv = 1.0f / sqrtf(ss);
+    for (int j = lane; j < nv; j += 32) {
+      float4 f = row[j];
+      f.x *= inv; f.y *= inv; f.z *= inv; f.w *= inv;
+      row[j] = f;
+    }
+  }
+}
+
 // SPPF pooling: see sppf.cuh (the body is shared with conv_chain_kernel, which runs it as an in-chain operation).
 __global__ void __launch_bounds__(256) sppf_pool_kernel(YpView cat4, int C) {
   extern __shared__ unsigned char sp_smem[];
@@ -290,6 +317,17 @@ extern "C" int yp_nhwc_to_nchw(const YpView* in, int32_t C, float* out, void* st
     dim3 grid(static_cast<unsigned>(yp::ceil_div64(HW, 32)), yp::ceil_div(C, 32), in->B);
     yp::nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(*in, C, out);
   }
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+extern "C" int yp_l2norm_nhwc(const YpView* v, void* stream) {
+  YP_REQUIRE(v && v->base, YP_ERR_ARG, "l2norm: null view");
+  YP_REQUIRE(v->format == YP_FMT_F32 && v->C % 4 == 0 && v->pix_stride % 4 == 0 && yp::aligned16(v->base), YP_ERR_SHAPE,
+             "l2norm: needs a plain fp32 view with 16-byte aligned rows (format %d, C %d, pixel stride %lld)", v->format, v->C, (long long)v->pix_stride);
+  const int64_t n_pix = static_cast<int64_t>(v->B) * v->H * v->W;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(yp::ceil_div64(n_pix, 8), static_cast<int64_t>(yp::sm_count()) * 8));
+  yp::l2norm_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*v, n_pix);
   YP_LAUNCH_OK();
   return YP_OK;
 }

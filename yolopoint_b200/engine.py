@@ -114,6 +114,13 @@ class Pool2Op:
     lane: int = 0
 
 
+@dataclass
+class L2NormOp:
+    """desc / ||desc||_2 over the channels of every pixel of a fp32 buffer, in place (descriptor widths > 256: version "x")."""
+    buf: str
+    lane: int = 0
+
+
 def _pad16(c):
     return (c + 15) // 16 * 16
 
@@ -134,11 +141,9 @@ class NetPlan:
         self.bufs: Dict[str, Tuple[int, int, int]] = {}   # name -> (stride level, C, fmt)
         self.ops: List[object] = []
         self._lane = 0
-        if self.D > 256:
-            # the descriptor L2 normalisation runs in the epilogue of the last descriptor-head conv, which needs all D channels of a
-            # pixel in one accumulator tile (<= 256 TMEM columns): version "x" (D = 320) is not supported by the inference engine
-            raise NotImplementedError(f"version {version!r}: descriptor width {self.D} > 256 is not supported by the B200 inference engine "
-                                      f"(train mode runs; see DESIGN.md section 8)")
+        # the descriptor L2 normalisation runs in the epilogue of the last descriptor-head conv when all D channels of a pixel fit one
+        # accumulator tile (<= 256 TMEM columns); version "x" (D = 320) runs that conv without it and yp_l2norm_nhwc behind it
+        self.fused_l2norm = self.D <= 256
         self.det_pad = _pad16(3 * self.no)
         self.semi_pad = _pad16(65)
         (self._build if model_name == "YOLOPoint" else self._build_v52)(c1, c2, c3, c4, c5, n1, n2, n3)
@@ -201,7 +206,9 @@ class NetPlan:
         dd = self._buf("dd", 3, c3)
         self._c3("BottleneckDesc", catd, 3, c3, n1, dd)
         desc = self._buf("desc", 3, c3, YP_FMT_F32)
-        self._conv("ConvDesc", dd, desc, 3, 1, c3, act=False, bn=False, l2norm=True)
+        self._conv("ConvDesc", dd, desc, 3, 1, c3, act=False, bn=False, l2norm=self.fused_l2norm)
+        if not self.fused_l2norm:
+            self.ops.append(L2NormOp("desc", self._lane))
         # yolo encoder
         self._lane = 0
         x4 = self._buf("x4", 4, c4)
@@ -290,7 +297,9 @@ class NetPlan:
         self.ops.append(Pool2Op(xa, S("catd", 0, c2), self._lane))
         self._conv("ConvDescB", xb, S("catd", c2, c2, upsample=2), 3, 2, c2)
         desc = self._buf("desc", 3, c3, YP_FMT_F32)
-        self._c2f("BottleneckDesc", catd, 3, c3, n1, desc, l2norm=True)
+        self._c2f("BottleneckDesc", catd, 3, c3, n1, desc, l2norm=self.fused_l2norm)
+        if not self.fused_l2norm:
+            self.ops.append(L2NormOp("desc", self._lane))
         # yolo encoder
         self._lane = 0
         x4 = self._buf("x4", 4, c4)
@@ -348,7 +357,7 @@ class NetPlan:
 # --------------------------------------------------------------------------------------------------
 def _op_reads_writes(op) -> Tuple[List[Tuple[str, int, int]], List[Tuple[str, int, int]]]:
     """(reads, writes) of an op as (buffer, first channel, end channel) ranges."""
-    if isinstance(op, PoolOp):
+    if isinstance(op, (PoolOp, L2NormOp)):
         return [(op.buf, 0, 1 << 30)], [(op.buf, 0, 1 << 30)]
     if isinstance(op, Pool2Op):
         return [(op.src.buf, op.src.c_off, op.src.c_off + op.src.C)], [(op.dst.buf, op.dst.c_off, op.dst.c_off + op.dst.C)]
@@ -567,6 +576,12 @@ class ShapePlan:
                 self.op_records.append(("pool", v))
                 self.launches.append((0, lambda st, v=v: _lib.check(L.yp_sppf_pool(C.byref(v), st)), "sppf_pool"))
                 continue
+            if isinstance(op, L2NormOp):
+                v = self.view(SliceRef(op.buf, 0, self.bufs[op.buf].shape[-1]))
+                self._keep.append(v)
+                self.op_records.append(("l2norm", v))
+                self.launches.append((op.lane, lambda st, v=v: _lib.check(L.yp_l2norm_nhwc(C.byref(v), st)), "l2norm"))
+                continue
             if isinstance(op, Pool2Op):
                 vi, vo = self.view(op.src), self.view(op.dst)
                 self._keep += [vi, vo]
@@ -618,7 +633,7 @@ class ShapePlan:
         the network waits for (last layer of the keypoint / descriptor head, Detect levels 0 and 1); every segment is one persistent
         kernel.  Falls back to the per-layer launch list when an op cannot be chained (YOLOPointv52's 2x2 max pool, bf16 operands)."""
         L, ops = _lib.lib(), self.eng.net.ops
-        if any(kind == "pool2" for kind, _ in self.op_records) or self.eng.precision != "fp32" or self.eng.algo != YP_ALGO_TCGEN05:
+        if any(kind in ("pool2", "l2norm") for kind, _ in self.op_records) or self.eng.precision != "fp32" or self.eng.algo != YP_ALGO_TCGEN05:
             return
         names = ["+".join(op.names) if isinstance(op, ConvOp) else "sppf_pool" for op in ops]
         lanes = [getattr(op, "lane", 0) for op in ops]
