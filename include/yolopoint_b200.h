@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YP_ABI_VERSION 7
+#define YP_ABI_VERSION 8
 
 typedef enum {
   YP_OK = 0,
@@ -126,6 +126,9 @@ typedef struct {
   const int32_t* n_rows;       /* device count of valid input pixels (descriptors of set 1), NULL = in.W */
   const int32_t* n_cols;       /* device count of valid output channels (descriptors of set 2), NULL = cout */
   int32_t col_off;             /* added to j in the key (column shard offset of the multi-GPU match) */
+  unsigned long long* col_key; /* optional [cout] keys (pre-filled with ~0): the epilogue also reduces key'(i, j) = dist_bits << 32 | i over the
+                                  input pixels i with an integer MIN into col_key[j] -- the other direction of the two-way match from the same
+                                  similarity tile (one pass instead of two) */
 } YpConvDesc;
 
 int yp_conv2d_nhwc_fwd(const YpConvDesc* desc, void* stream);

@@ -33,7 +33,7 @@ class YpConvDesc(C.Structure):
                 ("cout", C.c_int32), ("act", C.c_int32), ("epilogue", C.c_uint32), ("residual", YpView), ("n_out", C.c_int32),
                 ("out", YpView * 2), ("algo", C.c_int32), ("tile_n", C.c_int32), ("split_k", C.c_int32), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_uint64), ("n_taps", C.c_int32), ("tap_dh", C.c_int8 * 9), ("tap_dw", C.c_int8 * 9),
-                ("row_key", C.c_void_p), ("n_rows", C.c_void_p), ("n_cols", C.c_void_p), ("col_off", C.c_int32)]
+                ("row_key", C.c_void_p), ("n_rows", C.c_void_p), ("n_cols", C.c_void_p), ("col_off", C.c_int32), ("col_key", C.c_void_p)]
 
 
 class YpChainOp(C.Structure):
@@ -127,7 +127,7 @@ def lib(require_device: bool = False):
                     except AttributeError as e:  # pragma: no cover
                         raise YoloPointB200Error(f"{LIB_PATH} does not export {name}") from e
                     fn.restype, fn.argtypes = res, args
-                if handle.yp_abi_version() != 7:
+                if handle.yp_abi_version() != 8:
                     raise YoloPointB200Error("ABI version mismatch between _lib.py and libyolopoint_b200.so")
                 _lib = handle
     if require_device:

@@ -67,6 +67,7 @@ struct ConvArgs {
   int act, l2norm;
   int rowmin, col_off;                 // YP_EPI_ROWMIN: reduce distance keys over the output channels instead of storing
   unsigned long long* row_key;
+  unsigned long long* col_key;         // optional: column minima of the same tile (the other direction of the two-way match)
   const int* n_rows;
   const int* n_cols;
   const void* res_base;
@@ -556,6 +557,11 @@ __device__ __forceinline__ void conv_tile(const ConvMaps& maps, const ConvArgs& 
       const int n_rows = a.n_rows ? min(*a.n_rows, a.Wo) : a.Wo;
       const int n_cols = a.n_cols ? *a.n_cols : (int)(gy * a.Nt);
       unsigned long long best = ~0ull;
+      // Column minima of the same tile (key(i, j) with the ROW index in the low word: the match in the other direction, which used to
+      // be a second pass over the transposed problem): the tile's distances go to shared memory column-major (the pipeline stages
+      // are free: every MMA has retired), pitch 129 floats so that the row-wise writes and the column-wise scans are conflict-free.
+      float* dist_s = reinterpret_cast<float*>(smem_gen);
+      const bool row_ok = valid && ow < n_rows;
       for (int u = hf; u < a.Nt / 16; u += NG) {
         float v[16];
         load_acc16(u * 16, v);
@@ -566,9 +572,27 @@ __device__ __forceinline__ void conv_tile(const ConvMaps& maps, const ConvArgs& 
           const float dist = sqrtf(__fsub_rn(2.0f, __fmul_rn(2.0f, d)));
           const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(dist)) << 32) | static_cast<unsigned int>(j + a.col_off);
           if (j < n_cols) best = min(best, key);
+          if (a.col_key) dist_s[(u * 16 + e) * 129 + row] = row_ok ? dist : __int_as_float(0x7f800000);
         }
       }
-      if (valid && ow < n_rows && best != ~0ull) atomicMin(a.row_key + ow, best);
+      if (row_ok && best != ~0ull) atomicMin(a.row_key + ow, best);
+      if (a.col_key) {
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        // thread t scans half a column: column t % Nt... two threads per column when NT >= 2 Nt, each over 64 rows
+        const int per_col = NT / a.Nt >= 2 ? 2 : 1;
+        for (int idx = threadIdx.x; idx < a.Nt * per_col; idx += NT) {
+          const int c = idx / per_col, part = idx - c * per_col;
+          const int r0 = part * (128 / per_col), r1 = r0 + 128 / per_col;
+          unsigned long long cbest = ~0ull;
+          for (int r = r0; r < r1; ++r) {
+            const float dist = dist_s[c * 129 + r];
+            // row r of the tile is pixel (w0 + r) of the [1, 1, N1, D] view (Ht = 1, Wt = 128 for such views)
+            const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(dist)) << 32) | static_cast<unsigned int>(w0 + r);
+            cbest = min(cbest, key);
+          }
+          if (n0 + c < n_cols && (cbest >> 32) != 0x7f800000ull) atomicMin(a.col_key + n0 + c, cbest);
+        }
+      }
       run_epilogue = false;
     }
     if (run_epilogue) {
@@ -1977,7 +2001,8 @@ int prepare_conv(const YpConvDesc& d, ConvPlan& P, void* workspace, ConvMaps& ma
   a.act = d.act;
   a.l2norm = (d.epilogue & YP_EPI_L2NORM) ? 1 : 0;
   a.rowmin = (d.epilogue & YP_EPI_ROWMIN) ? 1 : 0;
-  a.row_key = d.row_key; a.n_rows = d.n_rows; a.n_cols = d.n_cols; a.col_off = d.col_off;
+  a.row_key = d.row_key; a.col_key = d.col_key; a.n_rows = d.n_rows; a.n_cols = d.n_cols; a.col_off = d.col_off;
+  if (a.rowmin && a.col_key) YP_REQUIRE(a.Ht == 1 && a.Wt == 128 && !a.patch, YP_ERR_SHAPE, "conv: YP_EPI_ROWMIN column keys expect 1 x 128 pixel tiles (got %d x %d)", a.Ht, a.Wt);
   if (a.rowmin) YP_REQUIRE(in.B == 1 && in.H == 1, YP_ERR_SHAPE, "conv: YP_EPI_ROWMIN expects the descriptors of set 1 as a [1, 1, N1, D] view");
   if (d.residual.base) {
     YP_REQUIRE(d.residual.C == d.cout && d.residual.H == Ho && d.residual.W == Wo && d.residual.B == in.B, YP_ERR_SHAPE, "conv: residual geometry mismatch");

@@ -168,7 +168,8 @@ def match_finalize(row_key: torch.Tensor, n1: Optional[torch.Tensor], col_key: t
     return m, cnt
 
 
-def _rowmin_pass(q: torch.Tensor, nq: Optional[torch.Tensor], k: torch.Tensor, nk: Optional[torch.Tensor], keys: torch.Tensor, col_off: int = 0):
+def _rowmin_pass(q: torch.Tensor, nq: Optional[torch.Tensor], k: torch.Tensor, nk: Optional[torch.Tensor], keys: torch.Tensor, col_off: int = 0,
+                 col_keys: Optional[torch.Tensor] = None):
     """keys[i] = min_j key(q_i, k_j) on the tcgen05 conv kernel (YP_EPI_ROWMIN): q [Nq,D] are the 'pixels' of a 1x1 conv whose
     weights are the k [Nk,D] descriptors; 3xTF32 operands (hi/lo planes), the Nq x Nk similarity matrix is never written."""
     from ._lib import YP_ACT_NONE, YP_ALGO_TCGEN05, YP_EPI_ROWMIN, YP_FMT_F32X2, YpConvDesc
@@ -186,6 +187,7 @@ def _rowmin_pass(q: torch.Tensor, nq: Optional[torch.Tensor], k: torch.Tensor, n
     d.ksize, d.stride, d.cout, d.act, d.epilogue, d.n_out = 1, 1, Nkp, YP_ACT_NONE, YP_EPI_ROWMIN, 0
     d.algo, d.tile_n, d.split_k = YP_ALGO_TCGEN05, 128, 1
     d.row_key = keys.data_ptr()
+    d.col_key = col_keys.data_ptr() if col_keys is not None else None      # column minima from the same tiles (one pass for both directions)
     d.n_rows = nq.data_ptr() if nq is not None else None
     if nk is None:
         nk = torch.tensor([Nk], dtype=torch.int32, device=k.device)
@@ -196,25 +198,32 @@ def _rowmin_pass(q: torch.Tensor, nq: Optional[torch.Tensor], k: torch.Tensor, n
 
 
 def match_partial_tc(d1: torch.Tensor, n1: Optional[torch.Tensor], d2: torch.Tensor, n2: Optional[torch.Tensor], col_off: int = 0):
-    """Tensor-core form of match_partial: two row-minimum passes (rows of d1 against d2, rows of d2 against d1)."""
+    """Tensor-core form of match_partial: ONE pass over the N1 x N2 similarity tiles; the epilogue reduces the row minima (best d2 for
+    every d1) and, through a shared-memory transpose of the tile, the column minima (best d1 for every d2).  ``YP_MATCH_TWO_PASS=1``
+    selects the earlier form (a second row-minimum pass over the transposed problem)."""
     _need_cuda(d1, "desc1")
     assert d1.is_contiguous() and d2.is_contiguous() and d1.dtype == torch.float32 and d2.dtype == torch.float32
     assert d1.shape[1] % 16 == 0, "descriptor dimension must be a multiple of 16"
     rk = torch.full((d1.shape[0],), -1, dtype=torch.int64, device=d1.device)      # all ones = "no candidate"
     ck = torch.full((d2.shape[0],), -1, dtype=torch.int64, device=d1.device)
-    keep = [_rowmin_pass(d1, n1, d2, n2, rk, col_off), _rowmin_pass(d2, n2, d1, n1, ck, 0)]
+    import os
+    if os.environ.get("YP_MATCH_TWO_PASS", "0") != "0":
+        keep = [_rowmin_pass(d1, n1, d2, n2, rk, col_off), _rowmin_pass(d2, n2, d1, n1, ck, 0)]
+    else:
+        keep = [_rowmin_pass(d1, n1, d2, n2, rk, col_off, col_keys=ck)]
     rk._yp_keep = keep
     return rk, ck
 
 
 def match_two_way(d1: torch.Tensor, n1, d2: torch.Tensor, n2, nn_thresh: float, algo: str = "auto"):
-    """Single-GPU two-way match of row-major descriptors.  algo: "simt" = fused fp32 FMA kernel (yp_match_partial), "tc" = two
-    3xTF32 tcgen05 row-minimum passes (yp_conv2d_nhwc_fwd + YP_EPI_ROWMIN), "auto" = tc from 8192 descriptors per side on (measured
-    crossover on B200: 0.89 vs 1.12 ms at 8192, 2.72 vs 4.38 ms at 16384, D = 256; below that the operand split costs more than it saves)."""
+    """Single-GPU two-way match of row-major descriptors.  algo: "simt" = fused fp32 FMA kernel (yp_match_partial), "tc" = one
+    3xTF32 tcgen05 pass over the similarity tiles whose epilogue reduces row AND column minima (yp_conv2d_nhwc_fwd + YP_EPI_ROWMIN with
+    col_key), "auto" = tc from 4096 descriptors per side on (measured on B200, D = 256: 4096: 0.215 vs 0.285 ms, 8192: 0.49 vs
+    1.12 ms, 16384: 1.54 vs 4.38 ms; below 4096 the operand split and the fixed cost of the pass exceed what it saves)."""
     if nn_thresh < 0.0:
         raise ValueError("'nn_thresh' should be non-negative")
     if algo == "auto":
-        algo = "tc" if min(d1.shape[0], d2.shape[0]) >= 8192 and d1.shape[1] % 16 == 0 else "simt"
+        algo = "tc" if min(d1.shape[0], d2.shape[0]) >= 4096 and d1.shape[1] % 16 == 0 else "simt"
     rk, ck = match_partial_tc(d1, n1, d2, n2) if algo == "tc" else match_partial(d1, n1, d2, n2)
     return match_finalize(rk, n1, ck, nn_thresh)
 
