@@ -60,7 +60,13 @@ def match_two_way_sharded(d1: torch.Tensor, d2_full_or_local: torch.Tensor, nn_t
         n2_total = d2_full_or_local.shape[0]
         lo, hi = shard_range(n2_total, rank, world)
         d2 = d2_full_or_local[lo:hi].contiguous()
-    if hi > lo:
+    if hi > lo and d1.is_cuda and d1.shape[0] >= 4096 and hi - lo >= 512 and d1.shape[1] % 16 == 0:
+        # large problems: one 3xTF32 tensor-core pass per shard (row and column minima in the epilogue); rows / columns without a
+        # candidate keep the all-ones key, which must lose the signed MIN of the exchange step
+        rk, ck = ops.match_partial_tc(d1, None, d2, None, col_off=lo)
+        big = torch.iinfo(torch.int64).max
+        rk, ck = torch.where(rk < 0, big, rk), torch.where(ck < 0, big, ck)
+    elif hi > lo:
         rk, ck = ops.match_partial(d1, None, d2, None, col_off=lo)
     else:
         rk = torch.full((d1.shape[0],), torch.iinfo(torch.int64).max, dtype=torch.int64, device=d1.device)

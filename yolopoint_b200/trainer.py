@@ -214,7 +214,7 @@ class TrainStep:
         pairs = Lz.descriptor_pairs(sample["warped_valid_mask"], sample["inv_homographies"], B, H // 8, W // 8, device=dev, **self.sparse_cfg)
         semi, desc, obj = self._forward(sample["image"], 0)
         semi_w, desc_w, _ = self._forward(sample["warped_image"], 1)
-        if self.graph_losses and len(obj) == 3:
+        if getattr(self, "graph_losses", False) and len(obj) == 3:
             res = self._graphed_losses(sample, semi, semi_w, desc, desc_w, obj, built, pairs)
             if res is not None:
                 return res
