@@ -1939,7 +1939,13 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   if (drain) {
     a.n_tiles_n = n_tiles;
     a.tiles_total = m_tiles * n_tiles;
-    P->grid = dim3(std::min(a.tiles_total, nsm), 1, 1);
+    // Persistent grid: at most nsm / drain_grid_div CTAs, every CTA an equal share of the tiles.  With several frames in flight a
+    // layer does not need every SM, and a CTA that walks two or three tiles overlaps the epilogue of one with the main loop of the
+    // next.  Measured (YOLOPoint-S 640x640 batch 1, 8 frames in flight): divisor 1 / 2 / 3 / 4 = 2372 / 2424 / 2461 / 2404 frames/s.
+    static const int grid_div = getenv("YP_CONV_DRAIN_GRID_DIV") ? std::max(1, atoi(getenv("YP_CONV_DRAIN_GRID_DIV"))) : 3;
+    const int max_ctas = std::max(1, nsm / grid_div);
+    const int per_cta = ceil_div(a.tiles_total, std::min(a.tiles_total, max_ctas));
+    P->grid = dim3(ceil_div(a.tiles_total, per_cta), 1, 1);
   }
   if (persist) {
     YP_REQUIRE(a.n_src <= 2 && cols <= 256, YP_ERR_SHAPE, "conv(persist): accumulator plan needs %d sources / %d columns", a.n_src, cols);
