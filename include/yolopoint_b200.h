@@ -215,6 +215,10 @@ int yp_bn_act_bwd(const void* dout, const void* y, int64_t P, int32_t C, const f
  * (see tools/conv_timeline.py); NULL switches it off.  Not thread safe. */
 int yp_debug_conv_timeline(void* device_buf_i64);
 
+/* fp32 [n] -> the (hi, lo) TF32 operand planes of the 3xTF32 path (hi = tf32(x), lo = tf32(x - hi), round to nearest away): what
+ * yolopoint_b200.engine.split_tf32 computes with PyTorch ops, as one kernel (operand preparation of the tensor-core match). */
+int yp_split_tf32(const float* src, int64_t n, float* hi, float* lo, void* stream);
+
 /* desc / ||desc||_2 over the channels of every pixel of a plain fp32 (YP_FMT_F32) NHWC view, in place -- the descriptor normalisation of
  * models/YOLOPoint.py:219-220 for descriptor widths that do not fit one accumulator tile (version "x", D = 320); narrower heads have it
  * fused into the last convolution's epilogue (YP_EPI_L2NORM). */

@@ -72,6 +72,7 @@ SIGNATURES = {
     "yp_debug_conv_timeline": (_i32, [_vp]),
     "yp_sppf_pool": (_i32, [_PV, _vp]),
     "yp_l2norm_nhwc": (_i32, [_PV, _vp]),
+    "yp_split_tf32": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "yp_maxpool2x2": (_i32, [_PV, _PV, _vp]),
     "yp_nchw_to_s2d": (_i32, [_vp, _i32, _i32, _i32, _PV, _vp]),
     "yp_frame_to_s2d": (_i32, [_vp, _i32, _i32, _i32, _PV, _vp]),

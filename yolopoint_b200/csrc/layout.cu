@@ -228,6 +228,18 @@ __global__ void __launch_bounds__(256) l2norm_rows_kernel(YpView v, int64_t n_pi
   }
 }
 
+// fp32 -> (hi, lo) TF32 operand planes (hi = tf32(x), lo = tf32(x - hi); cvt.rna): the operand split of the 3xTF32 tensor-core match
+// (descriptor rows become the "pixels" / "weights" of a 1x1 convolution).  One float4 per thread, HBM-bound: 4 B in, 8 B out per element.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ src, int64_t n4, float4* __restrict__ hi, float4* __restrict__ lo) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    float4 h, l;
+    h.x = tf32_round(v.x); h.y = tf32_round(v.y); h.z = tf32_round(v.z); h.w = tf32_round(v.w);
+    l.x = tf32_round(v.x - h.x); l.y = tf32_round(v.y - h.y); l.z = tf32_round(v.z - h.z); l.w = tf32_round(v.w - h.w);
+    hi[i] = h; lo[i] = l;
+  }
+}
+
 // SPPF pooling: see sppf.cuh (the body is shared with conv_chain_kernel, which runs it as an in-chain operation).
 __global__ void __launch_bounds__(256) sppf_pool_kernel(YpView cat4, int C) {
   extern __shared__ unsigned char sp_smem[];
@@ -328,6 +340,17 @@ extern "C" int yp_l2norm_nhwc(const YpView* v, void* stream) {
   const int64_t n_pix = static_cast<int64_t>(v->B) * v->H * v->W;
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(yp::ceil_div64(n_pix, 8), static_cast<int64_t>(yp::sm_count()) * 8));
   yp::l2norm_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*v, n_pix);
+  YP_LAUNCH_OK();
+  return YP_OK;
+}
+
+extern "C" int yp_split_tf32(const float* src, int64_t n, float* hi, float* lo, void* stream) {
+  YP_REQUIRE(src && hi && lo, YP_ERR_ARG, "split_tf32: null pointer");
+  YP_REQUIRE(n >= 0 && n % 4 == 0 && yp::aligned16(src) && yp::aligned16(hi) && yp::aligned16(lo), YP_ERR_ALIGN, "split_tf32: n must be a multiple of 4 and the buffers 16-byte aligned");
+  if (n == 0) return YP_OK;
+  const int64_t n4 = n / 4;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(yp::ceil_div64(n4, 256), static_cast<int64_t>(yp::sm_count()) * 16));
+  yp::split_tf32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(src), n4, reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo));
   YP_LAUNCH_OK();
   return YP_OK;
 }

@@ -178,9 +178,13 @@ def _rowmin_pass(q: torch.Tensor, nq: Optional[torch.Tensor], k: torch.Tensor, n
     Nq, D = q.shape
     Nk = k.shape[0]
     Nkp = (Nk + 127) // 128 * 128                     # N tile of 128 output channels
-    qa = split_tf32(q).view(2, 1, 1, Nq, D).contiguous()
-    kw = torch.zeros((2, Nkp, D), dtype=torch.float32, device=k.device)
-    kw[:, :Nk] = split_tf32(k)
+    st = _stream(q.device)
+    qa = torch.empty((2, 1, 1, Nq, D), dtype=torch.float32, device=q.device)
+    _lib.check(L.yp_split_tf32(q.data_ptr(), Nq * D, qa[0].data_ptr(), qa[1].data_ptr(), st))
+    kw = torch.empty((2, Nkp, D), dtype=torch.float32, device=k.device)
+    if Nkp > Nk:
+        kw[:, Nk:].zero_()                            # padding rows of the last N tile
+    _lib.check(L.yp_split_tf32(k.data_ptr(), Nk * D, kw[0].data_ptr(), kw[1].data_ptr(), st))
     d = YpConvDesc()
     d.in_ = make_view(qa, YP_FMT_F32X2, 0, D)
     d.weight, d.bias = kw.data_ptr(), None
