@@ -34,6 +34,18 @@ def _workspace(dev, kind: str, nbytes: int) -> torch.Tensor:
     return t
 
 
+_const_cache: dict = {}
+
+
+def _const_i32(dev, value: int) -> torch.Tensor:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(value))
+    t = _const_cache.get(key)
+    if t is None:
+        t = torch.tensor([int(value)], dtype=torch.int32, device=dev)
+        _const_cache[key] = t
+    return t
+
+
 def _need_cuda(t: torch.Tensor, what: str):
     if not (isinstance(t, torch.Tensor) and t.is_cuda):
         raise RuntimeError(f"{what} must be a CUDA tensor: yolopoint_b200 has no CPU path")
@@ -194,7 +206,7 @@ def _rowmin_pass(q: torch.Tensor, nq: Optional[torch.Tensor], k: torch.Tensor, n
     d.col_key = col_keys.data_ptr() if col_keys is not None else None      # column minima from the same tiles (one pass for both directions)
     d.n_rows = nq.data_ptr() if nq is not None else None
     if nk is None:
-        nk = torch.tensor([Nk], dtype=torch.int32, device=k.device)
+        nk = _const_i32(k.device, Nk)                 # cached device scalar (a fresh torch.tensor would be a blocking H2D copy per call)
     d.n_cols = nk.data_ptr()
     d.col_off = int(col_off)
     _lib.check(L.yp_conv2d_nhwc_fwd(C.byref(d), _stream(q.device)))
@@ -222,8 +234,8 @@ def match_partial_tc(d1: torch.Tensor, n1: Optional[torch.Tensor], d2: torch.Ten
 def match_two_way(d1: torch.Tensor, n1, d2: torch.Tensor, n2, nn_thresh: float, algo: str = "auto"):
     """Single-GPU two-way match of row-major descriptors.  algo: "simt" = fused fp32 FMA kernel (yp_match_partial), "tc" = one
     3xTF32 tcgen05 pass over the similarity tiles whose epilogue reduces row AND column minima (yp_conv2d_nhwc_fwd + YP_EPI_ROWMIN with
-    col_key), "auto" = tc from 4096 descriptors per side on (measured on B200, D = 256: 4096: 0.215 vs 0.285 ms, 8192: 0.49 vs
-    1.12 ms, 16384: 1.54 vs 4.38 ms; below 4096 the operand split and the fixed cost of the pass exceed what it saves)."""
+    col_key), "auto" = tc from 4096 descriptors per side on (measured on B200, D = 256: 4096: 0.153 vs 0.285 ms, 8192: 0.43 vs
+    1.12 ms, 16384: 1.46 vs 4.38 ms; at 2048: 0.166 vs 0.092 ms -- the fixed cost of the pass, ~0.14 ms, exceeds what it saves)."""
     if nn_thresh < 0.0:
         raise ValueError("'nn_thresh' should be non-negative")
     if algo == "auto":
