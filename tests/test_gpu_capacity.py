@@ -164,6 +164,17 @@ def test_frame_pipeline_grows_explicit_small_capacities():
         r = ref[0] if i == 0 else ref[i - 1]
         for a, b in zip(g, r):
             np.testing.assert_array_equal(a, b)
+    # and with three frames of the stream in flight on their own contexts / streams (frames_in_flight = 3) when it is discovered
+    small3 = FramePipeline(m, 1, H, W, max_pts=64, nms_cap=64, slot=5, frames_in_flight=3)
+    for f in frames[:3]:
+        small3.submit_host(f[None])
+    got3 = [small3.collect()[0]]
+    small3.submit_host(frames[3][None])
+    got3 += [small3.collect()[0] for _ in range(3)]
+    assert small3.regrown == 1 and small3.max_pts == small3.max_pts_bound()
+    for g, r in zip(got3, ref):
+        for a, b in zip(g, r):
+            np.testing.assert_array_equal(a, b)
 
 
 def test_bench_rank_seeds_do_not_raise():

@@ -115,3 +115,29 @@ def test_nhwc_to_nchw_export(B, H, W, Ct, c_off, Cv, C):
     _lib.check(L.yp_nhwc_to_nchw(ctypes.byref(v), C, out.data_ptr(), _st()))
     torch.cuda.synchronize()
     assert torch.equal(out, t[0, ..., c_off:c_off + C].permute(0, 3, 1, 2))
+
+
+def test_l2norm_rows_and_tf32_split_kernels():
+    """yp_l2norm_nhwc (descriptor normalisation for widths that do not fit one accumulator tile: version "x") against torch on a
+    channel slice of a wider buffer, and yp_split_tf32 (operand planes of the tensor-core match) bit-exact against the PyTorch
+    restatement of cvt.rna.tf32 (engine.split_tf32)."""
+    import ctypes as C
+    from yolopoint_b200 import _lib
+    from yolopoint_b200._lib import YP_FMT_F32
+    from yolopoint_b200.engine import make_view, split_tf32
+    L = _lib.lib(require_device=True)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    buf = torch.randn(1, 2, 9, 11, 320 + 16, generator=g).cuda()
+    ref = buf.clone()
+    ref[..., 16:] = ref[..., 16:] / ref[..., 16:].norm(dim=-1, keepdim=True)
+    v = make_view(buf, YP_FMT_F32, 16, 320)
+    _lib.check(L.yp_l2norm_nhwc(C.byref(v), st))
+    torch.cuda.synchronize()
+    assert torch.equal(buf[..., :16], ref[..., :16])                       # channels outside the slice untouched
+    assert float((buf[..., 16:] - ref[..., 16:]).abs().max()) < 2e-7
+    x = (torch.randn(1000, 256, generator=g) * torch.logspace(-6, 6, 1000).unsqueeze(1)).cuda()
+    out = torch.empty((2, 1000, 256), device="cuda")
+    _lib.check(L.yp_split_tf32(x.data_ptr(), x.numel(), out[0].data_ptr(), out[1].data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(out, split_tf32(x))
