@@ -36,7 +36,7 @@ WORKLOADS = {
     "s640v52": ("s", 640, 640, 1),  # YOLOPointv52-S (the model configs/kitti_inference.yaml names), configs[1] geometry
 }
 MODEL_NAME = {"s640v52": "YOLOPointv52"}   # every other workload runs the YOLOPoint (v5-style) network
-CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 7.27e6}   # profiles/r01_conv_tc_ncu_full.md: mean of the three YOLOPoint-S layer geometries captured (cold L2)
+CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 6.30e6}   # profiles/r02_conv_tc_wide_ncu_full.md: mean over the 53 conv launches of a YOLOPoint-S 640x640 pass captured (cold L2)
 NAMES = [str(i) for i in range(80)]
 # SURVEY.md section 8a, per frame (forward); s640v52: conv-module hook count on the reference YOLOPointv52-S
 CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398, "l640train": 135.526, "s640v52": 21.363}
@@ -523,7 +523,9 @@ def main():
                     "d2h_bytes_per_step": FPS * NS * pipe.d2h_bytes(), "steps": Ke / FPS},
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved_tf, "peak": peaks["tf"],
                          "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": CONV_DRAM_BYTES_PER_LAUNCH.get(args.workload),
-                         "traffic_note": "dram__bytes_read+write per conv launch, mean over the layers in profiles/r01_conv_tc_ncu_full.md (ncu, cold L2)",
+                         "traffic_note": "dram__bytes_read+write per conv launch, mean over the 53 conv launches of one pass captured in profiles/r02_conv_tc_wide_ncu_full.md "
+                                         "(ncu --set full, cold L2); algorithmic: 78.1 M activation elements x 8 B (hi, lo planes) / 65 launches = 9.6 MB written + read once, "
+                                         "i.e. the cold-cache traffic is below the algorithmic bytes because most operands are re-read from L2",
                          "peak_source": f"{peaks['src']} bf16 sustained",
                          "launches_per_step": FPS * plan.n_net_launches(), "avg_launch_us": (ms / (K * FPS) if pipe.F > 1 else net_ms) * 1e3 / plan.n_net_launches(),
                          "algorithmic_gflop_per_step": FPS * flops_step / 1e9, "single_pass_ms": net_ms,
