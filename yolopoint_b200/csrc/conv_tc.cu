@@ -1945,7 +1945,8 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     // layer does not need every SM, and a CTA that walks two or three tiles overlaps the epilogue of one with the main loop of the
     // next.  Measured (YOLOPoint-S 640x640 batch 1, 8 frames in flight): divisor 1 / 2 / 3 / 4 = 2372 / 2424 / 2461 / 2404 frames/s.
     static const int grid_div = getenv("YP_CONV_DRAIN_GRID_DIV") ? std::max(1, atoi(getenv("YP_CONV_DRAIN_GRID_DIV"))) : 3;
-    const int max_ctas = std::max(1, nsm / grid_div);
+    // (layers with more than 8 tiles per SM -- batched inputs -- keep every SM: they are long enough to fill the GPU on their own)
+    const int max_ctas = a.tiles_total > 8 * nsm ? nsm : std::max(1, nsm / grid_div);
     const int per_cta = ceil_div(a.tiles_total, std::min(a.tiles_total, max_ctas));
     P->grid = dim3(ceil_div(a.tiles_total, per_cta), 1, 1);
   }
