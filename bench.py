@@ -327,7 +327,7 @@ def main():
     config["frames_per_gpu_per_step"] = per_gpu * FPS
     config["step"] = f"{FPS} consecutive frame batch(es) of {per_gpu} frame(s): one pipeline window of the camera stream"
     config["streams_per_gpu"] = NS
-    config["conv_tile_policy"] = policy
+    config["conv_tile_policy"] = policy + (" (persistent grids capped at a third of the SMs)" if (policy == "wide" and per_gpu == 1 and args.in_flight >= 4) else "")
     config["frames_in_flight"] = (f"{args.in_flight}: consecutive frames of the one camera stream are software-pipelined, each a batch-{per_gpu} pass; "
                                   "only the in-box filter + match of frame i+1 wait for frame i") if args.in_flight > 1 else 1
     config["l2"] = f"inputs larger than L2: pool of {n_pool} frame batches ({n_pool * frame_bytes / 1e6:.0f} MB) cycled, weights stay L2-resident"
@@ -361,6 +361,7 @@ def main():
     model, sd = build_weights(version, model_name)
     model.precision = args.precision
     model.tile_policy = policy
+    model.wide_grid_div = 3 if (policy == "wide" and per_gpu == 1 and args.in_flight >= 4) else 1     # three layers of different frames share the GPU
     model = model.to(dev).eval()
     pipes = [FramePipeline(model, per_gpu, H, W, slot=i, frames_in_flight=args.in_flight) for i in range(NS)]
     cuda_streams = [torch.cuda.Stream(dev) for _ in range(NS)]

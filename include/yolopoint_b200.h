@@ -110,8 +110,10 @@ typedef struct {
   int32_t n_out;          /* 1 or 2 */
   YpView out[2];
   int32_t algo;           /* YpConvAlgo */
-  int32_t tile_n;         /* 0 = library heuristic; YP_TILE_WIDE = throughput plan (widest tile whose accumulator plan keeps fp32-grade accuracy; split_k
-                             is then chosen by the library); else the N (output-channel) tile: a divisor of cout, multiple of 16, <= 128 (fp32) / 256 (bf16) */
+  int32_t tile_n;         /* 0 = library heuristic; YP_TILE_WIDE (-1) = throughput plan (widest tile, accumulators drained into registers so that the
+                             fp32-grade accuracy holds at any width; split_k is then chosen by the library); -g (g >= 2) = the same with the persistent grid
+                             capped at #SMs / g CTAs (a caller that keeps several frames in flight shares the GPU between their layers);
+                             else the N (output-channel) tile: a divisor of cout, multiple of 16, <= 128 (fp32) / 256 (bf16) */
   int32_t split_k;        /* 0 = let the library slice K over several CTAs when the layer cannot fill the GPU, 1 = never, n = n slices */
   void* workspace;        /* split-K scratch (zero-initialised once by the caller, reusable by later launches on the same
                              stream; launches that may run concurrently need distinct workspaces); NULL -> never split */

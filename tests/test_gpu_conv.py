@@ -193,3 +193,12 @@ def test_conv_wide_plan(ci):
     c = dict(WIDE_CASES[ci], tile=-1)
     err = run_case(c, YP_FMT_F32X2, YP_ALGO_TCGEN05)
     print(f"wide plan case {ci}: rel err {err:.2e}")
+
+
+@pytest.mark.parametrize("ci", [1, 3, 8, 9, 10])
+def test_conv_wide_plan_shared_grid(ci):
+    """tile_n = -3: the same plan with the persistent grid capped at a third of the SMs (several tiles per CTA: what bench.py's
+    headline configuration launches)."""
+    c = dict(WIDE_CASES[ci], tile=-3)
+    err = run_case(c, YP_FMT_F32X2, YP_ALGO_TCGEN05)
+    print(f"wide plan (grid / 3) case {ci}: rel err {err:.2e}")

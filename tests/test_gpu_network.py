@@ -335,7 +335,7 @@ def test_wide_policy_pipeline_equals_latency_policy_indices():
     frames = [synthetic_frame(H, W, s)[None] for s in range(4)]
     ref_pipe = FramePipeline(m, 1, H, W)
     ref = [ref_pipe.step_host(f)[0] for f in frames]
-    eng = Engine(sd, "s", 80, torch.device("cuda:0"), tile_policy="wide")
+    eng = Engine(sd, "s", 80, torch.device("cuda:0"), tile_policy="wide", wide_grid_div=3)
     pipe = FramePipeline(eng, 1, H, W, frames_in_flight=8)
     for f in frames:
         pipe.submit_host(f)

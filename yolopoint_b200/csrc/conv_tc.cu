@@ -1686,7 +1686,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   static const bool allow_drain = getenv("YP_CONV_DRAIN") == nullptr || atoi(getenv("YP_CONV_DRAIN")) != 0;
   // Layers with a short K (few MMAs per accumulator anyway) keep the rotating-accumulator plans below, which run two CTAs per SM.
   static const int drain_min_steps = getenv("YP_CONV_DRAIN_MIN_STEPS") ? atoi(getenv("YP_CONV_DRAIN_MIN_STEPS")) : 0;
-  const bool drain = allow_drain && d.tile_n == YP_TILE_WIDE && tf32 && g_chain_budget == 0 && d.ksize != 0 && chunk_elems == 32 && d.cout % 32 == 0 &&
+  const bool drain = allow_drain && d.tile_n <= YP_TILE_WIDE && tf32 && g_chain_budget == 0 && d.ksize != 0 && chunk_elems == 32 && d.cout % 32 == 0 &&
                      !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && (out_fmt == YP_FMT_F32X2 || out_fmt == YP_FMT_F32) &&
                      num_kb * ksteps >= drain_min_steps;
   if (d.epilogue & YP_EPI_L2NORM) {
@@ -1697,7 +1697,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     for (int n = 128; n >= 32; n -= 32)
       if (d.cout % n == 0) { Nt = n; break; }
     split_req = 1;
-  } else if (d.tile_n == YP_TILE_WIDE) {
+  } else if (d.tile_n <= YP_TILE_WIDE) {
     // Throughput plan: the widest N tile (fewest re-reads of the activation tile, fewest MMAs per FLOP) whose accumulator plan still
     // keeps the fp32-grade accuracy of the 3xTF32 mode.  The tensor core adds into an fp32 accumulator with truncation, so the error
     // grows with the number of MMAs chained on one accumulator: a wide tile leaves TMEM room for fewer accumulators to rotate over
@@ -1777,7 +1777,7 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
   const bool persist = allow_persist && !chain && !tf32 && S == 1 && !(d.epilogue & (YP_EPI_L2NORM | YP_EPI_ROWMIN)) && out_fmt != YP_FMT_F32X2 &&
                        static_cast<long long>(m_tiles) * n_tiles > (getenv("YP_CONV_PERSIST_MIN") ? atoll(getenv("YP_CONV_PERSIST_MIN")) : 2LL * nsm);
   static const bool force_dense = getenv("YP_CONV_FORCE_DENSE") != nullptr && atoi(getenv("YP_CONV_FORCE_DENSE")) != 0;
-  const bool unstacked = !drain && d.tile_n == YP_TILE_WIDE && m_tiles < nsm && tf32 && Nt == 128 && !(d.epilogue & YP_EPI_L2NORM);   // needs all 512 TMEM columns
+  const bool unstacked = !drain && d.tile_n <= YP_TILE_WIDE && m_tiles < nsm && tf32 && Nt == 128 && !(d.epilogue & YP_EPI_L2NORM);   // needs all 512 TMEM columns
   const bool dense = !chain && !unstacked && !drain && ((allow_dense && (force_dense || static_cast<long long>(m_tiles) * n_tiles * S > nsm)) || persist);   // persist: 256 columns per accumulator buffer
   const int tmem_limit = dense ? 256 : 512;
 
@@ -1944,9 +1944,11 @@ int plan_conv_impl(const YpConvDesc& d, ConvPlan* P, bool allow_split, bool no_p
     // Persistent grid: at most nsm / drain_grid_div CTAs, every CTA an equal share of the tiles.  With several frames in flight a
     // layer does not need every SM, and a CTA that walks two or three tiles overlaps the epilogue of one with the main loop of the
     // next.  Measured (YOLOPoint-S 640x640 batch 1, 8 frames in flight): divisor 1 / 2 / 3 / 4 = 2372 / 2424 / 2461 / 2404 frames/s.
-    static const int grid_div = getenv("YP_CONV_DRAIN_GRID_DIV") ? std::max(1, atoi(getenv("YP_CONV_DRAIN_GRID_DIV"))) : 3;
-    // (layers with more than 8 tiles per SM -- batched inputs -- keep every SM: they are long enough to fill the GPU on their own)
-    const int max_ctas = a.tiles_total > 8 * nsm ? nsm : std::max(1, nsm / grid_div);
+    // The divisor comes with the descriptor (tile_n = -g, YP_TILE_WIDE = -1 = every SM): the caller knows how many frames it keeps
+    // in flight; YP_CONV_DRAIN_GRID_DIV overrides it.
+    static const int env_div = getenv("YP_CONV_DRAIN_GRID_DIV") ? std::max(1, atoi(getenv("YP_CONV_DRAIN_GRID_DIV"))) : 0;
+    const int grid_div = env_div ? env_div : std::max(1, -d.tile_n);
+    const int max_ctas = std::max(1, nsm / grid_div);
     const int per_cta = ceil_div(a.tiles_total, std::min(a.tiles_total, max_ctas));
     P->grid = dim3(ceil_div(a.tiles_total, per_cta), 1, 1);
   }

@@ -607,7 +607,7 @@ class ShapePlan:
                 # throughput plan (YP_TILE_WIDE): the widest N tile whose accumulator plan keeps the fp32-grade accuracy, K split only
                 # where the accuracy bound asks for it -- a layer then occupies few SMs, which is what several frames in flight want
                 if not op.l2norm:
-                    d.tile_n = -1
+                    d.tile_n = -max(1, int(eng.wide_grid_div))     # YP_TILE_WIDE, persistent grid capped at #SMs / wide_grid_div
                 d.split_k = 0
             elif tuned and eng.split_k:
                 d.tile_n, d.split_k = int(tuned[0]), int(tuned[1])
@@ -860,7 +860,7 @@ class ShapePlan:
 class Engine:
     def __init__(self, sd, version: str, nc: int, device, precision: str = "fp32", algo: int = YP_ALGO_TCGEN05, use_graphs: bool = True,
                  multi_stream: bool = True, split_k: bool = True, use_tuning: bool = True, model_name: str = "YOLOPoint", chain: Optional[bool] = None,
-                 tile_policy: Optional[str] = None):
+                 tile_policy: Optional[str] = None, wide_grid_div: Optional[int] = None):
         _lib.lib(require_device=True)
         self.device = torch.device(device)
         self.net = NetPlan(version, nc, precision, model_name)
@@ -869,6 +869,9 @@ class Engine:
         # "latency" = per-layer (tile_n, split_k) from the measured tables (smallest time of ONE pass); "wide" = widest N tile, no split-K
         self.tile_policy = tile_policy or os.environ.get("YP_TILE_POLICY", "latency")
         assert self.tile_policy in ("latency", "wide"), self.tile_policy
+        # wide plan: a layer's persistent kernel takes at most #SMs / wide_grid_div CTAs (1 = every SM; 3 measured best with 8 frames of
+        # YOLOPoint-S in flight, where three layers of different frames then share the GPU)
+        self.wide_grid_div = int(wide_grid_div or os.environ.get("YP_WIDE_GRID_DIV", "1"))
         # layer chains (one persistent kernel per network segment, yp_conv_chain_*): opt-in (chain=True or YP_CHAIN=1).  Measured on
         # B200 (YOLOPoint-S 640x640 batch 1, profiles/r02_chain.md): 1.005 ms per pass against 0.722 ms for the per-layer launch list
         # (CUDA graph + programmatic dependent launch) -- the per-layer cost is the CTA's own latency (first TMA, K loop, epilogue,

@@ -324,7 +324,7 @@ class Model(nn.Module):
                 raise RuntimeError("yolopoint_b200.Model runs inference on a CUDA (sm_100a) device only: call .cuda() first; "
                                    "there is no CPU fallback")
             self._engine = Engine(self.state_dict(), self.version, self.nc, dev, precision=self.precision, model_name=self.model_name,
-                                  tile_policy=getattr(self, "tile_policy", None))
+                                  tile_policy=getattr(self, "tile_policy", None), wide_grid_div=getattr(self, "wide_grid_div", None))
         return self._engine
 
     def invalidate_engine(self):
