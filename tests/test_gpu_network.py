@@ -368,3 +368,38 @@ def test_version_x_whole_frame_pipeline():
     if pts.shape == pts_ref.shape and np.array_equal(pts[:2], pts_ref[:2]) and pts.shape[1]:
         assert desc.shape == (320, pts.shape[1])
         np.testing.assert_allclose(desc, desc_ref, rtol=0, atol=1e-5)
+
+
+def test_frames_in_flight_device_path_host_far_ahead():
+    """Device path with the host enqueuing far ahead of the GPU (40 frames, 3 in flight, no synchronisation in the loop): the copy of
+    frame i into a context's input buffer must not overtake the conversion kernel of frame i - 4 that used the same buffer
+    (``FramePipeline.plan`` orders the current stream behind the context's previous frame).  Per-frame counts are logged on the
+    context's own stream and compared with the one-at-a-time sequence."""
+    m, _ = build("n")
+    H, W = 192, 256
+    dev = torch.device("cuda:0")
+    frames = [torch.from_numpy(synthetic_frame(H, W, s)[None]).to(dev) for s in range(10)]
+    order = [(7 * i) % 10 for i in range(40)]
+    ref_pipe = FramePipeline(m, 1, H, W, slot=6)
+    ref = []
+    for j in order:
+        ref_pipe.plan.frame_in.copy_(frames[j])
+        k = ref_pipe.step_device(True)
+        torch.cuda.synchronize()
+        ref.append(ref_pipe.d_counts[k][:3].cpu().numpy().copy())
+    pipe = FramePipeline(m, 1, H, W, slot=7, frames_in_flight=3)
+    pipe.prepare(host=False)
+    log = torch.zeros((len(order), 3, 1), dtype=torch.int32, device=dev)
+    big = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    for _ in range(20):
+        big.normal_()              # keep the GPU busy so that the host loop below runs far ahead of it
+    for i, j in enumerate(order):
+        pipe.plan.frame_in.copy_(frames[j])
+        k = pipe.step_device(True)
+        with torch.cuda.stream(pipe.cs[k]):
+            log[i].copy_(pipe.d_counts[k][:3])
+    pipe.join()
+    torch.cuda.synchronize()
+    got = log.cpu().numpy()
+    for i in range(len(order)):
+        np.testing.assert_array_equal(got[i], ref[i], err_msg=f"frame {i}")

@@ -60,8 +60,14 @@ class FramePipeline:
 
     @property
     def plan(self):
-        """Activation buffers / launch list of the context the NEXT frame runs in (``plan.frame_in`` is where that frame goes)."""
-        return self.plans[self.parity]
+        """Activation buffers / launch list of the context the NEXT frame runs in (``plan.frame_in`` / ``plan.x_in`` is where that frame
+        goes).  With frames in flight the context's previous frame may still be queued on its own stream: the current stream is made
+        to wait for it here, so that whatever the caller enqueues next on the current stream (the copy of the new frame into
+        ``frame_in``) cannot overtake the input conversion of the frame that used the buffer before."""
+        k = self.parity
+        if self.F > 1 and self._ctx_used[k]:
+            torch.cuda.current_stream(self.eng.device).wait_event(self.ev_frame[k])
+        return self.plans[k]
 
     def max_pts_bound(self) -> int:
         """Keypoints that can survive nms_fast with radius r on an H x W frame: survivors are >= r+1 pixels apart (Chebyshev)."""
