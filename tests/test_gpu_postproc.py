@@ -243,3 +243,25 @@ def test_homography_adaptation_vs_oracle_random(B, H, W):
     # letterbox slicing as the reference applies it
     padded = yp.homography_adaptation(torch.from_numpy(heat).cuda(), torch.from_numpy(mask).cuda(), torch.from_numpy(hinv).cuda(), pad=(4, 6, 3, 5))
     assert padded.shape == (1, len(range(H)[4:W - 6]), len(range(W)[3:H - 5]))       # (:103-109 bound the rows by the WIDTH and vice versa)
+
+
+@pytest.mark.parametrize("cap,algo", [(4096, "tc"), (1024, "simt")])
+def test_two_way_matcher_graph_equals_direct_call(cap, algo):
+    """ops.TwoWayMatcher (static operands + one CUDA graph per call) against ops.match_two_way on successive descriptor sets of
+    different sizes below the capacity: identical matches and counts (the device-side counts are read at replay time)."""
+    D = 256
+    matcher = ops.TwoWayMatcher(cap, cap, D, "cuda", 0.7, algo=algo)
+    g = torch.Generator(device="cpu").manual_seed(cap)
+    for n1, n2 in ((cap, cap), (cap - 37, cap - 500), (cap // 2, cap // 3)):
+        d1 = torch.randn(n1, D, generator=g); d1 /= d1.norm(dim=1, keepdim=True)
+        d2 = torch.randn(n2, D, generator=g)
+        k = min(n1, n2)
+        d2[:k] = d1[torch.randperm(n1, generator=g)[:k]] + 0.05 * torch.randn(k, D, generator=g)
+        d2 /= d2.norm(dim=1, keepdim=True)
+        d1, d2 = d1.cuda().contiguous(), d2.cuda().contiguous()
+        m_ref, c_ref = ops.match_two_way(d1, None, d2, None, 0.7, algo=algo)
+        m, c = matcher(d1, d2)
+        torch.cuda.synchronize()
+        n = int(c_ref.item())
+        assert int(c.item()) == n and n > 0
+        assert torch.equal(m[:n], m_ref[:n])

@@ -37,7 +37,14 @@ def main():
         d2 = d1[perm] + 0.05 * torch.randn(N, D, generator=g); d2 /= d2.norm(dim=1, keepdim=True)   # planted matches
         d1, d2 = d1.to(dev), d2.to(dev).contiguous()
         algo = os.environ.get("YP_MATCH_ALGO", "auto")
-        fn = (lambda: match_two_way_sharded(d1, d2, 0.7)) if world > 1 else (lambda: ops.match_two_way(d1, None, d2, None, 0.7, algo=algo))
+        if world > 1:
+            fn = lambda: match_two_way_sharded(d1, d2, 0.7)
+        elif os.environ.get("YP_MATCH_GRAPH", "1") != "0":
+            matcher = ops.TwoWayMatcher(N, N, D, dev, 0.7, algo=algo)     # static operands + one CUDA graph per call
+            matcher.d1.copy_(d1); matcher.d2.copy_(d2)
+            fn = lambda m=matcher: m(m.d1, m.d2)
+        else:
+            fn = lambda: ops.match_two_way(d1, None, d2, None, 0.7, algo=algo)
         for _ in range(3):
             m, cnt = fn()
         torch.cuda.synchronize()
