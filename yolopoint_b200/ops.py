@@ -257,6 +257,8 @@ class TwoWayMatcher:
         self.d2 = torch.zeros((n2_cap, D), dtype=torch.float32, device=dev)
         self.n1 = torch.full((1,), n1_cap, dtype=torch.int32, device=dev)
         self.n2 = torch.full((1,), n2_cap, dtype=torch.int32, device=dev)
+        if algo == "auto":      # without the per-call host work the tensor-core pass wins from 1024 descriptors on (0.030 vs 0.038 ms; 2048: 0.046 vs 0.088)
+            algo = "tc" if min(n1_cap, n2_cap) >= 1024 and D % 16 == 0 else "simt"
         self.nn_thresh, self.algo = float(nn_thresh), algo
         self.graph = None
         self.matches = self.count = None
