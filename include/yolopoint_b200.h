@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YP_ABI_VERSION 8
+#define YP_ABI_VERSION 9
 
 typedef enum {
   YP_OK = 0,
@@ -406,6 +406,42 @@ int yp_homography_adaptation(const float* heat, const float* mask, const float* 
 size_t yp_detector_loss_workspace_bytes(int32_t B, int32_t Hc, int32_t Wc);
 int yp_detector_loss(const float* semi, int64_t sB, int64_t sC, int64_t sH, int64_t sW, const float* labels2d, const float* mask2d,
                      int32_t B, int32_t Hc, int32_t Wc, float* dsemi, float* out2, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Object loss of the training step over all Detect levels, forward and gradient (csrc/object_loss.cu).
+ * Replaces ComputeObjectLoss.__call__ (utils/loss_functions.py:120-216: CIoU box loss via bbox_iou(..., CIoU=True) of
+ * utils/metrics_yolo.py:202-240, BCE objectness against the detached, clamped CIoU, BCE classes) on the fixed-shape target plan
+ * of ComputeObjectLoss.build_targets (:218-234; all 5 x anchors x targets assignment candidates with a validity mask).
+ * Per level: pred / dpred [cells, no] fp32 rows (cells = B * na * ny * nx, row = (x, y, w, h, obj, classes...) logits);
+ * valid [E] bytes, cell [E] flat (image, anchor, gj, gi) row index, tbox [E,4] target box relative to the cell, anchor [E,2] in cells,
+ * cls [E]; balance = the level's objectness weight.  dpred is fully written (d loss / d pred).
+ * out4 = (loss, box, obj, cls) with loss = w_box * box + w_obj * obj + w_cls * cls as the reference sums them before its batch-size factor.
+ * ---------------------------------------------------------------------------------------------- */
+#define YP_OBJ_LOSS_MAX_LEVELS 5
+typedef struct YpObjLossLevel {
+  const float* pred;
+  float* dpred;
+  const uint8_t* valid;
+  const int64_t* cell;
+  const float* tbox;
+  const float* anchor;
+  const int64_t* cls;
+  int64_t cells;
+  int32_t E;
+  float balance;
+} YpObjLossLevel;
+
+typedef struct YpObjLossParams {
+  float cp, cn;          /* positive / negative class targets (label smoothing) */
+  float cls_pw, obj_pw;  /* BCE positive-class weights */
+  float gr;              /* objectness target = (1 - gr) + gr * max(CIoU, 0) */
+  float w_box, w_obj, w_cls;
+  float eps;             /* 1e-7 in the reference */
+} YpObjLossParams;
+
+size_t yp_object_loss_workspace_bytes(const YpObjLossLevel* levels, int32_t nl);
+int yp_object_loss(const YpObjLossLevel* levels, int32_t nl, int32_t no, int32_t nc, const YpObjLossParams* hp, float* out4,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

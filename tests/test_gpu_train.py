@@ -246,3 +246,48 @@ def test_fused_detector_loss_matches_reference_golden_and_autograd(golden):
     assert abs(la.item() - lb.item()) < 1e-6 * abs(lb.item())
     assert _rel(xa.grad, xb.grad.double()) < 1e-5
     assert torch.equal(det.from_2d(x, lab, msk), det.from_2d(x, lab, msk))      # fixed-order reductions: bit-reproducible
+
+
+def test_fused_object_loss_matches_reference_golden_and_torch(golden):
+    """csrc/object_loss.cu (target claim + CIoU + objectness / class BCE over all levels, forward and gradient) against the vectors of
+    the UNMODIFIED reference (src/utils/loss_functions.py:120-216) and against the PyTorch statement of the same loss
+    (ComputeObjectLoss._call_torch) on crowded targets (many candidates per cell: owner rule, summed gradients), with label smoothing
+    and positive-class weights, on an empty label list, and with an upstream gradient factor."""
+    from yolopoint_b200 import Model, losses as Lz
+    cfg = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, iou_t=0.2, anchor_t=4.0, label_smoothing=0.0, fl_gamma=0.0)
+    g = golden("losses.npz")
+    torch.manual_seed(0)
+    m = Model(names=[str(i) for i in range(80)], version="n").cuda()
+    crit = Lz.ComputeObjectLoss(m, cfg, "cuda")
+    assert crit.fused
+    p = [torch.from_numpy(g[f"p{i}"]).cuda().requires_grad_(True) for i in range(3)]
+    loss, items = crit(p, torch.from_numpy(g["targets"]).cuda())
+    loss.backward()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["lobj"], rtol=2e-6)
+    np.testing.assert_allclose(items.cpu().numpy(), g["lobj_items"], rtol=2e-6)
+    np.testing.assert_allclose(p[0].grad.cpu().numpy(), g["g0"], rtol=2e-5, atol=1e-8)
+
+    cfg2 = dict(cfg, cls_pw=1.7, obj_pw=0.6, label_smoothing=0.1)
+    crit2 = Lz.ComputeObjectLoss(m, cfg2, "cuda")
+    gen = torch.Generator().manual_seed(11)
+    B = 4
+    shapes = [(B, 3, 24, 32, 85), (B, 3, 12, 16, 85), (B, 3, 6, 8, 85)]
+    for nt in (0, 1, 300):
+        tg = torch.cat((torch.randint(0, B, (nt, 1), generator=gen).float(), torch.randint(0, 80, (nt, 1), generator=gen).float(),
+                        0.3 + 0.4 * torch.rand(nt, 2, generator=gen), 0.02 + 0.5 * torch.rand(nt, 2, generator=gen)), 1).cuda()   # crowded centre
+        base = [torch.randn(s, generator=gen).cuda() * 1.5 for s in shapes]
+        pa = [t.clone().requires_grad_(True) for t in base]
+        pb = [t.clone().requires_grad_(True) for t in base]
+        la, ia = crit2(pa, tg)
+        crit2.fused = False
+        lb, ib = crit2(pb, tg)
+        crit2.fused = True
+        (la * 2.5).sum().backward()
+        (lb * 2.5).sum().backward()
+        assert la.shape == lb.shape == (1,) and ia.shape == ib.shape == (3,)
+        assert abs(la.item() - lb.item()) < 3e-6 * abs(lb.item()), (nt, la.item(), lb.item())
+        assert _rel(ia, ib.double()) < 3e-6, (nt, ia, ib)
+        for a, b in zip(pa, pb):
+            assert _rel(a.grad, b.grad.double()) < 2e-5, nt
+        la2, _ = crit2([t.clone() for t in base], tg)
+        assert torch.equal(la2, la.detach())                 # loss values: fixed-order reductions

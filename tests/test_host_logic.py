@@ -120,7 +120,7 @@ def test_c_abi_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.yp_abi_version() == 8
+    assert L.yp_abi_version() == 9
     # struct layouts must agree with the header (sizes only; offsets follow from the C rules both sides use)
     assert ctypes.sizeof(_lib.YpView) == 48 and ctypes.sizeof(_lib.YpNmsParams) == 40
 

@@ -93,3 +93,39 @@ def test_train_step_options_on_cpu():
     assert vals["infonce"] > 1.5 and vals["hinge"] < 1.5           # ln(1 + 10) = 2.4 at random init vs a hinge of order 1
     with pytest.raises(ValueError):
         TrainStep(m, desc_loss="triplet")
+
+
+def test_box_loss_math_matches_autograd(tmp_path):
+    """The per-candidate arithmetic of the fused object-loss kernel (yolopoint_b200/csrc/box_loss_math.cuh: box decode, CIoU and its
+    gradient carried by dual numbers, BCE-with-logits) compiled for the HOST and compared with PyTorch autograd in fp64 over 20 000
+    random candidates: CIoU 1e-6 abs, gradient 2e-6 abs (values of order 1)."""
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path / "libboxloss_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(here, "box_loss_host.cpp")])
+    L = C.CDLL(so)
+    rs = np.random.RandomState(0)
+    n = 20000
+    q = (rs.randn(n, 4) * 2).astype(np.float32)
+    an = rs.uniform(0.5, 8, (n, 2)).astype(np.float32)
+    tb = np.concatenate([rs.uniform(-0.5, 1.5, (n, 2)), rs.uniform(0.2, 12, (n, 2))], 1).astype(np.float32)
+    ci, gr = np.zeros(n, np.float32), np.zeros((n, 4), np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.yp_host_candidate_ciou(ptr(q), ptr(an), ptr(tb), n, C.c_float(1e-7), ptr(ci), ptr(gr))
+    tq = torch.tensor(q, dtype=torch.float64, requires_grad=True)
+    xy, wh = tq[:, 0:2].sigmoid() * 2 - 0.5, (tq[:, 2:4].sigmoid() * 2) ** 2 * torch.tensor(an, dtype=torch.float64)
+    c = Lz.ciou_xywh(torch.cat((xy, wh), 1), torch.tensor(tb, dtype=torch.float64))
+    c.sum().backward()
+    assert np.abs(ci - c.detach().numpy()).max() < 1e-6
+    assert np.abs(gr - tq.grad.numpy()).max() < 2e-6
+    x, t = (rs.randn(n) * 5).astype(np.float32), rs.rand(n).astype(np.float32)
+    lo, dx = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    L.yp_host_bce_logits(ptr(x), ptr(t), n, C.c_float(1.7), ptr(lo), ptr(dx))
+    tx = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(tx, torch.tensor(t, dtype=torch.float64), pos_weight=torch.tensor([1.7], dtype=torch.float64),
+                                                               reduction="none")
+    ref.sum().backward()
+    np.testing.assert_allclose(lo, ref.detach().numpy(), rtol=2e-6, atol=1e-6)
+    assert np.abs(dx - tx.grad.numpy()).max() < 1e-6

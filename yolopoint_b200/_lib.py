@@ -49,6 +49,16 @@ class YpNmsParams(C.Structure):
                 ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_wh", C.c_float), ("class_mask", C.c_void_p)]
 
 
+class YpObjLossLevel(C.Structure):
+    _fields_ = [("pred", C.c_void_p), ("dpred", C.c_void_p), ("valid", C.c_void_p), ("cell", C.c_void_p), ("tbox", C.c_void_p),
+                ("anchor", C.c_void_p), ("cls", C.c_void_p), ("cells", C.c_int64), ("E", C.c_int32), ("balance", C.c_float)]
+
+
+class YpObjLossParams(C.Structure):
+    _fields_ = [("cp", C.c_float), ("cn", C.c_float), ("cls_pw", C.c_float), ("obj_pw", C.c_float), ("gr", C.c_float),
+                ("w_box", C.c_float), ("w_obj", C.c_float), ("w_cls", C.c_float), ("eps", C.c_float)]
+
+
 _i32, _i64, _f32, _vp, _sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 _PV, _PC, _PN = C.POINTER(YpView), C.POINTER(YpConvDesc), C.POINTER(YpNmsParams)
 
@@ -98,6 +108,8 @@ SIGNATURES = {
     "yp_homography_adaptation": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "yp_detector_loss_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "yp_detector_loss": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "yp_object_loss_workspace_bytes": (_sz, [C.POINTER(YpObjLossLevel), _i32]),
+    "yp_object_loss": (_i32, [C.POINTER(YpObjLossLevel), _i32, _i32, _i32, C.POINTER(YpObjLossParams), _vp, _vp, _sz, _vp]),
     "yp_match_partial": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "yp_match_finalize": (_i32, [_vp, _vp, _i32, _vp, _i32, _f32, _vp, _vp, _vp]),
 }
@@ -128,7 +140,7 @@ def lib(require_device: bool = False):
                     except AttributeError as e:  # pragma: no cover
                         raise YoloPointB200Error(f"{LIB_PATH} does not export {name}") from e
                     fn.restype, fn.argtypes = res, args
-                if handle.yp_abi_version() != 8:
+                if handle.yp_abi_version() != 9:
                     raise YoloPointB200Error("ABI version mismatch between _lib.py and libyolopoint_b200.so")
                 _lib = handle
     if require_device:

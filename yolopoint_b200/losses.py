@@ -98,6 +98,7 @@ class ComputeObjectLoss:
         self.na, self.nc, self.nl, self.anchors = det.na, det.nc, det.nl, det.anchors
         self.balance = [4.0, 1.0, 0.4] if det.nl == 3 else [4.0, 1.0, 0.25, 0.06, 0.02]
         self.gr = 1.0
+        self.fused = True           # CUDA predictions: csrc/object_loss.cu (no fallback: a missing library raises)
 
     # -- labels only ---------------------------------------------------------------------------
     def build_targets(self, p, targets) -> TargetPlan:
@@ -134,9 +135,20 @@ class ComputeObjectLoss:
 
     # -- predictions -----------------------------------------------------------------------------
     def __call__(self, p, targets, built: Optional[TargetPlan] = None):
-        """-> (loss [1], detached (box, obj, cls) terms [3]).  ``built`` = a precomputed ``build_targets(p, targets)``."""
+        """-> (loss [1], detached (box, obj, cls) terms [3]).  ``built`` = a precomputed ``build_targets(p, targets)``.
+
+        On a CUDA device the whole loss over all levels and its gradient are four kernel launches (csrc/object_loss.cu,
+        ``fused=True``, the default there); ``fused=False`` / CPU tensors run the PyTorch statement of the same arithmetic below,
+        which is what the CPU tests pin to the reference's vectors and what the GPU tests check the kernels against."""
         dev = self.device
         plan = built if built is not None else self.build_targets(p, targets)
+        if self.fused and all(pi.is_cuda for pi in p):
+            out4 = _ObjectLossFused.apply(self, plan, *p)
+            return out4[0:1], out4[1:4].detach()
+        return self._call_torch(p, plan)
+
+    def _call_torch(self, p, plan: TargetPlan):
+        dev = self.device
         lbox = torch.zeros(1, device=dev)
         lobj = torch.zeros(1, device=dev)
         lcls = torch.zeros(1, device=dev)
@@ -170,6 +182,53 @@ class ComputeObjectLoss:
             lobj = lobj + F.binary_cross_entropy_with_logits(obj_logit, tobj[:-1], pos_weight=self.obj_pw) * self.balance[i]
         lbox, lobj, lcls = lbox * self.hyp["box"], lobj * self.hyp["obj"], lcls * self.hyp["cls"]
         return lbox + lobj + lcls, torch.cat((lbox, lobj, lcls)).detach()
+
+
+class _ObjectLossFused(torch.autograd.Function):
+    """ComputeObjectLoss over all Detect levels on the fixed-shape target plan: loss terms and d loss / d predictions from
+    ``yp_object_loss`` (claim / candidate / cells / finalize kernels, csrc/object_loss.cu).  -> [4] = (loss, box, obj, cls)."""
+
+    @staticmethod
+    def forward(ctx, crit, plan, *p):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib(require_device=True)
+        dev = p[0].device
+        nl, no = len(p), p[0].shape[-1]
+        assert nl <= 5 and all(pi.dtype == torch.float32 and pi.shape[-1] == no for pi in p), [(pi.dtype, pi.shape) for pi in p]
+        keep = []                                                   # device buffers the launches read: alive until enqueued
+        levels = (_lib.YpObjLossLevel * nl)()
+        grads = []
+        for i, pi in enumerate(p):
+            lv = plan.levels[i]
+            rows = pi.detach().contiguous()
+            d = torch.empty_like(rows)
+            E = int(lv["valid"].numel())
+            valid = lv["valid"].to(device=dev, dtype=torch.bool).contiguous()
+            cell = lv["cell"].to(device=dev, dtype=torch.int64).contiguous()
+            tbox = lv["tbox"].to(device=dev, dtype=torch.float32).contiguous()
+            anchor = lv["anchor"].to(device=dev, dtype=torch.float32).contiguous()
+            cls = lv["cls"].to(device=dev, dtype=torch.int64).contiguous()
+            keep += [rows, valid, cell, tbox, anchor, cls]
+            grads.append(d)
+            levels[i].pred, levels[i].dpred = rows.data_ptr(), d.data_ptr()
+            levels[i].valid, levels[i].cell, levels[i].tbox = valid.data_ptr(), cell.data_ptr(), tbox.data_ptr()
+            levels[i].anchor, levels[i].cls = anchor.data_ptr(), cls.data_ptr()
+            levels[i].cells, levels[i].E, levels[i].balance = rows.numel() // no, E, float(crit.balance[i])
+            assert int(lv["cells"]) == rows.numel() // no
+        hp = _lib.YpObjLossParams(cp=crit.cp, cn=crit.cn, cls_pw=float(crit.hyp["cls_pw"]), obj_pw=float(crit.hyp["obj_pw"]), gr=crit.gr,
+                                  w_box=float(crit.hyp["box"]), w_obj=float(crit.hyp["obj"]), w_cls=float(crit.hyp["cls"]), eps=1e-7)
+        ws = torch.empty(max(int(L.yp_object_loss_workspace_bytes(levels, nl)), 16), dtype=torch.uint8, device=dev)
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        _lib.check(L.yp_object_loss(levels, nl, no, crit.nc, C.byref(hp), out4.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        ctx.save_for_backward(*grads)
+        return out4
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = grad_out[0]                                             # only the total (out4[0]) carries gradient; the terms are reports
+        return (None, None) + tuple(d * g for d in ctx.saved_tensors)
 
 
 def labels2Dto3D(labels, cell_size=8, add_dustbin=True):
