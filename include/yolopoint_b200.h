@@ -443,6 +443,32 @@ size_t yp_object_loss_workspace_bytes(const YpObjLossLevel* levels, int32_t nl);
 int yp_object_loss(const YpObjLossLevel* levels, int32_t nl, int32_t no, int32_t nc, const YpObjLossParams* hp, float* out4,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Training-step glue on bf16 NHWC activations (csrc/glue.cu), each with its backward pass.
+ * yp_cat_nhwc_fwd / _bwd: torch.cat(parts, 1) (models/common.py:123-135, 151-165) with the resampling the network applies to a
+ *   part on the way in -- nn.Upsample(scale_factor=2, "nearest") (models/YOLOPoint.py:214, 222-223) or nn.MaxPool2d(2, 2)
+ *   (models/YOLOPoint.py:311).  out / dout: [B,H,W,sum C] contiguous; part i: src (and grad) [B,Hs,Ws,C_i] contiguous with
+ *   (Hs, Ws) = (H, W) for YP_CAT_COPY, (H/2, W/2) for YP_CAT_UP2, (2H, 2W) for YP_CAT_POOL2.  Backward writes every non-null
+ *   grad (YP_CAT_POOL2 also reads src: the gradient goes to the first maximum of each window in raster order, as max_pool2d's).
+ * yp_sppf_train_fwd / _bwd: SPPF's cat(x, m(x), m(m(x)), m(m(m(x)))), m = MaxPool2d(5, 1, 2) (models/common.py:213-229).
+ *   x / dx [B,H,W,C], out4 / dout4 [B,H,W,4C], arg [3][B][H*W][C] uint16 = the pixel of x every pooled value came from
+ *   (written by the forward pass, read by the backward pass).  C % 8 == 0, H*W <= 65535.
+ * ---------------------------------------------------------------------------------------------- */
+#define YP_CAT_MAX_PARTS 4
+#define YP_CAT_COPY 0
+#define YP_CAT_UP2 1
+#define YP_CAT_POOL2 2
+typedef struct YpCatPart {
+  const void* src;
+  void* grad;
+  int32_t C;
+  int32_t mode;
+} YpCatPart;
+int yp_cat_nhwc_fwd(const YpCatPart* parts, int32_t n, void* out, int32_t B, int32_t H, int32_t W, void* stream);
+int yp_cat_nhwc_bwd(const YpCatPart* parts, int32_t n, const void* dout, int32_t B, int32_t H, int32_t W, void* stream);
+int yp_sppf_train_fwd(const void* x, void* out4, uint16_t* arg, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+int yp_sppf_train_bwd(const void* dout4, const uint16_t* arg, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ YP_ALGO_TCGEN05, YP_ALGO_SIMT = 0, 1
 YP_EPI_L2NORM = 1
 YP_EPI_ROWMIN = 4
 YP_UP_PARITY = 16
+YP_CAT_COPY, YP_CAT_UP2, YP_CAT_POOL2 = 0, 1, 2
 STATUS = {0: "YP_OK", -1: "YP_ERR_SHAPE", -2: "YP_ERR_ALIGN", -3: "YP_ERR_ARCH", -4: "YP_ERR_CUDA",
           -5: "YP_ERR_CAPACITY", -6: "YP_ERR_ARG"}
 
@@ -47,6 +48,10 @@ class YpWgradDesc(C.Structure):
 class YpNmsParams(C.Structure):
     _fields_ = [("conf_thres", C.c_float), ("iou_thres", C.c_float), ("multi_label", C.c_int32), ("agnostic", C.c_int32),
                 ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_wh", C.c_float), ("class_mask", C.c_void_p)]
+
+
+class YpCatPart(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("grad", C.c_void_p), ("C", C.c_int32), ("mode", C.c_int32)]
 
 
 class YpObjLossLevel(C.Structure):
@@ -110,6 +115,10 @@ SIGNATURES = {
     "yp_detector_loss": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "yp_object_loss_workspace_bytes": (_sz, [C.POINTER(YpObjLossLevel), _i32]),
     "yp_object_loss": (_i32, [C.POINTER(YpObjLossLevel), _i32, _i32, _i32, C.POINTER(YpObjLossParams), _vp, _vp, _sz, _vp]),
+    "yp_cat_nhwc_fwd": (_i32, [C.POINTER(YpCatPart), _i32, _vp, _i32, _i32, _i32, _vp]),
+    "yp_cat_nhwc_bwd": (_i32, [C.POINTER(YpCatPart), _i32, _vp, _i32, _i32, _i32, _vp]),
+    "yp_sppf_train_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "yp_sppf_train_bwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "yp_match_partial": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "yp_match_finalize": (_i32, [_vp, _vp, _i32, _vp, _i32, _f32, _vp, _vp, _vp]),
 }

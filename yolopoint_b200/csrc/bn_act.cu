@@ -109,30 +109,32 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const uint4* __re
   }
 }
 
-// per channel: batch statistics -> (mean, rstd, scale, shift); running statistics update (momentum, unbiased variance)
-__global__ void bn_finalize_kernel(const float* __restrict__ acc, long long P, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps, float* __restrict__ save) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// per channel: batch statistics -> (mean, rstd, scale, shift).  Evaluated by every thread of the normalise pass for its own 8 channels
+// (a few fp64 operations per thread; a separate finalize launch per BatchNorm cost more in launch gaps than the arithmetic); the
+// threads of the first pixel chunk also publish the four vectors for the backward pass and update the running statistics
+// (momentum, unbiased variance).
+struct BnStats {
+  float mean, rstd, scale, shift;
+  double var;
+};
+__device__ __forceinline__ BnStats bn_channel_stats(const float* __restrict__ acc, long long P, int C, int c, float gamma, float beta, float eps) {
   const double n = static_cast<double>(P);
   const double m = acc[c] / n;
   double var = acc[C + c] / n - m * m;
   if (var < 0.0) var = 0.0;
-  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  const float sc = gamma[c] * rstd;
-  save[c] = static_cast<float>(m);
-  save[C + c] = rstd;
-  save[2 * C + c] = sc;
-  save[3 * C + c] = beta[c] - static_cast<float>(m) * sc;
-  if (running_mean) {
-    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(m);
-    const double unbiased = P > 1 ? var * n / (n - 1.0) : var;
-    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
-  }
+  BnStats r;
+  r.var = var;
+  r.mean = static_cast<float>(m);
+  r.rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  r.scale = gamma * r.rstd;
+  r.shift = beta - r.mean * r.scale;
+  return r;
 }
 
-__global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const uint4* __restrict__ y, long long P, int C, const float* __restrict__ save, int act,
-                                                                  uint4* __restrict__ out, int rows_per_block) {
+__global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const uint4* __restrict__ y, long long P, int C, const float* __restrict__ acc,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
+                                                                  float* __restrict__ save, int act, uint4* __restrict__ out, int rows_per_block) {
   const Layout L = make_layout(C);
   const int G = C / 8;
   const int gl = threadIdx.x % L.gpb, rl = threadIdx.x / L.gpb;
@@ -140,8 +142,22 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_fwd_kernel(const uint4* _
   const long long p0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long p1 = p0 + rows_per_block < P ? p0 + rows_per_block : P;
   float scale[8], shift[8];
+  const bool publish = blockIdx.x == 0 && rl == 0;      // one thread per channel group
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { scale[e] = save[2 * C + g * 8 + e]; shift[e] = save[3 * C + g * 8 + e]; }
+  for (int e = 0; e < 8; ++e) {
+    const int c = g * 8 + e;
+    const BnStats st = bn_channel_stats(acc, P, C, c, gamma[c], beta[c], eps);
+    scale[e] = st.scale; shift[e] = st.shift;
+    if (publish) {
+      save[c] = st.mean; save[C + c] = st.rstd; save[2 * C + c] = st.scale; save[3 * C + c] = st.shift;
+      if (running_mean) {
+        const double n = static_cast<double>(P);
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * st.mean;
+        const double unbiased = P > 1 ? st.var * n / (n - 1.0) : st.var;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+      }
+    }
+  }
   auto row = [&](const uint4& yu, long long p) {
     float v[8];
     unpack8(yu, v);
@@ -248,11 +264,10 @@ extern "C" int yp_bn_act_fwd(const void* y, int64_t P, int32_t C, const float* g
   YP_CUDA_OK(cudaMemsetAsync(acc, 0, 2 * sizeof(float) * C, st));
   int rc = yp::launch_reduce(0, y, nullptr, P, C, nullptr, act, acc, st);
   if (rc != YP_OK) return rc;
-  yp::bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, P, C, gamma, beta, running_mean, running_var, momentum, eps, save);
-  YP_LAUNCH_OK();
   int rows = 0;
   const dim3 grid = yp::pass_grid(P, C, 8, &rows);
-  yp::bn_apply_fwd_kernel<<<grid, yp::kBnThreads, 0, st>>>(static_cast<const uint4*>(y), P, C, save, act, static_cast<uint4*>(out), rows);
+  yp::bn_apply_fwd_kernel<<<grid, yp::kBnThreads, 0, st>>>(static_cast<const uint4*>(y), P, C, acc, gamma, beta, running_mean, running_var, momentum, eps, save,
+                                                        act, static_cast<uint4*>(out), rows);
   YP_LAUNCH_OK();
   return YP_OK;
 }

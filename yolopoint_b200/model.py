@@ -34,6 +34,19 @@ def make_divisible(x, divisor):  # src/utils/general_yolo.py:534
     return math.ceil(x / divisor) * divisor
 
 
+def _cat(mod, parts, modes=None):
+    """torch.cat(parts, 1) where part i is first passed through nn.Upsample(2, "nearest") (modes[i] == "up2") or nn.MaxPool2d(2, 2)
+    ("pool2").  In train mode on the B200 backend (train.enable marks the modules) this is one kernel forward and one backward
+    (csrc/glue.cu); otherwise the PyTorch ops of the reference."""
+    modes = list(modes) if modes is not None else ["copy"] * len(parts)
+    if getattr(mod, "_yp_glue", False) and mod.training:
+        from . import train as _train
+        if _train.glue_ok(parts):
+            return _train.cat_tc(parts, modes)
+    resample = {"copy": lambda t: t, "up2": lambda t: F.interpolate(t, scale_factor=(2, 2), mode="nearest"), "pool2": lambda t: F.max_pool2d(t, 2, 2)}
+    return torch.cat([resample[m](t) for t, m in zip(parts, modes)], 1)
+
+
 class Conv(nn.Module):
     """conv (no bias) -> BN -> SiLU (src/models/common.py:22-34)."""
 
@@ -74,7 +87,7 @@ class C3(nn.Module):
         self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, e=1.0) for _ in range(n)))
 
     def forward(self, x):
-        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+        return self.cv3(_cat(self, (self.m(self.cv1(x)), self.cv2(x))))
 
 
 class Bottleneckv8(nn.Module):
@@ -105,7 +118,7 @@ class C2f(nn.Module):
     def forward(self, x):
         y = list(self.cv1(x).chunk(2, 1))
         y.extend(m(y[-1]) for m in self.m)
-        return self.cv2(torch.cat(y, 1))
+        return self.cv2(_cat(self, y))
 
 
 class SPPF(nn.Module):
@@ -120,6 +133,10 @@ class SPPF(nn.Module):
 
     def forward(self, x):
         x = self.cv1(x)
+        if getattr(self, "_yp_glue", False) and self.training and self.m.kernel_size == 5:
+            from . import train as _train
+            if _train.glue_ok((x,)) and x.shape[2] * x.shape[3] <= 2048:
+                return self.cv2(_train.sppf_cat_tc(x))      # pooling cascade + concat: one kernel forward, one backward (csrc/glue.cu)
         y1 = self.m(x)
         y2 = self.m(y1)
         return self.cv2(torch.cat((x, y1, y2, self.m(y2)), 1))
@@ -189,15 +206,15 @@ class YOLOPoint(nn.Module):
         x = self.Conv3(xa)
         semi = self.ConvDet(self.BottleneckDet(x)).float()
         xb = self.Bottleneck2(x)
-        desc = torch.cat((self.ConvDescA(xa), self.ups(self.ConvDescB(xb))), 1)
+        desc = _cat(self, (self.ConvDescA(xa), self.ConvDescB(xb)), ("copy", "up2"))
         desc = self.ConvDesc(self.BottleneckDesc(desc)).float()
         desc = desc.div(torch.unsqueeze(torch.norm(desc, p=2, dim=1), 1))
         xc = self.Bottleneck3(self.Conv4(xb))
         xd = self.Conv6(self.SPPooling(self.Bottleneck4(self.Conv5(xc))))
-        xe = self.Conv7(self.Bottleneck5(torch.cat((self.ups(xd), xc), 1)))
-        xf = self.Bottleneck6(torch.cat((self.ups(xe), xb), 1))
-        xg = self.Bottleneck7(torch.cat((self.Conv8(xf), xe), 1))
-        xh = self.Bottleneck8(torch.cat((self.Conv9(xg), xd), 1))
+        xe = self.Conv7(self.Bottleneck5(_cat(self, (xd, xc), ("up2", "copy"))))
+        xf = self.Bottleneck6(_cat(self, (xe, xb), ("up2", "copy")))
+        xg = self.Bottleneck7(_cat(self, (self.Conv8(xf), xe)))
+        xh = self.Bottleneck8(_cat(self, (self.Conv9(xg), xd)))
         return {"semi": semi, "desc": desc, "objects": self.Detect([xf, xg, xh])}
 
 
@@ -234,14 +251,14 @@ class YOLOPointv52(nn.Module):
         x = self.Conv3(xa)
         semi = self.BottleneckDet(x).float()
         xb = self.Bottleneck2(x)
-        desc = self.BottleneckDesc(torch.cat((self.MaxPool(xa), self.ups(self.ConvDescB(xb))), 1)).float()
+        desc = self.BottleneckDesc(_cat(self, (xa, self.ConvDescB(xb)), ("pool2", "up2"))).float()
         desc = desc.div(torch.unsqueeze(torch.norm(desc, p=2, dim=1), 1))
         xc = self.Bottleneck3(self.Conv4(xb))
         xd = self.SPPooling(self.Bottleneck4(self.Conv5(xc)))
-        xe = self.Bottleneck5(torch.cat((self.ups(xd), xc), 1))
-        xf = self.Bottleneck6(torch.cat((self.ups(xe), xb), 1))
-        xg = self.Bottleneck7(torch.cat((self.Conv8(xf), xe), 1))
-        xh = self.Bottleneck8(torch.cat((self.Conv9(xg), xd), 1))
+        xe = self.Bottleneck5(_cat(self, (xd, xc), ("up2", "copy")))
+        xf = self.Bottleneck6(_cat(self, (xe, xb), ("up2", "copy")))
+        xg = self.Bottleneck7(_cat(self, (self.Conv8(xf), xe)))
+        xh = self.Bottleneck8(_cat(self, (self.Conv9(xg), xd)))
         return {"semi": semi, "desc": desc, "objects": self.Detect([xf, xg, xh])}
 
 

@@ -283,9 +283,100 @@ class _BnActTC(torch.autograd.Function):
 
 def bn_act_tc(y: torch.Tensor, bn: nn.BatchNorm2d, act: bool) -> torch.Tensor:
     out = _BnActTC.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, act)
-    if bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+    if bn.num_batches_tracked is not None and not getattr(bn, "_yp_defer_count", False):
+        bn.num_batches_tracked.add_(1)      # (trainer.TrainStep counts all BatchNorms of a step with one foreach add instead)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# glue between the convolutions: concat (+ nearest 2x upsampling / 2x2 max pooling of a part), SPPF pooling cascade
+# ------------------------------------------------------------------------------------------------------------------
+def _glue_ok(t: torch.Tensor) -> bool:
+    return t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4 and t.shape[1] % 8 == 0
+
+
+class _CatTC(torch.autograd.Function):
+    """torch.cat(parts, 1) of bf16 channels-last tensors where part i is first upsampled 2x (nearest) or 2x2 max-pooled according
+    to ``modes[i]``: one launch forward (yp_cat_nhwc_fwd), one launch backward for all parts (yp_cat_nhwc_bwd)."""
+
+    @staticmethod
+    def forward(ctx, modes, *parts):
+        L = _lib.lib(require_device=True)
+        parts = [_cl(p) for p in parts]
+        B = parts[0].shape[0]
+        scale = {_lib.YP_CAT_COPY: (1, 1), _lib.YP_CAT_UP2: (2, 1), _lib.YP_CAT_POOL2: (1, 2)}
+        hw = [(p.shape[2] * scale[m][0] // scale[m][1], p.shape[3] * scale[m][0] // scale[m][1]) for p, m in zip(parts, modes)]
+        assert all(s == hw[0] for s in hw) and all(p.shape[0] == B for p in parts), [tuple(p.shape) for p in parts]
+        H, W = hw[0]
+        out = torch.empty((B, sum(p.shape[1] for p in parts), H, W), dtype=torch.bfloat16, device=parts[0].device, memory_format=_CL)
+        arr = (_lib.YpCatPart * len(parts))()
+        for i, (p, m) in enumerate(zip(parts, modes)):
+            arr[i].src, arr[i].grad, arr[i].C, arr[i].mode = p.data_ptr(), None, p.shape[1], m
+        _lib.check(L.yp_cat_nhwc_fwd(arr, len(parts), out.data_ptr(), B, H, W, _stream()))
+        ctx.modes, ctx.geom = tuple(modes), (B, H, W)
+        ctx.shapes = [tuple(p.shape) for p in parts]
+        ctx.save_for_backward(*[p if m == _lib.YP_CAT_POOL2 else None for p, m in zip(parts, modes)])   # pooling routes by the source values
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib(require_device=True)
+        dout = _cl(dout)
+        B, H, W = ctx.geom
+        n = len(ctx.modes)
+        grads = [torch.empty(s, dtype=torch.bfloat16, device=dout.device, memory_format=_CL) if ctx.needs_input_grad[1 + i] else None
+                 for i, s in enumerate(ctx.shapes)]
+        arr = (_lib.YpCatPart * n)()
+        for i in range(n):
+            src = ctx.saved_tensors[i]
+            arr[i].src = src.data_ptr() if src is not None else None
+            arr[i].grad = grads[i].data_ptr() if grads[i] is not None else None
+            arr[i].C, arr[i].mode = ctx.shapes[i][1], ctx.modes[i]
+        _lib.check(L.yp_cat_nhwc_bwd(arr, n, dout.data_ptr(), B, H, W, _stream()))
+        return (None, *grads)
+
+
+def cat_tc(parts, modes=None) -> torch.Tensor:
+    """cat over channels with per-part resampling (``modes``: "copy" | "up2" | "pool2"); the caller checked ``glue_ok``."""
+    code = {"copy": _lib.YP_CAT_COPY, "up2": _lib.YP_CAT_UP2, "pool2": _lib.YP_CAT_POOL2}
+    modes = [code[m] for m in (modes or ["copy"] * len(parts))]
+    return _CatTC.apply(tuple(modes), *parts)
+
+
+def glue_ok(parts) -> bool:
+    """The concat / SPPF kernels take 1..4 bf16 CUDA tensors whose channel counts are multiples of 8."""
+    return 1 <= len(parts) <= 4 and all(_glue_ok(p) for p in parts)
+
+
+class _SppfTC(torch.autograd.Function):
+    """cat(x, m(x), m(m(x)), m(m(m(x)))) with m = MaxPool2d(5, 1, 2): yp_sppf_train_fwd records the source pixel of every pooled
+    value, yp_sppf_train_bwd scatters the three pooled gradients back to them."""
+
+    @staticmethod
+    def forward(ctx, x):
+        L = _lib.lib(require_device=True)
+        x = _cl(x)
+        B, Cc, H, W = x.shape
+        out = torch.empty((B, 4 * Cc, H, W), dtype=torch.bfloat16, device=x.device, memory_format=_CL)
+        arg = torch.empty((3, B, H * W, Cc), dtype=torch.int16, device=x.device)
+        _lib.check(L.yp_sppf_train_fwd(x.data_ptr(), out.data_ptr(), arg.data_ptr(), B, H, W, Cc, _stream()))
+        ctx.save_for_backward(arg)
+        ctx.shape = (B, Cc, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib(require_device=True)
+        (arg,) = ctx.saved_tensors
+        dout = _cl(dout)
+        B, Cc, H, W = ctx.shape
+        dx = torch.empty((B, Cc, H, W), dtype=torch.bfloat16, device=dout.device, memory_format=_CL)
+        _lib.check(L.yp_sppf_train_bwd(dout.data_ptr(), arg.data_ptr(), dx.data_ptr(), B, H, W, Cc, _stream()))
+        return dx
+
+
+def sppf_cat_tc(x: torch.Tensor) -> torch.Tensor:
+    return _SppfTC.apply(x)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -324,11 +415,16 @@ class TcConv2d(nn.Conv2d):
 
 def _conv_block_forward(self, x):
     """Conv.forward (conv -> BN -> SiLU, models/common.py:30-31) with the BN + activation on the fused streaming kernels."""
-    bn = getattr(self, "bn", None)
-    if (self.training and x.is_cuda and bn is not None and isinstance(self.conv, TcConv2d) and not self.conv._tc_cudnn and bn.momentum is not None
-            and bn.track_running_stats and bn.weight is not None and bn.weight.shape[0] % 8 == 0 and isinstance(self.act, (nn.SiLU, nn.Identity))):
-        return bn_act_tc(self.conv(x), bn, isinstance(self.act, nn.SiLU))
+    if self.training and x.is_cuda and fused_bn_block(self):
+        return bn_act_tc(self.conv(x), self.bn, isinstance(self.act, nn.SiLU))
     return self._yp_plain_forward(x)
+
+
+def fused_bn_block(block) -> bool:
+    """True when a Conv block's BatchNorm + activation run on yp_bn_act_fwd / yp_bn_act_bwd in train mode."""
+    bn = getattr(block, "bn", None)
+    return (bn is not None and isinstance(block.conv, TcConv2d) and not block.conv._tc_cudnn and bn.momentum is not None
+            and bn.track_running_stats and bn.weight is not None and bn.weight.shape[0] % 8 == 0 and isinstance(block.act, (nn.SiLU, nn.Identity)))
 
 
 def _stem_weight(w: torch.Tensor) -> torch.Tensor:
@@ -373,6 +469,7 @@ def enable(model: nn.Module, cudnn_crosscheck: bool = False) -> nn.Module:
         if type(mod) in (nn.Conv2d, TcConv2d):
             mod.__class__ = TcConv2d
             mod._tc_cudnn = cudnn_crosscheck
+        mod._yp_glue = not cudnn_crosscheck         # concat / upsample / pooling on csrc/glue.cu (model._cat, SPPF.forward)
     model._tc_train = True
     return model
 
@@ -381,5 +478,6 @@ def disable(model: nn.Module) -> nn.Module:
     for mod in model.modules():
         if type(mod) is TcConv2d:
             mod.__class__ = nn.Conv2d
+        mod._yp_glue = False
     model._tc_train = False
     return model

@@ -173,6 +173,7 @@ class TrainStep:
         self.loss_heads = {}                    # shape key -> graphed _LossHead (or None when the capture failed: eager losses)
         self.graph_losses = graph_sample is not None and os.environ.get("YP_TRAIN_GRAPH_LOSSES", "1") != "0"
         self.packs, self.repack_graph = [], None
+        self._bn_counts = []
         if graph_sample is not None:
             model.train()
             if getattr(model, "train_backend", None) == "b200":
@@ -181,6 +182,11 @@ class TrainStep:
                 from . import train as _train
                 _train.enable(model)
                 model._tc_train = "b200"
+                # num_batches_tracked of all BatchNorms: one foreach add per step instead of one tiny kernel per BatchNorm per pass
+                for mod in model.modules():
+                    if _train.fused_bn_block(mod) and mod.bn.num_batches_tracked is not None:
+                        mod.bn._yp_defer_count = True
+                        self._bn_counts.append(mod.bn.num_batches_tracked)
                 self.packs = _train.attach_weight_packs(model)
                 for pk in self.packs:
                     pk.refresh()
@@ -264,6 +270,8 @@ class TrainStep:
         if self.repack_graph is not None:
             self.repack_graph.replay()          # bf16 operand copies of the weights the optimizer just updated
         loss, _ = self.losses(sample)
+        if self._bn_counts:
+            torch._foreach_add_(self._bn_counts, 2)     # two forward passes per step (frame and warped frame)
         loss.backward()
         self.reducer.finish()
         if self.gradclip:
