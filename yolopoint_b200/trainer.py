@@ -167,6 +167,8 @@ class TrainStep:
         self.det_loss = Lz.ComputeDetectorLoss(self.device)
         self.sparse_cfg = dict(SPARSE_CFG if sparse_cfg is None else sparse_cfg)
         self.reducer = FlatGradReducer(list(model.parameters()), bucket_bytes, group)
+        # (the foreach form, not fused=True: the fused kernel updates the parameters without advancing their version counters, which
+        # the operand-pack cache of train.py keys on -- eager steps would then run on stale bf16 weight copies)
         self.opt = torch.optim.Adam(model.parameters(), lr=lr)
         self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lr_lambda=lambda e: (1 - e / epochs) * (1.0 - lrf) + lrf)
         self.graphed = None
