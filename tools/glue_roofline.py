@@ -1,6 +1,6 @@
 """Training glue kernels (csrc/glue.cu) and the fused object loss (csrc/object_loss.cu) at YOLOPoint-L 640x640 batch-8 sizes:
-CUDA-event time per call (inputs rotated over > 2 x L2), algorithmic bytes / time against the measured HBM copy bandwidth, and the
-same operation with the ATen ops the reference's module tree runs.   python tools/glue_roofline.py > profiles/r02_glue_roofline.md"""
+CUDA-event time per call inside CUDA-graph replays (as the training step runs them; inputs rotated over > 2 x L2), algorithmic
+bytes / time against the measured HBM copy bandwidth, and the same operation with the ATen kernels the reference's module tree runs.   python tools/glue_roofline.py > profiles/r02_glue_roofline.md"""
 import json
 import os
 import sys
@@ -20,6 +20,7 @@ CL = torch.channels_last
 
 
 def timed(fn, n_sets, iters=30):
+    """us per call, host launches (used for the eager object-loss comparison only)."""
     for i in range(3):
         fn(i % n_sets)
     torch.cuda.synchronize()
@@ -29,60 +30,130 @@ def timed(fn, n_sets, iters=30):
         fn(i % n_sets)
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3      # us
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+def graph_timed(fn, n_sets, replays=10):
+    """us per call with the calls of all input sets captured into ONE CUDA graph (no host launch cost between kernels)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for i in range(n_sets):
+            fn(i)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(n_sets):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (replays * n_sets) * 1e3
 
 
 def rnd(*shape):
     return torch.randn(*shape, device=dev).to(torch.bfloat16).contiguous(memory_format=CL)
 
 
+A = torch.ops.aten
+CODE = {"copy": 0, "up2": 1, "pool2": 2}
 rows = []
 B = 8
 cases = [("cat(ups(xd), xc)  40x40", [(512, 20, "up2"), (512, 40, "copy")]), ("cat(ups(xe), xb)  80x80", [(256, 40, "up2"), (256, 80, "copy")]),
          ("C3 cat 160x160 (64+64)", [(64, 160, "copy"), (64, 160, "copy")]), ("C3 cat 80x80 (128+128)", [(128, 80, "copy"), (128, 80, "copy")]),
          ("v52 cat(pool(xa), ups(descB)) 80x80", [(128, 160, "pool2"), (128, 40, "up2")])]
-ref_op = {"copy": lambda t: t, "up2": lambda t: F.interpolate(t, scale_factor=(2, 2), mode="nearest"), "pool2": lambda t: F.max_pool2d(t, 2, 2)}
-for name, parts in cases:
-    modes = [m for _, _, m in parts]
-    out_hw = parts[-1][1] * {"copy": 1, "up2": 2, "pool2": 1}[modes[-1]] // (2 if modes[-1] == "pool2" else 1)
-    nbytes_src = sum(B * c * hw * hw * 2 for c, hw, _ in parts)
-    nbytes_out = B * sum(c for c, _, _ in parts) * out_hw * out_hw * 2
-    n_sets = max(2, int(2 * 130e6 / (nbytes_src + nbytes_out)) + 1)
-    sets = [[rnd(B, c, hw, hw).requires_grad_(True) for c, hw, _ in parts] for _ in range(n_sets)]
-    gouts = [rnd(B, sum(c for c, _, _ in parts), out_hw, out_hw) for _ in range(n_sets)]
-    with torch.no_grad():
-        t_f = timed(lambda i: T._CatTC.apply(tuple({"copy": 0, "up2": 1, "pool2": 2}[m] for m in modes), *sets[i]), n_sets)
-        t_fa = timed(lambda i: torch.cat([ref_op[m](t) for t, m in zip(sets[i], modes)], 1), n_sets)
-    outs = [T.cat_tc(s, modes) for s in sets]
-    outs_a = [torch.cat([ref_op[m](t) for t, m in zip(s, modes)], 1) for s in sets]
-    t_b = timed(lambda i: torch.autograd.grad(outs[i], sets[i], gouts[i], retain_graph=True), n_sets)
-    t_ba = timed(lambda i: [g.contiguous(memory_format=CL) for g in torch.autograd.grad(outs_a[i], sets[i], gouts[i], retain_graph=True)], n_sets)
-    pool_extra = sum(B * c * hw * hw * 2 for c, hw, m in parts if m == "pool2")
-    rows.append((name + " fwd", t_f, (nbytes_src + nbytes_out) / t_f / 1e3, t_fa))
-    rows.append((name + " bwd", t_b, (nbytes_src + nbytes_out + pool_extra) / t_b / 1e3, t_ba))
-    del sets, gouts, outs, outs_a
+with torch.no_grad():
+    for name, parts in cases:
+        modes = [m for _, _, m in parts]
+        out_hw = parts[-1][1] * (2 if modes[-1] == "up2" else 1) // (2 if modes[-1] == "pool2" else 1)
+        Ct = sum(c for c, _, _ in parts)
+        nbytes_src = sum(B * c * hw * hw * 2 for c, hw, _ in parts)
+        nbytes_out = B * Ct * out_hw * out_hw * 2
+        n_sets = max(3, int(2 * 130e6 / (nbytes_src + nbytes_out)) + 1)
+        sets = [[rnd(B, c, hw, hw) for c, hw, _ in parts] for _ in range(n_sets)]
+        gouts = [rnd(B, Ct, out_hw, out_hw) for _ in range(n_sets)]
+        mcodes = tuple(CODE[m] for m in modes)
 
-for (C, hw) in ((512, 20), (256, 20)):
-    n_sets = 24
-    xs = [rnd(B, C, hw, hw).requires_grad_(True) for _ in range(n_sets)]
-    g = [rnd(B, 4 * C, hw, hw) for _ in range(n_sets)]
-    m = lambda t: F.max_pool2d(t, 5, 1, 2)
+        class Ctx:          # the backward launch of train._CatTC without the autograd engine around it
+            needs_input_grad = (False,) + (True,) * len(parts)
 
-    def aten(t):
-        y1 = m(t); y2 = m(y1)
-        return torch.cat((t, y1, y2, m(y2)), 1)
-    with torch.no_grad():
-        t_f = timed(lambda i: T._SppfTC.apply(xs[i]), n_sets)
-        t_fa = timed(lambda i: aten(xs[i]), n_sets)
-    outs = [T.sppf_cat_tc(x) for x in xs]
-    outs_a = [aten(x) for x in xs]
-    t_b = timed(lambda i: torch.autograd.grad(outs[i], xs[i], g[i], retain_graph=True), n_sets)
-    t_ba = timed(lambda i: torch.autograd.grad(outs_a[i], xs[i], g[i], retain_graph=True), n_sets)
-    nb = B * C * hw * hw * 2
-    rows.append((f"SPPF pool cascade + cat {C}ch {hw}x{hw} fwd", t_f, (nb * 5 + nb * 3) / t_f / 1e3, t_fa))       # x, out4, arg maps
-    rows.append((f"SPPF pool cascade + cat {C}ch {hw}x{hw} bwd", t_b, (nb * 4 + nb * 3 + nb) / t_b / 1e3, t_ba))
+            def save_for_backward(self, *t):
+                self.saved_tensors = t
+        ctxs = []
+        for st in sets:
+            c = Ctx()
+            c.modes, c.geom, c.shapes = mcodes, (B, out_hw, out_hw), [tuple(t.shape) for t in st]
+            c.saved_tensors = [t if m == "pool2" else None for t, m in zip(st, modes)]
+            ctxs.append(c)
 
-print("# Training glue kernels and fused object loss at YOLOPoint-L 640x640 batch-8 sizes (B200, CUDA events, inputs rotated over > 2 x L2)\n")
+        def aten_fwd(i):
+            outs = []
+            for t, m in zip(sets[i], modes):
+                outs.append(t if m == "copy" else F.interpolate(t, scale_factor=(2, 2), mode="nearest") if m == "up2" else F.max_pool2d(t, 2, 2))
+            return torch.cat(outs, 1)
+        idx = [[A.max_pool2d_with_indices(t, [2, 2], [2, 2])[1] if m == "pool2" else None for t, m in zip(st, modes)] for st in sets]
+
+        def aten_bwd(i):
+            res, c0 = [], 0
+            for k, (t, m) in enumerate(zip(sets[i], modes)):
+                gsl = gouts[i][:, c0:c0 + t.shape[1]]
+                c0 += t.shape[1]
+                if m == "copy":
+                    res.append(gsl.contiguous(memory_format=CL))          # what the consuming kernel needs
+                elif m == "up2":
+                    res.append(A.upsample_nearest2d_backward(gsl, [out_hw, out_hw], list(t.shape), 2.0, 2.0))
+                else:
+                    res.append(A.max_pool2d_with_indices_backward(gsl, t, [2, 2], [2, 2], [0, 0], [1, 1], False, idx[i][k]))
+            return res
+        t_f = graph_timed(lambda i: T._CatTC.forward(Ctx(), mcodes, *sets[i]), n_sets)
+        t_fa = graph_timed(aten_fwd, n_sets)
+        t_b = graph_timed(lambda i: T._CatTC.backward(ctxs[i], gouts[i]), n_sets)
+        t_ba = graph_timed(aten_bwd, n_sets)
+        pool_extra = sum(B * c * hw * hw * 2 for c, hw, m in parts if m == "pool2")
+        rows.append((name + " fwd", t_f, (nbytes_src + nbytes_out) / t_f / 1e3, t_fa))
+        rows.append((name + " bwd", t_b, (nbytes_src + nbytes_out + pool_extra) / t_b / 1e3, t_ba))
+        del sets, gouts, ctxs, idx
+
+    for (C, hw) in ((512, 20), (256, 20)):
+        n_sets = 24
+        xs = [rnd(B, C, hw, hw) for _ in range(n_sets)]
+        gs = [rnd(B, 4 * C, hw, hw) for _ in range(n_sets)]
+        pool = lambda t: A.max_pool2d_with_indices(t, [5, 5], [1, 1], [2, 2])
+
+        def aten_f(i):
+            y1, i1 = pool(xs[i]); y2, i2 = pool(y1); y3, i3 = pool(y2)
+            return torch.cat((xs[i], y1, y2, y3), 1), (y1, y2, i1, i2, i3)
+        saved = [aten_f(i)[1] for i in range(n_sets)]
+
+        def aten_b(i):
+            y1, y2, i1, i2, i3 = saved[i]
+            d0, d1, d2, d3 = gs[i].chunk(4, 1)
+            pb = lambda g, x, ix: A.max_pool2d_with_indices_backward(g, x, [5, 5], [1, 1], [2, 2], [1, 1], False, ix)
+            return d0 + pb(d1 + pb(d2 + pb(d3.contiguous(memory_format=CL), y2, i3), y1, i2), xs[i], i1)
+
+        class SCtx:
+            shape = (B, C, hw, hw)
+
+            def save_for_backward(self, *t):
+                self.saved_tensors = t
+        sctx = [SCtx() for _ in range(n_sets)]
+        for i in range(n_sets):
+            T._SppfTC.forward(sctx[i], xs[i])
+        t_f = graph_timed(lambda i: T._SppfTC.forward(SCtx(), xs[i]), n_sets)
+        t_fa = graph_timed(lambda i: aten_f(i)[0], n_sets)
+        t_b = graph_timed(lambda i: T._SppfTC.backward(sctx[i], gs[i]), n_sets)
+        t_ba = graph_timed(aten_b, n_sets)
+        nb = B * C * hw * hw * 2
+        rows.append((f"SPPF pool cascade + cat {C}ch {hw}x{hw} fwd", t_f, (nb * 5 + nb * 3) / t_f / 1e3, t_fa))       # x, out4, arg maps
+        rows.append((f"SPPF pool cascade + cat {C}ch {hw}x{hw} bwd", t_b, (nb * 4 + nb * 3 + nb) / t_b / 1e3, t_ba))
+
+print("# Training glue kernels and fused object loss at YOLOPoint-L 640x640 batch-8 sizes (B200, CUDA events around CUDA-graph replays of the calls, inputs rotated over > 2 x L2)\n")
 print(f"HBM peak used: {HBM:.0f} GB/s (MEASURED_PEAKS.json or the 6550 GB/s of round 1's records)\n")
 print("| operation | csrc/glue.cu, us | algorithmic GB/s | % of HBM peak | ATen ops, us | speed-up |")
 print("|---|---:|---:|---:|---:|---:|")

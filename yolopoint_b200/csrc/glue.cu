@@ -46,86 +46,128 @@ __device__ __forceinline__ void src_dims(const CatArgs& a, int part, int* Hs, in
   *Ws = a.mode[part] == YP_CAT_UP2 ? a.W / 2 : a.mode[part] == YP_CAT_POOL2 ? a.W * 2 : a.W;
 }
 
-__global__ void __launch_bounds__(256) cat_fwd_kernel(const CatArgs a, uint4* __restrict__ out) {
+constexpr int kCatUnroll = 4;   // independent 16-byte vectors a thread keeps in flight
+
+// value of output vector `idx` (pixel-major, G vectors per pixel).  Idx = uint32_t whenever the tensors allow it: the index arithmetic
+// (two divisions per vector) is then 32-bit -- 64-bit divisions made the first streaming kernels of this library issue-bound.
+template <typename Idx>
+__device__ __forceinline__ uint4 cat_fwd_value(const CatArgs& a, int G, Idx idx) {
+  const int g = static_cast<int>(idx % static_cast<Idx>(G));
+  const Idx pix = idx / static_cast<Idx>(G);
+  int part = 0;
+  while (part + 1 < a.n && g >= a.goff[part + 1]) ++part;
+  const int gl = g - a.goff[part], Gs = a.groups[part];
+  const uint4* s = a.src[part];
+  if (a.mode[part] == YP_CAT_COPY) return __ldg(s + static_cast<int64_t>(pix) * Gs + gl);
+  const int w = static_cast<int>(pix % static_cast<Idx>(a.W));
+  const Idx row = pix / static_cast<Idx>(a.W);
+  const int h = static_cast<int>(row % static_cast<Idx>(a.H)), b = static_cast<int>(row / static_cast<Idx>(a.H));
+  if (a.mode[part] == YP_CAT_UP2) return __ldg(s + ((static_cast<int64_t>(b) * (a.H / 2) + h / 2) * (a.W / 2) + w / 2) * Gs + gl);
+  // first maximum of the 2x2 window in raster order (max_pool2d)
+  const int Ws = 2 * a.W;
+  const int64_t p00 = (static_cast<int64_t>(b) * 2 * a.H + 2 * h) * Ws + 2 * w;
+  uint4 u[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) u[q] = __ldg(s + (p00 + (q >> 1) * Ws + (q & 1)) * Gs + gl);
+  __nv_bfloat16* bb = reinterpret_cast<__nv_bfloat16*>(&u[0]);
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    const __nv_bfloat16* uu = reinterpret_cast<const __nv_bfloat16*>(&u[q]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (__bfloat162float(uu[e]) > __bfloat162float(bb[e])) bb[e] = uu[e];
+  }
+  return u[0];
+}
+
+template <typename Idx>
+__global__ void __launch_bounds__(256) cat_fwd_kernel(const CatArgs a, uint4* __restrict__ out, Idx total) {
   const int G = a.goff[a.n];
-  const int64_t total = static_cast<int64_t>(a.B) * a.H * a.W * G;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % G);
-    const int64_t pix = idx / G;
-    int part = 0;
-    while (part + 1 < a.n && g >= a.goff[part + 1]) ++part;
-    const int gl = g - a.goff[part], Gs = a.groups[part];
-    const int w = static_cast<int>(pix % a.W), h = static_cast<int>((pix / a.W) % a.H), b = static_cast<int>(pix / (static_cast<int64_t>(a.W) * a.H));
-    const uint4* s = a.src[part];
-    uint4 v;
-    if (a.mode[part] == YP_CAT_COPY) {
-      v = __ldg(s + pix * Gs + gl);
-    } else if (a.mode[part] == YP_CAT_UP2) {
-      v = __ldg(s + ((static_cast<int64_t>(b) * (a.H / 2) + h / 2) * (a.W / 2) + w / 2) * Gs + gl);
-    } else {   // first maximum of the 2x2 window in raster order (max_pool2d)
-      const int Ws = 2 * a.W;
-      const int64_t p00 = (static_cast<int64_t>(b) * 2 * a.H + 2 * h) * Ws + 2 * w;
-      v = __ldg(s + p00 * Gs + gl);
-      __nv_bfloat16* bb = reinterpret_cast<__nv_bfloat16*>(&v);
+  const Idx stride = static_cast<Idx>(gridDim.x) * blockDim.x;
+  for (Idx idx = blockIdx.x * static_cast<Idx>(blockDim.x) + threadIdx.x; idx < total; idx += kCatUnroll * stride) {
+    uint4 v[kCatUnroll];
 #pragma unroll
-      for (int q = 1; q < 4; ++q) {
-        const uint4 u = __ldg(s + (p00 + (q >> 1) * Ws + (q & 1)) * Gs + gl);
-        const __nv_bfloat16* uu = reinterpret_cast<const __nv_bfloat16*>(&u);
+    for (int k = 0; k < kCatUnroll; ++k)
+      if (idx + k * stride < total) v[k] = cat_fwd_value<Idx>(a, G, idx + k * stride);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (__bfloat162float(uu[e]) > __bfloat162float(bb[e])) bb[e] = uu[e];
-      }
-    }
-    out[idx] = v;
+    for (int k = 0; k < kCatUnroll; ++k)
+      if (idx + k * stride < total) out[idx + k * stride] = v[k];
   }
 }
 
-__global__ void __launch_bounds__(256) cat_bwd_kernel(const CatArgs a, const uint4* __restrict__ dout) {
-  const int G = a.goff[a.n];
-  const int64_t total = a.voff[a.n];
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    int part = 0;
-    while (part + 1 < a.n && idx >= a.voff[part + 1]) ++part;
-    if (a.grad[part] == nullptr) continue;
-    const int64_t local = idx - a.voff[part];
-    const int Gs = a.groups[part], gl = static_cast<int>(local % Gs), g = a.goff[part] + gl;
-    const int64_t spix = local / Gs;
-    int Hs, Ws;
-    src_dims(a, part, &Hs, &Ws);
-    const int ws = static_cast<int>(spix % Ws), hs = static_cast<int>((spix / Ws) % Hs), b = static_cast<int>(spix / (static_cast<int64_t>(Ws) * Hs));
-    uint4 r;
-    if (a.mode[part] == YP_CAT_COPY) {
-      r = __ldg(dout + spix * G + g);
-    } else if (a.mode[part] == YP_CAT_UP2) {   // sum of the four children in fp32 (upsample_nearest2d backward)
-      const int64_t p00 = (static_cast<int64_t>(b) * a.H + 2 * hs) * a.W + 2 * ws;
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, f[8];
+// gradient vector `idx` of the flat list of all source vectors -> its part / position; returns false where the part wants no gradient
+template <typename Idx>
+__device__ __forceinline__ bool cat_bwd_value(const CatArgs& a, const uint4* __restrict__ dout, int G, Idx idx, int* part_out, Idx* local_out, uint4* r) {
+  int part = 0;
+  while (part + 1 < a.n && static_cast<int64_t>(idx) >= a.voff[part + 1]) ++part;
+  if (a.grad[part] == nullptr) return false;
+  const Idx local = idx - static_cast<Idx>(a.voff[part]);
+  const int Gs = a.groups[part], gl = static_cast<int>(local % static_cast<Idx>(Gs)), g = a.goff[part] + gl;
+  const Idx spix = local / static_cast<Idx>(Gs);
+  *part_out = part;
+  *local_out = local;
+  if (a.mode[part] == YP_CAT_COPY) {
+    *r = __ldg(dout + static_cast<int64_t>(spix) * G + g);
+    return true;
+  }
+  int Hs, Ws;
+  src_dims(a, part, &Hs, &Ws);
+  const int ws = static_cast<int>(spix % static_cast<Idx>(Ws));
+  const Idx row = spix / static_cast<Idx>(Ws);
+  const int hs = static_cast<int>(row % static_cast<Idx>(Hs)), b = static_cast<int>(row / static_cast<Idx>(Hs));
+  if (a.mode[part] == YP_CAT_UP2) {   // sum of the four children in fp32 (upsample_nearest2d backward)
+    const int64_t p00 = (static_cast<int64_t>(b) * a.H + 2 * hs) * a.W + 2 * ws;
+    uint4 u[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        unpack8(__ldg(dout + (p00 + (q >> 1) * a.W + (q & 1)) * G + g), f);
+    for (int q = 0; q < 4; ++q) u[q] = __ldg(dout + (p00 + (q >> 1) * a.W + (q & 1)) * G + g);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += f[e];
-      }
-      r = pack8(acc);
-    } else {   // this source pixel receives the window's gradient where it is the first maximum of its window
-      const int q_me = (hs & 1) * 2 + (ws & 1);
-      const int64_t p00 = (static_cast<int64_t>(b) * Hs + (hs & ~1)) * Ws + (ws & ~1);
-      float win[4][8];
+    for (int q = 0; q < 4; ++q) {
+      unpack8(u[q], f);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) unpack8(__ldg(a.src[part] + (p00 + (q >> 1) * Ws + (q & 1)) * Gs + gl), win[q]);
-      float d[8], o[8];
-      unpack8(__ldg(dout + ((static_cast<int64_t>(b) * a.H + hs / 2) * a.W + ws / 2) * G + g), d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        int arg = 0;
-        float best = win[0][e];
-#pragma unroll
-        for (int q = 1; q < 4; ++q)
-          if (win[q][e] > best) { best = win[q][e]; arg = q; }
-        o[e] = arg == q_me ? d[e] : 0.f;
-      }
-      r = pack8(o);
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
     }
-    a.grad[part][local] = r;
+    *r = pack8(acc);
+    return true;
+  }
+  // 2x2 pooling: this source pixel receives the window's gradient where it is the first maximum of its window
+  const int q_me = (hs & 1) * 2 + (ws & 1);
+  const int64_t p00 = (static_cast<int64_t>(b) * Hs + (hs & ~1)) * Ws + (ws & ~1);
+  uint4 u[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) u[q] = __ldg(a.src[part] + (p00 + (q >> 1) * Ws + (q & 1)) * Gs + gl);
+  const uint4 du = __ldg(dout + ((static_cast<int64_t>(b) * a.H + hs / 2) * a.W + ws / 2) * G + g);
+  float win[4][8], d[8], o[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) unpack8(u[q], win[q]);
+  unpack8(du, d);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    int arg = 0;
+    float best = win[0][e];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+      if (win[q][e] > best) { best = win[q][e]; arg = q; }
+    o[e] = arg == q_me ? d[e] : 0.f;
+  }
+  *r = pack8(o);
+  return true;
+}
+
+template <typename Idx>
+__global__ void __launch_bounds__(256) cat_bwd_kernel(const CatArgs a, const uint4* __restrict__ dout, Idx total) {
+  const int G = a.goff[a.n];
+  const Idx stride = static_cast<Idx>(gridDim.x) * blockDim.x;
+  for (Idx idx = blockIdx.x * static_cast<Idx>(blockDim.x) + threadIdx.x; idx < total; idx += kCatUnroll * stride) {
+    uint4 v[kCatUnroll];
+    int part[kCatUnroll];
+    Idx local[kCatUnroll];
+    bool ok[kCatUnroll];
+#pragma unroll
+    for (int k = 0; k < kCatUnroll; ++k) ok[k] = idx + k * stride < total && cat_bwd_value<Idx>(a, dout, G, idx + k * stride, &part[k], &local[k], &v[k]);
+#pragma unroll
+    for (int k = 0; k < kCatUnroll; ++k)
+      if (ok[k]) a.grad[part[k]][local[k]] = v[k];
   }
 }
 
@@ -236,7 +278,11 @@ extern "C" int yp_cat_nhwc_fwd(const YpCatPart* parts, int32_t n, void* out, int
   if (rc != YP_OK) return rc;
   YP_REQUIRE(out && yp::aligned16(out), YP_ERR_ALIGN, "cat_fwd: output missing or not 16-byte aligned");
   const int64_t total = static_cast<int64_t>(B) * H * W * a.goff[n];
-  yp::cat_fwd_kernel<<<yp::stream_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<uint4*>(out));
+  const unsigned blocks = yp::stream_blocks(yp::ceil_div64(total, yp::kCatUnroll));
+  if (total < (int64_t(1) << 31))   // (index + unroll * grid stride stays below 2^32)
+    yp::cat_fwd_kernel<uint32_t><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<uint4*>(out), static_cast<uint32_t>(total));
+  else
+    yp::cat_fwd_kernel<int64_t><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<uint4*>(out), total);
   YP_LAUNCH_OK();
   return YP_OK;
 }
@@ -246,7 +292,12 @@ extern "C" int yp_cat_nhwc_bwd(const YpCatPart* parts, int32_t n, const void* do
   const int rc = yp::fill_cat_args(parts, n, B, H, W, true, &a);
   if (rc != YP_OK) return rc;
   YP_REQUIRE(dout && yp::aligned16(dout), YP_ERR_ALIGN, "cat_bwd: output gradient missing or not 16-byte aligned");
-  yp::cat_bwd_kernel<<<yp::stream_blocks(a.voff[n]), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<const uint4*>(dout));
+  const int64_t total = a.voff[n];
+  const unsigned blocks = yp::stream_blocks(yp::ceil_div64(total, yp::kCatUnroll));
+  if (total < (int64_t(1) << 31))
+    yp::cat_bwd_kernel<uint32_t><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<const uint4*>(dout), static_cast<uint32_t>(total));
+  else
+    yp::cat_bwd_kernel<int64_t><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<const uint4*>(dout), total);
   YP_LAUNCH_OK();
   return YP_OK;
 }
