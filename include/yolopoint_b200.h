@@ -409,7 +409,7 @@ int yp_detector_loss(const float* semi, int64_t sB, int64_t sC, int64_t sH, int6
 
 /* ----------------------------------------------------------------------------------------------
  * Object loss of the training step over all Detect levels, forward and gradient (csrc/object_loss.cu).
- * Replaces ComputeObjectLoss.__call__ (utils/loss_functions.py:120-216: CIoU box loss via bbox_iou(..., CIoU=True) of
+ * Replaces ComputeObjectLoss.__call__ + build_targets (utils/loss_functions.py:120-234: CIoU box loss via bbox_iou(..., CIoU=True) of
  * utils/metrics_yolo.py:202-240, BCE objectness against the detached, clamped CIoU, BCE classes) on the fixed-shape target plan
  * of ComputeObjectLoss.build_targets (:218-234; all 5 x anchors x targets assignment candidates with a validity mask).
  * Per level: pred / dpred [cells, no] fp32 rows (cells = B * na * ny * nx, row = (x, y, w, h, obj, classes...) logits);
@@ -418,6 +418,7 @@ int yp_detector_loss(const float* semi, int64_t sB, int64_t sC, int64_t sH, int6
  * out4 = (loss, box, obj, cls) with loss = w_box * box + w_obj * obj + w_cls * cls as the reference sums them before its batch-size factor.
  * ---------------------------------------------------------------------------------------------- */
 #define YP_OBJ_LOSS_MAX_LEVELS 5
+#define YP_OBJ_LOSS_MAX_ANCHORS 8
 typedef struct YpObjLossLevel {
   const float* pred;
   float* dpred;
@@ -429,6 +430,12 @@ typedef struct YpObjLossLevel {
   int64_t cells;
   int32_t E;
   float balance;
+  /* targets != NULL: the target assignment itself (build_targets, :218-234) is evaluated inside the kernels from the label list
+   * targets [nt,6] = (image, class, x, y, w, h; box normalised to [0,1]) -- valid / cell / tbox / anchor / cls are then ignored and
+   * E must be 5 * na * nt (candidate order: offset variant, anchor, target).  Grid nx x ny, nb images, anchors in cells. */
+  const float* targets;
+  int32_t nt, na, nx, ny, nb;
+  float anchors[2 * YP_OBJ_LOSS_MAX_ANCHORS];
 } YpObjLossLevel;
 
 typedef struct YpObjLossParams {
@@ -437,6 +444,7 @@ typedef struct YpObjLossParams {
   float gr;              /* objectness target = (1 - gr) + gr * max(CIoU, 0) */
   float w_box, w_obj, w_cls;
   float eps;             /* 1e-7 in the reference */
+  float anchor_t;        /* target / anchor side-ratio bound of the assignment (4.0 in the reference's hyper-parameters) */
 } YpObjLossParams;
 
 size_t yp_object_loss_workspace_bytes(const YpObjLossLevel* levels, int32_t nl);

@@ -249,7 +249,7 @@ def test_fused_detector_loss_matches_reference_golden_and_autograd(golden):
 
 
 def test_fused_object_loss_matches_reference_golden_and_torch(golden):
-    """csrc/object_loss.cu (target claim + CIoU + objectness / class BCE over all levels, forward and gradient) against the vectors of
+    """csrc/object_loss.cu (target assignment + claim + CIoU + objectness / class BCE over all levels, forward and gradient) against the vectors of
     the UNMODIFIED reference (src/utils/loss_functions.py:120-216) and against the PyTorch statement of the same loss
     (ComputeObjectLoss._call_torch) on crowded targets (many candidates per cell: owner rule, summed gradients), with label smoothing
     and positive-class weights, on an empty label list, and with an upstream gradient factor."""
@@ -291,6 +291,13 @@ def test_fused_object_loss_matches_reference_golden_and_torch(golden):
             assert _rel(a.grad, b.grad.double()) < 2e-5, nt
         la2, _ = crit2([t.clone() for t in base], tg)
         assert torch.equal(la2, la.detach())                 # loss values: fixed-order reductions
+        # the same kernels on a host-built plan (TargetPlan arrays) instead of the in-kernel target assignment: identical candidates
+        pc = [t.clone().requires_grad_(True) for t in base]
+        lc, ic = crit2(pc, tg, crit2.build_targets(pc, tg))
+        lc.sum().backward()
+        assert torch.equal(lc.detach(), la.detach()) and torch.equal(ic, ia)
+        for a, c in zip(pa, pc):
+            assert _rel(a.grad, 2.5 * c.grad.double()) < 1e-5
 
 
 def test_glue_concat_resample_and_sppf_match_aten():

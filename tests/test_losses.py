@@ -129,3 +129,40 @@ def test_box_loss_math_matches_autograd(tmp_path):
     ref.sum().backward()
     np.testing.assert_allclose(lo, ref.detach().numpy(), rtol=2e-6, atol=1e-6)
     assert np.abs(dx - tx.grad.numpy()).max() < 1e-6
+
+
+def test_in_kernel_target_assignment_matches_build_targets(tmp_path):
+    """The target assignment the object-loss kernels evaluate per candidate (plan_candidate of csrc/box_loss_math.cuh, compiled for the
+    HOST here) against ComputeObjectLoss.build_targets on 5 000 targets incl. centres exactly on cell and half-cell borders, boxes
+    outside the image and extreme aspect ratios: validity, cell, relative box and class bit-identical on all three levels."""
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path / "libboxloss_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(here, "box_loss_host.cpp")])
+    L = C.CDLL(so)
+    m = Model(names=[str(i) for i in range(80)], version="n")
+    crit = Lz.ComputeObjectLoss(m, CFG, "cpu")
+    gen = torch.Generator().manual_seed(0)
+    B, nt = 4, 5000
+    tg = torch.cat((torch.randint(0, B, (nt, 1), generator=gen).float(), torch.randint(0, 80, (nt, 1), generator=gen).float(),
+                    torch.rand(nt, 2, generator=gen) * 1.1 - 0.05, torch.rand(nt, 2, generator=gen) ** 3 * 0.9 + 1e-3), 1)
+    tg[:200, 2] = torch.arange(200) / 160.0
+    tg[200:400, 3] = torch.arange(200) / 96.0 * 0.5
+    grids = ((48, 80), (24, 40), (12, 20))
+    plan = crit.build_targets([torch.empty((B, 3, ny, nx, 85), device="meta") for ny, nx in grids], tg)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    t32 = tg.numpy().astype(np.float32).copy()
+    for i, lv in enumerate(plan.levels):
+        ny, nx = grids[i]
+        na, E = 3, 5 * 3 * nt
+        an = np.asarray(crit.anchors_host[i], np.float32)
+        valid, cell, tbox, cls = np.zeros(E, np.uint8), np.zeros(E, np.int64), np.zeros((E, 4), np.float32), np.zeros(E, np.int32)
+        L.yp_host_plan_candidates(ptr(t32), nt, ptr(an), na, nx, ny, C.c_float(CFG["anchor_t"]), ptr(valid), ptr(cell), ptr(tbox), ptr(cls))
+        v = lv["valid"].numpy()
+        assert v.sum() > 1000
+        np.testing.assert_array_equal(valid.astype(bool), v)
+        np.testing.assert_array_equal(cell[v], lv["cell"].numpy()[v])
+        np.testing.assert_array_equal(tbox[v], lv["tbox"].numpy()[v])
+        np.testing.assert_array_equal(cls[v], lv["cls"].numpy()[v])

@@ -56,12 +56,14 @@ class YpCatPart(C.Structure):
 
 class YpObjLossLevel(C.Structure):
     _fields_ = [("pred", C.c_void_p), ("dpred", C.c_void_p), ("valid", C.c_void_p), ("cell", C.c_void_p), ("tbox", C.c_void_p),
-                ("anchor", C.c_void_p), ("cls", C.c_void_p), ("cells", C.c_int64), ("E", C.c_int32), ("balance", C.c_float)]
+                ("anchor", C.c_void_p), ("cls", C.c_void_p), ("cells", C.c_int64), ("E", C.c_int32), ("balance", C.c_float),
+                ("targets", C.c_void_p), ("nt", C.c_int32), ("na", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("nb", C.c_int32),
+                ("anchors", C.c_float * 16)]
 
 
 class YpObjLossParams(C.Structure):
     _fields_ = [("cp", C.c_float), ("cn", C.c_float), ("cls_pw", C.c_float), ("obj_pw", C.c_float), ("gr", C.c_float),
-                ("w_box", C.c_float), ("w_obj", C.c_float), ("w_cls", C.c_float), ("eps", C.c_float)]
+                ("w_box", C.c_float), ("w_obj", C.c_float), ("w_cls", C.c_float), ("eps", C.c_float), ("anchor_t", C.c_float)]
 
 
 _i32, _i64, _f32, _vp, _sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t

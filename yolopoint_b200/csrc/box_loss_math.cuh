@@ -83,6 +83,57 @@ YP_HD float candidate_ciou(const float* q, float aw, float ah, const float* tbox
   return c.v;
 }
 
+// Target assignment of one candidate (ComputeObjectLoss.build_targets, src/utils/loss_functions.py:218-234 in its fixed-shape form):
+// candidate = (offset variant o: centre, left, up, right, down; anchor (aw, ah) in cells; target tg = (image, class, x, y, w, h) with
+// the box normalised to [0, 1]) on an nx x ny grid.  Valid when no side of the target is more than anchor_t times longer or shorter
+// than the anchor's and, for o > 0, when the centre lies in the matching half of its cell and more than one cell away from that
+// border.  Every operation is the single fp32 operation the PyTorch statement performs (multiply, divide, remainder, truncation),
+// so borderline decisions agree bit for bit.
+struct CandPlan {
+  bool valid;
+  int img, cls, gi, gj;     // gi, gj clamped to the grid
+  float tbox[4];            // (x, y) relative to the UNclamped cell, (w, h) in cells
+};
+
+YP_HD float mul_rn(float a, float b) {   // a product that is rounded on its own (never contracted into an FMA with a following add)
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+
+YP_HD float remainder1(float x) {   // torch.remainder(x, 1): the sign follows the divisor
+  float r = fmodf(x, 1.f);
+  if (r != 0.f && r < 0.f) r += 1.f;
+  return r;
+}
+
+YP_HD CandPlan plan_candidate(const float* tg, float aw, float ah, int nx, int ny, int o, float anchor_t) {
+  CandPlan c;
+  const float fx = static_cast<float>(nx), fy = static_cast<float>(ny);
+  const float gx = mul_rn(tg[2], fx), gy = mul_rn(tg[3], fy), gw = mul_rn(tg[4], fx), gh = mul_rn(tg[5], fy);
+  const float rw = gw / aw, rh = gh / ah;
+  const float worst = fmaxf(fmaxf(rw, 1.f / rw), fmaxf(rh, 1.f / rh));
+  bool ok = worst < anchor_t;
+  float hx = 0.f, hy = 0.f;
+  if (o == 1) { ok = ok && remainder1(gx) < 0.5f && gx > 1.f; hx = 0.5f; }
+  else if (o == 2) { ok = ok && remainder1(gy) < 0.5f && gy > 1.f; hy = 0.5f; }
+  else if (o == 3) { const float ix = fx - gx; ok = ok && remainder1(ix) < 0.5f && ix > 1.f; hx = -0.5f; }
+  else if (o == 4) { const float iy = fy - gy; ok = ok && remainder1(iy) < 0.5f && iy > 1.f; hy = -0.5f; }
+  const long long cx = static_cast<long long>(gx - hx), cy = static_cast<long long>(gy - hy);   // truncation toward zero, like .long()
+  c.valid = ok;
+  c.img = static_cast<int>(static_cast<long long>(tg[0]));
+  c.cls = static_cast<int>(static_cast<long long>(tg[1]));
+  c.gi = static_cast<int>(cx < 0 ? 0 : cx > nx - 1 ? nx - 1 : cx);
+  c.gj = static_cast<int>(cy < 0 ? 0 : cy > ny - 1 ? ny - 1 : cy);
+  c.tbox[0] = gx - static_cast<float>(cx);
+  c.tbox[1] = gy - static_cast<float>(cy);
+  c.tbox[2] = gw;
+  c.tbox[3] = gh;
+  return c;
+}
+
 // BCE-with-logits term with a positive-class weight (torch.nn.functional.binary_cross_entropy_with_logits(pos_weight=pw)):
 // L = (1 - t) x + (1 + (pw - 1) t) softplus(-x);  *dx = dL/dx.
 YP_HD float bce_logits(float x, float t, float pw, float* dx) {

@@ -2,8 +2,8 @@
 // (ComputeObjectLoss, src/utils/loss_functions.py:90-234: CIoU box loss, BCE objectness against the detached CIoU, BCE classes)
 // over ALL Detect levels, forward AND gradient, in four small launches:
 //
-//   claim     one thread per assignment candidate (5 offsets x anchors x targets per level, validity mask from the host-side
-//             target plan): the LAST valid candidate of a cell in candidate order owns the cell's objectness target
+//   claim     one thread per assignment candidate (5 offsets x anchors x targets per level; the assignment rule of build_targets,
+//             :218-234, is evaluated here from the label list -- or read from a host-built plan): the LAST valid candidate of a cell in candidate order owns the cell's objectness target
 //             (the rule of `tobj[b, a, gj, gi] = iou`, :196, under duplicate indices) -- atomicMax on the candidate index;
 //             counts the valid candidates of each level
 //   candidate gather of the candidate's prediction row, box decode, CIoU and its gradient (box_loss_math.cuh), class BCE and its
@@ -30,7 +30,7 @@ struct ObjLevels {
   int64_t cand_off[kMaxLevels + 1];   // prefix sums of E
   int64_t cell_off[kMaxLevels + 1];   // prefix sums of cells
   int nl, no, nc;
-  float cp, cn, cls_pw, obj_pw, gr, w_box, w_obj, w_cls, eps;
+  float cp, cn, cls_pw, obj_pw, gr, w_box, w_obj, w_cls, eps, anchor_t;
 };
 
 __device__ __forceinline__ float block_sum_f(float v, float* red) {
@@ -52,13 +52,50 @@ __device__ __forceinline__ int level_of(const int64_t* off, int nl, int64_t idx)
   return l;
 }
 
+// candidate e of a level: from the host-built plan arrays, or (lv.targets) assigned here from the label list
+struct Cand {
+  bool valid;
+  int64_t cell;
+  float tbox[4];
+  float aw, ah;
+  int cls;
+};
+
+__device__ __forceinline__ Cand load_candidate(const YpObjLossLevel& lv, int64_t e, float anchor_t) {
+  Cand c;
+  c.valid = false;
+  if (e >= lv.E) return c;
+  if (lv.targets != nullptr) {
+    const int t = static_cast<int>(e % lv.nt), a = static_cast<int>((e / lv.nt) % lv.na), o = static_cast<int>(e / (static_cast<int64_t>(lv.nt) * lv.na));
+    c.aw = lv.anchors[2 * a];
+    c.ah = lv.anchors[2 * a + 1];
+    const CandPlan p = plan_candidate(lv.targets + 6 * static_cast<int64_t>(t), c.aw, c.ah, lv.nx, lv.ny, o, anchor_t);
+    c.valid = p.valid && p.img >= 0 && p.img < lv.nb;
+    c.cell = ((static_cast<int64_t>(p.img) * lv.na + a) * lv.ny + p.gj) * lv.nx + p.gi;
+    c.cls = p.cls;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c.tbox[k] = p.tbox[k];
+    return c;
+  }
+  if (lv.valid[e] == 0) return c;
+  c.cell = lv.cell[e];
+  c.valid = c.cell >= 0 && c.cell < lv.cells;
+  c.aw = lv.anchor[2 * e];
+  c.ah = lv.anchor[2 * e + 1];
+  c.cls = static_cast<int>(lv.cls[e]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c.tbox[k] = lv.tbox[4 * e + k];
+  return c;
+}
+
 __global__ void __launch_bounds__(kObjThreads) obj_claim_kernel(const ObjLevels L, int* __restrict__ owner, int* __restrict__ n_valid) {
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int l = level_of(L.cand_off, L.nl, idx);
   const int64_t e = idx - L.cand_off[l];
   const YpObjLossLevel& lv = L.lv[l];
-  const bool ok = e < lv.E && lv.valid[e] != 0 && lv.cell[e] >= 0 && lv.cell[e] < lv.cells;
-  if (ok) atomicMax(owner + L.cell_off[l] + lv.cell[e], static_cast<int>(e));
+  const Cand c = load_candidate(lv, e, L.anchor_t);
+  const bool ok = c.valid;
+  if (ok) atomicMax(owner + L.cell_off[l] + c.cell, static_cast<int>(e));
   const unsigned m = __ballot_sync(0xffffffffu, ok);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid + l, __popc(m));
 }
@@ -71,13 +108,14 @@ __global__ void __launch_bounds__(kObjThreads) obj_candidate_kernel(const ObjLev
   const int64_t e = idx - L.cand_off[l];
   const YpObjLossLevel& lv = L.lv[l];
   float box_term = 0.0f, cls_term = 0.0f;
-  if (e < lv.E && lv.valid[e] != 0 && lv.cell[e] >= 0 && lv.cell[e] < lv.cells) {
+  const Cand cd = load_candidate(lv, e, L.anchor_t);
+  if (cd.valid) {
     const int n = n_valid[l];
-    const int64_t cell = lv.cell[e];
+    const int64_t cell = cd.cell;
     const float* q = lv.pred + cell * L.no;
     float* dq = lv.dpred + cell * L.no;
     float g[4];
-    const float ciou = candidate_ciou(q, lv.anchor[2 * e], lv.anchor[2 * e + 1], lv.tbox + 4 * e, L.eps, g);
+    const float ciou = candidate_ciou(q, cd.aw, cd.ah, cd.tbox, L.eps, g);
     box_term = 1.0f - ciou;
     const float sb = -L.w_box / static_cast<float>(n);   // d (w_box * mean(1 - ciou)) / d ciou
 #pragma unroll
@@ -87,7 +125,7 @@ __global__ void __launch_bounds__(kObjThreads) obj_candidate_kernel(const ObjLev
       tobj[L.cell_off[l] + cell] = (1.0f - L.gr) + L.gr * score;
     }
     if (L.nc > 1) {
-      const int cls = static_cast<int>(lv.cls[e]);
+      const int cls = cd.cls;
       const float sc = L.w_cls / (static_cast<float>(n) * static_cast<float>(L.nc));
       for (int c = 0; c < L.nc; ++c) {
         float dx;
@@ -174,11 +212,17 @@ extern "C" int yp_object_loss(const YpObjLossLevel* levels, int32_t nl, int32_t 
   memset(&L, 0, sizeof(L));
   L.nl = nl; L.no = no; L.nc = nc;
   L.cp = hp->cp; L.cn = hp->cn; L.cls_pw = hp->cls_pw; L.obj_pw = hp->obj_pw; L.gr = hp->gr;
-  L.w_box = hp->w_box; L.w_obj = hp->w_obj; L.w_cls = hp->w_cls; L.eps = hp->eps;
+  L.w_box = hp->w_box; L.w_obj = hp->w_obj; L.w_cls = hp->w_cls; L.eps = hp->eps; L.anchor_t = hp->anchor_t;
   for (int l = 0; l < nl; ++l) {
     const YpObjLossLevel& lv = levels[l];
     YP_REQUIRE(lv.pred && lv.dpred && lv.cells > 0 && lv.cells < (int64_t(1) << 31) && lv.E >= 0, YP_ERR_ARG, "object_loss: level %d: bad prediction buffers", l);
-    YP_REQUIRE(lv.E == 0 || (lv.valid && lv.cell && lv.tbox && lv.anchor && lv.cls), YP_ERR_ARG, "object_loss: level %d: null target plan", l);
+    if (lv.targets != nullptr)
+      YP_REQUIRE(lv.na >= 1 && lv.na <= YP_OBJ_LOSS_MAX_ANCHORS && lv.nt >= 0 && lv.nx > 0 && lv.ny > 0 && lv.nb > 0 &&
+                     lv.cells == static_cast<int64_t>(lv.nb) * lv.na * lv.ny * lv.nx && static_cast<int64_t>(lv.E) == 5LL * lv.na * lv.nt,
+                 YP_ERR_SHAPE, "object_loss: level %d: nb=%d na=%d ny=%d nx=%d nt=%d do not match cells=%lld E=%d", l, lv.nb, lv.na, lv.ny, lv.nx, lv.nt,
+                 static_cast<long long>(lv.cells), lv.E);
+    else
+      YP_REQUIRE(lv.E == 0 || (lv.valid && lv.cell && lv.tbox && lv.anchor && lv.cls), YP_ERR_ARG, "object_loss: level %d: null target plan", l);
     L.lv[l] = lv;
     L.cand_off[l + 1] = L.cand_off[l] + yp::round_up(lv.E, yp::kObjThreads);
     L.cell_off[l + 1] = L.cell_off[l] + yp::round_up(lv.cells, yp::kObjThreads);

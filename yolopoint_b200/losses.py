@@ -99,6 +99,7 @@ class ComputeObjectLoss:
         self.balance = [4.0, 1.0, 0.4] if det.nl == 3 else [4.0, 1.0, 0.25, 0.06, 0.02]
         self.gr = 1.0
         self.fused = True           # CUDA predictions: csrc/object_loss.cu (no fallback: a missing library raises)
+        self.anchors_host = [[float(v) for v in a.flatten().tolist()] for a in det.anchors.detach().cpu()]   # per level, in cells (read once)
 
     # -- labels only ---------------------------------------------------------------------------
     def build_targets(self, p, targets) -> TargetPlan:
@@ -140,11 +141,11 @@ class ComputeObjectLoss:
         On a CUDA device the whole loss over all levels and its gradient are four kernel launches (csrc/object_loss.cu,
         ``fused=True``, the default there); ``fused=False`` / CPU tensors run the PyTorch statement of the same arithmetic below,
         which is what the CPU tests pin to the reference's vectors and what the GPU tests check the kernels against."""
-        dev = self.device
-        plan = built if built is not None else self.build_targets(p, targets)
         if self.fused and all(pi.is_cuda for pi in p):
-            out4 = _ObjectLossFused.apply(self, plan, *p)
+            # a precomputed plan is used as given; otherwise the target assignment runs inside the kernels from the label list
+            out4 = _ObjectLossFused.apply(self, built, None if built is not None else targets, *p)
             return out4[0:1], out4[1:4].detach()
+        plan = built if built is not None else self.build_targets(p, targets)
         return self._call_torch(p, plan)
 
     def _call_torch(self, p, plan: TargetPlan):
@@ -185,11 +186,12 @@ class ComputeObjectLoss:
 
 
 class _ObjectLossFused(torch.autograd.Function):
-    """ComputeObjectLoss over all Detect levels on the fixed-shape target plan: loss terms and d loss / d predictions from
-    ``yp_object_loss`` (claim / candidate / cells / finalize kernels, csrc/object_loss.cu).  -> [4] = (loss, box, obj, cls)."""
+    """ComputeObjectLoss over all Detect levels: loss terms and d loss / d predictions from ``yp_object_loss`` (claim / candidate /
+    cells / finalize kernels, csrc/object_loss.cu), with the target assignment evaluated inside the kernels from the label list
+    ``targets`` [nt,6] (``plan`` None) or read from a precomputed ``TargetPlan``.  -> [4] = (loss, box, obj, cls)."""
 
     @staticmethod
-    def forward(ctx, crit, plan, *p):
+    def forward(ctx, crit, plan, targets, *p):
         import ctypes as C
         from . import _lib
         L = _lib.lib(require_device=True)
@@ -199,25 +201,40 @@ class _ObjectLossFused(torch.autograd.Function):
         keep = []                                                   # device buffers the launches read: alive until enqueued
         levels = (_lib.YpObjLossLevel * nl)()
         grads = []
+        if plan is None:
+            tg = targets.to(device=dev, dtype=torch.float32).contiguous()
+            assert tg.dim() == 2 and tg.shape[1] == 6, tuple(tg.shape)
+            keep.append(tg)
         for i, pi in enumerate(p):
-            lv = plan.levels[i]
             rows = pi.detach().contiguous()
             d = torch.empty_like(rows)
+            keep.append(rows)
+            grads.append(d)
+            levels[i].pred, levels[i].dpred = rows.data_ptr(), d.data_ptr()
+            levels[i].cells, levels[i].balance = rows.numel() // no, float(crit.balance[i])
+            if plan is None:
+                B, na, ny, nx, _ = pi.shape
+                assert na == crit.na and 2 * na <= 16
+                levels[i].targets = tg.data_ptr() if tg.shape[0] else None
+                levels[i].nt, levels[i].na, levels[i].nx, levels[i].ny, levels[i].nb = tg.shape[0], na, nx, ny, B
+                levels[i].E = 5 * na * tg.shape[0]
+                for k, v in enumerate(crit.anchors_host[i]):
+                    levels[i].anchors[k] = v
+                continue
+            lv = plan.levels[i]
             E = int(lv["valid"].numel())
             valid = lv["valid"].to(device=dev, dtype=torch.bool).contiguous()
             cell = lv["cell"].to(device=dev, dtype=torch.int64).contiguous()
             tbox = lv["tbox"].to(device=dev, dtype=torch.float32).contiguous()
             anchor = lv["anchor"].to(device=dev, dtype=torch.float32).contiguous()
             cls = lv["cls"].to(device=dev, dtype=torch.int64).contiguous()
-            keep += [rows, valid, cell, tbox, anchor, cls]
-            grads.append(d)
-            levels[i].pred, levels[i].dpred = rows.data_ptr(), d.data_ptr()
+            keep += [valid, cell, tbox, anchor, cls]
             levels[i].valid, levels[i].cell, levels[i].tbox = valid.data_ptr(), cell.data_ptr(), tbox.data_ptr()
-            levels[i].anchor, levels[i].cls = anchor.data_ptr(), cls.data_ptr()
-            levels[i].cells, levels[i].E, levels[i].balance = rows.numel() // no, E, float(crit.balance[i])
+            levels[i].anchor, levels[i].cls, levels[i].E = anchor.data_ptr(), cls.data_ptr(), E
             assert int(lv["cells"]) == rows.numel() // no
         hp = _lib.YpObjLossParams(cp=crit.cp, cn=crit.cn, cls_pw=float(crit.hyp["cls_pw"]), obj_pw=float(crit.hyp["obj_pw"]), gr=crit.gr,
-                                  w_box=float(crit.hyp["box"]), w_obj=float(crit.hyp["obj"]), w_cls=float(crit.hyp["cls"]), eps=1e-7)
+                                  w_box=float(crit.hyp["box"]), w_obj=float(crit.hyp["obj"]), w_cls=float(crit.hyp["cls"]), eps=1e-7,
+                                  anchor_t=float(crit.hyp["anchor_t"]))
         ws = torch.empty(max(int(L.yp_object_loss_workspace_bytes(levels, nl)), 16), dtype=torch.uint8, device=dev)
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
         _lib.check(L.yp_object_loss(levels, nl, no, crit.nc, C.byref(hp), out4.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -228,7 +245,7 @@ class _ObjectLossFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         g = grad_out[0]                                             # only the total (out4[0]) carries gradient; the terms are reports
-        return (None, None) + tuple(d * g for d in ctx.saved_tensors)
+        return (None, None, None) + tuple(d * g for d in ctx.saved_tensors)
 
 
 def labels2Dto3D(labels, cell_size=8, add_dustbin=True):

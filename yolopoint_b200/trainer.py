@@ -133,9 +133,12 @@ class _LossHead(torch.nn.Module):
 
     def forward(self, semi, semi_w, desc, desc_w, p0, p1, p2, labels_2D, valid_mask, warped_labels, warped_valid_mask, inv_h, pa, pb, rnd, *plan):
         ts = self.ts[0]
-        levels = [dict(valid=plan[5 * i], cell=plan[5 * i + 1], tbox=plan[5 * i + 2], anchor=plan[5 * i + 3], cls=plan[5 * i + 4], cells=self.cells[i])
-                  for i in range(len(self.cells))]
-        loss_obj, _ = ts.obj_loss([p0, p1, p2], None, Lz.TargetPlan(levels))
+        if len(plan) == 1:          # the label list itself: the target assignment runs inside the object-loss kernels
+            loss_obj, _ = ts.obj_loss([p0, p1, p2], plan[0])
+        else:
+            levels = [dict(valid=plan[5 * i], cell=plan[5 * i + 1], tbox=plan[5 * i + 2], anchor=plan[5 * i + 3], cls=plan[5 * i + 4], cells=self.cells[i])
+                      for i in range(len(self.cells))]
+            loss_obj, _ = ts.obj_loss([p0, p1, p2], None, Lz.TargetPlan(levels))
         loss_det = ts.det_loss.from_2d(semi, labels_2D, valid_mask)
         loss_det_w = ts.det_loss.from_2d(semi_w, warped_labels, warped_valid_mask)
         loss_desc = ts.desc_loss(desc, desc_w, warped_valid_mask, inv_h, pairs=(pa, pb, rnd), **ts.sparse_cfg)
@@ -218,7 +221,8 @@ class TrainStep:
         B, _, H, W = sample["image"].shape
         det = getattr(m, "module", m).model.Detect
         shapes = [torch.empty((B, det.na, H // int(s), W // int(s), det.no), device="meta") for s in (8, 16, 32)]
-        built = self.obj_loss.build_targets(shapes, sample["box_labels"])
+        # (CUDA: the object-loss kernels assign the targets themselves from the label list; the PyTorch statement needs the plan)
+        built = None if (self.obj_loss.fused and dev.type == "cuda") else self.obj_loss.build_targets(shapes, sample["box_labels"])
         pairs = Lz.descriptor_pairs(sample["warped_valid_mask"], sample["inv_homographies"], B, H // 8, W // 8, device=dev, **self.sparse_cfg)
         semi, desc, obj = self._forward(sample["image"], 0)
         semi_w, desc_w, _ = self._forward(sample["warped_image"], 1)
@@ -240,13 +244,15 @@ class TrainStep:
         a signature whose capture fails runs the eager losses (returns None)."""
         dev = self.device
         f32 = lambda t: t.to(dev).float().contiguous()
-        plan = [lv[k] if k != "valid" else lv[k] for lv in built.levels for k in ("valid", "cell", "tbox", "anchor", "cls")]
-        plan = [t.contiguous() for t in plan]
+        if built is None:
+            plan = [f32(sample["box_labels"])]
+        else:
+            plan = [lv[k].contiguous() for lv in built.levels for k in ("valid", "cell", "tbox", "anchor", "cls")]
         args = [semi, semi_w, desc, desc_w, obj[0], obj[1], obj[2], f32(sample["labels_2D"]), f32(sample["valid_mask"]), f32(sample["warped_labels"]),
                 f32(sample["warped_valid_mask"]), f32(sample["inv_homographies"]), pairs[0].contiguous(), pairs[1].contiguous(), pairs[2].contiguous()] + plan
         key = tuple((tuple(t.shape), t.dtype) for t in args)
         if key not in self.loss_heads:
-            head = _LossHead(self, [lv["cells"] for lv in built.levels])
+            head = _LossHead(self, [o.numel() // o.shape[-1] for o in obj])
             try:
                 samples = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in args)
                 self.loss_heads[key] = torch.cuda.make_graphed_callables(head, samples, num_warmup_iters=2)
