@@ -141,3 +141,53 @@ def test_l2norm_rows_and_tf32_split_kernels():
     _lib.check(L.yp_split_tf32(x.data_ptr(), x.numel(), out[0].data_ptr(), out[1].data_ptr(), st))
     torch.cuda.synchronize()
     assert torch.equal(out, split_tf32(x))
+
+
+@pytest.mark.parametrize("fmt", ["f32x2", "bf16", "f32"])
+@pytest.mark.parametrize("B,H,W,Cc", [(1, 20, 20, 256), (2, 15, 20, 32), (3, 4, 3, 8), (1, 23, 40, 16)])
+def test_sppf_pool_equals_chained_maxpool(fmt, B, H, W, Cc):
+    """yp_sppf_pool alone (the network tests only see it through whole passes): slices 1..3 of the [B,H,W,4C] concat buffer ==
+    three chained nn.MaxPool2d(5, 1, 2) of slice 0 (src/models/common.py:220-229) on the stored values, for every activation
+    format; the operand planes of the winning element are copied bit-exactly (distinct values, so the winner is unique), slice 0
+    and the channels outside the view stay untouched.  Maps narrower than the window (4x3) exercise the clipped windows."""
+    import torch.nn.functional as F
+    from yolopoint_b200._lib import YP_FMT_F32
+    L = _lib.lib(require_device=True)
+    code = {"f32x2": YP_FMT_F32X2, "bf16": YP_FMT_BF16, "f32": YP_FMT_F32}[fmt]
+    g = torch.Generator().manual_seed(17 * B + W + Cc)
+    n = B * H * W * Cc
+    x = (torch.randperm(n, generator=g).float() / n * 8 - 4).reshape(B, H, W, Cc).cuda()      # distinct values: unique winners
+    planes, dt = (2, torch.float32) if fmt == "f32x2" else ((1, torch.bfloat16) if fmt == "bf16" else (1, torch.float32))
+    buf = torch.full((planes, B, H, W, 4 * Cc + 16), 7.0, dtype=dt, device="cuda")
+    if fmt == "f32x2":
+        buf[:, ..., 16:16 + Cc] = split_tf32(x)
+    else:
+        buf[0, ..., 16:16 + Cc] = x.to(dt)
+    before = buf.clone()
+    v = make_view(buf, code, 16, 4 * Cc)
+    _lib.check(L.yp_sppf_pool(C.byref(v), _st()))
+    torch.cuda.synchronize()
+    assert torch.equal(buf[..., :16 + Cc], before[..., :16 + Cc])
+    val = before[..., 16:16 + Cc].float().sum(0).permute(0, 3, 1, 2)                            # the value the kernel sees (hi + lo)
+    y = val
+    for k in (1, 2, 3):
+        y = F.max_pool2d(y, 5, 1, 2)
+        got = buf[..., 16 + k * Cc:16 + (k + 1) * Cc]
+        assert torch.equal(got.float().sum(0).permute(0, 3, 1, 2), y)
+        if fmt != "bf16":                                                                       # bf16 rounding makes equal values; their bits are equal too
+            w = 4 * k + 1
+            _, idx = F.max_pool2d(val, w, 1, w // 2, return_indices=True)                       # chained 5x5 pools == one clipped (4k+1)^2 window
+            for p in range(planes):
+                flat = before[p, ..., 16:16 + Cc].permute(0, 3, 1, 2).reshape(B, Cc, H * W)
+                want = torch.gather(flat, 2, idx.reshape(B, Cc, -1)).reshape(B, Cc, H, W)
+                assert torch.equal(got[p].permute(0, 3, 1, 2), want)
+
+
+def test_sppf_pool_rejects_bad_views():
+    from yolopoint_b200._lib import YP_FMT_F32
+    L = _lib.lib(require_device=True)
+    buf = torch.zeros((1, 1, 8, 8, 24), device="cuda")
+    assert L.yp_sppf_pool(C.byref(make_view(buf, YP_FMT_F32, 0, 6)), _st()) != 0       # 6 channels: not four slices of channel pairs
+    assert L.yp_sppf_pool(None, _st()) != 0
+    big = torch.zeros((1, 1, 300, 300, 8), device="cuda")
+    assert L.yp_sppf_pool(C.byref(make_view(big, YP_FMT_F32, 0, 8)), _st()) != 0       # 90 000 pixels: beyond the 16-bit source index
