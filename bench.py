@@ -36,7 +36,7 @@ WORKLOADS = {
     "s640v52": ("s", 640, 640, 1),  # YOLOPointv52-S (the model configs/kitti_inference.yaml names), configs[1] geometry
 }
 MODEL_NAME = {"s640v52": "YOLOPointv52"}   # every other workload runs the YOLOPoint (v5-style) network
-CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 6.30e6}   # profiles/r02_conv_tc_wide_ncu_full.md: mean over the 53 conv launches of a YOLOPoint-S 640x640 pass captured (cold L2)
+CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 6.43e6}   # profiles/r02_drain_pass_dram.md: dram read + write per launch, mean over the 64 conv launches of one pass of this plan (cold L2)
 NAMES = [str(i) for i in range(80)]
 E2E_REPEATS = 3                           # the end-to-end region is repeated and its median reported (see main())
 # SURVEY.md section 8a, per frame (forward); s640v52: conv-module hook count on the reference YOLOPointv52-S
@@ -555,9 +555,10 @@ def main():
                     "stat": f"median of {E2E_REPEATS} repeats of the same steps, each the max over ranks", "repeats_s": e2e_runs},
             "roofline": {"bound": "tensor", "kernel": conv_kernel_name, "achieved": achieved_tf, "peak": peaks["tf"],
                          "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf"], "traffic": CONV_DRAM_BYTES_PER_LAUNCH.get(args.workload),
-                         "traffic_note": "dram__bytes_read+write per conv launch, mean over the 53 conv launches of one pass captured in profiles/r02_conv_tc_wide_ncu_full.md "
-                                         "(ncu --set full, cold L2); algorithmic: 78.1 M activation elements x 8 B (hi, lo planes) / 65 launches = 9.6 MB written + read once, "
-                                         "i.e. the cold-cache traffic is below the algorithmic bytes because most operands are re-read from L2",
+                         "traffic_note": "dram__bytes_read+write per conv launch, mean over the 64 conv launches of one pass of the headline plan (ncu, cold L2, serialised launches: "
+                                         "profiles/r02_drain_pass_dram.md; --set full of 24 of them: profiles/r02_conv_tc_drain_ncu_full.md); algorithmic (tools/plan_bytes.py): 6.25 MB read "
+                                         "(activations in (hi, lo) planes + weights, each once) + 4.04 MB written per launch; the measured reads are 1.03x the algorithmic reads, the writes "
+                                         "stay in the write-back L2 beyond the end of the kernel and are read from there by the next layer",
                          "peak_source": f"{peaks['src']} bf16 sustained",
                          "launches_per_step": FPS * plan.n_net_launches(), "avg_launch_us": (ms / (K * FPS) if pipe.F > 1 else net_ms) * 1e3 / plan.n_net_launches(),
                          "algorithmic_gflop_per_step": FPS * flops_step / 1e9, "single_pass_ms": net_ms,
