@@ -227,3 +227,50 @@ def test_tracker_evaluation_variant(ns, capsys):
             ours.clear_desc()
     np.testing.assert_array_equal(ours.get_mscores(), ref.get_mscores())
     capsys.readouterr()
+
+
+def test_edge_cases_match_reference(ns):
+    """Empty / degenerate inputs of every post-processing function: the oracle returns what the reference returns (shape, dtype and
+    values) and raises where it raises (src/demo.py:300-341, src/utils/utils.py:118-182, 465-485, src/utils/general_yolo.py:124-235,
+    src/evaluations/descriptor_evaluation.py:148-181)."""
+    rs = np.random.RandomState(3)
+    d = rs.normal(0, 1, (32, 10)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=0)
+    e = np.zeros((32, 0), np.float32)
+    match = ns.PointTracker.nn_match_two_way
+    for a, b in ((e, d), (d, e), (e, e), (d[:, :1], d[:, :1]), (d, d)):
+        r, o = match(a, b, 0.7), O.nn_match_two_way(a, b, 0.7)
+        assert r.shape == o.shape and r.dtype == o.dtype
+        np.testing.assert_array_equal(o, r)
+    for bad in (lambda f: f(d, d, -1.0), lambda f: f(d, d[:16], 0.7)):
+        with pytest.raises((ValueError, AssertionError)) as er:
+            bad(match)
+        with pytest.raises(er.type):
+            bad(O.nn_match_two_way)
+    # keypoints: nothing above the threshold, one pixel, only border pixels, a constant map (ties: stable order decides)
+    h0 = np.zeros((40, 56), np.float32)
+    h1 = h0.copy(); h1[20, 30] = 0.9
+    hb = h0.copy(); hb[1, 1] = 0.9; hb[38, 54] = 0.8
+    hc = np.full((24, 24), 0.5, np.float32)
+    for h in (h0, h1, hb, hc):
+        r, o = ns.getPtsFromHeatmap(h, 0.1, 4), O.get_pts_from_heatmap(h, 0.1, 4)
+        assert np.asarray(r).shape == np.asarray(o).shape
+        np.testing.assert_array_equal(np.asarray(o), np.asarray(r))
+    for pts in (np.zeros((3, 0)), np.array([[5.0], [6.0], [0.7]])):
+        (rp, ri), (op, oi) = ns.nms_fast(pts, 40, 56, 4), O.nms_fast(pts, 40, 56, 4)
+        assert rp.shape == op.shape and rp.dtype == op.dtype and ri.dtype == oi.dtype
+        np.testing.assert_array_equal(op, rp)
+        np.testing.assert_array_equal(oi, ri)
+    # box NMS: no candidate in any image of the batch; thresholds outside [0, 1] are refused
+    p = np.zeros((2, 100, 6), np.float32)
+    r, o = ns.non_max_suppression(torch.from_numpy(p), 0.4, 0.45), O.non_max_suppression(p, 0.4, 0.45)
+    assert [tuple(t.shape) for t in r] == [tuple(t.shape) for t in o] == [(0, 6), (0, 6)]
+    for f, arg in ((ns.non_max_suppression, torch.from_numpy(p)), (O.non_max_suppression, p)):
+        with pytest.raises(AssertionError):
+            f(arg, 1.5, 0.45)
+        with pytest.raises(AssertionError):
+            f(arg, 0.4, -0.1)
+    # descriptor sampling with no points
+    c = rs.normal(0, 1, (1, 32, 10, 14)).astype(np.float32)
+    r, o = ns.sample_desc_from_points(torch.from_numpy(c), np.zeros((3, 0)), "cpu"), O.sample_desc_from_points(c, np.zeros((3, 0)))
+    assert r.shape == o.shape == (32, 0) and r.dtype == o.dtype
