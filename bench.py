@@ -38,6 +38,7 @@ WORKLOADS = {
 MODEL_NAME = {"s640v52": "YOLOPointv52"}   # every other workload runs the YOLOPoint (v5-style) network
 CONV_DRAM_BYTES_PER_LAUNCH = {"s640": 6.43e6}   # profiles/r02_drain_pass_dram.md: dram read + write per launch, mean over the 64 conv launches of one pass of this plan (cold L2)
 NAMES = [str(i) for i in range(80)]
+OTHER_CONFIGS_BUDGET_S = 300              # bound on the child runs of the other BASELINE configs reported under detail
 E2E_REPEATS = 3                           # the end-to-end region is repeated and its median reported (see main())
 # SURVEY.md section 8a, per frame (forward); s640v52: conv-module hook count on the reference YOLOPointv52-S
 CONV_GFLOP = {"s640": 21.023, "n480": 4.232, "m1280": 141.398, "l640train": 135.526, "s640v52": 21.363}
@@ -176,8 +177,14 @@ def other_configs():
     training step batch 8 per GPU."""
     import subprocess
     res = {}
+    t_start = time.perf_counter()
 
     def child(tag, cmd, pick, timeout=420):
+        left = OTHER_CONFIGS_BUDGET_S - (time.perf_counter() - t_start)
+        if left <= 0:            # the default command stays within minutes whatever the box does: later children are skipped, not awaited
+            res[tag] = {"skipped": f"time budget of {OTHER_CONFIGS_BUDGET_S} s for the other configs spent"}
+            return
+        timeout = min(timeout, left + 60)
         try:
             r = subprocess.run([sys.executable] + cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
             lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
