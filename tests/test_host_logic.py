@@ -125,6 +125,14 @@ def test_c_abi_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.YpView) == 48 and ctypes.sizeof(_lib.YpNmsParams) == 40
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every exported entry point to the reference code it stands in for (or says it has no counterpart)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = [name for name in _lib.SIGNATURES if name not in doc]
+    assert not missing, missing
+
+
 def test_frontend_host_side_without_gpu():
     """preprocess / restore_coords / template_filter of YoloPointFrontend are pure host code (src/demo.py:97-123, 187-195, 217-228)."""
     import yolopoint_b200 as yp
