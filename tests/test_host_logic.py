@@ -125,6 +125,32 @@ def test_c_abi_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.YpView) == 48 and ctypes.sizeof(_lib.YpNmsParams) == 40
 
 
+def test_api_argument_errors_and_loud_failure_without_gpu():
+    """The reference-named functions refuse bad arguments with the reference's exception types BEFORE touching the device
+    (src/demo.py:318-321: ValueError for a negative nn_thresh, assert on the descriptor widths; src/utils/general_yolo.py:146-147:
+    asserts on the thresholds), return the reference's empty result for empty descriptor sets (src/demo.py:316-317), and raise a
+    RuntimeError -- never compute on the CPU -- when asked for real work without a CUDA device."""
+    import yolopoint_b200 as yp
+    if torch.cuda.is_available():
+        pytest.skip("checks the behaviour of a machine without a GPU")
+    d = np.random.RandomState(0).normal(0, 1, (32, 10)).astype(np.float32)
+    with pytest.raises(ValueError):
+        yp.nn_match_two_way(d, d, -1.0)
+    with pytest.raises(AssertionError):
+        yp.nn_match_two_way(d, d[:16], 0.7)
+    with pytest.raises(AssertionError):
+        yp.non_max_suppression(torch.zeros(1, 10, 6), 1.5, 0.45)
+    with pytest.raises(AssertionError):
+        yp.non_max_suppression(torch.zeros(1, 10, 6), 0.4, -0.1)
+    m = yp.nn_match_two_way(np.zeros((32, 0), np.float32), d, 0.7)
+    assert m.shape == (3, 0) and m.dtype == np.float64
+    for call in (lambda: yp.nn_match_two_way(d, d, 0.7), lambda: yp.non_max_suppression(torch.rand(1, 10, 6), 0.4, 0.45),
+                 lambda: yp.flattenDetection(torch.rand(1, 65, 4, 4)), lambda: yp.getPtsFromHeatmap(np.zeros((32, 32), np.float32), 0.1, 4),
+                 lambda: yp.sample_desc_from_points(torch.rand(1, 32, 4, 4), np.zeros((3, 0)))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+
+
 def test_integration_doc_names_every_entry_point():
     """INTEGRATION.md maps every exported entry point to the reference code it stands in for (or says it has no counterpart)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
